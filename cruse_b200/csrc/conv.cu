@@ -1,0 +1,431 @@
+// conv.cu -- encoder / skip / decoder stages of the CRUSE U-Net on frame-major activations.
+//
+// Replaces nn.Conv2d((2,3), stride (1,2), pad (1,1)) + "[..., :-1, :]" + BatchNorm2d + act
+// (model/cruse_net.py:138,141,149-152), the (1,3) skip convs (:143,153-156) and
+// nn.ConvTranspose2d((1,3), stride (1,2)) + "[..., :-1]" + BatchNorm2d + act + skip add /
+// sigmoid (:161-164) of the reference.
+//
+// Layout: activations are [B, T, C, F] -- every frame is one contiguous C*F record (4 KB at
+// every stage of the 256-bin pyramid), so a CTA streams TT consecutive frames of one
+// utterance into shared memory with fully coalesced 128-bit loads (one extra look-back frame
+// for the causal (2,3) kernels), keeps the stage's whole weight tensor in shared memory, and
+// every thread register-tiles CO_T output channels x TT frames for one output bin.  Bias,
+// folded BatchNorm (eval) or per-channel sum / sum-of-squares partials (train), activation
+// and the decoder's skip add all live in the epilogue, so a stage reads its input once and
+// writes its output once (SURVEY.md App. B byte model).
+#include "common.cuh"
+
+namespace cruse {
+
+constexpr int CONV_TT = 8;    // frames per CTA
+constexpr int CONV_COT = 4;   // output channels per thread
+constexpr int CONV_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// forward conv, KT time taps (look-back), 3 freq taps, freq stride SF, freq pad 1.
+// smem: s_in[(TT+KT-1)][Cin][Fin+2]  (zero column on both sides),  s_w[Cin][KT*3][CoutP] (CoutP = Cout
+// rounded up to CONV_COT), s_stats[2*Cout]
+// ---------------------------------------------------------------------------------------------
+template <int KT, int SF>
+__global__ void __launch_bounds__(CONV_THREADS)
+conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha,
+                int act, float* __restrict__ out, float* __restrict__ stats_ws, int T, int Cin, int Fin, int Cout,
+                int Fout) {
+    extern __shared__ float smem[];
+    constexpr int TT = CONV_TT, COT = CONV_COT, NR = TT + KT - 1;
+    const int FinP = Fin + 2;
+    const int CoutP = (Cout + COT - 1) / COT * COT;
+    float* s_in = smem;
+    float* s_w = s_in + (((size_t)NR * Cin * FinP + 3) & ~(size_t)3);  // keep float4 alignment
+    float* s_stats = s_w + (size_t)Cin * KT * 3 * CoutP;
+
+    const int chunks = (T + TT - 1) / TT;
+    const int b = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
+    const int tid = threadIdx.x;
+
+    // weights: PyTorch [Cout][Cin][KT][3] -> s_w[ci][tap][co]
+    const int nw = Cin * KT * 3;
+    for (int i = tid; i < nw * CoutP; i += blockDim.x) {
+        const int co = i % CoutP, r = i / CoutP;  // r = ci*(KT*3) + tap
+        s_w[i] = (co < Cout) ? __ldg(w + (size_t)co * nw + r) : 0.f;
+    }
+    if (stats_ws)
+        for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
+    // input rows t0-(KT-1) .. t0+TT-1
+    const int rowlen = Cin * Fin;
+    const float* inb = in + (size_t)b * T * rowlen;
+    for (int r = 0; r < NR; ++r) {
+        const int t = t0 - (KT - 1) + r;
+        const bool valid = (t >= 0 && t < T);
+        float* dst = s_in + (size_t)r * Cin * FinP;
+        const float* src = inb + (size_t)t * rowlen;
+        if ((Fin & 3) == 0) {
+            for (int i = tid * 4; i < rowlen; i += blockDim.x * 4) {
+                float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int ci = i / Fin, f = i - ci * Fin;
+                float* d = dst + ci * FinP + 1 + f;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = tid; i < rowlen; i += blockDim.x) {
+                const int ci = i / Fin, f = i - ci * Fin;
+                dst[ci * FinP + 1 + f] = valid ? __ldg(src + i) : 0.f;
+            }
+        }
+        for (int ci = tid; ci < Cin; ci += blockDim.x) {
+            dst[ci * FinP] = 0.f;
+            dst[ci * FinP + Fin + 1] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    const int ncob = CoutP / COT;
+    const int items = Fout * ncob;
+    for (int item = tid; item < items; item += blockDim.x) {
+        const int fo = item % Fout, cob = item / Fout;
+        const int co0 = cob * COT;
+        float acc[TT][COT];
+#pragma unroll
+        for (int t = 0; t < TT; ++t)
+#pragma unroll
+            for (int c = 0; c < COT; ++c) acc[t][c] = 0.f;
+
+        const float* ip = s_in + SF * fo;  // padded index of tap kf=0 is SF*fo (unpadded SF*fo-1)
+        for (int ci = 0; ci < Cin; ++ci) {
+            float xv[NR][3];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const float* p = ip + ((size_t)r * Cin + ci) * FinP;
+                xv[r][0] = p[0]; xv[r][1] = p[1]; xv[r][2] = p[2];
+            }
+            const float* wp = s_w + (size_t)ci * KT * 3 * CoutP + co0;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                for (int kf = 0; kf < 3; ++kf) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + (kt * 3 + kf) * CoutP);
+#pragma unroll
+                    for (int t = 0; t < TT; ++t) {
+                        const float x = xv[t + kt][kf];  // out frame t uses rows t (kt=0: t-1) .. t+KT-1
+                        acc[t][0] = fmaf(wv.x, x, acc[t][0]);
+                        acc[t][1] = fmaf(wv.y, x, acc[t][1]);
+                        acc[t][2] = fmaf(wv.z, x, acc[t][2]);
+                        acc[t][3] = fmaf(wv.w, x, acc[t][3]);
+                    }
+                }
+        }
+        // epilogue
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+            const int co = co0 + c;
+            if (co >= Cout) continue;
+            const float bv = bias ? __ldg(bias + co) : 0.f;
+            const float sc = scale ? __ldg(scale + co) : 1.f, sh = scale ? __ldg(shift + co) : 0.f;
+            const float al = alpha ? __ldg(alpha + co) : 0.f;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                if (t0 + t < T) {
+                    float v = acc[t][c] + bv;
+                    s1 += v; s2 += v * v;
+                    v = apply_act(fmaf(v, sc, sh), act, al);
+                    out[(((size_t)b * T + t0 + t) * Cout + co) * Fout + fo] = v;
+                }
+            }
+            if (stats_ws) {
+                atomicAdd(&s_stats[co], s1);
+                atomicAdd(&s_stats[Cout + co], s2);
+            }
+        }
+    }
+    if (stats_ws) {
+        __syncthreads();
+        float* so = stats_ws + (size_t)blockIdx.x * 2 * Cout;
+        for (int i = tid; i < 2 * Cout; i += blockDim.x) so[i] = s_stats[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// transposed conv (1,3), stride (1,2), no padding, cropped to Fout:
+//   out[co, 2i]   = b + sum_ci W[ci,co,0]*in[ci,i] + W[ci,co,2]*in[ci,i-1]
+//   out[co, 2i+1] = b + sum_ci W[ci,co,1]*in[ci,i]
+// smem: s_in[TT][Cin][Fin+2], s_w[Cin][3][CoutP], s_stats[2*Cout]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CONV_THREADS)
+convT_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha,
+                 int act, const float* __restrict__ skip, float* __restrict__ out, float* __restrict__ stats_ws, int T,
+                 int Cin, int Fin, int Cout, int Fout) {
+    extern __shared__ float smem[];
+    constexpr int TT = CONV_TT, COT = CONV_COT;
+    const int FinP = Fin + 2;
+    const int CoutP = (Cout + COT - 1) / COT * COT;
+    float* s_in = smem;
+    float* s_w = s_in + (((size_t)TT * Cin * FinP + 3) & ~(size_t)3);  // keep float4 alignment
+    float* s_stats = s_w + (size_t)Cin * 3 * CoutP;
+    const int chunks = (T + TT - 1) / TT;
+    const int b = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
+    const int tid = threadIdx.x;
+
+    // weights: PyTorch [Cin][Cout][1][3] -> s_w[ci][kf][co]
+    for (int i = tid; i < Cin * 3 * CoutP; i += blockDim.x) {
+        const int co = i % CoutP, r = i / CoutP;
+        const int kf = r % 3, ci = r / 3;
+        s_w[i] = (co < Cout) ? __ldg(w + ((size_t)ci * Cout + co) * 3 + kf) : 0.f;
+    }
+    if (stats_ws)
+        for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
+    const int rowlen = Cin * Fin;
+    const float* inb = in + (size_t)b * T * rowlen;
+    for (int r = 0; r < TT; ++r) {
+        const int t = t0 + r;
+        const bool valid = t < T;
+        float* dst = s_in + (size_t)r * Cin * FinP;
+        const float* src = inb + (size_t)t * rowlen;
+        if ((Fin & 3) == 0) {
+            for (int i = tid * 4; i < rowlen; i += blockDim.x * 4) {
+                float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int ci = i / Fin, f = i - ci * Fin;
+                float* d = dst + ci * FinP + 1 + f;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = tid; i < rowlen; i += blockDim.x) {
+                const int ci = i / Fin, f = i - ci * Fin;
+                dst[ci * FinP + 1 + f] = valid ? __ldg(src + i) : 0.f;
+            }
+        }
+        for (int ci = tid; ci < Cin; ci += blockDim.x) {
+            dst[ci * FinP] = 0.f;
+            dst[ci * FinP + Fin + 1] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    const int npair = (Fout + 1) / 2;
+    const int ncob = CoutP / COT;
+    const int items = npair * ncob;
+    for (int item = tid; item < items; item += blockDim.x) {
+        const int i = item % npair, cob = item / npair;
+        const int co0 = cob * COT;
+        float ae[TT][COT], ao[TT][COT];
+#pragma unroll
+        for (int t = 0; t < TT; ++t)
+#pragma unroll
+            for (int c = 0; c < COT; ++c) { ae[t][c] = 0.f; ao[t][c] = 0.f; }
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float* wp = s_w + (size_t)ci * 3 * CoutP + co0;
+            const float4 w0 = *reinterpret_cast<const float4*>(wp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + CoutP);
+            const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * CoutP);
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                const float* p = s_in + ((size_t)t * Cin + ci) * FinP + i;  // p[0]=in[i-1], p[1]=in[i]
+                const float xm = p[0], x0 = p[1];
+                ae[t][0] = fmaf(w0.x, x0, fmaf(w2.x, xm, ae[t][0]));
+                ae[t][1] = fmaf(w0.y, x0, fmaf(w2.y, xm, ae[t][1]));
+                ae[t][2] = fmaf(w0.z, x0, fmaf(w2.z, xm, ae[t][2]));
+                ae[t][3] = fmaf(w0.w, x0, fmaf(w2.w, xm, ae[t][3]));
+                ao[t][0] = fmaf(w1.x, x0, ao[t][0]);
+                ao[t][1] = fmaf(w1.y, x0, ao[t][1]);
+                ao[t][2] = fmaf(w1.z, x0, ao[t][2]);
+                ao[t][3] = fmaf(w1.w, x0, ao[t][3]);
+            }
+        }
+        const int fe = 2 * i, fo = 2 * i + 1;
+        const bool has_odd = fo < Fout;
+#pragma unroll
+        for (int c = 0; c < COT; ++c) {
+            const int co = co0 + c;
+            if (co >= Cout) continue;
+            const float bv = bias ? __ldg(bias + co) : 0.f;
+            const float sc = scale ? __ldg(scale + co) : 1.f, sh = scale ? __ldg(shift + co) : 0.f;
+            const float al = alpha ? __ldg(alpha + co) : 0.f;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                if (t0 + t < T) {
+                    const size_t o = (((size_t)b * T + t0 + t) * Cout + co) * Fout;
+                    float v0 = ae[t][c] + bv, v1 = ao[t][c] + bv;
+                    s1 += v0; s2 += v0 * v0;
+                    v0 = apply_act(fmaf(v0, sc, sh), act, al);
+                    if (skip) v0 += __ldg(skip + o + fe);
+                    if (has_odd) {
+                        s1 += v1; s2 += v1 * v1;
+                        v1 = apply_act(fmaf(v1, sc, sh), act, al);
+                        if (skip) v1 += __ldg(skip + o + fo);
+                        if ((Fout & 1) == 0) {
+                            *reinterpret_cast<float2*>(out + o + fe) = make_float2(v0, v1);
+                        } else {
+                            out[o + fe] = v0; out[o + fo] = v1;
+                        }
+                    } else {
+                        out[o + fe] = v0;
+                    }
+                }
+            }
+            if (stats_ws) {
+                atomicAdd(&s_stats[co], s1);
+                atomicAdd(&s_stats[Cout + co], s2);
+            }
+        }
+    }
+    if (stats_ws) {
+        __syncthreads();
+        float* so = stats_ws + (size_t)blockIdx.x * 2 * Cout;
+        for (int i = tid; i < 2 * Cout; i += blockDim.x) so[i] = s_stats[i];
+    }
+}
+
+// one block per channel: reduce per-CTA partials in double
+__global__ void bn_finalize_kernel(const float* __restrict__ stats_ws, int nparts, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                   float* save_mean, float* save_invstd) {
+    const int c = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
+        s1 += (double)stats_ws[(size_t)p * 2 * C + c];
+        s2 += (double)stats_ws[(size_t)p * 2 * C + C + c];
+    }
+    __shared__ double sh1[32], sh2[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sh1[threadIdx.x >> 5] = s1; sh2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, q = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh1[i]; q += sh2[i]; }
+        const double mean = a / count;
+        double var = q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+        scale[c] = g * invstd;
+        shift[c] = bt - (float)mean * g * invstd;
+        if (save_mean) save_mean[c] = (float)mean;
+        if (save_invstd) save_invstd[c] = invstd;
+        if (running_mean) {
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+}
+
+__global__ void bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const float* __restrict__ alpha, int act,
+                                  const float* __restrict__ skip, float* __restrict__ y, long long total, int C, int F) {
+    // vectorised when F % 4 == 0 (a float4 never straddles a channel)
+    if ((F & 3) == 0) {
+        const long long n4 = total >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)(((i << 2) / F) % C);
+            const float sc = __ldg(scale + c), sh = __ldg(shift + c), al = alpha ? __ldg(alpha + c) : 0.f;
+            float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
+            v.x = apply_act(fmaf(v.x, sc, sh), act, al);
+            v.y = apply_act(fmaf(v.y, sc, sh), act, al);
+            v.z = apply_act(fmaf(v.z, sc, sh), act, al);
+            v.w = apply_act(fmaf(v.w, sc, sh), act, al);
+            if (skip) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(skip) + i);
+                v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+            }
+            reinterpret_cast<float4*>(y)[i] = v;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)((i / F) % C);
+            float v = apply_act(fmaf(__ldg(z + i), __ldg(scale + c), __ldg(shift + c)), act, alpha ? __ldg(alpha + c) : 0.f);
+            if (skip) v += __ldg(skip + i);
+            y[i] = v;
+        }
+    }
+}
+
+static size_t conv_smem_bytes(int KT, int Cin, int Fin, int Cout) {
+    const int CoutP = (Cout + CONV_COT - 1) / CONV_COT * CONV_COT;
+    return sizeof(float) * (((size_t)(CONV_TT + KT - 1) * Cin * (Fin + 2) + 3 & ~(size_t)3) + (size_t)Cin * KT * 3 * CoutP + 2 * (size_t)Cout);
+}
+
+}  // namespace cruse
+
+using namespace cruse;
+
+extern "C" int cruse_conv_nparts(int B, int T) { return B * ((T + CONV_TT - 1) / CONV_TT); }
+
+extern "C" int cruse_conv_fwd(const float* in, const float* w, const float* bias, const float* scale,
+                              const float* shift, const float* alpha, int act, float* out, float* stats_ws, int B,
+                              int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream) {
+    CRUSE_CHECK_ARG(in && w && out, "conv_fwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "conv_fwd: bad sizes");
+    CRUSE_CHECK_ARG((kt == 2 && fstride == 2) || (kt == 1 && fstride == 1), "conv_fwd: supported (kt,fstride) are (2,2) and (1,1), got (%d,%d)", kt, fstride);
+    const int expF = (Fin + 2 - 3) / fstride + 1;
+    CRUSE_CHECK_ARG(Fout == expF, "conv_fwd: Fout=%d, expected %d", Fout, expF);
+    CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd: scale and shift go together");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd: PReLU needs alpha");
+    const size_t smem = conv_smem_bytes(kt, Cin, Fin, Cout);
+    CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_fwd: stage (Cin=%d,Fin=%d,Cout=%d) needs %zu B shared memory", Cin, Fin, Cout, smem);
+    const int grid = cruse_conv_nparts(B, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kt == 2) {
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_kernel<2, 2><<<grid, CONV_THREADS, smem, st>>>(in, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
+    } else {
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(in, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
+    }
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_convT_fwd(const float* in, const float* w, const float* bias, const float* scale,
+                               const float* shift, const float* alpha, int act, const float* skip, float* out,
+                               float* stats_ws, int B, int T, int Cin, int Fin, int Cout, int Fout, void* stream) {
+    CRUSE_CHECK_ARG(in && w && out, "convT_fwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "convT_fwd: bad sizes");
+    CRUSE_CHECK_ARG(Fout > 0 && Fout <= 2 * Fin + 1, "convT_fwd: Fout=%d must be in (0, 2*Fin+1=%d]", Fout, 2 * Fin + 1);
+    CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "convT_fwd: scale and shift go together");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "convT_fwd: PReLU needs alpha");
+    const int CoutP = (Cout + CONV_COT - 1) / CONV_COT * CONV_COT;
+    const size_t smem = sizeof(float) * ((((size_t)CONV_TT * Cin * (Fin + 2) + 3) & ~(size_t)3) + (size_t)Cin * 3 * CoutP + 2 * (size_t)Cout);
+    CRUSE_CHECK_ARG(smem <= 227 * 1024, "convT_fwd: stage needs %zu B shared memory", smem);
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = cruse_conv_nparts(B, T);
+    convT_fwd_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(in, w, bias, scale, shift, alpha, act, skip, out, stats_ws, T,
+                                                                         Cin, Fin, Cout, Fout);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_bn_finalize(const float* stats_ws, int nparts, int C, double count, const float* gamma,
+                                 const float* beta, float eps, float momentum, float* running_mean,
+                                 float* running_var, float* scale, float* shift, float* save_mean,
+                                 float* save_invstd, void* stream) {
+    CRUSE_CHECK_ARG(stats_ws && scale && shift, "bn_finalize: null pointer");
+    CRUSE_CHECK_ARG(nparts > 0 && C > 0 && count > 0, "bn_finalize: bad sizes");
+    CRUSE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats go together");
+    bn_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(stats_ws, nparts, C, count, gamma, beta, eps, momentum, running_mean,
+                                                            running_var, scale, shift, save_mean, save_invstd);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
+                                const float* skip, float* y, long long n_frames, int C, int F, void* stream) {
+    CRUSE_CHECK_ARG(z && scale && shift && y, "bn_act_fwd: null pointer");
+    CRUSE_CHECK_ARG(n_frames > 0 && C > 0 && F > 0, "bn_act_fwd: bad sizes");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "bn_act_fwd: PReLU needs alpha");
+    const long long total = n_frames * C * F;
+    long long blocks = (total / 4 + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    bn_act_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, scale, shift, alpha, act, skip, y, total, C, F);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,338 @@
+// spectral.cu -- framed real FFT front-end (STFT) and mask*spectrum + overlap-add iSTFT back-end.
+//
+// Replaces torch.stft / torch.istft at train_base/acoustics/feature.py:22-30,53-61 and
+// utils/utils.py:390-400,417-433,448-454 of the reference.
+//
+// Design (HBM-bound stages, SURVEY.md App. B: 4.4 KB / 3.3 KB per frame):
+//  * one warp owns one frame: hop-strided samples are read coalesced (float2), windowed,
+//    packed as N/2 complex points, transformed by a mixed-radix (4,2,5,3) Stockham FFT that
+//    lives entirely in that warp's shared-memory ping-pong buffers (only __syncwarp between
+//    passes), then split into the N/2+1 real-FFT bins and written as coalesced float2.
+//  * the magnitude the network consumes (utils/utils.py:400) is emitted by the same kernel.
+//  * iSTFT: a CTA owns a run of consecutive frames of one utterance (+ halo frames that are
+//    recomputed), so the overlap-add is a shared-memory gather with no atomics; the mask
+//    multiply (PreProcess.masking) is fused into the spectrum load and the hann^2 envelope
+//    division into the store.
+#include "common.cuh"
+
+namespace cruse {
+
+struct FftPlan {
+    int nfac;
+    int fac[16];
+};
+
+static int make_plan(int M, FftPlan& p) {
+    p.nfac = 0;
+    int n = M;
+    while (n % 4 == 0) { p.fac[p.nfac++] = 4; n /= 4; }
+    while (n % 2 == 0) { p.fac[p.nfac++] = 2; n /= 2; }
+    while (n % 5 == 0) { p.fac[p.nfac++] = 5; n /= 5; }
+    while (n % 3 == 0) { p.fac[p.nfac++] = 3; n /= 3; }
+    return n == 1 ? 0 : -1;
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// tw[j] = exp(-2*pi*i*j/N), j in [0,N)
+__device__ __forceinline__ void build_twiddles(float2* tw, int N) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)N, &s, &c);
+        tw[j] = make_float2((float)c, (float)(-s));
+    }
+}
+
+// Complex FFT of size M executed by one warp on shared-memory buffers x -> (x|y).
+// Stockham autosort, decimation in frequency:  for radix r, n_cur = r*m, stride s:
+//   y[q + s*(r*p + k)] = W_{n_cur}^{p*k} * sum_j x[q + s*(p + m*j)] * W_r^{j*k}
+// INV conjugates every root (unnormalised inverse).  Returns the buffer holding the result.
+template <bool INV>
+__device__ float2* warp_fft(float2* x, float2* y, const float2* __restrict__ tw, int M, const FftPlan& plan, int lane) {
+    const int N = 2 * M;
+    int n_cur = M, s = 1;
+    for (int f = 0; f < plan.nfac; ++f) {
+        const int r = plan.fac[f];
+        const int m = n_cur / r;
+        const int twstep = N / n_cur;
+        const int nb = M / r;
+        for (int i = lane; i < nb; i += 32) {
+            const int p = i / s, q = i - p * s;
+            const float2* xi = x + q + s * p;
+            float2* yo = y + q + s * r * p;
+            const int sm = s * m;
+            if (r == 4) {
+                float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm], a3 = xi[3 * sm];
+                float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
+                float2 t3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);  // d * (+-i)
+                float2 b0 = cadd(t0, t2), b1 = cadd(t1, t3), b2 = csub(t0, t2), b3 = csub(t1, t3);
+                float2 w1 = tw[p * twstep], w2 = tw[2 * p * twstep], w3 = tw[3 * p * twstep];
+                if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+                yo[0] = b0;
+                yo[s] = cmul(b1, w1);
+                yo[2 * s] = cmul(b2, w2);
+                yo[3 * s] = cmul(b3, w3);
+            } else if (r == 2) {
+                float2 a0 = xi[0], a1 = xi[sm];
+                float2 w1 = tw[p * twstep];
+                if (INV) w1.y = -w1.y;
+                yo[0] = cadd(a0, a1);
+                yo[s] = cmul(csub(a0, a1), w1);
+            } else {  // r = 3 or 5: direct small DFT through the root table (r divides N)
+                float2 a[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) a[j] = (j < r) ? xi[j * sm] : make_float2(0.f, 0.f);
+                const int rstep = N / r;
+                for (int k = 0; k < r; ++k) {
+                    float2 acc = a[0];
+#pragma unroll
+                    for (int j = 1; j < 5; ++j) {
+                        if (j < r) {
+                            float2 w = tw[((j * k) % r) * rstep];
+                            if (INV) w.y = -w.y;
+                            acc = cadd(acc, cmul(a[j], w));
+                        }
+                    }
+                    float2 wk = tw[p * k * twstep];
+                    if (INV) wk.y = -wk.y;
+                    yo[k * s] = cmul(acc, wk);
+                }
+            }
+        }
+        __syncwarp();
+        float2* tmp = x; x = y; y = tmp;
+        n_cur = m;
+        s *= r;
+    }
+    return x;
+}
+
+__device__ __forceinline__ float load_padded(const float* __restrict__ xb, int i, int L, int pad_mode) {
+    if (i < 0) {
+        if (pad_mode == CRUSE_PAD_CONSTANT) return 0.f;
+        i = -i;
+    } else if (i >= L) {
+        if (pad_mode == CRUSE_PAD_CONSTANT) return 0.f;
+        i = 2 * (L - 1) - i;
+    }
+    return __ldg(xb + i);
+}
+
+__global__ void __launch_bounds__(256)
+stft_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ window, float* __restrict__ spec,
+                float* __restrict__ mag, int B, int L, int N, int hop, int T, int pad_mode, int mag_bins,
+                float mag_eps, FftPlan plan) {
+    extern __shared__ float2 sm_[];
+    const int M = N >> 1, NF = M + 1;
+    float2* tw = sm_;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float2* x = sm_ + N + (size_t)warp * 2 * M;
+    float2* y = x + M;
+    build_twiddles(tw, N);
+    __syncthreads();
+
+    const long long nframes = (long long)B * T;
+    for (long long fr = (long long)blockIdx.x * nwarps + warp; fr < nframes; fr += (long long)gridDim.x * nwarps) {
+        const int b = (int)(fr / T), t = (int)(fr - (long long)b * T);
+        const float* xb = wav + (long long)b * L;
+        const int start = t * hop - M;
+        const bool interior = (start >= 0) && (start + N <= L) && ((((long long)b * L + start) & 1) == 0);
+        if (interior) {
+            const float2* x2 = reinterpret_cast<const float2*>(xb + start);
+            const float2* w2 = reinterpret_cast<const float2*>(window);
+            for (int n = lane; n < M; n += 32) {
+                float2 v = __ldg(x2 + n), w = __ldg(w2 + n);
+                x[n] = make_float2(v.x * w.x, v.y * w.y);
+            }
+        } else {
+            for (int n = lane; n < M; n += 32) {
+                float v0 = load_padded(xb, start + 2 * n, L, pad_mode);
+                float v1 = load_padded(xb, start + 2 * n + 1, L, pad_mode);
+                x[n] = make_float2(v0 * __ldg(window + 2 * n), v1 * __ldg(window + 2 * n + 1));
+            }
+        }
+        __syncwarp();
+        const float2* Z = warp_fft<false>(x, y, tw, M, plan, lane);
+        float2* so = reinterpret_cast<float2*>(spec) + fr * NF;
+        float* mo = mag ? mag + fr * mag_bins : nullptr;
+        for (int k = lane; k <= M; k += 32) {
+            float2 zk = Z[k == M ? 0 : k];
+            float2 zc = Z[k == 0 ? 0 : M - k];
+            zc.y = -zc.y;
+            float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+            float2 xo = make_float2(d.y, -d.x);  // d / i
+            float2 X = cadd(xe, cmul(tw[k], xo));
+            so[k] = X;
+            if (mo && k < mag_bins) mo[k] = sqrtf(X.x * X.x + X.y * X.y + mag_eps);
+        }
+        __syncwarp();
+    }
+}
+
+// grid (chunks, B).  FC frames per chunk + halo recomputed frames in front.
+__global__ void __launch_bounds__(256)
+mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask, const float* __restrict__ window,
+                  float* __restrict__ est_spec, float* __restrict__ wav, int B, int L, int N, int hop, int T,
+                  int mask_bins, int FC, int halo, FftPlan plan) {
+    extern __shared__ float2 sm_[];
+    const int M = N >> 1, NF = M + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float2* tw = sm_;
+    float2* x = sm_ + N + (size_t)warp * 2 * M;
+    float2* y = x + M;
+    float* frames = reinterpret_cast<float*>(sm_ + N + (size_t)nwarps * 2 * M);
+    const int b = blockIdx.y, t0 = blockIdx.x * FC, tbeg = t0 - halo, nfr = FC + halo;
+    build_twiddles(tw, N);
+    __syncthreads();
+    const float inv_m = 1.0f / (float)M;
+
+    for (int fi = warp; fi < nfr; fi += nwarps) {
+        const int t = tbeg + fi;
+        if (t < 0 || t >= T) continue;  // never read by the gather below
+        const long long fr = (long long)b * T + t;
+        const float2* si = reinterpret_cast<const float2*>(spec) + fr * NF;
+        const float* mi = mask ? mask + fr * mask_bins : nullptr;
+        if (est_spec && t >= t0) {
+            float2* eo = reinterpret_cast<float2*>(est_spec) + fr * NF;
+            for (int k = lane; k <= M; k += 32) {
+                float2 v = __ldg(si + k);
+                float mk = (mi && k < mask_bins) ? __ldg(mi + k) : 1.f;
+                eo[k] = make_float2(v.x * mk, v.y * mk);
+            }
+        }
+        if (wav) {
+            for (int k = lane; k < M; k += 32) {
+                float2 xk = __ldg(si + k), xm = __ldg(si + (M - k));
+                float mk = (mi && k < mask_bins) ? __ldg(mi + k) : 1.f;
+                float mm = (mi && (M - k) < mask_bins) ? __ldg(mi + (M - k)) : 1.f;
+                xk.x *= mk; xk.y *= mk; xm.x *= mm; xm.y *= mm;
+                if (k == 0) { xk.y = 0.f; xm.y = 0.f; }  // c2r ignores imag of DC and Nyquist
+                xm.y = -xm.y;                             // conj(X[M-k])
+                float2 xe = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y + xm.y));
+                float2 d = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y - xm.y));
+                float2 w = tw[k];
+                w.y = -w.y;  // W_N^{-k}
+                float2 xo = cmul(d, w);
+                x[k] = make_float2(xe.x - xo.y, xe.y + xo.x);  // Xe + i*Xo
+            }
+            __syncwarp();
+            const float2* z = warp_fft<true>(x, y, tw, M, plan, lane);
+            float* fb = frames + (size_t)fi * N;
+            for (int n = lane; n < M; n += 32) {
+                float2 v = z[n];
+                fb[2 * n] = v.x * inv_m * __ldg(window + 2 * n);
+                fb[2 * n + 1] = v.y * inv_m * __ldg(window + 2 * n + 1);
+            }
+            __syncwarp();
+        }
+    }
+    if (!wav) return;
+    __syncthreads();
+
+    const bool last = (t0 + FC >= T);
+    const long long m_lo = (long long)t0 * hop;
+    long long m_hi = (long long)(t0 + FC) * hop;
+    if (last) {
+        long long a = (long long)(T - 1) * hop + N, c = (long long)L + M;
+        m_hi = a > c ? a : c;
+    }
+    float* wo = wav + (long long)b * L;
+    for (long long m = m_lo + threadIdx.x; m < m_hi; m += blockDim.x) {
+        const long long s = m - M;
+        if (s < 0 || s >= L) continue;
+        int t_hi = (int)(m / hop);
+        if (t_hi > T - 1) t_hi = T - 1;
+        long long num = m - N + hop;
+        int t_lo = num > 0 ? (int)(num / hop) : 0;
+        float sum = 0.f, env = 0.f;
+        for (int t = t_lo; t <= t_hi; ++t) {
+            const int off = (int)(m - (long long)t * hop);
+            sum += frames[(size_t)(t - tbeg) * N + off];
+            const float w = __ldg(window + off);
+            env += w * w;
+        }
+        wo[s] = env > 1e-11f ? sum / env : 0.f;
+    }
+}
+
+__global__ void mask_bwd_kernel(const float* __restrict__ dest, const float* __restrict__ spec,
+                                const float* __restrict__ gscale, float* __restrict__ dmask, long long rows, int NF,
+                                int mask_bins) {
+    const float g = gscale ? __ldg(gscale) : 1.f;
+    const long long total = rows * mask_bins;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / mask_bins;
+        const int f = (int)(i - r * mask_bins);
+        const float2 d = __ldg(reinterpret_cast<const float2*>(dest) + r * NF + f);
+        const float2 x = __ldg(reinterpret_cast<const float2*>(spec) + r * NF + f);
+        dmask[i] = g * (d.x * x.x + d.y * x.y);
+    }
+}
+
+}  // namespace cruse
+
+using namespace cruse;
+
+extern "C" int cruse_stft_fwd(const float* wav, const float* window, float* spec, float* mag, int B, int L, int n_fft,
+                              int hop, int T, int pad_mode, int mag_bins, float mag_eps, void* stream) {
+    CRUSE_CHECK_ARG(wav && window && spec, "stft_fwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && L > 0 && hop > 0 && n_fft >= 4 && (n_fft % 2) == 0, "stft_fwd: bad sizes B=%d L=%d n_fft=%d hop=%d", B, L, n_fft, hop);
+    CRUSE_CHECK_ARG(T == 1 + L / hop, "stft_fwd: T=%d must equal 1 + L/hop = %d (center=True)", T, 1 + L / hop);
+    CRUSE_CHECK_ARG(pad_mode == CRUSE_PAD_CONSTANT || L > n_fft / 2, "stft_fwd: reflect padding needs L > n_fft/2");
+    CRUSE_CHECK_ARG(mag_bins >= 0 && mag_bins <= n_fft / 2 + 1, "stft_fwd: mag_bins out of range");
+    FftPlan plan;
+    CRUSE_CHECK_ARG(make_plan(n_fft / 2, plan) == 0, "stft_fwd: n_fft/2=%d must factor into 2,3,5", n_fft / 2);
+    const int threads = 256, nwarps = threads / 32;
+    const size_t smem = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * n_fft);
+    CRUSE_CHECK_ARG(smem <= 200 * 1024, "stft_fwd: n_fft=%d too large for on-chip FFT", n_fft);
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(stft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nframes = (long long)B * T;
+    long long blocks = (nframes + nwarps - 1) / nwarps;
+    const long long cap = (long long)sm_count() * 4;  // persistent-ish: each CTA builds its twiddle table once
+    if (blocks > cap) blocks = cap;
+    stft_fwd_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(wav, window, spec, mag_bins > 0 ? mag : nullptr, B, L, n_fft,
+                                                                             hop, T, pad_mode, mag_bins, mag_eps, plan);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_mask_istft_fwd(const float* spec, const float* mask, const float* window, float* est_spec,
+                                    float* wav, int B, int L, int n_fft, int hop, int T, int mask_bins, void* stream) {
+    CRUSE_CHECK_ARG(spec && window, "mask_istft_fwd: null pointer");
+    CRUSE_CHECK_ARG(est_spec || wav, "mask_istft_fwd: nothing to compute");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && hop > 0 && n_fft >= 4 && (n_fft % 2) == 0 && hop <= n_fft, "mask_istft_fwd: bad sizes");
+    CRUSE_CHECK_ARG(mask_bins >= 0 && mask_bins <= n_fft / 2 + 1, "mask_istft_fwd: mask_bins out of range");
+    CRUSE_CHECK_ARG(!wav || L > 0, "mask_istft_fwd: L must be positive");
+    FftPlan plan;
+    CRUSE_CHECK_ARG(make_plan(n_fft / 2, plan) == 0, "mask_istft_fwd: n_fft/2=%d must factor into 2,3,5", n_fft / 2);
+    const int threads = 256, nwarps = threads / 32;
+    const int halo = (n_fft - 1) / hop;
+    int FC = 2 * nwarps - halo;
+    if (FC < 1) FC = nwarps;
+    const size_t smem = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * n_fft) + sizeof(float) * (size_t)(FC + halo) * n_fft;
+    CRUSE_CHECK_ARG(smem <= 220 * 1024, "mask_istft_fwd: n_fft=%d / hop=%d need too much shared memory", n_fft, hop);
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((T + FC - 1) / FC, B);
+    mask_istft_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(spec, mask_bins > 0 ? mask : nullptr, window, est_spec, wav, B, L,
+                                                                    n_fft, hop, T, mask_bins, FC, halo, plan);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, float* dmask, int B, int T,
+                              int NF, int mask_bins, void* stream) {
+    CRUSE_CHECK_ARG(dest && spec && dmask, "mask_bwd: null pointer");
+    CRUSE_CHECK_ARG(mask_bins > 0 && mask_bins <= NF, "mask_bwd: mask_bins out of range");
+    const long long rows = (long long)B * T, total = rows * mask_bins;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    mask_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dest, spec, gscale, dmask, rows, NF, mask_bins);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}

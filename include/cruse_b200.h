@@ -1,0 +1,133 @@
+/* cruse_b200.h -- C ABI of libcruse_sm100.so: the CRUSE hot path as sm_100a CUDA kernels.
+ *
+ * Drop-in boundary.  The reference (Okrio/CRUSE) is pure Python and has
+ * no FFI of its own; every arithmetic call on its hot path goes to a PyTorch library op.
+ * Each entry point below replaces one of those call sites (cited as reference file:line,
+ * paths relative to the reference root) and is what a ctypes stub in the reference would
+ * bind.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.  All pointers are DEVICE
+ *    pointers (fp32 unless stated) owned by the caller; kernels never allocate, free or
+ *    retain them.  `stream` is a cudaStream_t passed as void*.  All launches are
+ *    asynchronous on that stream and CUDA-graph capturable.
+ *  - return 0 on success, negative on error; cruse_last_error() returns a thread-local
+ *    message for the last failing call on this thread.
+ *  - activation tensors are FRAME-MAJOR:  [B, T, C, F]  (one STFT frame = C*F contiguous
+ *    floats).  For C == 1 this is bit-identical to the reference's [B, 1, T, F]; the GRU
+ *    view [B, T, C*F'] (model/cruse_net.py:39-40) is free.  Spectra are complex-interleaved
+ *    [B, T, NF, 2] with NF = n_fft/2 + 1.
+ *  - parameters are read in PyTorch's native layouts (Conv2d [Cout,Cin,kh,kw],
+ *    ConvTranspose2d [Cin,Cout,kh,kw], GRU weight_* [3H, I] rows ordered r,z,n).
+ */
+#ifndef CRUSE_B200_H
+#define CRUSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRUSE_MAX_GROUPS 8
+
+/* activation codes shared by conv / convT / bn_act kernels */
+#define CRUSE_ACT_NONE    0
+#define CRUSE_ACT_RELU    1   /* model/cruse_net.py:145 (nn.ReLU named elu)          */
+#define CRUSE_ACT_PRELU   2   /* optional per-channel PReLU (model/mtfaa.py:170)     */
+#define CRUSE_ACT_SIGMOID 3   /* model/cruse_net.py:164                              */
+
+#define CRUSE_PAD_REFLECT  0  /* train_base/acoustics/feature.py:22-30 (torch.stft default) */
+#define CRUSE_PAD_CONSTANT 1  /* utils/utils.py:396                                           */
+
+int cruse_version(void);
+const char* cruse_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int cruse_sm_count(void);
+
+/* ---- a1: STFT.  replaces torch.stft at train_base/acoustics/feature.py:22-30 and
+ *      utils/utils.py:390-396, fused with the magnitude of utils/utils.py:400.
+ *  wav [B,L]; window [n_fft]; spec [B,T,NF,2]; mag [B,T,mag_bins] or NULL
+ *  (mag = sqrt(re^2+im^2+mag_eps) of bins [0,mag_bins)).  T must be 1 + L/hop (center=True). */
+int cruse_stft_fwd(const float* wav, const float* window, float* spec, float* mag,
+                   int B, int L, int n_fft, int hop, int T, int pad_mode,
+                   int mag_bins, float mag_eps, void* stream);
+
+/* ---- a6+a7: mask*spectrum + iSTFT.  replaces PreProcess.masking utils/utils.py:417-433
+ *      (mag_mapping) and torch.istft at feature.py:53-61 / utils/utils.py:448-454.
+ *  spec [B,T,NF,2]; mask [B,T,mask_bins] or NULL (bins >= mask_bins pass through);
+ *  est_spec [B,T,NF,2] or NULL receives mask*spec; wav [B,L] or NULL receives the
+ *  overlap-add reconstruction (hann-squared envelope normalised, trimmed n_fft/2). */
+int cruse_mask_istft_fwd(const float* spec, const float* mask, const float* window,
+                         float* est_spec, float* wav,
+                         int B, int L, int n_fft, int hop, int T, int mask_bins, void* stream);
+
+/* backward of the mask apply: dmask[b,t,f] = gscale * (dre*Xre + dim*Xim), f < mask_bins.
+ * dest [B,T,NF,2] (row stride NF) ; gscale: device scalar or NULL (=1). */
+int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, float* dmask,
+                   int B, int T, int NF, int mask_bins, void* stream);
+
+/* ---- a2/a3: causal strided conv stage.  replaces nn.Conv2d + slice + BatchNorm2d + act at
+ *      model/cruse_net.py:138,141,149-152 (kt=2, fstride=2) and the skip convs :143,153-156
+ *      (kt=1, fstride=1).  Kernel (kt,3), freq padding 1, time taps look back only.
+ *  in [B,T,Cin,Fin]; w [Cout,Cin,kt,3]; bias [Cout]|NULL; out [B,T,Cout,Fout].
+ *  epilogue: v = conv+bias; if scale: v = v*scale[c]+shift[c]; v = act(v) (alpha = PReLU slopes).
+ *  stats_ws (optional, train-mode BN): per-CTA partial sums of the pre-affine value,
+ *  layout [nparts][2*Cout]; nparts = cruse_conv_nparts(B,T). */
+int cruse_conv_fwd(const float* in, const float* w, const float* bias,
+                   const float* scale, const float* shift, const float* alpha, int act,
+                   float* out, float* stats_ws,
+                   int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream);
+int cruse_conv_nparts(int B, int T);
+
+/* ---- a5: decoder stage.  replaces nn.ConvTranspose2d((1,3), stride (1,2)) + crop + BN + act
+ *      + skip add at model/cruse_net.py:161-164.   w [Cin,Cout,1,3]; output cropped to Fout
+ *      (<= 2*Fin+1).  Epilogue as cruse_conv_fwd, then `+ skip` ([B,T,Cout,Fout] or NULL). */
+int cruse_convT_fwd(const float* in, const float* w, const float* bias,
+                    const float* scale, const float* shift, const float* alpha, int act,
+                    const float* skip, float* out, float* stats_ws,
+                    int B, int T, int Cin, int Fin, int Cout, int Fout, void* stream);
+
+/* ---- train-mode BatchNorm2d (model/cruse_net.py:141-142): reduce the per-CTA partials,
+ *      emit scale/shift (and save mean/invstd), update running stats (momentum, unbiased var). */
+int cruse_bn_finalize(const float* stats_ws, int nparts, int C, double count,
+                      const float* gamma, const float* beta, float eps, float momentum,
+                      float* running_mean, float* running_var,
+                      float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+/* y = act(z*scale[c]+shift[c]) (+ skip); z,y [B,T,C,F] */
+int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
+                     const float* skip, float* y, long long n_frames, int C, int F, void* stream);
+
+/* ---- a4: grouped GRU.  replaces nn.GRU(H,H) x groups at model/cruse_net.py:23-31,43-50.
+ *  ih GEMM: xproj[m, g, :] = x[m, g*H:(g+1)*H] . w_ih[g]^T + b_ih[g] (+ b_hh[g] for r,z rows)
+ *  x [M, G*H] (M = B*T); xproj [M, G, 3H].  w_ih/b_ih/b_hh: HOST arrays of G device pointers. */
+int cruse_gru_ih_gemm(const float* x, const float* const* w_ih, const float* const* b_ih,
+                      const float* const* b_hh, float* xproj, int M, int G, int H, void* stream);
+/* recurrence over T with W_hh resident on chip (thread-block cluster per (group, 8-utterance slice)).
+ *  y[b,t, j*y_fs + g*y_gs] = h_t[g][b][j]   (layer 1: y_fs=G,y_gs=1 = the stack/flatten interleave of
+ *  cruse_net.py:43-45; layer 2: y_fs=1,y_gs=H = cat, :49-50).  h0/hT [G,B,H] or NULL (state carry,
+ *  model/based_model/cust_conv.py:303-325). */
+int cruse_gru_seq_fwd(const float* xproj, const float* const* w_hh, const float* const* b_hh,
+                      const float* h0, float* y, float* hT,
+                      int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
+
+/* ---- nn.LayerNorm(D) at model/cruse_net.py:32-33,46,51.  x,y [rows, D]; mean/rstd [rows] or NULL. */
+int cruse_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps,
+                        float* y, float* mean, float* rstd, long long rows, int D, void* stream);
+
+/* ---- a8: weighted-magnitude loss wo_male, loss_func/loss.py:121-148, forward + d/d(est).
+ *  Complex tensors are addressed as  re = p[b*sb + t*st + f*sf], im = p[... + im_off]  so both the
+ *  reference layout [B,2,T,F] and the internal [B,T,NF,2] are accepted without a copy.
+ *  loss: device scalar.  dest (optional): gradient of the loss w.r.t. est in est's layout
+ *  (same strides), unscaled by any upstream gradient.  ws: >= cruse_wo_male_ws_bytes() bytes. */
+typedef struct { long long sb, st, sf, im_off; } cruse_cplx_layout;
+int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
+                          const float* unproc, cruse_cplx_layout lunp, float* dest,
+                          float* loss, void* ws, int B, int T, int F, void* stream);
+size_t cruse_wo_male_ws_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRUSE_B200_H */

@@ -1,0 +1,355 @@
+"""CPU oracle for the CRUSE hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this file.  The product path (``cruse_b200``)
+never imports it and fails loudly when its CUDA library is missing.
+
+What it is: a minimal-repair restatement of the reference's algorithm for the
+path  STFT -> conv-recurrent U-Net -> mask*spectrum -> iSTFT -> weighted-magnitude
+loss, built from stock ``torch.nn`` CPU ops (torch CPU fp32 is the arithmetic
+authority).  Each function cites the reference lines it follows
+(paths relative to /root/reference) and each repair cites the defect it fixes
+(SURVEY.md Appendix A).
+
+PARITY PIN STATUS: **parity unpinned against reference golden vectors** -- the
+reference holds no golden vector, known-answer test or fixture for this path and
+its own model/loss/STFT files do not import.  What *is* pinned:
+the reference fragments that do run in the build container
+(``model/based_model/cust_conv.py`` Conv2dNormAct / GroupedGRULayer,
+``train_base/acoustics/mask.py`` complex_mul, ``train_base/loss.py`` si_snr_loss)
+were executed there by ``oracle/make_golden.py`` and their outputs are committed
+under ``tests/golden/ref_*.npz``; ``tests/test_oracle.py`` checks this file
+against them.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+EPS_MAG = 1e-8  # utils/utils.py:400  sqrt(re^2 + im^2 + 1e-8)
+
+
+# --------------------------------------------------------------------------
+# model/cruse_net.py:14-55  GGRU
+# --------------------------------------------------------------------------
+class GGRU(nn.Module):
+    """Grouped 2-layer GRU + LayerNorm bottleneck (model/cruse_net.py:14-55).
+
+    Kept exactly, including the layer-1 ``stack(dim=-1)+flatten`` interleave
+    (:43-45, output feature index = h*G + g) versus the layer-2 ``cat`` (:48-50).
+    Repair: :53 ``self.view`` -> ``out.view`` (App. A.1).
+    """
+
+    def __init__(self, in_features=None, out_features=None, mid_features=None,
+                 hidden_size=1024, groups=2):
+        super().__init__()
+        hidden_size_t = hidden_size // groups
+        self.gru_list1 = nn.ModuleList(
+            [nn.GRU(hidden_size_t, hidden_size_t, 1, batch_first=True) for _ in range(groups)])
+        self.gru_list2 = nn.ModuleList(
+            [nn.GRU(hidden_size_t, hidden_size_t, 1, batch_first=True) for _ in range(groups)])
+        self.ln1 = nn.LayerNorm(hidden_size)
+        self.ln2 = nn.LayerNorm(hidden_size)
+        self.groups = groups
+        self.mid_features = mid_features
+
+    def forward(self, x):
+        out = x.transpose(1, 2).contiguous()                       # :39  [B,T,C,F']
+        out = out.view(out.size(0), out.size(1), -1).contiguous()  # :40  [B,T,C*F']
+        out = torch.chunk(out, self.groups, dim=-1)                # :42
+        out = torch.stack([self.gru_list1[i](out[i])[0] for i in range(self.groups)], dim=-1)  # :43-44
+        out = torch.flatten(out, start_dim=-2, end_dim=-1)         # :45
+        out = self.ln1(out)                                        # :46
+        out = torch.chunk(out, self.groups, dim=-1)                # :48
+        out = torch.cat([self.gru_list2[i](out[i])[0] for i in range(self.groups)], dim=-1)    # :49-50
+        out = self.ln2(out)                                        # :51
+        out = out.view(out.size(0), out.size(1), x.size(1), -1).contiguous()  # :53 (repaired)
+        out = out.transpose(1, 2).contiguous()                     # :54
+        return out
+
+
+def freq_pyramid(in_feat: int, nlayers: int):
+    """Frequency sizes after each (k=3, s=2, p=1) encoder conv (model/cruse_net.py:134-138)."""
+    f = [in_feat]
+    for _ in range(nlayers):
+        f.append((f[-1] + 2 * 1 - 3) // 2 + 1)
+    return f
+
+
+# --------------------------------------------------------------------------
+# model/cruse_net.py:129-165  unet_2
+# --------------------------------------------------------------------------
+class unet_2(nn.Module):
+    """Repaired ``unet_2`` (model/cruse_net.py:129-165); repairs = SURVEY App. A.1.
+
+    Module creation order follows the reference loop (:137-143) so that default
+    initialisation under a fixed seed is reproducible and ``state_dict()`` is the
+    surface of SURVEY App. C.
+    """
+
+    def __init__(self, in_feat=161, ch=(1, 8, 16, 32, 64), stride=(1, 2), rnn_groups=4, act="relu"):
+        super().__init__()
+        self.laynum = len(ch) - 1
+        self.ker_x = 2
+        self.stride = tuple(stride)
+        self.padding = [self.ker_x - stride[0], 3 - stride[1]]          # :136
+        self.ch = tuple(ch)
+        self.in_feat = in_feat
+        self.freqs = freq_pyramid(in_feat, self.laynum)
+        self.act_kind = act
+        n = self.laynum
+        for i in range(n):
+            setattr(self, f"conv{i+1}", nn.Conv2d(ch[i], ch[i + 1], (self.ker_x, 3), self.stride, self.padding))  # :138
+            tmp = n - i
+            # :140 repaired: conv{tmp}_t is the transposed conv the forward uses (:161-164)
+            setattr(self, f"conv{tmp}_t", nn.ConvTranspose2d(ch[tmp], ch[tmp - 1], (1, 3), self.stride))
+            setattr(self, f"bn{i+1}", nn.BatchNorm2d(ch[i + 1]))                                                     # :141
+            if tmp >= 2:  # :142 repaired index/name; no BN on the sigmoid output layer (:164)
+                setattr(self, f"bn{tmp}_t", nn.BatchNorm2d(ch[tmp - 1]))
+            # :143 repaired: padding (0,1) keeps F so the skip can be added (:160-163)
+            setattr(self, f"skip_connect_{i+1}", nn.Conv2d(ch[i + 1], ch[i + 1], (1, 3), bias=False, padding=(0, 1)))
+        # :144 repaired: hidden size from the real conv arithmetic (1024 at F=256)
+        self.gru = GGRU(hidden_size=ch[-1] * self.freqs[-1], groups=rnn_groups)
+        self.elu = nn.ReLU()                                              # :145 (named elu, is ReLU)
+        self.fc = nn.Linear(in_feat, in_feat)                             # :146 unused, kept for state_dict
+        if act == "prelu":  # optional (north_star); absent for act="relu" so state_dict stays reference-shaped
+            for k in range(1, n + 1):
+                setattr(self, f"act{k}", nn.PReLU(ch[k]))
+            for k in range(n, 1, -1):
+                setattr(self, f"act{k}_t", nn.PReLU(ch[k - 1]))
+        elif act != "relu":
+            raise ValueError(f"act must be 'relu' or 'prelu', got {act!r}")
+
+    def _act(self, name, x):
+        if self.act_kind == "relu":
+            return self.elu(x)
+        return getattr(self, name)(x)
+
+    def forward(self, x):
+        n = self.laynum
+        p0 = self.padding[0]
+        e = []
+        out = x
+        for k in range(1, n + 1):                                         # :149-152 repaired
+            z = getattr(self, f"conv{k}")(out)[..., :-p0, :]
+            out = self._act(f"act{k}", getattr(self, f"bn{k}")(z))
+            e.append(out)
+        skips = [getattr(self, f"skip_connect_{k}")(e[k - 1]) for k in range(1, n + 1)]  # :153-156 repaired
+        out = self.gru(e[-1]) + skips[-1]                                 # :158-160
+        for k in range(n, 1, -1):                                         # :161-163 repaired (chained)
+            z = getattr(self, f"conv{k}_t")(out)[..., : self.freqs[k - 1]]
+            out = self._act(f"act{k}_t", getattr(self, f"bn{k}_t")(z)) + skips[k - 2]
+        return torch.sigmoid(self.conv1_t(out)[..., : self.freqs[0]])     # :164
+
+
+# --------------------------------------------------------------------------
+# train_base/acoustics/feature.py:10-61   stft / istft
+# --------------------------------------------------------------------------
+def stft(y, n_fft, hop_length, win_length, pad_mode="reflect"):
+    """feature.py:10-30 (pad_mode='constant' = PreProcess.pre_stft, utils/utils.py:396)."""
+    assert y.dim() == 2
+    return torch.stft(y, n_fft, hop_length, win_length, window=torch.hann_window(n_fft).to(y.device),
+                      return_complex=True, center=True, pad_mode=pad_mode)
+
+
+def istft(features, n_fft, hop_length, win_length, length=None, use_mag_phase=False):
+    """feature.py:33-61; repair: complex input required by torch>=2 (App. A.2)."""
+    if use_mag_phase:
+        assert isinstance(features, (tuple, list))
+        mag, phase = features
+        features = torch.stack([mag * torch.cos(phase), mag * torch.sin(phase)], dim=-1)
+    if not torch.is_complex(features):
+        features = torch.view_as_complex(features.contiguous())
+    return torch.istft(features, n_fft, hop_length, win_length,
+                       window=torch.hann_window(n_fft).to(features.device), length=length, center=True)
+
+
+# --------------------------------------------------------------------------
+# utils/utils.py:365-455   PreProcess
+# --------------------------------------------------------------------------
+class PreProcess:
+    """utils/utils.py:365-455, repaired for torch>=2 (return_complex, App. A.2)."""
+
+    def __init__(self, win_len, win_inc, fft_len, win_type="hanning", post_process_mode="mag_mapping",
+                 loss_mode="freq", use_cuda=False):
+        self.win_len, self.win_inc, self.fft_len = win_len, win_inc, fft_len
+        self.post_process_mode, self.loss_mode = post_process_mode, loss_mode
+        if win_type != "hanning":
+            raise ValueError("ERROR window type")
+        self.window = torch.hann_window(fft_len)
+
+    def pre_stft(self, inputs):
+        c = torch.stft(inputs, n_fft=self.fft_len, hop_length=self.win_inc, win_length=self.win_len,
+                       window=self.window, center=True, pad_mode="constant", return_complex=True)
+        stft_inputs = torch.view_as_real(c).transpose(1, 3).contiguous()   # [B,2,T,F]  (:397)
+        real = stft_inputs[:, 0, :, :]
+        imag = stft_inputs[:, 1, :, :]
+        spec_mags = torch.sqrt(real ** 2 + imag ** 2 + EPS_MAG)            # :400
+        spec_phase = torch.atan2(imag, real)
+        self.real, self.imag = real.unsqueeze(1), imag.unsqueeze(1)
+        self.spec_mags, self.spec_phase = spec_mags.unsqueeze(1), spec_phase.unsqueeze(1)
+        return stft_inputs, self.real, self.imag, self.spec_mags, self.spec_phase
+
+    def masking(self, mask_real, mask_imag=None):                          # :417-433
+        if self.post_process_mode == "mag_mapping":
+            out_real, out_imag = mask_real * self.real, mask_real * self.imag
+        elif self.post_process_mode == "complex_mapping":
+            out_real, out_imag = mask_real * self.real, mask_imag * self.imag
+        elif self.post_process_mode == "mapping":
+            out_real, out_imag = mask_real, mask_imag
+        else:
+            raise NotImplementedError
+        return torch.stack([out_real.squeeze(1), out_imag.squeeze(1)], dim=-1).contiguous()  # [B,T,F,2]
+
+    def reconstruction(self, stft_outputs, sig_len=None):                  # :443-455  in: [B,T,F,2]
+        c = torch.view_as_complex(stft_outputs.contiguous()).transpose(1, 2)  # -> [B,F,T]
+        return torch.istft(c, n_fft=self.fft_len, hop_length=self.win_inc, win_length=self.win_len,
+                           window=self.window, center=True, length=sig_len)
+
+
+def complex_mul(noisy_r, noisy_i, mask_r, mask_i):
+    """train_base/acoustics/mask.py:60-62."""
+    return noisy_r * mask_r - noisy_i * mask_i, noisy_r * mask_i + noisy_i * mask_r
+
+
+# --------------------------------------------------------------------------
+# loss_func/loss.py
+# --------------------------------------------------------------------------
+def wo_male(ref, est, unproc, norm=False, eps=1e-8):
+    """loss_func/loss.py:121-148; repairs :129 torch.size -> .size(), :139 index (App. A.4)."""
+    if ref.shape != est.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate wo-male, {ref.shape} vs {est.shape}")
+    alpha, beta, gamma = 2, 1, 1
+    B, C, T, F = ref.size()
+    mag_ref = torch.sqrt(ref[:, 0] ** 2 + ref[:, 1] ** 2)
+    mag_est = torch.sqrt(est[:, 0] ** 2 + est[:, 1] ** 2)
+    mag_unproc = torch.sqrt(unproc[:, 0] ** 2 + unproc[:, 1] ** 2)
+    iam = (mag_ref / mag_unproc) ** gamma
+    w_iam = torch.exp(alpha / (beta + iam))
+    loss = w_iam * torch.abs(torch.log10(mag_est + 1) - torch.log10(mag_ref + 1))
+    return torch.sum(loss) / (B * T * F * 1.0)
+
+
+def rmse(ref, est, eps=1e-8):
+    """loss_func/loss.py:59-78 (sum sqrt(err^2) / (B*T*F))."""
+    if ref.shape != est.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate rmse, {ref.shape} vs {est.shape}")
+    B, C, T, F = ref.size()
+    return torch.sum(torch.sqrt((est - ref) ** 2)) / (B * T * F)
+
+
+def c_rmse(ref, est, unproc=None, norm=False, eps=1e-8):
+    """loss_func/loss.py:88-118, arithmetic kept literally (incl. the tmp1/tmp2 mix at :107-109)."""
+    if ref.shape != est.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate c_mse, {ref.shape} vs {est.shape}")
+    c, beta = 0.3, 0.3
+    mag_ref = torch.sqrt(ref[:, 0] ** 2 + ref[:, 1] ** 2)
+    phase_ref = torch.atan2(ref[:, 1], ref[:, 0])
+    mag_est = torch.sqrt(est[:, 0] ** 2 + est[:, 1] ** 2)
+    phase_est = torch.atan2(est[:, 1], est[:, 0])
+    tmp1, tmp2 = torch.pow(mag_est, c), torch.pow(mag_ref, c)
+    tmp3 = tmp1 * torch.cos(phase_ref) + tmp1 * torch.sin(phase_ref) * 1j
+    tmp4 = tmp2 * torch.cos(phase_est) + tmp1 * torch.sin(phase_est) * 1j
+    tmp5 = torch.abs(tmp3 - tmp4)
+    loss1 = (tmp2 - tmp1) ** 2
+    return (1 - beta) * torch.sum(loss1) + beta * torch.sum(tmp5 ** 2)
+
+
+def sisnr(s1, s2, eps=1e-8):
+    """loss_func/loss.py:37-56."""
+    def l2(a, b):
+        return torch.sum(a * b, -1, keepdim=True)
+    s_target = l2(s1, s2) / (l2(s2, s2) + eps) * s2
+    e_noise = s1 - s_target
+    snr = 10 * torch.log10(l2(s_target, s_target) / (l2(e_noise, e_noise) + eps) + eps)
+    return torch.mean(snr)
+
+
+def si_snr_loss():
+    """train_base/loss.py:7-25."""
+    def si_snr(x, s, eps=1e-8):
+        def l2norm(mat, keep_dim=False):
+            return torch.norm(mat, dim=-1, keepdim=keep_dim)
+        if x.shape != s.shape:
+            raise RuntimeError(f"Dimension mismatch when calculate si_snr, {x.shape} vs {s.shape}")
+        x_zm = x - torch.mean(x, dim=-1, keepdim=True)
+        s_zm = s - torch.mean(s, dim=-1, keepdim=True)
+        t = torch.sum(x_zm * s_zm, dim=-1, keepdim=True) * s_zm / (l2norm(s_zm, keep_dim=True) ** 2 + eps)
+        return -torch.mean(20 * torch.log10(eps + l2norm(t) / (l2norm(x_zm - t) + eps)))
+    return si_snr
+
+
+class loss_func:
+    """loss_func/loss.py:16-34 dispatcher (arg order: wo_male(labels, inputs, noisy))."""
+
+    MODES = ['SI-SNR', 'SS-SNR', 'MSE', 'Normal_MSE', 'CN_MSE', 'D_MSE', 'WO_MALE', 'C_MSE']
+
+    def __init__(self, loss_mode):
+        assert loss_mode in self.MODES, "Loss mode must be one of ***"
+        self.loss_mode = loss_mode
+
+    def loss(self, inputs, labels, noisy=None):
+        if self.loss_mode == 'SI-SNR':
+            return -(sisnr(inputs, labels))
+        elif self.loss_mode == 'SS-SNR':
+            return 0
+        elif self.loss_mode == 'WO_MALE':
+            return wo_male(labels, inputs, noisy)
+        elif self.loss_mode == 'C_MSE':
+            return c_rmse(labels, inputs)
+        elif self.loss_mode == 'MSE':
+            return rmse(labels, inputs)
+
+
+# --------------------------------------------------------------------------
+# The hot path end to end, used by parity tests and cpu_baseline
+# --------------------------------------------------------------------------
+def spec_to_bctf(c):
+    """complex [B,F,T] -> real [B,2,T,F] (utils/utils.py:397-399 layout)."""
+    return torch.view_as_real(c).permute(0, 3, 2, 1).contiguous()
+
+
+def enhance(model, noisy, n_fft=512, hop=320, pad_mode="reflect"):
+    """noisy wav [B,L] -> (enhanced wav [B,L], est spec [B,2,T,NF], mask [B,1,T,F], noisy spec [B,2,T,NF])."""
+    X = spec_to_bctf(stft(noisy, n_fft, hop, n_fft, pad_mode))            # feature.py:10-30
+    F = model.in_feat
+    mag = torch.sqrt(X[:, 0:1] ** 2 + X[:, 1:2] ** 2 + EPS_MAG)[..., :F]   # utils.py:400
+    mask = model(mag)                                                     # cruse_net.py:147-165
+    full = torch.ones_like(X[:, 0:1])
+    full[..., :F] = mask                                                  # bins >= F pass through
+    est = X * full                                                        # utils.py:418-420 mag_mapping
+    c = torch.complex(est[:, 0], est[:, 1]).transpose(1, 2)               # [B,NF,T]
+    wav = istft(c, n_fft, hop, n_fft, length=noisy.shape[-1])             # feature.py:33-61
+    return wav, est, mask, X
+
+
+def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
+    """STFT + forward + mask + iSTFT + wo_male on the F bins the net sees."""
+    wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
+    S = spec_to_bctf(stft(clean, n_fft, hop, n_fft, pad_mode))
+    F = model.in_feat
+    loss = wo_male(S[..., :F], est[..., :F], X[..., :F])                  # loss.py:121-148
+    return loss, wav, est, mask
+
+
+def synth_batch(B, L, seed=20260):
+    """SURVEY section 8d synthetic data: clean/noise = 0.05*randn, noisy = clean+noise."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    clean = 0.05 * torch.randn(B, L, generator=g)
+    noise = 0.05 * torch.randn(B, L, generator=g)
+    return clean + noise, clean
+
+
+def make_model(in_feat=256, act="relu", seed=1234, eval_stats=True):
+    """SURVEY section 8d weights: manual_seed(1234) + default inits; eval BN stats randomised."""
+    torch.manual_seed(seed)
+    m = unet_2(in_feat=in_feat, act=act)
+    if eval_stats:
+        g = torch.Generator(device="cpu").manual_seed(seed + 1)
+        for mod in m.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+                mod.running_var.copy_(1 + 0.1 * torch.rand(mod.num_features, generator=g))
+    return m

@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the CRUSE hot path (STFT -> U-Net -> mask -> iSTFT -> wo_male loss) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload infer|stream]
+
+One "step" = one pass of the hot path over one batch of synthetic 16 kHz clips.  At N=1 the
+workload is BASELINE.json configs[1]: CRUSE (4-enc/4-dec, 256-GRU) inference fwd+loss, batch
+32 x 10 s, n_fft 512, hop 320 (20 ms) -> 32 x 501 = 16 032 STFT frames per step.  N>1 is weak
+scaling (every rank runs its own 32 x 10 s shard; the inference path has no data-path
+collective); timing = max over ranks, value = all ranks' frames / that time.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, N_FFT, HOP, F_BINS = 16000, 512, 320, 256
+WORKLOADS = {
+    # name: (clips per GPU, seconds per clip, description)
+    "infer": (32, 10.0, "cfg2: CRUSE 4enc/4dec 256-GRU inference fwd+loss, 32x10s per GPU, n_fft512 hop320"),
+}
+
+
+def synth_batch(B, L, seed):
+    """SURVEY.md 8d synthetic data (same formula the oracle's synth_batch uses)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    clean = 0.05 * torch.randn(B, L, generator=g)
+    noise = 0.05 * torch.randn(B, L, generator=g)
+    return clean + noise, clean
+
+
+def randomise_bn(model, seed=1235):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
+            mod.running_var.copy_(1 + 0.1 * torch.rand(mod.num_features, generator=g))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU path: the minimal-repair oracle (the reference sources do not import,
+    SURVEY.md section 0), torch CPU fp32 with all host threads, on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cruse_oracle as o
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B_full, secs, desc = WORKLOADS[args.workload]
+    Bs = min(B_full, args.ref_clips)
+    L = int(secs * SR)
+    T = 1 + L // HOP
+    model = o.make_model(F_BINS).eval()
+    noisy, clean = synth_batch(Bs, L, 20260)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            o.forward_loss(model, noisy, clean, N_FFT, HOP)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            loss, _, _, _ = o.forward_loss(model, noisy, clean, N_FFT, HOP)
+        dt = time.perf_counter() - t0
+    fps = Bs * T * args.steps / dt
+    sample = f"{Bs} of {B_full} clips x {secs:g}s per step (oracle port, torch {torch.__version__} CPU fp32)"
+    line = {
+        "impl": "reference", "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE fwd+loss", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": float(loss),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(workload, budget_s=15.0):
+    from oracle import cruse_oracle as o
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B_full, secs, _ = WORKLOADS[workload]
+    Bs, L = 4, int(secs * SR)
+    T = 1 + L // HOP
+    model = o.make_model(F_BINS).eval()
+    noisy, clean = synth_batch(Bs, L, 20260)
+    with torch.no_grad():
+        o.forward_loss(model, noisy, clean, N_FFT, HOP)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            o.forward_loss(model, noisy, clean, N_FFT, HOP)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > budget_s or n >= 20:
+                break
+    return {"value": Bs * T * n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{n} passes over {Bs} of {B_full} clips x {secs:g}s (oracle port, torch CPU fp32, {cores} threads)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from cruse_b200 import ops, pipeline
+    from cruse_b200.cruse_net import unet_2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    B, secs, desc = WORKLOADS[args.workload]
+    L = int(secs * SR)
+    T = 1 + L // HOP
+    frames = B * T
+
+    torch.manual_seed(1234)
+    model = unet_2(in_feat=F_BINS)
+    randomise_bn(model)
+    model = model.to(dev).eval()
+    noisy_h, clean_h = synth_batch(B, L, 20260 + rank)
+    noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
+    noisy, clean = noisy_h.to(dev), clean_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        with torch.no_grad():
+            return pipeline.forward_loss(model, noisy, clean, N_FFT, HOP)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- kernel-launch count of one step
+    prof = ops.Profile(timing=False)
+    ops.set_profile(prof)
+    loss = step()
+    ops.set_profile(None)
+    launches_per_step = prof.launches
+
+    # ---- timed region: K steps, device time by CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = step()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = frames * world * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: host buffers in, loss out, copies inside the timed region
+    for _ in range(2):
+        pipeline.forward_loss_host(model, noisy_h, clean_h, N_FFT, HOP)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(args.steps):
+            l_host = pipeline.forward_loss_host(model, noisy_h, clean_h, N_FFT, HOP)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": frames * world * args.steps / float(t.item()), "unit": "frames/s",
+           "h2d_bytes_per_step": int(noisy_h.numel() * 4 + clean_h.numel() * 4), "d2h_bytes_per_step": 4,
+           "ms_per_step": 1e3 * float(t.item()) / args.steps}
+
+    # ---- per-kernel device times of one step (CUDA events on the launching stream) -> roofline
+    pk = peaks()
+    rows_acc = {}
+    for _ in range(5):
+        flush.zero_()
+        prof = ops.Profile(timing=True)
+        ops.set_profile(prof)
+        step()
+        ops.set_profile(None)
+        for i, (n, tag, by, fl, ms) in enumerate(prof.rows()):
+            rows_acc.setdefault((i, n, tag, by, fl), []).append(ms)
+    kernels = []
+    for (i, n, tag, by, fl), mss in sorted(rows_acc.items()):
+        ms = sum(mss) / len(mss)
+        kernels.append({"call": n.replace("cruse_", ""), "tag": tag, "ms": round(ms, 4), "GBps": round(by / ms / 1e6, 1) if ms else None,
+                        "TFLOPs": round(fl / ms / 1e9, 2) if ms else None, "alg_bytes": by, "flops": fl})
+    step_ms_sum = sum(k["ms"] for k in kernels)
+    dom = max(kernels, key=lambda k: k["ms"])
+    roofline = {"kernel": f'{dom["call"]} [{dom["tag"]}]', "bound": "hbm", "achieved": dom["GBps"], "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "frac": round(dom["GBps"] / pk["hbm_gbs"], 4), "traffic": None,
+                "share_of_step": round(dom["ms"] / step_ms_sum, 3), "peak_source": pk["source"],
+                "note": "gru_seq is latency-bound by T sequential steps; see profiles/ for the per-kernel table"}
+
+    line = {
+        "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE fwd+loss", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "frames_per_step_per_gpu": frames, "l2": "256 MB flush write between timed steps",
+                   "launch": "eager ctypes launches on torch's current stream"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "clocks": sampler.summary(), "loss": float(loss), "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(args.workload)
+    if rank == 0:
+        if args.table:
+            with open(args.table, "w") as f:
+                f.write("| call | tag | ms | alg GB/s | frac of %.0f GB/s | TFLOP/s |\n|---|---|---:|---:|---:|---:|\n" % pk["hbm_gbs"])
+                for k in kernels:
+                    f.write(f'| {k["call"]} | {k["tag"]} | {k["ms"]:.4f} | {k["GBps"]} | {k["GBps"] / pk["hbm_gbs"]:.3f} | {k["TFLOPs"]} |\n')
+                f.write(f"\nsum of kernels {step_ms_sum:.3f} ms; timed step {total_ms / args.steps:.3f} ms; {frames} frames/step\n")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="infer", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the bounded CPU sample (--impl reference)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", default=None, help="write the per-kernel roofline table (markdown) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

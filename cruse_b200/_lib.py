@@ -1,0 +1,79 @@
+"""ctypes binding of libcruse_sm100.so (C ABI in include/cruse_b200.h).
+
+The library is the only compute path.  ``lib()`` raises ``RuntimeError`` when the shared
+object is missing -- there is deliberately no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcruse_sm100.so")
+
+c_fp = C.c_void_p      # device float*
+c_pp = C.c_void_p      # host array of device pointers
+c_int = C.c_int
+c_ll = C.c_longlong
+c_f = C.c_float
+c_d = C.c_double
+
+
+class CplxLayout(C.Structure):
+    """cruse_cplx_layout: re = p[b*sb + t*st + f*sf], im = p[... + im_off]."""
+    _fields_ = [("sb", c_ll), ("st", c_ll), ("sf", c_ll), ("im_off", c_ll)]
+
+
+# name -> (restype, argtypes).  Must list every symbol include/cruse_b200.h declares
+# (tests/test_abi.py parses the header and checks).
+SIGNATURES = {
+    "cruse_version": (c_int, []),
+    "cruse_last_error": (C.c_char_p, []),
+    "cruse_sm_count": (c_int, []),
+    "cruse_stft_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_fp]),
+    "cruse_mask_istft_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
+    "cruse_mask_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "cruse_conv_fwd": (c_int, [c_fp] * 7 + [c_int, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
+    "cruse_conv_nparts": (c_int, [c_int, c_int]),
+    "cruse_convT_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_f, c_f] + [c_fp] * 6 + [c_fp]),
+    "cruse_bn_fold": (c_int, [c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_int, c_fp]),
+    "cruse_bn_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_int, c_int, c_fp]),
+    "cruse_gru_ih_gemm": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),
+    "cruse_gru_seq_fwd": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),
+    "cruse_wo_male_fwd_bwd": (c_int, [c_fp, CplxLayout, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp,
+                                      c_int, c_int, c_int, c_fp]),
+    "cruse_wo_male_ws_bytes": (C.c_size_t, []),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: cruse_b200 has no CPU/eager fallback. "
+                    "Build it with `python -m cruse_b200.build` (needs nvcc, targets sm_100a).")
+            h = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(h, name)   # AttributeError if the .so is stale
+                fn.restype = res
+                fn.argtypes = args
+            _lib = h
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    """Reference convention = Python exceptions (loss.py:65-68, feature.py:352-354): rc != 0 -> RuntimeError."""
+    if rc != 0:
+        msg = lib().cruse_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what or 'cruse_b200'} failed (rc={rc}): {msg}")

@@ -1,0 +1,199 @@
+"""Drop-in ``unet_2`` / ``GGRU`` (reference: model/cruse_net.py:14-55, :129-165) on sm_100a kernels.
+
+The classes keep the reference's plugin surface: same constructor,
+``forward(x [B,1,T,F]) -> mask [B,1,T,F]``, and a ``state_dict()`` whose keys / shapes are those of
+the reference's stock ``torch.nn`` children (App. C) -- the children are created in the
+reference's order purely as PARAMETER CONTAINERS (so seeds, checkpoints, DDP and Adam behave
+identically) and are never called: every stage runs through ``libcruse_sm100.so``.
+There is no CPU path: a CPU tensor raises.
+
+Repairs to the reference's literal (non-running) code follow SURVEY.md Appendix A.1 and are the
+same ones the oracle makes; they are cited inline.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def freq_pyramid(in_feat: int, nlayers: int):
+    """bins after each (k=3, s=2, p=1) encoder conv (model/cruse_net.py:134-138)."""
+    f = [in_feat]
+    for _ in range(nlayers):
+        f.append((f[-1] + 2 - 3) // 2 + 1)
+    return f
+
+
+def _need_cuda(x, what):
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: cruse_b200 runs on sm_100a only; got a {x.device} tensor (no CPU fallback)")
+
+
+class GGRU(nn.Module):
+    """Grouped 2-layer GRU + LayerNorm bottleneck (model/cruse_net.py:14-55).
+
+    Layer 1 outputs are interleaved (stack(dim=-1)+flatten, :43-45 -> feature index h*G+g),
+    layer 2 outputs concatenated (:49-50); both orders are produced directly by the recurrence
+    kernel's store strides, so no shuffle/copy kernels run.
+    """
+
+    def __init__(self, in_features=None, out_features=None, mid_features=None, hidden_size=1024, groups=2):
+        super().__init__()
+        hidden_size_t = hidden_size // groups
+        if hidden_size_t * groups != hidden_size:
+            raise ValueError(f"hidden_size {hidden_size} not divisible by groups {groups}")
+        self.gru_list1 = nn.ModuleList(
+            [nn.GRU(hidden_size_t, hidden_size_t, 1, batch_first=True) for _ in range(groups)])   # :23-26
+        self.gru_list2 = nn.ModuleList(
+            [nn.GRU(hidden_size_t, hidden_size_t, 1, batch_first=True) for _ in range(groups)])   # :28-31
+        self.ln1 = nn.LayerNorm(hidden_size)                                                       # :32
+        self.ln2 = nn.LayerNorm(hidden_size)                                                       # :33
+        self.groups = groups
+        self.hidden_size = hidden_size
+        self.mid_features = mid_features
+
+    # -- internal frame-major entry: x [B,T,D] -> [B,T,D] (+ residual fused into ln2) ----------
+    def _layer(self, x2d, grus, B, T, interleave, h0=None, want_hT=False):
+        xproj = ops.gru_ih_gemm(x2d, [g.weight_ih_l0 for g in grus], [g.bias_ih_l0 for g in grus],
+                                [g.bias_hh_l0 for g in grus])
+        return ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
+                               interleave=interleave, h0=h0, want_hT=want_hT)
+
+    def forward_frames(self, x, residual=None, state=None, want_state=False):
+        """x [B,T,D] frame-major.  state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence
+        (streaming, model/based_model/cust_conv.py:303-325)."""
+        _need_cuda(x, "GGRU")
+        B, T, D = x.shape
+        if D != self.hidden_size:
+            raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
+        h1 = h2 = None
+        if state is not None:
+            h1, h2 = state
+        r1 = self._layer(x.reshape(B * T, D), self.gru_list1, B, T, True, h1, want_state)
+        y1, n1 = r1 if want_state else (r1, None)
+        z1 = ops.layernorm_fwd(y1, self.ln1.weight, self.ln1.bias, self.ln1.eps)
+        r2 = self._layer(z1.view(B * T, D), self.gru_list2, B, T, False, h2, want_state)
+        y2, n2 = r2 if want_state else (r2, None)
+        out = ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)
+        return (out, (n1, n2)) if want_state else out
+
+    def forward(self, x):
+        """reference layout: x [B,C,T,F'] -> [B,C,T,F'] (:37-55; :53 repaired to out.view)."""
+        _need_cuda(x, "GGRU")
+        B, Cc, T, Fp = x.shape
+        frames = x.transpose(1, 2).contiguous().view(B, T, Cc * Fp)      # :39-40 (layout plumbing)
+        out = self.forward_frames(frames)
+        return out.view(B, T, Cc, Fp).transpose(1, 2).contiguous()       # :53-54
+
+
+class unet_2(nn.Module):
+    """4-enc / 4-dec convolutional-recurrent U-Net mask estimator (model/cruse_net.py:129-165)."""
+
+    def __init__(self, in_feat=161, ch=(1, 8, 16, 32, 64), stride=(1, 2), rnn_groups=4, act="relu"):
+        super().__init__()
+        if tuple(stride) != (1, 2):
+            raise ValueError("unet_2: only the reference's stride (1,2) is supported")
+        self.laynum = len(ch) - 1
+        self.ker_x = 2
+        self.stride = tuple(stride)
+        self.padding = [self.ker_x - stride[0], 3 - stride[1]]                                       # :136
+        self.ch = tuple(ch)
+        self.in_feat = in_feat
+        self.freqs = freq_pyramid(in_feat, self.laynum)
+        self.act_kind = act
+        n = self.laynum
+        for i in range(n):                                                                          # :137-143
+            setattr(self, f"conv{i+1}", nn.Conv2d(ch[i], ch[i + 1], (self.ker_x, 3), self.stride, self.padding))
+            tmp = n - i
+            setattr(self, f"conv{tmp}_t", nn.ConvTranspose2d(ch[tmp], ch[tmp - 1], (1, 3), self.stride))  # :140 repaired
+            setattr(self, f"bn{i+1}", nn.BatchNorm2d(ch[i + 1]))
+            if tmp >= 2:
+                setattr(self, f"bn{tmp}_t", nn.BatchNorm2d(ch[tmp - 1]))                             # :142 repaired
+            setattr(self, f"skip_connect_{i+1}",
+                    nn.Conv2d(ch[i + 1], ch[i + 1], (1, 3), bias=False, padding=(0, 1)))             # :143 repaired
+        self.gru = GGRU(hidden_size=ch[-1] * self.freqs[-1], groups=rnn_groups)                      # :144 repaired
+        self.elu = nn.ReLU()                                                                         # :145
+        self.fc = nn.Linear(in_feat, in_feat)                                                        # :146 (unused)
+        if act == "prelu":
+            for k in range(1, n + 1):
+                setattr(self, f"act{k}", nn.PReLU(ch[k]))
+            for k in range(n, 1, -1):
+                setattr(self, f"act{k}_t", nn.PReLU(ch[k - 1]))
+        elif act != "relu":
+            raise ValueError(f"act must be 'relu' or 'prelu', got {act!r}")
+
+    # ------------------------------------------------------------------------------------
+    def _alpha(self, name):
+        return getattr(self, name).weight if self.act_kind == "prelu" else None
+
+    def _stage(self, h, conv, bn, alpha, kt_fs, train, hist=None):
+        """conv + BN + act.  eval: one fused kernel; train: conv(+stat partials) -> finalize -> bn_act."""
+        kt, fs = kt_fs
+        if not train:
+            scale, shift = ops.bn_fold(bn)
+            return ops.conv_fwd(h, conv.weight, conv.bias, scale, shift, alpha, self.act_kind, kt, fs, hist=hist)
+        z, stats = ops.conv_fwd(h, conv.weight, conv.bias, None, None, None, "none", kt, fs, want_stats=True)
+        B, T, Cn, F = z.shape
+        scale, shift, _, _ = ops.bn_finalize(stats, B * T * F, bn)
+        return ops.bn_act_fwd(z, scale, shift, alpha, self.act_kind)
+
+    def forward_frames(self, mag, state=None, want_state=False):
+        """mag [B,T,F] frame-major magnitudes -> mask [B,T,F].  (Internal zero-copy entry used by
+        cruse_b200.pipeline; ``forward`` wraps it with the reference's [B,1,T,F] layout.)
+        ``state`` (cruse_b200.streaming.StreamState) carries one frame of history per encoder conv and the
+        GRU hidden states between chunks of a stream; it is updated in place when ``want_state``."""
+        _need_cuda(mag, "unet_2")
+        B, T, F = mag.shape
+        if F != self.in_feat:
+            raise RuntimeError(f"unet_2: input has {F} bins, model was built for in_feat={self.in_feat}")
+        n = self.laynum
+        train = self.training
+        h = mag.view(B, T, 1, F)
+        enc, skips = [], []
+        hists = state.hist if state is not None and state.hist else [None] * n
+        new_hist = []
+        for k in range(1, n + 1):                                                                   # :149-152 repaired
+            if want_state:
+                new_hist.append(h[:, -1].contiguous())
+            h = self._stage(h, getattr(self, f"conv{k}"), getattr(self, f"bn{k}"), self._alpha(f"act{k}"), (2, 2), train,
+                            hist=hists[k - 1])
+            enc.append(h)
+            skips.append(ops.conv_fwd(h, getattr(self, f"skip_connect_{k}").weight, None, None, None, None,
+                                      "none", 1, 1))                                                 # :153-156
+        e4 = enc[-1]
+        D = e4.shape[2] * e4.shape[3]
+        g = self.gru.forward_frames(e4.view(B, T, D), residual=skips[-1].view(B, T, D),
+                                    state=state.gru if state is not None else None, want_state=want_state)  # :158-160
+        if want_state:
+            g, gru_state = g
+            state.hist, state.gru = new_hist, gru_state
+        out = g.view(B, T, e4.shape[2], e4.shape[3])
+        for k in range(n, 1, -1):                                                                   # :161-163 repaired
+            conv, bn = getattr(self, f"conv{k}_t"), getattr(self, f"bn{k}_t")
+            alpha = self._alpha(f"act{k}_t")
+            if not train:
+                scale, shift = ops.bn_fold(bn)
+                out = ops.convT_fwd(out, conv.weight, conv.bias, scale, shift, alpha, self.act_kind,
+                                    skips[k - 2], self.freqs[k - 1])
+            else:
+                z, stats = ops.convT_fwd(out, conv.weight, conv.bias, None, None, None, "none", None,
+                                         self.freqs[k - 1], want_stats=True)
+                scale, shift, _, _ = ops.bn_finalize(stats, B * T * self.freqs[k - 1], bn)
+                out = ops.bn_act_fwd(z, scale, shift, alpha, self.act_kind, skip=skips[k - 2])
+        mask = ops.convT_fwd(out, self.conv1_t.weight, self.conv1_t.bias, None, None, None, "sigmoid", None,
+                             self.freqs[0])                                                          # :164
+        mask = mask.view(B, T, F)
+        return mask
+
+    def forward(self, x):
+        """x [B,1,T,F] float32 CUDA -> mask [B,1,T,F] (model/cruse_net.py:147-165)."""
+        _need_cuda(x, "unet_2")
+        if x.dim() != 4 or x.shape[1] != self.ch[0] or self.ch[0] != 1:
+            raise RuntimeError(f"unet_2: expected input [B,1,T,F], got {tuple(x.shape)}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd import unet2_autograd_forward  # backward kernels
+            return unet2_autograd_forward(self, x)
+        B, _, T, F = x.shape
+        return self.forward_frames(x.contiguous().view(B, T, F)).view(B, 1, T, F)

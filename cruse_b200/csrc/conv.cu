@@ -28,7 +28,8 @@ constexpr int CONV_THREADS = 256;
 // ---------------------------------------------------------------------------------------------
 template <int KT, int SF>
 __global__ void __launch_bounds__(CONV_THREADS)
-conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, const float* __restrict__ w,
+                const float* __restrict__ bias,
                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha,
                 int act, float* __restrict__ out, float* __restrict__ stats_ws, int T, int Cin, int Fin, int Cout,
                 int Fout) {
@@ -57,9 +58,13 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const
     const float* inb = in + (size_t)b * T * rowlen;
     for (int r = 0; r < NR; ++r) {
         const int t = t0 - (KT - 1) + r;
-        const bool valid = (t >= 0 && t < T);
+        bool valid = (t >= 0 && t < T);
         float* dst = s_in + (size_t)r * Cin * FinP;
         const float* src = inb + (size_t)t * rowlen;
+        if (KT == 2 && t == -1 && hist) {  // streaming: frame -1 is the last input frame of the previous chunk
+            valid = true;
+            src = hist + (size_t)b * rowlen;
+        }
         if ((Fin & 3) == 0) {
             for (int i = tid * 4; i < rowlen; i += blockDim.x * 4) {
                 float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -317,6 +322,17 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats_ws, int npart
     }
 }
 
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float inv = 1.0f / sqrtf(var[c] + eps);
+    const float g = gamma ? gamma[c] : 1.f;
+    scale[c] = g * inv;
+    shift[c] = (beta ? beta[c] : 0.f) - mean[c] * g * inv;
+}
+
 __global__ void bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ alpha, int act,
                                   const float* __restrict__ skip, float* __restrict__ y, long long total, int C, int F) {
@@ -358,7 +374,7 @@ using namespace cruse;
 
 extern "C" int cruse_conv_nparts(int B, int T) { return B * ((T + CONV_TT - 1) / CONV_TT); }
 
-extern "C" int cruse_conv_fwd(const float* in, const float* w, const float* bias, const float* scale,
+extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w, const float* bias, const float* scale,
                               const float* shift, const float* alpha, int act, float* out, float* stats_ws, int B,
                               int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream) {
     CRUSE_CHECK_ARG(in && w && out, "conv_fwd: null pointer");
@@ -374,10 +390,10 @@ extern "C" int cruse_conv_fwd(const float* in, const float* w, const float* bias
     cudaStream_t st = (cudaStream_t)stream;
     if (kt == 2) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_kernel<2, 2><<<grid, CONV_THREADS, smem, st>>>(in, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
+        conv_fwd_kernel<2, 2><<<grid, CONV_THREADS, smem, st>>>(in, hist, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
     } else {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(in, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
+        conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(in, nullptr, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
     }
     CRUSE_LAUNCH_OK();
     return 0;
@@ -411,6 +427,15 @@ extern "C" int cruse_bn_finalize(const float* stats_ws, int nparts, int C, doubl
     CRUSE_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats go together");
     bn_finalize_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(stats_ws, nparts, C, count, gamma, beta, eps, momentum, running_mean,
                                                             running_var, scale, shift, save_mean, save_invstd);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                             const float* running_var, float eps, float* scale, float* shift, int C, void* stream) {
+    CRUSE_CHECK_ARG(running_mean && running_var && scale && shift, "bn_fold: null pointer");
+    CRUSE_CHECK_ARG(C > 0, "bn_fold: bad C");
+    bn_fold_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -264,7 +264,7 @@ static int launch_gru_seq(const float* xproj, const GroupPtrs& w_hh, const Group
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float eps, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     float eps, const float* __restrict__ res, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      long long rows, int D) {
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const bool vec = (D & 3) == 0;
@@ -303,11 +303,16 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                 o.y = (v.y - mean) * rstd * gm.y + bt.y;
                 o.z = (v.z - mean) * rstd * gm.z + bt.z;
                 o.w = (v.w - mean) * rstd * gm.w + bt.w;
+                if (res) {
+                    const float4 rv = __ldg(reinterpret_cast<const float4*>(res + row * D + i));
+                    o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                }
                 *reinterpret_cast<float4*>(yr + i) = o;
             }
         } else {
             for (int i = lane; i < D; i += 32)
-                yr[i] = (__ldg(xr + i) - mean) * rstd * (gamma ? __ldg(gamma + i) : 1.f) + (beta ? __ldg(beta + i) : 0.f);
+                yr[i] = (__ldg(xr + i) - mean) * rstd * (gamma ? __ldg(gamma + i) : 1.f) + (beta ? __ldg(beta + i) : 0.f) +
+                        (res ? __ldg(res + row * D + i) : 0.f);
         }
         if (lane == 0) {
             if (mean_out) mean_out[row] = mean;
@@ -371,14 +376,15 @@ extern "C" int cruse_gru_seq_fwd(const float* xproj, const float* const* w_hh, c
     }
 }
 
-extern "C" int cruse_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y,
-                                   float* mean, float* rstd, long long rows, int D, void* stream) {
+extern "C" int cruse_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps,
+                                   const float* residual, float* y, float* mean, float* rstd, long long rows, int D,
+                                   void* stream) {
     CRUSE_CHECK_ARG(x && y, "layernorm_fwd: null pointer");
     CRUSE_CHECK_ARG(rows > 0 && D > 0, "layernorm_fwd: bad sizes");
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, mean, rstd, rows, D);
+    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, residual, y, mean, rstd, rows, D);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -1,0 +1,75 @@
+"""Loss surface of the reference on the fused sm_100a kernel.
+
+``loss_func(mode).loss(inputs, labels, noisy)`` mirrors loss_func/loss.py:16-34 and
+``wo_male(ref, est, unproc)`` mirrors :121-148 (tensors ``[B,2,T,F]``, channel 0 = real,
+1 = imag).  ``wo_male`` is differentiable w.r.t. ``est``: forward value and gradient come
+out of the same streaming pass.  Factory ``wo_male_loss()`` follows the name -> callable
+convention of train_base/loss.py that tools/train_stand.py:73-75 uses.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class _WoMale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, est, unproc, layout):
+        lay = ops.layout_bctf if layout == "bctf" else ops.layout_btf2
+        if layout == "bctf":
+            B, _, T, F = est.shape
+        else:
+            B, T, F, _ = est.shape
+        need = est.requires_grad
+        ref_c, est_c, unp_c = ref.contiguous(), est.contiguous(), unproc.contiguous()
+        loss, dest = ops.wo_male_fwd_bwd(ref_c, lay(ref_c), est_c, lay(est_c), unp_c, lay(unp_c), B, T, F,
+                                         want_grad=need)
+        ctx.save_for_backward(dest)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dest,) = ctx.saved_tensors
+        return None, (dest * g if dest is not None else None), None, None
+
+
+def wo_male(ref, est, unproc, norm=False, eps=1e-8):
+    """loss_func/loss.py:121-148 (repairs: App. A.4).  ref/est/unproc [B,2,T,F] -> 0-dim loss."""
+    if ref.shape != est.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate wo-male, {ref.shape} vs {est.shape}")   # :122-125
+    if unproc.shape != ref.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate wo-male, {ref.shape} vs {unproc.shape}")
+    return _WoMale.apply(ref, est, unproc, "bctf")
+
+
+def wo_male_frames(ref, est, unproc, F):
+    """same loss on internal interleaved spectra [B,T,NF,2], restricted to bins [0,F) -- zero-copy."""
+    B, T, NF, _ = est.shape
+    loss, _ = ops.wo_male_fwd_bwd(ref, ops.layout_btf2(ref), est, ops.layout_btf2(est), unproc,
+                                  ops.layout_btf2(unproc), B, T, F, want_grad=False)
+    return loss
+
+
+def wo_male_loss():
+    """factory in the style of train_base/loss.py:7-25: returns loss(est, ref, noisy)."""
+    def loss(est, ref, noisy):
+        return wo_male(ref, est, noisy)
+    return loss
+
+
+class loss_func:
+    """loss_func/loss.py:16-34 dispatcher; only the hot-path mode is built (others: SURVEY 8f2)."""
+
+    MODES = ['SI-SNR', 'SS-SNR', 'MSE', 'Normal_MSE', 'CN_MSE', 'D_MSE', 'WO_MALE', 'C_MSE']
+
+    def __init__(self, loss_mode):
+        assert loss_mode in self.MODES, "Loss mode must be one of ***"      # :19-21
+        self.loss_mode = loss_mode
+
+    def loss(self, inputs, labels, noisy=None):
+        if self.loss_mode == 'WO_MALE':
+            return wo_male(labels, inputs, noisy)                            # :29-30 (arg order)
+        if self.loss_mode == 'SS-SNR':
+            return 0                                                         # :27-28
+        raise NotImplementedError(f"loss mode {self.loss_mode!r} is outside the built hot path (SURVEY.md 8f2)")

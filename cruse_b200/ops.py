@@ -1,0 +1,318 @@
+"""Thin tensor-level wrappers over the C ABI (include/cruse_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function
+checks its tensors, allocates outputs with the caching allocator, and launches the sm_100a
+kernels on ``torch.cuda.current_stream()``.  Activations are frame-major ``[B, T, C, F]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import CplxLayout, check, lib
+
+ACT = {"none": 0, "relu": 1, "prelu": 2, "sigmoid": 3}
+PAD = {"reflect": 0, "constant": 1}
+
+
+# kernels launched per C-ABI call (everything else launches exactly one)
+LAUNCHES = {"cruse_wo_male_fwd_bwd": 2}
+
+
+class Profile:
+    """Optional per-call instrumentation used by bench.py: counts kernel launches and, when
+    ``timing`` is on, brackets every C-ABI call with CUDA events on the launching stream."""
+
+    def __init__(self, timing=False):
+        self.timing = timing
+        self.launches = 0
+        self.events = []      # (name, tag, algorithmic bytes, flops, start_event, end_event)
+
+    def rows(self):
+        """[(name, tag, bytes, flops, ms)] in launch order."""
+        torch.cuda.synchronize()
+        return [(n, tag, by, fl, a.elapsed_time(b)) for n, tag, by, fl, a, b in self.events]
+
+
+_profile = None
+
+
+def set_profile(p):
+    global _profile
+    _profile = p
+
+
+def _call(name, *args, meta=None):
+    """meta = (tag, algorithmic_bytes, flops) of this launch -- the roofline numerators."""
+    fn = getattr(lib(), name)
+    prof = _profile
+    if prof is None:
+        check(fn(*args), name)
+        return
+    prof.launches += LAUNCHES.get(name, 1)
+    if prof.timing:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(fn(*args), name)
+        b.record()
+        tag, by, fl = meta if meta is not None else ("", 0, 0)
+        prof.events.append((name, tag, by, fl, a, b))
+    else:
+        check(fn(*args), name)
+
+
+def _nb(*tensors):
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, name, ndim=None):
+    if t is None:
+        return
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{name}: expected a CUDA tensor (cruse_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+
+
+def _ptr_table(tensors):
+    if tensors is None:
+        return None
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+# ------------------------------------------------------------------------------------------
+# a1 / a6 / a7 : spectral front and back end
+# ------------------------------------------------------------------------------------------
+def stft_fwd(wav, window, n_fft, hop, pad_mode="reflect", mag_bins=0, mag_eps=1e-8):
+    """wav [B,L] -> (spec [B,T,NF,2], mag [B,T,mag_bins] | None).  feature.py:10-30 + utils.py:400."""
+    _req(wav, "wav", 2)
+    _req(window, "window", 1)
+    B, L = wav.shape
+    if window.numel() != n_fft:
+        raise RuntimeError(f"stft: window length {window.numel()} != n_fft {n_fft}")
+    T = 1 + L // hop
+    NF = n_fft // 2 + 1
+    spec = torch.empty(B, T, NF, 2, device=wav.device, dtype=torch.float32)
+    mag = torch.empty(B, T, mag_bins, device=wav.device, dtype=torch.float32) if mag_bins > 0 else None
+    _call("cruse_stft_fwd", _p(wav), _p(window), _p(spec), _p(mag), B, L, n_fft, hop, T, PAD[pad_mode],
+                               mag_bins, mag_eps, _stream(),
+          meta=(f"stft n{n_fft} h{hop}", _nb(wav, spec, mag), int(B * T * 2.5 * n_fft * 9)))
+    return spec, mag
+
+
+def mask_istft_fwd(spec, mask, window, n_fft, hop, length, want_est=True, want_wav=True):
+    """spec [B,T,NF,2] (* mask [B,T,Fm]) -> (est_spec | None, wav [B,length] | None).  utils.py:417-454."""
+    _req(spec, "spec", 4)
+    _req(mask, "mask")
+    _req(window, "window", 1)
+    B, T, NF, _ = spec.shape
+    if NF != n_fft // 2 + 1:
+        raise RuntimeError(f"mask_istft: spec has {NF} bins, n_fft={n_fft} needs {n_fft // 2 + 1}")
+    mask_bins = 0
+    if mask is not None:
+        mask_bins = mask.shape[-1]
+        if mask.numel() != B * T * mask_bins:
+            raise RuntimeError(f"mask_istft: mask shape {tuple(mask.shape)} does not match spec {tuple(spec.shape)}")
+    est = torch.empty_like(spec) if want_est else None
+    wav = torch.empty(B, length, device=spec.device, dtype=torch.float32) if want_wav else None
+    _call("cruse_mask_istft_fwd", _p(spec), _p(mask), _p(window), _p(est), _p(wav), B, length if want_wav else 0,
+                                     n_fft, hop, T, mask_bins, _stream(),
+          meta=(f"mask_istft n{n_fft} h{hop}", _nb(spec, mask, est, wav), int(B * T * 2.5 * n_fft * 9) if want_wav else 0))
+    return est, wav
+
+
+def mask_bwd(dest, spec, mask_bins, gscale=None):
+    """dmask[b,t,f] = gscale * Re(conj(X) * dEst), f < mask_bins."""
+    _req(dest, "dest", 4)
+    _req(spec, "spec", 4)
+    B, T, NF, _ = spec.shape
+    dmask = torch.empty(B, T, mask_bins, device=spec.device, dtype=torch.float32)
+    _call("cruse_mask_bwd", _p(dest), _p(spec), _p(gscale), _p(dmask), B, T, NF, mask_bins, _stream())
+    return dmask
+
+
+# ------------------------------------------------------------------------------------------
+# a2 / a3 / a5 : conv stages
+# ------------------------------------------------------------------------------------------
+def conv_nparts(B, T):
+    return lib().cruse_conv_nparts(B, T)
+
+
+def conv_fwd(x, w, bias, scale, shift, alpha, act, kt, fstride, want_stats=False, hist=None):
+    """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout] (+ per-CTA BN partials [nparts, 2*Cout])."""
+    _req(x, "x", 4)
+    _req(w, "w", 4)
+    for n, t in (("bias", bias), ("scale", scale), ("shift", shift), ("alpha", alpha)):
+        _req(t, n)
+    B, T, Cin, Fin = x.shape
+    Cout = w.shape[0]
+    if tuple(w.shape) != (Cout, Cin, kt, 3):
+        raise RuntimeError(f"conv_fwd: weight shape {tuple(w.shape)} != ({Cout},{Cin},{kt},3)")
+    Fout = (Fin + 2 - 3) // fstride + 1
+    out = torch.empty(B, T, Cout, Fout, device=x.device, dtype=torch.float32)
+    stats = torch.empty(conv_nparts(B, T), 2 * Cout, device=x.device, dtype=torch.float32) if want_stats else None
+    _req(hist, "hist")
+    if hist is not None and (kt != 2 or hist.numel() != B * Cin * Fin):
+        raise RuntimeError(f"conv_fwd: hist must be [B,Cin,Fin] and kt == 2, got {tuple(hist.shape)}")
+    _call("cruse_conv_fwd", _p(x), _p(hist), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(out), _p(stats),
+                               B, T, Cin, Fin, Cout, Fout, kt, fstride, _stream(),
+          meta=(f"conv{kt}x3 {Cin}->{Cout} F{Fin}->{Fout}", _nb(x, out, w, bias), 2 * B * T * Cout * Fout * Cin * kt * 3))
+    return (out, stats) if want_stats else out
+
+
+def convT_fwd(x, w, bias, scale, shift, alpha, act, skip, Fout, want_stats=False):
+    """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout];  w [Cin,Cout,1,3] (ConvTranspose2d layout)."""
+    _req(x, "x", 4)
+    _req(w, "w", 4)
+    for n, t in (("bias", bias), ("scale", scale), ("shift", shift), ("alpha", alpha), ("skip", skip)):
+        _req(t, n)
+    B, T, Cin, Fin = x.shape
+    Cout = w.shape[1]
+    if tuple(w.shape) != (Cin, Cout, 1, 3):
+        raise RuntimeError(f"convT_fwd: weight shape {tuple(w.shape)} != ({Cin},{Cout},1,3)")
+    if skip is not None and tuple(skip.shape) != (B, T, Cout, Fout):
+        raise RuntimeError(f"convT_fwd: skip shape {tuple(skip.shape)} != {(B, T, Cout, Fout)}")
+    out = torch.empty(B, T, Cout, Fout, device=x.device, dtype=torch.float32)
+    stats = torch.empty(conv_nparts(B, T), 2 * Cout, device=x.device, dtype=torch.float32) if want_stats else None
+    _call("cruse_convT_fwd", _p(x), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(skip), _p(out),
+                                _p(stats), B, T, Cin, Fin, Cout, Fout, _stream(),
+          meta=(f"convT1x3 {Cin}->{Cout} F{Fin}->{Fout}", _nb(x, out, skip, w, bias), 2 * B * T * Cin * Fin * Cout * 3))
+    return (out, stats) if want_stats else out
+
+
+def bn_fold(bn):
+    """eval-mode BatchNorm2d -> per-channel (scale, shift)."""
+    Cn = bn.num_features
+    scale = torch.empty(Cn, device=bn.running_mean.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    _call("cruse_bn_fold", _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var), float(bn.eps),
+                              _p(scale), _p(shift), Cn, _stream())
+    return scale, shift
+
+
+def bn_finalize(stats, count, bn, update_running=True):
+    """train-mode BatchNorm2d: per-CTA partials -> (scale, shift, save_mean, save_invstd); updates running stats."""
+    _req(stats, "stats", 2)
+    nparts, C2 = stats.shape
+    Cn = C2 // 2
+    dev = stats.device
+    scale = torch.empty(Cn, device=dev, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale)
+    invstd = torch.empty_like(scale)
+    upd = update_running and bn.track_running_stats and bn.running_mean is not None
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    _call("cruse_bn_finalize", _p(stats), nparts, Cn, float(count), _p(bn.weight), _p(bn.bias), float(bn.eps),
+                                  float(mom), _p(bn.running_mean) if upd else None,
+                                  _p(bn.running_var) if upd else None, _p(scale), _p(shift), _p(mean), _p(invstd),
+                                  _stream())
+    if upd and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return scale, shift, mean, invstd
+
+
+def bn_act_fwd(z, scale, shift, alpha, act, skip=None):
+    _req(z, "z", 4)
+    B, T, Cn, F = z.shape
+    y = torch.empty_like(z)
+    _call("cruse_bn_act_fwd", _p(z), _p(scale), _p(shift), _p(alpha), ACT[act], _p(skip), _p(y), B * T, Cn, F,
+          _stream(), meta=(f"bn_act C{Cn} F{F}", _nb(z, y, skip), 2 * z.numel()))
+    return y
+
+
+# ------------------------------------------------------------------------------------------
+# a4 : grouped GRU + LayerNorm
+# ------------------------------------------------------------------------------------------
+def gru_ih_gemm(x, w_ih, b_ih, b_hh):
+    """x [M, G*H] -> xproj [M, G, 3H] = x_g . w_ih[g]^T + b_ih[g] (+ b_hh[g] on the r,z rows)."""
+    _req(x, "x", 2)
+    G = len(w_ih)
+    H = w_ih[0].shape[1]
+    M = x.shape[0]
+    if x.shape[1] != G * H:
+        raise RuntimeError(f"gru_ih_gemm: x has {x.shape[1]} features, expected {G}*{H}")
+    for t in list(w_ih) + list(b_ih or []) + list(b_hh or []):
+        _req(t, "gru weight")
+    xproj = torch.empty(M, G, 3 * H, device=x.device, dtype=torch.float32)
+    tw, tbi, tbh = _ptr_table(w_ih), _ptr_table(b_ih), _ptr_table(b_hh)
+    _call("cruse_gru_ih_gemm", _p(x), tw, tbi, tbh, _p(xproj), M, G, H, _stream(),
+          meta=(f"gru_ih G{G} H{H}", _nb(x, xproj, *w_ih), 2 * M * G * H * 3 * H))
+    return xproj
+
+
+def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False):
+    """recurrence over T; y [B,T,G*H] with y[..., j*G+g] (interleave, cruse_net.py:43-45) or y[..., g*H+j] (cat)."""
+    _req(xproj, "xproj", 3)
+    _req(h0, "h0")
+    G = len(w_hh)
+    H = w_hh[0].shape[1]
+    if tuple(xproj.shape) != (B * T, G, 3 * H):
+        raise RuntimeError(f"gru_seq_fwd: xproj shape {tuple(xproj.shape)} != {(B * T, G, 3 * H)}")
+    y = torch.empty(B, T, G * H, device=xproj.device, dtype=torch.float32)
+    hT = torch.empty(G, B, H, device=xproj.device, dtype=torch.float32) if want_hT else None
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    tw, tb = _ptr_table(w_hh), _ptr_table(b_hh)
+    _call("cruse_gru_seq_fwd", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), B, T, G, H, y_fs, y_gs, _stream(),
+          meta=(f"gru_seq G{G} H{H} T{T}", _nb(xproj, y, *w_hh), 2 * B * T * G * H * 3 * H))
+    return (y, hT) if want_hT else y
+
+
+def layernorm_fwd(x, gamma, beta, eps, residual=None, want_stats=False):
+    _req(x, "x")
+    _req(residual, "residual")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if want_stats else None
+    _call("cruse_layernorm_fwd", _p(x), _p(gamma), _p(beta), float(eps), _p(residual), _p(y), _p(mean), _p(rstd),
+                                    rows, D, _stream(), meta=(f"layernorm D{D}", _nb(x, y, residual), 8 * x.numel()))
+    return (y, mean, rstd) if want_stats else y
+
+
+# ------------------------------------------------------------------------------------------
+# a8 : weighted-magnitude loss
+# ------------------------------------------------------------------------------------------
+def layout_bctf(t):
+    """reference layout [B,2,T,F] (loss.py:129-140)."""
+    B, two, T, F = t.shape
+    return CplxLayout(2 * T * F, F, 1, T * F)
+
+
+def layout_btf2(t):
+    """internal interleaved layout [B,T,NF,2]."""
+    B, T, NF, two = t.shape
+    return CplxLayout(T * NF * 2, NF * 2, 2, 1)
+
+
+def _loss_ws(device):
+    # per-call workspace from the caching allocator: keeps the op re-entrant across streams
+    return torch.empty(lib().cruse_wo_male_ws_bytes() // 4, device=device, dtype=torch.float32)
+
+
+def wo_male_fwd_bwd(ref, lref, est, lest, unp, lunp, B, T, F, want_grad=False):
+    """-> (loss 0-dim tensor, dL/d est in est's layout | None)."""
+    _req(ref, "ref")
+    _req(est, "est")
+    _req(unp, "unproc")
+    loss = torch.empty((), device=est.device, dtype=torch.float32)
+    dest = torch.zeros_like(est) if want_grad else None
+    ws = _loss_ws(est.device)
+    _call("cruse_wo_male_fwd_bwd", _p(ref), lref, _p(est), lest, _p(unp), lunp, _p(dest), _p(loss), _p(ws),
+                                      B, T, F, _stream(),
+          meta=("wo_male", B * T * F * 8 * (4 if want_grad else 3), 30 * B * T * F))
+    return loss, dest

@@ -72,10 +72,12 @@ int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, fl
  *      model/cruse_net.py:138,141,149-152 (kt=2, fstride=2) and the skip convs :143,153-156
  *      (kt=1, fstride=1).  Kernel (kt,3), freq padding 1, time taps look back only.
  *  in [B,T,Cin,Fin]; w [Cout,Cin,kt,3]; bias [Cout]|NULL; out [B,T,Cout,Fout].
+ *  hist [B,Cin,Fin]|NULL: the input frame preceding t=0 (streaming chunks; NULL = zero padding, i.e.
+ *  the start of an utterance; state-carry convention of model/based_model/cust_conv.py:303-325).
  *  epilogue: v = conv+bias; if scale: v = v*scale[c]+shift[c]; v = act(v) (alpha = PReLU slopes).
  *  stats_ws (optional, train-mode BN): per-CTA partial sums of the pre-affine value,
  *  layout [nparts][2*Cout]; nparts = cruse_conv_nparts(B,T). */
-int cruse_conv_fwd(const float* in, const float* w, const float* bias,
+int cruse_conv_fwd(const float* in, const float* hist, const float* w, const float* bias,
                    const float* scale, const float* shift, const float* alpha, int act,
                    float* out, float* stats_ws,
                    int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream);
@@ -95,6 +97,9 @@ int cruse_bn_finalize(const float* stats_ws, int nparts, int C, double count,
                       const float* gamma, const float* beta, float eps, float momentum,
                       float* running_mean, float* running_var,
                       float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+/* eval-mode BatchNorm2d folded to an affine: scale = gamma/sqrt(var+eps), shift = beta - mean*scale */
+int cruse_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                  float eps, float* scale, float* shift, int C, void* stream);
 /* y = act(z*scale[c]+shift[c]) (+ skip); z,y [B,T,C,F] */
 int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
                      const float* skip, float* y, long long n_frames, int C, int F, void* stream);
@@ -112,9 +117,11 @@ int cruse_gru_seq_fwd(const float* xproj, const float* const* w_hh, const float*
                       const float* h0, float* y, float* hT,
                       int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
 
-/* ---- nn.LayerNorm(D) at model/cruse_net.py:32-33,46,51.  x,y [rows, D]; mean/rstd [rows] or NULL. */
+/* ---- nn.LayerNorm(D) at model/cruse_net.py:32-33,46,51.  x,y [rows, D]; mean/rstd [rows] or NULL.
+ *      residual [rows, D] or NULL is added after the affine (fuses `+ skip4`, cruse_net.py:160). */
 int cruse_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps,
-                        float* y, float* mean, float* rstd, long long rows, int D, void* stream);
+                        const float* residual, float* y, float* mean, float* rstd,
+                        long long rows, int D, void* stream);
 
 /* ---- a8: weighted-magnitude loss wo_male, loss_func/loss.py:121-148, forward + d/d(est).
  *  Complex tensors are addressed as  re = p[b*sb + t*st + f*sf], im = p[... + im_off]  so both the

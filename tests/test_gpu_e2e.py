@@ -1,0 +1,142 @@
+"""GPU: the whole hot path (STFT -> U-Net -> mask -> iSTFT -> wo_male) against the oracle and the committed
+golden vectors; size-independent properties at BASELINE sizes; streaming == batched."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _pair(F, act, cuda, eval_stats=True):
+    from cruse_b200.cruse_net import unet_2
+    from oracle import cruse_oracle as o
+    ref = o.make_model(F, act=act, eval_stats=eval_stats)
+    ours = unet_2(in_feat=F, act=act)
+    ours.load_state_dict(ref.state_dict())
+    return ours.to(cuda), ref
+
+
+@pytest.mark.parametrize("tag", ["B", "R"])
+@pytest.mark.parametrize("act", ["relu", "prelu"])
+def test_golden_end_to_end(cuda, golden_dir, tag, act):
+    from cruse_b200 import pipeline
+    g = np.load(os.path.join(golden_dir, f"oracle_fwd_{tag}_{act}.npz"))
+    F, n_fft, hop = int(g["F"]), int(g["n_fft"]), int(g["hop"])
+    ours, _ = _pair(F, act, cuda)
+    ours.eval()
+    with torch.no_grad():
+        loss, wav, est, mask = pipeline.forward_loss(ours, torch.from_numpy(g["noisy"]).to(cuda),
+                                                     torch.from_numpy(g["clean"]).to(cuda), n_fft, hop)
+    B, _, T, NF = g["est"].shape
+    assert rel_err(mask, torch.from_numpy(g["mask"]).view(B, T, F)) <= 1e-4
+    est_ref = torch.from_numpy(g["est"]).permute(0, 2, 3, 1)                   # [B,2,T,NF] -> [B,T,NF,2]
+    assert rel_err(est, est_ref) <= 1e-4
+    assert float(((est.cpu() - est_ref) ** 2).mean()) < 1e-4                    # BASELINE: enhanced-spectrum MSE
+    assert rel_err(wav, torch.from_numpy(g["wav"])) <= 1e-4
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+@pytest.mark.parametrize("F,n_fft,hop,B,L", [(256, 512, 320, 2, 16000), (161, 320, 160, 3, 8000)])
+def test_forward_matches_oracle_eval_and_module_surface(cuda, F, n_fft, hop, B, L):
+    from cruse_b200 import pipeline
+    from oracle import cruse_oracle as o
+    ours, ref = _pair(F, "relu", cuda)
+    ours.eval(); ref.eval()
+    noisy, clean = o.synth_batch(B, L)
+    with torch.no_grad():
+        l0, w0, e0, m0 = o.forward_loss(ref, noisy, clean, n_fft, hop)
+        l1, w1, e1, m1 = pipeline.forward_loss(ours, noisy.to(cuda), clean.to(cuda), n_fft, hop)
+        # the nn.Module surface of the reference: [B,1,T,F] in, [B,1,T,F] out
+        X = o.spec_to_bctf(o.stft(noisy, n_fft, hop, n_fft))
+        mag = torch.sqrt(X[:, 0:1] ** 2 + X[:, 1:2] ** 2 + 1e-8)[..., :F]
+        m2 = ours(mag.to(cuda))
+    assert m2.shape == m0.shape and rel_err(m2, m0) <= 1e-4
+    T = m0.shape[2]
+    assert rel_err(m1, m0.view(B, T, F)) <= 1e-4
+    assert rel_err(e1, e0.permute(0, 2, 3, 1)) <= 1e-4
+    assert rel_err(w1, w0) <= 1e-4
+    assert abs(float(l1) - float(l0)) <= 2e-5 * abs(float(l0))
+
+
+def test_forward_train_mode_batchnorm(cuda):
+    """train-mode forward uses batch statistics and updates running stats like nn.BatchNorm2d."""
+    from oracle import cruse_oracle as o
+    ours, ref = _pair(256, "prelu", cuda, eval_stats=False)
+    ours.train(); ref.train()
+    torch.manual_seed(11)
+    x = torch.rand(3, 1, 21, 256)
+    with torch.no_grad():
+        want = ref(x)
+        got = ours(x.to(cuda))
+    assert rel_err(got, want) <= 2e-4
+    for k in ("bn1", "bn4", "bn3_t"):
+        assert rel_err(getattr(ours, k).running_mean, getattr(ref, k).running_mean) <= 1e-4
+        assert rel_err(getattr(ours, k).running_var, getattr(ref, k).running_var) <= 1e-4
+
+
+def test_streaming_matches_batched(cuda):
+    """causal model: feeding frames in chunks with carried GRU state and one frame of conv history
+    reproduces the batched forward."""
+    ours, _ = _pair(256, "relu", cuda)
+    ours.eval()
+    torch.manual_seed(12)
+    B, T, F = 4, 24, 256
+    mag = torch.rand(B, T, F, device=cuda)
+    with torch.no_grad():
+        full = ours.forward_frames(mag)
+        from cruse_b200 import streaming
+        st, outs = streaming.StreamState(), []
+        for t0 in range(0, T, 6):
+            outs.append(streaming.step(ours, mag[:, t0:t0 + 6].contiguous(), st))
+    assert rel_err(torch.cat(outs, dim=1), full) <= 1e-5
+
+
+def test_properties_at_baseline_sizes(cuda):
+    """BASELINE cfg-2 size (32 x 10 s): checks that need no CPU oracle run."""
+    from cruse_b200 import acoustics, ops, pipeline
+    from cruse_b200.cruse_net import unet_2
+    torch.manual_seed(13)
+    B, L, n_fft, hop, F = 32, 160000, 512, 320, 256
+    y = 0.05 * torch.randn(B, L, device=cuda)
+    spec, mag = acoustics.stft_frames(y, n_fft, hop, n_fft, mag_bins=F)
+    T = 1 + L // hop
+    assert spec.shape == (B, T, 257, 2)
+    # round trip with unit mask
+    ones = torch.ones(B, T, F, device=cuda)
+    est, wav = ops.mask_istft_fwd(spec, ones, acoustics.hann_window(n_fft, n_fft, cuda), n_fft, hop, L)
+    assert torch.equal(est, spec)
+    assert rel_err(wav, y) <= 5e-6
+    # linearity of the STFT
+    y2 = 0.05 * torch.randn(B, L, device=cuda)
+    s2, _ = acoustics.stft_frames(y2, n_fft, hop, n_fft)
+    s3, _ = acoustics.stft_frames(y + 2 * y2, n_fft, hop, n_fft)
+    assert rel_err(s3, spec + 2 * s2) <= 1e-5
+    # Parseval on an interior frame
+    fr = (y[0, 10 * hop - 256: 10 * hop + 256] * torch.hann_window(512, device=cuda)).double()
+    e_t = float((fr ** 2).sum())
+    sp = spec[0, 10].double()
+    p = (sp ** 2).sum(-1)
+    e_f = float((p[0] + p[256] + 2 * p[1:256].sum()) / 512)
+    assert abs(e_t - e_f) <= 1e-5 * e_t
+    # full-size forward: mask in (0,1), finite, batch-permutation equivariant
+    m = unet_2(in_feat=F).to(cuda).eval()
+    with torch.no_grad():
+        loss, wav, est, mask = pipeline.forward_loss(m, y, y2, n_fft, hop)
+        perm = torch.randperm(B, device=cuda)
+        _, _, _, mask_p = pipeline.forward_loss(m, y[perm].contiguous(), y2[perm].contiguous(), n_fft, hop)
+    assert torch.isfinite(mask).all() and float(mask.min()) > 0 and float(mask.max()) < 1
+    assert torch.isfinite(loss) and torch.isfinite(wav).all()
+    assert torch.equal(mask_p, mask[perm])
+    # causality: changing the last second of audio leaves earlier mask frames untouched
+    y3 = y.clone(); y3[:, -16000:] = 0
+    with torch.no_grad():
+        _, _, _, mask3 = pipeline.forward_loss(m, y3, y2, n_fft, hop)
+    t_safe = (L - 16000 - 256) // hop - 1
+    assert torch.equal(mask3[:, :t_safe], mask[:, :t_safe])

@@ -1,0 +1,284 @@
+"""GPU: per-kernel parity of libcruse_sm100.so (through the C ABI wrappers) against stock torch CPU ops
+and the oracle, on the same seeded inputs.  Tolerances (fp32 kernels): max|d| / max|ref| <= 1e-5
+unless stated (SURVEY.md section 8d parity gates)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ STFT / iSTFT
+@pytest.mark.parametrize("n_fft,hop,L,B", [(512, 320, 16000, 3), (320, 160, 8000, 2), (512, 320, 3333, 1),
+                                           (512, 128, 4096, 2), (96, 24, 1000, 2)])
+@pytest.mark.parametrize("pad_mode", ["reflect", "constant"])
+def test_stft_matches_torch(cuda, n_fft, hop, L, B, pad_mode):
+    from cruse_b200 import acoustics
+    torch.manual_seed(0)
+    y = torch.randn(B, L)
+    ref = torch.stft(y, n_fft, hop, n_fft, window=torch.hann_window(n_fft), return_complex=True, center=True,
+                     pad_mode=pad_mode)                                    # feature.py:22-30
+    got = acoustics.stft(y.to(cuda), n_fft, hop, n_fft, pad_mode=pad_mode)
+    assert got.shape == ref.shape and got.dtype == torch.complex64
+    assert rel_err(torch.view_as_real(got), torch.view_as_real(ref)) <= 2e-6
+    spec, mag = acoustics.stft_frames(y.to(cuda), n_fft, hop, n_fft, pad_mode, mag_bins=n_fft // 2, mag_eps=1e-8)
+    r = torch.view_as_real(ref).permute(0, 2, 1, 3)
+    refmag = torch.sqrt(r[..., 0] ** 2 + r[..., 1] ** 2 + 1e-8)[..., : n_fft // 2]   # utils.py:400
+    assert rel_err(mag, refmag) <= 2e-6
+
+
+@pytest.mark.parametrize("n_fft,hop,L,B", [(512, 320, 16000, 2), (320, 160, 8000, 2), (512, 320, 3333, 1),
+                                           (512, 128, 4096, 2), (512, 320, 64000, 2)])
+def test_istft_matches_torch_and_round_trips(cuda, n_fft, hop, L, B):
+    from cruse_b200 import acoustics
+    torch.manual_seed(1)
+    y = torch.randn(B, L)
+    c = torch.stft(y, n_fft, hop, n_fft, window=torch.hann_window(n_fft), return_complex=True, center=True)
+    c = c * (0.5 + torch.rand(c.shape))       # a non-consistent spectrum: tests the OLA itself, not just inversion
+    ref = torch.istft(c, n_fft, hop, n_fft, window=torch.hann_window(n_fft), center=True, length=L)  # feature.py:53-61
+    got = acoustics.istft(c.to(cuda), n_fft, hop, n_fft, length=L)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= 5e-6
+    # property: istft(stft(y)) == y on our own kernels
+    back = acoustics.istft(acoustics.stft(y.to(cuda), n_fft, hop, n_fft), n_fft, hop, n_fft, length=L)
+    assert rel_err(back, y) <= 5e-6
+
+
+def test_preprocess_surface(cuda):
+    from cruse_b200.acoustics import PreProcess
+    from oracle import cruse_oracle as o
+    torch.manual_seed(2)
+    y = torch.randn(2, 8000)
+    ours, ref = PreProcess(512, 320, 512), o.PreProcess(512, 320, 512)
+    a, b = ours.pre_stft(y.to(cuda)), ref.pre_stft(y)
+    for u, v in zip(a, b):
+        assert u.shape == v.shape
+    for i in range(4):
+        assert rel_err(a[i], b[i]) <= 3e-6
+    mask = torch.rand(2, 1, a[0].shape[2], 257)
+    e1, e2 = ours.masking(mask.to(cuda)), ref.masking(mask)
+    assert e1.shape == e2.shape and rel_err(e1, e2) <= 3e-6
+    w1, w2 = ours.reconstruction(e1, 8000), ref.reconstruction(e2, 8000)
+    assert rel_err(w1, w2) <= 5e-6
+
+
+# ------------------------------------------------------------------ conv stages
+def _to_frames(x):      # [B,C,T,F] -> [B,T,C,F]
+    return x.permute(0, 2, 1, 3).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,F", [(1, 8, 256), (8, 16, 128), (16, 32, 64), (32, 64, 32), (1, 8, 161), (8, 16, 81),
+                                        (32, 64, 21), (3, 5, 37)])
+@pytest.mark.parametrize("act", ["relu", "prelu"])
+def test_encoder_stage_eval(cuda, cin, cout, F, act):
+    from cruse_b200 import ops
+    torch.manual_seed(3)
+    B, T = 2, 19
+    conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), (1, 1))
+    bn = nn.BatchNorm2d(cout).eval()
+    bn.running_mean.copy_(0.1 * torch.randn(cout)); bn.running_var.copy_(1 + 0.1 * torch.rand(cout))
+    bn.weight.data.copy_(1 + 0.1 * torch.randn(cout)); bn.bias.data.copy_(0.1 * torch.randn(cout))
+    pre = nn.PReLU(cout); pre.weight.data.copy_(0.1 + 0.3 * torch.rand(cout))
+    x = torch.randn(B, cin, T, F)
+    with torch.no_grad():
+        z = bn(conv(x)[..., :-1, :])                                  # cruse_net.py:149 repaired
+        ref = torch.relu(z) if act == "relu" else pre(z)
+    bn_c = bn.to(cuda)
+    scale, shift = ops.bn_fold(bn_c)
+    got = ops.conv_fwd(_to_frames(x).to(cuda), conv.weight.detach().to(cuda), conv.bias.detach().to(cuda), scale, shift,
+                       pre.weight.detach().to(cuda) if act == "prelu" else None, act, 2, 2)
+    assert rel_err(got, _to_frames(ref)) <= 1e-5
+
+
+@pytest.mark.parametrize("c,F", [(8, 128), (64, 16), (16, 41), (5, 7)])
+def test_skip_conv(cuda, c, F):
+    from cruse_b200 import ops
+    torch.manual_seed(4)
+    conv = nn.Conv2d(c, c, (1, 3), bias=False, padding=(0, 1))          # cruse_net.py:143 repaired
+    x = torch.randn(2, c, 11, F)
+    with torch.no_grad():
+        ref = conv(x)
+    got = ops.conv_fwd(_to_frames(x).to(cuda), conv.weight.detach().to(cuda), None, None, None, None, "none", 1, 1)
+    assert rel_err(got, _to_frames(ref)) <= 1e-5
+
+
+def test_encoder_stage_train_bn_matches_torch_and_reference_fragment(cuda, golden_dir):
+    from cruse_b200 import ops
+    for name, cin, cout in (("a", 1, 8), ("b", 8, 16)):
+        g = np.load(os.path.join(golden_dir, f"ref_conv2dnormact_train_{name}.npz"))
+        x = torch.from_numpy(g["x"])
+        bn = nn.BatchNorm2d(cout)
+        bn.weight.data.copy_(torch.from_numpy(g["sd.2.weight"])); bn.bias.data.copy_(torch.from_numpy(g["sd.2.bias"]))
+        bn = bn.to(cuda).train()
+        w, b = torch.from_numpy(g["sd.1.weight"]).to(cuda), torch.from_numpy(g["sd.1.bias"]).to(cuda)
+        z, stats = ops.conv_fwd(_to_frames(x).to(cuda), w, b, None, None, None, "none", 2, 2, want_stats=True)
+        B, T, Cn, F = z.shape
+        scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * F, bn)
+        y = ops.bn_act_fwd(z, scale, shift, None, "relu")
+        assert rel_err(y, _to_frames(torch.from_numpy(g["y_train"]))) <= 1e-5      # reference Conv2dNormAct output
+        # running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance)
+        conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), (1, 1)); conv.weight.data.copy_(w.cpu()); conv.bias.data.copy_(b.cpu())
+        bn_ref = nn.BatchNorm2d(cout).train()
+        with torch.no_grad():
+            bn_ref(conv(x)[..., :-1, :])
+        assert rel_err(bn.running_mean, bn_ref.running_mean) <= 1e-5
+        assert rel_err(bn.running_var, bn_ref.running_var) <= 1e-5
+        assert int(bn.num_batches_tracked) == 1
+
+
+def test_reference_conv2dnormact_eval_fixture(cuda, golden_dir):
+    from cruse_b200 import ops
+    g = np.load(os.path.join(golden_dir, "ref_conv2dnormact_eval.npz"))
+    bn = nn.BatchNorm2d(8).eval()
+    bn.weight.data.copy_(torch.from_numpy(g["sd.2.weight"])); bn.bias.data.copy_(torch.from_numpy(g["sd.2.bias"]))
+    bn.running_mean.copy_(torch.from_numpy(g["sd.2.running_mean"])); bn.running_var.copy_(torch.from_numpy(g["sd.2.running_var"]))
+    scale, shift = ops.bn_fold(bn.to(cuda))
+    got = ops.conv_fwd(_to_frames(torch.from_numpy(g["x"])).to(cuda), torch.from_numpy(g["sd.1.weight"]).to(cuda),
+                       torch.from_numpy(g["sd.1.bias"]).to(cuda), scale, shift, None, "relu", 2, 2)
+    assert rel_err(got, _to_frames(torch.from_numpy(g["y"]))) <= 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,Fin,Fout", [(64, 32, 16, 32), (32, 16, 32, 64), (16, 8, 64, 128), (8, 1, 128, 256),
+                                               (64, 32, 11, 21), (8, 1, 81, 161), (5, 3, 9, 19)])
+@pytest.mark.parametrize("last", [False, True])
+def test_decoder_stage_eval(cuda, cin, cout, Fin, Fout, last):
+    from cruse_b200 import ops
+    torch.manual_seed(5)
+    B, T = 2, 13
+    conv = nn.ConvTranspose2d(cin, cout, (1, 3), (1, 2))
+    x = torch.randn(B, cin, T, Fin)
+    with torch.no_grad():
+        z = conv(x)[..., :Fout]                                         # cruse_net.py:161-164
+    xc, wc, bc = _to_frames(x).to(cuda), conv.weight.detach().to(cuda), conv.bias.detach().to(cuda)
+    if last:
+        ref = torch.sigmoid(z)
+        got = ops.convT_fwd(xc, wc, bc, None, None, None, "sigmoid", None, Fout)
+    else:
+        bn = nn.BatchNorm2d(cout).eval()
+        bn.running_mean.copy_(0.1 * torch.randn(cout)); bn.running_var.copy_(1 + 0.1 * torch.rand(cout))
+        skip = torch.randn(B, cout, T, Fout)
+        with torch.no_grad():
+            ref = torch.relu(bn(z)) + skip
+        scale, shift = ops.bn_fold(bn.to(cuda))
+        got = ops.convT_fwd(xc, wc, bc, scale, shift, None, "relu", _to_frames(skip).to(cuda), Fout)
+    assert rel_err(got, _to_frames(ref)) <= 1e-5
+
+
+# ------------------------------------------------------------------ GRU / LayerNorm
+@pytest.mark.parametrize("G,H,B,T", [(4, 256, 3, 9), (4, 176, 9, 5), (2, 32, 17, 4), (4, 256, 8, 33)])
+def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T):
+    from cruse_b200 import ops
+    torch.manual_seed(6)
+    grus = [nn.GRU(H, H, 1, batch_first=True) for _ in range(G)]
+    x = torch.randn(B, T, G * H)
+    h0 = 0.5 * torch.randn(G, B, H)
+    with torch.no_grad():
+        outs = [grus[g](x[..., g * H:(g + 1) * H].contiguous(), h0[g:g + 1].contiguous()) for g in range(G)]
+        y_cat = torch.cat([a for a, _ in outs], dim=-1)                               # cruse_net.py:49-50
+        y_int = torch.flatten(torch.stack([a for a, _ in outs], dim=-1), -2, -1)      # cruse_net.py:43-45
+        hT = torch.cat([b for _, b in outs], dim=0)
+    dev = lambda ts: [t.detach().to(cuda) for t in ts]
+    w_ih, w_hh = dev([g.weight_ih_l0 for g in grus]), dev([g.weight_hh_l0 for g in grus])
+    b_ih, b_hh = dev([g.bias_ih_l0 for g in grus]), dev([g.bias_hh_l0 for g in grus])
+    xproj = ops.gru_ih_gemm(x.view(B * T, G * H).to(cuda), w_ih, b_ih, b_hh)
+    got_cat, got_h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.to(cuda), want_hT=True)
+    got_int = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=True, h0=h0.to(cuda))
+    assert rel_err(got_cat, y_cat) <= 2e-5
+    assert rel_err(got_int, y_int) <= 2e-5
+    assert rel_err(got_h, hT) <= 2e-5
+
+
+def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
+    """reference GroupedGRULayer output (cust_conv.py:303-325) incl. explicit state; and T steps of 1 frame
+    with carried state == one call over T frames."""
+    from cruse_b200 import ops
+    g = np.load(os.path.join(golden_dir, "ref_groupedgru.npz"))
+    G, H = 4, 8
+    x, h0 = torch.from_numpy(g["x"]).to(cuda), torch.from_numpy(g["h0"]).to(cuda)
+    B, T, _ = x.shape
+    P = lambda k: [torch.from_numpy(g[f"sd.layers.{i}.{k}"]).to(cuda) for i in range(G)]
+    w_ih, w_hh, b_ih, b_hh = P("weight_ih_l0"), P("weight_hh_l0"), P("bias_ih_l0"), P("bias_hh_l0")
+    xproj = ops.gru_ih_gemm(x.reshape(B * T, G * H).contiguous(), w_ih, b_ih, b_hh)
+    y, h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.contiguous(), want_hT=True)
+    assert rel_err(y, torch.from_numpy(g["y"])) <= 2e-5
+    assert rel_err(h, torch.from_numpy(g["h"])) <= 2e-5
+    y0 = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False)
+    assert rel_err(y0, torch.from_numpy(g["y_zero"])) <= 2e-5
+    # streaming
+    hs, ys = h0.contiguous(), []
+    for t in range(T):
+        xp = ops.gru_ih_gemm(x[:, t].contiguous(), w_ih, b_ih, b_hh)
+        yt, hs = ops.gru_seq_fwd(xp, w_hh, b_hh, B, 1, interleave=False, h0=hs, want_hT=True)
+        ys.append(yt)
+    assert rel_err(torch.cat(ys, dim=1), y) <= 1e-6
+    assert rel_err(hs, h) <= 1e-6
+
+
+@pytest.mark.parametrize("rows,D", [(37, 1024), (5, 704), (3, 33)])
+def test_layernorm(cuda, rows, D):
+    from cruse_b200 import ops
+    torch.manual_seed(7)
+    ln = nn.LayerNorm(D)
+    ln.weight.data.copy_(1 + 0.1 * torch.randn(D)); ln.bias.data.copy_(0.1 * torch.randn(D))
+    x, res = 3 * torch.randn(rows, D) + 1, torch.randn(rows, D)
+    with torch.no_grad():
+        ref = ln(x)
+    lnc = ln.to(cuda)
+    assert rel_err(ops.layernorm_fwd(x.to(cuda), lnc.weight, lnc.bias, ln.eps), ref) <= 2e-6
+    assert rel_err(ops.layernorm_fwd(x.to(cuda), lnc.weight, lnc.bias, ln.eps, residual=res.to(cuda)), ref + res) <= 2e-6
+
+
+def test_ggru_module_matches_oracle(cuda):
+    from cruse_b200.cruse_net import GGRU
+    from oracle import cruse_oracle as o
+    for hidden, groups, shape in ((1024, 4, (2, 64, 7, 16)), (704, 4, (3, 64, 5, 11))):
+        torch.manual_seed(8)
+        ref = o.GGRU(hidden_size=hidden, groups=groups)
+        ours = GGRU(hidden_size=hidden, groups=groups)
+        ours.load_state_dict(ref.state_dict())
+        x = torch.randn(*shape)
+        with torch.no_grad():
+            want = ref(x)
+            got = ours.to(cuda)(x.to(cuda))
+        assert got.shape == want.shape and rel_err(got, want) <= 3e-5
+
+
+# ------------------------------------------------------------------ loss
+def test_wo_male_value_and_gradient(cuda, golden_dir):
+    from cruse_b200 import loss as L
+    from oracle import cruse_oracle as o
+    torch.manual_seed(9)
+    B, T, F = 3, 17, 256
+    ref, unp = torch.randn(B, 2, T, F), torch.randn(B, 2, T, F)
+    est = torch.randn(B, 2, T, F, requires_grad=True)
+    want = o.wo_male(ref, est, unp)
+    want.backward()
+    est_c = est.detach().to(cuda).requires_grad_(True)
+    got = L.wo_male(ref.to(cuda), est_c, unp.to(cuda))
+    (2.0 * got).backward()
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    assert rel_err(est_c.grad, 2.0 * est.grad) <= 1e-5
+    assert abs(float(L.loss_func("WO_MALE").loss(est_c.detach(), ref.to(cuda), unp.to(cuda))) - float(want)) <= 1e-5 * abs(float(want))
+    g = np.load(os.path.join(golden_dir, "oracle_wo_male_kat.npz"))
+    v = L.wo_male(*(torch.from_numpy(g[k]).to(cuda) for k in ("ref", "est", "unproc")))
+    assert abs(float(v) - float(g["loss"])) <= 1e-6
+    with pytest.raises(RuntimeError, match="Dimension mismatch"):
+        L.wo_male(ref.to(cuda), est_c[:, :, :5], unp.to(cuda))
+
+
+def test_mask_bwd(cuda):
+    from cruse_b200 import ops
+    torch.manual_seed(10)
+    B, T, NF, F = 2, 5, 257, 256
+    X, dE = torch.randn(B, T, NF, 2), torch.randn(B, T, NF, 2)
+    want = (X[..., :F, 0] * dE[..., :F, 0] + X[..., :F, 1] * dE[..., :F, 1])
+    got = ops.mask_bwd(dE.to(cuda), X.to(cuda), F)
+    assert rel_err(got, want) <= 1e-6

@@ -41,6 +41,7 @@ SIGNATURES = {
     "cruse_bn_fold": (c_int, [c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_int, c_fp]),
     "cruse_bn_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_int, c_int, c_fp]),
     "cruse_gru_ih_gemm": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),
+    "cruse_gru_ih_gemm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),
     "cruse_gru_seq_fwd": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),
     "cruse_wo_male_fwd_bwd": (c_int, [c_fp, CplxLayout, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp,

@@ -12,9 +12,11 @@
 //   (double buffered); each step is 768 FFMA/thread against broadcast float4 reads of h, a
 //   3-stage warp-shuffle transpose-reduce over the 8 k-slices that leaves lane `s` holding the
 //   gate pre-activations of utterance s, fp32 gate math, and a DSMEM scatter of the new h slice
-//   to all 8 CTAs followed by one cluster barrier.  x-projections (and biases) come precomputed
-//   from the GEMM and are prefetched one step ahead.
+//   to all 8 CTAs with st.async, whose byte credits complete an mbarrier in each receiving CTA
+//   (double-buffered h, no fence and no cluster barrier inside the time loop).  x-projections
+//   (and biases) come precomputed from the GEMM and are prefetched one step ahead.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -142,8 +144,14 @@ gru_seq_kernel(const float* __restrict__ xproj, GroupPtrs w_hh, GroupPtrs b_hh, 
     }
     const float b_hn = (uvalid && b_hh.p[g]) ? __ldg(b_hh.p[g] + 2 * H + unit) : 0.f;
 
-    // ---- initial state
+    // ---- initial state + the two "h_{t+1} has landed" mbarriers (one per h buffer)
+    __shared__ __align__(8) uint64_t hbar[2];
     for (int i = tid; i < 2 * GRU_BS * HP; i += blockDim.x) (&hbuf[0][0][0])[i] = 0.f;
+    if (tid == 0) {
+        tc::mbar_init(&hbar[0], 1);
+        tc::mbar_init(&hbar[1], 1);
+        tc::fence_barrier_init();
+    }
     __syncthreads();
     if (h0) {
         for (int i = tid; i < GRU_BS * H; i += blockDim.x) {
@@ -153,7 +161,7 @@ gru_seq_kernel(const float* __restrict__ xproj, GroupPtrs w_hh, GroupPtrs b_hh, 
         }
     }
     __syncthreads();
-    cluster.sync();  // all CTAs initialised before any remote write lands
+    cluster.sync();  // every CTA's buffers + barriers are initialised before any remote write lands
 
     const int bg = bslice * GRU_BS + slice;  // after the reduce, lane `slice` owns utterance `slice`
     const bool valid = uvalid && bg < B;
@@ -163,15 +171,29 @@ gru_seq_kernel(const float* __restrict__ xproj, GroupPtrs w_hh, GroupPtrs b_hh, 
     float* yp = y + ((size_t)(valid ? bg : 0) * T) * ((size_t)G * H) + (size_t)(uvalid ? unit : 0) * y_fs + (size_t)g * y_gs;
     const size_t ystep = (size_t)G * H;
 
-    float* rem[GRU_NC];
+    // shared::cluster addresses of "my" h element and of the barriers in each of the 8 CTAs
+    uint32_t rem_h[GRU_NC], rem_bar[GRU_NC];
+    {
+        const uint32_t lh = tc::smem_u32(&hbuf[0][slice][unit]), lb = tc::smem_u32(&hbar[0]);
 #pragma unroll
-    for (int c = 0; c < GRU_NC; ++c) rem[c] = cluster.map_shared_rank(&hbuf[0][slice][unit], c);
+        for (int c = 0; c < GRU_NC; ++c) {
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_h[c]) : "r"(lh), "r"(c));
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_bar[c]) : "r"(lb), "r"(c));
+        }
+    }
+    constexpr uint32_t STEP_BYTES = GRU_NC * (KPT * 8) * 4;  // every thread of every CTA sends one float per step
 
     float xr = 0.f, xz = 0.f, xn = 0.f;
     if (valid && T > 0) { xr = __ldg(xp); xz = __ldg(xp + H); xn = __ldg(xp + 2 * H); }
     float hnew = 0.f;
     int p = 0;
+    uint32_t ph0 = 0, ph1 = 0;
     for (int t = 0; t < T; ++t) {
+        // h_t is in hbuf[p]: locally initialised for t == 0, otherwise delivered by st.async from all 8 CTAs
+        if (t > 0) {
+            if (p) { tc::mbar_wait(&hbar[1], ph1); ph1 ^= 1; } else { tc::mbar_wait(&hbar[0], ph0); ph0 ^= 1; }
+        }
+        if (tid == 0) tc::mbar_expect_tx(&hbar[p ^ 1], STEP_BYTES);  // arm the barrier h_{t+1} will complete
         // prefetch step t+1
         float nxr = 0.f, nxz = 0.f, nxn = 0.f;
         if (valid && t + 1 < T) {
@@ -229,15 +251,20 @@ gru_seq_kernel(const float* __restrict__ xproj, GroupPtrs w_hh, GroupPtrs b_hh, 
         const float z = sigmoidf_(xz + s3[1]);
         const float n = tanhf(xn + r * (s3[2] + b_hn));
         hnew = valid ? ((1.f - z) * n + z * hold) : 0.f;
-        const int poff = (p ^ 1) * (GRU_BS * HP);
+        // scatter h_{t+1}[unit] of utterance `slice` into the other buffer of all 8 CTAs; each store also
+        // credits 4 bytes on the destination CTA's barrier, so no fence / cluster barrier is needed per step
+        const uint32_t poff = (uint32_t)(p ^ 1) * (GRU_BS * HP * 4), boff = (uint32_t)(p ^ 1) * 8;
 #pragma unroll
-        for (int c = 0; c < GRU_NC; ++c) rem[c][poff] = hnew;
+        for (int c = 0; c < GRU_NC; ++c)
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(rem_h[c] + poff),
+                         "r"(__float_as_uint(hnew)), "r"(rem_bar[c] + boff)
+                         : "memory");
         if (valid) yp[(size_t)t * ystep] = hnew;
-        cluster.sync();
         p ^= 1;
         xr = nxr; xz = nxz; xn = nxn;
     }
     if (hT && valid) hT[((size_t)g * B + bg) * H + unit] = (T > 0) ? hnew : hbuf[0][slice][unit];
+    cluster.sync();  // nobody exits while peers may still be writing into its shared memory
 }
 
 template <int KPT>

@@ -1,0 +1,202 @@
+// gru_ih_tc.cu -- the GRU input projections ("the GRU's three dense matmuls", W_ir|W_iz|W_in stacked
+// as weight_ih_l0 [3H, H]) on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the
+// accumulator in TMEM, operands staged by TMA.
+//
+// Replaces the input half of 8x nn.GRU (model/cruse_net.py:23-31,43-50; cuDNN's RNN input GEMM on the
+// reference path):   xproj[m, g, n] = sum_k x[m, g*H + k] * w_ih[g][n, k] + b_ih[g][n] (+ b_hh[g][n], n < 2H)
+//
+// Mapping: one CTA per (n-tile of 256 gate rows, m-tile of 128 frames, group).  A = 128 frames x 32 k
+// and B = 256 weight rows x 32 k fp32 boxes arrive by TMA in the 128-byte-swizzled K-major layout the
+// UMMA shared-memory descriptors address directly (both operands are K-major in HBM already: x rows and
+// PyTorch's [3H, H] weight rows), rounded fp32 -> tf32 by the TMA unit (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32).
+// Warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer (4 x m128 n256 k8 per k-block),
+// warps 2-5 = epilogue (tcgen05.ld 32 lanes x 32 columns, + bias, 128-bit stores).  Two CTAs fit per SM
+// (2 x 96 KB stages, 2 x 256 TMEM columns), so one CTA's epilogue overlaps the other's main loop.
+// Out-of-range frames / k / gate rows are zero-filled by TMA and masked in the epilogue, so any M and
+// any H % 4 == 0 work (config R: H = 176).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cruse {
+
+int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
+                 bool as_tf32) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static thread_local EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p ||
+            q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled entry point not available");
+            return -2;
+        }
+        fn = (EncodeFn)p;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch_bytes & 15)) {
+        set_error("TMA needs a 16-byte aligned base (%p) and row pitch (%llu B)", (const void*)base, (unsigned long long)pitch_bytes);
+        return -1;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch_bytes};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, as_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes);
+        return -2;
+    }
+    return 0;
+}
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32;          // tile; BK fp32 = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int IH_THREADS = 192;
+constexpr int IH_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BN * 4 /*bias*/ + 64 /*barriers*/;
+
+struct IhMaps {
+    CUtensorMap a[CRUSE_MAX_GROUPS];
+    CUtensorMap b[CRUSE_MAX_GROUPS];
+};
+struct IhPtrs {
+    const float* b_ih[CRUSE_MAX_GROUPS];
+    const float* b_hh[CRUSE_MAX_GROUPS];
+};
+
+__global__ void __launch_bounds__(IH_THREADS)
+gru_ih_tc_kernel(const __grid_constant__ IhMaps maps, const IhPtrs ptrs, float* __restrict__ xproj, int M, int G, int H) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles: 1024-byte aligned
+    uint8_t* tiles = smem_raw + (base - tc::smem_u32(smem_raw));
+    float* s_bias = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_bias + BN);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, g = blockIdx.z;
+    const int N = 3 * H;
+    const int nkb = (H + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&maps.a[g]);
+        tc::tma_prefetch_desc(&maps.b[g]);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<BN>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+                tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+                uint8_t* st = tiles + s * STAGE_BYTES;
+                tc::tma_load_2d(st, &maps.a[g], kb * BK, m0, &full[s]);
+                tc::tma_load_2d(st + A_BYTES, &maps.b[g], kb * BK, n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, BM, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                tc::mbar_wait(&full[s], (kb / STAGES) & 1);
+                tc::tc_fence_after();
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {   // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
+                    tc::umma_tf32(tmem_d, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc,
+                                  (kb | k) ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[s]);           // frees the stage when these MMAs have read it
+            }
+            tc::umma_commit(acc_full);                // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int quad = warp & 3;
+        const float* bi = ptrs.b_ih[g];
+        const float* bh = ptrs.b_hh[g];
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+            const int n = n0 + i;
+            float b = 0.f;
+            if (n < N) b = (bi ? __ldg(bi + n) : 0.f) + ((bh && n < 2 * H) ? __ldg(bh + n) : 0.f);
+            s_bias[i] = b;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+        tc::mbar_wait(acc_full, 0);
+        tc::tc_fence_after();
+        const int m = m0 + quad * 32 + lane;
+        float* orow = xproj + ((size_t)m * G + g) * N + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            if (n0 + c >= N) break;                      // warp-uniform
+            float v[32];
+            tc::tmem_ld_32x32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+            tc::tmem_ld_wait();
+            if (m < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n0 + c + j + 3 < N) {
+                        *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[j] + s_bias[c + j], v[j + 1] + s_bias[c + j + 1],
+                                                                               v[j + 2] + s_bias[c + j + 2], v[j + 3] + s_bias[c + j + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n0 + c + j + e < N) orow[c + j + e] = v[j + e] + s_bias[c + j + e];
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<BN>(tmem_d);
+}
+
+}  // namespace
+}  // namespace cruse
+
+using namespace cruse;
+
+extern "C" int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
+                                    const float* const* b_hh, float* xproj, int M, int G, int H, void* stream) {
+    CRUSE_CHECK_ARG(x && xproj && w_ih, "gru_ih_gemm_tc: null pointer");
+    CRUSE_CHECK_ARG(M > 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0,
+                    "gru_ih_gemm_tc: bad sizes M=%d G=%d H=%d (H%%4==0, G<=%d)", M, G, H, CRUSE_MAX_GROUPS);
+    IhMaps maps;
+    IhPtrs ptrs;
+    for (int g = 0; g < CRUSE_MAX_GROUPS; ++g) { ptrs.b_ih[g] = nullptr; ptrs.b_hh[g] = nullptr; }
+    for (int g = 0; g < G; ++g) {
+        CRUSE_CHECK_ARG(w_ih[g], "gru_ih_gemm_tc: null weight pointer for group %d", g);
+        // A: this group's H columns of x (row pitch G*H floats); B: weight_ih_l0 [3H, H]
+        if (int rc = make_tmap_2d(&maps.a[g], x + (size_t)g * H, (uint64_t)M, (uint64_t)H, (uint64_t)G * H * 4, BM, true)) return rc;
+        if (int rc = make_tmap_2d(&maps.b[g], w_ih[g], (uint64_t)3 * H, (uint64_t)H, (uint64_t)H * 4, BN, true)) return rc;
+        ptrs.b_ih[g] = b_ih ? b_ih[g] : nullptr;
+        ptrs.b_hh[g] = b_hh ? b_hh[g] : nullptr;
+    }
+    for (int g = G; g < CRUSE_MAX_GROUPS; ++g) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; }
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(gru_ih_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
+    dim3 grid((3 * H + BN - 1) / BN, (M + BM - 1) / BM, G);
+    gru_ih_tc_kernel<<<grid, IH_THREADS, IH_SMEM, (cudaStream_t)stream>>>(maps, ptrs, xproj, M, G, H);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}

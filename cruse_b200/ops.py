@@ -7,6 +7,7 @@ kernels on ``torch.cuda.current_stream()``.  Activations are frame-major ``[B, T
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -237,8 +238,13 @@ def bn_act_fwd(z, scale, shift, alpha, act, skip=None):
 # ------------------------------------------------------------------------------------------
 # a4 : grouped GRU + LayerNorm
 # ------------------------------------------------------------------------------------------
-def gru_ih_gemm(x, w_ih, b_ih, b_hh):
+# "tf32": tcgen05 tensor cores (default); "fp32": exact-fp32 CUDA-core GEMM (parity debugging)
+GRU_IH_MODE = os.environ.get("CRUSE_GRU_IH", "tf32")
+
+
+def gru_ih_gemm(x, w_ih, b_ih, b_hh, mode=None):
     """x [M, G*H] -> xproj [M, G, 3H] = x_g . w_ih[g]^T + b_ih[g] (+ b_hh[g] on the r,z rows)."""
+    mode = mode or GRU_IH_MODE
     _req(x, "x", 2)
     G = len(w_ih)
     H = w_ih[0].shape[1]
@@ -249,8 +255,10 @@ def gru_ih_gemm(x, w_ih, b_ih, b_hh):
         _req(t, "gru weight")
     xproj = torch.empty(M, G, 3 * H, device=x.device, dtype=torch.float32)
     tw, tbi, tbh = _ptr_table(w_ih), _ptr_table(b_ih), _ptr_table(b_hh)
-    _call("cruse_gru_ih_gemm", _p(x), tw, tbi, tbh, _p(xproj), M, G, H, _stream(),
-          meta=(f"gru_ih G{G} H{H}", _nb(x, xproj, *w_ih), 2 * M * G * H * 3 * H))
+    if mode not in ("tf32", "fp32"):
+        raise RuntimeError(f"gru_ih_gemm: unknown mode {mode!r}")
+    _call("cruse_gru_ih_gemm_tc" if mode == "tf32" else "cruse_gru_ih_gemm", _p(x), tw, tbi, tbh, _p(xproj), M, G, H,
+          _stream(), meta=(f"gru_ih[{mode}] G{G} H{H}", _nb(x, xproj, *w_ih), 2 * M * G * H * 3 * H))
     return xproj
 
 

@@ -109,6 +109,10 @@ int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, con
  *  x [M, G*H] (M = B*T); xproj [M, G, 3H].  w_ih/b_ih/b_hh: HOST arrays of G device pointers. */
 int cruse_gru_ih_gemm(const float* x, const float* const* w_ih, const float* const* b_ih,
                       const float* const* b_hh, float* xproj, int M, int G, int H, void* stream);
+/* same contract on the tensor cores: tcgen05.mma kind::tf32 (fp32 operands rounded to tf32 by the TMA
+ * unit, fp32 accumulation in TMEM).  Needs 16-byte aligned x / w_ih rows (H % 4 == 0). */
+int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
+                         const float* const* b_hh, float* xproj, int M, int G, int H, void* stream);
 /* recurrence over T with W_hh resident on chip (thread-block cluster per (group, 8-utterance slice)).
  *  y[b,t, j*y_fs + g*y_gs] = h_t[g][b][j]   (layer 1: y_fs=G,y_gs=1 = the stack/flatten interleave of
  *  cruse_net.py:43-45; layer 2: y_fs=1,y_gs=H = cat, :49-50).  h0/hT [G,B,H] or NULL (state carry,

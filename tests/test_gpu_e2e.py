@@ -8,6 +8,28 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# Stated tolerances (max|d| / max|ref|).  "fp32": every kernel accumulates and multiplies in fp32.
+# "tf32" (default product mode): the GRU input projections run on tcgen05 kind::tf32 (operands rounded
+# to 10-bit mantissa by the TMA unit, fp32 accumulate) -> 1e-3 gate of SURVEY.md section 8d; the
+# BASELINE gate "enhanced-spectrum MSE < 1e-4" holds in both.
+TOL = {"fp32": 1e-4, "tf32": 1e-3}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _log(msg):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_errors.log"), "a") as f:
+        f.write(msg + "\n")
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def ih_mode(request):
+    from cruse_b200 import ops
+    old = ops.GRU_IH_MODE
+    ops.GRU_IH_MODE = request.param
+    yield request.param
+    ops.GRU_IH_MODE = old
+
 
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
@@ -25,7 +47,7 @@ def _pair(F, act, cuda, eval_stats=True):
 
 @pytest.mark.parametrize("tag", ["B", "R"])
 @pytest.mark.parametrize("act", ["relu", "prelu"])
-def test_golden_end_to_end(cuda, golden_dir, tag, act):
+def test_golden_end_to_end(cuda, golden_dir, tag, act, ih_mode):
     from cruse_b200 import pipeline
     g = np.load(os.path.join(golden_dir, f"oracle_fwd_{tag}_{act}.npz"))
     F, n_fft, hop = int(g["F"]), int(g["n_fft"]), int(g["hop"])
@@ -35,16 +57,18 @@ def test_golden_end_to_end(cuda, golden_dir, tag, act):
         loss, wav, est, mask = pipeline.forward_loss(ours, torch.from_numpy(g["noisy"]).to(cuda),
                                                      torch.from_numpy(g["clean"]).to(cuda), n_fft, hop)
     B, _, T, NF = g["est"].shape
-    assert rel_err(mask, torch.from_numpy(g["mask"]).view(B, T, F)) <= 1e-4
+    tol = TOL[ih_mode]
     est_ref = torch.from_numpy(g["est"]).permute(0, 2, 3, 1)                   # [B,2,T,NF] -> [B,T,NF,2]
-    assert rel_err(est, est_ref) <= 1e-4
-    assert float(((est.cpu() - est_ref) ** 2).mean()) < 1e-4                    # BASELINE: enhanced-spectrum MSE
-    assert rel_err(wav, torch.from_numpy(g["wav"])) <= 1e-4
-    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    errs = (rel_err(mask, torch.from_numpy(g["mask"]).view(B, T, F)), rel_err(est, est_ref),
+            rel_err(wav, torch.from_numpy(g["wav"])), abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])),
+            float(((est.cpu() - est_ref) ** 2).mean()))
+    _log(f"golden {tag} {act} {ih_mode}: mask {errs[0]:.2e} est {errs[1]:.2e} wav {errs[2]:.2e} loss {errs[3]:.2e} specMSE {errs[4]:.2e}")
+    assert errs[0] <= tol and errs[1] <= tol and errs[2] <= tol and errs[3] <= tol
+    assert errs[4] < 1e-4                                                       # BASELINE: enhanced-spectrum MSE
 
 
 @pytest.mark.parametrize("F,n_fft,hop,B,L", [(256, 512, 320, 2, 16000), (161, 320, 160, 3, 8000)])
-def test_forward_matches_oracle_eval_and_module_surface(cuda, F, n_fft, hop, B, L):
+def test_forward_matches_oracle_eval_and_module_surface(cuda, F, n_fft, hop, B, L, ih_mode):
     from cruse_b200 import pipeline
     from oracle import cruse_oracle as o
     ours, ref = _pair(F, "relu", cuda)
@@ -57,12 +81,14 @@ def test_forward_matches_oracle_eval_and_module_surface(cuda, F, n_fft, hop, B, 
         X = o.spec_to_bctf(o.stft(noisy, n_fft, hop, n_fft))
         mag = torch.sqrt(X[:, 0:1] ** 2 + X[:, 1:2] ** 2 + 1e-8)[..., :F]
         m2 = ours(mag.to(cuda))
-    assert m2.shape == m0.shape and rel_err(m2, m0) <= 1e-4
+    tol = TOL[ih_mode]
     T = m0.shape[2]
-    assert rel_err(m1, m0.view(B, T, F)) <= 1e-4
-    assert rel_err(e1, e0.permute(0, 2, 3, 1)) <= 1e-4
-    assert rel_err(w1, w0) <= 1e-4
-    assert abs(float(l1) - float(l0)) <= 2e-5 * abs(float(l0))
+    errs = (rel_err(m2, m0), rel_err(m1, m0.view(B, T, F)), rel_err(e1, e0.permute(0, 2, 3, 1)), rel_err(w1, w0),
+            abs(float(l1) - float(l0)) / abs(float(l0)), float(((e1.cpu() - e0.permute(0, 2, 3, 1)) ** 2).mean()))
+    _log(f"oracle F{F} T{T} {ih_mode}: module-mask {errs[0]:.2e} mask {errs[1]:.2e} est {errs[2]:.2e} wav {errs[3]:.2e} "
+         f"loss {errs[4]:.2e} specMSE {errs[5]:.2e}")
+    assert m2.shape == m0.shape
+    assert all(e <= tol for e in errs[:5]) and errs[5] < 1e-4
 
 
 def test_forward_train_mode_batchnorm(cuda):
@@ -75,7 +101,7 @@ def test_forward_train_mode_batchnorm(cuda):
     with torch.no_grad():
         want = ref(x)
         got = ours(x.to(cuda))
-    assert rel_err(got, want) <= 2e-4
+    assert rel_err(got, want) <= 1e-3
     for k in ("bn1", "bn4", "bn3_t"):
         assert rel_err(getattr(ours, k).running_mean, getattr(ref, k).running_mean) <= 1e-4
         assert rel_err(getattr(ours, k).running_var, getattr(ref, k).running_var) <= 1e-4
@@ -95,7 +121,7 @@ def test_streaming_matches_batched(cuda):
         st, outs = streaming.StreamState(), []
         for t0 in range(0, T, 6):
             outs.append(streaming.step(ours, mag[:, t0:t0 + 6].contiguous(), st))
-    assert rel_err(torch.cat(outs, dim=1), full) <= 1e-5
+    assert rel_err(torch.cat(outs, dim=1), full) <= 1e-4
 
 
 def test_properties_at_baseline_sizes(cuda):
@@ -140,3 +166,26 @@ def test_properties_at_baseline_sizes(cuda):
         _, _, _, mask3 = pipeline.forward_loss(m, y3, y2, n_fft, hop)
     t_safe = (L - 16000 - 256) // hop - 1
     assert torch.equal(mask3[:, :t_safe], mask[:, :t_safe])
+
+
+def test_long_sequence_drift_T1001(cuda):
+    """measure the tf32 drift of the recurrence input over T = 1001 frames against the oracle
+    (one 10 s clip at hop 160, config R geometry is covered above; here config B at 20 s)."""
+    from cruse_b200 import ops, pipeline
+    from oracle import cruse_oracle as o
+    ours, ref = _pair(256, "relu", cuda)
+    ours.eval(); ref.eval()
+    noisy, clean = o.synth_batch(1, 320000)       # T = 1001 at hop 320
+    with torch.no_grad():
+        l0, w0, e0, m0 = o.forward_loss(ref, noisy, clean, 512, 320)
+        for mode in ("fp32", "tf32"):
+            old, ops.GRU_IH_MODE = ops.GRU_IH_MODE, mode
+            try:
+                l1, w1, e1, m1 = pipeline.forward_loss(ours, noisy.to(cuda), clean.to(cuda), 512, 320)
+            finally:
+                ops.GRU_IH_MODE = old
+            T = m0.shape[2]
+            em = rel_err(m1, m0.view(1, T, 256))
+            mse = float(((e1.cpu() - e0.permute(0, 2, 3, 1)) ** 2).mean())
+            _log(f"drift T{T} {mode}: mask {em:.2e} specMSE {mse:.2e} loss {abs(float(l1) - float(l0)) / abs(float(l0)):.2e}")
+            assert em <= TOL[mode] and mse < 1e-4

@@ -173,8 +173,9 @@ def test_decoder_stage_eval(cuda, cin, cout, Fin, Fout, last):
 
 
 # ------------------------------------------------------------------ GRU / LayerNorm
-@pytest.mark.parametrize("G,H,B,T", [(4, 256, 3, 9), (4, 176, 9, 5), (2, 32, 17, 4), (4, 256, 8, 33)])
-def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T):
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("G,H,B,T", [(4, 256, 3, 9), (4, 176, 9, 5), (2, 32, 17, 4), (4, 256, 8, 33), (4, 256, 40, 20)])
+def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T, mode, tol):
     from cruse_b200 import ops
     torch.manual_seed(6)
     grus = [nn.GRU(H, H, 1, batch_first=True) for _ in range(G)]
@@ -188,12 +189,16 @@ def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T):
     dev = lambda ts: [t.detach().to(cuda) for t in ts]
     w_ih, w_hh = dev([g.weight_ih_l0 for g in grus]), dev([g.weight_hh_l0 for g in grus])
     b_ih, b_hh = dev([g.bias_ih_l0 for g in grus]), dev([g.bias_hh_l0 for g in grus])
-    xproj = ops.gru_ih_gemm(x.view(B * T, G * H).to(cuda), w_ih, b_ih, b_hh)
+    xproj = ops.gru_ih_gemm(x.view(B * T, G * H).to(cuda), w_ih, b_ih, b_hh, mode=mode)
+    with torch.no_grad():   # the projection itself: x_g W_ih^T + b_ih (+ b_hh on r,z)
+        want = torch.stack([x.view(B * T, G, H)[:, g] @ grus[g].weight_ih_l0.T + grus[g].bias_ih_l0 +
+                            torch.cat([grus[g].bias_hh_l0[:2 * H], torch.zeros(H)]) for g in range(G)], dim=1)
+    assert rel_err(xproj, want) <= tol
     got_cat, got_h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.to(cuda), want_hT=True)
     got_int = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=True, h0=h0.to(cuda))
-    assert rel_err(got_cat, y_cat) <= 2e-5
-    assert rel_err(got_int, y_int) <= 2e-5
-    assert rel_err(got_h, hT) <= 2e-5
+    assert rel_err(got_cat, y_cat) <= tol
+    assert rel_err(got_int, y_int) <= tol
+    assert rel_err(got_h, hT) <= tol
 
 
 def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
@@ -206,7 +211,7 @@ def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
     B, T, _ = x.shape
     P = lambda k: [torch.from_numpy(g[f"sd.layers.{i}.{k}"]).to(cuda) for i in range(G)]
     w_ih, w_hh, b_ih, b_hh = P("weight_ih_l0"), P("weight_hh_l0"), P("bias_ih_l0"), P("bias_hh_l0")
-    xproj = ops.gru_ih_gemm(x.reshape(B * T, G * H).contiguous(), w_ih, b_ih, b_hh)
+    xproj = ops.gru_ih_gemm(x.reshape(B * T, G * H).contiguous(), w_ih, b_ih, b_hh, mode="fp32")
     y, h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.contiguous(), want_hT=True)
     assert rel_err(y, torch.from_numpy(g["y"])) <= 2e-5
     assert rel_err(h, torch.from_numpy(g["h"])) <= 2e-5
@@ -215,7 +220,7 @@ def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
     # streaming
     hs, ys = h0.contiguous(), []
     for t in range(T):
-        xp = ops.gru_ih_gemm(x[:, t].contiguous(), w_ih, b_ih, b_hh)
+        xp = ops.gru_ih_gemm(x[:, t].contiguous(), w_ih, b_ih, b_hh, mode="fp32")
         yt, hs = ops.gru_seq_fwd(xp, w_hh, b_hh, B, 1, interleave=False, h0=hs, want_hT=True)
         ys.append(yt)
     assert rel_err(torch.cat(ys, dim=1), y) <= 1e-6
@@ -248,7 +253,7 @@ def test_ggru_module_matches_oracle(cuda):
         with torch.no_grad():
             want = ref(x)
             got = ours.to(cuda)(x.to(cuda))
-        assert got.shape == want.shape and rel_err(got, want) <= 3e-5
+        assert got.shape == want.shape and rel_err(got, want) <= 1e-3
 
 
 # ------------------------------------------------------------------ loss

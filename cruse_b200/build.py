@@ -55,7 +55,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         src, obj = pair
         if not force and not _stale(obj, [src] + headers):
             return ""
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = os.environ.get("CRUSE_EXTRA_NVCC_FLAGS", "").split()       # developer instrumentation only
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

@@ -36,6 +36,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// one lane of a fully converged warp (the compiler can then keep single-thread tcgen05 issue on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -262,8 +262,14 @@ def gru_ih_gemm(x, w_ih, b_ih, b_hh, mode=None):
     return xproj
 
 
-def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False):
-    """recurrence over T; y [B,T,G*H] with y[..., j*G+g] (interleave, cruse_net.py:43-45) or y[..., g*H+j] (cat)."""
+# "tf32": tcgen05 recurrence (default); "fp32": exact-fp32 register-resident CUDA-core recurrence
+GRU_SEQ_MODE = os.environ.get("CRUSE_GRU_SEQ", "tf32")
+
+
+def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False, mode=None, want_gates=False):
+    """recurrence over T; y [B,T,G*H] with y[..., j*G+g] (interleave, cruse_net.py:43-45) or y[..., g*H+j] (cat).
+    want_gates (tf32 mode only): also returns gates [B,T,G,4,H] = r, z, n, W_hn.h+b_hn (saved for backward)."""
+    mode = mode or GRU_SEQ_MODE
     _req(xproj, "xproj", 3)
     _req(h0, "h0")
     G = len(w_hh)
@@ -274,8 +280,21 @@ def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False):
     hT = torch.empty(G, B, H, device=xproj.device, dtype=torch.float32) if want_hT else None
     y_fs, y_gs = (G, 1) if interleave else (1, H)
     tw, tb = _ptr_table(w_hh), _ptr_table(b_hh)
-    _call("cruse_gru_seq_fwd", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), B, T, G, H, y_fs, y_gs, _stream(),
-          meta=(f"gru_seq G{G} H{H} T{T}", _nb(xproj, y, *w_hh), 2 * B * T * G * H * 3 * H))
+    gates = None
+    if mode == "tf32":
+        if want_gates:
+            gates = torch.empty(B, T, G, 4, H, device=xproj.device, dtype=torch.float32)
+        _call("cruse_gru_seq_fwd_tc", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), _p(gates), B, T, G, H, y_fs, y_gs,
+              _stream(), meta=(f"gru_seq[tf32] G{G} H{H} T{T}", _nb(xproj, y, gates, *w_hh), 2 * B * T * G * H * 3 * H))
+    elif mode == "fp32":
+        if want_gates:
+            raise RuntimeError("gru_seq_fwd: want_gates needs mode='tf32'")
+        _call("cruse_gru_seq_fwd", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), B, T, G, H, y_fs, y_gs, _stream(),
+              meta=(f"gru_seq[fp32] G{G} H{H} T{T}", _nb(xproj, y, *w_hh), 2 * B * T * G * H * 3 * H))
+    else:
+        raise RuntimeError(f"gru_seq_fwd: unknown mode {mode!r}")
+    if want_gates:
+        return (y, hT, gates) if want_hT else (y, gates)
     return (y, hT) if want_hT else y
 
 

@@ -120,6 +120,17 @@ int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* 
 int cruse_gru_seq_fwd(const float* xproj, const float* const* w_hh, const float* const* b_hh,
                       const float* h0, float* y, float* hT,
                       int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
+/* same contract with the per-step W_hh.h product on the tensor cores (tcgen05.mma kind::tf32, W_hh slice
+ * resident in shared memory, accumulator in TMEM; one cluster of ceil(H/32) CTAs per (group, 16 utterances)).
+ * Only the matmul operands are rounded to tf32; gate math and the z*h carry stay fp32.  H % 4 == 0, H <= 256.
+ * gates [B,T,G,4,H] or NULL: saves r, z, n and (W_hn.h + b_hn) of every step for the backward pass. */
+int cruse_gru_seq_fwd_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh,
+                         const float* h0, float* y, float* hT, float* gates,
+                         int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
+
+/* how many clusters of the tcgen05 recurrence kernel the current device can hold at once (each serves 16
+ * utterances of one group); B*G/16 above this runs in waves.  <0 on error. */
+int cruse_gru_seq_tc_max_clusters(int H);
 
 /* ---- nn.LayerNorm(D) at model/cruse_net.py:32-33,46,51.  x,y [rows, D]; mean/rstd [rows] or NULL.
  *      residual [rows, D] or NULL is added after the affine (fuses `+ skip4`, cruse_net.py:160). */

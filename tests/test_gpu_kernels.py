@@ -194,11 +194,19 @@ def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T, mode, tol):
         want = torch.stack([x.view(B * T, G, H)[:, g] @ grus[g].weight_ih_l0.T + grus[g].bias_ih_l0 +
                             torch.cat([grus[g].bias_hh_l0[:2 * H], torch.zeros(H)]) for g in range(G)], dim=1)
     assert rel_err(xproj, want) <= tol
-    got_cat, got_h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.to(cuda), want_hT=True)
-    got_int = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=True, h0=h0.to(cuda))
+    got_cat, got_h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.to(cuda), want_hT=True, mode=mode)
+    got_int = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=True, h0=h0.to(cuda), mode=mode)
     assert rel_err(got_cat, y_cat) <= tol
     assert rel_err(got_int, y_int) <= tol
     assert rel_err(got_h, hT) <= tol
+    if mode == "tf32":   # saved gates (for backward) are consistent with the outputs: h_t = (1-z) n + z h_{t-1}
+        y2, gates = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.to(cuda), mode=mode, want_gates=True)
+        assert torch.equal(y2, got_cat)
+        r, z, n, hn = gates.unbind(3)                                               # [B,T,G,H] each
+        hprev = torch.cat([h0.to(cuda).permute(1, 0, 2).unsqueeze(1), y2.view(B, T, G, H)[:, :-1]], dim=1)
+        assert rel_err((1 - z) * n + z * hprev, y2.view(B, T, G, H)) <= 1e-6
+        xn = xproj.view(B, T, G, 3 * H)[..., 2 * H:]
+        assert rel_err(torch.tanh(xn + r * hn), n) <= 1e-5
 
 
 def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
@@ -212,19 +220,20 @@ def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
     P = lambda k: [torch.from_numpy(g[f"sd.layers.{i}.{k}"]).to(cuda) for i in range(G)]
     w_ih, w_hh, b_ih, b_hh = P("weight_ih_l0"), P("weight_hh_l0"), P("bias_ih_l0"), P("bias_hh_l0")
     xproj = ops.gru_ih_gemm(x.reshape(B * T, G * H).contiguous(), w_ih, b_ih, b_hh, mode="fp32")
-    y, h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.contiguous(), want_hT=True)
-    assert rel_err(y, torch.from_numpy(g["y"])) <= 2e-5
-    assert rel_err(h, torch.from_numpy(g["h"])) <= 2e-5
-    y0 = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False)
-    assert rel_err(y0, torch.from_numpy(g["y_zero"])) <= 2e-5
-    # streaming
-    hs, ys = h0.contiguous(), []
-    for t in range(T):
-        xp = ops.gru_ih_gemm(x[:, t].contiguous(), w_ih, b_ih, b_hh, mode="fp32")
-        yt, hs = ops.gru_seq_fwd(xp, w_hh, b_hh, B, 1, interleave=False, h0=hs, want_hT=True)
-        ys.append(yt)
-    assert rel_err(torch.cat(ys, dim=1), y) <= 1e-6
-    assert rel_err(hs, h) <= 1e-6
+    for mode, tol, tol_stream in (("fp32", 2e-5, 1e-6), ("tf32", 1e-3, 1e-3)):
+        y, h = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.contiguous(), want_hT=True, mode=mode)
+        assert rel_err(y, torch.from_numpy(g["y"])) <= tol
+        assert rel_err(h, torch.from_numpy(g["h"])) <= tol
+        y0 = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, mode=mode)
+        assert rel_err(y0, torch.from_numpy(g["y_zero"])) <= tol
+        # streaming
+        hs, ys = h0.contiguous(), []
+        for t in range(T):
+            xp = ops.gru_ih_gemm(x[:, t].contiguous(), w_ih, b_ih, b_hh, mode="fp32")
+            yt, hs = ops.gru_seq_fwd(xp, w_hh, b_hh, B, 1, interleave=False, h0=hs, want_hT=True, mode=mode)
+            ys.append(yt)
+        assert rel_err(torch.cat(ys, dim=1), y) <= tol_stream
+        assert rel_err(hs, h) <= tol_stream
 
 
 @pytest.mark.parametrize("rows,D", [(37, 1024), (5, 704), (3, 33)])

@@ -33,7 +33,7 @@ SIGNATURES = {
     "cruse_sm_count": (c_int, []),
     "cruse_stft_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_fp]),
     "cruse_mask_istft_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_fp]),
-    "cruse_mask_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "cruse_mask_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_conv_fwd": (c_int, [c_fp] * 7 + [c_int, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
     "cruse_conv_nparts": (c_int, [c_int, c_int]),
     "cruse_convT_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
@@ -49,6 +49,20 @@ SIGNATURES = {
     "cruse_wo_male_fwd_bwd": (c_int, [c_fp, CplxLayout, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp,
                                       c_int, c_int, c_int, c_fp]),
     "cruse_wo_male_ws_bytes": (C.c_size_t, []),
+    # ---- a9 backward
+    "cruse_colsum": (c_int, [c_fp, c_int, c_int, c_fp, c_int, c_fp]),
+    "cruse_conv_dgrad": (c_int, [c_fp, c_fp, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
+    "cruse_conv_wgrad": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
+    "cruse_conv_wgrad_ws_bytes": (C.c_size_t, [c_int] * 7),
+    "cruse_convT_dgrad": (c_int, [c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_convT_wgrad": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_convT_wgrad_ws_bytes": (C.c_size_t, [c_int] * 6),
+    "cruse_bn_bwd_nparts": (c_int, [c_ll]),
+    "cruse_bn_act_bwd_reduce": (c_int, [c_fp] * 5 + [c_int] + [c_fp] * 3 + [c_ll, c_int, c_int, c_fp]),
+    "cruse_bn_bwd_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "cruse_bn_act_bwd_apply": (c_int, [c_fp] * 5 + [c_int] + [c_fp] * 4 + [c_ll, c_int, c_int, c_fp]),
+    "cruse_layernorm_bwd_nparts": (c_int, [c_ll]),
+    "cruse_layernorm_bwd": (c_int, [c_fp] * 7 + [c_ll, c_int, c_fp]),
 }
 
 _lock = threading.Lock()

@@ -26,16 +26,20 @@ constexpr int CONV_THREADS = 256;
 // smem: s_in[(TT+KT-1)][Cin][Fin+2]  (zero column on both sides),  s_w[Cin][KT*3][CoutP] (CoutP = Cout
 // rounded up to CONV_COT), s_stats[2*Cout]
 // ---------------------------------------------------------------------------------------------
+// wmode selects how `w` is read: 0 = Conv2d weight [Cout][Cin][KT][3] (forward);
+//   1 = data gradient of a (1,3)/stride-1 conv: w is that conv's weight [Cin_k][Cout_k][1][3], taps flipped;
+//   2 = data gradient of a ConvTranspose2d (1,3)/stride-2: w is its weight [Cout_k][Cin_k][1][3] (run with SF=2, pad_left=0).
+// pad_left = zero columns left of bin 0 (1 for the forward convs); addend (optional) is added to the result.
 template <int KT, int SF>
 __global__ void __launch_bounds__(CONV_THREADS)
 conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, const float* __restrict__ w,
                 const float* __restrict__ bias,
                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha,
-                int act, float* __restrict__ out, float* __restrict__ stats_ws, int T, int Cin, int Fin, int Cout,
-                int Fout) {
+                int act, const float* __restrict__ addend, float* __restrict__ out, float* __restrict__ stats_ws, int T, int Cin, int Fin, int Cout,
+                int Fout, int pad_left, int wmode) {
     extern __shared__ float smem[];
     constexpr int TT = CONV_TT, COT = CONV_COT, NR = TT + KT - 1;
-    const int FinP = Fin + 2;
+    const int FinP = Fin + 3;   // zero column left, two right (the stride-2 gradient form reads up to bin Fin+1)
     const int CoutP = (Cout + COT - 1) / COT * COT;
     float* s_in = smem;
     float* s_w = s_in + (((size_t)NR * Cin * FinP + 3) & ~(size_t)3);  // keep float4 alignment
@@ -49,7 +53,17 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, co
     const int nw = Cin * KT * 3;
     for (int i = tid; i < nw * CoutP; i += blockDim.x) {
         const int co = i % CoutP, r = i / CoutP;  // r = ci*(KT*3) + tap
-        s_w[i] = (co < Cout) ? __ldg(w + (size_t)co * nw + r) : 0.f;
+        float v = 0.f;
+        if (co < Cout) {
+            if (wmode == 0) {
+                v = __ldg(w + (size_t)co * nw + r);
+            } else {
+                const int ci = r / 3, kf = r - ci * 3;                         // KT == 1 in the gradient modes
+                v = (wmode == 1) ? __ldg(w + ((size_t)ci * Cout + co) * 3 + (2 - kf))     // [Cin_k][Cout_k][1][3], flipped
+                                 : __ldg(w + ((size_t)co * Cin + ci) * 3 + kf);           // [Cout_k][Cin_k][1][3]
+            }
+        }
+        s_w[i] = v;
     }
     if (stats_ws)
         for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
@@ -81,6 +95,7 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, co
         for (int ci = tid; ci < Cin; ci += blockDim.x) {
             dst[ci * FinP] = 0.f;
             dst[ci * FinP + Fin + 1] = 0.f;
+            dst[ci * FinP + Fin + 2] = 0.f;
         }
     }
     __syncthreads();
@@ -96,7 +111,7 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, co
 #pragma unroll
             for (int c = 0; c < COT; ++c) acc[t][c] = 0.f;
 
-        const float* ip = s_in + SF * fo;  // padded index of tap kf=0 is SF*fo (unpadded SF*fo-1)
+        const float* ip = s_in + SF * fo + (1 - pad_left);  // smem column 0 is the zero pad: tap kf=0 of output fo sits at unpadded SF*fo - pad_left
         for (int ci = 0; ci < Cin; ++ci) {
             float xv[NR][3];
 #pragma unroll
@@ -135,7 +150,9 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, co
                     float v = acc[t][c] + bv;
                     s1 += v; s2 += v * v;
                     v = apply_act(fmaf(v, sc, sh), act, al);
-                    out[(((size_t)b * T + t0 + t) * Cout + co) * Fout + fo] = v;
+                    const size_t o = (((size_t)b * T + t0 + t) * Cout + co) * Fout + fo;
+                    if (addend) v += __ldg(addend + o);
+                    out[o] = v;
                 }
             }
             if (stats_ws) {
@@ -157,33 +174,37 @@ conv_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hist, co
 //   out[co, 2i+1] = b + sum_ci W[ci,co,1]*in[ci,i]
 // smem: s_in[TT][Cin][Fin+2], s_w[Cin][3][CoutP], s_stats[2*Cout]
 // ---------------------------------------------------------------------------------------------
+// KT = 2 is the data gradient of the causal (2,3)/stride-(1,2) encoder conv (w = that conv's weight
+// [Cin_k][Cout_k][2][3]): time tap kt reads input frame t + 1 - kt (kt = 0 looks one frame AHEAD), and the
+// result is shifted by `oshift` = 1 bins (convT output u = f + 1, because the conv padded one bin on the left).
+template <int KT>
 __global__ void __launch_bounds__(CONV_THREADS)
 convT_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha,
                  int act, const float* __restrict__ skip, float* __restrict__ out, float* __restrict__ stats_ws, int T,
-                 int Cin, int Fin, int Cout, int Fout) {
+                 int Cin, int Fin, int Cout, int Fout, int oshift) {
     extern __shared__ float smem[];
-    constexpr int TT = CONV_TT, COT = CONV_COT;
+    constexpr int TT = CONV_TT, COT = CONV_COT, NR = CONV_TT + KT - 1;
     const int FinP = Fin + 2;
     const int CoutP = (Cout + COT - 1) / COT * COT;
     float* s_in = smem;
-    float* s_w = s_in + (((size_t)TT * Cin * FinP + 3) & ~(size_t)3);  // keep float4 alignment
-    float* s_stats = s_w + (size_t)Cin * 3 * CoutP;
+    float* s_w = s_in + (((size_t)NR * Cin * FinP + 3) & ~(size_t)3);  // keep float4 alignment
+    float* s_stats = s_w + (size_t)Cin * KT * 3 * CoutP;
     const int chunks = (T + TT - 1) / TT;
     const int b = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * TT;
     const int tid = threadIdx.x;
 
-    // weights: PyTorch [Cin][Cout][1][3] -> s_w[ci][kf][co]
-    for (int i = tid; i < Cin * 3 * CoutP; i += blockDim.x) {
+    // weights: PyTorch [Cin][Cout][KT][3] -> s_w[ci][kt*3+kf][co]
+    for (int i = tid; i < Cin * KT * 3 * CoutP; i += blockDim.x) {
         const int co = i % CoutP, r = i / CoutP;
-        const int kf = r % 3, ci = r / 3;
-        s_w[i] = (co < Cout) ? __ldg(w + ((size_t)ci * Cout + co) * 3 + kf) : 0.f;
+        const int tap = r % (KT * 3), ci = r / (KT * 3);
+        s_w[i] = (co < Cout) ? __ldg(w + ((size_t)ci * Cout + co) * (KT * 3) + tap) : 0.f;
     }
     if (stats_ws)
         for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
     const int rowlen = Cin * Fin;
     const float* inb = in + (size_t)b * T * rowlen;
-    for (int r = 0; r < TT; ++r) {
+    for (int r = 0; r < NR; ++r) {
         const int t = t0 + r;
         const bool valid = t < T;
         float* dst = s_in + (size_t)r * Cin * FinP;
@@ -208,7 +229,7 @@ convT_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, cons
     }
     __syncthreads();
 
-    const int npair = (Fout + 1) / 2;
+    const int npair = (Fout + oshift + 1) / 2;
     const int ncob = CoutP / COT;
     const int items = npair * ncob;
     for (int item = tid; item < items; item += blockDim.x) {
@@ -220,25 +241,29 @@ convT_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, cons
 #pragma unroll
             for (int c = 0; c < COT; ++c) { ae[t][c] = 0.f; ao[t][c] = 0.f; }
         for (int ci = 0; ci < Cin; ++ci) {
-            const float* wp = s_w + (size_t)ci * 3 * CoutP + co0;
-            const float4 w0 = *reinterpret_cast<const float4*>(wp);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + CoutP);
-            const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * CoutP);
 #pragma unroll
-            for (int t = 0; t < TT; ++t) {
-                const float* p = s_in + ((size_t)t * Cin + ci) * FinP + i;  // p[0]=in[i-1], p[1]=in[i]
-                const float xm = p[0], x0 = p[1];
-                ae[t][0] = fmaf(w0.x, x0, fmaf(w2.x, xm, ae[t][0]));
-                ae[t][1] = fmaf(w0.y, x0, fmaf(w2.y, xm, ae[t][1]));
-                ae[t][2] = fmaf(w0.z, x0, fmaf(w2.z, xm, ae[t][2]));
-                ae[t][3] = fmaf(w0.w, x0, fmaf(w2.w, xm, ae[t][3]));
-                ao[t][0] = fmaf(w1.x, x0, ao[t][0]);
-                ao[t][1] = fmaf(w1.y, x0, ao[t][1]);
-                ao[t][2] = fmaf(w1.z, x0, ao[t][2]);
-                ao[t][3] = fmaf(w1.w, x0, ao[t][3]);
+            for (int kt = 0; kt < KT; ++kt) {
+                const float* wp = s_w + ((size_t)ci * KT + kt) * 3 * CoutP + co0;
+                const float4 w0 = *reinterpret_cast<const float4*>(wp);
+                const float4 w1 = *reinterpret_cast<const float4*>(wp + CoutP);
+                const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * CoutP);
+#pragma unroll
+                for (int t = 0; t < TT; ++t) {
+                    const float* p = s_in + ((size_t)(t + (KT - 1) - kt) * Cin + ci) * FinP + i;  // p[0]=in[i-1], p[1]=in[i]
+                    const float xm = p[0], x0 = p[1];
+                    ae[t][0] = fmaf(w0.x, x0, fmaf(w2.x, xm, ae[t][0]));
+                    ae[t][1] = fmaf(w0.y, x0, fmaf(w2.y, xm, ae[t][1]));
+                    ae[t][2] = fmaf(w0.z, x0, fmaf(w2.z, xm, ae[t][2]));
+                    ae[t][3] = fmaf(w0.w, x0, fmaf(w2.w, xm, ae[t][3]));
+                    ao[t][0] = fmaf(w1.x, x0, ao[t][0]);
+                    ao[t][1] = fmaf(w1.y, x0, ao[t][1]);
+                    ao[t][2] = fmaf(w1.z, x0, ao[t][2]);
+                    ao[t][3] = fmaf(w1.w, x0, ao[t][3]);
+                }
             }
         }
-        const int fe = 2 * i, fo = 2 * i + 1;
+        const int fe = 2 * i - oshift, fo = 2 * i + 1 - oshift;
+        const bool has_even = fe >= 0 && fe < Fout;
         const bool has_odd = fo < Fout;
 #pragma unroll
         for (int c = 0; c < COT; ++c) {
@@ -253,20 +278,21 @@ convT_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, cons
                 if (t0 + t < T) {
                     const size_t o = (((size_t)b * T + t0 + t) * Cout + co) * Fout;
                     float v0 = ae[t][c] + bv, v1 = ao[t][c] + bv;
-                    s1 += v0; s2 += v0 * v0;
-                    v0 = apply_act(fmaf(v0, sc, sh), act, al);
-                    if (skip) v0 += __ldg(skip + o + fe);
+                    if (has_even) {
+                        s1 += v0; s2 += v0 * v0;
+                        v0 = apply_act(fmaf(v0, sc, sh), act, al);
+                        if (skip) v0 += __ldg(skip + o + fe);
+                    }
                     if (has_odd) {
                         s1 += v1; s2 += v1 * v1;
                         v1 = apply_act(fmaf(v1, sc, sh), act, al);
                         if (skip) v1 += __ldg(skip + o + fo);
-                        if ((Fout & 1) == 0) {
-                            *reinterpret_cast<float2*>(out + o + fe) = make_float2(v0, v1);
-                        } else {
-                            out[o + fe] = v0; out[o + fo] = v1;
-                        }
+                    }
+                    if (has_even && has_odd && oshift == 0 && (Fout & 1) == 0) {
+                        *reinterpret_cast<float2*>(out + o + fe) = make_float2(v0, v1);
                     } else {
-                        out[o + fe] = v0;
+                        if (has_even) out[o + fe] = v0;
+                        if (has_odd) out[o + fo] = v1;
                     }
                 }
             }
@@ -365,7 +391,7 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ z, const float* __re
 
 static size_t conv_smem_bytes(int KT, int Cin, int Fin, int Cout) {
     const int CoutP = (Cout + CONV_COT - 1) / CONV_COT * CONV_COT;
-    return sizeof(float) * (((size_t)(CONV_TT + KT - 1) * Cin * (Fin + 2) + 3 & ~(size_t)3) + (size_t)Cin * KT * 3 * CoutP + 2 * (size_t)Cout);
+    return sizeof(float) * (((size_t)(CONV_TT + KT - 1) * Cin * (Fin + 3) + 3 & ~(size_t)3) + (size_t)Cin * KT * 3 * CoutP + 2 * (size_t)Cout);
 }
 
 }  // namespace cruse
@@ -390,10 +416,10 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
     cudaStream_t st = (cudaStream_t)stream;
     if (kt == 2) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_kernel<2, 2><<<grid, CONV_THREADS, smem, st>>>(in, hist, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
+        conv_fwd_kernel<2, 2><<<grid, CONV_THREADS, smem, st>>>(in, hist, w, bias, scale, shift, alpha, act, nullptr, out, stats_ws, T, Cin, Fin, Cout, Fout, 1, 0);
     } else {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(in, nullptr, w, bias, scale, shift, alpha, act, out, stats_ws, T, Cin, Fin, Cout, Fout);
+        conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(in, nullptr, w, bias, scale, shift, alpha, act, nullptr, out, stats_ws, T, Cin, Fin, Cout, Fout, 1, 0);
     }
     CRUSE_LAUNCH_OK();
     return 0;
@@ -410,10 +436,54 @@ extern "C" int cruse_convT_fwd(const float* in, const float* w, const float* bia
     const int CoutP = (Cout + CONV_COT - 1) / CONV_COT * CONV_COT;
     const size_t smem = sizeof(float) * ((((size_t)CONV_TT * Cin * (Fin + 2) + 3) & ~(size_t)3) + (size_t)Cin * 3 * CoutP + 2 * (size_t)Cout);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "convT_fwd: stage needs %zu B shared memory", smem);
-    CRUSE_CUDA_OK(cudaFuncSetAttribute(convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(convT_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = cruse_conv_nparts(B, T);
-    convT_fwd_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(in, w, bias, scale, shift, alpha, act, skip, out, stats_ws, T,
-                                                                         Cin, Fin, Cout, Fout);
+    convT_fwd_kernel<1><<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(in, w, bias, scale, shift, alpha, act, skip, out, stats_ws, T,
+                                                                         Cin, Fin, Cout, Fout, 0);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ---- data gradients: the forward kernels run "backwards" with re-indexed weights -------------------
+extern "C" int cruse_conv_dgrad(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin,
+                                int Fin, int Cout, int Fout, int kt, int fstride, void* stream) {
+    CRUSE_CHECK_ARG(dz && w && din, "conv_dgrad: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "conv_dgrad: bad sizes");
+    CRUSE_CHECK_ARG((kt == 2 && fstride == 2) || (kt == 1 && fstride == 1), "conv_dgrad: supported (kt,fstride) are (2,2) and (1,1), got (%d,%d)", kt, fstride);
+    CRUSE_CHECK_ARG(Fout == (Fin + 2 - 3) / fstride + 1, "conv_dgrad: Fout=%d does not match Fin=%d", Fout, Fin);
+    const int grid = cruse_conv_nparts(B, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kt == 1) {
+        // din[ci,f] = sum_co sum_kf W[co,ci,0,kf] dz[co,f+1-kf]: a (1,3) conv over dz with flipped taps, channels swapped
+        const size_t smem = conv_smem_bytes(1, Cout, Fout, Cin);
+        CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_dgrad: stage needs %zu B shared memory", smem);
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(dz, nullptr, w, nullptr, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, addend, din,
+                                                                nullptr, T, Cout, Fout, Cin, Fin, 1, 1);
+    } else {
+        // transposed conv with two time taps (frame t and t+1) over dz, output shifted by the conv's left pad
+        const int CoutP = (Cin + CONV_COT - 1) / CONV_COT * CONV_COT;
+        const size_t smem = sizeof(float) * ((((size_t)(CONV_TT + 1) * Cout * (Fout + 2) + 3) & ~(size_t)3) + (size_t)Cout * 6 * CoutP + 2 * (size_t)Cin);
+        CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_dgrad: stage needs %zu B shared memory", smem);
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(convT_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        convT_fwd_kernel<2><<<grid, CONV_THREADS, smem, st>>>(dz, w, nullptr, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, addend, din, nullptr, T,
+                                                              Cout, Fout, Cin, Fin, 1);
+    }
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_convT_dgrad(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin,
+                                 int Fin, int Cout, int Fout, void* stream) {
+    CRUSE_CHECK_ARG(dz && w && din, "convT_dgrad: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "convT_dgrad: bad sizes");
+    CRUSE_CHECK_ARG(Fout > 0 && Fout <= 2 * Fin + 1 && Fout >= 2 * Fin - 1, "convT_dgrad: Fout=%d must be within [2*Fin-1, 2*Fin+1] (Fin=%d)", Fout, Fin);
+    // din[ci,i] = sum_co sum_k W[ci,co,0,k] dz[co,2i+k]: a stride-2 conv over dz without left padding
+    const size_t smem = conv_smem_bytes(1, Cout, Fout, Cin);
+    CRUSE_CHECK_ARG(smem <= 227 * 1024, "convT_dgrad: stage needs %zu B shared memory", smem);
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_fwd_kernel<1, 2><<<cruse_conv_nparts(B, T), CONV_THREADS, smem, (cudaStream_t)stream>>>(
+        dz, nullptr, w, nullptr, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, addend, din, nullptr, T, Cout, Fout, Cin, Fin, 0, 2);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -261,8 +261,8 @@ mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask
 }
 
 __global__ void mask_bwd_kernel(const float* __restrict__ dest, const float* __restrict__ spec,
-                                const float* __restrict__ gscale, float* __restrict__ dmask, long long rows, int NF,
-                                int mask_bins) {
+                                const float* __restrict__ gscale, const float* __restrict__ mask, float* __restrict__ dmask,
+                                long long rows, int NF, int mask_bins) {
     const float g = gscale ? __ldg(gscale) : 1.f;
     const long long total = rows * mask_bins;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -270,7 +270,9 @@ __global__ void mask_bwd_kernel(const float* __restrict__ dest, const float* __r
         const int f = (int)(i - r * mask_bins);
         const float2 d = __ldg(reinterpret_cast<const float2*>(dest) + r * NF + f);
         const float2 x = __ldg(reinterpret_cast<const float2*>(spec) + r * NF + f);
-        dmask[i] = g * (d.x * x.x + d.y * x.y);
+        float v = g * (d.x * x.x + d.y * x.y);
+        if (mask) { const float m = __ldg(mask + i); v *= m * (1.f - m); }   // through the sigmoid of cruse_net.py:164
+        dmask[i] = v;
     }
 }
 
@@ -324,15 +326,15 @@ extern "C" int cruse_mask_istft_fwd(const float* spec, const float* mask, const 
     return 0;
 }
 
-extern "C" int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, float* dmask, int B, int T,
-                              int NF, int mask_bins, void* stream) {
+extern "C" int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, const float* mask, float* dmask,
+                              int B, int T, int NF, int mask_bins, void* stream) {
     CRUSE_CHECK_ARG(dest && spec && dmask, "mask_bwd: null pointer");
     CRUSE_CHECK_ARG(mask_bins > 0 && mask_bins <= NF, "mask_bwd: mask_bins out of range");
     const long long rows = (long long)B * T, total = rows * mask_bins;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    mask_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dest, spec, gscale, dmask, rows, NF, mask_bins);
+    mask_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dest, spec, gscale, mask, dmask, rows, NF, mask_bins);
     CRUSE_LAUNCH_OK();
     return 0;
 }

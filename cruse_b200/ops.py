@@ -136,13 +136,16 @@ def mask_istft_fwd(spec, mask, window, n_fft, hop, length, want_est=True, want_w
     return est, wav
 
 
-def mask_bwd(dest, spec, mask_bins, gscale=None):
-    """dmask[b,t,f] = gscale * Re(conj(X) * dEst), f < mask_bins."""
+def mask_bwd(dest, spec, mask_bins, gscale=None, mask=None):
+    """dmask[b,t,f] = gscale * Re(conj(X) * dEst), f < mask_bins; with ``mask`` given the result is the gradient
+    before the sigmoid (times mask*(1-mask))."""
     _req(dest, "dest", 4)
     _req(spec, "spec", 4)
+    _req(mask, "mask")
     B, T, NF, _ = spec.shape
     dmask = torch.empty(B, T, mask_bins, device=spec.device, dtype=torch.float32)
-    _call("cruse_mask_bwd", _p(dest), _p(spec), _p(gscale), _p(dmask), B, T, NF, mask_bins, _stream())
+    _call("cruse_mask_bwd", _p(dest), _p(spec), _p(gscale), _p(mask), _p(dmask), B, T, NF, mask_bins, _stream(),
+          meta=("mask_bwd", _nb(dmask, mask) + 2 * 8 * B * T * mask_bins, 6 * B * T * mask_bins))
     return dmask
 
 
@@ -343,3 +346,102 @@ def wo_male_fwd_bwd(ref, lref, est, lest, unp, lunp, B, T, F, want_grad=False):
                                       B, T, F, _stream(),
           meta=("wo_male", B * T * F * 8 * (4 if want_grad else 3), 30 * B * T * F))
     return loss, dest
+
+
+# ------------------------------------------------------------------------------------------
+# a9 : backward
+# ------------------------------------------------------------------------------------------
+def _ws(nbytes, device):
+    return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32)
+
+
+def conv_dgrad(dz, w, in_shape, kt, fstride, addend=None):
+    """data gradient of conv_fwd: dz [B,T,Cout,Fout] -> din [B,T,Cin,Fin] (+ addend)."""
+    _req(dz, "dz", 4)
+    _req(w, "w", 4)
+    _req(addend, "addend")
+    B, T, Cin, Fin = in_shape
+    Cout, Fout = dz.shape[2], dz.shape[3]
+    din = torch.empty(B, T, Cin, Fin, device=dz.device, dtype=torch.float32)
+    _call("cruse_conv_dgrad", _p(dz), _p(w), _p(addend), _p(din), B, T, Cin, Fin, Cout, Fout, kt, fstride, _stream(),
+          meta=(f"conv{kt}x3 dgrad {Cout}->{Cin} F{Fout}->{Fin}", _nb(dz, din, addend, w), 2 * B * T * Cout * Fout * Cin * kt * 3))
+    return din
+
+
+def conv_wgrad(x, dz, kt, fstride, want_bias=True):
+    """weight/bias gradient of conv_fwd -> (dw [Cout,Cin,kt,3], dbias [Cout] | None)."""
+    _req(x, "x", 4)
+    _req(dz, "dz", 4)
+    B, T, Cin, Fin = x.shape
+    Cout, Fout = dz.shape[2], dz.shape[3]
+    dw = torch.empty(Cout, Cin, kt, 3, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_bias else None
+    ws = _ws(lib().cruse_conv_wgrad_ws_bytes(B, T, Cin, Fin, Cout, Fout, kt), x.device)
+    _call("cruse_conv_wgrad", _p(x), _p(dz), _p(dw), _p(db), _p(ws), B, T, Cin, Fin, Cout, Fout, kt, fstride, _stream(),
+          meta=(f"conv{kt}x3 wgrad {Cin}->{Cout} F{Fin}->{Fout}", _nb(x, dz, dw), 2 * B * T * Cout * Fout * Cin * kt * 3))
+    return dw, db
+
+
+def convT_dgrad(dz, w, in_shape, addend=None):
+    """data gradient of convT_fwd: dz [B,T,Cout,Fout] -> din [B,T,Cin,Fin] (+ addend)."""
+    _req(dz, "dz", 4)
+    _req(w, "w", 4)
+    _req(addend, "addend")
+    B, T, Cin, Fin = in_shape
+    Cout, Fout = dz.shape[2], dz.shape[3]
+    din = torch.empty(B, T, Cin, Fin, device=dz.device, dtype=torch.float32)
+    _call("cruse_convT_dgrad", _p(dz), _p(w), _p(addend), _p(din), B, T, Cin, Fin, Cout, Fout, _stream(),
+          meta=(f"convT1x3 dgrad {Cout}->{Cin} F{Fout}->{Fin}", _nb(dz, din, addend, w), 2 * B * T * Cin * Fin * Cout * 3))
+    return din
+
+
+def convT_wgrad(x, dz, want_bias=True):
+    """weight/bias gradient of convT_fwd -> (dw [Cin,Cout,1,3], dbias [Cout] | None)."""
+    _req(x, "x", 4)
+    _req(dz, "dz", 4)
+    B, T, Cin, Fin = x.shape
+    Cout, Fout = dz.shape[2], dz.shape[3]
+    dw = torch.empty(Cin, Cout, 1, 3, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=x.device, dtype=torch.float32) if want_bias else None
+    ws = _ws(lib().cruse_convT_wgrad_ws_bytes(B, T, Cin, Fin, Cout, Fout), x.device)
+    _call("cruse_convT_wgrad", _p(x), _p(dz), _p(dw), _p(db), _p(ws), B, T, Cin, Fin, Cout, Fout, _stream(),
+          meta=(f"convT1x3 wgrad {Cin}->{Cout} F{Fin}->{Fout}", _nb(x, dz, dw), 2 * B * T * Cin * Fin * Cout * 3))
+    return dw, db
+
+
+def bn_act_bwd(dy, z, scale, shift, alpha, act, mean, invstd, gamma, count, training=True):
+    """backward of y = act(BN(z)): -> (dz, dgamma, dbeta, dalpha | None).  Two streaming passes over (dy, z)."""
+    _req(dy, "dy", 4)
+    _req(z, "z", 4)
+    B, T, Cn, F = z.shape
+    dev = z.device
+    nparts = lib().cruse_bn_bwd_nparts(B * T)
+    partials = torch.empty(nparts, 3 * Cn, device=dev, dtype=torch.float32)
+    _call("cruse_bn_act_bwd_reduce", _p(dy), _p(z), _p(scale), _p(shift), _p(alpha), ACT[act], _p(mean), _p(invstd),
+          _p(partials), B * T, Cn, F, _stream(), meta=(f"bn_act_bwd_reduce C{Cn} F{F}", _nb(dy, z), 6 * z.numel()))
+    dgamma = torch.empty(Cn, device=dev, dtype=torch.float32)
+    dbeta = torch.empty_like(dgamma)
+    dalpha = torch.empty_like(dgamma) if act == "prelu" else None
+    coef = torch.empty(3 * Cn, device=dev, dtype=torch.float32)
+    _call("cruse_bn_bwd_finalize", _p(partials), nparts, Cn, float(count), _p(gamma), _p(invstd), 1 if training else 0,
+          _p(dgamma), _p(dbeta), _p(dalpha), _p(coef), _stream())
+    dz = torch.empty_like(z)
+    _call("cruse_bn_act_bwd_apply", _p(dy), _p(z), _p(scale), _p(shift), _p(alpha), ACT[act], _p(mean), _p(invstd),
+          _p(coef), _p(dz), B * T, Cn, F, _stream(), meta=(f"bn_act_bwd_apply C{Cn} F{F}", _nb(dy, z, dz), 8 * z.numel()))
+    return dz, dgamma, dbeta, dalpha
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd):
+    """-> (dx, dgamma, dbeta)."""
+    _req(dy, "dy")
+    _req(x, "x")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    nparts = lib().cruse_layernorm_bwd_nparts(rows)
+    partials = torch.empty(nparts, 2 * D, device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    _call("cruse_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(partials), rows, D, _stream(),
+          meta=(f"layernorm_bwd D{D}", _nb(dy, x, dx), 12 * x.numel()))
+    dgb = torch.empty(2 * D, device=x.device, dtype=torch.float32)
+    _call("cruse_colsum", _p(partials), nparts, 2 * D, _p(dgb), 0, _stream())
+    return dx, dgb[:D], dgb[D:]

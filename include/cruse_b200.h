@@ -64,8 +64,9 @@ int cruse_mask_istft_fwd(const float* spec, const float* mask, const float* wind
                          int B, int L, int n_fft, int hop, int T, int mask_bins, void* stream);
 
 /* backward of the mask apply: dmask[b,t,f] = gscale * (dre*Xre + dim*Xim), f < mask_bins.
- * dest [B,T,NF,2] (row stride NF) ; gscale: device scalar or NULL (=1). */
-int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, float* dmask,
+ * dest [B,T,NF,2] (row stride NF) ; gscale: device scalar or NULL (=1).  mask [B,T,mask_bins] or NULL: when given
+ * the result is multiplied by mask*(1-mask), i.e. it is the gradient BEFORE the sigmoid of model/cruse_net.py:164. */
+int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, const float* mask, float* dmask,
                    int B, int T, int NF, int mask_bins, void* stream);
 
 /* ---- a2/a3: causal strided conv stage.  replaces nn.Conv2d + slice + BatchNorm2d + act at
@@ -148,6 +149,52 @@ int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float*
                           const float* unproc, cruse_cplx_layout lunp, float* dest,
                           float* loss, void* ws, int B, int T, int F, void* stream);
 size_t cruse_wo_male_ws_bytes(void);
+
+/* =====================================================================================================
+ * a9: backward of a2-a8 (what autograd + cuDNN/ATen compute on the reference path for the modules of
+ * model/cruse_net.py:14-55,129-165).  Gradients are written (not accumulated) into caller buffers.
+ * ===================================================================================================== */
+
+/* out[j] (+)= sum_p ws[p*n + j]: fixed-order reduction of per-CTA partials */
+int cruse_colsum(const float* ws, int nparts, int n, float* out, int accumulate, void* stream);
+
+/* data gradient of cruse_conv_fwd (same B,T,Cin,Fin,Cout,Fout,kt,fstride as the forward call):
+ *   din[B,T,Cin,Fin] = conv^T(dz[B,T,Cout,Fout], w) (+ addend[B,T,Cin,Fin] or NULL) */
+int cruse_conv_dgrad(const float* dz, const float* w, const float* addend, float* din,
+                     int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream);
+/* weight / bias gradient of cruse_conv_fwd: dw [Cout,Cin,kt,3], dbias [Cout] or NULL.
+ * ws: >= cruse_conv_wgrad_ws_bytes(...) bytes of scratch. */
+int cruse_conv_wgrad(const float* in, const float* dz, float* dw, float* dbias, void* ws,
+                     int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream);
+size_t cruse_conv_wgrad_ws_bytes(int B, int T, int Cin, int Fin, int Cout, int Fout, int kt);
+/* same for cruse_convT_fwd (w, dw in ConvTranspose2d layout [Cin,Cout,1,3]) */
+int cruse_convT_dgrad(const float* dz, const float* w, const float* addend, float* din,
+                      int B, int T, int Cin, int Fin, int Cout, int Fout, void* stream);
+int cruse_convT_wgrad(const float* in, const float* dz, float* dw, float* dbias, void* ws,
+                      int B, int T, int Cin, int Fin, int Cout, int Fout, void* stream);
+size_t cruse_convT_wgrad_ws_bytes(int B, int T, int Cin, int Fin, int Cout, int Fout);
+
+/* backward of  y = act(z*scale[c]+shift[c]) (+skip)  with BatchNorm2d in front (z = conv output, pre-BN):
+ *  pass 1 (reduce):   partials[nparts][3*C] = per-CTA { sum da, sum da*xhat, sum dy*a*[a<=0] },
+ *                     a = z*scale+shift, da = dy*act'(a), xhat = (z-mean[c])*invstd[c]; nparts = cruse_bn_bwd_nparts()
+ *  pass 2 (finalize): dgamma = S2, dbeta = S1, dalpha = S3 (PReLU slope); coef[3*C] = {A, M1, M2} with
+ *                     training: A = gamma*invstd, M1 = S1/count, M2 = S2/count; eval: A = gamma*invstd, M1 = M2 = 0
+ *  pass 3 (apply):    dz = A*(da - M1 - xhat*M2) */
+int cruse_bn_bwd_nparts(long long n_frames);
+int cruse_bn_act_bwd_reduce(const float* dy, const float* z, const float* scale, const float* shift, const float* alpha,
+                            int act, const float* mean, const float* invstd, float* partials,
+                            long long n_frames, int C, int F, void* stream);
+int cruse_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* invstd,
+                          int training, float* dgamma, float* dbeta, float* dalpha, float* coef, void* stream);
+int cruse_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, const float* shift, const float* alpha,
+                           int act, const float* mean, const float* invstd, const float* coef, float* dz,
+                           long long n_frames, int C, int F, void* stream);
+
+/* nn.LayerNorm backward.  x, dy, dx [rows, D]; mean/rstd [rows] from cruse_layernorm_fwd.
+ * partials [cruse_layernorm_bwd_nparts(rows)][2*D] = per-CTA { dgamma, dbeta }; reduce with cruse_colsum. */
+int cruse_layernorm_bwd_nparts(long long rows);
+int cruse_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                        float* dx, float* partials, long long rows, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,158 @@
+"""GPU: backward kernels against torch autograd of the stock modules the reference
+uses (model/cruse_net.py:138-146: Conv2d / ConvTranspose2d / BatchNorm2d / GRU / LayerNorm).  Tolerances are
+max|d| / max|ref| per gradient tensor."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _to_frames(x):      # [B,C,T,F] -> [B,T,C,F]
+    return x.permute(0, 2, 1, 3).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,F,act", [(1, 8, 256, "relu"), (8, 16, 128, "prelu"), (16, 32, 64, "relu"), (32, 64, 32, "prelu"),
+                                           (8, 16, 81, "relu"), (3, 5, 21, "prelu")])
+def test_encoder_stage_backward(cuda, cin, cout, F, act):
+    """conv(2,3)/s(1,2) + causal slice + train-mode BN + act: dgrad, wgrad, dbias, dgamma, dbeta, dalpha."""
+    from cruse_b200 import ops
+    torch.manual_seed(20)
+    B, T = 3, 11
+    conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), (1, 1))
+    bn = nn.BatchNorm2d(cout)
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.2)
+    actm = nn.PReLU(cout) if act == "prelu" else nn.ReLU()
+    if act == "prelu":
+        actm.weight.data.uniform_(0.1, 0.4)
+    x = torch.randn(B, cin, T, F, requires_grad=True)
+    y = actm(bn(conv(x)[..., :-1, :]))
+    gy = torch.randn_like(y)
+    y.backward(gy)
+
+    xc = _to_frames(x.detach()).to(cuda)
+    w, b = conv.weight.detach().to(cuda), conv.bias.detach().to(cuda)
+    gamma, beta = bn.weight.detach().to(cuda), bn.bias.detach().to(cuda)
+    alpha = actm.weight.detach().to(cuda) if act == "prelu" else None
+    bn2 = nn.BatchNorm2d(cout).to(cuda)
+    bn2.weight.data.copy_(gamma); bn2.bias.data.copy_(beta)
+    z, stats = ops.conv_fwd(xc, w, b, None, None, None, "none", 2, 2, want_stats=True)
+    Fo = z.shape[3]
+    scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * Fo, bn2)
+    yc = ops.bn_act_fwd(z, scale, shift, alpha, act)
+    assert rel_err(yc, _to_frames(y)) <= 2e-5
+    dz, dgamma, dbeta, dalpha = ops.bn_act_bwd(_to_frames(gy).to(cuda), z, scale, shift, alpha, act, mean, invstd, gamma, B * T * Fo)
+    dw, db = ops.conv_wgrad(xc, dz, 2, 2)
+    dx = ops.conv_dgrad(dz, w, xc.shape, 2, 2)
+    assert rel_err(dgamma, bn.weight.grad) <= 1e-4
+    assert rel_err(dbeta, bn.bias.grad) <= 1e-4
+    if act == "prelu":
+        assert rel_err(dalpha, actm.weight.grad) <= 1e-4
+    assert rel_err(dw, conv.weight.grad) <= 1e-4
+    assert rel_err(dx, _to_frames(x.grad)) <= 1e-4
+    # conv bias gradient is analytically 0 in front of a train-mode BN: compare on the absolute scale of dz sums
+    assert float((db.cpu() - conv.bias.grad).abs().max()) <= 1e-4 * float(dz.abs().sum(dim=(0, 1, 3)).max())
+    # addend path
+    add = torch.randn_like(xc)
+    assert rel_err(ops.conv_dgrad(dz, w, xc.shape, 2, 2, addend=add), _to_frames(x.grad).to(cuda) + add) <= 1e-4
+
+
+@pytest.mark.parametrize("c,F", [(8, 128), (64, 16), (16, 41), (5, 7)])
+def test_skip_conv_backward(cuda, c, F):
+    from cruse_b200 import ops
+    torch.manual_seed(21)
+    B, T = 2, 9
+    conv = nn.Conv2d(c, c, (1, 3), bias=False, padding=(0, 1))
+    x = torch.randn(B, c, T, F, requires_grad=True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xc, gc, w = _to_frames(x.detach()).to(cuda), _to_frames(gy).to(cuda), conv.weight.detach().to(cuda)
+    dw, db = ops.conv_wgrad(xc, gc, 1, 1, want_bias=False)
+    assert db is None
+    assert rel_err(dw, conv.weight.grad) <= 1e-4
+    assert rel_err(ops.conv_dgrad(gc, w, xc.shape, 1, 1), _to_frames(x.grad)) <= 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,Fin,Fout,act", [(64, 32, 16, 32, "relu"), (32, 16, 32, 64, "prelu"), (16, 8, 64, 128, "relu"),
+                                                   (64, 32, 11, 21, "prelu"), (16, 8, 41, 81, "relu")])
+def test_decoder_stage_backward(cuda, cin, cout, Fin, Fout, act):
+    """ConvTranspose2d(1,3)/s(1,2) + crop + train BN + act + skip."""
+    from cruse_b200 import ops
+    torch.manual_seed(22)
+    B, T = 2, 10
+    conv = nn.ConvTranspose2d(cin, cout, (1, 3), (1, 2))
+    bn = nn.BatchNorm2d(cout)
+    bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_(0, 0.2)
+    actm = nn.PReLU(cout) if act == "prelu" else nn.ReLU()
+    x = torch.randn(B, cin, T, Fin, requires_grad=True)
+    skip = torch.randn(B, cout, T, Fout)
+    y = actm(bn(conv(x)[..., :Fout])) + skip
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xc = _to_frames(x.detach()).to(cuda)
+    w, b = conv.weight.detach().to(cuda), conv.bias.detach().to(cuda)
+    gamma = bn.weight.detach().to(cuda)
+    alpha = actm.weight.detach().to(cuda) if act == "prelu" else None
+    bn2 = nn.BatchNorm2d(cout).to(cuda)
+    bn2.weight.data.copy_(gamma); bn2.bias.data.copy_(bn.bias.detach())
+    z, stats = ops.convT_fwd(xc, w, b, None, None, None, "none", None, Fout, want_stats=True)
+    scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * Fout, bn2)
+    yc = ops.bn_act_fwd(z, scale, shift, alpha, act, skip=_to_frames(skip).to(cuda))
+    assert rel_err(yc, _to_frames(y)) <= 2e-5
+    dz, dgamma, dbeta, dalpha = ops.bn_act_bwd(_to_frames(gy).to(cuda), z, scale, shift, alpha, act, mean, invstd, gamma, B * T * Fout)
+    dw, db = ops.convT_wgrad(xc, dz)
+    dx = ops.convT_dgrad(dz, w, xc.shape)
+    assert rel_err(dgamma, bn.weight.grad) <= 1e-4
+    assert rel_err(dbeta, bn.bias.grad) <= 1e-4
+    if act == "prelu":
+        assert rel_err(dalpha, actm.weight.grad) <= 1e-4
+    assert rel_err(dw, conv.weight.grad) <= 1e-4
+    assert rel_err(dx, _to_frames(x.grad)) <= 1e-4
+    assert float((db.cpu() - conv.bias.grad).abs().max()) <= 1e-4 * float(dz.abs().sum(dim=(0, 1, 3)).max())
+
+
+def test_mask_layer_backward(cuda):
+    """last decoder stage: sigmoid(convT(8->1)) and the mask apply, gradient wrt the pre-sigmoid output and weights."""
+    from cruse_b200 import ops
+    torch.manual_seed(23)
+    B, T, Fin, F, NF = 2, 7, 128, 256, 257
+    conv = nn.ConvTranspose2d(8, 1, (1, 3), (1, 2))
+    x = torch.randn(B, 8, T, Fin, requires_grad=True)
+    X = torch.randn(B, T, NF, 2)
+    mask = torch.sigmoid(conv(x)[..., :F])                       # [B,1,T,F]
+    est = mask.squeeze(1).unsqueeze(-1) * X[:, :, :F]
+    gE = torch.randn(B, T, NF, 2)
+    (est * gE[:, :, :F]).sum().backward()
+    xc, w, b = _to_frames(x.detach()).to(cuda), conv.weight.detach().to(cuda), conv.bias.detach().to(cuda)
+    m = ops.convT_fwd(xc, w, b, None, None, None, "sigmoid", None, F)
+    dzc = ops.mask_bwd(gE.to(cuda), X.to(cuda), F, mask=m.view(B, T, F)).view(B, T, 1, F)
+    dw, db = ops.convT_wgrad(xc, dzc)
+    dx = ops.convT_dgrad(dzc, w, xc.shape)
+    assert rel_err(dw, conv.weight.grad) <= 1e-4
+    assert rel_err(db, conv.bias.grad) <= 1e-4
+    assert rel_err(dx, _to_frames(x.grad)) <= 1e-4
+
+
+@pytest.mark.parametrize("rows,D", [(37, 1024), (5, 704), (300, 64)])
+def test_layernorm_backward(cuda, rows, D):
+    from cruse_b200 import ops
+    torch.manual_seed(24)
+    ln = nn.LayerNorm(D)
+    ln.weight.data.uniform_(0.5, 1.5); ln.bias.data.normal_(0, 0.2)
+    x = (2 * torch.randn(rows, D) + 0.5).requires_grad_(True)
+    y = ln(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    g = ln.weight.detach().to(cuda)
+    yc, mean, rstd = ops.layernorm_fwd(x.detach().to(cuda), g, ln.bias.detach().to(cuda), ln.eps, want_stats=True)
+    assert rel_err(yc, y) <= 2e-6
+    dx, dg, db = ops.layernorm_bwd(gy.to(cuda), x.detach().to(cuda), g, mean, rstd)
+    assert rel_err(dx, x.grad) <= 1e-5
+    assert rel_err(dg, ln.weight.grad) <= 1e-5
+    assert rel_err(db, ln.bias.grad) <= 1e-5

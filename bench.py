@@ -29,7 +29,14 @@ SR, N_FFT, HOP, F_BINS = 16000, 512, 320, 256
 WORKLOADS = {
     # name: (clips per GPU, seconds per clip, description)
     "infer": (32, 10.0, "cfg2: CRUSE 4enc/4dec 256-GRU inference fwd+loss, 32x10s per GPU, n_fft512 hop320"),
+    # BASELINE configs[2] / [3]: train step = STFT + fwd (train-mode BN) + wo_male + backward (+ 1 flat grad allreduce, N>1)
+    "train": (64, 4.0, "cfg3: CRUSE train step (STFT+fwd+wo_male+bwd, no optimizer), 64x4s per GPU, n_fft512 hop320"),
 }
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/ncu_*_full.md),
+# cfg2 shapes; None where no capture exists yet
+NCU_TRAFFIC = {"gru_seq_fwd_tc": 249.8e6, "gru_seq_fwd": 269.4e6}
 
 
 def synth_batch(B, L, seed):
@@ -117,19 +124,30 @@ def run_reference(args):
     Bs = min(B_full, args.ref_clips)
     L = int(secs * SR)
     T = 1 + L // HOP
-    model = o.make_model(F_BINS).eval()
+    train = args.workload == "train"
+    model = o.make_model(F_BINS, eval_stats=not train)
+    model.train(train)
     noisy, clean = synth_batch(Bs, L, 20260)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            o.forward_loss(model, noisy, clean, N_FFT, HOP)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            loss, _, _, _ = o.forward_loss(model, noisy, clean, N_FFT, HOP)
-        dt = time.perf_counter() - t0
+
+    def cpu_step():
+        if train:
+            model.zero_grad(set_to_none=True)
+            loss = o.forward_loss(model, noisy, clean, N_FFT, HOP)[0]
+            loss.backward()
+            return loss.detach()
+        with torch.no_grad():
+            return o.forward_loss(model, noisy, clean, N_FFT, HOP)[0]
+
+    for _ in range(args.warmup):
+        cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = cpu_step()
+    dt = time.perf_counter() - t0
     fps = Bs * T * args.steps / dt
     sample = f"{Bs} of {B_full} clips x {secs:g}s per step (oracle port, torch {torch.__version__} CPU fp32)"
     line = {
-        "impl": "reference", "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE fwd+loss", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE " + ("fwd+loss+bwd" if train else "fwd+loss"), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "sample": sample},
@@ -147,17 +165,27 @@ def cpu_baseline_leg(workload, budget_s=15.0):
     B_full, secs, _ = WORKLOADS[workload]
     Bs, L = 4, int(secs * SR)
     T = 1 + L // HOP
-    model = o.make_model(F_BINS).eval()
+    train = workload == "train"
+    model = o.make_model(F_BINS, eval_stats=not train)
+    model.train(train)
     noisy, clean = synth_batch(Bs, L, 20260)
-    with torch.no_grad():
-        o.forward_loss(model, noisy, clean, N_FFT, HOP)
-        n, t0 = 0, time.perf_counter()
-        while True:
-            o.forward_loss(model, noisy, clean, N_FFT, HOP)
-            n += 1
-            dt = time.perf_counter() - t0
-            if dt > budget_s or n >= 20:
-                break
+
+    def cpu_step():
+        if train:
+            model.zero_grad(set_to_none=True)
+            o.forward_loss(model, noisy, clean, N_FFT, HOP)[0].backward()
+        else:
+            with torch.no_grad():
+                o.forward_loss(model, noisy, clean, N_FFT, HOP)
+
+    cpu_step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        cpu_step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 20:
+            break
     return {"value": Bs * T * n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{n} passes over {Bs} of {B_full} clips x {secs:g}s (oracle port, torch CPU fp32, {cores} threads)"}
 
@@ -189,15 +217,36 @@ def run_ours(args):
     torch.manual_seed(1234)
     model = unet_2(in_feat=F_BINS)
     randomise_bn(model)
-    model = model.to(dev).eval()
+    train = args.workload == "train"
+    model = model.to(dev)
+    model.train(train)
+    if train and world > 1:
+        from cruse_b200 import distrib
+        distrib.broadcast_model(model)
     noisy_h, clean_h = synth_batch(B, L, 20260 + rank)
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
     noisy, clean = noisy_h.to(dev), clean_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    params = [p for p in model.parameters()]
+
+    def run(nz, cl):
+        if not train:
+            with torch.no_grad():
+                return pipeline.forward_loss(model, nz, cl, N_FFT, HOP)[0]
+        for p in params:
+            p.grad = None
+        loss = pipeline.train_forward_loss(model, nz, cl, N_FFT, HOP)
+        loss.backward()
+        if world > 1:
+            distrib.sync_grad(params)          # the one collective of the path: flat fp32 gradient all_reduce over NCCL
+        return loss.detach()
 
     def step():
-        with torch.no_grad():
-            return pipeline.forward_loss(model, noisy, clean, N_FFT, HOP)[0]
+        return run(noisy, clean)
+
+    def step_host():
+        loss = run(noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True))
+        return loss.to("cpu")
 
     def barrier():
         if world > 1:
@@ -239,12 +288,11 @@ def run_ours(args):
 
     # ---- e2e: host buffers in, loss out, copies inside the timed region
     for _ in range(2):
-        pipeline.forward_loss_host(model, noisy_h, clean_h, N_FFT, HOP)
+        step_host()
     barrier()
     t0 = time.perf_counter()
-    with torch.no_grad():
-        for _ in range(args.steps):
-            l_host = pipeline.forward_loss_host(model, noisy_h, clean_h, N_FFT, HOP)
+    for _ in range(args.steps):
+        l_host = step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -273,16 +321,19 @@ def run_ours(args):
     step_ms_sum = sum(k["ms"] for k in kernels)
     dom = max(kernels, key=lambda k: k["ms"])
     roofline = {"kernel": f'{dom["call"]} [{dom["tag"]}]', "bound": "hbm", "achieved": dom["GBps"], "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": round(dom["GBps"] / pk["hbm_gbs"], 4), "traffic": None,
+                "unit": "GB/s", "frac": round(dom["GBps"] / pk["hbm_gbs"], 4), "traffic": NCU_TRAFFIC.get(dom["call"]),
                 "share_of_step": round(dom["ms"] / step_ms_sum, 3), "peak_source": pk["source"],
-                "note": "gru_seq is latency-bound by T sequential steps; see profiles/ for the per-kernel table"}
+                "note": "the kernel with the largest share of the step; the GRU recurrences are latency-bound by T sequential "
+                        "steps (us/step in DESIGN.md); every launch with its algorithmic GB/s and TFLOP/s is under 'kernels'"}
 
     line = {
-        "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE fwd+loss", "value": value, "unit": "frames/s", "n_gpus": world,
+        "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE " + ("fwd+loss+bwd" if train else "fwd+loss"), "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step_per_gpu": frames, "l2": "256 MB flush write between timed steps",
-                   "launch": "eager ctypes launches on torch's current stream"},
+                   "launch": "eager ctypes launches on torch's current stream",
+                   "gru_matmul_operands": "tf32 (tcgen05), fp32 accumulate; everything else fp32",
+                   "collective": ("one flat fp32 gradient all_reduce (NCCL) per step" if (train and world > 1) else "none")},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(), "loss": float(loss), "kernels": kernels,
     }
@@ -306,7 +357,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="infer", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="infer", choices=sorted(WORKLOADS),
+                    help="infer = BASELINE configs[1] (the headline, default); train = configs[2]/[3]")
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the bounded CPU sample (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", default=None, help="write the per-kernel roofline table (markdown) here")

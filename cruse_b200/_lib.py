@@ -61,8 +61,12 @@ SIGNATURES = {
     "cruse_bn_act_bwd_reduce": (c_int, [c_fp] * 5 + [c_int] + [c_fp] * 3 + [c_ll, c_int, c_int, c_fp]),
     "cruse_bn_bwd_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "cruse_bn_act_bwd_apply": (c_int, [c_fp] * 5 + [c_int] + [c_fp] * 4 + [c_ll, c_int, c_int, c_fp]),
+    "cruse_sigmoid_bwd": (c_int, [c_fp, c_fp, c_fp, c_ll, c_fp]),
     "cruse_layernorm_bwd_nparts": (c_int, [c_ll]),
     "cruse_layernorm_bwd": (c_int, [c_fp] * 7 + [c_ll, c_int, c_fp]),
+    "cruse_gru_seq_bwd_tc": (c_int, [c_fp, c_fp, c_fp, c_fp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_gemm_tn_tc": (c_int, [c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_fp]),
+    "cruse_transpose_gcm": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_int, c_ll, c_fp]),
 }
 
 _lock = threading.Lock()

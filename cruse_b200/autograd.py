@@ -1,7 +1,245 @@
-"""Backward of the hot path.  Filled in by the backward-kernel milestone."""
+"""Training path: forward with saved intermediates + backward of the U-Net on the sm_100a kernels
+(SURVEY.md section 8 row a9 -- what autograd/cuDNN do on the reference path for model/cruse_net.py:14-55,129-165).
+
+``unet2_autograd_forward(model, x)`` is what ``unet_2.forward`` calls when gradients are enabled: one
+``torch.autograd.Function`` whose inputs are the module's parameters, so ``loss.backward()``,
+optimizers and DDP see ordinary ``.grad`` tensors.  All arithmetic is in ``libcruse_sm100.so``; torch
+only sequences launches and owns the buffers.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# grouped-GRU layer
+# ------------------------------------------------------------------------------------------------
+def gru_layer_fwd_train(x2d, grus, B, T, interleave):
+    """x2d [B*T, G*H] -> (y [B,T,G*H], saved)"""
+    w_ih = [g.weight_ih_l0 for g in grus]
+    xproj = ops.gru_ih_gemm(x2d, w_ih, [g.bias_ih_l0 for g in grus], [g.bias_hh_l0 for g in grus], mode="tf32")
+    y, gates = ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
+                               interleave=interleave, mode="tf32", want_gates=True)
+    return y, (x2d, y, gates)
+
+
+def _splitk(M):
+    """K = B*T of the weight-gradient GEMMs is split so that ~all SMs get a CTA (3 m-tiles x G x splitk)."""
+    return max(1, min(16, M // 1024))
+
+
+def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True):
+    """dy [B,T,G*H] (layout of y) -> (dx [B*T, G*H] | None, {param: grad})"""
+    x2d, y, gates = saved
+    G = len(grus)
+    H = grus[0].hidden_size
+    M = B * T
+    w_ih = [g.weight_ih_l0 for g in grus]
+    w_hh = [g.weight_hh_l0 for g in grus]
+    dxproj, dpre, dbias, _ = ops.gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave)
+    dev = dy.device
+    grads = {}
+    # ---- bias gradients: xproj carried b_ih (all gates) + b_hh (r,z); W_hn.h carried b_hh (n)
+    for gi, g in enumerate(grus):
+        grads[g.bias_ih_l0] = dbias[gi, :3].reshape(3 * H)
+        grads[g.bias_hh_l0] = torch.cat([dbias[gi, 0], dbias[gi, 1], dbias[gi, 3]])
+    # ---- dx = dxproj . W_ih   ([M,3H] x [3H,H]); B operand must be K-major -> W_ih^T copies (0.75 MB each)
+    dx = None
+    if need_dx:
+        dx = torch.empty(M, G * H, device=dev, dtype=torch.float32)
+        w_t = [w.detach().t().contiguous() for w in w_ih]                       # [H, 3H]
+        ops.gemm_tn_tc([dxproj[:, gi] for gi in range(G)], w_t, [dx[:, gi * H:] for gi in range(G)],
+                       M, H, 3 * H, G * 3 * H, 3 * H, G * H)
+    # ---- weight gradients: dW_ih = dxproj^T . x, dW_hh = dpre^T . h_{t-1}; reduction index (b,t) made innermost
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    dxT = ops.transpose_gcm(dxproj, M, G, 3 * H, G * 3 * H, 3 * H, 1)           # [G, 3H, M4]
+    dpT = ops.transpose_gcm(dpre, M, G, 3 * H, G * 3 * H, 3 * H, 1)
+    xT = ops.transpose_gcm(x2d, M, G, H, G * H, H, 1)                           # [G, H, M4]
+    hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # h_{t-1}
+    M4 = dxT.shape[-1]
+    sk = _splitk(M)
+    plane = 3 * H * H
+    part = torch.empty(2, G, sk, plane, device=dev, dtype=torch.float32)
+    ops.gemm_tn_tc([dxT[gi] for gi in range(G)], [xT[gi] for gi in range(G)], [part[0, gi] for gi in range(G)],
+                   3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
+    ops.gemm_tn_tc([dpT[gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
+                   3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
+    dw = torch.empty(2, G, plane, device=dev, dtype=torch.float32)
+    for a in range(2):
+        for gi in range(G):
+            ops.colsum(part[a, gi], sk, plane, dw[a, gi])
+    for gi, g in enumerate(grus):
+        grads[g.weight_ih_l0] = dw[0, gi].view(3 * H, H)
+        grads[g.weight_hh_l0] = dw[1, gi].view(3 * H, H)
+    return dx, grads
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole U-Net
+# ------------------------------------------------------------------------------------------------
+def _bn_buffers(bn):
+    return bn.weight, bn.bias
+
+
+class _Unet2Fn(torch.autograd.Function):
+    """mag [B,T,F] -> mask [B,T,F]; differentiable w.r.t. every parameter of the module (not w.r.t. mag)."""
+
+    @staticmethod
+    def forward(ctx, model, mag, names, *params):
+        m = model
+        n = m.laynum
+        B, T, F = mag.shape
+        act = m.act_kind
+        train = m.training
+        sv = {}
+        h = mag.view(B, T, 1, F)
+        enc_in, enc_z, enc_bn, skips = [], [], [], []
+        for k in range(1, n + 1):                                                    # cruse_net.py:149-156
+            conv, bn = getattr(m, f"conv{k}"), getattr(m, f"bn{k}")
+            alpha = m._alpha(f"act{k}")
+            enc_in.append(h)
+            z, stats = ops.conv_fwd(h, conv.weight, conv.bias, None, None, None, "none", 2, 2, want_stats=True)
+            Fo = z.shape[3]
+            if train:
+                scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * Fo, bn)
+            else:
+                scale, shift = ops.bn_fold(bn)
+                mean, invstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
+            h = ops.bn_act_fwd(z, scale, shift, alpha, act)
+            enc_z.append(z)
+            enc_bn.append((scale, shift, mean, invstd))
+            skips.append(ops.conv_fwd(h, getattr(m, f"skip_connect_{k}").weight, None, None, None, None, "none", 1, 1))
+        e4 = h
+        C4, F4 = e4.shape[2], e4.shape[3]
+        D = C4 * F4
+        gru = m.gru
+        x2d = e4.view(B * T, D)
+        y1, sv1 = gru_layer_fwd_train(x2d, gru.gru_list1, B, T, True)                # :42-45
+        z1, mean1, rstd1 = ops.layernorm_fwd(y1, gru.ln1.weight, gru.ln1.bias, gru.ln1.eps, want_stats=True)
+        y2, sv2 = gru_layer_fwd_train(z1.view(B * T, D), gru.gru_list2, B, T, False)  # :48-50
+        out, mean2, rstd2 = ops.layernorm_fwd(y2, gru.ln2.weight, gru.ln2.bias, gru.ln2.eps,
+                                              residual=skips[-1].view(B, T, D), want_stats=True)   # :51,160
+        out = out.view(B, T, C4, F4)
+        dec_in, dec_z, dec_bn = [], [], []
+        for k in range(n, 1, -1):                                                    # :161-163
+            conv, bn = getattr(m, f"conv{k}_t"), getattr(m, f"bn{k}_t")
+            alpha = m._alpha(f"act{k}_t")
+            dec_in.append(out)
+            z, stats = ops.convT_fwd(out, conv.weight, conv.bias, None, None, None, "none", None, m.freqs[k - 1],
+                                     want_stats=True)
+            if train:
+                scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * m.freqs[k - 1], bn)
+            else:
+                scale, shift = ops.bn_fold(bn)
+                mean, invstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
+            out = ops.bn_act_fwd(z, scale, shift, alpha, act, skip=skips[k - 2])
+            dec_z.append(z)
+            dec_bn.append((scale, shift, mean, invstd))
+        mask = ops.convT_fwd(out, m.conv1_t.weight, m.conv1_t.bias, None, None, None, "sigmoid", None, m.freqs[0])  # :164
+        ctx.model = m
+        ctx.names = names
+        ctx.train = train
+        ctx.dims = (B, T, F, D, C4, F4)
+        ctx.sv = dict(enc_in=enc_in, enc_z=enc_z, enc_bn=enc_bn, e4=e4, sv1=sv1, y1=y1, ln1=(mean1, rstd1), sv2=sv2, y2=y2,
+                      ln2=(mean2, rstd2), dec_in=dec_in, dec_z=dec_z, dec_bn=dec_bn, d2=out, mask=mask)
+        return mask.view(B, T, F)
+
+    @staticmethod
+    def backward(ctx, dmask):
+        m, sv = ctx.model, ctx.sv
+        n = m.laynum
+        B, T, F, D, C4, F4 = ctx.dims
+        act, train = m.act_kind, ctx.train
+        G = {}                                                    # parameter tensor -> gradient
+        dmask = dmask.contiguous()
+        # ---- last decoder stage: mask = sigmoid(convT(d2))           cruse_net.py:164
+        dz = ops.sigmoid_bwd(dmask.view(B, T, 1, F), sv["mask"])
+        G[m.conv1_t.weight], G[m.conv1_t.bias] = ops.convT_wgrad(sv["d2"], dz)
+        d_out = ops.convT_dgrad(dz, m.conv1_t.weight, sv["d2"].shape)
+        # ---- decoder stages k = 2..n: out = act(BN(convT_k(in))) + skip_{k-1}       :161-163
+        dskip = [None] * n                                        # gradient w.r.t. skip_k output (index k-1)
+        for k in range(2, n + 1):
+            i = n - k                                             # position in the forward lists (k = n first)
+            conv, bn = getattr(m, f"conv{k}_t"), getattr(m, f"bn{k}_t")
+            alpha = m._alpha(f"act{k}_t")
+            scale, shift, mean, invstd = sv["dec_bn"][i]
+            z, x_in = sv["dec_z"][i], sv["dec_in"][i]
+            dskip[k - 2] = d_out
+            dzk, dgamma, dbeta, dalpha = ops.bn_act_bwd(d_out, z, scale, shift, alpha, act, mean, invstd, bn.weight,
+                                                        B * T * z.shape[3], training=train)
+            G[bn.weight], G[bn.bias] = dgamma, dbeta
+            if dalpha is not None:
+                G[getattr(m, f"act{k}_t").weight] = dalpha
+            G[conv.weight], G[conv.bias] = ops.convT_wgrad(x_in, dzk)
+            d_out = ops.convT_dgrad(dzk, conv.weight, x_in.shape)
+        dskip[n - 1] = d_out                                      # out = g + skip4     :160
+        # ---- GGRU                                                              :37-55
+        gru = m.gru
+        dgo = d_out.view(B * T, D)
+        dy2, G[gru.ln2.weight], G[gru.ln2.bias] = ops.layernorm_bwd(dgo, sv["y2"].view(B * T, D), gru.ln2.weight, *sv["ln2"])
+        dz1, g2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False)
+        G.update(g2)
+        dy1, G[gru.ln1.weight], G[gru.ln1.bias] = ops.layernorm_bwd(dz1, sv["y1"].view(B * T, D), gru.ln1.weight, *sv["ln1"])
+        de, g1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True)
+        G.update(g1)
+        de = de.view(B, T, C4, F4)
+        # ---- encoder stages k = n..1 with their skip convs                      :149-156
+        for k in range(n, 0, -1):
+            conv, bn, skipc = getattr(m, f"conv{k}"), getattr(m, f"bn{k}"), getattr(m, f"skip_connect_{k}")
+            alpha = m._alpha(f"act{k}")
+            e_k = sv["e4"] if k == n else sv["enc_in"][k]         # output of stage k = input of stage k+1
+            x_in, z = sv["enc_in"][k - 1], sv["enc_z"][k - 1]
+            scale, shift, mean, invstd = sv["enc_bn"][k - 1]
+            G[skipc.weight], _ = ops.conv_wgrad(e_k, dskip[k - 1], 1, 1, want_bias=False)
+            de = ops.conv_dgrad(dskip[k - 1], skipc.weight, e_k.shape, 1, 1, addend=de)
+            dzk, dgamma, dbeta, dalpha = ops.bn_act_bwd(de, z, scale, shift, alpha, act, mean, invstd, bn.weight,
+                                                        B * T * z.shape[3], training=train)
+            G[bn.weight], G[bn.bias] = dgamma, dbeta
+            if dalpha is not None:
+                G[getattr(m, f"act{k}").weight] = dalpha
+            G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
+            if k > 1:
+                de = ops.conv_dgrad(dzk, conv.weight, x_in.shape, 2, 2)
+        named = dict(m.named_parameters())
+        out = []
+        for nm in ctx.names:
+            g = G.get(named[nm])
+            out.append(g.reshape(named[nm].shape) if g is not None else None)
+        ctx.sv = None
+        return (None, None, None, *out)
+
+
+def unet2_frames_autograd(model, mag):
+    """mag [B,T,F] -> mask [B,T,F] with gradients to the module's parameters."""
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    params = [dict(model.named_parameters())[n] for n in names]
+    return _Unet2Fn.apply(model, mag.contiguous(), tuple(names), *params)
 
 
 def unet2_autograd_forward(model, x):
-    raise NotImplementedError(
-        "cruse_b200: the backward kernels (conv dgrad/wgrad, GRU BPTT, BN/LN backward) are not built yet; "
-        "call the model under torch.no_grad() / model.requires_grad_(False) for inference")
+    """reference surface: x [B,1,T,F] -> mask [B,1,T,F]  (model/cruse_net.py:147-165)."""
+    B, _, T, F = x.shape
+    return unet2_frames_autograd(model, x.contiguous().view(B, T, F)).view(B, 1, T, F)
+
+
+class _MaskApplyFn(torch.autograd.Function):
+    """est[b,t,f,:] = mask[b,t,f] * X[b,t,f,:] for f < F, X beyond (utils/utils.py:417-420, mag_mapping)."""
+
+    @staticmethod
+    def forward(ctx, mask, X, n_fft, hop):
+        from .acoustics import hann_window
+        est, _ = ops.mask_istft_fwd(X, mask, hann_window(n_fft, n_fft, X.device), n_fft, hop, 0, want_est=True, want_wav=False)
+        ctx.save_for_backward(X)
+        ctx.F = mask.shape[-1]
+        return est
+
+    @staticmethod
+    def backward(ctx, dest):
+        (X,) = ctx.saved_tensors
+        return ops.mask_bwd(dest.contiguous(), X, ctx.F), None, None, None
+
+
+def mask_apply(mask, X, n_fft, hop):
+    return _MaskApplyFn.apply(mask, X, n_fft, hop)

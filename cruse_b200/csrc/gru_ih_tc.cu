@@ -14,6 +14,9 @@
 // (2 x 96 KB stages, 2 x 256 TMEM columns), so one CTA's epilogue overlaps the other's main loop.
 // Out-of-range frames / k / gate rows are zero-filled by TMA and masked in the epilogue, so any M and
 // any H % 4 == 0 work (config R: H = 176).
+//
+// The same kernel is exported as a general "TN" GEMM  C[m,n] = sum_k A[m,k] B[n,k]  (both operands K-major,
+// optional split-K into partial planes) for the GRU backward: dx = dxproj . W_ih, dW = dpre^T . h (a9).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -62,17 +65,18 @@ constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTE
 constexpr int IH_THREADS = 192;
 constexpr int IH_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BN * 4 /*bias*/ + 64 /*barriers*/;
 
-struct IhMaps {
+// G independent problems  C_g[m, n] = sum_k A_g[m, k] * B_g[n, k] + bias1_g[n] + (n < bias2_rows ? bias2_g[n] : 0)
+struct GemmArgs {
     CUtensorMap a[CRUSE_MAX_GROUPS];
     CUtensorMap b[CRUSE_MAX_GROUPS];
-};
-struct IhPtrs {
-    const float* b_ih[CRUSE_MAX_GROUPS];
-    const float* b_hh[CRUSE_MAX_GROUPS];
+    const float* bias1[CRUSE_MAX_GROUPS];
+    const float* bias2[CRUSE_MAX_GROUPS];
+    float* out[CRUSE_MAX_GROUPS];
 };
 
 __global__ void __launch_bounds__(IH_THREADS)
-gru_ih_tc_kernel(const __grid_constant__ IhMaps maps, const IhPtrs ptrs, float* __restrict__ xproj, int M, int G, int H) {
+gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, long long ldc, int bias2_rows, int splitk,
+                  long long c_plane) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles: 1024-byte aligned
     uint8_t* tiles = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -83,13 +87,15 @@ gru_ih_tc_kernel(const __grid_constant__ IhMaps maps, const IhPtrs ptrs, float* 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, g = blockIdx.z;
-    const int N = 3 * H;
-    const int nkb = (H + BK - 1) / BK;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int g = blockIdx.z / splitk, split = blockIdx.z - g * splitk;
+    const int nkb_all = (K + BK - 1) / BK;
+    const int kb_begin = (int)((long long)nkb_all * split / splitk), kb_end = (int)((long long)nkb_all * (split + 1) / splitk);
+    const int nkb = kb_end - kb_begin;
 
     if (warp == 0 && lane == 0) {
-        tc::tma_prefetch_desc(&maps.a[g]);
-        tc::tma_prefetch_desc(&maps.b[g]);
+        tc::tma_prefetch_desc(&args.a[g]);
+        tc::tma_prefetch_desc(&args.b[g]);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(acc_full, 1);
         tc::fence_barrier_init();
@@ -103,59 +109,67 @@ gru_ih_tc_kernel(const __grid_constant__ IhMaps maps, const IhPtrs ptrs, float* 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                tc::mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
                 uint8_t* st = tiles + s * STAGE_BYTES;
-                tc::tma_load_2d(st, &maps.a[g], kb * BK, m0, &full[s]);
-                tc::tma_load_2d(st + A_BYTES, &maps.b[g], kb * BK, n0, &full[s]);
+                tc::tma_load_2d(st, &args.a[g], (kb_begin + i) * BK, m0, &full[s]);
+                tc::tma_load_2d(st + A_BYTES, &args.b[g], (kb_begin + i) * BK, n0, &full[s]);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, BM, BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                tc::mbar_wait(&full[s], (kb / STAGES) & 1);
-                tc::tc_fence_after();
+        // ===== MMA issuer (one elected lane of a converged warp) =====
+        constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, BM, BN);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            tc::mbar_wait(&full[s], (i / STAGES) & 1);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
                 const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {   // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
-                    tc::umma_tf32(tmem_d, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc,
-                                  (kb | k) ? 1u : 0u);
-                }
+                for (int k = 0; k < BK / 8; ++k)     // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
+                    tc::umma_tf32(tmem_d, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc, (i | k) ? 1u : 0u);
                 tc::umma_commit(&empty[s]);           // frees the stage when these MMAs have read it
             }
-            tc::umma_commit(acc_full);                // accumulator complete
+            __syncwarp();
         }
+        if (tc::elect_one()) tc::umma_commit(acc_full);   // accumulator complete
+        __syncwarp();
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int quad = warp & 3;
-        const float* bi = ptrs.b_ih[g];
-        const float* bh = ptrs.b_hh[g];
+        const float* b1 = (split == 0) ? args.bias1[g] : nullptr;
+        const float* b2 = (split == 0) ? args.bias2[g] : nullptr;
         for (int i = threadIdx.x - 64; i < BN; i += 128) {
             const int n = n0 + i;
             float b = 0.f;
-            if (n < N) b = (bi ? __ldg(bi + n) : 0.f) + ((bh && n < 2 * H) ? __ldg(bh + n) : 0.f);
+            if (n < N) b = (b1 ? __ldg(b1 + n) : 0.f) + ((b2 && n < bias2_rows) ? __ldg(b2 + n) : 0.f);
             s_bias[i] = b;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
-        tc::mbar_wait(acc_full, 0);
-        tc::tc_fence_after();
         const int m = m0 + quad * 32 + lane;
-        float* orow = xproj + ((size_t)m * G + g) * N + n0;
+        float* orow = args.out[g] + (size_t)split * c_plane + (size_t)m * ldc + n0;
+        const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(args.out[g]) & 15) == 0) && ((c_plane & 3) == 0);
+        if (nkb > 0) {
+            tc::mbar_wait(acc_full, 0);
+            tc::tc_fence_after();
+        }
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= N) break;                      // warp-uniform
             float v[32];
-            tc::tmem_ld_32x32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-            tc::tmem_ld_wait();
+            if (nkb > 0) {
+                tc::tmem_ld_32x32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
             if (m < M) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    if (n0 + c + j + 3 < N) {
+                    if (vec_ok && n0 + c + j + 3 < N) {
                         *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[j] + s_bias[c + j], v[j + 1] + s_bias[c + j + 1],
                                                                                v[j + 2] + s_bias[c + j + 2], v[j + 3] + s_bias[c + j + 3]);
                     } else {
@@ -172,6 +186,19 @@ gru_ih_tc_kernel(const __grid_constant__ IhMaps maps, const IhPtrs ptrs, float* 
     if (warp == 1) tc::tmem_dealloc<BN>(tmem_d);
 }
 
+int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int bias2_rows, int splitk, long long c_plane,
+                cudaStream_t st) {
+    for (int g = G; g < CRUSE_MAX_GROUPS; ++g) {
+        args.a[g] = args.a[0]; args.b[g] = args.b[0];
+        args.bias1[g] = nullptr; args.bias2[g] = nullptr; args.out[g] = nullptr;
+    }
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, G * splitk);
+    gemm_tn_tc_kernel<<<grid, IH_THREADS, IH_SMEM, st>>>(args, M, N, K, ldc, bias2_rows, splitk, c_plane);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 }  // namespace
 }  // namespace cruse
 
@@ -182,21 +209,35 @@ extern "C" int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, co
     CRUSE_CHECK_ARG(x && xproj && w_ih, "gru_ih_gemm_tc: null pointer");
     CRUSE_CHECK_ARG(M > 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0,
                     "gru_ih_gemm_tc: bad sizes M=%d G=%d H=%d (H%%4==0, G<=%d)", M, G, H, CRUSE_MAX_GROUPS);
-    IhMaps maps;
-    IhPtrs ptrs;
-    for (int g = 0; g < CRUSE_MAX_GROUPS; ++g) { ptrs.b_ih[g] = nullptr; ptrs.b_hh[g] = nullptr; }
+    GemmArgs args;
     for (int g = 0; g < G; ++g) {
         CRUSE_CHECK_ARG(w_ih[g], "gru_ih_gemm_tc: null weight pointer for group %d", g);
         // A: this group's H columns of x (row pitch G*H floats); B: weight_ih_l0 [3H, H]
-        if (int rc = make_tmap_2d(&maps.a[g], x + (size_t)g * H, (uint64_t)M, (uint64_t)H, (uint64_t)G * H * 4, BM, true)) return rc;
-        if (int rc = make_tmap_2d(&maps.b[g], w_ih[g], (uint64_t)3 * H, (uint64_t)H, (uint64_t)H * 4, BN, true)) return rc;
-        ptrs.b_ih[g] = b_ih ? b_ih[g] : nullptr;
-        ptrs.b_hh[g] = b_hh ? b_hh[g] : nullptr;
+        if (int rc = make_tmap_2d(&args.a[g], x + (size_t)g * H, (uint64_t)M, (uint64_t)H, (uint64_t)G * H * 4, BM, true)) return rc;
+        if (int rc = make_tmap_2d(&args.b[g], w_ih[g], (uint64_t)3 * H, (uint64_t)H, (uint64_t)H * 4, BN, true)) return rc;
+        args.bias1[g] = b_ih ? b_ih[g] : nullptr;
+        args.bias2[g] = b_hh ? b_hh[g] : nullptr;
+        args.out[g] = xproj + (size_t)g * 3 * H;
     }
-    for (int g = G; g < CRUSE_MAX_GROUPS; ++g) { maps.a[g] = maps.a[0]; maps.b[g] = maps.b[0]; }
-    CRUSE_CUDA_OK(cudaFuncSetAttribute(gru_ih_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
-    dim3 grid((3 * H + BN - 1) / BN, (M + BM - 1) / BM, G);
-    gru_ih_tc_kernel<<<grid, IH_THREADS, IH_SMEM, (cudaStream_t)stream>>>(maps, ptrs, xproj, M, G, H);
-    CRUSE_LAUNCH_OK();
-    return 0;
+    return launch_gemm(args, G, M, 3 * H, H, (long long)G * 3 * H, 2 * H, 1, 0, (cudaStream_t)stream);
+}
+
+extern "C" int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C, int G,
+                                int M, int N, int K, long long lda, long long ldb, long long ldc, int splitk,
+                                long long c_plane, void* stream) {
+    CRUSE_CHECK_ARG(A && Bm && C, "gemm_tn_tc: null pointer table");
+    CRUSE_CHECK_ARG(G > 0 && G <= CRUSE_MAX_GROUPS && M > 0 && N > 0 && K > 0 && splitk >= 1 && splitk <= 64,
+                    "gemm_tn_tc: bad sizes G=%d M=%d N=%d K=%d splitk=%d", G, M, N, K, splitk);
+    CRUSE_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0 && lda >= K && ldb >= K && ldc >= N, "gemm_tn_tc: bad pitches lda=%lld ldb=%lld ldc=%lld", lda, ldb, ldc);
+    CRUSE_CHECK_ARG(splitk == 1 || (bias == nullptr && c_plane >= (long long)M * ldc), "gemm_tn_tc: split-K needs bias == NULL and c_plane >= M*ldc");
+    GemmArgs args;
+    for (int g = 0; g < G; ++g) {
+        CRUSE_CHECK_ARG(A[g] && Bm[g] && C[g], "gemm_tn_tc: null pointer for problem %d", g);
+        if (int rc = make_tmap_2d(&args.a[g], A[g], (uint64_t)M, (uint64_t)K, (uint64_t)lda * 4, BM, true)) return rc;
+        if (int rc = make_tmap_2d(&args.b[g], Bm[g], (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, BN, true)) return rc;
+        args.bias1[g] = bias ? bias[g] : nullptr;
+        args.bias2[g] = nullptr;
+        args.out[g] = C[g];
+    }
+    return launch_gemm(args, G, M, N, K, ldc, 0, splitk, c_plane, (cudaStream_t)stream);
 }

@@ -209,6 +209,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) o[i] = s_part[i];
 }
 
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float s = __ldg(y + i);
+        dz[i] = __ldg(dy + i) * s * (1.f - s);
+    }
+}
+
 static int nb_grid(long long n_frames) {
     long long g = (long long)sm_count() * 4;
     if (g > n_frames) g = n_frames;
@@ -268,6 +275,16 @@ extern "C" int cruse_bn_act_bwd_apply(const float* dy, const float* z, const flo
         bn_act_bwd_kernel<4, true><<<(int)g, NB_THREADS, 0, st>>>(dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, nullptr, n_frames, C, F);
     else
         bn_act_bwd_kernel<1, true><<<(int)g, NB_THREADS, 0, st>>>(dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, nullptr, n_frames, C, F);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_sigmoid_bwd(const float* dy, const float* y, float* dz, long long n, void* stream) {
+    CRUSE_CHECK_ARG(dy && y && dz && n > 0, "sigmoid_bwd: bad arguments");
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    sigmoid_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -1,0 +1,57 @@
+"""Data-parallel plumbing of the hot path (SURVEY.md section 8 rows a10 / e).
+
+The batch axis shards across ranks with no data-path collective; the ONE exchange per training step is the
+gradient average.  ``sync_grad`` keeps the semantics of the reference's ``loss_func/distrib.py:100-116``
+(all_reduce SUM then divide by world size, parameters without a gradient are skipped) but issues a single
+collective on one flat fp32 buffer (12.9 MB at config B) instead of one per parameter: over NCCL / NVLink 5 that
+is one launch whose cost is latency, not bandwidth.  ``broadcast_model`` mirrors ``broadcast_tensors``
+(``distrib.py:57-72``).  Backend-agnostic: NCCL on the GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+
+
+def is_distributed(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def sync_grad(params, group=None):
+    """average ``p.grad`` over all ranks with ONE all_reduce (loss_func/distrib.py:100-116 semantics)."""
+    if not is_distributed(group):
+        return None
+    ps = [p for p in params if p.grad is not None]
+    if not ps:
+        return None
+    flat = _flatten_dense_tensors([p.grad.data for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world_size(group))
+    for p, g in zip(ps, _unflatten_dense_tensors(flat, [p.grad.data for p in ps])):
+        p.grad.data.copy_(g)
+    return flat.numel() * flat.element_size()
+
+
+def broadcast_model(model, src=0, group=None):
+    """rank ``src``'s parameters and buffers to everybody (start-of-training sync, distrib.py:57-72)."""
+    if not is_distributed(group):
+        return
+    tensors = [t.data for t in list(model.parameters()) + list(model.buffers()) if torch.is_floating_point(t)]
+    flat = _flatten_dense_tensors(tensors)
+    dist.broadcast(flat, src=src, group=group)
+    for t, v in zip(tensors, _unflatten_dense_tensors(flat, tensors)):
+        t.copy_(v)
+
+
+def shard_batch(n_items: int, rank: int, world: int):
+    """contiguous shard [lo, hi) of a batch axis (bench / tests; the reference's DistributedSampler strides instead,
+    tools/train_stand.py:48-51 -- either is a partition, the path has no cross-sample op besides BN statistics,
+    which stay per replica as in the reference)."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)

@@ -15,12 +15,14 @@ from . import ops
 
 class _WoMale(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ref, est, unproc, layout):
+    def forward(ctx, ref, est, unproc, layout, nbins=None):
         lay = ops.layout_bctf if layout == "bctf" else ops.layout_btf2
         if layout == "bctf":
             B, _, T, F = est.shape
         else:
             B, T, F, _ = est.shape
+        if nbins is not None:
+            F = nbins                      # loss over bins [0, nbins) only; the gradient of the other bins is 0
         need = est.requires_grad
         ref_c, est_c, unp_c = ref.contiguous(), est.contiguous(), unproc.contiguous()
         loss, dest = ops.wo_male_fwd_bwd(ref_c, lay(ref_c), est_c, lay(est_c), unp_c, lay(unp_c), B, T, F,
@@ -31,7 +33,7 @@ class _WoMale(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dest,) = ctx.saved_tensors
-        return None, (dest * g if dest is not None else None), None, None
+        return None, (dest * g if dest is not None else None), None, None, None
 
 
 def wo_male(ref, est, unproc, norm=False, eps=1e-8):
@@ -49,6 +51,11 @@ def wo_male_frames(ref, est, unproc, F):
     loss, _ = ops.wo_male_fwd_bwd(ref, ops.layout_btf2(ref), est, ops.layout_btf2(est), unproc,
                                   ops.layout_btf2(unproc), B, T, F, want_grad=False)
     return loss
+
+
+def wo_male_frames_autograd(ref, est, unproc, F):
+    """wo_male on interleaved spectra [B,T,NF,2] over bins [0,F), differentiable w.r.t. est (training path)."""
+    return _WoMale.apply(ref, est, unproc, "btf2", F)
 
 
 def wo_male_loss():

@@ -355,6 +355,12 @@ def _ws(nbytes, device):
     return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32)
 
 
+def colsum(ws, nparts, n, out, accumulate=False):
+    """out[j] (+)= sum_p ws[p*n + j]"""
+    _call("cruse_colsum", _p(ws), nparts, n, _p(out), 1 if accumulate else 0, _stream())
+    return out
+
+
 def conv_dgrad(dz, w, in_shape, kt, fstride, addend=None):
     """data gradient of conv_fwd: dz [B,T,Cout,Fout] -> din [B,T,Cin,Fin] (+ addend)."""
     _req(dz, "dz", 4)
@@ -445,3 +451,56 @@ def layernorm_bwd(dy, x, gamma, mean, rstd):
     dgb = torch.empty(2 * D, device=x.device, dtype=torch.float32)
     _call("cruse_colsum", _p(partials), nparts, 2 * D, _p(dgb), 0, _stream())
     return dx, dgb[:D], dgb[D:]
+
+
+def gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave, h0=None, want_dh0=False):
+    """BPTT of one grouped-GRU layer -> (dxproj [B*T,G,3H], dpre [B*T,G,3H], dbias [G,4,H] = sums of (da_r,da_z,da_n,dhn),
+    dh0 [G,B,H] | None)."""
+    _req(dy, "dy", 3)
+    _req(y, "y", 3)
+    _req(gates, "gates", 5)
+    _req(h0, "h0")
+    G = len(w_hh)
+    H = w_hh[0].shape[1]
+    if tuple(gates.shape) != (B, T, G, 4, H) or tuple(y.shape) != (B, T, G * H) or tuple(dy.shape) != (B, T, G * H):
+        raise RuntimeError(f"gru_seq_bwd: shapes dy {tuple(dy.shape)} y {tuple(y.shape)} gates {tuple(gates.shape)} vs B={B} T={T} G={G} H={H}")
+    dxproj = torch.empty(B * T, G, 3 * H, device=y.device, dtype=torch.float32)
+    dpre = torch.empty_like(dxproj)
+    dh0 = torch.empty(G, B, H, device=y.device, dtype=torch.float32) if want_dh0 else None
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    tw = _ptr_table(w_hh)
+    nsl = (B + 15) // 16
+    dbp = torch.zeros(nsl, G * 4 * H, device=y.device, dtype=torch.float32)
+    _call("cruse_gru_seq_bwd_tc", _p(dy), _p(y), _p(gates), _p(h0), tw, _p(dxproj), _p(dpre), _p(dh0), _p(dbp), B, T, G, H,
+          y_fs, y_gs, _stream(),
+          meta=(f"gru_seq_bwd[tf32] G{G} H{H} T{T}", _nb(dy, y, gates, dxproj, dpre, *w_hh), 2 * B * T * G * H * 3 * H))
+    dbias = torch.empty(G * 4 * H, device=y.device, dtype=torch.float32)
+    _call("cruse_colsum", _p(dbp), nsl, G * 4 * H, _p(dbias), 0, _stream())
+    return dxproj, dpre, dbias.view(G, 4, H), dh0
+
+
+def transpose_gcm(x, M, G, Cn, ld, gs, cs, shift_T=0, h0=None, Bn=0):
+    """out[g][c][m] = x[m*ld + g*gs + c*cs] (row pitch = M rounded up to 4 floats for TMA); with shift_T the source
+    row is m-1 (t == 0 -> h0 or 0)."""
+    M4 = (M + 3) // 4 * 4
+    out = torch.empty(G, Cn, M4, device=x.device, dtype=torch.float32)
+    _call("cruse_transpose_gcm", _p(x), _p(h0), _p(out), M, G, Cn, ld, gs, cs, shift_T, Bn, M4, _stream(),
+          meta=(f"transpose G{G} C{Cn}", 2 * G * Cn * M * 4, 0))
+    return out
+
+
+def gemm_tn_tc(A, Bm, C, M, N, K, lda, ldb, ldc, bias=None, splitk=1, c_plane=0):
+    """G GEMMs C_g[m,n] = sum_k A_g[m,k] B_g[n,k] (+bias_g[n]); A/Bm/C/bias: lists of tensors (views allowed: only
+    data_ptr and the given pitches are used)."""
+    G = len(A)
+    ta, tb, tcs, tbias = _ptr_table(A), _ptr_table(Bm), _ptr_table(C), _ptr_table(bias)
+    _call("cruse_gemm_tn_tc", ta, tb, tbias, tcs, G, M, N, K, lda, ldb, ldc, splitk, c_plane, _stream(),
+          meta=(f"gemm_tn[tf32] G{G} {M}x{N}x{K} splitk{splitk}", 4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
+
+
+def sigmoid_bwd(dy, y):
+    _req(dy, "dy")
+    _req(y, "y")
+    dz = torch.empty_like(y)
+    _call("cruse_sigmoid_bwd", _p(dy), _p(y), _p(dz), y.numel(), _stream(), meta=("sigmoid_bwd", _nb(dy, y, dz), 3 * y.numel()))
+    return dz

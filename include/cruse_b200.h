@@ -190,11 +190,36 @@ int cruse_bn_act_bwd_apply(const float* dy, const float* z, const float* scale, 
                            int act, const float* mean, const float* invstd, const float* coef, float* dz,
                            long long n_frames, int C, int F, void* stream);
 
+/* dz = dy * y * (1 - y): backward of the mask sigmoid (model/cruse_net.py:164) given its output y */
+int cruse_sigmoid_bwd(const float* dy, const float* y, float* dz, long long n, void* stream);
+
 /* nn.LayerNorm backward.  x, dy, dx [rows, D]; mean/rstd [rows] from cruse_layernorm_fwd.
  * partials [cruse_layernorm_bwd_nparts(rows)][2*D] = per-CTA { dgamma, dbeta }; reduce with cruse_colsum. */
 int cruse_layernorm_bwd_nparts(long long rows);
 int cruse_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                         float* dx, float* partials, long long rows, int D, void* stream);
+
+/* grouped-GRU backpropagation through time (cuDNN RNN backward on the reference path, model/cruse_net.py:23-31,43-50).
+ *  dy [B,T,G*H]: gradient w.r.t. the layer output, addressed like y (y_fs, y_gs); y: the forward output (h_t);
+ *  gates [B,T,G,4,H] from cruse_gru_seq_fwd_tc; h0 [G,B,H] or NULL.
+ *  dxproj [B,T,G,3H] = (da_r, da_z, da_n): gradient of the input projections (and of b_ih; its r,z part also of b_hh);
+ *  dpre   [B,T,G,3H] = (da_r, da_z, dhn):  gradient of W_hh.h + b_hh;  dh0 [G,B,H] or NULL.
+ *  dbias_part [ceil(B/16), G, 4, H] or NULL, ZERO-INITIALISED by the caller: per-utterance-slice sums over t of
+ *  (da_r, da_z, da_n, dhn); column-sum over the first dim gives db_ih = (r,z,n) and db_hh = (r,z,hn). */
+int cruse_gru_seq_bwd_tc(const float* dy, const float* y, const float* gates, const float* h0,
+                         const float* const* w_hh, float* dxproj, float* dpre, float* dh0, float* dbias_part,
+                         int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
+/* G independent GEMMs on tcgen05 (tf32 operands, fp32 accumulate):  C_g[m,n] = sum_k A_g[m,k] * B_g[n,k] (+ bias_g[n]).
+ * A_g [M,K] row pitch lda, B_g [N,K] row pitch ldb (both K-major), C_g row pitch ldc (floats).  splitk > 1 writes
+ * splitk partial planes C_g + s*c_plane (bias must be NULL); sum them with cruse_colsum.
+ * Used for dx = dxproj . W_ih and dW = dpre^T . h of the GRU backward. */
+int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C,
+                     int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                     int splitk, long long c_plane, void* stream);
+/* out[(g*Cn + c)*ldo + m] = in[m*ld + g*gs + c*cs] (m < M, c < Cn): puts the (b,t) index innermost for the weight-gradient
+ * GEMMs.  shift_T > 0: row m = b*shift_T + t reads row m-1 (h_{t-1} from y) and t == 0 reads h0[g][b][c] (or 0 if NULL; Bn = B). */
+int cruse_transpose_gcm(const float* in, const float* h0, float* out, long long M, int G, int Cn,
+                        long long ld, long long gs, long long cs, int shift_T, int Bn, long long ldo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,13 @@
 
 namespace cruse {
 
+// conv_tc.cu: tensor-core (tcgen05) implicit-GEMM instantiations for the 256-bin pyramid in eval mode
+int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
+                cudaStream_t st);
+int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                 int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
+
 constexpr int CONV_TT = 8;    // frames per CTA
 constexpr int CONV_COT = 4;   // output channels per thread
 constexpr int CONV_THREADS = 256;
@@ -410,10 +417,14 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
     CRUSE_CHECK_ARG(Fout == expF, "conv_fwd: Fout=%d, expected %d", Fout, expF);
     CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd: scale and shift go together");
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd: PReLU needs alpha");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!hist && !stats_ws) {     // eval-mode stage of the 256-bin pyramid: tcgen05 implicit GEMM (conv_tc.cu)
+        const int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st);
+        if (rc) return rc < 0 ? rc : 0;
+    }
     const size_t smem = conv_smem_bytes(kt, Cin, Fin, Cout);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_fwd: stage (Cin=%d,Fin=%d,Cout=%d) needs %zu B shared memory", Cin, Fin, Cout, smem);
     const int grid = cruse_conv_nparts(B, T);
-    cudaStream_t st = (cudaStream_t)stream;
     if (kt == 2) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_fwd_kernel<2, 2><<<grid, CONV_THREADS, smem, st>>>(in, hist, w, bias, scale, shift, alpha, act, nullptr, out, stats_ws, T, Cin, Fin, Cout, Fout, 1, 0);
@@ -433,6 +444,10 @@ extern "C" int cruse_convT_fwd(const float* in, const float* w, const float* bia
     CRUSE_CHECK_ARG(Fout > 0 && Fout <= 2 * Fin + 1, "convT_fwd: Fout=%d must be in (0, 2*Fin+1=%d]", Fout, 2 * Fin + 1);
     CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "convT_fwd: scale and shift go together");
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "convT_fwd: PReLU needs alpha");
+    if (!stats_ws) {
+        const int rc = convT_tc_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        if (rc) return rc < 0 ? rc : 0;
+    }
     const int CoutP = (Cout + CONV_COT - 1) / CONV_COT * CONV_COT;
     const size_t smem = sizeof(float) * ((((size_t)CONV_TT * Cin * (Fin + 2) + 3) & ~(size_t)3) + (size_t)Cin * 3 * CoutP + 2 * (size_t)Cout);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "convT_fwd: stage needs %zu B shared memory", smem);

@@ -1,0 +1,448 @@
+// conv_tc.cu -- the conv / skip-conv / transposed-conv stages of the U-Net as implicit GEMMs on the
+// 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in tensor memory).
+//
+// Replaces, for the 256-bin pyramid in eval mode, the CUDA-core kernels of conv.cu behind the same C ABI
+// (cruse_conv_fwd / cruse_convT_fwd): nn.Conv2d((2,3), stride (1,2), pad (1,1)) + "[..., :-1, :]" +
+// folded BatchNorm2d + act (model/cruse_net.py:138,141,149-152), the (1,3) skip convs (:143,153-156) and
+// nn.ConvTranspose2d((1,3), stride (1,2)) + "[..., :-1]" + BatchNorm2d + act + skip add (:161-163).
+//
+// GEMM view.  Activations stay frame-major [B, T, C, F].  One M tile = 128 output positions = TF = 128/FO
+// consecutive frames x FO bins of one utterance; N = Cout (conv) or (Cout, even/odd output bin) (convT);
+// K = (frequency tap, input channel), the two time taps of the causal encoder convs are NOT materialised:
+// the A tile holds TF+1 frames and the kt = 1 tap is the same shared-memory tile addressed FO rows further
+// down (a descriptor offset, FO*128 bytes, a multiple of the 1024-byte swizzle atom).
+//
+// Data movement.  HBM -> registers with coalesced 8-byte (stride-2 stages) / 4-byte loads, every input
+// element read ONCE per tile; the frequency taps of a row are the lane's own values plus one
+// warp shuffle from the neighbouring bin; registers -> shared memory directly in the K-major
+// SWIZZLE_128B layout the UMMA descriptors address (lane = 16 rows x 2 channel pairs, so each 8-byte
+// store instruction is bank-conflict free), fp32 -> tf32 rounded (cvt.rna) on the way.  Weights are re-laid
+// once per CTA into the same layout and stay resident.  No im2col buffer ever exists in HBM.
+//
+// Pipeline (persistent CTA, one per SM): 2 x 8 producer warps alternate over the ring of A-tile groups
+// (all loads of a group are in flight before the ring slot is waited for), one warp issues the MMAs
+// (elect.one) and recycles ring slots with tcgen05.commit, four warps run the epilogue out of a
+// double-buffered TMEM accumulator (tcgen05.ld -> + bias, folded BN, act, + skip -> global), so loads,
+// tensor math and stores of consecutive tiles overlap.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace cruse {
+namespace {
+
+constexpr int CT_NPW = 8;                                  // producer warps per set
+constexpr int CT_SETS = 2;                                 // producer sets, alternating over A-tile groups
+constexpr int CT_PROD_WARPS = CT_NPW * CT_SETS;
+constexpr int CT_MMA_WARP = CT_PROD_WARPS;
+constexpr int CT_EPI_WARP0 = CT_PROD_WARPS + 1;
+constexpr int CT_EPI_WARPS = 8;                            // two per TMEM lane quadrant, splitting the accumulator columns
+constexpr int CT_THREADS = (CT_PROD_WARPS + 1 + CT_EPI_WARPS) * 32;   // 800
+constexpr int CT_SMEM_BUDGET = 222 * 1024;
+
+struct ConvTcArgs {
+    const float* in;
+    const float* w;
+    const float* bias;
+    const float* scale;
+    const float* shift;
+    const float* alpha;
+    const float* addend;
+    float* out;
+    int B, T, act;
+};
+
+// MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
+// to 2*FO bins (FO = input bins).
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO>
+struct ConvTcCfg {
+    static constexpr int TAPS = MODE == 0 ? 3 : 2;                 // conv: kf = 0,1,2; convT: {x[i], x[i-1]}
+    static constexpr int N = MODE == 0 ? COUT : 2 * COUT;
+    static constexpr int NPAD = N < 16 ? 16 : N;                   // UMMA M=128 needs N % 16 == 0
+    static constexpr int TF = 128 / FO;                            // frames per tile
+    static constexpr int NFR = TF + KT - 1;                        // frames held by one A slot
+    static constexpr int SR = NFR * FO;                            // rows per slot
+    static constexpr int SLOT_BYTES = SR * 128;
+    static constexpr int CB = CIN < 32 ? CIN : 32;                 // input channels per group
+    static constexpr int NG = CIN / CB;                            // groups per tile
+    static constexpr int KG = TAPS * CB;                           // K per group
+    static constexpr int S = (KG + 31) / 32;                       // slots (32-float K blocks) per group
+    static constexpr int GROUP_BYTES = S * SLOT_BYTES;
+    static constexpr int NKB = NG * S * KT;                        // weight K blocks
+    static constexpr int B_BYTES = NKB * NPAD * 128;
+    static constexpr int FIN = MODE == 0 ? SF * FO : FO;
+    static constexpr int RD_FIT = (CT_SMEM_BUDGET - B_BYTES - 2048) / GROUP_BYTES;
+    static constexpr int RD = RD_FIT > 4 ? 4 : RD_FIT;             // ring depth (groups)
+    static constexpr int ITEMS = NFR * (CB / 4) * (FO / 16);       // (frame, 4 channels, 16 rows) patches per group
+    static constexpr int NIT = ITEMS / CT_NPW;
+    static constexpr int TMEM_COLS = 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : 128);
+    static constexpr int SMEM = 1024 + RD * GROUP_BYTES + B_BYTES + COUT * 16 + 256;
+    static_assert(128 % FO == 0 && FO % 16 == 0, "FO must divide 128 and be a multiple of 16");
+    static_assert(CIN % 4 == 0 && CIN % CB == 0, "channel blocking");
+    static_assert(ITEMS % CT_NPW == 0, "producer items must split evenly over the warps of a set");
+    static_assert(RD >= 2, "ring needs two groups");
+    static_assert(NPAD % 16 == 0 && NPAD <= 64, "N tile");
+    static_assert(MODE == 0 || (KT == 1 && SF == 1), "convT instantiation");
+};
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {   // this warp's 32 lanes x 16 columns
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO>
+__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
+    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms are 1024-byte aligned
+    uint8_t* ring = smem_raw + (base - tc::smem_u32(smem_raw));
+    uint8_t* sB = ring + C::RD * C::GROUP_BYTES;
+    float4* s_par = reinterpret_cast<float4*>(sB + C::B_BYTES);                // per channel: scale, bias*scale + shift, alpha
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_par + COUT);
+    uint64_t* empty = full + 4;
+    uint64_t* acc_full = empty + 4;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.T;
+    const int chunks = (T + C::TF - 1) / C::TF;
+    const int ntiles = a.B * chunks;
+
+    // ---- one-time setup: barriers, TMEM, weights in UMMA layout, epilogue parameters
+    if (tid == 0) {
+        for (int i = 0; i < C::RD; ++i) { tc::mbar_init(&full[i], CT_NPW * 32); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], CT_EPI_WARPS * 32); }
+        tc::fence_barrier_init();
+    }
+    if (warp == CT_MMA_WARP) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    {
+        constexpr int WTOT = C::NKB * C::NPAD * 32, WU = 8;
+        for (int i0 = tid; i0 < WTOT; i0 += CT_THREADS * WU) {
+            float wv[WU];
+#pragma unroll
+            for (int u = 0; u < WU; ++u) {            // WU independent loads in flight per thread
+                const int i = i0 + u * CT_THREADS;
+                const int kk = i & 31, n = (i >> 5) % C::NPAD, kbi = (i >> 5) / C::NPAD;
+                const int kt = kbi % KT, gs = kbi / KT, s = gs % C::S, g = gs / C::S;
+                const int k = s * 32 + kk;                       // K index inside the group: tap * CB + channel
+                float v = 0.f;
+                if (i < WTOT && k < C::KG && n < C::N) {
+                    const int tap = k / C::CB, ci = g * C::CB + (k - tap * C::CB);
+                    if (MODE == 0) {
+                        v = __ldg(a.w + (((size_t)n * CIN + ci) * KT + kt) * 3 + tap);                 // Conv2d [Cout][Cin][KT][3]
+                    } else {
+                        const int co = n >> 1, ph = n & 1;                                            // ConvTranspose2d [Cin][Cout][1][3]
+                        // out[2i] = W[..,0] x[i] + W[..,2] x[i-1];  out[2i+1] = W[..,1] x[i]
+                        if (tap == 0) v = __ldg(a.w + ((size_t)ci * COUT + co) * 3 + ph);
+                        else if (ph == 0) v = __ldg(a.w + ((size_t)ci * COUT + co) * 3 + 2);
+                    }
+                }
+                wv[u] = v;
+            }
+#pragma unroll
+            for (int u = 0; u < WU; ++u) {
+                const int i = i0 + u * CT_THREADS;
+                if (i < WTOT) {
+                    const int kk = i & 31, n = (i >> 5) % C::NPAD, kbi = (i >> 5) / C::NPAD;
+                    const uint32_t off = (uint32_t)kbi * (C::NPAD * 128) + (uint32_t)(n >> 3) * 1024 + (uint32_t)(n & 7) * 128 +
+                                         (uint32_t)(((kk >> 2) ^ (n & 7)) << 4) + (uint32_t)(kk & 3) * 4;
+                    *reinterpret_cast<uint32_t*>(sB + off) = f32_to_tf32(wv[u]);
+                }
+            }
+        }
+    }
+    // K padding inside a slot (CIN = 8: 24 of 32) is never written by the producers: zero the ring once
+    if (C::KG % 32 != 0)
+        for (int i = tid; i < C::RD * C::GROUP_BYTES / 16; i += CT_THREADS) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < COUT; i += CT_THREADS) {
+        const float bi = a.bias ? __ldg(a.bias + i) : 0.f, sc = a.scale ? __ldg(a.scale + i) : 1.f, sh = a.shift ? __ldg(a.shift + i) : 0.f;
+        s_par[i] = make_float4(sc, fmaf(bi, sc, sh), a.alpha ? __ldg(a.alpha + i) : 0.f, 0.f);
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp < CT_PROD_WARPS) {
+        // ================= producers: HBM -> registers -> swizzled K-major A tiles =================
+        const int set = warp / CT_NPW, wq = warp % CT_NPW;
+        // lane -> (row of a 16-row patch, channel pair of a 4-channel chunk): one 8-byte load instruction covers
+        // 2 channels x 16 bins (two full 128-byte lines when SF == 2), one 8-byte store instruction is conflict free
+        // (per half warp: 8 row phases x 2 channel pairs = 16 distinct 8-byte bank pairs of the swizzled tile)
+        const int row16 = lane >> 1, ep = lane & 1;
+        int j = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b = tile / chunks, t0 = (tile - b * chunks) * C::TF;
+#pragma unroll 1
+            for (int g = 0; g < C::NG; ++g, ++j) {
+                if ((j % CT_SETS) != set) continue;
+                constexpr int NV = (MODE == 0 && SF == 2) ? 2 : 1;
+                float va[C::NIT][NV], vb[C::NIT][NV], ea[C::NIT], eb[C::NIT];     // channel ci0 / ci0+1: values, edge value
+#pragma unroll
+                for (int it = 0; it < C::NIT; ++it) {
+                    const int item = it * CT_NPW + wq;
+                    const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
+                    const int t = t0 - (KT - 1) + fr;
+                    const bool valid = (t >= 0) && (t < T);
+                    const int fo = fg * 16 + row16, ci0 = g * C::CB + cg * 4 + 2 * ep;
+                    const float* src = a.in + (((size_t)b * T + t) * CIN + ci0) * C::FIN + (MODE == 0 ? SF : 1) * fo;
+#pragma unroll
+                    for (int q = 0; q < NV; ++q) { va[it][q] = 0.f; vb[it][q] = 0.f; }
+                    ea[it] = 0.f; eb[it] = 0.f;
+                    if (valid) {
+                        if (MODE == 0 && SF == 2) {
+                            const float2 p = __ldg(reinterpret_cast<const float2*>(src));
+                            const float2 q = __ldg(reinterpret_cast<const float2*>(src + C::FIN));
+                            va[it][0] = p.x; va[it][NV - 1] = p.y; vb[it][0] = q.x; vb[it][NV - 1] = q.y;
+                        } else {
+                            va[it][0] = __ldg(src);
+                            vb[it][0] = __ldg(src + C::FIN);
+                        }
+                        if (row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
+                        if (MODE == 0 && SF == 1 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
+                    }
+                }
+                const int r = j % C::RD;
+                tc::mbar_wait(&empty[r], ((j / C::RD) & 1) ^ 1);
+                uint8_t* grp = ring + r * C::GROUP_BYTES;
+#pragma unroll
+                for (int it = 0; it < C::NIT; ++it) {
+                    const int item = it * CT_NPW + wq;
+                    const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
+                    const int row = fr * FO + fg * 16 + row16;
+                    float ta[3], tb[3];
+                    if (MODE == 0 && SF == 2) {          // taps read bins 2fo-1, 2fo, 2fo+1
+                        float la = __shfl_up_sync(0xffffffffu, va[it][NV - 1], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][NV - 1], 2);
+                        if (row16 == 0) { la = ea[it]; lb = eb[it]; }
+                        ta[0] = la; ta[1] = va[it][0]; ta[2] = va[it][NV - 1];
+                        tb[0] = lb; tb[1] = vb[it][0]; tb[2] = vb[it][NV - 1];
+                    } else if (MODE == 0) {              // taps read bins fo-1, fo, fo+1
+                        float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
+                        float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
+                        if (row16 == 0) { la = ea[it]; lb = eb[it]; }
+                        if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
+                        ta[0] = la; ta[1] = va[it][0]; ta[2] = ra;
+                        tb[0] = lb; tb[1] = vb[it][0]; tb[2] = rb;
+                    } else {                             // convT: K taps = x[i], x[i-1]
+                        float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
+                        if (row16 == 0) { la = ea[it]; lb = eb[it]; }
+                        ta[0] = va[it][0]; ta[1] = la; ta[2] = 0.f;
+                        tb[0] = vb[it][0]; tb[1] = lb; tb[2] = 0.f;
+                    }
+                    uint8_t* rowp = grp + (row >> 3) * 1024 + (row16 & 7) * 128 + ep * 8;     // row & 7 == row16 & 7
+#pragma unroll
+                    for (int tap = 0; tap < C::TAPS; ++tap) {
+                        const int k = tap * C::CB + cg * 4;                                   // + 2*ep (+1)
+                        const int slot = k >> 5, ch = (k & 31) >> 2;
+                        *reinterpret_cast<uint2*>(rowp + slot * C::SLOT_BYTES + ((ch ^ (row16 & 7)) << 4)) =
+                            make_uint2(f32_to_tf32(ta[tap]), f32_to_tf32(tb[tap]));
+                    }
+                }
+                tc::fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                tc::mbar_arrive(&full[r]);
+            }
+        }
+    } else if (warp == CT_MMA_WARP) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, 128, C::NPAD);
+        const uint32_t sB_u32 = base + C::RD * C::GROUP_BYTES;
+        int j = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int ab = lt & 1;
+            tc::mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d = tmem_d + (uint32_t)(ab * C::NPAD);
+#pragma unroll 1
+            for (int g = 0; g < C::NG; ++g, ++j) {
+                const int r = j % C::RD;
+                tc::mbar_wait(&full[r], (j / C::RD) & 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t ga = base + r * C::GROUP_BYTES;
+#pragma unroll
+                    for (int s = 0; s < C::S; ++s) {
+                        const int kvalid = (C::KG - 32 * s) < 32 ? (C::KG - 32 * s) : 32;
+                        const int ksteps = (kvalid + 7) / 8;
+#pragma unroll
+                        for (int kt = 0; kt < KT; ++kt) {
+                            const uint32_t sa = ga + s * C::SLOT_BYTES + kt * (FO * 128);
+                            const uint32_t sb = sB_u32 + (uint32_t)(((g * C::S + s) * KT + kt) * (C::NPAD * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps)
+                                    tc::umma_tf32(d, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc,
+                                                  (g | s | kt | k) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    tc::umma_commit(&empty[r]);                     // ring slot free once these MMAs have read it
+                    if (g == C::NG - 1) tc::umma_commit(&acc_full[ab]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> bias, folded BN, act, + skip -> global =================
+        const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int chalf = (warp - CT_EPI_WARP0) >> 2;                // which half of the accumulator columns
+        constexpr int NCH = C::NPAD / 16;                            // 16-column chunks; chunk c belongs to half (c * 2 / NCH)
+        const int row = quad * 32 + lane;
+        const int tl = row / FO, fo = row % FO;
+        const int act = a.act;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int b = tile / chunks, t0 = (tile - b * chunks) * C::TF;
+            const int ab = lt & 1;
+            const int t = t0 + tl;
+            const bool valid = t < T;
+            tc::mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < C::NPAD; c0 += 16) {
+                if (NCH >= 2 ? ((c0 / 16) * 2 / NCH != chalf) : (chalf != 0)) continue;      // warp-uniform
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * C::NPAD + c0), v);
+                tc::tmem_ld_wait();
+                if (!valid) continue;
+                if (MODE == 0) {
+                    const size_t o0 = (((size_t)b * T + t) * COUT) * FO + fo;
+                    float ad[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)      // all skip loads of the chunk in flight before the first store (out may alias nothing, but the compiler cannot know)
+                        ad[q] = (a.addend && c0 + q < COUT) ? __ldg(a.addend + o0 + (size_t)(c0 + q) * FO) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int co = c0 + q;
+                        if (co < COUT) {
+                            const float4 pr = s_par[co];
+                            const float x = apply_act(fmaf(v[q], pr.x, pr.y), act, pr.z) + ad[q];
+                            a.out[o0 + (size_t)co * FO] = x;
+                        }
+                    }
+                } else {
+                    const size_t o0 = (((size_t)b * T + t) * COUT) * (2 * FO) + 2 * fo;
+                    float2 ad[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        ad[q] = (a.addend && (c0 >> 1) + q < COUT) ? __ldg(reinterpret_cast<const float2*>(a.addend + o0 + (size_t)((c0 >> 1) + q) * (2 * FO)))
+                                                                  : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int co = (c0 >> 1) + q;
+                        if (co < COUT) {
+                            const float4 pr = s_par[co];
+                            const float x0 = apply_act(fmaf(v[2 * q], pr.x, pr.y), act, pr.z) + ad[q].x;
+                            const float x1 = apply_act(fmaf(v[2 * q + 1], pr.x, pr.y), act, pr.z) + ad[q].y;
+                            *reinterpret_cast<float2*>(a.out + o0 + (size_t)co * (2 * FO)) = make_float2(x0, x1);
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[ab]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == CT_MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
+}
+
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO>
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
+    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO>;
+    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO>;
+    static bool attr_set = false;                                   // per instantiation; benign if raced
+    if (!attr_set) {
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    const int chunks = (a.T + C::TF - 1) / C::TF;
+    const long long ntiles = (long long)a.B * chunks;
+    const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    kern<<<grid, CT_THREADS, C::SMEM, st>>>(a);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+// process-wide numeric mode of the conv stages: 1 = tf32 tensor cores (default), 0 = exact-fp32 CUDA cores.
+// Initialised from the environment (CRUSE_CONV=fp32|tf32), switchable through cruse_conv_set_mode().
+int g_conv_mode = -1;
+int conv_mode() {
+    if (g_conv_mode < 0) {
+        const char* e = getenv("CRUSE_CONV");
+        g_conv_mode = (e && strcmp(e, "fp32") == 0) ? 0 : 1;
+    }
+    return g_conv_mode;
+}
+bool conv_tc_enabled() { return conv_mode() == 1; }
+
+}  // namespace
+
+// Returns 1 when the stage was launched on the tensor cores, 0 when no instantiation matches (the caller then
+// runs the CUDA-core kernel), < 0 on error.
+int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
+                cudaStream_t st) {
+    if (!conv_tc_enabled()) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act};
+    int rc = 0;
+#define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_)                                                              \
+    if (kt == KT_ && fstride == SF_ && Cin == CI_ && Cout == CO_ && Fout == FO_ && Fin == SF_ * FO_) {      \
+        rc = launch_conv_tc<0, KT_, SF_, CI_, CO_, FO_>(a, st);                                             \
+        return rc ? rc : 1;                                                                                 \
+    }
+    CRUSE_CT_CONV(2, 2, 8, 16, 64)
+    CRUSE_CT_CONV(2, 2, 16, 32, 32)
+    CRUSE_CT_CONV(2, 2, 32, 64, 16)
+    CRUSE_CT_CONV(1, 1, 8, 8, 128)
+    CRUSE_CT_CONV(1, 1, 16, 16, 64)
+    CRUSE_CT_CONV(1, 1, 32, 32, 32)
+    CRUSE_CT_CONV(1, 1, 64, 64, 16)
+#undef CRUSE_CT_CONV
+    return 0;
+}
+
+int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                 int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
+    if (!conv_tc_enabled()) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act};
+    int rc = 0;
+#define CRUSE_CT_CONVT(CI_, CO_, FI_)                                                \
+    if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \
+        rc = launch_conv_tc<1, 1, 1, CI_, CO_, FI_>(a, st);                          \
+        return rc ? rc : 1;                                                          \
+    }
+    CRUSE_CT_CONVT(64, 32, 16)
+    CRUSE_CT_CONVT(32, 16, 32)
+    CRUSE_CT_CONVT(16, 8, 64)
+#undef CRUSE_CT_CONVT
+    return 0;
+}
+
+}  // namespace cruse
+
+extern "C" int cruse_conv_get_mode(void) { return cruse::conv_mode(); }
+extern "C" int cruse_conv_set_mode(int mode) {
+    if (mode != 0 && mode != 1) {
+        cruse::set_error("conv_set_mode: mode must be 0 (fp32 CUDA cores) or 1 (tf32 tensor cores), got %d", mode);
+        return -1;
+    }
+    cruse::g_conv_mode = mode;
+    return 0;
+}

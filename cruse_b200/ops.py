@@ -504,3 +504,17 @@ def sigmoid_bwd(dy, y):
     dz = torch.empty_like(y)
     _call("cruse_sigmoid_bwd", _p(dy), _p(y), _p(dz), y.numel(), _stream(), meta=("sigmoid_bwd", _nb(dy, y, dz), 3 * y.numel()))
     return dz
+
+
+# ------------------------------------------------------------------------------------------
+# numeric mode of the eval-mode conv stages (include/cruse_b200.h: cruse_conv_set_mode)
+# ------------------------------------------------------------------------------------------
+def set_conv_mode(mode: str):
+    """'tf32' = tcgen05 implicit GEMM (default), 'fp32' = exact-fp32 CUDA-core kernels."""
+    if mode not in ("tf32", "fp32"):
+        raise RuntimeError(f"set_conv_mode: unknown mode {mode!r}")
+    check(lib().cruse_conv_set_mode(1 if mode == "tf32" else 0), "cruse_conv_set_mode")
+
+
+def get_conv_mode() -> str:
+    return "tf32" if lib().cruse_conv_get_mode() == 1 else "fp32"

@@ -83,6 +83,12 @@ int cruse_conv_fwd(const float* in, const float* hist, const float* w, const flo
                    float* out, float* stats_ws,
                    int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream);
 int cruse_conv_nparts(int B, int T);
+/* numeric mode of the eval-mode conv / convT stages of the 256-bin pyramid (no `hist`, no `stats_ws`):
+ *   1 = implicit GEMM on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulate; default),
+ *   0 = exact-fp32 CUDA-core kernels.  Initial value from the environment (CRUSE_CONV=fp32|tf32).
+ * Stages without a tensor-core instantiation (Cin == 1, Cout == 1, odd bin counts) always run in fp32. */
+int cruse_conv_get_mode(void);
+int cruse_conv_set_mode(int mode);
 
 /* ---- a5: decoder stage.  replaces nn.ConvTranspose2d((1,3), stride (1,2)) + crop + BN + act
  *      + skip add at model/cruse_net.py:161-164.   w [Cin,Cout,1,3]; output cropped to Fout

@@ -71,6 +71,17 @@ def test_preprocess_surface(cuda):
 
 
 # ------------------------------------------------------------------ conv stages
+@pytest.fixture(autouse=True)
+def _exact_conv_mode(cuda):
+    """the per-kernel tests in this file check the exact-fp32 CUDA-core conv kernels to 1e-5; the tensor-core
+    (tf32) instantiations are checked separately below to the stated 1e-3 gate."""
+    from cruse_b200 import ops
+    old = ops.get_conv_mode()
+    ops.set_conv_mode("fp32")
+    yield
+    ops.set_conv_mode(old)
+
+
 def _to_frames(x):      # [B,C,T,F] -> [B,T,C,F]
     return x.permute(0, 2, 1, 3).contiguous()
 
@@ -170,6 +181,52 @@ def test_decoder_stage_eval(cuda, cin, cout, Fin, Fout, last):
         scale, shift = ops.bn_fold(bn.to(cuda))
         got = ops.convT_fwd(xc, wc, bc, scale, shift, None, "relu", _to_frames(skip).to(cuda), Fout)
     assert rel_err(got, _to_frames(ref)) <= 1e-5
+
+
+@pytest.mark.parametrize("B,T", [(2, 19), (1, 1), (3, 64)])
+@pytest.mark.parametrize("kind,cin,cout,F", [("enc", 8, 16, 128), ("enc", 16, 32, 64), ("enc", 32, 64, 32),
+                                             ("skip", 8, 8, 128), ("skip", 16, 16, 64), ("skip", 32, 32, 32), ("skip", 64, 64, 16),
+                                             ("dec", 64, 32, 16), ("dec", 32, 16, 32), ("dec", 16, 8, 64)])
+def test_conv_stages_on_tensor_cores(cuda, kind, cin, cout, F, B, T):
+    """tcgen05 implicit-GEMM instantiations (conv_tc.cu, kind::tf32, fp32 accumulate) of the 256-bin pyramid against
+    torch fp32 on the CPU; stated tolerance 1e-3 (operands rounded to a 10-bit mantissa).  T = 19 / 1 exercise ragged
+    last tiles (frames past the end are zero rows of the GEMM and never stored), T = 64 whole tiles."""
+    from cruse_b200 import ops
+    torch.manual_seed(11)
+    ops.set_conv_mode("tf32")
+    if kind == "enc":
+        conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), (1, 1))
+        bn = nn.BatchNorm2d(cout).eval()
+        bn.running_mean.copy_(0.1 * torch.randn(cout)); bn.running_var.copy_(1 + 0.1 * torch.rand(cout))
+        bn.weight.data.copy_(1 + 0.1 * torch.randn(cout)); bn.bias.data.copy_(0.1 * torch.randn(cout))
+        pre = nn.PReLU(cout); pre.weight.data.copy_(0.1 + 0.3 * torch.rand(cout))
+        x = torch.randn(B, cin, T, F)
+        with torch.no_grad():
+            ref = pre(bn(conv(x)[..., :-1, :]))
+        scale, shift = ops.bn_fold(bn.to(cuda))
+        got = ops.conv_fwd(_to_frames(x).to(cuda), conv.weight.detach().to(cuda), conv.bias.detach().to(cuda), scale, shift,
+                           pre.weight.detach().to(cuda), "prelu", 2, 2)
+    elif kind == "skip":
+        conv = nn.Conv2d(cin, cout, (1, 3), bias=False, padding=(0, 1))
+        x = torch.randn(B, cin, T, F)
+        with torch.no_grad():
+            ref = conv(x)
+        got = ops.conv_fwd(_to_frames(x).to(cuda), conv.weight.detach().to(cuda), None, None, None, None, "none", 1, 1)
+    else:
+        conv = nn.ConvTranspose2d(cin, cout, (1, 3), (1, 2))
+        bn = nn.BatchNorm2d(cout).eval()
+        bn.running_mean.copy_(0.1 * torch.randn(cout)); bn.running_var.copy_(1 + 0.1 * torch.rand(cout))
+        x = torch.randn(B, cin, T, F)
+        skip = torch.randn(B, cout, T, 2 * F)
+        with torch.no_grad():
+            ref = torch.relu(bn(conv(x)[..., :2 * F])) + skip
+        scale, shift = ops.bn_fold(bn.to(cuda))
+        got = ops.convT_fwd(_to_frames(x).to(cuda), conv.weight.detach().to(cuda), conv.bias.detach().to(cuda), scale, shift, None,
+                            "relu", _to_frames(skip).to(cuda), 2 * F)
+    err = rel_err(got, _to_frames(ref))
+    assert err <= 1e-3, err
+    # the same call in exact-fp32 mode must agree with torch to 1e-5: proves the dispatch really switched kernels
+    assert err > 1e-7
 
 
 # ------------------------------------------------------------------ GRU / LayerNorm

@@ -47,6 +47,8 @@ SIGNATURES = {
     "cruse_gru_seq_fwd": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gru_seq_fwd_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gru_seq_tc_max_clusters": (c_int, [c_int]),
+    "cruse_gru_ih_gemm_tm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "cruse_gru_seq_chunk_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp]),
     "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),
     "cruse_wo_male_fwd_bwd": (c_int, [c_fp, CplxLayout, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp,
                                       c_int, c_int, c_int, c_fp]),

@@ -61,6 +61,67 @@ class GGRU(nn.Module):
         return ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
                                interleave=interleave, h0=h0, want_hT=want_hT)
 
+    # -- two-layer wavefront ----------------------------------------------------------------------
+    # The recurrence is the only part of the path that is sequential in time (T steps of ~1 us per layer), and one
+    # layer only occupies G*ceil(B/16) clusters of 8 SMs.  Layer 2 (+ LayerNorm 1 and its input projections) of
+    # frames [t0,t1) depends only on layer 1 up to t1, so the layers run side by side on three streams, one chunk of
+    # frames apart; GRU-internal buffers are time-major so a chunk is a contiguous row range.
+    WAVEFRONT_MIN_T = 96
+    WAVEFRONT_CHUNKS = 8
+    _side_streams = {}
+
+    @classmethod
+    def _streams(cls, device):
+        key = (device.type, device.index)
+        if key not in cls._side_streams:
+            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device) for _ in range(3))
+        return cls._side_streams[key]
+
+    def _wavefront(self, x, residual):
+        B, T, D = x.shape
+        G, H = self.groups, D // self.groups
+        dev = x.device
+        g1, g2 = self.gru_list1, self.gru_list2
+        w_hh1, b_hh1 = [g.weight_hh_l0 for g in g1], [g.bias_hh_l0 for g in g1]
+        w_hh2, b_hh2 = [g.weight_hh_l0 for g in g2], [g.bias_hh_l0 for g in g2]
+        w_ih2, b_ih2 = [g.weight_ih_l0 for g in g2], [g.bias_ih_l0 for g in g2]
+        main = torch.cuda.current_stream(dev)
+        sA, sC, sB = self._streams(dev)
+        xp1 = ops.gru_ih_gemm_tm(x.reshape(B * T, D), [g.weight_ih_l0 for g in g1], [g.bias_ih_l0 for g in g1], b_hh1, B, T)
+        # every buffer is allocated on the caller's stream and outlives the join below
+        y1 = torch.empty(T, B, D, device=dev, dtype=torch.float32)
+        z1 = torch.empty(T, B, D, device=dev, dtype=torch.float32)
+        xp2 = torch.empty(T, B, G, 3 * H, device=dev, dtype=torch.float32)
+        y2 = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+        hA = [torch.empty(G, B, H, device=dev, dtype=torch.float32) for _ in range(2)]
+        hB = [torch.empty(G, B, H, device=dev, dtype=torch.float32) for _ in range(2)]
+        nch = max(2, min(self.WAVEFRONT_CHUNKS, T // 32))
+        bounds = [T * k // nch for k in range(nch + 1)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for s_ in (sA, sC, sB):
+            s_.wait_event(fork)
+        tw, tb = ops._ptr_table(w_ih2), ops._ptr_table(b_ih2)
+        for k in range(nch):
+            t0, t1 = bounds[k], bounds[k + 1]
+            with torch.cuda.stream(sA):                                   # layer 1, frames [t0,t1)  (:41-45)
+                ops.gru_seq_chunk(xp1, w_hh1, b_hh1, hA[(k + 1) & 1] if k else None, y1, hA[k & 1], t0, t1, True, True)
+                eA = torch.cuda.Event()
+                eA.record(sA)
+            with torch.cuda.stream(sC):                                   # LayerNorm 1 + layer-2 input projections (:46-48)
+                sC.wait_event(eA)
+                ops.layernorm_fwd_into(y1[t0:t1], self.ln1.weight, self.ln1.bias, self.ln1.eps, z1[t0:t1])
+                ops.gru_ih_gemm_into(z1[t0:t1].view(-1, D), w_ih2, b_ih2, b_hh2, xp2[t0:t1], tables=(tw, tb))
+                eC = torch.cuda.Event()
+                eC.record(sC)
+            with torch.cuda.stream(sB):                                   # layer 2, frames [t0,t1)  (:49-50)
+                sB.wait_event(eC)
+                ops.gru_seq_chunk(xp2, w_hh2, b_hh2, hB[(k + 1) & 1] if k else None, y2, hB[k & 1], t0, t1, False, False)
+        join = torch.cuda.Event()
+        join.record(sB)
+        main.wait_event(join)
+        return ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)   # :51 (+ skip4, :160)
+
     def forward_frames(self, x, residual=None, state=None, want_state=False):
         """x [B,T,D] frame-major.  state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence
         (streaming, model/based_model/cust_conv.py:303-325)."""
@@ -68,6 +129,11 @@ class GGRU(nn.Module):
         B, T, D = x.shape
         if D != self.hidden_size:
             raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
+        # both layers side by side need 2*G*ceil(B/32) co-resident clusters
+        if (state is None and not want_state and T >= self.WAVEFRONT_MIN_T and ops.GRU_SEQ_MODE == "tf32"
+                and ops.GRU_IH_MODE == "tf32" and ops.GRU_WAVEFRONT
+                and 2 * self.groups * ((B + 31) // 32) <= ops.gru_seq_max_clusters(D // self.groups)):
+            return self._wavefront(x, residual)
         h1 = h2 = None
         if state is not None:
             h1, h2 = state

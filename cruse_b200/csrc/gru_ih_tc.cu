@@ -76,7 +76,7 @@ struct GemmArgs {
 
 __global__ void __launch_bounds__(IH_THREADS)
 gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, long long ldc, int bias2_rows, int splitk,
-                  long long c_plane) {
+                  long long c_plane, int tm_T) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles: 1024-byte aligned
     uint8_t* tiles = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -149,7 +149,10 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
         const int m = m0 + quad * 32 + lane;
-        float* orow = args.out[g] + (size_t)split * c_plane + (size_t)m * ldc + n0;
+        // tm_T > 0: A rows are (utterance b, frame t) = b*tm_T + t, C rows are written time-major (t*B + b)
+        size_t mrow = (size_t)m;
+        if (tm_T > 0) { const int bq = m / tm_T; mrow = (size_t)(m - bq * tm_T) * (size_t)(M / tm_T) + bq; }
+        float* orow = args.out[g] + (size_t)split * c_plane + mrow * ldc + n0;
         const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(args.out[g]) & 15) == 0) && ((c_plane & 3) == 0);
         if (nkb > 0) {
             tc::mbar_wait(acc_full, 0);
@@ -187,14 +190,14 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
 }
 
 int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int bias2_rows, int splitk, long long c_plane,
-                cudaStream_t st) {
+                cudaStream_t st, int tm_T = 0) {
     for (int g = G; g < CRUSE_MAX_GROUPS; ++g) {
         args.a[g] = args.a[0]; args.b[g] = args.b[0];
         args.bias1[g] = nullptr; args.bias2[g] = nullptr; args.out[g] = nullptr;
     }
     CRUSE_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, G * splitk);
-    gemm_tn_tc_kernel<<<grid, IH_THREADS, IH_SMEM, st>>>(args, M, N, K, ldc, bias2_rows, splitk, c_plane);
+    gemm_tn_tc_kernel<<<grid, IH_THREADS, IH_SMEM, st>>>(args, M, N, K, ldc, bias2_rows, splitk, c_plane, tm_T);
     CRUSE_LAUNCH_OK();
     return 0;
 }
@@ -204,11 +207,12 @@ int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int b
 
 using namespace cruse;
 
-extern "C" int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
-                                    const float* const* b_hh, float* xproj, int M, int G, int H, void* stream) {
+static int gru_ih_gemm_tc_impl(const float* x, const float* const* w_ih, const float* const* b_ih, const float* const* b_hh,
+                               float* xproj, int M, int G, int H, int tm_T, void* stream) {
     CRUSE_CHECK_ARG(x && xproj && w_ih, "gru_ih_gemm_tc: null pointer");
     CRUSE_CHECK_ARG(M > 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0,
                     "gru_ih_gemm_tc: bad sizes M=%d G=%d H=%d (H%%4==0, G<=%d)", M, G, H, CRUSE_MAX_GROUPS);
+    CRUSE_CHECK_ARG(tm_T == 0 || (tm_T > 0 && M % tm_T == 0), "gru_ih_gemm_tm_tc: M=%d is not a multiple of T=%d", M, tm_T);
     GemmArgs args;
     for (int g = 0; g < G; ++g) {
         CRUSE_CHECK_ARG(w_ih[g], "gru_ih_gemm_tc: null weight pointer for group %d", g);
@@ -219,7 +223,18 @@ extern "C" int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, co
         args.bias2[g] = b_hh ? b_hh[g] : nullptr;
         args.out[g] = xproj + (size_t)g * 3 * H;
     }
-    return launch_gemm(args, G, M, 3 * H, H, (long long)G * 3 * H, 2 * H, 1, 0, (cudaStream_t)stream);
+    return launch_gemm(args, G, M, 3 * H, H, (long long)G * 3 * H, 2 * H, 1, 0, (cudaStream_t)stream, tm_T);
+}
+
+extern "C" int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
+                                    const float* const* b_hh, float* xproj, int M, int G, int H, void* stream) {
+    return gru_ih_gemm_tc_impl(x, w_ih, b_ih, b_hh, xproj, M, G, H, 0, stream);
+}
+
+extern "C" int cruse_gru_ih_gemm_tm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
+                                       const float* const* b_hh, float* xproj, int B, int T, int G, int H, void* stream) {
+    CRUSE_CHECK_ARG(B > 0 && T > 0, "gru_ih_gemm_tm_tc: bad sizes B=%d T=%d", B, T);
+    return gru_ih_gemm_tc_impl(x, w_ih, b_ih, b_hh, xproj, B * T, G, H, T, stream);
 }
 
 extern "C" int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C, int G,

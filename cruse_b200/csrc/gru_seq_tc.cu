@@ -1,25 +1,35 @@
 // gru_seq_tc.cu -- the GRU recurrence (the T sequential steps of nn.GRU, model/cruse_net.py:23-31,43-50
 // of the reference; cuDNN's persistent RNN kernel on the reference path) on the 5th-generation tensor
-// cores, one thread-block cluster per (group, 16-utterance slice).
+// cores, one thread-block cluster per (group, PAIR of 16-utterance slices).
 //
 // Per step the recurrent half of the cell is   pre[3H] = W_hh[g] . h_{t-1}   for every utterance: a
-// [3H x H] . [H x 16] product.  The cluster splits the H hidden units 32 per CTA (H = 256 -> 8 CTAs);
-// CTA c keeps the 96 gate rows {r,z,n} x {its 32 units} of W_hh resident in TENSOR MEMORY for the whole
-// sequence as the A operand of ONE tcgen05.mma shape (M = 128 [96 used], N = 16 utterances, K = H,
+// [3H x H] . [H x 16] product per slice.  The cluster splits the H hidden units 32 per CTA (H = 256 -> 8
+// CTAs); CTA c keeps the 96 gate rows {r,z,n} x {its 32 units} of W_hh resident in TENSOR MEMORY for the
+// whole sequence as the A operand of ONE tcgen05.mma shape (M = 128 [96 used], N = 16 utterances, K = H,
 // kind::tf32, fp32 accumulation in TMEM; lane = gate row, column = k, 256 of the 512 TMEM columns).
 // (A first version kept the slice in shared memory: every step then re-streams 128 KB through the
 // 128 B/clk shared-memory port, measured 47 clk per K=8 MMA; from TMEM the same MMA is not port-bound.)
 // The B operand is h_{t-1} itself in shared memory ([16 utterances][H], K-major, 128-byte swizzle), double buffered.
-// After the MMA the accumulator (lane = gate row, column = utterance) is pulled out with tcgen05.ld,
-// transposed through a small shared-memory pad so that every thread owns (utterance, 2 adjacent
-// units), the gates are evaluated in fp32 (the z*h_{t-1} carry uses the thread's own full-precision
-// register copy, only the matmul operand is rounded to tf32), and the new 2 KB h slice -- which is
-// exactly k-block `c` of everybody's next B operand -- is scattered to all CTAs of the cluster with
-// st.async (8-byte DSMEM stores that credit the destination CTA's mbarrier).  No cluster barrier and
-// no fence sits inside the time loop: step t+1's MMA is released by the byte count of h_t arriving.
+//
+// The step is a latency chain (h arrival -> 32 MMAs -> commit -> tcgen05.ld -> gate math -> scatter), so one
+// cluster runs TWO independent slices of 16 utterances software-pipelined against each other: warp 8 issues the
+// MMAs of slice 0 then slice 1 every step (both read the same W_hh in TMEM, separate accumulators), warps 0-3
+// and 4-7 are the two slices' warpgroups.  While one slice waits for its h exchange and tensor-core pass the
+// other does its gate math, which roughly halves the time per (utterance, step) and halves the clusters a
+// layer needs -- so both GRU layers of the bottleneck fit on the GPU side by side (cruse_net.GGRU._wavefront).
+//
+// Per slice and step: the accumulator (lane = gate row, column = utterance) is pulled out with tcgen05.ld,
+// transposed through a small shared-memory pad so that every thread owns (utterance, 4 adjacent units), the
+// gates are evaluated in fp32 (the z*h_{t-1} carry uses the thread's own full-precision register copy, only
+// the matmul operand is rounded to tf32), and the new h slice -- exactly k-block `c` of everybody's next B
+// operand -- is scattered to all CTAs of the cluster with st.async (16-byte DSMEM stores that credit the
+// destination CTA's mbarrier).  No cluster barrier and no fence sits inside the time loop: step t+1's MMA is
+// released by the byte count of h_t arriving; the slice warpgroups only meet on their own named barrier.
 //
 // x-projections (+ folded biases) come from the tcgen05 input GEMM (gru_ih_tc.cu) and are prefetched
-// one step ahead.  Optional `gates` output saves r, z, n and W_hn.h+b_hn for the backward pass.
+// two steps ahead.  Optional `gates` output saves r, z, n and W_hn.h+b_hn for the backward pass.  Rows of
+// xproj / y are addressed through (utterance, frame) strides so the same kernel runs whole sequences in
+// frame order and time chunks of time-major buffers.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cooperative_groups.h>
@@ -29,11 +39,14 @@ namespace cg = cooperative_groups;
 namespace cruse {
 namespace {
 
-constexpr int SQ_NB16 = 16;                  // utterances per cluster = MMA N = 16 * NI  (NI = 1 or 2)
+constexpr int SQ_NB = 16;                    // utterances per slice = MMA N
 constexpr int SQ_U = 32;                     // hidden units per CTA (= one 128-byte k-block of the B operand)
-constexpr int SQ_THREADS = 256;              // thread -> (utterance tid/16, unit pair tid%16)
-constexpr int SQ_TMEM_COLS = 512;            // A: up to 256 columns (K) + D: 16 columns -> whole TMEM (1 CTA/SM)
-constexpr int SQ_D_COL = 256;                // accumulator column offset
+constexpr int SQ_WG = 128;                   // threads per slice warpgroup: thread -> (utterance wt/8, 4 adjacent units)
+constexpr int SQ_THREADS = 2 * SQ_WG + 32;   // two slice warpgroups + the MMA-issuing warp
+constexpr int SQ_TMEM_COLS = 512;            // A: up to 256 columns (K) + 2 x D: 16 columns -> whole TMEM (1 CTA/SM)
+constexpr int SQ_D_COL = 256;                // accumulator column offset (slice s at + 16*s)
+constexpr int SQ_H_KB = SQ_NB * 128;         // bytes of one B k-block tile: 16 rows x 32 tf32
+constexpr int SQ_PRE_LD = SQ_NB + 1;         // padded leading dim of the gate-row x utterance pad
 
 #ifdef CRUSE_SEQ_TIMING
 // developer instrumentation (never built into the shipped library): per-step clock64 stamps of cluster 0 / CTA 0
@@ -97,53 +110,52 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
-template <int NC, int NI>
+template <int NC>
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const float* __restrict__ h0, float* __restrict__ y,
-                  float* __restrict__ hT, float* __restrict__ gates, int B, int T, int G, int H, int y_fs, int y_gs) {
-    constexpr int NB = SQ_NB16 * NI;              // utterances per cluster = MMA N
-    constexpr int H_KB = NB * 128;               // bytes of one B k-block tile: NB rows x 32 tf32
-    constexpr int PRE_LD = NB + 1;               // padded leading dim of the gate-row x utterance pad
+                  float* __restrict__ hT, float* __restrict__ gates, int B, int T, int G, int H, int y_fs, int y_gs,
+                  long long x_bs, long long x_ts, long long y_bs, long long y_ts) {
+    // row (b, t) of xproj is b*x_bs + t*x_ts, of y b*y_bs + t*y_ts ([B,T] frame order: (T,1); time-major [T,B]: (1,B))
+    constexpr int SLICE_BYTES = 2 * NC * SQ_H_KB;        // two h buffers of one slice
     extern __shared__ uint8_t smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int g = blockIdx.y, bslice = blockIdx.z;
+    const int g = blockIdx.y, bpair = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sH = smem_raw + (base - tc::smem_u32(smem_raw));          // 2 buffers x NC k-blocks x H_KB
-    float* sPre = reinterpret_cast<float*>(sH + 2 * NC * H_KB);        // [96][PRE_LD]
-    uint64_t* hbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sPre + 96 * PRE_LD) + 7) & ~(uintptr_t)7);
-    uint64_t* acc_full = hbar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint8_t* sH = smem_raw + (base - tc::smem_u32(smem_raw));          // [slice][buffer][NC k-blocks][16 x 128 B]
+    float* sPre = reinterpret_cast<float*>(sH + 2 * SLICE_BYTES);      // [slice][96][PRE_LD]
+    uint64_t* hbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sPre + 2 * 96 * SQ_PRE_LD) + 7) & ~(uintptr_t)7);   // [slice][buffer]
+    uint64_t* acc_full = hbar + 4;                                     // [slice]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
-    // ---- thread -> (utterances b + 16*i, units u0, u0+1)
-    const int b = tid >> 4, jp = tid & 15;
-    const int u0 = rank * SQ_U + 2 * jp;
-    const bool uvalid = u0 < H;                     // H is even, so u0+1 < H as well
-    int bg[NI];
-    bool valid[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        bg[i] = bslice * NB + b + 16 * i;
-        valid[i] = uvalid && bg[i] < B;
-    }
+    // ---- warps 0-3 / 4-7 = slice 0 / 1: thread -> (utterance b, units u0 .. u0+3)
+    const int sl = (warp >> 2) & 1;
+    const int wt = tid & (SQ_WG - 1);
+    const int b = wt >> 3, jq = wt & 7;
+    const int u0 = rank * SQ_U + 4 * jq;
+    const bool uvalid = u0 < H;                       // H % 4 == 0, so u0+3 < H as well
+    const int bg = (bpair * 2 + sl) * SQ_NB + b;
+    const bool valid = uvalid && bg < B && warp < 8;
+    const bool act0 = (bpair * 2) * SQ_NB < B, act1 = (bpair * 2 + 1) * SQ_NB < B;   // slice has any utterance (CTA-uniform)
+    const bool my_act = sl ? act1 : act0;
 
-    for (int i = tid; i < 2 * NC * H_KB / 16; i += SQ_THREADS) reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 2 * SLICE_BYTES / 16; i += SQ_THREADS) reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
-        tc::mbar_init(&hbar[0], 1);
-        tc::mbar_init(&hbar[1], 1);
-        tc::mbar_init(acc_full, 1);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&hbar[i], 1);
+        tc::mbar_init(&acc_full[0], 1);
+        tc::mbar_init(&acc_full[1], 1);
         tc::fence_barrier_init();
     }
-    if (warp == 3) tc::tmem_alloc<SQ_TMEM_COLS>(tmem_slot);
+    if (warp == 8) tc::tmem_alloc<SQ_TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // ---- W_hh slice -> tensor memory (A operand): lane q*32+j = gate q of hidden unit rank*32+j, column = k, tf32.
     //      A warp can only touch its own lane quadrant (warp % 4); warps 0-3 / 4-7 split the k-blocks.
-    {
+    if (warp < 8) {
         const float* W = ptrs.w_hh[g];
         const int q = warp & 3, unit = rank * SQ_U + lane;
         const bool rowvalid = q < 3 && unit < H;
@@ -161,20 +173,17 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    // ---- h_0 -> hbuf[0] (tf32 operand copy) and the thread's own full-precision copy
-    float2 hold[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) hold[i] = make_float2(0.f, 0.f);
-    if (h0) {
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-            if (valid[i]) hold[i] = __ldg(reinterpret_cast<const float2*>(h0 + ((size_t)g * B + bg[i]) * H + u0));
-        for (int i = tid; i < NB * (H / 2); i += SQ_THREADS) {      // every CTA needs the whole h_0 of its utterances
-            const int bb = i / (H / 2), k = (i - bb * (H / 2)) * 2;
-            const int bgg = bslice * NB + bb;
+    // ---- h_0 -> buffer 0 of my slice (tf32 operand copy) and the thread's own full-precision copy
+    float4 hold = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h0 && warp < 8 && my_act) {
+        if (valid) hold = __ldg(reinterpret_cast<const float4*>(h0 + ((size_t)g * B + bg) * H + u0));
+        uint8_t* dstb = sH + sl * SLICE_BYTES;
+        for (int i = wt; i < SQ_NB * (H / 4); i += SQ_WG) {      // every CTA needs the whole h_0 of its utterances
+            const int bb = i / (H / 4), k = (i - bb * (H / 4)) * 4;
+            const int bgg = (bpair * 2 + sl) * SQ_NB + bb;
             if (bgg < B) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(h0 + ((size_t)g * B + bgg) * H + k));
-                *reinterpret_cast<float2*>(sH + sw128_off(bb, k, H_KB)) = make_float2(to_tf32(v.x), to_tf32(v.y));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(h0 + ((size_t)g * B + bgg) * H + k));
+                *reinterpret_cast<float4*>(dstb + sw128_off(bb, k, SQ_H_KB)) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
             }
         }
     }
@@ -182,194 +191,177 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_d = tmem_base + SQ_D_COL;
     cluster.sync();                    // every CTA's buffers + barriers exist before any remote store lands
 
-    // ---- remote (shared::cluster) addresses of my 8-byte h slot and of the barriers in every CTA of the cluster
-    uint32_t rem_h[NC], rem_bar[NC];
-    {
-        const uint32_t lh = tc::smem_u32(sH) + (uint32_t)rank * H_KB + sw128_off(b, 2 * jp, H_KB);
-        const uint32_t lb = tc::smem_u32(&hbar[0]);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_h[c]) : "r"(lh), "r"(c));
-            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_bar[c]) : "r"(lb), "r"(c));
-        }
-    }
-    constexpr uint32_t STEP_BYTES = (uint32_t)NC * SQ_THREADS * 8 * NI;   // all of h_t: NB x 32*NC floats
-
+    constexpr uint32_t STEP_BYTES = (uint32_t)NC * SQ_WG * 16;     // all of h_t of one slice: 16 x 32*NC floats
+    constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, 128, SQ_NB);
     const size_t N3 = (size_t)3 * H;
-    const size_t xstep = (size_t)G * N3;
-    const size_t ystep = (size_t)G * H;
-    const float* xp[NI];
-    float* yp[NI];
-    float* gp[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const size_t bt = (size_t)(valid[i] ? bg[i] : 0) * T;
-        xp[i] = xproj + (bt * G + g) * N3 + (uvalid ? u0 : 0);
-        yp[i] = y + bt * ystep + (size_t)(uvalid ? u0 : 0) * y_fs + (size_t)g * y_gs;
-        gp[i] = gates ? gates + (bt * G + g) * (4 * (size_t)H) + (uvalid ? u0 : 0) : nullptr;
-    }
-    float2 b_hn = make_float2(0.f, 0.f);
-    if (uvalid && ptrs.b_hh[g]) b_hn = __ldg(reinterpret_cast<const float2*>(ptrs.b_hh[g] + 2 * H + u0));
 
-    // x-projections are streamed from HBM two steps ahead of their use (a step is shorter than a DRAM round trip)
-    float2 xr[NI], xz[NI], xn[NI], x1r[NI], x1z[NI], x1n[NI];
+    if (warp == 8) {
+        // ================= MMA issuer: pre = W_slice . h_t for slice 0, then slice 1, every step =================
+        // h_t (t >= 1) is arrival number (t-1)/2 on buffer t&1 of its slice -> wait parity ((t-1)>>1)&1
+        int p = 0;
+        for (int t = 0; t < T; ++t) {
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        xr[i] = xz[i] = xn[i] = x1r[i] = x1z[i] = x1n[i] = make_float2(0.f, 0.f);
-        if (valid[i] && T > 0) {
-            xr[i] = __ldg(reinterpret_cast<const float2*>(xp[i]));
-            xz[i] = __ldg(reinterpret_cast<const float2*>(xp[i] + H));
-            xn[i] = __ldg(reinterpret_cast<const float2*>(xp[i] + 2 * H));
-        }
-        if (valid[i] && T > 1) {
-            x1r[i] = __ldg(reinterpret_cast<const float2*>(xp[i] + xstep));
-            x1z[i] = __ldg(reinterpret_cast<const float2*>(xp[i] + xstep + H));
-            x1n[i] = __ldg(reinterpret_cast<const float2*>(xp[i] + xstep + 2 * H));
-        }
-    }
-    constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, 128, NB);
-
-    int p = 0;
-    uint32_t ph0 = 0, ph1 = 0;
-    for (int t = 0; t < T; ++t) {
-        if (tid == 0) tc::mbar_expect_tx(&hbar[p ^ 1], STEP_BYTES);   // arm the barrier h_{t+1} will complete
-        if (warp == 3) {
-            // ===== MMA issue: pre = W_slice . h_t.  The whole warp waits (converged), one elected lane issues =====
-            SEQ_STAMP(0);
-            if (t > 0) {
-                if (p) { tc::mbar_wait(&hbar[1], ph1); ph1 ^= 1; } else { tc::mbar_wait(&hbar[0], ph0); ph0 ^= 1; }
-                tc::fence_proxy_async_smem();          // h_t was written by (remote) generic-proxy stores
+            for (int s = 0; s < 2; ++s) {
+                if (!(s ? act1 : act0)) continue;
+                if (lane == 0) tc::mbar_expect_tx(&hbar[s * 2 + (p ^ 1)], STEP_BYTES);   // arm the barrier h_{t+1} will complete
+                if (s == 0) SEQ_STAMP(0);
+                if (t > 0) {
+                    tc::mbar_wait(&hbar[s * 2 + p], (uint32_t)(((t - 1) >> 1) & 1));
+                    tc::fence_proxy_async_smem();          // h_t was written by (remote) generic-proxy stores
+                }
+                tc::tc_fence_after();
+                if (s == 0) SEQ_STAMP(1);
+                const uint64_t bdesc0 = tc::smem_desc_sw128(base + (uint32_t)s * SLICE_BYTES + (uint32_t)p * (NC * SQ_H_KB));
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < NC; ++kb)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_tf32_ts(tmem_base + SQ_D_COL + 16 * s, tmem_base + (uint32_t)(kb * 32 + ks * 8),
+                                         bdesc0 + (uint64_t)((kb * SQ_H_KB + ks * 32) >> 4), idesc, (kb | ks) ? 1u : 0u);
+                    tc::umma_commit(&acc_full[s]);
+                }
+                __syncwarp();
+                if (s == 0) SEQ_STAMP(2);
             }
-            tc::tc_fence_after();
-            SEQ_STAMP(1);
-            const uint64_t bdesc0 = tc::smem_desc_sw128(base + (uint32_t)p * (NC * H_KB));
-            if (tc::elect_one()) {
-#pragma unroll
-                for (int kb = 0; kb < NC; ++kb)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(kb * 32 + ks * 8), bdesc0 + (uint64_t)((kb * H_KB + ks * 32) >> 4),
-                                     idesc, (kb | ks) ? 1u : 0u);
-                tc::umma_commit(acc_full);
-            }
-            __syncwarp();
-            SEQ_STAMP(2);
+            p ^= 1;
         }
-        // prefetch the x-projections of step t+2 while the tensor core works
-        float2 nxr[NI], nxz[NI], nxn[NI];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            nxr[i] = nxz[i] = nxn[i] = make_float2(0.f, 0.f);
-            if (valid[i] && t + 2 < T) {
-                const float* q = xp[i] + (size_t)(t + 2) * xstep;
-                nxr[i] = __ldg(reinterpret_cast<const float2*>(q));
-                nxz[i] = __ldg(reinterpret_cast<const float2*>(q + H));
-                nxn[i] = __ldg(reinterpret_cast<const float2*>(q + 2 * H));
-            }
+        // drain: the last step's scatter is still in flight towards my buffers -- wait for it before anybody exits
+        if (T > 0) {
+            if (act0) tc::mbar_wait(&hbar[0 + p], (uint32_t)(((T - 1) >> 1) & 1));
+            if (act1) tc::mbar_wait(&hbar[2 + p], (uint32_t)(((T - 1) >> 1) & 1));
         }
-        tc::mbar_wait(acc_full, (uint32_t)(t & 1));
-        tc::tc_fence_after();
-        if (tid == 0) SEQ_STAMP(3);
-        if (warp < 3) {
-            // accumulator lanes 32*warp.. = gate `warp` of my CTA's 32 units; columns = utterances
-            float* dst = sPre + (warp * 32 + lane) * PRE_LD;
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                float v[16];
-                tmem_ld_32x16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(16 * i), v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 16; ++c) dst[16 * i + c] = v[c];
-            }
-        }
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) SEQ_STAMP(4);
-        float2 hnew[NI], gr[NI], gz[NI], gn[NI], ghn[NI];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const int bb = b + 16 * i;
-            const float pr0 = sPre[(0 * 32 + 2 * jp) * PRE_LD + bb], pr1 = sPre[(0 * 32 + 2 * jp + 1) * PRE_LD + bb];
-            const float pz0 = sPre[(1 * 32 + 2 * jp) * PRE_LD + bb], pz1 = sPre[(1 * 32 + 2 * jp + 1) * PRE_LD + bb];
-            ghn[i].x = sPre[(2 * 32 + 2 * jp) * PRE_LD + bb] + b_hn.x;
-            ghn[i].y = sPre[(2 * 32 + 2 * jp + 1) * PRE_LD + bb] + b_hn.y;
-            gr[i].x = sigmoid_fast(xr[i].x + pr0); gr[i].y = sigmoid_fast(xr[i].y + pr1);
-            gz[i].x = sigmoid_fast(xz[i].x + pz0); gz[i].y = sigmoid_fast(xz[i].y + pz1);
-            gn[i].x = tanh_fast(xn[i].x + gr[i].x * ghn[i].x); gn[i].y = tanh_fast(xn[i].y + gr[i].y * ghn[i].y);
-            hnew[i].x = valid[i] ? ((1.f - gz[i].x) * gn[i].x + gz[i].x * hold[i].x) : 0.f;
-            hnew[i].y = valid[i] ? ((1.f - gz[i].y) * gn[i].y + gz[i].y * hold[i].y) : 0.f;
-            hold[i] = hnew[i];
-        }
-        if (tid == 0) SEQ_STAMP(7);
-        // scatter my 8 bytes per utterance of h_{t+1} (tf32-rounded operand copy) into the other buffer of every CTA
+    } else if (my_act) {
+        // ================= slice warpgroup: accumulator -> gates -> h_{t+1} scatter =================
+        float* myPre = sPre + sl * (96 * SQ_PRE_LD);
+        const uint32_t tmem_d = tmem_base + SQ_D_COL + 16 * sl;
+        // remote (shared::cluster) addresses of my 16-byte h slot and of the slice's barriers in every CTA of the cluster
+        uint32_t rem_h[NC], rem_bar[NC];
         {
-            const uint32_t poff = (uint32_t)(p ^ 1) * (NC * H_KB), boff = (uint32_t)(p ^ 1) * 8;
+            const uint32_t lh = tc::smem_u32(sH) + (uint32_t)sl * SLICE_BYTES + (uint32_t)rank * SQ_H_KB + sw128_off(b, 4 * jq, SQ_H_KB);
+            const uint32_t lb = tc::smem_u32(&hbar[sl * 2]);
 #pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const uint32_t w0 = __float_as_uint(to_tf32(hnew[i].x)), w1 = __float_as_uint(to_tf32(hnew[i].y));
+            for (int c = 0; c < NC; ++c) {
+                asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_h[c]) : "r"(lh), "r"(c));
+                asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_bar[c]) : "r"(lb), "r"(c));
+            }
+        }
+        const size_t xstep = (size_t)x_ts * G * N3;
+        const size_t ystep = (size_t)y_ts * G * H;
+        const size_t bsel = (size_t)(valid ? bg : 0);
+        const float* xp = xproj + (bsel * (size_t)x_bs * G + g) * N3 + (uvalid ? u0 : 0);
+        float* yp = y + bsel * (size_t)y_bs * G * H + (size_t)(uvalid ? u0 : 0) * y_fs + (size_t)g * y_gs;
+        float* gp = gates ? gates + ((bsel * T) * G + g) * (4 * (size_t)H) + (uvalid ? u0 : 0) : nullptr;   // gates: always [B,T]
+        float4 b_hn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (uvalid && ptrs.b_hh[g]) b_hn = __ldg(reinterpret_cast<const float4*>(ptrs.b_hh[g] + 2 * H + u0));
+
+        // x-projections are streamed from HBM two steps ahead of their use (a step is shorter than a DRAM round trip)
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xr = zero4, xz = zero4, xn = zero4, x1r = zero4, x1z = zero4, x1n = zero4;
+        if (valid && T > 0) {
+            xr = __ldg(reinterpret_cast<const float4*>(xp));
+            xz = __ldg(reinterpret_cast<const float4*>(xp + H));
+            xn = __ldg(reinterpret_cast<const float4*>(xp + 2 * H));
+        }
+        if (valid && T > 1) {
+            x1r = __ldg(reinterpret_cast<const float4*>(xp + xstep));
+            x1z = __ldg(reinterpret_cast<const float4*>(xp + xstep + H));
+            x1n = __ldg(reinterpret_cast<const float4*>(xp + xstep + 2 * H));
+        }
+        const int q = warp & 3;
+        int p = 0;
+        for (int t = 0; t < T; ++t) {
+            // prefetch the x-projections of step t+2 while the tensor core works
+            float4 nxr = zero4, nxz = zero4, nxn = zero4;
+            if (valid && t + 2 < T) {
+                const float* xq = xp + (size_t)(t + 2) * xstep;
+                nxr = __ldg(reinterpret_cast<const float4*>(xq));
+                nxz = __ldg(reinterpret_cast<const float4*>(xq + H));
+                nxn = __ldg(reinterpret_cast<const float4*>(xq + 2 * H));
+            }
+            tc::mbar_wait(&acc_full[sl], (uint32_t)(t & 1));
+            tc::tc_fence_after();
+            if (sl == 0 && wt == 0) SEQ_STAMP(3);
+            if (q < 3) {
+                // accumulator lanes 32*q.. = gate q of my CTA's 32 units; columns = the slice's utterances
+                float v[16];
+                tmem_ld_32x16(tmem_d + ((uint32_t)(q * 32) << 16), v);
+                tc::tmem_ld_wait();
+                float* dst = myPre + (q * 32 + lane) * SQ_PRE_LD;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) dst[c] = v[c];
+            }
+            tc::tc_fence_before();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");     // this slice's four warps only
+            if (sl == 0 && wt == 0) SEQ_STAMP(4);
+            float hn[4], gr[4], gz[4], gn[4], ghn[4];
+            const float xrv[4] = {xr.x, xr.y, xr.z, xr.w}, xzv[4] = {xz.x, xz.y, xz.z, xz.w}, xnv[4] = {xn.x, xn.y, xn.z, xn.w};
+            const float bhv[4] = {b_hn.x, b_hn.y, b_hn.z, b_hn.w}, hov[4] = {hold.x, hold.y, hold.z, hold.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float pr = myPre[(0 * 32 + 4 * jq + e) * SQ_PRE_LD + b];
+                const float pz = myPre[(1 * 32 + 4 * jq + e) * SQ_PRE_LD + b];
+                ghn[e] = myPre[(2 * 32 + 4 * jq + e) * SQ_PRE_LD + b] + bhv[e];
+                gr[e] = sigmoid_fast(xrv[e] + pr);
+                gz[e] = sigmoid_fast(xzv[e] + pz);
+                gn[e] = tanh_fast(xnv[e] + gr[e] * ghn[e]);
+                hn[e] = valid ? ((1.f - gz[e]) * gn[e] + gz[e] * hov[e]) : 0.f;
+            }
+            hold = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            if (sl == 0 && wt == 0) SEQ_STAMP(7);
+            // scatter my 16 bytes of h_{t+1} (tf32-rounded operand copy) into the other buffer of every CTA
+            {
+                const uint32_t poff = (uint32_t)(p ^ 1) * (NC * SQ_H_KB), boff = (uint32_t)(p ^ 1) * 8;
+                const uint32_t w0 = __float_as_uint(to_tf32(hn[0])), w1 = __float_as_uint(to_tf32(hn[1]));
+                const uint32_t w2 = __float_as_uint(to_tf32(hn[2])), w3 = __float_as_uint(to_tf32(hn[3]));
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
-                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(
-                                     rem_h[c] + poff + (uint32_t)(i * 2048)),      // utterance b+16 = two 8-row groups further
-                                 "r"(w0), "r"(w1), "r"(rem_bar[c] + boff)
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                                     rem_h[c] + poff),
+                                 "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(rem_bar[c] + boff)
                                  : "memory");
             }
-        }
-        if (tid == 0) SEQ_STAMP(5);
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            if (!valid[i]) continue;
-            float* yo = yp[i] + (size_t)t * ystep;
-            if (y_fs == 1) {
-                *reinterpret_cast<float2*>(yo) = hnew[i];
-            } else {
-                yo[0] = hnew[i].x;
-                yo[y_fs] = hnew[i].y;
+            if (sl == 0 && wt == 0) SEQ_STAMP(5);
+            if (valid) {
+                float* yo = yp + (size_t)t * ystep;
+                if (y_fs == 1) {
+                    *reinterpret_cast<float4*>(yo) = hold;
+                } else {
+                    yo[0] = hn[0]; yo[y_fs] = hn[1]; yo[2 * y_fs] = hn[2]; yo[3 * y_fs] = hn[3];
+                }
+                if (gp) {
+                    float* go = gp + (size_t)t * G * 4 * H;
+                    *reinterpret_cast<float4*>(go) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+                    *reinterpret_cast<float4*>(go + H) = make_float4(gz[0], gz[1], gz[2], gz[3]);
+                    *reinterpret_cast<float4*>(go + 2 * H) = make_float4(gn[0], gn[1], gn[2], gn[3]);
+                    *reinterpret_cast<float4*>(go + 3 * H) = make_float4(ghn[0], ghn[1], ghn[2], ghn[3]);
+                }
             }
-            if (gp[i]) {
-                float* go = gp[i] + (size_t)t * G * 4 * H;
-                *reinterpret_cast<float2*>(go) = gr[i];
-                *reinterpret_cast<float2*>(go + H) = gz[i];
-                *reinterpret_cast<float2*>(go + 2 * H) = gn[i];
-                *reinterpret_cast<float2*>(go + 3 * H) = ghn[i];
-            }
+            if (sl == 0 && wt == 0) SEQ_STAMP(6);
+            p ^= 1;
+            xr = x1r; xz = x1z; xn = x1n;
+            x1r = nxr; x1z = nxz; x1n = nxn;
         }
-        if (tid == 0) SEQ_STAMP(6);
-        p ^= 1;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            xr[i] = x1r[i]; xz[i] = x1z[i]; xn[i] = x1n[i];
-            x1r[i] = nxr[i]; x1z[i] = nxz[i]; x1n[i] = nxn[i];
-        }
-    }
-    if (hT) {
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-            if (valid[i]) *reinterpret_cast<float2*>(hT + ((size_t)g * B + bg[i]) * H + u0) = hold[i];
-    }
-    // drain: the last step's scatter is still in flight towards my buffers -- wait for it before anybody exits
-    if (T > 0 && warp == 3) {
-        if (p) tc::mbar_wait(&hbar[1], ph1); else tc::mbar_wait(&hbar[0], ph0);
+        if (hT && valid) *reinterpret_cast<float4*>(hT + ((size_t)g * B + bg) * H + u0) = hold;
     }
     tc::tc_fence_before();
     __syncthreads();
     cluster.sync();
-    if (warp == 3) tc::tmem_dealloc<SQ_TMEM_COLS>(tmem_base);
+    if (warp == 8) tc::tmem_dealloc<SQ_TMEM_COLS>(tmem_base);
 }
 
-constexpr size_t seq_smem_bytes(int NC, int NI) {
-    return 1024 + 2 * (size_t)NC * (SQ_NB16 * NI * 128) + (96 * (SQ_NB16 * NI + 1) + 4) * 4 + 64;
+constexpr size_t seq_smem_bytes(int NC) {
+    return 1024 + 2 * 2 * (size_t)NC * SQ_H_KB + (2 * 96 * SQ_PRE_LD + 4) * 4 + 128;
 }
 
-template <int NC, int NI>
-void seq_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int G, int nslices, cudaStream_t st) {
+template <int NC>
+void seq_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int G, int npairs, cudaStream_t st) {
     cfg = cudaLaunchConfig_t{};
-    cfg.gridDim = dim3(NC, G, nslices);
+    cfg.gridDim = dim3(NC, G, npairs);
     cfg.blockDim = dim3(SQ_THREADS);
-    cfg.dynamicSmemBytes = seq_smem_bytes(NC, NI);
+    cfg.dynamicSmemBytes = seq_smem_bytes(NC);
     cfg.stream = st;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NC;
@@ -379,37 +371,30 @@ void seq_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int G, int nsli
     cfg.numAttrs = 1;
 }
 
-template <int NC, int NI>
+template <int NC>
 int max_clusters_tc() {
-    if (cudaFuncSetAttribute(gru_seq_tc_kernel<NC, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(NC, NI)) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gru_seq_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(NC)) != cudaSuccess) return -2;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    seq_cfg<NC, NI>(cfg, attr, 1, 1024, nullptr);
+    seq_cfg<NC>(cfg, attr, 1, 1024, nullptr);
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gru_seq_tc_kernel<NC, NI>, &cfg) != cudaSuccess) return -2;
+    if (cudaOccupancyMaxActiveClusters(&n, gru_seq_tc_kernel<NC>, &cfg) != cudaSuccess) return -2;
     return n;
-}
-
-template <int NC, int NI>
-int launch_seq_tc(const float* xproj, const SeqPtrs& ptrs, const float* h0, float* y, float* hT, float* gates, int B, int T,
-                  int G, int H, int y_fs, int y_gs, cudaStream_t st) {
-    CRUSE_CUDA_OK(cudaFuncSetAttribute(gru_seq_tc_kernel<NC, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(NC, NI)));
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    seq_cfg<NC, NI>(cfg, attr, G, (B + SQ_NB16 * NI - 1) / (SQ_NB16 * NI), st);
-    CRUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gru_seq_tc_kernel<NC, NI>, xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs));
-    return 0;
 }
 
 template <int NC>
 int launch_seq_tc_nc(const float* xproj, const SeqPtrs& ptrs, const float* h0, float* y, float* hT, float* gates, int B, int T,
-                     int G, int H, int y_fs, int y_gs, cudaStream_t st) {
-    // 16 utterances per cluster while all clusters are co-resident (shortest step); 32 when that avoids a second wave
-    static thread_local int cap16 = -1;
-    if (cap16 < 0) cap16 = max_clusters_tc<NC, 1>();
-    const int need16 = G * ((B + 15) / 16);
-    if (cap16 > 0 && need16 > cap16) return launch_seq_tc<NC, 2>(xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, st);
-    return launch_seq_tc<NC, 1>(xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, st);
+                     int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts, long long y_bs, long long y_ts, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(gru_seq_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(NC)));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    seq_cfg<NC>(cfg, attr, G, (B + 2 * SQ_NB - 1) / (2 * SQ_NB), st);      // one cluster per (group, pair of 16-utterance slices)
+    CRUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gru_seq_tc_kernel<NC>, xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts));
+    return 0;
 }
 
 }  // namespace
@@ -437,16 +422,16 @@ extern "C" int cruse_debug_seq_timing(long long* out_host, int n) {
     }
 
 extern "C" int cruse_gru_seq_tc_max_clusters(int H) {
-#define CALL(N) max_clusters_tc<N, 1>()
+#define CALL(N) max_clusters_tc<N>()
     SEQ_TC_DISPATCH((H + SQ_U - 1) / SQ_U, CALL)
 #undef CALL
     set_error("gru_seq_tc_max_clusters: unsupported H=%d", H);
     return -1;
 }
 
-extern "C" int cruse_gru_seq_fwd_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0,
-                                    float* y, float* hT, float* gates, int B, int T, int G, int H, int y_fs, int y_gs,
-                                    void* stream) {
+static int gru_seq_tc_impl(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0, float* y,
+                           float* hT, float* gates, int B, int T, int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts,
+                           long long y_bs, long long y_ts, void* stream) {
     CRUSE_CHECK_ARG(xproj && y && w_hh, "gru_seq_fwd_tc: null pointer");
     CRUSE_CHECK_ARG(B > 0 && T >= 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0 && H <= 256,
                     "gru_seq_fwd_tc: bad sizes B=%d T=%d G=%d H=%d (H%%4==0, H<=256, G<=%d)", B, T, G, H, CRUSE_MAX_GROUPS);
@@ -458,9 +443,22 @@ extern "C" int cruse_gru_seq_fwd_tc(const float* xproj, const float* const* w_hh
         ptrs.b_hh[i] = b_hh ? b_hh[i] : nullptr;
     }
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(N) launch_seq_tc_nc<N>(xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, st)
+#define CALL(N) launch_seq_tc_nc<N>(xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, st)
     SEQ_TC_DISPATCH((H + SQ_U - 1) / SQ_U, CALL)
 #undef CALL
     set_error("gru_seq_fwd_tc: unsupported H=%d", H);
     return -1;
+}
+
+extern "C" int cruse_gru_seq_fwd_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0,
+                                    float* y, float* hT, float* gates, int B, int T, int G, int H, int y_fs, int y_gs,
+                                    void* stream) {
+    return gru_seq_tc_impl(xproj, w_hh, b_hh, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, T, 1, T, 1, stream);
+}
+
+extern "C" int cruse_gru_seq_chunk_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0,
+                                      float* y, float* hT, int B, int Tc, int G, int H, int y_fs, int y_gs, long long x_bs,
+                                      long long x_ts, long long y_bs, long long y_ts, void* stream) {
+    CRUSE_CHECK_ARG(x_bs > 0 && x_ts > 0 && y_bs > 0 && y_ts > 0, "gru_seq_chunk_tc: row strides must be positive");
+    return gru_seq_tc_impl(xproj, w_hh, b_hh, h0, y, hT, nullptr, B, Tc, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, stream);
 }

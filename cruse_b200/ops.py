@@ -156,8 +156,15 @@ def conv_nparts(B, T):
     return lib().cruse_conv_nparts(B, T)
 
 
-def conv_fwd(x, w, bias, scale, shift, alpha, act, kt, fstride, want_stats=False, hist=None):
-    """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout] (+ per-CTA BN partials [nparts, 2*Cout])."""
+def conv_fwd(x, w, bias, scale, shift, alpha, act, kt, fstride, want_stats=False, hist=None, exact=False):
+    """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout] (+ per-CTA BN partials [nparts, 2*Cout]).
+    exact=True pins this call to the exact-fp32 CUDA-core kernel whatever the process-wide conv mode is."""
+    if exact and get_conv_mode() == "tf32":
+        set_conv_mode("fp32")
+        try:
+            return conv_fwd(x, w, bias, scale, shift, alpha, act, kt, fstride, want_stats, hist)
+        finally:
+            set_conv_mode("tf32")
     _req(x, "x", 4)
     _req(w, "w", 4)
     for n, t in (("bias", bias), ("scale", scale), ("shift", shift), ("alpha", alpha)):
@@ -299,6 +306,64 @@ def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False, mod
     if want_gates:
         return (y, hT, gates) if want_hT else (y, gates)
     return (y, hT) if want_hT else y
+
+
+def gru_ih_gemm_tm(x, w_ih, b_ih, b_hh, B, T):
+    """x [B*T, G*H] in frame order -> xproj [T, B, G, 3H] TIME-MAJOR (tcgen05, tf32): a chunk of frames of the
+    result is one contiguous row range, which is what the two-layer wavefront needs."""
+    _req(x, "x", 2)
+    G = len(w_ih)
+    H = w_ih[0].shape[1]
+    if tuple(x.shape) != (B * T, G * H):
+        raise RuntimeError(f"gru_ih_gemm_tm: x shape {tuple(x.shape)} != {(B * T, G * H)}")
+    xproj = torch.empty(T, B, G, 3 * H, device=x.device, dtype=torch.float32)
+    _call("cruse_gru_ih_gemm_tm_tc", _p(x), _ptr_table(w_ih), _ptr_table(b_ih), _ptr_table(b_hh), _p(xproj), B, T, G, H,
+          _stream(), meta=(f"gru_ih[tf32,tm] G{G} H{H}", _nb(x, xproj, *w_ih), 2 * B * T * G * H * 3 * H))
+    return xproj
+
+
+def gru_seq_chunk(xproj_tm, w_hh, b_hh, h0, y, hT, t0, t1, interleave, y_time_major):
+    """frames [t0, t1) of the recurrence: xproj_tm [T,B,G,3H] time-major; y either time-major [T,B,G*H] or frame
+    order [B,T,G*H]; h0 / hT [G,B,H] carry the state from / to the neighbouring chunks (h0 None = zero state)."""
+    T, B, G, H3 = xproj_tm.shape
+    H = H3 // 3
+    if y_time_major:
+        y_bs, y_ts, yoff = 1, B, t0 * B * G * H
+    else:
+        y_bs, y_ts, yoff = T, 1, t0 * G * H
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    _call("cruse_gru_seq_chunk_tc", xproj_tm.data_ptr() + 4 * t0 * B * G * H3, _ptr_table(w_hh), _ptr_table(b_hh), _p(h0),
+          y.data_ptr() + 4 * yoff, _p(hT), B, t1 - t0, G, H, y_fs, y_gs, 1, B, y_bs, y_ts, _stream(),
+          meta=(f"gru_seq_chunk[tf32] G{G} H{H} T{t1 - t0}", 4 * (t1 - t0) * B * G * (H3 + H), 2 * B * (t1 - t0) * G * H * 3 * H))
+
+
+# two-layer wavefront of the GGRU bottleneck (cruse_net.GGRU._wavefront); CRUSE_GRU_WAVEFRONT=0 runs the layers back to back
+GRU_WAVEFRONT = os.environ.get("CRUSE_GRU_WAVEFRONT", "1") != "0"
+
+
+def gru_seq_max_clusters(H):
+    n = lib().cruse_gru_seq_tc_max_clusters(H)
+    if n < 0:
+        check(n, "cruse_gru_seq_tc_max_clusters")
+    return n
+
+
+def layernorm_fwd_into(x, gamma, beta, eps, y):
+    """LayerNorm over the rows of a contiguous slice, written into a preallocated slice (no allocation: runs on side streams)."""
+    D = x.shape[-1]
+    rows = x.numel() // D
+    _call("cruse_layernorm_fwd", _p(x), _p(gamma), _p(beta), float(eps), None, _p(y), None, None, rows, D, _stream(),
+          meta=(f"layernorm D{D}", _nb(x, y), 8 * x.numel()))
+
+
+def gru_ih_gemm_into(x, w_ih, b_ih, b_hh, xproj, tables=None):
+    """tcgen05 input projections of a contiguous row range into a preallocated xproj slice."""
+    G = len(w_ih)
+    H = w_ih[0].shape[1]
+    M = x.shape[0]
+    tw, tbi = tables if tables is not None else (_ptr_table(w_ih), _ptr_table(b_ih))
+    _call("cruse_gru_ih_gemm_tc", _p(x), tw, tbi, _ptr_table(b_hh), _p(xproj), M, G, H, _stream(),
+          meta=(f"gru_ih[tf32] G{G} H{H}", _nb(x, xproj, *w_ih), 2 * M * G * H * 3 * H))
 
 
 def layernorm_fwd(x, gamma, beta, eps, residual=None, want_stats=False):

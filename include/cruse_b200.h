@@ -128,15 +128,29 @@ int cruse_gru_seq_fwd(const float* xproj, const float* const* w_hh, const float*
                       const float* h0, float* y, float* hT,
                       int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
 /* same contract with the per-step W_hh.h product on the tensor cores (tcgen05.mma kind::tf32, W_hh slice
- * resident in shared memory, accumulator in TMEM; one cluster of ceil(H/32) CTAs per (group, 16 utterances)).
+ * resident in tensor memory, accumulators in TMEM; one cluster of ceil(H/32) CTAs per (group, 2 x 16 utterances)).
  * Only the matmul operands are rounded to tf32; gate math and the z*h carry stay fp32.  H % 4 == 0, H <= 256.
  * gates [B,T,G,4,H] or NULL: saves r, z, n and (W_hn.h + b_hn) of every step for the backward pass. */
 int cruse_gru_seq_fwd_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh,
                          const float* h0, float* y, float* hT, float* gates,
                          int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
 
-/* how many clusters of the tcgen05 recurrence kernel the current device can hold at once (each serves 16
- * utterances of one group); B*G/16 above this runs in waves.  <0 on error. */
+/* the two entry points of the time-chunked two-layer wavefront (layer 2 of model/cruse_net.py:47-50 starts on chunk k
+ * while layer 1, :41-45, is still running chunk k+1; GRU-internal buffers are TIME-MAJOR [T, B, ...] so that a chunk of
+ * frames is one contiguous row range):
+ *  cruse_gru_ih_gemm_tm_tc: as cruse_gru_ih_gemm_tc for x [B*T, G*H] in frame order, but row (b,t) of the result is
+ *    written to row t*B + b of xproj [T, B, G, 3H].
+ *  cruse_gru_seq_chunk_tc: Tc steps of the recurrence from state h0 to state hT (both [G,B,H], hT may be NULL);
+ *    row (b, t) of xproj / y is b*x_bs + t*x_ts / b*y_bs + t*y_ts rows (a row = G*3H / G*H floats) past the pointers,
+ *    which the caller has already advanced to the chunk's first frame. */
+int cruse_gru_ih_gemm_tm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
+                            const float* const* b_hh, float* xproj, int B, int T, int G, int H, void* stream);
+int cruse_gru_seq_chunk_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh,
+                           const float* h0, float* y, float* hT, int B, int Tc, int G, int H, int y_fs, int y_gs,
+                           long long x_bs, long long x_ts, long long y_bs, long long y_ts, void* stream);
+
+/* how many clusters of the tcgen05 recurrence kernel the current device can hold at once (each serves two
+ * software-pipelined slices of 16 utterances of one group); G*ceil(B/32) above this runs in waves.  <0 on error. */
 int cruse_gru_seq_tc_max_clusters(int H);
 
 /* ---- nn.LayerNorm(D) at model/cruse_net.py:32-33,46,51.  x,y [rows, D]; mean/rstd [rows] or NULL.

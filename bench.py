@@ -241,10 +241,24 @@ def run_ours(args):
             distrib.sync_grad(params)          # the one collective of the path: flat fp32 gradient all_reduce over NCCL
         return loss.detach()
 
+    # inference: the whole step (~60 launches on 4 streams) is captured once into a CUDA graph and replayed
+    captured = None
+    if not train and not args.no_graph:
+        captured = pipeline.CapturedForwardLoss(model, B, L, N_FFT, HOP)
+        captured.noisy.copy_(noisy)
+        captured.clean.copy_(clean)
+
+    def step_eager():
+        return run(noisy, clean)
+
     def step():
+        if captured is not None:
+            return captured.replay()
         return run(noisy, clean)
 
     def step_host():
+        if captured is not None:
+            return captured(noisy_h, clean_h)[0].to("cpu")
         loss = run(noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True))
         return loss.to("cpu")
 
@@ -260,7 +274,7 @@ def run_ours(args):
     # ---- kernel-launch count of one step
     prof = ops.Profile(timing=False)
     ops.set_profile(prof)
-    loss = step()
+    loss = step_eager()
     ops.set_profile(None)
     launches_per_step = prof.launches
 
@@ -309,7 +323,7 @@ def run_ours(args):
         flush.zero_()
         prof = ops.Profile(timing=True)
         ops.set_profile(prof)
-        step()
+        step_eager()
         ops.set_profile(None)
         for i, (n, tag, by, fl, ms) in enumerate(prof.rows()):
             rows_acc.setdefault((i, n, tag, by, fl), []).append(ms)
@@ -331,8 +345,10 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step_per_gpu": frames, "l2": "256 MB flush write between timed steps",
-                   "launch": "eager ctypes launches on torch's current stream",
-                   "gru_matmul_operands": "tf32 (tcgen05), fp32 accumulate; everything else fp32",
+                   "launch": ("one CUDA graph replay per step (captured from the ctypes launches, 4 streams)" if captured is not None
+                              else "eager ctypes launches on torch's current stream"),
+                   "tensor_core_operands": "tf32 (tcgen05, fp32 accumulate in TMEM) in the conv / convT implicit GEMMs and both GRU matmuls; everything else fp32",
+                   "gru": "two layers side by side (time-chunked wavefront, 3 streams), 2 x 16 utterances software-pipelined per cluster",
                    "collective": ("one flat fp32 gradient all_reduce (NCCL) per step" if (train and world > 1) else "none")},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(), "loss": float(loss), "kernels": kernels,
@@ -361,6 +377,7 @@ def main():
                     help="infer = BASELINE configs[1] (the headline, default); train = configs[2]/[3]")
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the bounded CPU sample (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="inference: launch eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--table", default=None, help="write the per-kernel roofline table (markdown) here")
     args = ap.parse_args()
     if args.impl == "reference":

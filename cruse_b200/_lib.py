@@ -50,6 +50,7 @@ SIGNATURES = {
     "cruse_gru_ih_gemm_tm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_gru_seq_chunk_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp]),
     "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),
+    "cruse_layernorm_interleave_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_ll, c_int, c_int, c_fp]),
     "cruse_wo_male_fwd_bwd": (c_int, [c_fp, CplxLayout, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp,
                                       c_int, c_int, c_int, c_fp]),
     "cruse_wo_male_ws_bytes": (C.c_size_t, []),

@@ -105,12 +105,16 @@ class GGRU(nn.Module):
         for k in range(nch):
             t0, t1 = bounds[k], bounds[k + 1]
             with torch.cuda.stream(sA):                                   # layer 1, frames [t0,t1)  (:41-45)
-                ops.gru_seq_chunk(xp1, w_hh1, b_hh1, hA[(k + 1) & 1] if k else None, y1, hA[k & 1], t0, t1, True, True)
+                # layer-1 outputs are stored concatenated (16-byte stores); LayerNorm 1 applies the :43-45 interleave
+                ops.gru_seq_chunk(xp1, w_hh1, b_hh1, hA[(k + 1) & 1] if k else None, y1, hA[k & 1], t0, t1, G != 4, True)
                 eA = torch.cuda.Event()
                 eA.record(sA)
             with torch.cuda.stream(sC):                                   # LayerNorm 1 + layer-2 input projections (:46-48)
                 sC.wait_event(eA)
-                ops.layernorm_fwd_into(y1[t0:t1], self.ln1.weight, self.ln1.bias, self.ln1.eps, z1[t0:t1])
+                if G == 4:
+                    ops.layernorm_interleave_fwd_into(y1[t0:t1], self.ln1.weight, self.ln1.bias, self.ln1.eps, z1[t0:t1], G)
+                else:
+                    ops.layernorm_fwd_into(y1[t0:t1], self.ln1.weight, self.ln1.bias, self.ln1.eps, z1[t0:t1])
                 ops.gru_ih_gemm_into(z1[t0:t1].view(-1, D), w_ih2, b_ih2, b_hh2, xp2[t0:t1], tables=(tw, tb))
                 eC = torch.cuda.Event()
                 eC.record(sC)

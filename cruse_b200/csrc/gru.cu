@@ -403,6 +403,53 @@ extern "C" int cruse_gru_seq_fwd(const float* xproj, const float* const* w_hh, c
     }
 }
 
+namespace cruse {
+// LayerNorm over a row whose INPUT is the concatenation [G][H] of the grouped GRU outputs and whose OUTPUT is the
+// stack(dim=-1)+flatten interleave of model/cruse_net.py:43-45 (feature j = h*G + g), fused: the recurrence kernel
+// then stores 16 contiguous bytes per thread and step instead of four 4-byte stores 16 bytes apart.  G == 4.
+__global__ void __launch_bounds__(256)
+layernorm_interleave4_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, float* __restrict__ y, long long rows, int H) {
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int D = 4 * H;
+    for (long long row = (long long)blockIdx.x * nwarps + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * nwarps) {
+        const float* xr = x + row * D;
+        float* yr = y + row * D;
+        float s = 0.f;
+        for (int h = lane; h < H; h += 32) s += (__ldg(xr + h) + __ldg(xr + H + h)) + (__ldg(xr + 2 * H + h) + __ldg(xr + 3 * H + h));
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+        for (int h = lane; h < H; h += 32) {
+            const float a = __ldg(xr + h) - mean, b = __ldg(xr + H + h) - mean, c = __ldg(xr + 2 * H + h) - mean, d = __ldg(xr + 3 * H + h) - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+        for (int h = lane; h < H; h += 32) {
+            const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + 4 * h)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o;
+            o.x = (__ldg(xr + h) - mean) * rstd * gm.x + bt.x;
+            o.y = (__ldg(xr + H + h) - mean) * rstd * gm.y + bt.y;
+            o.z = (__ldg(xr + 2 * H + h) - mean) * rstd * gm.z + bt.z;
+            o.w = (__ldg(xr + 3 * H + h) - mean) * rstd * gm.w + bt.w;
+            *reinterpret_cast<float4*>(yr + 4 * h) = o;
+        }
+    }
+}
+}  // namespace cruse
+
+extern "C" int cruse_layernorm_interleave_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y,
+                                              long long rows, int D, int G, void* stream) {
+    CRUSE_CHECK_ARG(x && y, "layernorm_interleave_fwd: null pointer");
+    CRUSE_CHECK_ARG(rows > 0 && D > 0 && G == 4 && D % 4 == 0, "layernorm_interleave_fwd: needs G == 4 and D %% 4 == 0 (rows=%lld D=%d G=%d)", rows, D, G);
+    long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)cruse::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cruse::layernorm_interleave4_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, rows, D / 4);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int cruse_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps,
                                    const float* residual, float* y, float* mean, float* rstd, long long rows, int D,
                                    void* stream) {

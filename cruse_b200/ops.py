@@ -341,11 +341,18 @@ def gru_seq_chunk(xproj_tm, w_hh, b_hh, h0, y, hT, t0, t1, interleave, y_time_ma
 GRU_WAVEFRONT = os.environ.get("CRUSE_GRU_WAVEFRONT", "1") != "0"
 
 
+_max_clusters_cache = {}
+
+
 def gru_seq_max_clusters(H):
-    n = lib().cruse_gru_seq_tc_max_clusters(H)
-    if n < 0:
-        check(n, "cruse_gru_seq_tc_max_clusters")
-    return n
+    """co-resident clusters of the recurrence kernel on the current device (a device property: cached)."""
+    key = (torch.cuda.current_device(), H)
+    if key not in _max_clusters_cache:
+        n = lib().cruse_gru_seq_tc_max_clusters(H)
+        if n < 0:
+            check(n, "cruse_gru_seq_tc_max_clusters")
+        _max_clusters_cache[key] = n
+    return _max_clusters_cache[key]
 
 
 def layernorm_fwd_into(x, gamma, beta, eps, y):
@@ -354,6 +361,15 @@ def layernorm_fwd_into(x, gamma, beta, eps, y):
     rows = x.numel() // D
     _call("cruse_layernorm_fwd", _p(x), _p(gamma), _p(beta), float(eps), None, _p(y), None, None, rows, D, _stream(),
           meta=(f"layernorm D{D}", _nb(x, y), 8 * x.numel()))
+
+
+def layernorm_interleave_fwd_into(x, gamma, beta, eps, y, G):
+    """LayerNorm of rows stored as the concatenation of the G group outputs, written in the interleaved feature order
+    of cruse_net.py:43-45 into a preallocated slice."""
+    D = x.shape[-1]
+    rows = x.numel() // D
+    _call("cruse_layernorm_interleave_fwd", _p(x), _p(gamma), _p(beta), float(eps), _p(y), rows, D, G, _stream(),
+          meta=(f"layernorm_il D{D}", _nb(x, y), 8 * x.numel()))
 
 
 def gru_ih_gemm_into(x, w_ih, b_ih, b_hh, xproj, tables=None):

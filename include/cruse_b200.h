@@ -158,6 +158,11 @@ int cruse_gru_seq_tc_max_clusters(int H);
 int cruse_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps,
                         const float* residual, float* y, float* mean, float* rstd,
                         long long rows, int D, void* stream);
+/* LayerNorm 1 of the bottleneck fused with the stack(dim=-1)+flatten interleave of model/cruse_net.py:43-46:
+ * x [rows, D] holds the G group outputs CONCATENATED ([G][D/G]), y[row, h*G + g] = LN(x)[g*H + h]*gamma[h*G+g]+beta[h*G+g]
+ * (statistics are permutation invariant).  G == 4. */
+int cruse_layernorm_interleave_fwd(const float* x, const float* gamma, const float* beta, float eps, float* y,
+                                   long long rows, int D, int G, void* stream);
 
 /* ---- a8: weighted-magnitude loss wo_male, loss_func/loss.py:121-148, forward + d/d(est).
  *  Complex tensors are addressed as  re = p[b*sb + t*st + f*sf], im = p[... + im_off]  so both the

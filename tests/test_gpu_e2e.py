@@ -195,3 +195,31 @@ def test_long_sequence_drift_T1001(cuda):
             mse = float(((e1.cpu() - e0.permute(0, 2, 3, 1)) ** 2).mean())
             _log(f"drift T{T} {mode}: mask {em:.2e} specMSE {mse:.2e} loss {abs(float(l1) - float(l0)) / abs(float(l0)):.2e}")
             assert em <= TOL[mode] and mse < 1e-4
+
+
+def test_captured_graph_and_wavefront_match_eager(cuda):
+    """the CUDA-graph replay of the step (pipeline.CapturedForwardLoss) and the two-layer GRU wavefront are scheduling
+    changes only: bit-identical loss / mask to the eager launch sequence, for new inputs copied into the static buffers,
+    and the wavefront agrees with the back-to-back layers to the tf32 gate."""
+    from cruse_b200 import ops, pipeline
+    from oracle import cruse_oracle as o
+    ours, _ = _pair(256, "relu", cuda)
+    ours.eval()
+    B, L = 3, 64000                                     # T = 201 >= GGRU.WAVEFRONT_MIN_T
+    cap = pipeline.CapturedForwardLoss(ours, B, L, 512, 320)
+    for seed in (1, 2):
+        g = torch.Generator().manual_seed(seed)
+        noisy, clean = 0.1 * torch.randn(B, L, generator=g), 0.05 * torch.randn(B, L, generator=g)
+        with torch.no_grad():
+            l0, w0, e0, m0 = pipeline.forward_loss(ours, noisy.to(cuda), clean.to(cuda), 512, 320)
+        l1, w1, e1, m1 = cap(noisy.pin_memory(), clean.pin_memory())
+        torch.cuda.synchronize()
+        assert torch.equal(l0, l1) and torch.equal(m0, m1) and torch.equal(w0, w1)
+    old = ops.GRU_WAVEFRONT
+    ops.GRU_WAVEFRONT = False
+    try:
+        with torch.no_grad():
+            l2, w2, e2, m2 = pipeline.forward_loss(ours, noisy.to(cuda), clean.to(cuda), 512, 320)
+    finally:
+        ops.GRU_WAVEFRONT = old
+    assert rel_err(m2, m0) <= 1e-3 and abs(float(l2) - float(l0)) <= 1e-3 * abs(float(l0))

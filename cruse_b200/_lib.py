@@ -41,6 +41,7 @@ SIGNATURES = {
     "cruse_convT_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_f, c_f] + [c_fp] * 6 + [c_fp]),
     "cruse_bn_fold": (c_int, [c_fp, c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_int, c_fp]),
+    "cruse_bn_fold_many": (c_int, [c_pp] * 4 + [c_fp, c_pp, c_pp, c_fp, c_int, c_fp]),
     "cruse_bn_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_int, c_int, c_fp]),
     "cruse_gru_ih_gemm": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),
     "cruse_gru_ih_gemm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),

@@ -198,11 +198,11 @@ class unet_2(nn.Module):
     def _alpha(self, name):
         return getattr(self, name).weight if self.act_kind == "prelu" else None
 
-    def _stage(self, h, conv, bn, alpha, kt_fs, train, hist=None):
+    def _stage(self, h, conv, bn, alpha, kt_fs, train, hist=None, fold=None):
         """conv + BN + act.  eval: one fused kernel; train: conv(+stat partials) -> finalize -> bn_act."""
         kt, fs = kt_fs
         if not train:
-            scale, shift = ops.bn_fold(bn)
+            scale, shift = fold if fold is not None else ops.bn_fold(bn)
             return ops.conv_fwd(h, conv.weight, conv.bias, scale, shift, alpha, self.act_kind, kt, fs, hist=hist)
         z, stats = ops.conv_fwd(h, conv.weight, conv.bias, None, None, None, "none", kt, fs, want_stats=True)
         B, T, Cn, F = z.shape
@@ -224,11 +224,15 @@ class unet_2(nn.Module):
         enc, skips = [], []
         hists = state.hist if state is not None and state.hist else [None] * n
         new_hist = []
+        folds = {}
+        if not train:                                   # all eval-mode BatchNorm folds of the pass in one launch
+            names = [f"bn{k}" for k in range(1, n + 1)] + [f"bn{k}_t" for k in range(n, 1, -1)]
+            folds = dict(zip(names, ops.bn_fold_many([getattr(self, nm) for nm in names])))
         for k in range(1, n + 1):                                                                   # :149-152 repaired
             if want_state:
                 new_hist.append(h[:, -1].contiguous())
             h = self._stage(h, getattr(self, f"conv{k}"), getattr(self, f"bn{k}"), self._alpha(f"act{k}"), (2, 2), train,
-                            hist=hists[k - 1])
+                            hist=hists[k - 1], fold=folds.get(f"bn{k}"))
             enc.append(h)
             skips.append(ops.conv_fwd(h, getattr(self, f"skip_connect_{k}").weight, None, None, None, None,
                                       "none", 1, 1))                                                 # :153-156
@@ -244,7 +248,7 @@ class unet_2(nn.Module):
             conv, bn = getattr(self, f"conv{k}_t"), getattr(self, f"bn{k}_t")
             alpha = self._alpha(f"act{k}_t")
             if not train:
-                scale, shift = ops.bn_fold(bn)
+                scale, shift = folds[f"bn{k}_t"]
                 out = ops.convT_fwd(out, conv.weight, conv.bias, scale, shift, alpha, self.act_kind,
                                     skips[k - 2], self.freqs[k - 1])
             else:

@@ -525,6 +525,50 @@ extern "C" int cruse_bn_fold(const float* gamma, const float* beta, const float*
     return 0;
 }
 
+namespace cruse {
+struct BnFoldMany {
+    const float* gamma[8];
+    const float* beta[8];
+    const float* mean[8];
+    const float* var[8];
+    float* scale[8];
+    float* shift[8];
+    float eps[8];
+    int C[8];
+};
+__global__ void bn_fold_many_kernel(const BnFoldMany a) {
+    const int i = blockIdx.x;
+    for (int c = threadIdx.x; c < a.C[i]; c += blockDim.x) {
+        const float inv = 1.0f / sqrtf(a.var[i][c] + a.eps[i]);
+        const float g = a.gamma[i] ? a.gamma[i][c] : 1.f;
+        a.scale[i][c] = g * inv;
+        a.shift[i][c] = (a.beta[i] ? a.beta[i][c] : 0.f) - a.mean[i][c] * g * inv;
+    }
+}
+}  // namespace cruse
+
+extern "C" int cruse_bn_fold_many(const float* const* gamma, const float* const* beta, const float* const* running_mean,
+                                  const float* const* running_var, const float* eps, float* const* scale, float* const* shift,
+                                  const int* C, int n, void* stream) {
+    CRUSE_CHECK_ARG(running_mean && running_var && scale && shift && eps && C, "bn_fold_many: null pointer");
+    CRUSE_CHECK_ARG(n > 0 && n <= 8, "bn_fold_many: n=%d must be in [1, 8]", n);
+    cruse::BnFoldMany a;
+    for (int i = 0; i < n; ++i) {
+        CRUSE_CHECK_ARG(running_mean[i] && running_var[i] && scale[i] && shift[i] && C[i] > 0, "bn_fold_many: bad entry %d", i);
+        a.gamma[i] = gamma ? gamma[i] : nullptr;
+        a.beta[i] = beta ? beta[i] : nullptr;
+        a.mean[i] = running_mean[i];
+        a.var[i] = running_var[i];
+        a.scale[i] = scale[i];
+        a.shift[i] = shift[i];
+        a.eps[i] = eps[i];
+        a.C[i] = C[i];
+    }
+    cruse::bn_fold_many_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(a);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
                                 const float* skip, float* y, long long n_frames, int C, int F, void* stream) {
     CRUSE_CHECK_ARG(z && scale && shift && y, "bn_act_fwd: null pointer");

@@ -160,16 +160,21 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         const int q = warp & 3, unit = rank * SQ_U + lane;
         const bool rowvalid = q < 3 && unit < H;
         const float* wrow = W + ((size_t)(rowvalid ? q : 0) * H + (rowvalid ? unit : 0)) * H;
-        for (int kb = (warp >> 2); kb < NC; kb += 2) {
-            float v[32];
+        // two k-blocks (16 independent 16-byte loads) in flight per round: this prologue is paid once per time chunk
+        for (int kb0 = (warp >> 2); kb0 < NC; kb0 += 4) {
+            float v[2][32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = kb * 32 + i * 4;
-                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rowvalid && k < H) f = __ldg(reinterpret_cast<const float4*>(wrow + k));
-                v[i * 4 + 0] = to_tf32(f.x); v[i * 4 + 1] = to_tf32(f.y); v[i * 4 + 2] = to_tf32(f.z); v[i * 4 + 3] = to_tf32(f.w);
-            }
-            tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kb * 32), v);
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = (kb0 + 2 * u) * 32 + i * 4;
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rowvalid && kb0 + 2 * u < NC && k < H) f = __ldg(reinterpret_cast<const float4*>(wrow + k));
+                    v[u][i * 4 + 0] = to_tf32(f.x); v[u][i * 4 + 1] = to_tf32(f.y); v[u][i * 4 + 2] = to_tf32(f.z); v[u][i * 4 + 3] = to_tf32(f.w);
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (kb0 + 2 * u < NC) tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kb0 + 2 * u) * 32), v[u]);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -178,14 +183,20 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
     if (h0 && warp < 8 && my_act) {
         if (valid) hold = __ldg(reinterpret_cast<const float4*>(h0 + ((size_t)g * B + bg) * H + u0));
         uint8_t* dstb = sH + sl * SLICE_BYTES;
-        for (int i = wt; i < SQ_NB * (H / 4); i += SQ_WG) {      // every CTA needs the whole h_0 of its utterances
-            const int bb = i / (H / 4), k = (i - bb * (H / 4)) * 4;
-            const int bgg = (bpair * 2 + sl) * SQ_NB + bb;
-            if (bgg < B) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(h0 + ((size_t)g * B + bgg) * H + k));
-                *reinterpret_cast<float4*>(dstb + sw128_off(bb, k, SQ_H_KB)) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-            }
+        // every CTA needs the whole h_0 of its utterances: thread -> (utterance wt/8, 16-byte chunk wt%8) of every k-block,
+        // all NC loads in flight at once
+        const int bb = wt >> 3, c4 = wt & 7;
+        const int bgg = (bpair * 2 + sl) * SQ_NB + bb;
+        float4 hv[NC];
+#pragma unroll
+        for (int kb = 0; kb < NC; ++kb) {
+            const int k = kb * 32 + c4 * 4;
+            hv[kb] = (bgg < B && k < H) ? __ldg(reinterpret_cast<const float4*>(h0 + ((size_t)g * B + bgg) * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int kb = 0; kb < NC; ++kb)
+            *reinterpret_cast<float4*>(dstb + sw128_off(bb, kb * 32 + c4 * 4, SQ_H_KB)) =
+                make_float4(to_tf32(hv[kb].x), to_tf32(hv[kb].y), to_tf32(hv[kb].z), to_tf32(hv[kb].w));
     }
     tc::fence_proxy_async_smem();      // generic-proxy smem writes (h_0) -> visible to the tensor core's async proxy
     tc::tc_fence_before();

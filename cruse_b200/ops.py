@@ -215,6 +215,25 @@ def bn_fold(bn):
     return scale, shift
 
 
+def bn_fold_many(bns):
+    """eval-mode fold of up to 8 BatchNorm2d layers in one launch -> [(scale, shift), ...]."""
+    n = len(bns)
+    dev = bns[0].running_mean.device
+    total = sum(b.num_features for b in bns)
+    buf = torch.empty(2, total, device=dev, dtype=torch.float32)
+    out, off = [], 0
+    for b in bns:
+        out.append((buf[0, off:off + b.num_features], buf[1, off:off + b.num_features]))
+        off += b.num_features
+    tab = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+    eps = (C.c_float * n)(*[float(b.eps) for b in bns])
+    cs = (C.c_int * n)(*[b.num_features for b in bns])
+    _call("cruse_bn_fold_many", tab([b.weight for b in bns]), tab([b.bias for b in bns]), tab([b.running_mean for b in bns]),
+          tab([b.running_var for b in bns]), C.cast(eps, C.c_void_p), tab([o[0] for o in out]), tab([o[1] for o in out]),
+          C.cast(cs, C.c_void_p), n, _stream())
+    return out
+
+
 def bn_finalize(stats, count, bn, update_running=True):
     """train-mode BatchNorm2d: per-CTA partials -> (scale, shift, save_mean, save_invstd); updates running stats."""
     _req(stats, "stats", 2)

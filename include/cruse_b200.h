@@ -107,6 +107,11 @@ int cruse_bn_finalize(const float* stats_ws, int nparts, int C, double count,
 /* eval-mode BatchNorm2d folded to an affine: scale = gamma/sqrt(var+eps), shift = beta - mean*scale */
 int cruse_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   float eps, float* scale, float* shift, int C, void* stream);
+/* the same for up to 8 BatchNorm2d layers in ONE launch (all eval-mode folds of a forward pass): HOST arrays of n
+ * device pointers / sizes; gamma / beta tables (or single entries) may be NULL. */
+int cruse_bn_fold_many(const float* const* gamma, const float* const* beta, const float* const* running_mean,
+                       const float* const* running_var, const float* eps, float* const* scale, float* const* shift,
+                       const int* C, int n, void* stream);
 /* y = act(z*scale[c]+shift[c]) (+ skip); z,y [B,T,C,F] */
 int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
                      const float* skip, float* y, long long n_frames, int C, int F, void* stream);

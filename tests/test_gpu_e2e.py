@@ -215,6 +215,11 @@ def test_captured_graph_and_wavefront_match_eager(cuda):
         l1, w1, e1, m1 = cap(noisy.pin_memory(), clean.pin_memory())
         torch.cuda.synchronize()
         assert torch.equal(l0, l1) and torch.equal(m0, m1) and torch.equal(w0, w1)
+    # double-buffered host input path: same numbers
+    t1 = cap.prefetch(noisy.pin_memory(), clean.pin_memory())
+    l3 = cap.run_prefetched(t1)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(l3, l0)
     old = ops.GRU_WAVEFRONT
     ops.GRU_WAVEFRONT = False
     try:

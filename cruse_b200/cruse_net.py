@@ -74,10 +74,13 @@ class GGRU(nn.Module):
     def _streams(cls, device):
         key = (device.type, device.index)
         if key not in cls._side_streams:
-            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device) for _ in range(3))
+            # the latency-critical recurrence chunks get scheduling priority over whatever runs beside them
+            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(3))
         return cls._side_streams[key]
 
-    def _wavefront(self, x, residual):
+    def _wavefront(self, x, residual, side=None):
+        """``side(fork_event) -> (residual, ready_event)``: optional independent work (the skip convs) launched on a
+        low-priority stream once the wavefront starts; it fills the SMs the recurrence leaves free."""
         B, T, D = x.shape
         G, H = self.groups, D // self.groups
         dev = x.device
@@ -101,6 +104,7 @@ class GGRU(nn.Module):
         fork.record(main)
         for s_ in (sA, sC, sB):
             s_.wait_event(fork)
+        side_ready = None
         tw, tb = ops._ptr_table(w_ih2), ops._ptr_table(b_ih2)
         for k in range(nch):
             t0, t1 = bounds[k], bounds[k + 1]
@@ -121,23 +125,32 @@ class GGRU(nn.Module):
             with torch.cuda.stream(sB):                                   # layer 2, frames [t0,t1)  (:49-50)
                 sB.wait_event(eC)
                 ops.gru_seq_chunk(xp2, w_hh2, b_hh2, hB[(k + 1) & 1] if k else None, y2, hB[k & 1], t0, t1, False, False)
+            if k == 0 and side is not None:                               # after the first chunks are queued
+                residual, side_ready = side(fork)
         join = torch.cuda.Event()
         join.record(sB)
         main.wait_event(join)
+        if side_ready is not None:
+            main.wait_event(side_ready)
         return ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)   # :51 (+ skip4, :160)
 
-    def forward_frames(self, x, residual=None, state=None, want_state=False):
+    def uses_wavefront(self, B, T, state=None, want_state=False):
+        # both layers side by side need 2*G*ceil(B/32) co-resident clusters
+        return (state is None and not want_state and T >= self.WAVEFRONT_MIN_T and ops.GRU_SEQ_MODE == "tf32"
+                and ops.GRU_IH_MODE == "tf32" and ops.GRU_WAVEFRONT
+                and 2 * self.groups * ((B + 31) // 32) <= ops.gru_seq_max_clusters(self.hidden_size // self.groups))
+
+    def forward_frames(self, x, residual=None, state=None, want_state=False, side=None):
         """x [B,T,D] frame-major.  state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence
         (streaming, model/based_model/cust_conv.py:303-325)."""
         _need_cuda(x, "GGRU")
         B, T, D = x.shape
         if D != self.hidden_size:
             raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
-        # both layers side by side need 2*G*ceil(B/32) co-resident clusters
-        if (state is None and not want_state and T >= self.WAVEFRONT_MIN_T and ops.GRU_SEQ_MODE == "tf32"
-                and ops.GRU_IH_MODE == "tf32" and ops.GRU_WAVEFRONT
-                and 2 * self.groups * ((B + 31) // 32) <= ops.gru_seq_max_clusters(D // self.groups)):
-            return self._wavefront(x, residual)
+        if self.uses_wavefront(B, T, state, want_state):
+            return self._wavefront(x, residual, side)
+        if side is not None:
+            raise RuntimeError("GGRU: side work needs the wavefront path")
         h1 = h2 = None
         if state is not None:
             h1, h2 = state
@@ -195,6 +208,15 @@ class unet_2(nn.Module):
             raise ValueError(f"act must be 'relu' or 'prelu', got {act!r}")
 
     # ------------------------------------------------------------------------------------
+    _skip_streams = {}
+
+    @classmethod
+    def _skip_stream(cls, device):
+        key = (device.type, device.index)
+        if key not in cls._skip_streams:
+            cls._skip_streams[key] = torch.cuda.Stream(device=device, priority=0)
+        return cls._skip_streams[key]
+
     def _alpha(self, name):
         return getattr(self, name).weight if self.act_kind == "prelu" else None
 
@@ -222,6 +244,9 @@ class unet_2(nn.Module):
         train = self.training
         h = mag.view(B, T, 1, F)
         enc, skips = [], []
+        # eval, whole utterances: the skip convs leave the critical path and run beside the GRU wavefront
+        overlap = (not train and ops.OVERLAP_SKIPS and ops.get_conv_mode() == "tf32" and F == 256
+                   and self.gru.uses_wavefront(B, T, state.gru if state is not None else None, want_state))
         hists = state.hist if state is not None and state.hist else [None] * n
         new_hist = []
         folds = {}
@@ -234,12 +259,41 @@ class unet_2(nn.Module):
             h = self._stage(h, getattr(self, f"conv{k}"), getattr(self, f"bn{k}"), self._alpha(f"act{k}"), (2, 2), train,
                             hist=hists[k - 1], fold=folds.get(f"bn{k}"))
             enc.append(h)
-            skips.append(ops.conv_fwd(h, getattr(self, f"skip_connect_{k}").weight, None, None, None, None,
-                                      "none", 1, 1))                                                 # :153-156
+            if not overlap:
+                skips.append(ops.conv_fwd(h, getattr(self, f"skip_connect_{k}").weight, None, None, None, None,
+                                          "none", 1, 1))                                             # :153-156
         e4 = enc[-1]
         D = e4.shape[2] * e4.shape[3]
-        g = self.gru.forward_frames(e4.view(B, T, D), residual=skips[-1].view(B, T, D),
-                                    state=state.gru if state is not None else None, want_state=want_state)  # :158-160
+        side = None
+        if overlap:
+            dev = mag.device
+            main = torch.cuda.current_stream(dev)
+            s_skip = self._skip_stream(dev)
+            skips = [None] * n
+
+            def side(fork_event):
+                # the four skip convs (:153-156) on a low-priority stream beside the recurrence; skip4 first (LayerNorm 2 adds it)
+                s_skip.wait_event(fork_event)
+                ops.set_conv_max_ctas(ops.SKIP_MAX_CTAS)
+                try:
+                    with torch.cuda.stream(s_skip):
+                        for k in range(n, 0, -1):
+                            skips[k - 1] = ops.conv_fwd(enc[k - 1], getattr(self, f"skip_connect_{k}").weight, None, None, None,
+                                                        None, "none", 1, 1)
+                            skips[k - 1].record_stream(main)
+                            if k == n:
+                                ev4 = torch.cuda.Event()
+                                ev4.record(s_skip)
+                        self._skips_done = torch.cuda.Event()
+                        self._skips_done.record(s_skip)
+                finally:
+                    ops.set_conv_max_ctas(0)
+                return skips[n - 1].view(B, T, D), ev4
+
+        g = self.gru.forward_frames(e4.view(B, T, D), residual=None if overlap else skips[-1].view(B, T, D),
+                                    state=state.gru if state is not None else None, want_state=want_state, side=side)  # :158-160
+        if overlap:
+            torch.cuda.current_stream(mag.device).wait_event(self._skips_done)
         if want_state:
             g, gru_state = g
             state.hist, state.gru = new_hist, gru_state

@@ -41,6 +41,9 @@ constexpr int CT_EPI_WARPS = 8;                            // two per TMEM lane 
 constexpr int CT_THREADS = (CT_PROD_WARPS + 1 + CT_EPI_WARPS) * 32;   // 800
 constexpr int CT_SMEM_BUDGET = 222 * 1024;
 
+// optional cap on the persistent grid (0 = one CTA per SM): lets a stage run beside the GRU wavefront on the SMs it leaves free
+int g_conv_max_ctas = 0;
+
 struct ConvTcArgs {
     const float* in;
     const float* w;
@@ -372,7 +375,8 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
     }
     const int chunks = (a.T + C::TF - 1) / C::TF;
     const long long ntiles = (long long)a.B * chunks;
-    const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    if (g_conv_max_ctas > 0 && grid > g_conv_max_ctas) grid = g_conv_max_ctas;
     kern<<<grid, CT_THREADS, C::SMEM, st>>>(a);
     CRUSE_LAUNCH_OK();
     return 0;
@@ -389,6 +393,7 @@ int conv_mode() {
     return g_conv_mode;
 }
 bool conv_tc_enabled() { return conv_mode() == 1; }
+
 
 }  // namespace
 
@@ -444,5 +449,14 @@ extern "C" int cruse_conv_set_mode(int mode) {
         return -1;
     }
     cruse::g_conv_mode = mode;
+    return 0;
+}
+
+extern "C" int cruse_conv_set_max_ctas(int n) {
+    if (n < 0) {
+        cruse::set_error("conv_set_max_ctas: n must be >= 0, got %d", n);
+        return -1;
+    }
+    cruse::g_conv_max_ctas = n;
     return 0;
 }

@@ -618,3 +618,13 @@ def set_conv_mode(mode: str):
 
 def get_conv_mode() -> str:
     return "tf32" if lib().cruse_conv_get_mode() == 1 else "fp32"
+
+
+def set_conv_max_ctas(n: int):
+    """cap (0 = none) on the persistent grid of the tensor-core conv stages launched from now on."""
+    check(lib().cruse_conv_set_max_ctas(int(n)), "cruse_conv_set_max_ctas")
+
+
+# run the skip convs (and the clean-speech STFT) on a low-priority side stream beside the GRU wavefront
+OVERLAP_SKIPS = os.environ.get("CRUSE_OVERLAP_SKIPS", "1") != "0"
+SKIP_MAX_CTAS = int(os.environ.get("CRUSE_SKIP_MAX_CTAS", "0"))     # 0 = no cap (measured best on B200: 1.90 vs 1.94 ms at 80)

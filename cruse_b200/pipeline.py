@@ -26,10 +26,36 @@ def enhance(model, noisy, n_fft=512, hop=320, pad_mode="reflect"):
 
 def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
     """STFT + forward + mask + iSTFT + wo_male over the F bins the net sees -> (loss, wav, est, mask)."""
-    wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
-    S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
+    if ops.OVERLAP_SKIPS and noisy.is_cuda:
+        # the clean-speech STFT is independent of the network: low-priority side stream, joined before the loss
+        dev = noisy.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
+            S.record_stream(main)
+            done = torch.cuda.Event()
+            done.record(side)
+        wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
+        main.wait_event(done)
+    else:
+        wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
+        S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
     loss = wo_male_frames(S, est, X, model.in_feat)                                          # loss.py:121-148
     return loss, wav, est, mask
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device, priority=0)
+    return _side_streams[key]
 
 
 def forward_loss_host(model, noisy_host, clean_host, n_fft=512, hop=320, pad_mode="reflect", want_wav=False):

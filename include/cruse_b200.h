@@ -89,6 +89,9 @@ int cruse_conv_nparts(int B, int T);
  * Stages without a tensor-core instantiation (Cin == 1, Cout == 1, odd bin counts) always run in fp32. */
 int cruse_conv_get_mode(void);
 int cruse_conv_set_mode(int mode);
+/* cap the persistent grid of the tensor-core conv stages launched from now on (0 = one CTA per SM, the default):
+ * used to run the skip convs on the SMs the GRU wavefront leaves free. */
+int cruse_conv_set_max_ctas(int n);
 
 /* ---- a5: decoder stage.  replaces nn.ConvTranspose2d((1,3), stride (1,2)) + crop + BN + act
  *      + skip add at model/cruse_net.py:161-164.   w [Cin,Cout,1,3]; output cropped to Fout

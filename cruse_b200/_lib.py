@@ -36,6 +36,7 @@ SIGNATURES = {
     "cruse_mask_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_conv_fwd": (c_int, [c_fp] * 7 + [c_int, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
     "cruse_conv_nparts": (c_int, [c_int, c_int]),
+    "cruse_conv_fwd_tm": (c_int, [c_fp] * 6 + [c_int, c_fp] + [c_int] * 10 + [c_fp]),
     "cruse_conv_get_mode": (c_int, []),
     "cruse_conv_set_mode": (c_int, [c_int]),
     "cruse_conv_set_max_ctas": (c_int, [c_int]),

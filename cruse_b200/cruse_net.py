@@ -75,13 +75,18 @@ class GGRU(nn.Module):
         key = (device.type, device.index)
         if key not in cls._side_streams:
             # the latency-critical recurrence chunks get scheduling priority over whatever runs beside them
-            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(3))
+            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(4))
         return cls._side_streams[key]
 
-    def _wavefront(self, x, residual, side=None):
+    def _wavefront(self, x, residual, side=None, time_major=False):
         """``side(fork_event) -> (residual, ready_event)``: optional independent work (the skip convs) launched on a
-        low-priority stream once the wavefront starts; it fills the SMs the recurrence leaves free."""
-        B, T, D = x.shape
+        low-priority stream once the wavefront starts; it fills the SMs the recurrence leaves free.
+        ``time_major``: x is [T,B,D] (written so by the last encoder stage); the layer-1 input projections then run per
+        chunk on contiguous rows and join the wavefront instead of preceding it."""
+        if time_major:
+            T, B, D = x.shape
+        else:
+            B, T, D = x.shape
         G, H = self.groups, D // self.groups
         dev = x.device
         g1, g2 = self.gru_list1, self.gru_list2
@@ -89,8 +94,12 @@ class GGRU(nn.Module):
         w_hh2, b_hh2 = [g.weight_hh_l0 for g in g2], [g.bias_hh_l0 for g in g2]
         w_ih2, b_ih2 = [g.weight_ih_l0 for g in g2], [g.bias_ih_l0 for g in g2]
         main = torch.cuda.current_stream(dev)
-        sA, sC, sB = self._streams(dev)
-        xp1 = ops.gru_ih_gemm_tm(x.reshape(B * T, D), [g.weight_ih_l0 for g in g1], [g.bias_ih_l0 for g in g1], b_hh1, B, T)
+        sA, sC, sB, sD = self._streams(dev)
+        w_ih1, b_ih1 = [g.weight_ih_l0 for g in g1], [g.bias_ih_l0 for g in g1]
+        if time_major:
+            xp1 = torch.empty(T, B, G, 3 * H, device=dev, dtype=torch.float32)
+        else:
+            xp1 = ops.gru_ih_gemm_tm(x.reshape(B * T, D), w_ih1, b_ih1, b_hh1, B, T)
         # every buffer is allocated on the caller's stream and outlives the join below
         y1 = torch.empty(T, B, D, device=dev, dtype=torch.float32)
         z1 = torch.empty(T, B, D, device=dev, dtype=torch.float32)
@@ -102,13 +111,22 @@ class GGRU(nn.Module):
         bounds = [T * k // nch for k in range(nch + 1)]
         fork = torch.cuda.Event()
         fork.record(main)
-        for s_ in (sA, sC, sB):
+        for s_ in (sA, sC, sB, sD):
             s_.wait_event(fork)
         side_ready = None
+        tw1, tb1 = ops._ptr_table(w_ih1), ops._ptr_table(b_ih1)
         tw, tb = ops._ptr_table(w_ih2), ops._ptr_table(b_ih2)
         for k in range(nch):
             t0, t1 = bounds[k], bounds[k + 1]
+            eD = None
+            if time_major:
+                with torch.cuda.stream(sD):                               # layer-1 input projections of frames [t0,t1)
+                    ops.gru_ih_gemm_into(x[t0:t1].view(-1, D), w_ih1, b_ih1, b_hh1, xp1[t0:t1], tables=(tw1, tb1))
+                    eD = torch.cuda.Event()
+                    eD.record(sD)
             with torch.cuda.stream(sA):                                   # layer 1, frames [t0,t1)  (:41-45)
+                if eD is not None:
+                    sA.wait_event(eD)
                 # layer-1 outputs are stored concatenated (16-byte stores); LayerNorm 1 applies the :43-45 interleave
                 ops.gru_seq_chunk(xp1, w_hh1, b_hh1, hA[(k + 1) & 1] if k else None, y1, hA[k & 1], t0, t1, G != 4, True)
                 eA = torch.cuda.Event()
@@ -140,17 +158,20 @@ class GGRU(nn.Module):
                 and ops.GRU_IH_MODE == "tf32" and ops.GRU_WAVEFRONT
                 and 2 * self.groups * ((B + 31) // 32) <= ops.gru_seq_max_clusters(self.hidden_size // self.groups))
 
-    def forward_frames(self, x, residual=None, state=None, want_state=False, side=None):
-        """x [B,T,D] frame-major.  state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence
-        (streaming, model/based_model/cust_conv.py:303-325)."""
+    def forward_frames(self, x, residual=None, state=None, want_state=False, side=None, time_major=False):
+        """x [B,T,D] frame-major ([T,B,D] with ``time_major``, wavefront path only); the result is always [B,T,D].
+        state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence (streaming, model/based_model/cust_conv.py:303-325)."""
         _need_cuda(x, "GGRU")
-        B, T, D = x.shape
+        if time_major:
+            T, B, D = x.shape
+        else:
+            B, T, D = x.shape
         if D != self.hidden_size:
             raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
         if self.uses_wavefront(B, T, state, want_state):
-            return self._wavefront(x, residual, side)
-        if side is not None:
-            raise RuntimeError("GGRU: side work needs the wavefront path")
+            return self._wavefront(x, residual, side, time_major)
+        if side is not None or time_major:
+            raise RuntimeError("GGRU: side work / time-major input need the wavefront path")
         h1 = h2 = None
         if state is not None:
             h1, h2 = state
@@ -256,14 +277,22 @@ class unet_2(nn.Module):
         for k in range(1, n + 1):                                                                   # :149-152 repaired
             if want_state:
                 new_hist.append(h[:, -1].contiguous())
-            h = self._stage(h, getattr(self, f"conv{k}"), getattr(self, f"bn{k}"), self._alpha(f"act{k}"), (2, 2), train,
-                            hist=hists[k - 1], fold=folds.get(f"bn{k}"))
+            if overlap and k == n:
+                # the last encoder stage writes the GRU input TIME-MAJOR [T,B,C,F']: chunks of frames become contiguous rows
+                scale, shift = folds[f"bn{k}"]
+                conv = getattr(self, f"conv{k}")
+                h = ops.conv_fwd_tm(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2, B, T,
+                                    False, True)
+            else:
+                h = self._stage(h, getattr(self, f"conv{k}"), getattr(self, f"bn{k}"), self._alpha(f"act{k}"), (2, 2), train,
+                                hist=hists[k - 1], fold=folds.get(f"bn{k}"))
             enc.append(h)
             if not overlap:
                 skips.append(ops.conv_fwd(h, getattr(self, f"skip_connect_{k}").weight, None, None, None, None,
                                           "none", 1, 1))                                             # :153-156
         e4 = enc[-1]
-        D = e4.shape[2] * e4.shape[3]
+        C4, F4 = e4.shape[2], e4.shape[3]
+        D = C4 * F4
         side = None
         if overlap:
             dev = mag.device
@@ -278,8 +307,11 @@ class unet_2(nn.Module):
                 try:
                     with torch.cuda.stream(s_skip):
                         for k in range(n, 0, -1):
-                            skips[k - 1] = ops.conv_fwd(enc[k - 1], getattr(self, f"skip_connect_{k}").weight, None, None, None,
-                                                        None, "none", 1, 1)
+                            wk = getattr(self, f"skip_connect_{k}").weight
+                            if k == n:      # reads the time-major e4, writes frame order
+                                skips[k - 1] = ops.conv_fwd_tm(enc[k - 1], wk, None, None, None, None, "none", 1, 1, B, T, True, False)
+                            else:
+                                skips[k - 1] = ops.conv_fwd(enc[k - 1], wk, None, None, None, None, "none", 1, 1)
                             skips[k - 1].record_stream(main)
                             if k == n:
                                 ev4 = torch.cuda.Event()
@@ -290,14 +322,16 @@ class unet_2(nn.Module):
                     ops.set_conv_max_ctas(0)
                 return skips[n - 1].view(B, T, D), ev4
 
-        g = self.gru.forward_frames(e4.view(B, T, D), residual=None if overlap else skips[-1].view(B, T, D),
-                                    state=state.gru if state is not None else None, want_state=want_state, side=side)  # :158-160
+        g = self.gru.forward_frames(e4.view(T, B, D) if overlap else e4.view(B, T, D),
+                                    residual=None if overlap else skips[-1].view(B, T, D),
+                                    state=state.gru if state is not None else None, want_state=want_state, side=side,
+                                    time_major=overlap)                                              # :158-160
         if overlap:
             torch.cuda.current_stream(mag.device).wait_event(self._skips_done)
         if want_state:
             g, gru_state = g
             state.hist, state.gru = new_hist, gru_state
-        out = g.view(B, T, e4.shape[2], e4.shape[3])
+        out = g.view(B, T, C4, F4)
         for k in range(n, 1, -1):                                                                   # :161-163 repaired
             conv, bn = getattr(self, f"conv{k}_t"), getattr(self, f"bn{k}_t")
             alpha = self._alpha(f"act{k}_t")

@@ -20,7 +20,7 @@ namespace cruse {
 // conv_tc.cu: tensor-core (tcgen05) implicit-GEMM instantiations for the 256-bin pyramid in eval mode
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                cudaStream_t st);
+                int in_tm, int out_tm, cudaStream_t st);
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
 
@@ -419,7 +419,7 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd: PReLU needs alpha");
     cudaStream_t st = (cudaStream_t)stream;
     if (!hist && !stats_ws) {     // eval-mode stage of the 256-bin pyramid: tcgen05 implicit GEMM (conv_tc.cu)
-        const int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st);
+        const int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
         if (rc) return rc < 0 ? rc : 0;
     }
     const size_t smem = conv_smem_bytes(kt, Cin, Fin, Cout);
@@ -433,6 +433,21 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
         conv_fwd_kernel<1, 1><<<grid, CONV_THREADS, smem, st>>>(in, nullptr, w, bias, scale, shift, alpha, act, nullptr, out, stats_ws, T, Cin, Fin, Cout, Fout, 1, 0);
     }
     CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_conv_fwd_tm(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                                 const float* alpha, int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout,
+                                 int kt, int fstride, int in_time_major, int out_time_major, void* stream) {
+    CRUSE_CHECK_ARG(in && w && out, "conv_fwd_tm: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "conv_fwd_tm: bad sizes");
+    CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd_tm: scale and shift go together");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd_tm: PReLU needs alpha");
+    const int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride,
+                               in_time_major ? 1 : 0, out_time_major ? 1 : 0, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    CRUSE_CHECK_ARG(rc == 1, "conv_fwd_tm: no tensor-core instantiation for kt=%d fstride=%d Cin=%d Cout=%d Fin=%d (or conv mode is fp32)", kt,
+                    fstride, Cin, Cout, Fin);
     return 0;
 }
 

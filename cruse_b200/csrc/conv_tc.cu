@@ -44,6 +44,14 @@ constexpr int CT_SMEM_BUDGET = 222 * 1024;
 // optional cap on the persistent grid (0 = one CTA per SM): lets a stage run beside the GRU wavefront on the SMs it leaves free
 int g_conv_max_ctas = 0;
 
+#ifdef CRUSE_CT_TIMING
+// developer instrumentation (never built into the shipped library): clock64 stamps of CTA 0, [tile][slot]
+__device__ long long g_ct_timing[64 * 16];
+#define CT_STAMP(tile_local, slot) do { if (blockIdx.x == 0 && (tile_local) < 64 && (threadIdx.x & 31) == 0) g_ct_timing[(tile_local) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define CT_STAMP(tile_local, slot) do {} while (0)
+#endif
+
 struct ConvTcArgs {
     const float* in;
     const float* w;
@@ -54,6 +62,7 @@ struct ConvTcArgs {
     const float* addend;
     float* out;
     int B, T, act;
+    int in_tm, out_tm;      // frame records of in / out are ordered time-major (t*B + b) instead of (b*T + t)
 };
 
 // MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
@@ -75,7 +84,7 @@ struct ConvTcCfg {
     static constexpr int NKB = NG * S * KT;                        // weight K blocks
     static constexpr int B_BYTES = NKB * NPAD * 128;
     static constexpr int FIN = MODE == 0 ? SF * FO : FO;
-    static constexpr int RD_FIT = (CT_SMEM_BUDGET - B_BYTES - 2048) / GROUP_BYTES;
+    static constexpr int RD_FIT = (CT_SMEM_BUDGET - B_BYTES) / GROUP_BYTES;
     static constexpr int RD = RD_FIT > 4 ? 4 : RD_FIT;             // ring depth (groups)
     static constexpr int ITEMS = NFR * (CB / 4) * (FO / 16);       // (frame, 4 channels, 16 rows) patches per group
     static constexpr int NIT = ITEMS / CT_NPW;
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) CT_STAMP(63, 14);                               // kernel start
     const int T = a.T;
     const int chunks = (T + C::TF - 1) / C::TF;
     const int ntiles = a.B * chunks;
@@ -179,6 +189,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    if (warp == 0) CT_STAMP(63, 13);                               // setup done
 
     if (warp < CT_PROD_WARPS) {
         // ================= producers: HBM -> registers -> swizzled K-major A tiles =================
@@ -187,77 +198,97 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
         // 2 channels x 16 bins (two full 128-byte lines when SF == 2), one 8-byte store instruction is conflict free
         // (per half warp: 8 row phases x 2 channel pairs = 16 distinct 8-byte bank pairs of the swizzled tile)
         const int row16 = lane >> 1, ep = lane & 1;
-        int j = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // Software pipeline over this set's groups (j = set, set+2, ...): the registers of a group are split in two halves;
+        // while half 0 of group j is being converted and stored, the loads of half 0 of the set's NEXT group are already
+        // in flight (and likewise for half 1), so HBM requests are outstanding during the whole store phase.
+        constexpr int NV = (MODE == 0 && SF == 2) ? 2 : 1;
+        constexpr int NH0 = (C::NIT + 1) / 2;
+        float va[C::NIT][NV], vb[C::NIT][NV], ea[C::NIT], eb[C::NIT];     // channel ci0 / ci0+1: values, edge value
+        const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
+        const int ngroups = ntl * C::NG;
+
+        auto load_items = [&](int lo, int hi, int j) {
+            const int tile = blockIdx.x + (j / C::NG) * gridDim.x, g = j % C::NG;
             const int b = tile / chunks, t0 = (tile - b * chunks) * C::TF;
-#pragma unroll 1
-            for (int g = 0; g < C::NG; ++g, ++j) {
-                if ((j % CT_SETS) != set) continue;
-                constexpr int NV = (MODE == 0 && SF == 2) ? 2 : 1;
-                float va[C::NIT][NV], vb[C::NIT][NV], ea[C::NIT], eb[C::NIT];     // channel ci0 / ci0+1: values, edge value
 #pragma unroll
-                for (int it = 0; it < C::NIT; ++it) {
-                    const int item = it * CT_NPW + wq;
-                    const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
-                    const int t = t0 - (KT - 1) + fr;
-                    const bool valid = (t >= 0) && (t < T);
-                    const int fo = fg * 16 + row16, ci0 = g * C::CB + cg * 4 + 2 * ep;
-                    const float* src = a.in + (((size_t)b * T + t) * CIN + ci0) * C::FIN + (MODE == 0 ? SF : 1) * fo;
+            for (int it = 0; it < C::NIT; ++it) {
+                if (it < lo || it >= hi) continue;
+                const int item = it * CT_NPW + wq;
+                const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
+                const int t = t0 - (KT - 1) + fr;
+                const bool valid = (t >= 0) && (t < T);
+                const int fo = fg * 16 + row16, ci0 = g * C::CB + cg * 4 + 2 * ep;
+                const float* src = a.in + ((a.in_tm ? (size_t)t * a.B + b : (size_t)b * T + t) * CIN + ci0) * C::FIN + (MODE == 0 ? SF : 1) * fo;
 #pragma unroll
-                    for (int q = 0; q < NV; ++q) { va[it][q] = 0.f; vb[it][q] = 0.f; }
-                    ea[it] = 0.f; eb[it] = 0.f;
-                    if (valid) {
-                        if (MODE == 0 && SF == 2) {
-                            const float2 p = __ldg(reinterpret_cast<const float2*>(src));
-                            const float2 q = __ldg(reinterpret_cast<const float2*>(src + C::FIN));
-                            va[it][0] = p.x; va[it][NV - 1] = p.y; vb[it][0] = q.x; vb[it][NV - 1] = q.y;
-                        } else {
-                            va[it][0] = __ldg(src);
-                            vb[it][0] = __ldg(src + C::FIN);
-                        }
-                        if (row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
-                        if (MODE == 0 && SF == 1 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
+                for (int q = 0; q < NV; ++q) { va[it][q] = 0.f; vb[it][q] = 0.f; }
+                ea[it] = 0.f; eb[it] = 0.f;
+                if (valid) {
+                    if (MODE == 0 && SF == 2) {
+                        const float2 p = __ldg(reinterpret_cast<const float2*>(src));
+                        const float2 q = __ldg(reinterpret_cast<const float2*>(src + C::FIN));
+                        va[it][0] = p.x; va[it][NV - 1] = p.y; vb[it][0] = q.x; vb[it][NV - 1] = q.y;
+                    } else {
+                        va[it][0] = __ldg(src);
+                        vb[it][0] = __ldg(src + C::FIN);
                     }
+                    if (row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
+                    if (MODE == 0 && SF == 1 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
                 }
-                const int r = j % C::RD;
-                tc::mbar_wait(&empty[r], ((j / C::RD) & 1) ^ 1);
-                uint8_t* grp = ring + r * C::GROUP_BYTES;
-#pragma unroll
-                for (int it = 0; it < C::NIT; ++it) {
-                    const int item = it * CT_NPW + wq;
-                    const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
-                    const int row = fr * FO + fg * 16 + row16;
-                    float ta[3], tb[3];
-                    if (MODE == 0 && SF == 2) {          // taps read bins 2fo-1, 2fo, 2fo+1
-                        float la = __shfl_up_sync(0xffffffffu, va[it][NV - 1], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][NV - 1], 2);
-                        if (row16 == 0) { la = ea[it]; lb = eb[it]; }
-                        ta[0] = la; ta[1] = va[it][0]; ta[2] = va[it][NV - 1];
-                        tb[0] = lb; tb[1] = vb[it][0]; tb[2] = vb[it][NV - 1];
-                    } else if (MODE == 0) {              // taps read bins fo-1, fo, fo+1
-                        float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
-                        float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
-                        if (row16 == 0) { la = ea[it]; lb = eb[it]; }
-                        if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
-                        ta[0] = la; ta[1] = va[it][0]; ta[2] = ra;
-                        tb[0] = lb; tb[1] = vb[it][0]; tb[2] = rb;
-                    } else {                             // convT: K taps = x[i], x[i-1]
-                        float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
-                        if (row16 == 0) { la = ea[it]; lb = eb[it]; }
-                        ta[0] = va[it][0]; ta[1] = la; ta[2] = 0.f;
-                        tb[0] = vb[it][0]; tb[1] = lb; tb[2] = 0.f;
-                    }
-                    uint8_t* rowp = grp + (row >> 3) * 1024 + (row16 & 7) * 128 + ep * 8;     // row & 7 == row16 & 7
-#pragma unroll
-                    for (int tap = 0; tap < C::TAPS; ++tap) {
-                        const int k = tap * C::CB + cg * 4;                                   // + 2*ep (+1)
-                        const int slot = k >> 5, ch = (k & 31) >> 2;
-                        *reinterpret_cast<uint2*>(rowp + slot * C::SLOT_BYTES + ((ch ^ (row16 & 7)) << 4)) =
-                            make_uint2(f32_to_tf32(ta[tap]), f32_to_tf32(tb[tap]));
-                    }
-                }
-                tc::fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async-proxy reads
-                tc::mbar_arrive(&full[r]);
             }
+        };
+        auto store_items = [&](int lo, int hi, uint8_t* grp) {
+#pragma unroll
+            for (int it = 0; it < C::NIT; ++it) {
+                if (it < lo || it >= hi) continue;
+                const int item = it * CT_NPW + wq;
+                const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
+                const int row = fr * FO + fg * 16 + row16;
+                float ta[3], tb[3];
+                if (MODE == 0 && SF == 2) {          // taps read bins 2fo-1, 2fo, 2fo+1
+                    float la = __shfl_up_sync(0xffffffffu, va[it][NV - 1], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][NV - 1], 2);
+                    if (row16 == 0) { la = ea[it]; lb = eb[it]; }
+                    ta[0] = la; ta[1] = va[it][0]; ta[2] = va[it][NV - 1];
+                    tb[0] = lb; tb[1] = vb[it][0]; tb[2] = vb[it][NV - 1];
+                } else if (MODE == 0) {              // taps read bins fo-1, fo, fo+1
+                    float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
+                    float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
+                    if (row16 == 0) { la = ea[it]; lb = eb[it]; }
+                    if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
+                    ta[0] = la; ta[1] = va[it][0]; ta[2] = ra;
+                    tb[0] = lb; tb[1] = vb[it][0]; tb[2] = rb;
+                } else {                             // convT: K taps = x[i], x[i-1]
+                    float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
+                    if (row16 == 0) { la = ea[it]; lb = eb[it]; }
+                    ta[0] = va[it][0]; ta[1] = la; ta[2] = 0.f;
+                    tb[0] = vb[it][0]; tb[1] = lb; tb[2] = 0.f;
+                }
+                uint8_t* rowp = grp + (row >> 3) * 1024 + (row16 & 7) * 128 + ep * 8;     // row & 7 == row16 & 7
+#pragma unroll
+                for (int tap = 0; tap < C::TAPS; ++tap) {
+                    const int k = tap * C::CB + cg * 4;                                   // + 2*ep (+1)
+                    const int slot = k >> 5, ch = (k & 31) >> 2;
+                    *reinterpret_cast<uint2*>(rowp + slot * C::SLOT_BYTES + ((ch ^ (row16 & 7)) << 4)) =
+                        make_uint2(f32_to_tf32(ta[tap]), f32_to_tf32(tb[tap]));
+                }
+            }
+        };
+
+        if (set < ngroups) load_items(0, C::NIT, set);
+#pragma unroll 1
+        for (int j = set; j < ngroups; j += CT_SETS) {
+            const int r = j % C::RD;
+            const bool more = j + CT_SETS < ngroups;
+            if (wq == 0) CT_STAMP(j, 0 + set * 3);
+            tc::mbar_wait_backoff(&empty[r], ((j / C::RD) & 1) ^ 1);
+            if (wq == 0) CT_STAMP(j, 1 + set * 3);            // ring slot free
+            uint8_t* grp = ring + r * C::GROUP_BYTES;
+            store_items(0, NH0, grp);
+            if (more) load_items(0, NH0, j + CT_SETS);
+            store_items(NH0, C::NIT, grp);
+            if (more) load_items(NH0, C::NIT, j + CT_SETS);
+            tc::fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            tc::mbar_arrive(&full[r]);
+            if (wq == 0) CT_STAMP(j, 2 + set * 3);            // stored + arrived
         }
     } else if (warp == CT_MMA_WARP) {
         // ================= MMA issuer =================
@@ -266,14 +297,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
         int j = 0, lt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int ab = lt & 1;
+            CT_STAMP(lt, 6);
             tc::mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);
             tc::tc_fence_after();
+            CT_STAMP(lt, 7);                                       // accumulator buffer free
             const uint32_t d = tmem_d + (uint32_t)(ab * C::NPAD);
 #pragma unroll 1
             for (int g = 0; g < C::NG; ++g, ++j) {
                 const int r = j % C::RD;
                 tc::mbar_wait(&full[r], (j / C::RD) & 1);
                 tc::tc_fence_after();
+                if (g == C::NG - 1) CT_STAMP(lt, 8);               // last A group of the tile landed
                 if (tc::elect_one()) {
                     const uint32_t ga = base + r * C::GROUP_BYTES;
 #pragma unroll
@@ -296,6 +330,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
                     if (g == C::NG - 1) tc::umma_commit(&acc_full[ab]);
                 }
                 __syncwarp();
+                if (g == C::NG - 1) CT_STAMP(lt, 9);               // MMAs issued
             }
         }
     } else {
@@ -303,6 +338,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
         const int chalf = (warp - CT_EPI_WARP0) >> 2;                // which half of the accumulator columns
         constexpr int NCH = C::NPAD / 16;                            // 16-column chunks; chunk c belongs to half (c * 2 / NCH)
+        constexpr int MYCH = NCH >= 2 ? NCH / 2 : 1;
+        const bool have = NCH >= 2 || chalf == 0;                    // warp-uniform
         const int row = quad * 32 + lane;
         const int tl = row / FO, fo = row % FO;
         const int act = a.act;
@@ -312,51 +349,61 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
             const int ab = lt & 1;
             const int t = t0 + tl;
             const bool valid = t < T;
+            if (warp == CT_EPI_WARP0) CT_STAMP(lt, 10);
             tc::mbar_wait(&acc_full[ab], (lt >> 1) & 1);
             tc::tc_fence_after();
+            if (warp == CT_EPI_WARP0) CT_STAMP(lt, 11);           // accumulator complete
+            // pull this warp's share of the accumulator into registers and hand the TMEM buffer straight back to the MMA
+            // warp (relaxed arrive: it must not wait for this or the previous tile's global stores to be performed)
+            float v[MYCH][16];
+            if (have) {
 #pragma unroll
-            for (int c0 = 0; c0 < C::NPAD; c0 += 16) {
-                if (NCH >= 2 ? ((c0 / 16) * 2 / NCH != chalf) : (chalf != 0)) continue;      // warp-uniform
-                float v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * C::NPAD + c0), v);
+                for (int i = 0; i < MYCH; ++i)
+                    tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * C::NPAD + (NCH >= 2 ? chalf * MYCH + i : 0) * 16), v[i]);
                 tc::tmem_ld_wait();
-                if (!valid) continue;
-                if (MODE == 0) {
-                    const size_t o0 = (((size_t)b * T + t) * COUT) * FO + fo;
-                    float ad[16];
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive_relaxed(&acc_empty[ab]);
+            if (have && valid) {
+                const size_t rec = a.out_tm ? (size_t)t * a.B + b : (size_t)b * T + t;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q)      // all skip loads of the chunk in flight before the first store (out may alias nothing, but the compiler cannot know)
-                        ad[q] = (a.addend && c0 + q < COUT) ? __ldg(a.addend + o0 + (size_t)(c0 + q) * FO) : 0.f;
+                for (int i = 0; i < MYCH; ++i) {
+                    const int c0 = (NCH >= 2 ? chalf * MYCH + i : 0) * 16;
+                    if (MODE == 0) {
+                        const size_t o0 = rec * COUT * FO + fo;
+                        float ad[16];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int co = c0 + q;
-                        if (co < COUT) {
-                            const float4 pr = s_par[co];
-                            const float x = apply_act(fmaf(v[q], pr.x, pr.y), act, pr.z) + ad[q];
-                            a.out[o0 + (size_t)co * FO] = x;
+                        for (int q = 0; q < 16; ++q)      // all skip loads of the chunk in flight before the first store
+                            ad[q] = (a.addend && c0 + q < COUT) ? __ldg(a.addend + o0 + (size_t)(c0 + q) * FO) : 0.f;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const int co = c0 + q;
+                            if (co < COUT) {
+                                const float4 pr = s_par[co];
+                                a.out[o0 + (size_t)co * FO] = apply_act(fmaf(v[i][q], pr.x, pr.y), act, pr.z) + ad[q];
+                            }
                         }
-                    }
-                } else {
-                    const size_t o0 = (((size_t)b * T + t) * COUT) * (2 * FO) + 2 * fo;
-                    float2 ad[8];
+                    } else {
+                        const size_t o0 = rec * COUT * (2 * FO) + 2 * fo;
+                        float2 ad[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        ad[q] = (a.addend && (c0 >> 1) + q < COUT) ? __ldg(reinterpret_cast<const float2*>(a.addend + o0 + (size_t)((c0 >> 1) + q) * (2 * FO)))
-                                                                  : make_float2(0.f, 0.f);
+                        for (int q = 0; q < 8; ++q)
+                            ad[q] = (a.addend && (c0 >> 1) + q < COUT) ? __ldg(reinterpret_cast<const float2*>(a.addend + o0 + (size_t)((c0 >> 1) + q) * (2 * FO)))
+                                                                      : make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int co = (c0 >> 1) + q;
-                        if (co < COUT) {
-                            const float4 pr = s_par[co];
-                            const float x0 = apply_act(fmaf(v[2 * q], pr.x, pr.y), act, pr.z) + ad[q].x;
-                            const float x1 = apply_act(fmaf(v[2 * q + 1], pr.x, pr.y), act, pr.z) + ad[q].y;
-                            *reinterpret_cast<float2*>(a.out + o0 + (size_t)co * (2 * FO)) = make_float2(x0, x1);
+                        for (int q = 0; q < 8; ++q) {
+                            const int co = (c0 >> 1) + q;
+                            if (co < COUT) {
+                                const float4 pr = s_par[co];
+                                *reinterpret_cast<float2*>(a.out + o0 + (size_t)co * (2 * FO)) =
+                                    make_float2(apply_act(fmaf(v[i][2 * q], pr.x, pr.y), act, pr.z) + ad[q].x,
+                                                apply_act(fmaf(v[i][2 * q + 1], pr.x, pr.y), act, pr.z) + ad[q].y);
+                            }
                         }
                     }
                 }
             }
-            tc::tc_fence_before();
-            tc::mbar_arrive(&acc_empty[ab]);
+            if (warp == CT_EPI_WARP0) CT_STAMP(lt, 12);           // tile stored
         }
     }
     tc::tc_fence_before();
@@ -401,10 +448,10 @@ bool conv_tc_enabled() { return conv_mode() == 1; }
 // runs the CUDA-core kernel), < 0 on error.
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                cudaStream_t st) {
+                int in_tm, int out_tm, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm};
     int rc = 0;
 #define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_)                                                              \
     if (kt == KT_ && fstride == SF_ && Cin == CI_ && Cout == CO_ && Fout == FO_ && Fin == SF_ * FO_) {      \
@@ -426,7 +473,7 @@ int convT_tc_try(const float* in, const float* w, const float* bias, const float
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0};
     int rc = 0;
 #define CRUSE_CT_CONVT(CI_, CO_, FI_)                                                \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \
@@ -460,3 +507,9 @@ extern "C" int cruse_conv_set_max_ctas(int n) {
     cruse::g_conv_max_ctas = n;
     return 0;
 }
+
+#ifdef CRUSE_CT_TIMING
+extern "C" int cruse_debug_ct_timing(long long* out_host, int n) {
+    return (int)cudaMemcpyFromSymbol(out_host, cruse::g_ct_timing, sizeof(long long) * n);
+}
+#endif

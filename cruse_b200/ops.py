@@ -185,6 +185,24 @@ def conv_fwd(x, w, bias, scale, shift, alpha, act, kt, fstride, want_stats=False
     return (out, stats) if want_stats else out
 
 
+def conv_fwd_tm(x, w, bias, scale, shift, alpha, act, kt, fstride, B, T, in_tm, out_tm):
+    """eval-mode tensor-core stage whose input and / or output frame records are time-major: x [B*T, Cin, Fin] records
+    ordered (t, b) when in_tm else (b, t); the result is [T, B, Cout, Fout] when out_tm else [B, T, Cout, Fout]."""
+    _req(x, "x")
+    _req(w, "w", 4)
+    Cout, Cin = w.shape[0], w.shape[1]
+    Fin = x.shape[-1]
+    if x.numel() != B * T * Cin * Fin:
+        raise RuntimeError(f"conv_fwd_tm: x has {x.numel()} elements, expected {B}*{T}*{Cin}*{Fin}")
+    Fout = (Fin + 2 - 3) // fstride + 1
+    out = torch.empty((T, B, Cout, Fout) if out_tm else (B, T, Cout, Fout), device=x.device, dtype=torch.float32)
+    _call("cruse_conv_fwd_tm", _p(x), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(out), B, T, Cin, Fin, Cout, Fout,
+          kt, fstride, 1 if in_tm else 0, 1 if out_tm else 0, _stream(),
+          meta=(f"conv{kt}x3 {Cin}->{Cout} F{Fin}->{Fout}{' tm' if (in_tm or out_tm) else ''}", _nb(x, out, w, bias),
+                2 * B * T * Cout * Fout * Cin * kt * 3))
+    return out
+
+
 def convT_fwd(x, w, bias, scale, shift, alpha, act, skip, Fout, want_stats=False):
     """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout];  w [Cin,Cout,1,3] (ConvTranspose2d layout)."""
     _req(x, "x", 4)

@@ -83,6 +83,13 @@ int cruse_conv_fwd(const float* in, const float* hist, const float* w, const flo
                    float* out, float* stats_ws,
                    int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, void* stream);
 int cruse_conv_nparts(int B, int T);
+/* the same stage (eval mode: no hist, no statistics) with the frame records of `in` and / or `out` ordered TIME-MAJOR
+ * ([T, B, C, F] instead of [B, T, C, F]): the last encoder stage writes the GRU input time-major so that the input
+ * projections of the two-layer wavefront run per chunk of frames on contiguous rows.  Tensor-core instantiations only
+ * (returns an error for shapes without one or in fp32 conv mode). */
+int cruse_conv_fwd_tm(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                      const float* alpha, int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout,
+                      int kt, int fstride, int in_time_major, int out_time_major, void* stream);
 /* numeric mode of the eval-mode conv / convT stages of the 256-bin pyramid (no `hist`, no `stats_ws`):
  *   1 = implicit GEMM on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulate; default),
  *   0 = exact-fp32 CUDA-core kernels.  Initial value from the environment (CRUSE_CONV=fp32|tf32).

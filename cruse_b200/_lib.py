@@ -56,6 +56,7 @@ SIGNATURES = {
     "cruse_layernorm_interleave_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_ll, c_int, c_int, c_fp]),
     "cruse_wo_male_fwd_bwd": (c_int, [c_fp, CplxLayout, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp,
                                       c_int, c_int, c_int, c_fp]),
+    "cruse_wo_male_masked_fwd": (c_int, [c_fp, CplxLayout, c_fp, c_fp, CplxLayout, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "cruse_wo_male_ws_bytes": (C.c_size_t, []),
     # ---- a9 backward
     "cruse_colsum": (c_int, [c_fp, c_int, c_int, c_fp, c_int, c_fp]),

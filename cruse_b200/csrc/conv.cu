@@ -24,6 +24,12 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
 
+// conv_edge.cu: streaming kernels for the single-channel stages (Cin == 1 / Cout == 1), eval mode
+int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                  int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st);
+int convT_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                   int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
+
 constexpr int CONV_TT = 8;    // frames per CTA
 constexpr int CONV_COT = 4;   // output channels per thread
 constexpr int CONV_THREADS = 256;
@@ -419,8 +425,10 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd: PReLU needs alpha");
     cudaStream_t st = (cudaStream_t)stream;
     if (!hist && !stats_ws) {     // eval-mode stage of the 256-bin pyramid: tcgen05 implicit GEMM (conv_tc.cu)
-        const int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
+        int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
         if (rc) return rc < 0 ? rc : 0;
+        rc = conv_edge_try(in, w, bias, scale, shift, alpha, act, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st);
+        if (rc) { if (rc < 0) set_error("conv_fwd: streaming stage-1 kernel launch failed"); return rc < 0 ? rc : 0; }
     }
     const size_t smem = conv_smem_bytes(kt, Cin, Fin, Cout);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_fwd: stage (Cin=%d,Fin=%d,Cout=%d) needs %zu B shared memory", Cin, Fin, Cout, smem);
@@ -460,8 +468,10 @@ extern "C" int cruse_convT_fwd(const float* in, const float* w, const float* bia
     CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "convT_fwd: scale and shift go together");
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "convT_fwd: PReLU needs alpha");
     if (!stats_ws) {
-        const int rc = convT_tc_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        int rc = convT_tc_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
         if (rc) return rc < 0 ? rc : 0;
+        rc = convT_edge_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        if (rc) { if (rc < 0) set_error("convT_fwd: streaming last-stage kernel launch failed"); return rc < 0 ? rc : 0; }
     }
     const int CoutP = (Cout + CONV_COT - 1) / CONV_COT * CONV_COT;
     const size_t smem = sizeof(float) * ((((size_t)CONV_TT * Cin * (Fin + 2) + 3) & ~(size_t)3) + (size_t)Cin * 3 * CoutP + 2 * (size_t)Cout);

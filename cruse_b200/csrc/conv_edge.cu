@@ -1,0 +1,123 @@
+// conv_edge.cu -- the two stages of the U-Net that have a single channel on one side: the first encoder stage
+// (Conv2d(1 -> C, (2,3), stride (1,2), pad (1,1)) + "[..., :-1, :]" + folded BN + act, model/cruse_net.py:138,141,149-152)
+// and the last decoder stage (ConvTranspose2d(C -> 1, (1,3), stride (1,2)) + "[..., :-1]" + sigmoid, :164).
+//
+// With one channel on one side there is no GEMM to speak of (K = 6 resp. N = 2): these are pure HBM streams --
+// 1 KB in / 4 KB out per frame (stage 1) and 4 KB in / 1 KB out (last stage) -- so they are written as streaming
+// kernels: one thread per (frame, bin), every global access a fully coalesced 128/256-byte warp transaction, the
+// neighbouring bin through a warp shuffle, all weights and folded BN parameters in registers.  Exact fp32.
+// Used for eval-mode whole-utterance calls (no history frame, no batch statistics); everything else stays on conv.cu.
+#include "common.cuh"
+
+namespace cruse {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// stage 1: in [frames, 1, Fin] (Fin = 2*Fout), out [frames, COUT, Fout];  out[t] uses in[t-1] (kt = 0) and in[t] (kt = 1)
+// block = Fout threads = one frame; frame t-1 of the same utterance is re-read through L1/L2
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128)
+enc1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha, int act,
+                   float* __restrict__ out, int T, int Fout, long long nframes) {
+    __shared__ float s_w[COUT * 6 + 3 * COUT];
+    for (int i = threadIdx.x; i < COUT * 6; i += blockDim.x) s_w[i] = __ldg(w + i);            // [COUT][1][2][3]
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+        const float sc = scale ? __ldg(scale + i) : 1.f;
+        s_w[COUT * 6 + i] = sc;
+        s_w[COUT * 7 + i] = fmaf(bias ? __ldg(bias + i) : 0.f, sc, shift ? __ldg(shift + i) : 0.f);
+        s_w[COUT * 8 + i] = alpha ? __ldg(alpha + i) : 0.f;
+    }
+    __syncthreads();
+    const int Fin = 2 * Fout;
+    const int lane = threadIdx.x & 31;
+    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+        const int t = (int)(fr % T);
+        for (int fo = threadIdx.x; fo < Fout; fo += blockDim.x) {        // Fout is a multiple of 32: warps stay converged
+            const float* cur = in + fr * Fin + 2 * fo;
+            const float2 c = __ldg(reinterpret_cast<const float2*>(cur));
+            float2 p = make_float2(0.f, 0.f);
+            if (t > 0) p = __ldg(reinterpret_cast<const float2*>(cur - Fin));
+            // bin 2fo-1 = the odd element of the previous thread (previous warp's last lane: one extra 4-byte load)
+            float cl = __shfl_up_sync(0xffffffffu, c.y, 1), pl = __shfl_up_sync(0xffffffffu, p.y, 1);
+            if (lane == 0) {
+                cl = fo > 0 ? __ldg(cur - 1) : 0.f;
+                pl = (fo > 0 && t > 0) ? __ldg(cur - Fin - 1) : 0.f;
+            }
+            float* o = out + fr * (long long)(COUT * Fout) + fo;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float* wc = s_w + co * 6;
+                float v = wc[0] * pl;
+                v = fmaf(wc[1], p.x, v); v = fmaf(wc[2], p.y, v);
+                v = fmaf(wc[3], cl, v); v = fmaf(wc[4], c.x, v); v = fmaf(wc[5], c.y, v);
+                o[(size_t)co * Fout] = apply_act(fmaf(v, s_w[COUT * 6 + co], s_w[COUT * 7 + co]), act, s_w[COUT * 8 + co]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// last stage: in [frames, CIN, Fin], out [frames, 1, 2*Fin]:
+//   out[2i] = b + sum_ci W[ci,0,0] x[ci,i] + W[ci,0,2] x[ci,i-1];   out[2i+1] = b + sum_ci W[ci,0,1] x[ci,i]
+// ---------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(128)
+dec1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha, int act,
+                   float* __restrict__ out, int Fin, long long nframes) {
+    __shared__ float s_w[CIN * 3];
+    for (int i = threadIdx.x; i < CIN * 3; i += blockDim.x) s_w[i] = __ldg(w + i);             // [CIN][1][1][3]
+    __syncthreads();
+    const float sc = scale ? __ldg(scale) : 1.f;
+    const float sh = fmaf(bias ? __ldg(bias) : 0.f, sc, shift ? __ldg(shift) : 0.f);
+    const float al = alpha ? __ldg(alpha) : 0.f;
+    const int lane = threadIdx.x & 31;
+    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+        for (int i = threadIdx.x; i < Fin; i += blockDim.x) {
+            const float* x = in + fr * (long long)(CIN * Fin) + i;
+            float xv[CIN];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) xv[ci] = __ldg(x + (size_t)ci * Fin);
+            float e = 0.f, o = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                float xm = __shfl_up_sync(0xffffffffu, xv[ci], 1);
+                if (lane == 0) xm = i > 0 ? __ldg(x + (size_t)ci * Fin - 1) : 0.f;
+                e = fmaf(s_w[ci * 3 + 0], xv[ci], e);
+                e = fmaf(s_w[ci * 3 + 2], xm, e);
+                o = fmaf(s_w[ci * 3 + 1], xv[ci], o);
+            }
+            *reinterpret_cast<float2*>(out + fr * (long long)(2 * Fin) + 2 * i) =
+                make_float2(apply_act(fmaf(e, sc, sh), act, al), apply_act(fmaf(o, sc, sh), act, al));
+        }
+    }
+}
+
+}  // namespace
+
+// Returns 1 when the stage was launched here, 0 when the shape is not one of these (caller runs the general kernel).
+int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                  int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st) {
+    if (!(Cin == 1 && Cout == 8 && kt == 2 && fstride == 2 && Fin == 2 * Fout && (Fout % 32) == 0 && Fout <= 128)) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 7) != 0) return 0;
+    const long long nframes = (long long)B * T;
+    const long long cap = (long long)sm_count() * 16;
+    const int grid = (int)(nframes < cap ? nframes : cap);
+    enc1_stream_kernel<8><<<grid, Fout < 128 ? Fout : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, T, Fout, nframes);
+    return cudaGetLastError() == cudaSuccess ? 1 : -3;
+}
+
+int convT_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                   int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
+    if (!(Cout == 1 && Cin == 8 && Fout == 2 * Fin && (Fin % 32) == 0 && skip == nullptr)) return 0;
+    if ((reinterpret_cast<uintptr_t>(out) & 7) != 0) return 0;
+    const long long nframes = (long long)B * T;
+    const long long cap = (long long)sm_count() * 16;
+    const int grid = (int)(nframes < cap ? nframes : cap);
+    dec1_stream_kernel<8><<<grid, Fin < 128 ? Fin : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, Fin, nframes);
+    return cudaGetLastError() == cudaSuccess ? 1 : -3;
+}
+
+}  // namespace cruse

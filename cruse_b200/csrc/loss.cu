@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, const float* __restrict__ est,
                        cruse_cplx_layout le, const float* __restrict__ unp, cruse_cplx_layout lu,
                        float* __restrict__ dest, float* __restrict__ partials, int T, int F, long long total,
-                       float inv_count) {
+                       float inv_count, const float* __restrict__ mask) {
+    // mask != NULL: the estimate is mask[b,t,f] * unproc[b,t,f] computed on the fly (PreProcess.masking, utils/utils.py:417-433,
+    // fused into the loss so that it does not have to wait for -- and runs beside -- the mask*spectrum + iSTFT kernel)
     const float alpha = 2.f, beta = 1.f;              // loss.py:126-128 (gamma = 1)
     const float inv_ln10 = 0.43429448190325176f;
     float acc = 0.f;
@@ -33,8 +35,14 @@ wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, cons
         const long long b = bt / T;
         const float2 r = ld_cplx(ref, b * lr.sb + t * lr.st + f * lr.sf, lr.im_off);
         const long long eoff = b * le.sb + t * le.st + f * le.sf;
-        const float2 e = ld_cplx(est, eoff, le.im_off);
         const float2 u = ld_cplx(unp, b * lu.sb + t * lu.st + f * lu.sf, lu.im_off);
+        float2 e;
+        if (mask) {
+            const float mk = __ldg(mask + i);
+            e = make_float2(u.x * mk, u.y * mk);
+        } else {
+            e = ld_cplx(est, eoff, le.im_off);
+        }
         const float mr = sqrtf(r.x * r.x + r.y * r.y);
         const float me = sqrtf(e.x * e.x + e.y * e.y);
         const float mu = sqrtf(u.x * u.x + u.y * u.y);
@@ -88,10 +96,10 @@ using namespace cruse;
 
 extern "C" size_t cruse_wo_male_ws_bytes(void) { return sizeof(float) * LOSS_MAX_PARTS; }
 
-extern "C" int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
-                                     const float* unproc, cruse_cplx_layout lunp, float* dest, float* loss, void* ws,
-                                     int B, int T, int F, void* stream) {
-    CRUSE_CHECK_ARG(ref && est && unproc && loss && ws, "wo_male: null pointer");
+static int wo_male_launch(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest, const float* unproc,
+                          cruse_cplx_layout lunp, const float* mask, float* dest, float* loss, void* ws, int B, int T, int F,
+                          void* stream) {
+    CRUSE_CHECK_ARG(ref && (est || mask) && unproc && loss && ws, "wo_male: null pointer");
     CRUSE_CHECK_ARG(B > 0 && T > 0 && F > 0, "wo_male: bad sizes B=%d T=%d F=%d", B, T, F);
     const long long total = (long long)B * T * F;
     long long blocks = (total + LOSS_THREADS * 4 - 1) / (LOSS_THREADS * 4);
@@ -102,9 +110,22 @@ extern "C" int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, c
     cudaStream_t st = (cudaStream_t)stream;
     const double inv = 1.0 / (double)total;
     wo_male_partial_kernel<<<(unsigned)blocks, LOSS_THREADS, 0, st>>>(ref, lref, est, lest, unproc, lunp, dest, (float*)ws, T, F, total,
-                                                                      (float)inv);
+                                                                      (float)inv, mask);
     CRUSE_LAUNCH_OK();
     sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)blocks, inv, loss);
     CRUSE_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
+                                     const float* unproc, cruse_cplx_layout lunp, float* dest, float* loss, void* ws,
+                                     int B, int T, int F, void* stream) {
+    CRUSE_CHECK_ARG(est, "wo_male: null pointer");
+    return wo_male_launch(ref, lref, est, lest, unproc, lunp, nullptr, dest, loss, ws, B, T, F, stream);
+}
+
+extern "C" int cruse_wo_male_masked_fwd(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
+                                        cruse_cplx_layout lunp, float* loss, void* ws, int B, int T, int F, void* stream) {
+    CRUSE_CHECK_ARG(mask, "wo_male_masked: null pointer");
+    return wo_male_launch(ref, lref, nullptr, lunp, unproc, lunp, mask, nullptr, loss, ws, B, T, F, stream);
 }

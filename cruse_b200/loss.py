@@ -53,6 +53,13 @@ def wo_male_frames(ref, est, unproc, F):
     return loss
 
 
+def wo_male_frames_masked(ref, mask, unproc, F):
+    """the same value with est = mask * unproc formed inside the loss kernel (mask [B,T,F]): no dependence on the stored
+    estimate, so it can run beside the mask*spectrum + iSTFT kernel."""
+    B, T, NF, _ = unproc.shape
+    return ops.wo_male_masked_fwd(ref, ops.layout_btf2(ref), mask, unproc, ops.layout_btf2(unproc), B, T, F)
+
+
 def wo_male_frames_autograd(ref, est, unproc, F):
     """wo_male on interleaved spectra [B,T,NF,2] over bins [0,F), differentiable w.r.t. est (training path)."""
     return _WoMale.apply(ref, est, unproc, "btf2", F)

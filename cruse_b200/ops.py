@@ -18,7 +18,7 @@ PAD = {"reflect": 0, "constant": 1}
 
 
 # kernels launched per C-ABI call (everything else launches exactly one)
-LAUNCHES = {"cruse_wo_male_fwd_bwd": 2}
+LAUNCHES = {"cruse_wo_male_fwd_bwd": 2, "cruse_wo_male_masked_fwd": 2}
 
 
 class Profile:
@@ -464,6 +464,20 @@ def wo_male_fwd_bwd(ref, lref, est, lest, unp, lunp, B, T, F, want_grad=False):
                                       B, T, F, _stream(),
           meta=("wo_male", B * T * F * 8 * (4 if want_grad else 3), 30 * B * T * F))
     return loss, dest
+
+
+def wo_male_masked_fwd(ref, lref, mask, unp, lunp, B, T, F):
+    """loss value with the estimate formed on the fly as mask * unproc (mask [B,T,F])."""
+    _req(ref, "ref")
+    _req(mask, "mask")
+    _req(unp, "unproc")
+    if mask.numel() != B * T * F:
+        raise RuntimeError(f"wo_male_masked: mask has {mask.numel()} elements, expected {B}*{T}*{F}")
+    loss = torch.empty((), device=mask.device, dtype=torch.float32)
+    ws = _loss_ws(mask.device)
+    _call("cruse_wo_male_masked_fwd", _p(ref), lref, _p(mask), _p(unp), lunp, _p(loss), _p(ws), B, T, F, _stream(),
+          meta=("wo_male[mask fused]", B * T * F * (8 * 2 + 4), 30 * B * T * F))
+    return loss
 
 
 # ------------------------------------------------------------------------------------------

@@ -10,7 +10,7 @@ import torch
 
 from . import ops
 from .acoustics import hann_window, stft_frames
-from .loss import wo_male_frames
+from .loss import wo_male_frames, wo_male_frames_masked
 
 EPS_MAG = 1e-8   # utils/utils.py:400
 
@@ -27,8 +27,11 @@ def enhance(model, noisy, n_fft=512, hop=320, pad_mode="reflect"):
 def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
     """STFT + forward + mask + iSTFT + wo_male over the F bins the net sees -> (loss, wav, est, mask)."""
     if ops.OVERLAP_SKIPS and noisy.is_cuda:
-        # the clean-speech STFT is independent of the network: low-priority side stream, joined before the loss
+        # Two things here do not depend on what the critical path is doing and run on a low-priority side stream:
+        # the clean-speech STFT (beside the encoder) and the loss itself, which forms est = mask*X on the fly and therefore
+        # runs beside the mask*spectrum + iSTFT kernel instead of after it.
         dev = noisy.device
+        F = model.in_feat
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
         fork = torch.cuda.Event()
@@ -37,13 +40,21 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         with torch.cuda.stream(side):
             S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
             S.record_stream(main)
+        X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)   # feature.py:10-30, utils.py:400
+        mask = model.forward_frames(mag)                                                        # cruse_net.py:147-165
+        have_mask = torch.cuda.Event()
+        have_mask.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(have_mask)
+            loss = wo_male_frames_masked(S, mask, X, F)                                          # loss.py:121-148 on mask*X
+            loss.record_stream(main)
             done = torch.cuda.Event()
             done.record(side)
-        wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
+        est, wav = ops.mask_istft_fwd(X, mask, hann_window(n_fft, n_fft, dev), n_fft, hop, noisy.shape[-1])
         main.wait_event(done)
-    else:
-        wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
-        S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
+        return loss, wav, est, mask
+    wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
+    S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
     loss = wo_male_frames(S, est, X, model.in_feat)                                          # loss.py:121-148
     return loss, wav, est, mask
 

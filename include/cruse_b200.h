@@ -188,6 +188,11 @@ typedef struct { long long sb, st, sf, im_off; } cruse_cplx_layout;
 int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
                           const float* unproc, cruse_cplx_layout lunp, float* dest,
                           float* loss, void* ws, int B, int T, int F, void* stream);
+/* forward value only, with the estimate formed on the fly as mask[b,t,f] * unproc[b,t,f] (mask [B,T,F] contiguous):
+ * PreProcess.masking (utils/utils.py:417-433, mag_mapping) fused into the loss, so the loss does not wait for the
+ * mask*spectrum + iSTFT kernel and runs beside it.  Bit-identical to cruse_wo_male_fwd_bwd on the stored estimate. */
+int cruse_wo_male_masked_fwd(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
+                             cruse_cplx_layout lunp, float* loss, void* ws, int B, int T, int F, void* stream);
 size_t cruse_wo_male_ws_bytes(void);
 
 /* =====================================================================================================

@@ -107,8 +107,15 @@ class GGRU(nn.Module):
         y2 = torch.empty(B, T, D, device=dev, dtype=torch.float32)
         hA = [torch.empty(G, B, H, device=dev, dtype=torch.float32) for _ in range(2)]
         hB = [torch.empty(G, B, H, device=dev, dtype=torch.float32) for _ in range(2)]
+        # chunk boundaries: layer 2 finishes one (LayerNorm + projections + LAST chunk) after layer 1 and starts one FIRST chunk
+        # after it, so the first and last chunks are short and the ones in between long (fewer relaunches)
         nch = max(2, min(self.WAVEFRONT_CHUNKS, T // 32))
-        bounds = [T * k // nch for k in range(nch + 1)]
+        if nch >= 4:
+            edge = max(16, T // (3 * nch))
+            inner = [edge + (T - 2 * edge) * k // (nch - 2) for k in range(nch - 1)]
+            bounds = [0] + inner + [T]
+        else:
+            bounds = [T * k // nch for k in range(nch + 1)]
         fork = torch.cuda.Event()
         fork.record(main)
         for s_ in (sA, sC, sB, sD):
@@ -116,17 +123,21 @@ class GGRU(nn.Module):
         side_ready = None
         tw1, tb1 = ops._ptr_table(w_ih1), ops._ptr_table(b_ih1)
         tw, tb = ops._ptr_table(w_ih2), ops._ptr_table(b_ih2)
+        eD = [None] * nch
+        if time_major:
+            # layer-1 input projections, one launch per chunk, all queued up front on their own stream: chunk 0 gates the
+            # start of the wavefront, the rest stay ahead of layer 1
+            with torch.cuda.stream(sD):
+                for k in range(nch):
+                    t0, t1 = bounds[k], bounds[k + 1]
+                    ops.gru_ih_gemm_into(x[t0:t1].view(-1, D), w_ih1, b_ih1, b_hh1, xp1[t0:t1], tables=(tw1, tb1))
+                    eD[k] = torch.cuda.Event()
+                    eD[k].record(sD)
         for k in range(nch):
             t0, t1 = bounds[k], bounds[k + 1]
-            eD = None
-            if time_major:
-                with torch.cuda.stream(sD):                               # layer-1 input projections of frames [t0,t1)
-                    ops.gru_ih_gemm_into(x[t0:t1].view(-1, D), w_ih1, b_ih1, b_hh1, xp1[t0:t1], tables=(tw1, tb1))
-                    eD = torch.cuda.Event()
-                    eD.record(sD)
             with torch.cuda.stream(sA):                                   # layer 1, frames [t0,t1)  (:41-45)
-                if eD is not None:
-                    sA.wait_event(eD)
+                if eD[k] is not None:
+                    sA.wait_event(eD[k])
                 # layer-1 outputs are stored concatenated (16-byte stores); LayerNorm 1 applies the :43-45 interleave
                 ops.gru_seq_chunk(xp1, w_hh1, b_hh1, hA[(k + 1) & 1] if k else None, y1, hA[k & 1], t0, t1, G != 4, True)
                 eA = torch.cuda.Event()
@@ -143,8 +154,10 @@ class GGRU(nn.Module):
             with torch.cuda.stream(sB):                                   # layer 2, frames [t0,t1)  (:49-50)
                 sB.wait_event(eC)
                 ops.gru_seq_chunk(xp2, w_hh2, b_hh2, hB[(k + 1) & 1] if k else None, y2, hB[k & 1], t0, t1, False, False)
-            if k == 0 and side is not None:                               # after the first chunks are queued
-                residual, side_ready = side(fork)
+            if k == 0 and side is not None:
+                # the side work (skip convs) starts once the layer-1 projections are through, so that it does not take the
+                # SMs those need to stay ahead of the recurrence
+                residual, side_ready = side(eD[nch - 1] if time_major else fork)
         join = torch.cuda.Event()
         join.record(sB)
         main.wait_event(join)

@@ -34,13 +34,13 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         F = model.in_feat
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
+        X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)   # feature.py:10-30, utils.py:400
         fork = torch.cuda.Event()
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
             S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
             S.record_stream(main)
-        X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)   # feature.py:10-30, utils.py:400
         mask = model.forward_frames(mag)                                                        # cruse_net.py:147-165
         have_mask = torch.cuda.Event()
         have_mask.record(main)

@@ -67,12 +67,14 @@ struct ConvTcArgs {
 
 // MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
 // to 2*FO bins (FO = input bins).
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO>
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
 struct ConvTcCfg {
     static constexpr int TAPS = MODE == 0 ? 3 : 2;                 // conv: kf = 0,1,2; convT: {x[i], x[i-1]}
     static constexpr int N = MODE == 0 ? COUT : 2 * COUT;
     static constexpr int NPAD = N < 16 ? 16 : N;                   // UMMA M=128 needs N % 16 == 0
-    static constexpr int TF = 128 / FO;                            // frames per tile
+    static constexpr int TF = GM * (128 / FO);                     // frames per tile = GM MMA tiles of 128 rows: short-frame
+                                                                   // stages (FO >= 32) batch several so that the per-tile
+                                                                   // barrier round trips are paid once per ~8 frames
     static constexpr int NFR = TF + KT - 1;                        // frames held by one A slot
     static constexpr int SR = NFR * FO;                            // rows per slot
     static constexpr int SLOT_BYTES = SR * 128;
@@ -88,13 +90,15 @@ struct ConvTcCfg {
     static constexpr int RD = RD_FIT > 4 ? 4 : RD_FIT;             // ring depth (groups)
     static constexpr int ITEMS = NFR * (CB / 4) * (FO / 16);       // (frame, 4 channels, 16 rows) patches per group
     static constexpr int NIT = ITEMS / CT_NPW;
-    static constexpr int TMEM_COLS = 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : 128);
+    static constexpr int ACC_COLS = GM * NPAD;                     // one accumulator buffer: GM tiles side by side
+    static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256));
     static constexpr int SMEM = 1024 + RD * GROUP_BYTES + B_BYTES + COUT * 16 + 256;
     static_assert(128 % FO == 0 && FO % 16 == 0, "FO must divide 128 and be a multiple of 16");
     static_assert(CIN % 4 == 0 && CIN % CB == 0, "channel blocking");
     static_assert(ITEMS % CT_NPW == 0, "producer items must split evenly over the warps of a set");
     static_assert(RD >= 2, "ring needs two groups");
-    static_assert(NPAD % 16 == 0 && NPAD <= 64, "N tile");
+    static_assert(NPAD % 16 == 0 && NPAD <= 64 && 2 * ACC_COLS <= 256, "N tile");
+    static_assert(NIT <= 9, "producer register budget: at most 9 patches per warp and group");
     static_assert(MODE == 0 || (KT == 1 && SF == 1), "convT instantiation");
 };
 
@@ -114,9 +118,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {   // this 
         : "memory");
 }
 
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO>
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
 __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
-    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO>;
+    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms are 1024-byte aligned
     uint8_t* ring = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
             tc::mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);
             tc::tc_fence_after();
             CT_STAMP(lt, 7);                                       // accumulator buffer free
-            const uint32_t d = tmem_d + (uint32_t)(ab * C::NPAD);
+            const uint32_t d0 = tmem_d + (uint32_t)(ab * C::ACC_COLS);
 #pragma unroll 1
             for (int g = 0; g < C::NG; ++g, ++j) {
                 const int r = j % C::RD;
@@ -311,18 +315,21 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
                 if (tc::elect_one()) {
                     const uint32_t ga = base + r * C::GROUP_BYTES;
 #pragma unroll
-                    for (int s = 0; s < C::S; ++s) {
-                        const int kvalid = (C::KG - 32 * s) < 32 ? (C::KG - 32 * s) : 32;
-                        const int ksteps = (kvalid + 7) / 8;
+                    for (int mt = 0; mt < GM; ++mt) {                // GM MMA tiles of 128 rows share the slot group
 #pragma unroll
-                        for (int kt = 0; kt < KT; ++kt) {
-                            const uint32_t sa = ga + s * C::SLOT_BYTES + kt * (FO * 128);
-                            const uint32_t sb = sB_u32 + (uint32_t)(((g * C::S + s) * KT + kt) * (C::NPAD * 128));
+                        for (int s = 0; s < C::S; ++s) {
+                            const int kvalid = (C::KG - 32 * s) < 32 ? (C::KG - 32 * s) : 32;
+                            const int ksteps = (kvalid + 7) / 8;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k < ksteps)
-                                    tc::umma_tf32(d, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc,
-                                                  (g | s | kt | k) ? 1u : 0u);
+                            for (int kt = 0; kt < KT; ++kt) {
+                                const uint32_t sa = ga + s * C::SLOT_BYTES + (mt * 128 + kt * FO) * 128;
+                                const uint32_t sb = sB_u32 + (uint32_t)(((g * C::S + s) * KT + kt) * (C::NPAD * 128));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (k < ksteps)
+                                        tc::umma_tf32(d0 + mt * C::NPAD, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc,
+                                                      (g | s | kt | k) ? 1u : 0u);
+                                }
                             }
                         }
                     }
@@ -337,38 +344,42 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
         // ================= epilogue: TMEM -> registers -> bias, folded BN, act, + skip -> global =================
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
         const int chalf = (warp - CT_EPI_WARP0) >> 2;                // which half of the accumulator columns
-        constexpr int NCH = C::NPAD / 16;                            // 16-column chunks; chunk c belongs to half (c * 2 / NCH)
-        constexpr int MYCH = NCH >= 2 ? NCH / 2 : 1;
-        const bool have = NCH >= 2 || chalf == 0;                    // warp-uniform
-        const int row = quad * 32 + lane;
-        const int tl = row / FO, fo = row % FO;
+        // work units = (MMA tile mt, 16-column chunk): the two warps of a quadrant take alternate units
+        constexpr int NCH = C::NPAD / 16;
+        constexpr int NU = GM * NCH;
+        constexpr int MYU = NU >= 2 ? NU / 2 : 1;
+        const bool have = NU >= 2 || chalf == 0;                     // warp-uniform
         const int act = a.act;
         int lt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int b = tile / chunks, t0 = (tile - b * chunks) * C::TF;
             const int ab = lt & 1;
-            const int t = t0 + tl;
-            const bool valid = t < T;
             if (warp == CT_EPI_WARP0) CT_STAMP(lt, 10);
             tc::mbar_wait(&acc_full[ab], (lt >> 1) & 1);
             tc::tc_fence_after();
             if (warp == CT_EPI_WARP0) CT_STAMP(lt, 11);           // accumulator complete
             // pull this warp's share of the accumulator into registers and hand the TMEM buffer straight back to the MMA
             // warp (relaxed arrive: it must not wait for this or the previous tile's global stores to be performed)
-            float v[MYCH][16];
+            float v[MYU][16];
             if (have) {
 #pragma unroll
-                for (int i = 0; i < MYCH; ++i)
-                    tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * C::NPAD + (NCH >= 2 ? chalf * MYCH + i : 0) * 16), v[i]);
+                for (int i = 0; i < MYU; ++i) {
+                    const int u = NU >= 2 ? chalf + 2 * i : 0, mt = u / NCH, ch = u % NCH;
+                    tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * C::ACC_COLS + mt * C::NPAD + ch * 16), v[i]);
+                }
                 tc::tmem_ld_wait();
             }
             tc::tc_fence_before();
             tc::mbar_arrive_relaxed(&acc_empty[ab]);
-            if (have && valid) {
-                const size_t rec = a.out_tm ? (size_t)t * a.B + b : (size_t)b * T + t;
+            if (have) {
 #pragma unroll
-                for (int i = 0; i < MYCH; ++i) {
-                    const int c0 = (NCH >= 2 ? chalf * MYCH + i : 0) * 16;
+                for (int i = 0; i < MYU; ++i) {
+                    const int u = NU >= 2 ? chalf + 2 * i : 0, mt = u / NCH, c0 = (u % NCH) * 16;
+                    const int row = mt * 128 + quad * 32 + lane;
+                    const int tl = row / FO, fo = row % FO;
+                    const int t = t0 + tl;
+                    if (t >= T) continue;
+                    const size_t rec = a.out_tm ? (size_t)t * a.B + b : (size_t)b * T + t;
                     if (MODE == 0) {
                         const size_t o0 = rec * COUT * FO + fo;
                         float ad[16];
@@ -411,10 +422,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
     if (warp == CT_MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO>
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
-    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO>;
-    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO>;
+    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
+    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO, GM>;
     static bool attr_set = false;                                   // per instantiation; benign if raced
     if (!attr_set) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -453,18 +464,19 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
     ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm};
     int rc = 0;
-#define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_)                                                              \
+    // last argument: MMA tiles (128 rows) per pipeline step; stages with long frames (FO >= 32) batch several of them
+#define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_)                                                         \
     if (kt == KT_ && fstride == SF_ && Cin == CI_ && Cout == CO_ && Fout == FO_ && Fin == SF_ * FO_) {      \
-        rc = launch_conv_tc<0, KT_, SF_, CI_, CO_, FO_>(a, st);                                             \
+        rc = launch_conv_tc<0, KT_, SF_, CI_, CO_, FO_, GM_>(a, st);                                        \
         return rc ? rc : 1;                                                                                 \
     }
-    CRUSE_CT_CONV(2, 2, 8, 16, 64)
-    CRUSE_CT_CONV(2, 2, 16, 32, 32)
-    CRUSE_CT_CONV(2, 2, 32, 64, 16)
-    CRUSE_CT_CONV(1, 1, 8, 8, 128)
-    CRUSE_CT_CONV(1, 1, 16, 16, 64)
-    CRUSE_CT_CONV(1, 1, 32, 32, 32)
-    CRUSE_CT_CONV(1, 1, 64, 64, 16)
+    CRUSE_CT_CONV(2, 2, 8, 16, 64, 4)
+    CRUSE_CT_CONV(2, 2, 16, 32, 32, 1)
+    CRUSE_CT_CONV(2, 2, 32, 64, 16, 1)
+    CRUSE_CT_CONV(1, 1, 8, 8, 128, 4)
+    CRUSE_CT_CONV(1, 1, 16, 16, 64, 1)
+    CRUSE_CT_CONV(1, 1, 32, 32, 32, 1)
+    CRUSE_CT_CONV(1, 1, 64, 64, 16, 1)
 #undef CRUSE_CT_CONV
     return 0;
 }
@@ -475,14 +487,14 @@ int convT_tc_try(const float* in, const float* w, const float* bias, const float
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
     ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0};
     int rc = 0;
-#define CRUSE_CT_CONVT(CI_, CO_, FI_)                                                \
+#define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_)                                           \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \
-        rc = launch_conv_tc<1, 1, 1, CI_, CO_, FI_>(a, st);                          \
+        rc = launch_conv_tc<1, 1, 1, CI_, CO_, FI_, GM_>(a, st);                     \
         return rc ? rc : 1;                                                          \
     }
-    CRUSE_CT_CONVT(64, 32, 16)
-    CRUSE_CT_CONVT(32, 16, 32)
-    CRUSE_CT_CONVT(16, 8, 64)
+    CRUSE_CT_CONVT(64, 32, 16, 1)
+    CRUSE_CT_CONVT(32, 16, 32, 1)
+    CRUSE_CT_CONVT(16, 8, 64, 2)
 #undef CRUSE_CT_CONVT
     return 0;
 }

@@ -268,30 +268,33 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         float4 b_hn = make_float4(0.f, 0.f, 0.f, 0.f);
         if (uvalid && ptrs.b_hh[g]) b_hn = __ldg(reinterpret_cast<const float4*>(ptrs.b_hh[g] + 2 * H + u0));
 
-        // x-projections are streamed from HBM two steps ahead of their use (a step is shorter than a DRAM round trip)
+        // x-projections are streamed from HBM PF steps ahead of their use (a step is shorter than a DRAM round trip, and
+        // the skip convs / input projections running beside the recurrence load the memory system)
+        constexpr int PF = 4;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 xr = zero4, xz = zero4, xn = zero4, x1r = zero4, x1z = zero4, x1n = zero4;
-        if (valid && T > 0) {
-            xr = __ldg(reinterpret_cast<const float4*>(xp));
-            xz = __ldg(reinterpret_cast<const float4*>(xp + H));
-            xn = __ldg(reinterpret_cast<const float4*>(xp + 2 * H));
-        }
-        if (valid && T > 1) {
-            x1r = __ldg(reinterpret_cast<const float4*>(xp + xstep));
-            x1z = __ldg(reinterpret_cast<const float4*>(xp + xstep + H));
-            x1n = __ldg(reinterpret_cast<const float4*>(xp + xstep + 2 * H));
+        float4 xq_r[PF], xq_z[PF], xq_n[PF];                          // queue: [0] = current step, [PF-1] = newest prefetch
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+            xq_r[d] = xq_z[d] = xq_n[d] = zero4;
+            if (valid && d < T) {
+                const float* xq = xp + (size_t)d * xstep;
+                xq_r[d] = __ldg(reinterpret_cast<const float4*>(xq));
+                xq_z[d] = __ldg(reinterpret_cast<const float4*>(xq + H));
+                xq_n[d] = __ldg(reinterpret_cast<const float4*>(xq + 2 * H));
+            }
         }
         const int q = warp & 3;
         int p = 0;
         for (int t = 0; t < T; ++t) {
-            // prefetch the x-projections of step t+2 while the tensor core works
+            // prefetch the x-projections of step t+PF while the tensor core works
             float4 nxr = zero4, nxz = zero4, nxn = zero4;
-            if (valid && t + 2 < T) {
-                const float* xq = xp + (size_t)(t + 2) * xstep;
+            if (valid && t + PF < T) {
+                const float* xq = xp + (size_t)(t + PF) * xstep;
                 nxr = __ldg(reinterpret_cast<const float4*>(xq));
                 nxz = __ldg(reinterpret_cast<const float4*>(xq + H));
                 nxn = __ldg(reinterpret_cast<const float4*>(xq + 2 * H));
             }
+            const float4 xr = xq_r[0], xz = xq_z[0], xn = xq_n[0];
             tc::mbar_wait(&acc_full[sl], (uint32_t)(t & 1));
             tc::tc_fence_after();
             if (sl == 0 && wt == 0) SEQ_STAMP(3);
@@ -352,8 +355,9 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
             }
             if (sl == 0 && wt == 0) SEQ_STAMP(6);
             p ^= 1;
-            xr = x1r; xz = x1z; xn = x1n;
-            x1r = nxr; x1z = nxz; x1n = nxn;
+#pragma unroll
+            for (int d = 0; d + 1 < PF; ++d) { xq_r[d] = xq_r[d + 1]; xq_z[d] = xq_z[d + 1]; xq_n[d] = xq_n[d + 1]; }
+            xq_r[PF - 1] = nxr; xq_z[PF - 1] = nxz; xq_n[PF - 1] = nxn;
         }
         if (hT && valid) *reinterpret_cast<float4*>(hT + ((size_t)g * B + bg) * H + u0) = hold;
     }

@@ -50,6 +50,9 @@ SIGNATURES = {
     "cruse_gru_seq_fwd": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gru_seq_fwd_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gru_seq_tc_max_clusters": (c_int, [c_int]),
+    "cruse_gru_seq_flagged_tc": (c_int, [c_fp, c_pp, c_pp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp, c_int, c_fp, C.c_uint, c_fp, c_fp, c_fp]),
+    "cruse_flag_wait": (c_int, [c_fp, C.c_uint, c_fp, c_fp]),
+    "cruse_flag_set": (c_int, [c_fp, C.c_uint, c_fp]),
     "cruse_gru_ih_gemm_tm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_gru_seq_chunk_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp]),
     "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),

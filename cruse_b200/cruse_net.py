@@ -67,7 +67,8 @@ class GGRU(nn.Module):
     # frames [t0,t1) depends only on layer 1 up to t1, so the layers run side by side on three streams, one chunk of
     # frames apart; GRU-internal buffers are time-major so a chunk is a contiguous row range.
     WAVEFRONT_MIN_T = 96
-    WAVEFRONT_CHUNKS = 8
+    WAVEFRONT_CHUNKS = 8            # relaunch mode: one recurrence launch per chunk
+    WAVEFRONT_FLAG_CHUNKS = 8      # flag mode: chunks only gate the hand-over between the layers (ABI limit 16)
     _side_streams = {}
 
     @classmethod
@@ -109,14 +110,32 @@ class GGRU(nn.Module):
         hB = [torch.empty(G, B, H, device=dev, dtype=torch.float32) for _ in range(2)]
         # chunk boundaries: layer 2 finishes one (LayerNorm + projections + LAST chunk) after layer 1 and starts one FIRST chunk
         # after it, so the first and last chunks are short and the ones in between long (fewer relaunches)
-        nch = max(2, min(self.WAVEFRONT_CHUNKS, T // 32))
-        if nch >= 4:
+        flag_mode = ops.GRU_WAVEFRONT_MODE == "flags" and time_major
+        if flag_mode:
+            # flag-synchronised chunks cost no relaunch, so they are short: layer 2 trails layer 1 by one chunk + its LayerNorm
+            # and projections
+            nch = max(2, min(self.WAVEFRONT_FLAG_CHUNKS, T // 24))
+            bounds = [T * k // nch for k in range(nch + 1)]
+        else:
+            nch = max(2, min(self.WAVEFRONT_CHUNKS, T // 32))
+        if flag_mode:
+            pass
+        elif nch >= 4:
             edge = max(16, T // (3 * nch))
             inner = [edge + (T - 2 * edge) * k // (nch - 2) for k in range(nch - 1)]
             bounds = [0] + inner + [T]
         else:
             bounds = [T * k // nch for k in range(nch + 1)]
-        fork = torch.cuda.Event()
+        H = D // G
+        flagged = flag_mode and all(bounds[k + 1] - bounds[k] >= 8 for k in range(nch))
+        if flagged:
+            # one launch per layer; chunk hand-over through device flags: [0,nch) layer-1 projections ready, [nch,2nch) layer-1
+            # chunk stored (counts (CTA, slice) pairs), [2nch,3nch) layer-2 projections ready, [3nch] error
+            flags = torch.zeros(3 * nch + 1, device=dev, dtype=torch.int32)
+            f_ih1, f_l1, f_ih2, f_err = flags[0:nch], flags[nch:2 * nch], flags[2 * nch:3 * nch], flags[3 * nch:]
+            self._wavefront_err = f_err
+            n_wg = G * ((H + 31) // 32) * ((B + 15) // 16)
+        fork = torch.cuda.Event()                                         # (after the flags are zeroed)
         fork.record(main)
         for s_ in (sA, sC, sB, sD):
             s_.wait_event(fork)
@@ -131,9 +150,34 @@ class GGRU(nn.Module):
                 for k in range(nch):
                     t0, t1 = bounds[k], bounds[k + 1]
                     ops.gru_ih_gemm_into(x[t0:t1].view(-1, D), w_ih1, b_ih1, b_hh1, xp1[t0:t1], tables=(tw1, tb1))
+                    if flagged:
+                        ops.flag_set(f_ih1[k:k + 1])
                     eD[k] = torch.cuda.Event()
                     eD[k].record(sD)
-        for k in range(nch):
+        if flagged:
+            # host launch order = dependency order (projections, layer 1, LayerNorm + projections, layer 2), so the spinning
+            # kernels also terminate when a tool serialises the launches
+            with torch.cuda.stream(sA):                                   # layer 1, all frames  (:41-45)
+                ops.gru_seq_flagged(xp1, w_hh1, b_hh1, y1, G != 4, True, bounds, f_ih1, 1, f_l1, f_err)
+            with torch.cuda.stream(sC):                                   # LayerNorm 1 + layer-2 input projections per chunk (:46-48)
+                for k in range(nch):
+                    t0, t1 = bounds[k], bounds[k + 1]
+                    ops.flag_wait(f_l1[k:k + 1], n_wg, f_err)
+                    if G == 4:
+                        ops.layernorm_interleave_fwd_into(y1[t0:t1], self.ln1.weight, self.ln1.bias, self.ln1.eps, z1[t0:t1], G)
+                    else:
+                        ops.layernorm_fwd_into(y1[t0:t1], self.ln1.weight, self.ln1.bias, self.ln1.eps, z1[t0:t1])
+                    ops.gru_ih_gemm_into(z1[t0:t1].view(-1, D), w_ih2, b_ih2, b_hh2, xp2[t0:t1], tables=(tw, tb))
+                    ops.flag_set(f_ih2[k:k + 1])
+            with torch.cuda.stream(sB):                                   # layer 2, all frames  (:49-50)
+                ops.gru_seq_flagged(xp2, w_hh2, b_hh2, y2, False, False, bounds, f_ih2, 1, None, f_err)
+            if side is not None:
+                residual, side_ready = side(eD[nch - 1])
+            for s_ in (sA, sC, sD):                                       # join every branch (graph capture needs it)
+                ev = torch.cuda.Event()
+                ev.record(s_)
+                main.wait_event(ev)
+        for k in range(nch if not flagged else 0):
             t0, t1 = bounds[k], bounds[k + 1]
             with torch.cuda.stream(sA):                                   # layer 1, frames [t0,t1)  (:41-45)
                 if eD[k] is not None:

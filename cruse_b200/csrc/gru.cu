@@ -407,6 +407,7 @@ namespace cruse {
 // LayerNorm over a row whose INPUT is the concatenation [G][H] of the grouped GRU outputs and whose OUTPUT is the
 // stack(dim=-1)+flatten interleave of model/cruse_net.py:43-45 (feature j = h*G + g), fused: the recurrence kernel
 // then stores 16 contiguous bytes per thread and step instead of four 4-byte stores 16 bytes apart.  G == 4.
+template <int HPL>      // hidden units per lane = H / 32 (H = 256 -> 8): the whole row lives in registers, one read pass
 __global__ void __launch_bounds__(256)
 layernorm_interleave4_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps, float* __restrict__ y, long long rows, int H) {
@@ -415,24 +416,38 @@ layernorm_interleave4_fwd_kernel(const float* __restrict__ x, const float* __res
     for (long long row = (long long)blockIdx.x * nwarps + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * nwarps) {
         const float* xr = x + row * D;
         float* yr = y + row * D;
+        float v[HPL][4];
         float s = 0.f;
-        for (int h = lane; h < H; h += 32) s += (__ldg(xr + h) + __ldg(xr + H + h)) + (__ldg(xr + 2 * H + h) + __ldg(xr + 3 * H + h));
+#pragma unroll
+        for (int i = 0; i < HPL; ++i) {
+            const int h = lane + 32 * i;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) v[i][g] = (h < H) ? __ldcs(xr + g * H + h) : 0.f;     // read once, streaming
+            s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+        }
         const float mean = warp_sum(s) / (float)D;
         float q = 0.f;
-        for (int h = lane; h < H; h += 32) {
-            const float a = __ldg(xr + h) - mean, b = __ldg(xr + H + h) - mean, c = __ldg(xr + 2 * H + h) - mean, d = __ldg(xr + 3 * H + h) - mean;
-            q += (a * a + b * b) + (c * c + d * d);
+#pragma unroll
+        for (int i = 0; i < HPL; ++i) {
+            if (lane + 32 * i < H) {
+                const float a = v[i][0] - mean, b = v[i][1] - mean, c = v[i][2] - mean, d = v[i][3] - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
         }
         const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
-        for (int h = lane; h < H; h += 32) {
-            const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + 4 * h)) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 o;
-            o.x = (__ldg(xr + h) - mean) * rstd * gm.x + bt.x;
-            o.y = (__ldg(xr + H + h) - mean) * rstd * gm.y + bt.y;
-            o.z = (__ldg(xr + 2 * H + h) - mean) * rstd * gm.z + bt.z;
-            o.w = (__ldg(xr + 3 * H + h) - mean) * rstd * gm.w + bt.w;
-            *reinterpret_cast<float4*>(yr + 4 * h) = o;
+#pragma unroll
+        for (int i = 0; i < HPL; ++i) {
+            const int h = lane + 32 * i;
+            if (h < H) {
+                const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + 4 * h)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta + 4 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 o;
+                o.x = (v[i][0] - mean) * rstd * gm.x + bt.x;
+                o.y = (v[i][1] - mean) * rstd * gm.y + bt.y;
+                o.z = (v[i][2] - mean) * rstd * gm.z + bt.z;
+                o.w = (v[i][3] - mean) * rstd * gm.w + bt.w;
+                *reinterpret_cast<float4*>(yr + 4 * h) = o;
+            }
         }
     }
 }
@@ -445,7 +460,12 @@ extern "C" int cruse_layernorm_interleave_fwd(const float* x, const float* gamma
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)cruse::sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    cruse::layernorm_interleave4_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, rows, D / 4);
+    const int H = D / 4;
+    CRUSE_CHECK_ARG(H <= 512, "layernorm_interleave_fwd: D = %d too large (D/4 <= 512)", D);
+    if (H <= 256)
+        cruse::layernorm_interleave4_fwd_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, rows, H);
+    else
+        cruse::layernorm_interleave4_fwd_kernel<16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, rows, H);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -33,6 +33,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cooperative_groups.h>
+#include <cstring>
 
 namespace cg = cooperative_groups;
 
@@ -55,6 +56,41 @@ __device__ long long g_seq_timing[8 * 2048];
 #else
 #define SEQ_STAMP(slot) do {} while (0)
 #endif
+
+// Optional chunk-level synchronisation with OTHER kernels running beside this one (the two-layer wavefront without
+// relaunches, cruse_net.GGRU._wavefront): before frame bounds[k] is prefetched the slice waits until wait[k] >= wait_target
+// (set by a tiny kernel queued behind the producer of that chunk's x-projections), and after frame bounds[k+1]-1 is stored it
+// adds 1 to done[k] (release) so that a consumer queued behind cruse_flag_wait may read y up to there.  nchunks == 0: off.
+struct SeqSync {
+    const unsigned* wait;
+    unsigned* done;
+    int* err;
+    unsigned wait_target;
+    int nchunks;
+    int bounds[18];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin (one thread) until *flag >= target; gives up after 2 s and records it, so a broken dependency never hangs the GPU
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned target, int* err) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_gpu(flag) < target) {
+        __nanosleep(200);
+        if (globaltimer_ns() - t0 > 2000000000ull) {
+            if (err) atomicExch(err, 1);
+            break;
+        }
+    }
+}
 
 struct SeqPtrs {
     const float* w_hh[CRUSE_MAX_GROUPS];
@@ -114,7 +150,7 @@ template <int NC>
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const float* __restrict__ h0, float* __restrict__ y,
                   float* __restrict__ hT, float* __restrict__ gates, int B, int T, int G, int H, int y_fs, int y_gs,
-                  long long x_bs, long long x_ts, long long y_bs, long long y_ts) {
+                  long long x_bs, long long x_ts, long long y_bs, long long y_ts, const SeqSync sync) {
     // row (b, t) of xproj is b*x_bs + t*x_ts, of y b*y_bs + t*y_ts ([B,T] frame order: (T,1); time-major [T,B]: (1,B))
     constexpr int SLICE_BYTES = 2 * NC * SQ_H_KB;        // two h buffers of one slice
     extern __shared__ uint8_t smem_raw[];
@@ -273,14 +309,28 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         constexpr int PF = 4;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 xq_r[PF], xq_z[PF], xq_n[PF];                          // queue: [0] = current step, [PF-1] = newest prefetch
+        int kw = 0, kd = 0;                                           // next chunk to wait for / to report
+        int next_wait = sync.nchunks > 0 ? sync.bounds[0] : -1;       // first frame of chunk kw (-1: nothing to wait for)
+        int next_done = sync.nchunks > 0 ? sync.bounds[1] : -1;       // one past the last frame of chunk kd
+        auto chunk_gate = [&](int tp) {                               // called (WG-uniformly) before frame tp is prefetched
+            if (tp == next_wait) {
+                if (sync.wait) {
+                    if (wt == 0) spin_until(sync.wait + kw, sync.wait_target, sync.err);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");
+                }
+                ++kw;
+                next_wait = kw < sync.nchunks ? sync.bounds[kw] : -1;
+            }
+        };
 #pragma unroll
         for (int d = 0; d < PF; ++d) {
             xq_r[d] = xq_z[d] = xq_n[d] = zero4;
+            if (d < T) chunk_gate(d);
             if (valid && d < T) {
                 const float* xq = xp + (size_t)d * xstep;
-                xq_r[d] = __ldg(reinterpret_cast<const float4*>(xq));
-                xq_z[d] = __ldg(reinterpret_cast<const float4*>(xq + H));
-                xq_n[d] = __ldg(reinterpret_cast<const float4*>(xq + 2 * H));
+                xq_r[d] = __ldcg(reinterpret_cast<const float4*>(xq));
+                xq_z[d] = __ldcg(reinterpret_cast<const float4*>(xq + H));
+                xq_n[d] = __ldcg(reinterpret_cast<const float4*>(xq + 2 * H));
             }
         }
         const int q = warp & 3;
@@ -288,11 +338,12 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         for (int t = 0; t < T; ++t) {
             // prefetch the x-projections of step t+PF while the tensor core works
             float4 nxr = zero4, nxz = zero4, nxn = zero4;
+            if (t + PF < T) chunk_gate(t + PF);
             if (valid && t + PF < T) {
                 const float* xq = xp + (size_t)(t + PF) * xstep;
-                nxr = __ldg(reinterpret_cast<const float4*>(xq));
-                nxz = __ldg(reinterpret_cast<const float4*>(xq + H));
-                nxn = __ldg(reinterpret_cast<const float4*>(xq + 2 * H));
+                nxr = __ldcg(reinterpret_cast<const float4*>(xq));
+                nxz = __ldcg(reinterpret_cast<const float4*>(xq + H));
+                nxn = __ldcg(reinterpret_cast<const float4*>(xq + 2 * H));
             }
             const float4 xr = xq_r[0], xz = xq_z[0], xn = xq_n[0];
             tc::mbar_wait(&acc_full[sl], (uint32_t)(t & 1));
@@ -354,6 +405,15 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                 }
             }
             if (sl == 0 && wt == 0) SEQ_STAMP(6);
+            if (t + 1 == next_done) {                                  // chunk kd is stored: publish it
+                if (sync.done) {
+                    __threadfence();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");
+                    if (wt == 0) atomicAdd(sync.done + kd, 1u);
+                }
+                ++kd;
+                next_done = kd < sync.nchunks ? sync.bounds[kd + 1] : -1;
+            }
             p ^= 1;
 #pragma unroll
             for (int d = 0; d + 1 < PF; ++d) { xq_r[d] = xq_r[d + 1]; xq_z[d] = xq_z[d + 1]; xq_n[d] = xq_n[d + 1]; }
@@ -367,8 +427,13 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
     if (warp == 8) tc::tmem_dealloc<SQ_TMEM_COLS>(tmem_base);
 }
 
+// The request is padded to 136 KB although the kernel uses ~78 KB: the recurrence holds all 512 TMEM columns of its SM, so a
+// tensor-core GEMM CTA (gru_ih_tc.cu, 99.5 KB shared memory, 256 TMEM columns) co-scheduled on the same SM would sit in
+// tcgen05.alloc until the recurrence CTA exits.  With 136 KB taken no such CTA fits beside it, and the input projections
+// that run beside the wavefront go to the SMs the recurrence does not use.
 constexpr size_t seq_smem_bytes(int NC) {
-    return 1024 + 2 * 2 * (size_t)NC * SQ_H_KB + (2 * 96 * SQ_PRE_LD + 4) * 4 + 128;
+    const size_t used = 1024 + 2 * 2 * (size_t)NC * SQ_H_KB + (2 * 96 * SQ_PRE_LD + 4) * 4 + 128;
+    return used > 136 * 1024 ? used : 136 * 1024;
 }
 
 template <int NC>
@@ -399,7 +464,8 @@ int max_clusters_tc() {
 
 template <int NC>
 int launch_seq_tc_nc(const float* xproj, const SeqPtrs& ptrs, const float* h0, float* y, float* hT, float* gates, int B, int T,
-                     int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts, long long y_bs, long long y_ts, cudaStream_t st) {
+                     int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts, long long y_bs, long long y_ts, const SeqSync& sync,
+                     cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(gru_seq_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(NC)));
@@ -408,7 +474,7 @@ int launch_seq_tc_nc(const float* xproj, const SeqPtrs& ptrs, const float* h0, f
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     seq_cfg<NC>(cfg, attr, G, (B + 2 * SQ_NB - 1) / (2 * SQ_NB), st);      // one cluster per (group, pair of 16-utterance slices)
-    CRUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gru_seq_tc_kernel<NC>, xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts));
+    CRUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, gru_seq_tc_kernel<NC>, xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, sync));
     return 0;
 }
 
@@ -446,8 +512,11 @@ extern "C" int cruse_gru_seq_tc_max_clusters(int H) {
 
 static int gru_seq_tc_impl(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0, float* y,
                            float* hT, float* gates, int B, int T, int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts,
-                           long long y_bs, long long y_ts, void* stream) {
+                           long long y_bs, long long y_ts, void* stream, const SeqSync* syncp = nullptr) {
     CRUSE_CHECK_ARG(xproj && y && w_hh, "gru_seq_fwd_tc: null pointer");
+    SeqSync sync;
+    memset(&sync, 0, sizeof(sync));
+    if (syncp) sync = *syncp;
     CRUSE_CHECK_ARG(B > 0 && T >= 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0 && H <= 256,
                     "gru_seq_fwd_tc: bad sizes B=%d T=%d G=%d H=%d (H%%4==0, H<=256, G<=%d)", B, T, G, H, CRUSE_MAX_GROUPS);
     SeqPtrs ptrs;
@@ -458,7 +527,7 @@ static int gru_seq_tc_impl(const float* xproj, const float* const* w_hh, const f
         ptrs.b_hh[i] = b_hh ? b_hh[i] : nullptr;
     }
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(N) launch_seq_tc_nc<N>(xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, st)
+#define CALL(N) launch_seq_tc_nc<N>(xproj, ptrs, h0, y, hT, gates, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, sync, st)
     SEQ_TC_DISPATCH((H + SQ_U - 1) / SQ_U, CALL)
 #undef CALL
     set_error("gru_seq_fwd_tc: unsupported H=%d", H);
@@ -476,4 +545,50 @@ extern "C" int cruse_gru_seq_chunk_tc(const float* xproj, const float* const* w_
                                       long long x_ts, long long y_bs, long long y_ts, void* stream) {
     CRUSE_CHECK_ARG(x_bs > 0 && x_ts > 0 && y_bs > 0 && y_ts > 0, "gru_seq_chunk_tc: row strides must be positive");
     return gru_seq_tc_impl(xproj, w_hh, b_hh, h0, y, hT, nullptr, B, Tc, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, stream);
+}
+
+// ---- the wavefront without relaunches: one launch per layer, chunk-level flags between the kernels ------------------
+namespace cruse {
+namespace {
+__global__ void flag_wait_kernel(const unsigned* flag, unsigned target, int* err) {
+    if (threadIdx.x == 0) spin_until(flag, target, err);
+}
+__global__ void flag_set_kernel(unsigned* flag, unsigned value) {
+    __threadfence();
+    atomicExch(flag, value);
+}
+}  // namespace
+}  // namespace cruse
+
+extern "C" int cruse_flag_wait(const unsigned* flag, unsigned target, int* err, void* stream) {
+    CRUSE_CHECK_ARG(flag, "flag_wait: null pointer");
+    cruse::flag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag, target, err);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_flag_set(unsigned* flag, unsigned value, void* stream) {
+    CRUSE_CHECK_ARG(flag, "flag_set: null pointer");
+    cruse::flag_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_gru_seq_flagged_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh, float* y, int B,
+                                        int T, int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts, long long y_bs,
+                                        long long y_ts, const int* bounds, int nchunks, const unsigned* wait_flags,
+                                        unsigned wait_target, unsigned* done_flags, int* err, void* stream) {
+    CRUSE_CHECK_ARG(bounds && nchunks >= 1 && nchunks <= 16, "gru_seq_flagged_tc: 1 <= nchunks <= 16 chunk bounds needed");
+    CRUSE_CHECK_ARG(bounds[0] == 0 && bounds[nchunks] == T, "gru_seq_flagged_tc: bounds must run from 0 to T");
+    for (int k = 0; k < nchunks; ++k)
+        CRUSE_CHECK_ARG(bounds[k + 1] - bounds[k] >= 8, "gru_seq_flagged_tc: chunk %d has %d frames, at least 8 are needed", k, bounds[k + 1] - bounds[k]);
+    SeqSync sync;
+    memset(&sync, 0, sizeof(sync));
+    sync.wait = wait_flags;
+    sync.done = done_flags;
+    sync.err = err;
+    sync.wait_target = wait_target;
+    sync.nchunks = nchunks;
+    for (int k = 0; k <= nchunks; ++k) sync.bounds[k] = bounds[k];
+    return gru_seq_tc_impl(xproj, w_hh, b_hh, nullptr, y, nullptr, nullptr, B, T, G, H, y_fs, y_gs, x_bs, x_ts, y_bs, y_ts, stream, &sync);
 }

@@ -392,6 +392,34 @@ def gru_seq_max_clusters(H):
     return _max_clusters_cache[key]
 
 
+# how the wavefront synchronises its chunks: "flags" = one launch per layer + device-side chunk flags (default);
+# "relaunch" = one recurrence launch per chunk, CUDA events between the streams (no spinning kernels: use this under
+# tools that serialise kernels, e.g. ncu / compute-sanitizer)
+GRU_WAVEFRONT_MODE = os.environ.get("CRUSE_GRU_WAVEFRONT_MODE", "flags")
+
+
+def gru_seq_flagged(xproj_tm, w_hh, b_hh, y, interleave, y_time_major, bounds, wait_flags, wait_target, done_flags, err):
+    """all T frames of one layer in ONE launch; chunk k starts once wait_flags[k] >= wait_target and bumps done_flags[k]
+    when it is stored (include/cruse_b200.h: cruse_gru_seq_flagged_tc)."""
+    T, B, G, H3 = xproj_tm.shape
+    H = H3 // 3
+    y_bs, y_ts = (1, B) if y_time_major else (T, 1)
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    nch = len(bounds) - 1
+    barr = (C.c_int * (nch + 1))(*bounds)
+    _call("cruse_gru_seq_flagged_tc", _p(xproj_tm), _ptr_table(w_hh), _ptr_table(b_hh), _p(y), B, T, G, H, y_fs, y_gs, 1, B, y_bs, y_ts,
+          C.cast(barr, C.c_void_p), nch, _p(wait_flags), int(wait_target), _p(done_flags), _p(err), _stream(),
+          meta=(f"gru_seq_flagged[tf32] G{G} H{H} T{T}", 4 * T * B * G * (H3 + H), 2 * B * T * G * H * 3 * H))
+
+
+def flag_set(flag, value=1):
+    _call("cruse_flag_set", _p(flag), int(value), _stream())
+
+
+def flag_wait(flag, target, err):
+    _call("cruse_flag_wait", _p(flag), int(target), _p(err), _stream())
+
+
 def layernorm_fwd_into(x, gamma, beta, eps, y):
     """LayerNorm over the rows of a contiguous slice, written into a preallocated slice (no allocation: runs on side streams)."""
     D = x.shape[-1]

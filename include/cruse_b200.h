@@ -164,6 +164,20 @@ int cruse_gru_seq_chunk_tc(const float* xproj, const float* const* w_hh, const f
                            const float* h0, float* y, float* hT, int B, int Tc, int G, int H, int y_fs, int y_gs,
                            long long x_bs, long long x_ts, long long y_bs, long long y_ts, void* stream);
 
+/* The same wavefront WITHOUT relaunching the recurrence per chunk: one launch per layer over all T frames; before the
+ * x-projections of frame bounds[k] are fetched the kernel waits (bounded spin, 2 s, then *err = 1) until
+ * wait_flags[k] >= wait_target, and after frame bounds[k+1]-1 has been stored every (CTA, slice) adds 1 to done_flags[k]
+ * (release), i.e. done_flags[k] reaches G * ceil(H/32) * ceil(B/16).  cruse_flag_set / cruse_flag_wait are the one-thread
+ * kernels the host queues behind a producer / in front of a consumer on its stream.  bounds: HOST array of nchunks+1
+ * frame indices (0 .. T, chunks of at least 8 frames); wait_flags / done_flags / err: device, may be NULL. */
+int cruse_gru_seq_flagged_tc(const float* xproj, const float* const* w_hh, const float* const* b_hh, float* y,
+                             int B, int T, int G, int H, int y_fs, int y_gs,
+                             long long x_bs, long long x_ts, long long y_bs, long long y_ts,
+                             const int* bounds, int nchunks, const unsigned* wait_flags, unsigned wait_target,
+                             unsigned* done_flags, int* err, void* stream);
+int cruse_flag_wait(const unsigned* flag, unsigned target, int* err, void* stream);
+int cruse_flag_set(unsigned* flag, unsigned value, void* stream);
+
 /* how many clusters of the tcgen05 recurrence kernel the current device can hold at once (each serves two
  * software-pipelined slices of 16 utterances of one group); G*ceil(B/32) above this runs in waves.  <0 on error. */
 int cruse_gru_seq_tc_max_clusters(int H);

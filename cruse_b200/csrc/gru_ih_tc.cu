@@ -158,6 +158,14 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
             tc::mbar_wait(acc_full, 0);
             tc::tc_fence_after();
         }
+        // The accumulator comes out of TMEM with lane = row: storing it directly would make every 16-byte store of a warp hit
+        // 32 different rows (ldc floats apart) -- half-sector strided writes.  Instead each warp transposes its 32 x 32 chunk
+        // through shared memory (the operand stages are free once the accumulator is complete; pitch 36 floats keeps both the
+        // 16-byte stores by row and the 16-byte loads by column group bank-conflict free) and writes 4 full 128-byte row
+        // segments per instruction.
+        float* stg = reinterpret_cast<float*>(tiles) + quad * (32 * 36);
+        const int rr = lane >> 3, cc = (lane & 7) * 4;           // store phase: lane -> (row rr + 4i, columns cc..cc+3)
+        float* obase = args.out[g] + (size_t)split * c_plane + n0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= N) break;                      // warp-uniform
@@ -169,7 +177,24 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
-            if (m < M) {
+            if (vec_ok && n0 + c + 32 <= N) {
+                __syncwarp();                               // the previous chunk's loads from the staging tile are done
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j] + s_bias[c + j], v[j + 1] + s_bias[c + j + 1],
+                                                                                   v[j + 2] + s_bias[c + j + 2], v[j + 3] + s_bias[c + j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rr + 4 * i;
+                    const int mm = m0 + quad * 32 + r;
+                    if (mm < M) {
+                        size_t mr = (size_t)mm;
+                        if (tm_T > 0) { const int bq = mm / tm_T; mr = (size_t)(mm - bq * tm_T) * (size_t)(M / tm_T) + bq; }
+                        *reinterpret_cast<float4*>(obase + mr * ldc + c + cc) = *reinterpret_cast<const float4*>(stg + r * 36 + cc);
+                    }
+                }
+            } else if (m < M) {                            // ragged N edge / unaligned C: direct stores
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (vec_ok && n0 + c + j + 3 < N) {

@@ -228,3 +228,27 @@ def test_captured_graph_and_wavefront_match_eager(cuda):
     finally:
         ops.GRU_WAVEFRONT = old
     assert rel_err(m2, m0) <= 1e-3 and abs(float(l2) - float(l0)) <= 1e-3 * abs(float(l0))
+
+
+def test_wavefront_modes_agree_and_no_flag_timeout(cuda):
+    """the flag-synchronised wavefront (one recurrence launch per layer, device-side chunk flags) and the relaunch wavefront
+    (one launch per chunk, CUDA events) are the same arithmetic in a different schedule: bit-identical masks; the bounded
+    spins of the flag mode must never time out (error flag stays 0)."""
+    from cruse_b200 import ops, pipeline
+    ours, _ = _pair(256, "relu", cuda)
+    ours.eval()
+    g = torch.Generator().manual_seed(5)
+    noisy, clean = 0.1 * torch.randn(5, 96000, generator=g), 0.05 * torch.randn(5, 96000, generator=g)     # T = 301
+    out = {}
+    old = ops.GRU_WAVEFRONT_MODE
+    try:
+        for mode in ("flags", "relaunch"):
+            ops.GRU_WAVEFRONT_MODE = mode
+            with torch.no_grad():
+                out[mode] = pipeline.forward_loss(ours, noisy.to(cuda), clean.to(cuda), 512, 320)
+            torch.cuda.synchronize()
+            if mode == "flags":
+                assert int(ours.gru._wavefront_err.item()) == 0
+    finally:
+        ops.GRU_WAVEFRONT_MODE = old
+    assert torch.equal(out["flags"][3], out["relaunch"][3]) and torch.equal(out["flags"][0], out["relaunch"][0])

@@ -28,14 +28,17 @@ wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, cons
     const float alpha = 2.f, beta = 1.f;              // loss.py:126-128 (gamma = 1)
     const float inv_ln10 = 0.43429448190325176f;
     float acc = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(i % F);
-        const long long bt = i / F;
-        const int t = (int)(bt % T);
-        const long long b = bt / T;
-        const float2 r = ld_cplx(ref, b * lr.sb + t * lr.st + f * lr.sf, lr.im_off);
-        const long long eoff = b * le.sb + t * le.st + f * le.sf;
-        const float2 u = ld_cplx(unp, b * lu.sb + t * lu.st + f * lu.sf, lu.im_off);
+    // one (b, t) row of F bins per CTA iteration; (b, t) advance incrementally -- no 64-bit division per element
+    const long long rows = total / F;
+    int t = (int)(blockIdx.x % T);
+    long long b = blockIdx.x / T;
+    for (long long bt = blockIdx.x; bt < rows; bt += gridDim.x) {
+      const long long rbase = b * lr.sb + t * lr.st, ebase = b * le.sb + t * le.st, ubase = b * lu.sb + t * lu.st;
+      for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const long long i = bt * F + f;
+        const float2 r = ld_cplx(ref, rbase + f * lr.sf, lr.im_off);
+        const long long eoff = ebase + f * le.sf;
+        const float2 u = ld_cplx(unp, ubase + f * lu.sf, lu.im_off);
         float2 e;
         if (mask) {
             const float mk = __ldg(mask + i);
@@ -62,6 +65,10 @@ wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, cons
                 dest[eoff + le.im_off] = s * e.y;
             }
         }
+      }
+      t += (int)(gridDim.x % T);
+      b += gridDim.x / T;
+      if (t >= T) { t -= T; ++b; }
     }
     __shared__ float sh[LOSS_THREADS / 32];
     acc = warp_sum(acc);
@@ -102,7 +109,7 @@ static int wo_male_launch(const float* ref, cruse_cplx_layout lref, const float*
     CRUSE_CHECK_ARG(ref && (est || mask) && unproc && loss && ws, "wo_male: null pointer");
     CRUSE_CHECK_ARG(B > 0 && T > 0 && F > 0, "wo_male: bad sizes B=%d T=%d F=%d", B, T, F);
     const long long total = (long long)B * T * F;
-    long long blocks = (total + LOSS_THREADS * 4 - 1) / (LOSS_THREADS * 4);
+    long long blocks = (long long)B * T;                       // one (b, t) row per CTA iteration
     long long cap = (long long)sm_count() * 8;
     if (cap > LOSS_MAX_PARTS) cap = LOSS_MAX_PARTS;
     if (blocks > cap) blocks = cap;

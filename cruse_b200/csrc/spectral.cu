@@ -242,21 +242,26 @@ mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask
         m_hi = a > c ? a : c;
     }
     float* wo = wav + (long long)b * L;
-    for (long long m = m_lo + threadIdx.x; m < m_hi; m += blockDim.x) {
-        const long long s = m - M;
-        if (s < 0 || s >= L) continue;
-        int t_hi = (int)(m / hop);
-        if (t_hi > T - 1) t_hi = T - 1;
-        long long num = m - N + hop;
-        int t_lo = num > 0 ? (int)(num / hop) : 0;
-        float sum = 0.f, env = 0.f;
-        for (int t = t_lo; t <= t_hi; ++t) {
-            const int off = (int)(m - (long long)t * hop);
-            sum += frames[(size_t)(t - tbeg) * N + off];
-            const float w = __ldg(window + off);
-            env += w * w;
+    // overlap-add by (frame slot i, offset r inside the hop): sample m = (t0+i)*hop + r is covered by frame t0+i at offset r,
+    // frame t0+i-1 at offset r+hop, ... while the offset stays below N -- no division per sample
+    const int nslots = (int)((m_hi - m_lo + hop - 1) / hop);
+    for (int i = 0; i < nslots; ++i) {
+        const int tt = t0 + i;
+        for (int r = threadIdx.x; r < hop; r += blockDim.x) {
+            const long long m = m_lo + (long long)i * hop + r;
+            const long long sidx = m - M;
+            if (m >= m_hi || sidx < 0 || sidx >= L) continue;
+            float sum = 0.f, env = 0.f;
+            int t = tt;
+            for (int off = r; off < N; off += hop, --t) {
+                if (t < 0) break;
+                if (t > T - 1) continue;
+                sum += frames[(size_t)(t - tbeg) * N + off];
+                const float w = __ldg(window + off);
+                env += w * w;
+            }
+            wo[sidx] = env > 1e-11f ? sum / env : 0.f;
         }
-        wo[s] = env > 1e-11f ? sum / env : 0.f;
     }
 }
 

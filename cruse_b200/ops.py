@@ -395,7 +395,12 @@ def gru_seq_max_clusters(H):
 # how the wavefront synchronises its chunks: "flags" = one launch per layer + device-side chunk flags (default);
 # "relaunch" = one recurrence launch per chunk, CUDA events between the streams (no spinning kernels: use this under
 # tools that serialise kernels, e.g. ncu / compute-sanitizer)
-GRU_WAVEFRONT_MODE = os.environ.get("CRUSE_GRU_WAVEFRONT_MODE", "flags")
+def _under_kernel_serialising_tool():
+    # Nsight Compute (ncu) replays / serialises kernels; its injection sets these variables in the profiled process
+    return any(k in os.environ for k in ("NV_TPS_LAUNCH_TOKEN", "NV_NSIGHT_INJECTION_PORT_BASE", "NV_COMPUTE_PROFILER_PERFWORKS_DIR"))
+
+
+GRU_WAVEFRONT_MODE = os.environ.get("CRUSE_GRU_WAVEFRONT_MODE", "relaunch" if _under_kernel_serialising_tool() else "flags")
 
 
 def gru_seq_flagged(xproj_tm, w_hh, b_hh, y, interleave, y_time_major, bounds, wait_flags, wait_target, done_flags, err):

@@ -33,12 +33,10 @@ namespace cruse {
 namespace {
 
 constexpr int CT_NPW = 8;                                  // producer warps per set
-constexpr int CT_SETS = 2;                                 // producer sets, alternating over A-tile groups
-constexpr int CT_PROD_WARPS = CT_NPW * CT_SETS;
-constexpr int CT_MMA_WARP = CT_PROD_WARPS;
-constexpr int CT_EPI_WARP0 = CT_PROD_WARPS + 1;
+// producer sets (NS, per instantiation): 2 sets of 8 warps alternate over the A-tile groups, or 1 set where the deep
+// load bursts of two sets delay the epilogue's stores more than they help (measured per stage, see the dispatch table)
 constexpr int CT_EPI_WARPS = 8;                            // two per TMEM lane quadrant, splitting the accumulator columns
-constexpr int CT_THREADS = (CT_PROD_WARPS + 1 + CT_EPI_WARPS) * 32;   // 800
+constexpr int ct_threads(int ns) { return (CT_NPW * ns + 1 + CT_EPI_WARPS) * 32; }   // 800 / 544
 constexpr int CT_SMEM_BUDGET = 222 * 1024;
 
 // optional cap on the persistent grid (0 = one CTA per SM): lets a stage run beside the GRU wavefront on the SMs it leaves free
@@ -118,8 +116,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {   // this 
         : "memory");
 }
 
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
-__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs a) {
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS>
+__global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTcArgs a) {
+    constexpr int CT_SETS = NS, CT_PROD_WARPS = CT_NPW * NS, CT_MMA_WARP = CT_PROD_WARPS, CT_EPI_WARP0 = CT_PROD_WARPS + 1;
+    constexpr int CT_THREADS = ct_threads(NS);
     using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms are 1024-byte aligned
@@ -422,10 +422,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const ConvTcArgs
     if (warp == CT_MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS>
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
     using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
-    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO, GM>;
+    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO, GM, NS>;
     static bool attr_set = false;                                   // per instantiation; benign if raced
     if (!attr_set) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -435,7 +435,7 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
     const long long ntiles = (long long)a.B * chunks;
     int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
     if (g_conv_max_ctas > 0 && grid > g_conv_max_ctas) grid = g_conv_max_ctas;
-    kern<<<grid, CT_THREADS, C::SMEM, st>>>(a);
+    kern<<<grid, ct_threads(NS), C::SMEM, st>>>(a);
     CRUSE_LAUNCH_OK();
     return 0;
 }
@@ -465,18 +465,18 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
     ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm};
     int rc = 0;
     // last argument: MMA tiles (128 rows) per pipeline step; stages with long frames (FO >= 32) batch several of them
-#define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_)                                                         \
+#define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_, NS_)                                                    \
     if (kt == KT_ && fstride == SF_ && Cin == CI_ && Cout == CO_ && Fout == FO_ && Fin == SF_ * FO_) {      \
-        rc = launch_conv_tc<0, KT_, SF_, CI_, CO_, FO_, GM_>(a, st);                                        \
+        rc = launch_conv_tc<0, KT_, SF_, CI_, CO_, FO_, GM_, NS_>(a, st);                                   \
         return rc ? rc : 1;                                                                                 \
     }
-    CRUSE_CT_CONV(2, 2, 8, 16, 64, 4)
-    CRUSE_CT_CONV(2, 2, 16, 32, 32, 1)
-    CRUSE_CT_CONV(2, 2, 32, 64, 16, 1)
-    CRUSE_CT_CONV(1, 1, 8, 8, 128, 4)
-    CRUSE_CT_CONV(1, 1, 16, 16, 64, 1)
-    CRUSE_CT_CONV(1, 1, 32, 32, 32, 1)
-    CRUSE_CT_CONV(1, 1, 64, 64, 16, 1)
+    CRUSE_CT_CONV(2, 2, 8, 16, 64, 4, 2)
+    CRUSE_CT_CONV(2, 2, 16, 32, 32, 1, 2)
+    CRUSE_CT_CONV(2, 2, 32, 64, 16, 1, 1)
+    CRUSE_CT_CONV(1, 1, 8, 8, 128, 4, 2)
+    CRUSE_CT_CONV(1, 1, 16, 16, 64, 1, 2)
+    CRUSE_CT_CONV(1, 1, 32, 32, 32, 1, 2)
+    CRUSE_CT_CONV(1, 1, 64, 64, 16, 1, 2)
 #undef CRUSE_CT_CONV
     return 0;
 }
@@ -487,14 +487,14 @@ int convT_tc_try(const float* in, const float* w, const float* bias, const float
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
     ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0};
     int rc = 0;
-#define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_)                                           \
+#define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_, NS_)                                      \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \
-        rc = launch_conv_tc<1, 1, 1, CI_, CO_, FI_, GM_>(a, st);                     \
+        rc = launch_conv_tc<1, 1, 1, CI_, CO_, FI_, GM_, NS_>(a, st);                \
         return rc ? rc : 1;                                                          \
     }
-    CRUSE_CT_CONVT(64, 32, 16, 1)
-    CRUSE_CT_CONVT(32, 16, 32, 1)
-    CRUSE_CT_CONVT(16, 8, 64, 2)
+    CRUSE_CT_CONVT(64, 32, 16, 1, 1)
+    CRUSE_CT_CONVT(32, 16, 32, 1, 2)
+    CRUSE_CT_CONVT(16, 8, 64, 2, 2)
 #undef CRUSE_CT_CONVT
     return 0;
 }

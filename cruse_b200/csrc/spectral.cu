@@ -111,6 +111,44 @@ __device__ float2* warp_fft(float2* x, float2* y, const float2* __restrict__ tw,
     return x;
 }
 
+// The same transform specialised for M = 256 = 4^4 (n_fft = 512, the geometry of the benchmark): four radix-4 passes
+// with compile-time strides -- no divisions, the four inputs of a butterfly are always 64 apart, the last pass needs no
+// twiddles.  Result is back in x (even number of ping-pong passes).
+template <bool INV, int S>
+__device__ __forceinline__ void fft256_pass(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw, int lane) {
+    constexpr int TWSTEP = 2 * S;                      // N / n_cur = 512 / (256 / S)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        const int p = i / S, q = i % S;                // S is a power of two: shift / mask
+        const float2 a0 = x[i], a1 = x[i + 64], a2 = x[i + 128], a3 = x[i + 192];
+        const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
+        const float2 t3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);  // d * (+-i)
+        const float2 b0 = cadd(t0, t2), b1 = cadd(t1, t3), b2 = csub(t0, t2), b3 = csub(t1, t3);
+        float2* yo = y + q + 4 * S * p;
+        if (S == 64) {                                 // p == 0: all roots are 1
+            yo[0] = b0; yo[S] = b1; yo[2 * S] = b2; yo[3 * S] = b3;
+        } else {
+            float2 w1 = tw[p * TWSTEP], w2 = tw[2 * p * TWSTEP], w3 = tw[3 * p * TWSTEP];
+            if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+            yo[0] = b0;
+            yo[S] = cmul(b1, w1);
+            yo[2 * S] = cmul(b2, w2);
+            yo[3 * S] = cmul(b3, w3);
+        }
+    }
+    __syncwarp();
+}
+
+template <bool INV>
+__device__ __forceinline__ float2* warp_fft256(float2* x, float2* y, const float2* __restrict__ tw, int lane) {
+    fft256_pass<INV, 1>(x, y, tw, lane);
+    fft256_pass<INV, 4>(y, x, tw, lane);
+    fft256_pass<INV, 16>(x, y, tw, lane);
+    fft256_pass<INV, 64>(y, x, tw, lane);
+    return x;
+}
+
 __device__ __forceinline__ float load_padded(const float* __restrict__ xb, int i, int L, int pad_mode) {
     if (i < 0) {
         if (pad_mode == CRUSE_PAD_CONSTANT) return 0.f;
@@ -156,7 +194,7 @@ stft_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ window,
             }
         }
         __syncwarp();
-        const float2* Z = warp_fft<false>(x, y, tw, M, plan, lane);
+        const float2* Z = (M == 256) ? warp_fft256<false>(x, y, tw, lane) : warp_fft<false>(x, y, tw, M, plan, lane);
         float2* so = reinterpret_cast<float2*>(spec) + fr * NF;
         float* mo = mag ? mag + fr * mag_bins : nullptr;
         for (int k = lane; k <= M; k += 32) {
@@ -221,7 +259,7 @@ mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask
                 x[k] = make_float2(xe.x - xo.y, xe.y + xo.x);  // Xe + i*Xo
             }
             __syncwarp();
-            const float2* z = warp_fft<true>(x, y, tw, M, plan, lane);
+            const float2* z = (M == 256) ? warp_fft256<true>(x, y, tw, lane) : warp_fft<true>(x, y, tw, M, plan, lane);
             float* fb = frames + (size_t)fi * N;
             for (int n = lane; n < M; n += 32) {
                 float2 v = z[n];
@@ -300,7 +338,7 @@ extern "C" int cruse_stft_fwd(const float* wav, const float* window, float* spec
     CRUSE_CUDA_OK(cudaFuncSetAttribute(stft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long nframes = (long long)B * T;
     long long blocks = (nframes + nwarps - 1) / nwarps;
-    const long long cap = (long long)sm_count() * 4;  // persistent-ish: each CTA builds its twiddle table once
+    const long long cap = (long long)sm_count() * 6;  // persistent-ish (6 CTAs of 36 KB fit an SM): each CTA builds its twiddle table once
     if (blocks > cap) blocks = cap;
     stft_fwd_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(wav, window, spec, mag_bins > 0 ? mag : nullptr, B, L, n_fft,
                                                                              hop, T, pad_mode, mag_bins, mag_eps, plan);

@@ -15,6 +15,10 @@
 
 namespace cruse {
 
+// conv_wgrad_tc.cu: the same reduction as a split-K tcgen05 GEMM (tf32) for the 256-bin pyramid
+int conv_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt,
+                      int fstride, int pitch, int max_grid, cudaStream_t st);
+
 constexpr int WG_TT = 8;
 constexpr int WG_THREADS = 256;
 
@@ -190,10 +194,17 @@ extern "C" int cruse_conv_wgrad(const float* in, const float* dz, float* dw, flo
     CRUSE_CHECK_ARG(Fout == (Fin + 2 - 3) / fstride + 1, "conv_wgrad: Fout=%d does not match Fin=%d", Fout, Fin);
     const size_t smem = wgrad_smem(kt, Cin, Fin, Cout, Fout);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_wgrad: stage needs %zu B shared memory", smem);
-    const int grid = wgrad_grid(B, T, smem);
+    int grid = wgrad_grid(B, T, smem);
     const int nW = Cout * Cin * kt * 3;
     cudaStream_t st = (cudaStream_t)stream;
-    if (kt == 2) {
+    int np_tc = 0;
+    if (cruse_conv_get_mode() == 1) {       // tf32 mode: tensor-core split-K GEMM; same partial layout, same fixed-order reduction
+        np_tc = conv_wgrad_tc_try(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout, kt, fstride, nW + Cout, grid, st);
+        if (np_tc < 0) return np_tc;
+    }
+    if (np_tc > 0) {
+        grid = np_tc;
+    } else if (kt == 2) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_wgrad_kernel<0, 2, 2><<<grid, WG_THREADS, smem, st>>>(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout);
     } else {

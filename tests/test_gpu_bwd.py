@@ -19,9 +19,52 @@ def _to_frames(x):      # [B,C,T,F] -> [B,T,C,F]
     return x.permute(0, 2, 1, 3).contiguous()
 
 
+@pytest.fixture
+def exact_conv(cuda):
+    """the per-kernel conv backward tests check the exact-fp32 CUDA-core kernels to 1e-4; the tensor-core (tf32) weight
+    gradient is checked separately to its own stated gate"""
+    from cruse_b200 import ops
+    old = ops.get_conv_mode()
+    ops.set_conv_mode("fp32")
+    yield
+    ops.set_conv_mode(old)
+
+
+@pytest.mark.parametrize("kind,cin,cout,F", [("enc", 8, 16, 128), ("enc", 16, 32, 64), ("enc", 32, 64, 32),
+                                             ("skip", 8, 8, 128), ("skip", 16, 16, 64), ("skip", 32, 32, 32), ("skip", 64, 64, 16)])
+@pytest.mark.parametrize("B,T", [(3, 11), (2, 64)])
+def test_conv_weight_gradient_on_tensor_cores(cuda, kind, cin, cout, F, B, T):
+    """split-K tcgen05 weight gradient (conv_wgrad_tc.cu, tf32 operands, fp32 accumulation over all B*T*Fout positions in
+    TMEM) against torch autograd in fp32; stated tolerance 2e-3 of max|dW| (same gate as the tf32 GRU weight gradients).
+    B*T = 33 frames exercises the ragged last k-block / frames without a predecessor."""
+    from cruse_b200 import ops
+    torch.manual_seed(31)
+    ops.set_conv_mode("tf32")
+    if kind == "enc":
+        conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), (1, 1))
+        x = torch.randn(B, cin, T, F, requires_grad=True)
+        z = conv(x)[..., :-1, :]
+        kt, fs = 2, 2
+    else:
+        conv = nn.Conv2d(cin, cout, (1, 3), bias=False, padding=(0, 1))
+        x = torch.randn(B, cin, T, F, requires_grad=True)
+        z = conv(x)
+        kt, fs = 1, 1
+    gz = torch.randn_like(z)
+    z.backward(gz)
+    dw, db = ops.conv_wgrad(_to_frames(x.detach()).to(cuda), _to_frames(gz).to(cuda), kt, fs)
+    assert rel_err(dw, conv.weight.grad) <= 2e-3
+    if conv.bias is not None:
+        assert rel_err(db, conv.bias.grad) <= 2e-3
+    ops.set_conv_mode("fp32")            # the exact kernel on the same inputs: proves the dispatch switched
+    dw32, _ = ops.conv_wgrad(_to_frames(x.detach()).to(cuda), _to_frames(gz).to(cuda), kt, fs)
+    ops.set_conv_mode("tf32")
+    assert rel_err(dw32, conv.weight.grad) <= 1e-4 and not torch.equal(dw32, dw)
+
+
 @pytest.mark.parametrize("cin,cout,F,act", [(1, 8, 256, "relu"), (8, 16, 128, "prelu"), (16, 32, 64, "relu"), (32, 64, 32, "prelu"),
                                            (8, 16, 81, "relu"), (3, 5, 21, "prelu")])
-def test_encoder_stage_backward(cuda, cin, cout, F, act):
+def test_encoder_stage_backward(cuda, exact_conv, cin, cout, F, act):
     """conv(2,3)/s(1,2) + causal slice + train-mode BN + act: dgrad, wgrad, dbias, dgamma, dbeta, dalpha."""
     from cruse_b200 import ops
     torch.manual_seed(20)
@@ -65,7 +108,7 @@ def test_encoder_stage_backward(cuda, cin, cout, F, act):
 
 
 @pytest.mark.parametrize("c,F", [(8, 128), (64, 16), (16, 41), (5, 7)])
-def test_skip_conv_backward(cuda, c, F):
+def test_skip_conv_backward(cuda, exact_conv, c, F):
     from cruse_b200 import ops
     torch.manual_seed(21)
     B, T = 2, 9
@@ -83,7 +126,7 @@ def test_skip_conv_backward(cuda, c, F):
 
 @pytest.mark.parametrize("cin,cout,Fin,Fout,act", [(64, 32, 16, 32, "relu"), (32, 16, 32, 64, "prelu"), (16, 8, 64, 128, "relu"),
                                                    (64, 32, 11, 21, "prelu"), (16, 8, 41, 81, "relu")])
-def test_decoder_stage_backward(cuda, cin, cout, Fin, Fout, act):
+def test_decoder_stage_backward(cuda, exact_conv, cin, cout, Fin, Fout, act):
     """ConvTranspose2d(1,3)/s(1,2) + crop + train BN + act + skip."""
     from cruse_b200 import ops
     torch.manual_seed(22)

@@ -19,6 +19,9 @@ namespace cruse {
 int conv_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt,
                       int fstride, int pitch, int max_grid, cudaStream_t st);
 
+int convT_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int pitch,
+                       int max_grid, cudaStream_t st);
+
 constexpr int WG_TT = 8;
 constexpr int WG_THREADS = 256;
 
@@ -238,12 +241,21 @@ extern "C" int cruse_convT_wgrad(const float* in, const float* dz, float* dw, fl
     CRUSE_CHECK_ARG(Fout >= 2 * Fin - 2 && Fout <= 2 * Fin && Fout > 0, "convT_wgrad: Fout=%d must be in [2*Fin-2, 2*Fin] (Fin=%d)", Fout, Fin);
     const size_t smem = wgrad_smem(1, Cin, Fin, Cout, Fout);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "convT_wgrad: stage needs %zu B shared memory", smem);
-    const int grid = wgrad_grid(B, T, smem);
+    int grid = wgrad_grid(B, T, smem);
     const int nW = Cout * Cin * 3, n = nW + Cout;
     cudaStream_t st = (cudaStream_t)stream;
-    CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_wgrad_kernel<1, 1, 2><<<grid, WG_THREADS, smem, st>>>(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout);
-    CRUSE_LAUNCH_OK();
+    int np_tc = 0;
+    if (cruse_conv_get_mode() == 1) {
+        np_tc = convT_wgrad_tc_try(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout, n, grid, st);
+        if (np_tc < 0) return np_tc;
+    }
+    if (np_tc > 0) {
+        grid = np_tc;
+    } else {
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_wgrad_kernel<1, 1, 2><<<grid, WG_THREADS, smem, st>>>(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout);
+        CRUSE_LAUNCH_OK();
+    }
     colsum_kernel<<<(nW + 255) / 256, 256, 0, st>>>((const float*)ws, grid, n, nW, dw, 0);
     CRUSE_LAUNCH_OK();
     if (dbias) {

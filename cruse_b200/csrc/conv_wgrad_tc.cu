@@ -18,6 +18,10 @@
 // whole launch; at the end the CTA writes its partial [Cout x Cin*KT*3 | Cout] and cruse_conv_wgrad sums the
 // partials in a fixed order (deterministic, no atomics).  Replaces the CUDA-core kernel of conv_bwd.cu (0.2-0.9 ms
 // per stage) when the conv mode is tf32.
+//
+// MODE 1 is the transposed conv of the decoder, dW[ci, (co,k)] = sum_p x[p, ci] * dz[b,t,co, 2i+k]: the plain operand
+// (A, lanes) is the input x, the tapped operand (B, columns) is dz read at bins 2i, 2i+1, 2i+2 (cropped), and the row of
+// ones sits in A: its accumulator lane holds sum_p dz[.., 2i+k], i.e. dbias[co] = columns (co,0) + (co,1).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,23 +36,27 @@ constexpr int WT_THREADS = (WT_PROD_WARPS + 1) * 32;   // 544
 constexpr int WT_STAGES = 4;
 constexpr int WT_TMEM_COLS = 256;
 
-template <int KT, int SF, int CIN, int COUT, int FO>
+// MODE 0: conv (KT x 3, stride SF, pad 1): plain operand A = dz (CP = Cout channels), tapped operand B = x (CQ = Cin).
+// MODE 1: convT (1 x 3, stride 2):          plain operand A = x (CP = Cin channels),  tapped operand B = dz (CQ = Cout).
+// FO = bins per frame of the POSITIONS (= of the plain operand); the tapped operand has TSF * FO bins.
+template <int MODE, int KT, int SF, int CP, int CQ, int FO>
 struct WgradCfg {
     static constexpr int NTAP = KT * 3;
-    static constexpr int NW = CIN * NTAP;                          // weight columns per output channel
+    static constexpr int NW = CQ * NTAP;                           // accumulator columns that are weights
     static constexpr int NWP = (NW + 15) / 16 * 16;
-    static constexpr int N = NWP + 16;                             // + the bias block (row NWP = ones)
-    static constexpr int FIN = SF * FO;
-    static constexpr int A_BYTES = 128 * 128;                      // 128 rows (co, zero above COUT) x 32 positions
+    static constexpr int N = MODE == 0 ? NWP + 16 : NWP;           // conv: + the bias block (row NWP of B = ones)
+    static constexpr int TSF = MODE == 0 ? SF : 2;                 // bins of the tapped operand per position
+    static constexpr int FQ = TSF * FO;
+    static constexpr int A_BYTES = 128 * 128;                      // 128 rows (zero above CP [+1]) x 32 positions
     static constexpr int B_BYTES = N * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SMEM = 1024 + WT_STAGES * STAGE_BYTES + 256;
-    static constexpr int NA = COUT / WT_NPW;                       // dz rows per producer warp and k-block
-    static constexpr int NC = CIN / WT_NPW;                        // input channels per producer warp and k-block
-    static_assert(COUT % WT_NPW == 0 && CIN % WT_NPW == 0, "channels must split over the producer warps");
-    static_assert(N <= WT_TMEM_COLS && N % 16 == 0, "accumulator columns");
+    static constexpr int NA = CP / WT_NPW;                         // plain rows per producer warp and k-block
+    static constexpr int NC = CQ / WT_NPW;                         // tapped channels per producer warp and k-block
+    static_assert(CP % WT_NPW == 0 && CQ % WT_NPW == 0, "channels must split over the producer warps");
+    static_assert(N <= WT_TMEM_COLS && N % 16 == 0 && CP + 1 <= 128, "accumulator shape");
     static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
-    static_assert(FO % 16 == 0, "bins per frame");
+    static_assert(FO % 16 == 0 && (MODE == 0 || KT == 1), "geometry");
 };
 
 __device__ __forceinline__ uint32_t to_tf32_bits(float v) {
@@ -60,10 +68,12 @@ __device__ __forceinline__ uint32_t to_tf32_bits(float v) {
 // byte offset of (row r, position k) inside a K-major SWIZZLE_128B tile of 128-byte rows
 __device__ __forceinline__ uint32_t row_off(int r, int k) { return (uint32_t)(r * 128 + ((((k >> 2) ^ (r & 7))) << 4) + ((k & 3) << 2)); }
 
-template <int KT, int SF, int CIN, int COUT, int FO>
+template <int MODE, int KT, int SF, int CP, int CQ, int FO>
 __global__ void __launch_bounds__(WT_THREADS, 1)
-conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ ws, int B, int T, int pitch) {
-    using C = WgradCfg<KT, SF, CIN, COUT, FO>;
+conv_wgrad_tc_kernel(const float* __restrict__ pl, const float* __restrict__ tp, float* __restrict__ ws, int B, int T, int pitch) {
+    // pl = plain operand [B,T,CP,FO] (conv: dz, convT: x);  tp = tapped operand [B,T,CQ,FQ] (conv: x, convT: dz)
+    using C = WgradCfg<MODE, KT, SF, CP, CQ, FO>;
+    constexpr int TS = C::TSF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* stages = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -88,7 +98,8 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
     __syncthreads();
     for (int i = tid; i < WT_STAGES * 32; i += WT_THREADS) {
         const int s = i >> 5, k = i & 31;
-        *reinterpret_cast<float*>(stages + s * C::STAGE_BYTES + C::A_BYTES + row_off(C::NWP, k)) = 1.0f;
+        if (MODE == 0) *reinterpret_cast<float*>(stages + s * C::STAGE_BYTES + C::A_BYTES + row_off(C::NWP, k)) = 1.0f;
+        else *reinterpret_cast<float*>(stages + s * C::STAGE_BYTES + row_off(CP, k)) = 1.0f;
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before();
@@ -99,11 +110,10 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
     if (warp < WT_PROD_WARPS) {
         // ================= producers =================
         const int set = warp / WT_NPW, wq = warp % WT_NPW;
-        float av[C::NA];                                    // dz rows co = wq + 8*i
-        float xv[C::NC][KT][SF == 2 ? 2 : 1];               // input channel ci = wq + 8*i, time tap kt: bins SF*fo (, SF*fo+1)
+        float av[C::NA];                                    // plain rows c = wq + 8*i
+        float xv[C::NC][KT][TS];                            // tapped channel c = wq + 8*i, time tap kt: bins TS*f (, TS*f+1)
         float xe[C::NC][KT][2];                             // neighbours that are not in the warp: [0] left of lane 0, [1] right of lane 31
         int fo_cur = 0;
-        bool pv_cur = false;
 
         auto load_kb = [&](int j) {                         // j = local k-block index of this CTA
             const long long P = ((long long)blockIdx.x + (long long)j * gridDim.x) * 32 + lane;
@@ -112,22 +122,21 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
             const int fo = pv ? (int)(P - g * FO) : 0;
             const int t = (int)(g % T);
             fo_cur = fo;
-            pv_cur = pv;
-            const float* dzp = dz + (size_t)g * (COUT * FO) + fo;
+            const float* pp = pl + (size_t)g * (CP * FO) + fo;
 #pragma unroll
-            for (int i = 0; i < C::NA; ++i) av[i] = pv ? __ldg(dzp + (size_t)(wq + WT_NPW * i) * FO) : 0.f;
+            for (int i = 0; i < C::NA; ++i) av[i] = pv ? __ldg(pp + (size_t)(wq + WT_NPW * i) * FO) : 0.f;
 #pragma unroll
             for (int i = 0; i < C::NC; ++i) {
-                const int ci = wq + WT_NPW * i;
+                const int cq = wq + WT_NPW * i;
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt) {
                     const bool fv = pv && (t - (KT - 1) + kt >= 0);          // the frame of this time tap exists
-                    const float* xp = x + ((size_t)(g - (KT - 1) + kt) * CIN + ci) * C::FIN + SF * fo;
-                    if (SF == 2) {
+                    const float* xp = tp + ((size_t)(g - (KT - 1) + kt) * CQ + cq) * C::FQ + TS * fo;
+                    if (TS == 2) {
                         const float2 v = fv ? __ldg(reinterpret_cast<const float2*>(xp)) : make_float2(0.f, 0.f);
-                        xv[i][kt][0] = v.x; xv[i][kt][SF == 2 ? 1 : 0] = v.y;
-                        xe[i][kt][0] = (fv && lane == 0 && fo > 0) ? __ldg(xp - 1) : 0.f;
-                        xe[i][kt][1] = 0.f;
+                        xv[i][kt][0] = v.x; xv[i][kt][TS - 1] = v.y;
+                        xe[i][kt][0] = (MODE == 0 && fv && lane == 0 && fo > 0) ? __ldg(xp - 1) : 0.f;
+                        xe[i][kt][1] = (MODE == 1 && fv && lane == 31 && fo < FO - 1) ? __ldg(xp + 2) : 0.f;
                     } else {
                         xv[i][kt][0] = fv ? __ldg(xp) : 0.f;
                         xe[i][kt][0] = (fv && lane == 0 && fo > 0) ? __ldg(xp - 1) : 0.f;
@@ -145,16 +154,21 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
                 *reinterpret_cast<uint32_t*>(sA + row_off(wq + WT_NPW * i, lane)) = to_tf32_bits(av[i]);
 #pragma unroll
             for (int i = 0; i < C::NC; ++i) {
-                const int ci = wq + WT_NPW * i;
+                const int cq = wq + WT_NPW * i;
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt) {
-                    float t0, t1, t2;                                         // taps kf = 0, 1, 2
-                    if (SF == 2) {                                            // bins 2fo-1, 2fo, 2fo+1
-                        float l = __shfl_up_sync(0xffffffffu, xv[i][kt][SF == 2 ? 1 : 0], 1);
+                    float t0, t1, t2;                                         // taps 0, 1, 2
+                    if (MODE == 1) {                                          // convT: dz bins 2i, 2i+1, 2i+2 (the last one cropped)
+                        float r = __shfl_down_sync(0xffffffffu, xv[i][kt][0], 1);
+                        if (lane == 31) r = xe[i][kt][1];
+                        if (fo == FO - 1) r = 0.f;
+                        t0 = xv[i][kt][0]; t1 = xv[i][kt][TS - 1]; t2 = r;
+                    } else if (TS == 2) {                                     // conv stride 2: bins 2fo-1, 2fo, 2fo+1
+                        float l = __shfl_up_sync(0xffffffffu, xv[i][kt][TS - 1], 1);
                         if (lane == 0) l = xe[i][kt][0];
                         if (fo == 0) l = 0.f;
-                        t0 = l; t1 = xv[i][kt][0]; t2 = xv[i][kt][SF == 2 ? 1 : 0];
-                    } else {                                                  // bins fo-1, fo, fo+1
+                        t0 = l; t1 = xv[i][kt][0]; t2 = xv[i][kt][TS - 1];
+                    } else {                                                  // conv stride 1: bins fo-1, fo, fo+1
                         float l = __shfl_up_sync(0xffffffffu, xv[i][kt][0], 1);
                         float r = __shfl_down_sync(0xffffffffu, xv[i][kt][0], 1);
                         if (lane == 0) l = xe[i][kt][0];
@@ -163,7 +177,7 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
                         if (fo == FO - 1) r = 0.f;
                         t0 = l; t1 = xv[i][kt][0]; t2 = r;
                     }
-                    const int n0 = (ci * KT + kt) * 3;
+                    const int n0 = (cq * KT + kt) * 3;
                     *reinterpret_cast<uint32_t*>(sB + row_off(n0 + 0, lane)) = to_tf32_bits(t0);
                     *reinterpret_cast<uint32_t*>(sB + row_off(n0 + 1, lane)) = to_tf32_bits(t1);
                     *reinterpret_cast<uint32_t*>(sB + row_off(n0 + 2, lane)) = to_tf32_bits(t2);
@@ -182,7 +196,6 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
             tc::mbar_arrive(&full[s]);
             if (j + WT_SETS < my_nkb) load_kb(j + WT_SETS);
         }
-        (void)pv_cur;
     } else {
         // ================= MMA issuer =================
         constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, 128, C::N);
@@ -207,6 +220,8 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
     if (warp < 4) {
         float* o = ws + (size_t)blockIdx.x * pitch;
         const int co = warp * 32 + lane;
+        if (MODE == 1 && tid < CQ) o[(size_t)CP * C::NW + tid] = 0.f;     // bias partial is accumulated from two columns below
+        if (MODE == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
         if (my_nkb > 0) {
             tc::mbar_wait(acc_full, 0);
             tc::tc_fence_after();
@@ -227,12 +242,26 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
 #pragma unroll
                 for (int q = 0; q < 16; ++q) v[q] = 0.f;
             }
-            if (co < COUT) {
+            if (MODE == 0) {
+                if (co < CP) {                                   // lane = co; columns = (ci,kt,kf) | bias
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int n = c0 + q;
-                    if (n < C::NW) o[(size_t)co * C::NW + n] = v[q];
-                    else if (n == C::NWP) o[(size_t)COUT * C::NW + co] = v[q];
+                    for (int q = 0; q < 16; ++q) {
+                        const int n = c0 + q;
+                        if (n < C::NW) o[(size_t)co * C::NW + n] = v[q];
+                        else if (n == C::NWP) o[(size_t)CP * C::NW + co] = v[q];
+                    }
+                }
+            } else {
+                if (co < CP) {                                   // lane = ci; columns = (co,k)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (c0 + q < C::NW) o[(size_t)co * C::NW + c0 + q] = v[q];
+                } else if (co == CP) {                           // the lane of ones: sum_p dz[co, 2i+k]  ->  dbias = k=0 + k=1
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int n = c0 + q;
+                        if (n < C::NW && (n % 3) != 2) atomicAdd(o + (size_t)CP * C::NW + n / 3, v[q]);
+                    }
                 }
             }
         }
@@ -242,10 +271,10 @@ conv_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dz, 
     if (warp == WT_MMA_WARP) tc::tmem_dealloc<WT_TMEM_COLS>(tmem_d);
 }
 
-template <int KT, int SF, int CIN, int COUT, int FO>
-int launch_wgrad_tc(const float* x, const float* dz, float* ws, int B, int T, int pitch, int max_grid, cudaStream_t st) {
-    using C = WgradCfg<KT, SF, CIN, COUT, FO>;
-    auto kern = conv_wgrad_tc_kernel<KT, SF, CIN, COUT, FO>;
+template <int MODE, int KT, int SF, int CP, int CQ, int FO>
+int launch_wgrad_tc(const float* pl, const float* tp, float* ws, int B, int T, int pitch, int max_grid, cudaStream_t st) {
+    using C = WgradCfg<MODE, KT, SF, CP, CQ, FO>;
+    auto kern = conv_wgrad_tc_kernel<MODE, KT, SF, CP, CQ, FO>;
     static bool attr_set = false;
     if (!attr_set) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -255,7 +284,7 @@ int launch_wgrad_tc(const float* x, const float* dz, float* ws, int B, int T, in
     int grid = sm_count();
     if (grid > max_grid) grid = max_grid;
     if ((long long)grid > nkb) grid = (int)nkb;
-    kern<<<grid, WT_THREADS, C::SMEM, st>>>(x, dz, ws, B, T, pitch);
+    kern<<<grid, WT_THREADS, C::SMEM, st>>>(pl, tp, ws, B, T, pitch);
     CRUSE_LAUNCH_OK();
     return grid;
 }
@@ -269,7 +298,7 @@ int conv_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, 
     if ((reinterpret_cast<uintptr_t>(x) & 7) != 0) return 0;
 #define CRUSE_WT(KT_, SF_, CI_, CO_, FO_) \
     if (kt == KT_ && fstride == SF_ && Cin == CI_ && Cout == CO_ && Fout == FO_ && Fin == SF_ * FO_) \
-        return launch_wgrad_tc<KT_, SF_, CI_, CO_, FO_>(x, dz, ws, B, T, pitch, max_grid, st);
+        return launch_wgrad_tc<0, KT_, SF_, CO_, CI_, FO_>(dz, x, ws, B, T, pitch, max_grid, st);
     CRUSE_WT(2, 2, 8, 16, 64)
     CRUSE_WT(2, 2, 16, 32, 32)
     CRUSE_WT(2, 2, 32, 64, 16)
@@ -278,6 +307,20 @@ int conv_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, 
     CRUSE_WT(1, 1, 32, 32, 32)
     CRUSE_WT(1, 1, 64, 64, 16)
 #undef CRUSE_WT
+    return 0;
+}
+
+// the same for the transposed conv (partial layout [Cin x Cout*3 weights | Cout bias sums])
+int convT_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int pitch,
+                       int max_grid, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(dz) & 7) != 0) return 0;
+#define CRUSE_WTT(CI_, CO_, FI_) \
+    if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) \
+        return launch_wgrad_tc<1, 1, 2, CI_, CO_, FI_>(x, dz, ws, B, T, pitch, max_grid, st);
+    CRUSE_WTT(64, 32, 16)
+    CRUSE_WTT(32, 16, 32)
+    CRUSE_WTT(16, 8, 64)
+#undef CRUSE_WTT
     return 0;
 }
 

@@ -62,6 +62,27 @@ def test_conv_weight_gradient_on_tensor_cores(cuda, kind, cin, cout, F, B, T):
     assert rel_err(dw32, conv.weight.grad) <= 1e-4 and not torch.equal(dw32, dw)
 
 
+@pytest.mark.parametrize("cin,cout,Fin", [(64, 32, 16), (32, 16, 32), (16, 8, 64)])
+@pytest.mark.parametrize("B,T", [(3, 11), (2, 64)])
+def test_convT_weight_gradient_on_tensor_cores(cuda, cin, cout, Fin, B, T):
+    """the decoder's transposed-conv weight / bias gradients on the same split-K tcgen05 kernel (MODE 1); tolerance 2e-3."""
+    from cruse_b200 import ops
+    torch.manual_seed(32)
+    ops.set_conv_mode("tf32")
+    conv = nn.ConvTranspose2d(cin, cout, (1, 3), (1, 2))
+    x = torch.randn(B, cin, T, Fin, requires_grad=True)
+    z = conv(x)[..., :2 * Fin]
+    gz = torch.randn_like(z)
+    z.backward(gz)
+    dw, db = ops.convT_wgrad(_to_frames(x.detach()).to(cuda), _to_frames(gz).to(cuda))
+    assert rel_err(dw, conv.weight.grad) <= 2e-3
+    assert rel_err(db, conv.bias.grad) <= 2e-3
+    ops.set_conv_mode("fp32")
+    dw32, _ = ops.convT_wgrad(_to_frames(x.detach()).to(cuda), _to_frames(gz).to(cuda))
+    ops.set_conv_mode("tf32")
+    assert rel_err(dw32, conv.weight.grad) <= 1e-4 and not torch.equal(dw32, dw)
+
+
 @pytest.mark.parametrize("cin,cout,F,act", [(1, 8, 256, "relu"), (8, 16, 128, "prelu"), (16, 32, 64, "relu"), (32, 64, 32, "prelu"),
                                            (8, 16, 81, "relu"), (3, 5, 21, "prelu")])
 def test_encoder_stage_backward(cuda, exact_conv, cin, cout, F, act):

@@ -110,9 +110,7 @@ class _Unet2Fn(torch.autograd.Function):
             h = ops.bn_act_fwd(z, scale, shift, alpha, act)
             enc_z.append(z)
             enc_bn.append((scale, shift, mean, invstd))
-            # exact-fp32 skip convs in the differentiable forward: the data / weight gradients are exact-fp32 kernels,
-            # and the tf32 tensor-core instantiations are an inference (eval, no-grad) fast path
-            skips.append(ops.conv_fwd(h, getattr(m, f"skip_connect_{k}").weight, None, None, None, None, "none", 1, 1, exact=True))
+            skips.append(ops.conv_fwd(h, getattr(m, f"skip_connect_{k}").weight, None, None, None, None, "none", 1, 1))
         e4 = h
         C4, F4 = e4.shape[2], e4.shape[3]
         D = C4 * F4

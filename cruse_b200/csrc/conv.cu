@@ -322,6 +322,33 @@ convT_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, cons
     }
 }
 
+// Per-channel sum / sum of squares of a stage output z [B,T,C,F] (pre-BatchNorm) in the per-chunk partial layout the conv
+// kernels emit ([nparts][2*C], one partial per 8 frames of one utterance): used when the conv itself ran on the tensor
+// cores (conv_tc.cu has no statistics epilogue).  One warp owns a channel, lanes stride over its 8 x F values, the warp
+// shuffle reduction has a fixed order -> deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ z, float* __restrict__ stats_ws, int T, int C, int F) {
+    const int chunks = (T + CONV_TT - 1) / CONV_TT;
+    const int b = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * CONV_TT;
+    const int nfr = (T - t0) < CONV_TT ? (T - t0) : CONV_TT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float* zb = z + ((size_t)b * T + t0) * C * F;
+    float* so = stats_ws + (size_t)blockIdx.x * 2 * C;
+    const int per_fr4 = F >> 2;                                  // float4 per (frame, channel) row; F % 4 == 0
+    for (int c = warp; c < C; c += nwarps) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = lane; i < nfr * per_fr4; i += 32) {
+            const int fr = i / per_fr4, q = i - fr * per_fr4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(zb + ((size_t)fr * C + c) * F) + q);
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) { so[c] = s1; so[C + c] = s2; }
+    }
+}
+
 // one block per channel: reduce per-CTA partials in double
 __global__ void bn_finalize_kernel(const float* __restrict__ stats_ws, int nparts, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -424,6 +451,16 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
     CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd: scale and shift go together");
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd: PReLU needs alpha");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!hist && stats_ws && (Fout & 3) == 0 && !scale && act == CRUSE_ACT_NONE) {
+        // train-mode stage: the conv (+ bias) on the tensor cores, then one pass over z for the BatchNorm partial sums
+        const int rc = conv_tc_try(in, w, bias, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            bn_stats_kernel<<<cruse_conv_nparts(B, T), 256, 0, st>>>(out, stats_ws, T, Cout, Fout);
+            CRUSE_LAUNCH_OK();
+            return 0;
+        }
+    }
     if (!hist && !stats_ws) {     // eval-mode stage of the 256-bin pyramid: tcgen05 implicit GEMM (conv_tc.cu)
         int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
         if (rc) return rc < 0 ? rc : 0;
@@ -467,6 +504,15 @@ extern "C" int cruse_convT_fwd(const float* in, const float* w, const float* bia
     CRUSE_CHECK_ARG(Fout > 0 && Fout <= 2 * Fin + 1, "convT_fwd: Fout=%d must be in (0, 2*Fin+1=%d]", Fout, 2 * Fin + 1);
     CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "convT_fwd: scale and shift go together");
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "convT_fwd: PReLU needs alpha");
+    if (stats_ws && (Fout & 3) == 0 && !scale && act == CRUSE_ACT_NONE && !skip) {
+        const int rc = convT_tc_try(in, w, bias, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, nullptr, out, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            bn_stats_kernel<<<cruse_conv_nparts(B, T), 256, 0, (cudaStream_t)stream>>>(out, stats_ws, T, Cout, Fout);
+            CRUSE_LAUNCH_OK();
+            return 0;
+        }
+    }
     if (!stats_ws) {
         int rc = convT_tc_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
         if (rc) return rc < 0 ? rc : 0;

@@ -94,20 +94,29 @@ def test_forward_matches_oracle_eval_and_module_surface(cuda, F, n_fft, hop, B, 
     assert all(e <= tol for e in errs[:5]) and errs[5] < 1e-4
 
 
-def test_forward_train_mode_batchnorm(cuda):
-    """train-mode forward uses batch statistics and updates running stats like nn.BatchNorm2d."""
+@pytest.mark.parametrize("conv_mode,tol_stats", [("fp32", 1e-4), ("tf32", 2e-3)])
+def test_forward_train_mode_batchnorm(cuda, conv_mode, tol_stats):
+    """train-mode forward uses batch statistics and updates running stats like nn.BatchNorm2d.  In tf32 conv mode the conv
+    stages run on the tensor cores also here (the BatchNorm partial sums then come from one extra pass over z) and the
+    statistics carry the tf32 operand rounding: stated gate 2e-3."""
+    from cruse_b200 import ops
     from oracle import cruse_oracle as o
-    ours, ref = _pair(256, "prelu", cuda, eval_stats=False)
-    ours.train(); ref.train()
-    torch.manual_seed(11)
-    x = torch.rand(3, 1, 21, 256)
-    with torch.no_grad():
-        want = ref(x)
-        got = ours(x.to(cuda))
+    old = ops.get_conv_mode()
+    ops.set_conv_mode(conv_mode)
+    try:
+        ours, ref = _pair(256, "prelu", cuda, eval_stats=False)
+        ours.train(); ref.train()
+        torch.manual_seed(11)
+        x = torch.rand(3, 1, 21, 256)
+        with torch.no_grad():
+            want = ref(x)
+            got = ours(x.to(cuda))
+    finally:
+        ops.set_conv_mode(old)
     assert rel_err(got, want) <= 1e-3
     for k in ("bn1", "bn4", "bn3_t"):
-        assert rel_err(getattr(ours, k).running_mean, getattr(ref, k).running_mean) <= 1e-4
-        assert rel_err(getattr(ours, k).running_var, getattr(ref, k).running_var) <= 1e-4
+        assert rel_err(getattr(ours, k).running_mean, getattr(ref, k).running_mean) <= tol_stats
+        assert rel_err(getattr(ours, k).running_var, getattr(ref, k).running_var) <= tol_stats
 
 
 def test_streaming_matches_batched(cuda):

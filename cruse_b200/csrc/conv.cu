@@ -20,7 +20,7 @@ namespace cruse {
 // conv_tc.cu: tensor-core (tcgen05) implicit-GEMM instantiations for the 256-bin pyramid in eval mode
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                int in_tm, int out_tm, cudaStream_t st);
+                int in_tm, int out_tm, int wmode, cudaStream_t st);
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
 
@@ -453,7 +453,7 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
     cudaStream_t st = (cudaStream_t)stream;
     if (!hist && stats_ws && (Fout & 3) == 0 && !scale && act == CRUSE_ACT_NONE) {
         // train-mode stage: the conv (+ bias) on the tensor cores, then one pass over z for the BatchNorm partial sums
-        const int rc = conv_tc_try(in, w, bias, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
+        const int rc = conv_tc_try(in, w, bias, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, 0, st);
         if (rc < 0) return rc;
         if (rc == 1) {
             bn_stats_kernel<<<cruse_conv_nparts(B, T), 256, 0, st>>>(out, stats_ws, T, Cout, Fout);
@@ -462,7 +462,7 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
         }
     }
     if (!hist && !stats_ws) {     // eval-mode stage of the 256-bin pyramid: tcgen05 implicit GEMM (conv_tc.cu)
-        int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, st);
+        int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, 0, st);
         if (rc) return rc < 0 ? rc : 0;
         rc = conv_edge_try(in, w, bias, scale, shift, alpha, act, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st);
         if (rc) { if (rc < 0) set_error("conv_fwd: streaming stage-1 kernel launch failed"); return rc < 0 ? rc : 0; }
@@ -489,7 +489,7 @@ extern "C" int cruse_conv_fwd_tm(const float* in, const float* w, const float* b
     CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd_tm: scale and shift go together");
     CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd_tm: PReLU needs alpha");
     const int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride,
-                               in_time_major ? 1 : 0, out_time_major ? 1 : 0, (cudaStream_t)stream);
+                               in_time_major ? 1 : 0, out_time_major ? 1 : 0, 0, (cudaStream_t)stream);
     if (rc < 0) return rc;
     CRUSE_CHECK_ARG(rc == 1, "conv_fwd_tm: no tensor-core instantiation for kt=%d fstride=%d Cin=%d Cout=%d Fin=%d (or conv mode is fp32)", kt,
                     fstride, Cin, Cout, Fin);
@@ -541,6 +541,10 @@ extern "C" int cruse_conv_dgrad(const float* dz, const float* w, const float* ad
     cudaStream_t st = (cudaStream_t)stream;
     if (kt == 1) {
         // din[ci,f] = sum_co sum_kf W[co,ci,0,kf] dz[co,f+1-kf]: a (1,3) conv over dz with flipped taps, channels swapped
+        {   // tf32 mode: the same implicit GEMM as the forward skip conv (conv_tc.cu), weights read transposed + flipped
+            const int rc = conv_tc_try(dz, w, nullptr, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, addend, din, B, T, Cout, Fout, Cin, Fin, 1, 1, 0, 0, 1, st);
+            if (rc) return rc < 0 ? rc : 0;
+        }
         const size_t smem = conv_smem_bytes(1, Cout, Fout, Cin);
         CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_dgrad: stage needs %zu B shared memory", smem);
         CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -61,6 +61,8 @@ struct ConvTcArgs {
     float* out;
     int B, T, act;
     int in_tm, out_tm;      // frame records of in / out are ordered time-major (t*B + b) instead of (b*T + t)
+    int wmode;              // 0: w is this conv's weight; 1 (KT == 1 conv only): data gradient of a (1,3)/stride-1 conv --
+                            //    w is THAT conv's weight [Cin_here][Cout_here][1][3], taps flipped
 };
 
 // MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
@@ -159,7 +161,8 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 if (i < WTOT && k < C::KG && n < C::N) {
                     const int tap = k / C::CB, ci = g * C::CB + (k - tap * C::CB);
                     if (MODE == 0) {
-                        v = __ldg(a.w + (((size_t)n * CIN + ci) * KT + kt) * 3 + tap);                 // Conv2d [Cout][Cin][KT][3]
+                        v = a.wmode == 1 ? __ldg(a.w + ((size_t)ci * COUT + n) * 3 + (2 - tap))        // dgrad: [Cin][Cout][1][3], flipped
+                                         : __ldg(a.w + (((size_t)n * CIN + ci) * KT + kt) * 3 + tap);  // Conv2d [Cout][Cin][KT][3]
                     } else {
                         const int co = n >> 1, ph = n & 1;                                            // ConvTranspose2d [Cin][Cout][1][3]
                         // out[2i] = W[..,0] x[i] + W[..,2] x[i-1];  out[2i+1] = W[..,1] x[i]
@@ -459,10 +462,11 @@ bool conv_tc_enabled() { return conv_mode() == 1; }
 // runs the CUDA-core kernel), < 0 on error.
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                int in_tm, int out_tm, cudaStream_t st) {
+                int in_tm, int out_tm, int wmode, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
+    if (wmode != 0 && !(wmode == 1 && kt == 1 && fstride == 1)) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, wmode};
     int rc = 0;
     // last argument: MMA tiles (128 rows) per pipeline step; stages with long frames (FO >= 32) batch several of them
 #define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_, NS_)                                                    \
@@ -485,7 +489,7 @@ int convT_tc_try(const float* in, const float* w, const float* bias, const float
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, 0};
     int rc = 0;
 #define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_, NS_)                                      \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \

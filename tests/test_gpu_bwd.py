@@ -62,6 +62,23 @@ def test_conv_weight_gradient_on_tensor_cores(cuda, kind, cin, cout, F, B, T):
     assert rel_err(dw32, conv.weight.grad) <= 1e-4 and not torch.equal(dw32, dw)
 
 
+@pytest.mark.parametrize("c,F", [(8, 128), (16, 64), (32, 32), (64, 16)])
+def test_skip_conv_data_gradient_on_tensor_cores(cuda, c, F):
+    """data gradient of the (1,3) skip convs = the same tcgen05 implicit GEMM with the weights read transposed and
+    flipped (conv_tc.cu wmode 1), + the accumulate-into input; tolerance 1e-3."""
+    from cruse_b200 import ops
+    torch.manual_seed(33)
+    ops.set_conv_mode("tf32")
+    conv = nn.Conv2d(c, c, (1, 3), bias=False, padding=(0, 1))
+    x = torch.randn(2, c, 19, F, requires_grad=True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    add = torch.randn(2, 19, c, F).to(cuda)
+    got = ops.conv_dgrad(_to_frames(gy).to(cuda), conv.weight.detach().to(cuda), (2, 19, c, F), 1, 1, addend=add)
+    assert rel_err(got, _to_frames(x.grad).to(cuda) + add) <= 1e-3
+
+
 @pytest.mark.parametrize("cin,cout,Fin", [(64, 32, 16), (32, 16, 32), (16, 8, 64)])
 @pytest.mark.parametrize("B,T", [(3, 11), (2, 64)])
 def test_convT_weight_gradient_on_tensor_cores(cuda, cin, cout, Fin, B, T):

@@ -23,6 +23,8 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
                 int in_tm, int out_tm, int wmode, cudaStream_t st);
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
+int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
+                       int Fout, cudaStream_t st);
 
 // conv_edge.cu: streaming kernels for the single-channel stages (Cin == 1 / Cout == 1), eval mode
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
@@ -569,6 +571,10 @@ extern "C" int cruse_convT_dgrad(const float* dz, const float* w, const float* a
     CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "convT_dgrad: bad sizes");
     CRUSE_CHECK_ARG(Fout > 0 && Fout <= 2 * Fin + 1 && Fout >= 2 * Fin - 1, "convT_dgrad: Fout=%d must be within [2*Fin-1, 2*Fin+1] (Fin=%d)", Fout, Fin);
     // din[ci,i] = sum_co sum_k W[ci,co,0,k] dz[co,2i+k]: a stride-2 conv over dz without left padding
+    {
+        const int rc = convT_dgrad_tc_try(dz, w, addend, din, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        if (rc) return rc < 0 ? rc : 0;
+    }
     const size_t smem = conv_smem_bytes(1, Cout, Fout, Cin);
     CRUSE_CHECK_ARG(smem <= 227 * 1024, "convT_dgrad: stage needs %zu B shared memory", smem);
     CRUSE_CUDA_OK(cudaFuncSetAttribute(conv_fwd_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -66,11 +66,13 @@ struct ConvTcArgs {
 };
 
 // MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
-// to 2*FO bins (FO = input bins).
+// to 2*FO bins (FO = input bins).  MODE 3: conv 1 x 3, stride 2, NO left pad (taps at bins 2fo, 2fo+1, 2fo+2, the last one
+// cropped at the right edge) = the data gradient of the transposed conv.
 template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
 struct ConvTcCfg {
-    static constexpr int TAPS = MODE == 0 ? 3 : 2;                 // conv: kf = 0,1,2; convT: {x[i], x[i-1]}
-    static constexpr int N = MODE == 0 ? COUT : 2 * COUT;
+    static constexpr bool CONVLIKE = MODE == 0 || MODE == 3;
+    static constexpr int TAPS = CONVLIKE ? 3 : 2;                  // conv: kf = 0,1,2; convT: {x[i], x[i-1]}
+    static constexpr int N = CONVLIKE ? COUT : 2 * COUT;
     static constexpr int NPAD = N < 16 ? 16 : N;                   // UMMA M=128 needs N % 16 == 0
     static constexpr int TF = GM * (128 / FO);                     // frames per tile = GM MMA tiles of 128 rows: short-frame
                                                                    // stages (FO >= 32) batch several so that the per-tile
@@ -85,7 +87,7 @@ struct ConvTcCfg {
     static constexpr int GROUP_BYTES = S * SLOT_BYTES;
     static constexpr int NKB = NG * S * KT;                        // weight K blocks
     static constexpr int B_BYTES = NKB * NPAD * 128;
-    static constexpr int FIN = MODE == 0 ? SF * FO : FO;
+    static constexpr int FIN = CONVLIKE ? SF * FO : FO;
     static constexpr int RD_FIT = (CT_SMEM_BUDGET - B_BYTES) / GROUP_BYTES;
     static constexpr int RD = RD_FIT > 4 ? 4 : RD_FIT;             // ring depth (groups)
     static constexpr int ITEMS = NFR * (CB / 4) * (FO / 16);       // (frame, 4 channels, 16 rows) patches per group
@@ -99,7 +101,7 @@ struct ConvTcCfg {
     static_assert(RD >= 2, "ring needs two groups");
     static_assert(NPAD % 16 == 0 && NPAD <= 64 && 2 * ACC_COLS <= 256, "N tile");
     static_assert(NIT <= 9, "producer register budget: at most 9 patches per warp and group");
-    static_assert(MODE == 0 || (KT == 1 && SF == 1), "convT instantiation");
+    static_assert(MODE == 0 || (MODE == 1 && KT == 1 && SF == 1) || (MODE == 3 && KT == 1 && SF == 2), "instantiation");
 };
 
 __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 float v = 0.f;
                 if (i < WTOT && k < C::KG && n < C::N) {
                     const int tap = k / C::CB, ci = g * C::CB + (k - tap * C::CB);
-                    if (MODE == 0) {
+                    if (C::CONVLIKE) {
                         v = a.wmode == 1 ? __ldg(a.w + ((size_t)ci * COUT + n) * 3 + (2 - tap))        // dgrad: [Cin][Cout][1][3], flipped
                                          : __ldg(a.w + (((size_t)n * CIN + ci) * KT + kt) * 3 + tap);  // Conv2d [Cout][Cin][KT][3]
                     } else {
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
         // Software pipeline over this set's groups (j = set, set+2, ...): the registers of a group are split in two halves;
         // while half 0 of group j is being converted and stored, the loads of half 0 of the set's NEXT group are already
         // in flight (and likewise for half 1), so HBM requests are outstanding during the whole store phase.
-        constexpr int NV = (MODE == 0 && SF == 2) ? 2 : 1;
+        constexpr int NV = (C::CONVLIKE && SF == 2) ? 2 : 1;
         constexpr int NH0 = (C::NIT + 1) / 2;
         float va[C::NIT][NV], vb[C::NIT][NV], ea[C::NIT], eb[C::NIT];     // channel ci0 / ci0+1: values, edge value
         const int ntl = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
@@ -225,12 +227,12 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 const int t = t0 - (KT - 1) + fr;
                 const bool valid = (t >= 0) && (t < T);
                 const int fo = fg * 16 + row16, ci0 = g * C::CB + cg * 4 + 2 * ep;
-                const float* src = a.in + ((a.in_tm ? (size_t)t * a.B + b : (size_t)b * T + t) * CIN + ci0) * C::FIN + (MODE == 0 ? SF : 1) * fo;
+                const float* src = a.in + ((a.in_tm ? (size_t)t * a.B + b : (size_t)b * T + t) * CIN + ci0) * C::FIN + (C::CONVLIKE ? SF : 1) * fo;
 #pragma unroll
                 for (int q = 0; q < NV; ++q) { va[it][q] = 0.f; vb[it][q] = 0.f; }
                 ea[it] = 0.f; eb[it] = 0.f;
                 if (valid) {
-                    if (MODE == 0 && SF == 2) {
+                    if (C::CONVLIKE && SF == 2) {
                         const float2 p = __ldg(reinterpret_cast<const float2*>(src));
                         const float2 q = __ldg(reinterpret_cast<const float2*>(src + C::FIN));
                         va[it][0] = p.x; va[it][NV - 1] = p.y; vb[it][0] = q.x; vb[it][NV - 1] = q.y;
@@ -238,7 +240,8 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                         va[it][0] = __ldg(src);
                         vb[it][0] = __ldg(src + C::FIN);
                     }
-                    if (row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
+                    if (MODE != 3 && row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
+                    if (MODE == 3 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 2); eb[it] = __ldg(src + C::FIN + 2); }
                     if (MODE == 0 && SF == 1 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
                 }
             }
@@ -251,7 +254,12 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
                 const int row = fr * FO + fg * 16 + row16;
                 float ta[3], tb[3];
-                if (MODE == 0 && SF == 2) {          // taps read bins 2fo-1, 2fo, 2fo+1
+                if (MODE == 3) {                     // taps read bins 2fo, 2fo+1, 2fo+2 (cropped)
+                    float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
+                    if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
+                    ta[0] = va[it][0]; ta[1] = va[it][NV - 1]; ta[2] = ra;
+                    tb[0] = vb[it][0]; tb[1] = vb[it][NV - 1]; tb[2] = rb;
+                } else if (MODE == 0 && SF == 2) {   // taps read bins 2fo-1, 2fo, 2fo+1
                     float la = __shfl_up_sync(0xffffffffu, va[it][NV - 1], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][NV - 1], 2);
                     if (row16 == 0) { la = ea[it]; lb = eb[it]; }
                     ta[0] = la; ta[1] = va[it][0]; ta[2] = va[it][NV - 1];
@@ -383,7 +391,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                     const int t = t0 + tl;
                     if (t >= T) continue;
                     const size_t rec = a.out_tm ? (size_t)t * a.B + b : (size_t)b * T + t;
-                    if (MODE == 0) {
+                    if (C::CONVLIKE) {
                         const size_t o0 = rec * COUT * FO + fo;
                         float ad[16];
 #pragma unroll
@@ -482,6 +490,26 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
     CRUSE_CT_CONV(1, 1, 32, 32, 32, 1, 2)
     CRUSE_CT_CONV(1, 1, 64, 64, 16, 1, 2)
 #undef CRUSE_CT_CONV
+    return 0;
+}
+
+// data gradient of the transposed conv: din[ci, i] = sum_co sum_k W[ci,co,0,k] dz[co, 2i+k] -- a (1,3)/stride-2 conv over dz
+// without left pad; w is the ConvTranspose2d weight [Cin][Cout][1][3], which is exactly the [out][in][1][3] this conv reads
+int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
+                       int Fout, cudaStream_t st) {
+    if (!conv_tc_enabled()) return 0;
+    if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, 0};
+    int rc = 0;
+#define CRUSE_CT_TD(CO_, CI_, FI_, NS_)                                              \
+    if (Cout == CO_ && Cin == CI_ && Fin == FI_ && Fout == 2 * FI_) {                \
+        rc = launch_conv_tc<3, 1, 2, CO_, CI_, FI_, 1, NS_>(a, st);                  \
+        return rc ? rc : 1;                                                          \
+    }
+    CRUSE_CT_TD(8, 16, 64, 2)
+    CRUSE_CT_TD(16, 32, 32, 2)
+    CRUSE_CT_TD(32, 64, 16, 1)
+#undef CRUSE_CT_TD
     return 0;
 }
 

@@ -80,6 +80,22 @@ def test_skip_conv_data_gradient_on_tensor_cores(cuda, c, F):
 
 
 @pytest.mark.parametrize("cin,cout,Fin", [(64, 32, 16), (32, 16, 32), (16, 8, 64)])
+def test_convT_data_gradient_on_tensor_cores(cuda, cin, cout, Fin):
+    """data gradient of the decoder's transposed convs = a (1,3)/stride-2 conv over dz without left pad on the tcgen05
+    implicit-GEMM kernel (conv_tc.cu MODE 3); tolerance 1e-3."""
+    from cruse_b200 import ops
+    torch.manual_seed(34)
+    ops.set_conv_mode("tf32")
+    conv = nn.ConvTranspose2d(cin, cout, (1, 3), (1, 2))
+    x = torch.randn(2, cin, 19, Fin, requires_grad=True)
+    z = conv(x)[..., :2 * Fin]
+    gz = torch.randn_like(z)
+    z.backward(gz)
+    got = ops.convT_dgrad(_to_frames(gz).to(cuda), conv.weight.detach().to(cuda), (2, 19, cin, Fin))
+    assert rel_err(got, _to_frames(x.grad)) <= 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,Fin", [(64, 32, 16), (32, 16, 32), (16, 8, 64)])
 @pytest.mark.parametrize("B,T", [(3, 11), (2, 64)])
 def test_convT_weight_gradient_on_tensor_cores(cuda, cin, cout, Fin, B, T):
     """the decoder's transposed-conv weight / bias gradients on the same split-K tcgen05 kernel (MODE 1); tolerance 2e-3."""

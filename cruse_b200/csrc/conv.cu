@@ -23,6 +23,8 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
                 int in_tm, int out_tm, int wmode, cudaStream_t st);
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
+int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
+                      int Fout, int kt, cudaStream_t st);
 int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
                        int Fout, cudaStream_t st);
 
@@ -554,6 +556,10 @@ extern "C" int cruse_conv_dgrad(const float* dz, const float* w, const float* ad
                                                                 nullptr, T, Cout, Fout, Cin, Fin, 1, 1);
     } else {
         // transposed conv with two time taps (frame t and t+1) over dz, output shifted by the conv's left pad
+        {
+            const int rc = conv_dgrad_tc_try(dz, w, addend, din, B, T, Cin, Fin, Cout, Fout, kt, st);
+            if (rc) return rc < 0 ? rc : 0;
+        }
         const int CoutP = (Cin + CONV_COT - 1) / CONV_COT * CONV_COT;
         const size_t smem = sizeof(float) * ((((size_t)(CONV_TT + 1) * Cout * (Fout + 2) + 3) & ~(size_t)3) + (size_t)Cout * 6 * CoutP + 2 * (size_t)Cin);
         CRUSE_CHECK_ARG(smem <= 227 * 1024, "conv_dgrad: stage needs %zu B shared memory", smem);

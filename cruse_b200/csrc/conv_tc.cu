@@ -67,7 +67,9 @@ struct ConvTcArgs {
 
 // MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
 // to 2*FO bins (FO = input bins).  MODE 3: conv 1 x 3, stride 2, NO left pad (taps at bins 2fo, 2fo+1, 2fo+2, the last one
-// cropped at the right edge) = the data gradient of the transposed conv.
+// cropped at the right edge) = the data gradient of the transposed conv.  MODE 2: the data gradient of the KT x 3 / stride-2
+// conv: a transposed conv over dz (FO = dz bins, output 2*FO bins) whose frequency taps are {dz[i], dz[i+1]} and whose time taps
+// look FORWARD (frame t and t+1); CIN = channels of dz (the conv's Cout), COUT = channels of the gradient (the conv's Cin).
 template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
 struct ConvTcCfg {
     static constexpr bool CONVLIKE = MODE == 0 || MODE == 3;
@@ -100,8 +102,8 @@ struct ConvTcCfg {
     static_assert(ITEMS % CT_NPW == 0, "producer items must split evenly over the warps of a set");
     static_assert(RD >= 2, "ring needs two groups");
     static_assert(NPAD % 16 == 0 && NPAD <= 64 && 2 * ACC_COLS <= 256, "N tile");
-    static_assert(NIT <= 9, "producer register budget: at most 9 patches per warp and group");
-    static_assert(MODE == 0 || (MODE == 1 && KT == 1 && SF == 1) || (MODE == 3 && KT == 1 && SF == 2), "instantiation");
+    static_assert(NIT <= (MODE == 2 ? 10 : 9), "producer register budget: at most 9 patches per warp and group (10 with one value per patch)");
+    static_assert(MODE == 0 || (MODE == 1 && KT == 1 && SF == 1) || (MODE == 3 && KT == 1 && SF == 2) || (MODE == 2 && SF == 1), "instantiation");
 };
 
 __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
@@ -165,6 +167,12 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                     if (C::CONVLIKE) {
                         v = a.wmode == 1 ? __ldg(a.w + ((size_t)ci * COUT + n) * 3 + (2 - tap))        // dgrad: [Cin][Cout][1][3], flipped
                                          : __ldg(a.w + (((size_t)n * CIN + ci) * KT + kt) * 3 + tap);  // Conv2d [Cout][Cin][KT][3]
+                    } else if (MODE == 2) {
+                        const int co = n >> 1, ph = n & 1;                                            // Conv2d [CIN][COUT][KT][3] (out, in)
+                        // dx[2i] = W[..,1] dz[i];  dx[2i+1] = W[..,2] dz[i] + W[..,0] dz[i+1]
+                        const float* wp = a.w + (((size_t)ci * COUT + co) * KT + kt) * 3;
+                        if (tap == 0) v = __ldg(wp + 1 + ph);
+                        else if (ph == 1) v = __ldg(wp);
                     } else {
                         const int co = n >> 1, ph = n & 1;                                            // ConvTranspose2d [Cin][Cout][1][3]
                         // out[2i] = W[..,0] x[i] + W[..,2] x[i-1];  out[2i+1] = W[..,1] x[i]
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 if (it < lo || it >= hi) continue;
                 const int item = it * CT_NPW + wq;
                 const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
-                const int t = t0 - (KT - 1) + fr;
+                const int t = MODE == 2 ? t0 + fr : t0 - (KT - 1) + fr;
                 const bool valid = (t >= 0) && (t < T);
                 const int fo = fg * 16 + row16, ci0 = g * C::CB + cg * 4 + 2 * ep;
                 const float* src = a.in + ((a.in_tm ? (size_t)t * a.B + b : (size_t)b * T + t) * CIN + ci0) * C::FIN + (C::CONVLIKE ? SF : 1) * fo;
@@ -240,9 +248,9 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                         va[it][0] = __ldg(src);
                         vb[it][0] = __ldg(src + C::FIN);
                     }
-                    if (MODE != 3 && row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
+                    if ((MODE == 0 || MODE == 1) && row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
                     if (MODE == 3 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 2); eb[it] = __ldg(src + C::FIN + 2); }
-                    if (MODE == 0 && SF == 1 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
+                    if (((MODE == 0 && SF == 1) || MODE == 2) && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
                 }
             }
         };
@@ -271,6 +279,11 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                     if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
                     ta[0] = la; ta[1] = va[it][0]; ta[2] = ra;
                     tb[0] = lb; tb[1] = vb[it][0]; tb[2] = rb;
+                } else if (MODE == 2) {              // conv dgrad: K taps = dz[i], dz[i+1]
+                    float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
+                    if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
+                    ta[0] = va[it][0]; ta[1] = ra; ta[2] = 0.f;
+                    tb[0] = vb[it][0]; tb[1] = rb; tb[2] = 0.f;
                 } else {                             // convT: K taps = x[i], x[i-1]
                     float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
                     if (row16 == 0) { la = ea[it]; lb = eb[it]; }
@@ -333,7 +346,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                             const int ksteps = (kvalid + 7) / 8;
 #pragma unroll
                             for (int kt = 0; kt < KT; ++kt) {
-                                const uint32_t sa = ga + s * C::SLOT_BYTES + (mt * 128 + kt * FO) * 128;
+                                const uint32_t sa = ga + s * C::SLOT_BYTES + (mt * 128 + (MODE == 2 ? KT - 1 - kt : kt) * FO) * 128;
                                 const uint32_t sb = sB_u32 + (uint32_t)(((g * C::S + s) * KT + kt) * (C::NPAD * 128));
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -510,6 +523,25 @@ int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, flo
     CRUSE_CT_TD(16, 32, 32, 2)
     CRUSE_CT_TD(32, 64, 16, 1)
 #undef CRUSE_CT_TD
+    return 0;
+}
+
+// data gradient of the (2,3)/stride-(1,2) encoder conv (MODE 2); w is the Conv2d weight [Cout][Cin][2][3]
+int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
+                      int Fout, int kt, cudaStream_t st) {
+    if (!conv_tc_enabled() || kt != 2) return 0;
+    if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, 0};
+    int rc = 0;
+#define CRUSE_CT_CD(CO_, CI_, FO_, GM_, NS_)                                         \
+    if (Cout == CO_ && Cin == CI_ && Fout == FO_ && Fin == 2 * FO_) {                \
+        rc = launch_conv_tc<2, 2, 1, CO_, CI_, FO_, GM_, NS_>(a, st);                \
+        return rc ? rc : 1;                                                          \
+    }
+    CRUSE_CT_CD(64, 32, 16, 1, 1)
+    CRUSE_CT_CD(32, 16, 32, 1, 2)
+    CRUSE_CT_CD(16, 8, 64, 1, 2)
+#undef CRUSE_CT_CD
     return 0;
 }
 

@@ -79,6 +79,32 @@ def test_skip_conv_data_gradient_on_tensor_cores(cuda, c, F):
     assert rel_err(got, _to_frames(x.grad).to(cuda) + add) <= 1e-3
 
 
+@pytest.mark.parametrize("cin,cout,Fin", [(8, 16, 128), (16, 32, 64), (32, 64, 32)])
+@pytest.mark.parametrize("B,T", [(2, 19), (3, 1), (1, 64)])
+def test_encoder_conv_data_gradient_on_tensor_cores(cuda, cin, cout, Fin, B, T):
+    """data gradient of the encoder's (2,3)/stride-(1,2) causal convs = a transposed conv over dz with forward-looking time
+    taps on the tcgen05 implicit-GEMM kernel (conv_tc.cu MODE 2), with and without the skip-path addend; tolerance 1e-3."""
+    from cruse_b200 import ops
+    torch.manual_seed(35)
+    ops.set_conv_mode("tf32")
+    conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), padding=(0, 1))
+    x = torch.randn(B, cin, T, Fin, requires_grad=True)
+    z = conv(torch.nn.functional.pad(x, (0, 0, 1, 0)))
+    gz = torch.randn_like(z)
+    z.backward(gz)
+    w = conv.weight.detach().to(cuda)
+    want = _to_frames(x.grad).to(cuda)
+    got = ops.conv_dgrad(_to_frames(gz).to(cuda), w, (B, T, cin, Fin), 2, 2)
+    assert rel_err(got, want) <= 1e-3
+    add = torch.randn(B, T, cin, Fin).to(cuda)
+    got = ops.conv_dgrad(_to_frames(gz).to(cuda), w, (B, T, cin, Fin), 2, 2, addend=add)
+    assert rel_err(got, want + add) <= 1e-3
+    ops.set_conv_mode("fp32")
+    exact = ops.conv_dgrad(_to_frames(gz).to(cuda), w, (B, T, cin, Fin), 2, 2)
+    ops.set_conv_mode("tf32")
+    assert rel_err(exact, want) <= 1e-4 and not torch.equal(exact, got - add)      # the two modes really are different kernels
+
+
 @pytest.mark.parametrize("cin,cout,Fin", [(64, 32, 16), (32, 16, 32), (16, 8, 64)])
 def test_convT_data_gradient_on_tensor_cores(cuda, cin, cout, Fin):
     """data gradient of the decoder's transposed convs = a (1,3)/stride-2 conv over dz without left pad on the tcgen05

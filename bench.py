@@ -247,8 +247,8 @@ def run_ours(args):
 
     # inference: the whole step (~60 launches on 4 streams) is captured once into a CUDA graph and replayed
     captured = None
-    if not train and not args.no_graph:
-        captured = pipeline.CapturedForwardLoss(model, B, L, N_FFT, HOP)
+    if not args.no_graph:
+        captured = (pipeline.CapturedTrainStep if train else pipeline.CapturedForwardLoss)(model, B, L, N_FFT, HOP)
         captured.noisy.copy_(noisy)
         captured.clean.copy_(clean)
 
@@ -257,12 +257,18 @@ def run_ours(args):
 
     def step():
         if captured is not None:
-            return captured.replay()
+            loss = captured.replay()
+            if train and world > 1:
+                distrib.sync_grad(params)
+            return loss
         return run(noisy, clean)
 
     def step_host():
         if captured is not None:
-            return captured(noisy_h, clean_h)[0].to("cpu")
+            out = captured(noisy_h, clean_h)
+            if train and world > 1:
+                distrib.sync_grad(params)
+            return (out if train else out[0]).to("cpu")
         loss = run(noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True))
         return loss.to("cpu")
 
@@ -315,7 +321,10 @@ def run_ours(args):
         ticket = captured.prefetch(noisy_h, clean_h)
         for i in range(args.steps):
             nxt = captured.prefetch(noisy_h, clean_h) if i + 1 < args.steps else None
-            l_host = captured.run_prefetched(ticket)[0].to("cpu")
+            out = captured.run_prefetched(ticket)
+            if train and world > 1:
+                distrib.sync_grad(params)
+            l_host = (out if train else out[0]).to("cpu")
             ticket = nxt
     else:
         for _ in range(args.steps):

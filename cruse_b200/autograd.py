@@ -25,20 +25,103 @@ def gru_layer_fwd_train(x2d, grus, B, T, interleave):
     return y, (x2d, y, gates)
 
 
+class _SideWork:
+    """Weight-gradient kernels are off the backward's critical path (nothing downstream reads them), while the two BPTT
+    launches on it occupy only 8*G*slices of the 148 SMs for ~0.6 ms each.  ``run`` enqueues such work on a second stream
+    behind an event recorded on the main stream; ``join`` (before backward returns) makes the main stream wait for it.
+    Every tensor handed to the side stream is kept alive until the join so that the caching allocator cannot give its
+    block to a later main-stream allocation while the side stream is still reading it."""
+
+    def __init__(self, device, enabled):
+        self.enabled = enabled and device.type == "cuda"
+        self.keep = []
+        if self.enabled:
+            from .pipeline import _side_stream
+            self.main = torch.cuda.current_stream(device)
+            self.side = _side_stream(device)
+            self.hp = _high_priority_stream(device)
+
+    def mark(self):
+        """event at the current point of the main stream (None when disabled)"""
+        if not self.enabled:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        return ev
+
+    def critical(self, fn, after):
+        """run ``fn`` (the BPTT launch) on a high-priority stream behind ``after`` and let the main stream continue behind
+        it: work queued on the side stream behind the same event then starts AFTER the BPTT has taken its SMs (a cluster
+        needs 8 free SMs in one GPC; persistent side CTAs spread over all GPCs would otherwise keep it waiting)."""
+        if not self.enabled:
+            return fn()
+        self.hp.wait_event(after)
+        with torch.cuda.stream(self.hp):
+            out = fn()
+            done = torch.cuda.Event()
+            done.record(self.hp)
+        self.main.wait_event(done)
+        return out
+
+    def run(self, fn, *tensors, after=None, max_ctas=0):
+        if not self.enabled:
+            return fn()
+        ev = after if after is not None else self.mark()
+        self.side.wait_event(ev)
+        self.keep.extend(tensors)
+        if max_ctas:
+            ops.set_conv_max_ctas(max_ctas)
+        try:
+            with torch.cuda.stream(self.side):
+                out = fn()
+        finally:
+            if max_ctas:
+                ops.set_conv_max_ctas(0)
+        self.keep.append(out)
+        return out
+
+    def join(self):
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+        self.keep.clear()
+
+
+_hp_streams = {}
+
+
+def _high_priority_stream(device):
+    key = (device.type, device.index)
+    if key not in _hp_streams:
+        _hp_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _hp_streams[key]
+
+
 def _splitk(M):
     """K = B*T of the weight-gradient GEMMs is split so that ~all SMs get a CTA (3 m-tiles x G x splitk)."""
     return max(1, min(16, M // 1024))
 
 
-def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True):
-    """dy [B,T,G*H] (layout of y) -> (dx [B*T, G*H] | None, {param: grad})"""
+def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, beside=None, own_wgrads_on_side=True):
+    """dy [B,T,G*H] (layout of y) -> (dx [B*T, G*H] | None, {param: grad}); with ``side`` the weight gradients are
+    enqueued on the side stream (valid on the main stream after ``side.join()``) and ``beside(after_event)`` is called right
+    after the BPTT launch to queue side work that should run next to it"""
     x2d, y, gates = saved
     G = len(grus)
     H = grus[0].hidden_size
     M = B * T
     w_ih = [g.weight_ih_l0 for g in grus]
     w_hh = [g.weight_hh_l0 for g in grus]
-    dxproj, dpre, dbias, _ = ops.gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave)
+    if side is not None and side.enabled:
+        ready = side.mark()
+        dxproj, dpre, dbias, _ = side.critical(lambda: ops.gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave), ready)
+        if beside is not None:
+            beside(ready)
+    else:
+        dxproj, dpre, dbias, _ = ops.gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave)
+        if beside is not None:
+            beside(None)
     dev = dy.device
     grads = {}
     # ---- bias gradients: xproj carried b_ih (all gates) + b_hh (r,z); W_hn.h carried b_hh (n)
@@ -54,22 +137,27 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True):
                        M, H, 3 * H, G * 3 * H, 3 * H, G * H)
     # ---- weight gradients: dW_ih = dxproj^T . x, dW_hh = dpre^T . h_{t-1}; reduction index (b,t) made innermost
     y_fs, y_gs = (G, 1) if interleave else (1, H)
-    dxT = ops.transpose_gcm(dxproj, M, G, 3 * H, G * 3 * H, 3 * H, 1)           # [G, 3H, M4]
-    dpT = ops.transpose_gcm(dpre, M, G, 3 * H, G * 3 * H, 3 * H, 1)
-    xT = ops.transpose_gcm(x2d, M, G, H, G * H, H, 1)                           # [G, H, M4]
-    hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # h_{t-1}
-    M4 = dxT.shape[-1]
-    sk = _splitk(M)
     plane = 3 * H * H
-    part = torch.empty(2, G, sk, plane, device=dev, dtype=torch.float32)
-    ops.gemm_tn_tc([dxT[gi] for gi in range(G)], [xT[gi] for gi in range(G)], [part[0, gi] for gi in range(G)],
-                   3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
-    ops.gemm_tn_tc([dpT[gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
-                   3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
-    dw = torch.empty(2, G, plane, device=dev, dtype=torch.float32)
-    for a in range(2):
-        for gi in range(G):
-            ops.colsum(part[a, gi], sk, plane, dw[a, gi])
+
+    def weight_grads():
+        dxT = ops.transpose_gcm(dxproj, M, G, 3 * H, G * 3 * H, 3 * H, 1)           # [G, 3H, M4]
+        dpT = ops.transpose_gcm(dpre, M, G, 3 * H, G * 3 * H, 3 * H, 1)
+        xT = ops.transpose_gcm(x2d, M, G, H, G * H, H, 1)                           # [G, H, M4]
+        hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # h_{t-1}
+        M4 = dxT.shape[-1]
+        sk = _splitk(M)
+        part = torch.empty(2, G, sk, plane, device=dev, dtype=torch.float32)
+        ops.gemm_tn_tc([dxT[gi] for gi in range(G)], [xT[gi] for gi in range(G)], [part[0, gi] for gi in range(G)],
+                       3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
+        ops.gemm_tn_tc([dpT[gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
+                       3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
+        dw_ = torch.empty(2, G, plane, device=dev, dtype=torch.float32)
+        for a in range(2):
+            for gi in range(G):
+                ops.colsum(part[a, gi], sk, plane, dw_[a, gi])
+        return dw_
+
+    dw = side.run(weight_grads, dxproj, dpre, x2d, y) if (side is not None and own_wgrads_on_side) else weight_grads()
     for gi, g in enumerate(grus):
         grads[g.weight_ih_l0] = dw[0, gi].view(3 * H, H)
         grads[g.weight_hh_l0] = dw[1, gi].view(3 * H, H)
@@ -154,6 +242,16 @@ class _Unet2Fn(torch.autograd.Function):
         act, train = m.act_kind, ctx.train
         G = {}                                                    # parameter tensor -> gradient
         dmask = dmask.contiguous()
+        side = _SideWork(dmask.device, ops.OVERLAP_BWD)
+        cap = 0                                                   # persistent side kernels sized to the SMs the BPTT leaves free
+        if side.enabled and ops.BWD_SIDE_CAP:
+            ng = len(m.gru.gru_list1)
+            clusters = ng * ((B + 15) // 16)                      # gru_bwd_tc.cu launch_bwd_nc: 16-utterance slices if they fit
+            if clusters > ops.gru_seq_max_clusters(m.gru.gru_list1[0].hidden_size):
+                clusters = ng * ((B + 31) // 32)
+            free_sms = torch.cuda.get_device_properties(dmask.device).multi_processor_count - 8 * clusters
+            cap = free_sms if free_sms >= 32 else 0
+        deferred = []                                             # decoder / skip weight gradients: run beside the BPTT
         # ---- last decoder stage: mask = sigmoid(convT(d2))           cruse_net.py:164
         dz = ops.sigmoid_bwd(dmask.view(B, T, 1, F), sv["mask"])
         G[m.conv1_t.weight], G[m.conv1_t.bias] = ops.convT_wgrad(sv["d2"], dz)
@@ -172,17 +270,27 @@ class _Unet2Fn(torch.autograd.Function):
             G[bn.weight], G[bn.bias] = dgamma, dbeta
             if dalpha is not None:
                 G[getattr(m, f"act{k}_t").weight] = dalpha
-            G[conv.weight], G[conv.bias] = ops.convT_wgrad(x_in, dzk)
+            deferred.append((conv, x_in, dzk))
             d_out = ops.convT_dgrad(dzk, conv.weight, x_in.shape)
         dskip[n - 1] = d_out                                      # out = g + skip4     :160
+
+        def decoder_weight_grads():
+            for conv_, x_, dz_ in deferred:
+                G[conv_.weight], G[conv_.bias] = ops.convT_wgrad(x_, dz_)
+            for k_ in range(n, 0, -1):
+                e_ = sv["e4"] if k_ == n else sv["enc_in"][k_]
+                G[getattr(m, f"skip_connect_{k_}").weight], _ = ops.conv_wgrad(e_, dskip[k_ - 1], 1, 1, want_bias=False)
         # ---- GGRU                                                              :37-55
         gru = m.gru
         dgo = d_out.view(B * T, D)
         dy2, G[gru.ln2.weight], G[gru.ln2.bias] = ops.layernorm_bwd(dgo, sv["y2"].view(B * T, D), gru.ln2.weight, *sv["ln2"])
-        dz1, g2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False)
+        dz1, g2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False, side=side,
+                                beside=lambda ev: side.run(decoder_weight_grads, *[t for d in deferred for t in d[1:]], *dskip,
+                                                           after=ev, max_ctas=cap))
         G.update(g2)
         dy1, G[gru.ln1.weight], G[gru.ln1.bias] = ops.layernorm_bwd(dz1, sv["y1"].view(B * T, D), gru.ln1.weight, *sv["ln1"])
-        de, g1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True)
+        de, g1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True, side=side,
+                               own_wgrads_on_side=ops.BWD_SIDE_L1)
         G.update(g1)
         de = de.view(B, T, C4, F4)
         # ---- encoder stages k = n..1 with their skip convs                      :149-156
@@ -192,7 +300,6 @@ class _Unet2Fn(torch.autograd.Function):
             e_k = sv["e4"] if k == n else sv["enc_in"][k]         # output of stage k = input of stage k+1
             x_in, z = sv["enc_in"][k - 1], sv["enc_z"][k - 1]
             scale, shift, mean, invstd = sv["enc_bn"][k - 1]
-            G[skipc.weight], _ = ops.conv_wgrad(e_k, dskip[k - 1], 1, 1, want_bias=False)
             de = ops.conv_dgrad(dskip[k - 1], skipc.weight, e_k.shape, 1, 1, addend=de)
             dzk, dgamma, dbeta, dalpha = ops.bn_act_bwd(de, z, scale, shift, alpha, act, mean, invstd, bn.weight,
                                                         B * T * z.shape[3], training=train)
@@ -202,6 +309,7 @@ class _Unet2Fn(torch.autograd.Function):
             G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
             if k > 1:
                 de = ops.conv_dgrad(dzk, conv.weight, x_in.shape, 2, 2)
+        side.join()
         named = dict(m.named_parameters())
         out = []
         for nm in ctx.names:

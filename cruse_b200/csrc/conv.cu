@@ -28,7 +28,9 @@ int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, floa
 int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
                        int Fout, cudaStream_t st);
 
-// conv_edge.cu: streaming kernels for the single-channel stages (Cin == 1 / Cout == 1), eval mode
+// conv_edge.cu: streaming kernels for the single-channel stages (Cin == 1 / Cout == 1)
+int convT_edge_dgrad_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
+                         int Fout, cudaStream_t st);
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                   int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st);
 int convT_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
@@ -459,7 +461,12 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
         // train-mode stage: the conv (+ bias) on the tensor cores, then one pass over z for the BatchNorm partial sums
         const int rc = conv_tc_try(in, w, bias, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, 0, st);
         if (rc < 0) return rc;
-        if (rc == 1) {
+        int done = rc;
+        if (!done) {          // stage 1 (Cin == 1): the exact-fp32 streaming kernel, statistics by the same deterministic pass
+            done = conv_edge_try(in, w, bias, nullptr, nullptr, nullptr, CRUSE_ACT_NONE, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st);
+            if (done < 0) { set_error("conv_fwd: streaming stage-1 kernel launch failed"); return done; }
+        }
+        if (done == 1) {
             bn_stats_kernel<<<cruse_conv_nparts(B, T), 256, 0, st>>>(out, stats_ws, T, Cout, Fout);
             CRUSE_LAUNCH_OK();
             return 0;
@@ -578,7 +585,9 @@ extern "C" int cruse_convT_dgrad(const float* dz, const float* w, const float* a
     CRUSE_CHECK_ARG(Fout > 0 && Fout <= 2 * Fin + 1 && Fout >= 2 * Fin - 1, "convT_dgrad: Fout=%d must be within [2*Fin-1, 2*Fin+1] (Fin=%d)", Fout, Fin);
     // din[ci,i] = sum_co sum_k W[ci,co,0,k] dz[co,2i+k]: a stride-2 conv over dz without left padding
     {
-        const int rc = convT_dgrad_tc_try(dz, w, addend, din, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        int rc = convT_edge_dgrad_try(dz, w, addend, din, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
+        if (rc) { if (rc < 0) set_error("convT_dgrad: streaming last-stage kernel launch failed"); return rc < 0 ? rc : 0; }
+        rc = convT_dgrad_tc_try(dz, w, addend, din, B, T, Cin, Fin, Cout, Fout, (cudaStream_t)stream);
         if (rc) return rc < 0 ? rc : 0;
     }
     const size_t smem = conv_smem_bytes(1, Cout, Fout, Cin);

@@ -22,6 +22,12 @@ int conv_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, 
 int convT_wgrad_tc_try(const float* x, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int pitch,
                        int max_grid, cudaStream_t st);
 
+// conv_edge.cu: streaming kernels for the single-channel stages (exact fp32, either numeric mode)
+int conv_edge_wgrad_try(const float* in, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt,
+                        int fstride, int pitch, int max_grid, cudaStream_t st);
+int convT_edge_wgrad_try(const float* in, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int pitch,
+                         int max_grid, cudaStream_t st);
+
 constexpr int WG_TT = 8;
 constexpr int WG_THREADS = 256;
 
@@ -200,8 +206,9 @@ extern "C" int cruse_conv_wgrad(const float* in, const float* dz, float* dw, flo
     int grid = wgrad_grid(B, T, smem);
     const int nW = Cout * Cin * kt * 3;
     cudaStream_t st = (cudaStream_t)stream;
-    int np_tc = 0;
-    if (cruse_conv_get_mode() == 1) {       // tf32 mode: tensor-core split-K GEMM; same partial layout, same fixed-order reduction
+    int np_tc = conv_edge_wgrad_try(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout, kt, fstride, nW + Cout, grid, st);
+    if (np_tc < 0) { set_error("conv_wgrad: streaming stage-1 kernel launch failed"); return np_tc; }
+    if (np_tc == 0 && cruse_conv_get_mode() == 1) {       // tf32 mode: tensor-core split-K GEMM; same partial layout, same fixed-order reduction
         np_tc = conv_wgrad_tc_try(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout, kt, fstride, nW + Cout, grid, st);
         if (np_tc < 0) return np_tc;
     }
@@ -244,8 +251,9 @@ extern "C" int cruse_convT_wgrad(const float* in, const float* dz, float* dw, fl
     int grid = wgrad_grid(B, T, smem);
     const int nW = Cout * Cin * 3, n = nW + Cout;
     cudaStream_t st = (cudaStream_t)stream;
-    int np_tc = 0;
-    if (cruse_conv_get_mode() == 1) {
+    int np_tc = convT_edge_wgrad_try(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout, n, grid, st);
+    if (np_tc < 0) { set_error("convT_wgrad: streaming last-stage kernel launch failed"); return np_tc; }
+    if (np_tc == 0 && cruse_conv_get_mode() == 1) {
         np_tc = convT_wgrad_tc_try(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout, n, grid, st);
         if (np_tc < 0) return np_tc;
     }

@@ -95,7 +95,162 @@ dec1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward of the same two stages (training step).  The weight gradients are reductions over every (frame, bin) of
+// 6 resp. 3 taps x 8 channels: each thread keeps all of them in registers while the CTA strides over frames, one block
+// reduction at the end, one partial row [weights | bias] per CTA (summed in fixed order by colsum_kernel: deterministic).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[N], float* s_red, float* dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        float v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp * N + j] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < nwarps; ++w) v += s_red[w * N + j];
+        dst[j] = v;
+    }
+}
+
+// stage 1: dW[co][0][kt][kf] = sum dz[co,t,fo] * x[t-1+kt, 2fo-1+kf], dbias[co] = sum dz[co,t,fo]
+template <int COUT>
+__global__ void __launch_bounds__(128)
+enc1_wgrad_stream_kernel(const float* __restrict__ in, const float* __restrict__ dz, float* __restrict__ ws, int T, int Fout,
+                         long long nframes, int pitch) {
+    __shared__ float s_red[4 * COUT * 7];
+    float acc[COUT * 7];                                   // [co][6 taps] then [co] bias
+#pragma unroll
+    for (int j = 0; j < COUT * 7; ++j) acc[j] = 0.f;
+    const int Fin = 2 * Fout;
+    const int lane = threadIdx.x & 31;
+    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+        const int t = (int)(fr % T);
+        for (int fo = threadIdx.x; fo < Fout; fo += blockDim.x) {
+            const float* cur = in + fr * Fin + 2 * fo;
+            const float2 c = __ldg(reinterpret_cast<const float2*>(cur));
+            float2 p = make_float2(0.f, 0.f);
+            if (t > 0) p = __ldg(reinterpret_cast<const float2*>(cur - Fin));
+            float cl = __shfl_up_sync(0xffffffffu, c.y, 1), pl = __shfl_up_sync(0xffffffffu, p.y, 1);
+            if (lane == 0) {
+                cl = fo > 0 ? __ldg(cur - 1) : 0.f;
+                pl = (fo > 0 && t > 0) ? __ldg(cur - Fin - 1) : 0.f;
+            }
+            const float* g = dz + fr * (long long)(COUT * Fout) + fo;
+            float gv[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) gv[co] = __ldg(g + (size_t)co * Fout);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                acc[co * 6 + 0] = fmaf(gv[co], pl, acc[co * 6 + 0]);
+                acc[co * 6 + 1] = fmaf(gv[co], p.x, acc[co * 6 + 1]);
+                acc[co * 6 + 2] = fmaf(gv[co], p.y, acc[co * 6 + 2]);
+                acc[co * 6 + 3] = fmaf(gv[co], cl, acc[co * 6 + 3]);
+                acc[co * 6 + 4] = fmaf(gv[co], c.x, acc[co * 6 + 4]);
+                acc[co * 6 + 5] = fmaf(gv[co], c.y, acc[co * 6 + 5]);
+                acc[COUT * 6 + co] += gv[co];
+            }
+        }
+    }
+    block_reduce_store<COUT * 7>(acc, s_red, ws + (size_t)blockIdx.x * pitch);
+}
+
+// last stage: dW[ci][0][k] = sum_i x[ci,i] * dz[2i+k] (2i+k < 2*Fin), dbias = sum dz
+template <int CIN>
+__global__ void __launch_bounds__(128)
+dec1_wgrad_stream_kernel(const float* __restrict__ in, const float* __restrict__ dz, float* __restrict__ ws, int Fin,
+                         long long nframes, int pitch) {
+    __shared__ float s_red[4 * (CIN * 3 + 1)];
+    float acc[CIN * 3 + 1];
+#pragma unroll
+    for (int j = 0; j < CIN * 3 + 1; ++j) acc[j] = 0.f;
+    const int lane = threadIdx.x & 31;
+    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+        for (int i = threadIdx.x; i < Fin; i += blockDim.x) {
+            const float* gp = dz + fr * (long long)(2 * Fin) + 2 * i;
+            const float2 g = __ldg(reinterpret_cast<const float2*>(gp));
+            float gn = __shfl_down_sync(0xffffffffu, g.x, 1);
+            if (lane == 31) gn = i + 1 < Fin ? __ldg(gp + 2) : 0.f;
+            const float* x = in + fr * (long long)(CIN * Fin) + i;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float xv = __ldg(x + (size_t)ci * Fin);
+                acc[ci * 3 + 0] = fmaf(xv, g.x, acc[ci * 3 + 0]);
+                acc[ci * 3 + 1] = fmaf(xv, g.y, acc[ci * 3 + 1]);
+                acc[ci * 3 + 2] = fmaf(xv, gn, acc[ci * 3 + 2]);
+            }
+            acc[CIN * 3] += g.x + g.y;
+        }
+    }
+    block_reduce_store<CIN * 3 + 1>(acc, s_red, ws + (size_t)blockIdx.x * pitch);
+}
+
+// last stage: din[ci,i] = sum_k W[ci,0,k] dz[2i+k]
+template <int CIN>
+__global__ void __launch_bounds__(128)
+dec1_dgrad_stream_kernel(const float* __restrict__ dz, const float* __restrict__ w, float* __restrict__ din, int Fin, long long nframes) {
+    __shared__ float s_w[CIN * 3];
+    for (int i = threadIdx.x; i < CIN * 3; i += blockDim.x) s_w[i] = __ldg(w + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+        for (int i = threadIdx.x; i < Fin; i += blockDim.x) {
+            const float* gp = dz + fr * (long long)(2 * Fin) + 2 * i;
+            const float2 g = __ldg(reinterpret_cast<const float2*>(gp));
+            float gn = __shfl_down_sync(0xffffffffu, g.x, 1);
+            if (lane == 31) gn = i + 1 < Fin ? __ldg(gp + 2) : 0.f;
+            float* o = din + fr * (long long)(CIN * Fin) + i;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+                o[(size_t)ci * Fin] = fmaf(s_w[ci * 3 + 2], gn, fmaf(s_w[ci * 3 + 1], g.y, s_w[ci * 3] * g.x));
+        }
+    }
+}
+
 }  // namespace
+
+// Weight / bias gradient of stage 1: returns the number of partial rows written to ws (pitch floats each), 0 = not this shape.
+int conv_edge_wgrad_try(const float* in, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt,
+                        int fstride, int pitch, int max_grid, cudaStream_t st) {
+    if (!(Cin == 1 && Cout == 8 && kt == 2 && fstride == 2 && Fin == 2 * Fout && (Fout % 32) == 0 && Fout <= 128)) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 7) != 0 || max_grid < 1) return 0;
+    const long long nframes = (long long)B * T;
+    long long grid = (long long)sm_count() * 4;
+    if (grid > nframes) grid = nframes;
+    if (grid > max_grid) grid = max_grid;
+    enc1_wgrad_stream_kernel<8><<<(int)grid, Fout < 128 ? Fout : 128, 0, st>>>(in, dz, ws, T, Fout, nframes, pitch);
+    return cudaGetLastError() == cudaSuccess ? (int)grid : -3;
+}
+
+// Weight / bias gradient of the last decoder stage (same contract).
+int convT_edge_wgrad_try(const float* in, const float* dz, float* ws, int B, int T, int Cin, int Fin, int Cout, int Fout, int pitch,
+                         int max_grid, cudaStream_t st) {
+    if (!(Cout == 1 && Cin == 8 && Fout == 2 * Fin && (Fin % 32) == 0)) return 0;
+    if ((reinterpret_cast<uintptr_t>(dz) & 7) != 0 || max_grid < 1) return 0;
+    const long long nframes = (long long)B * T;
+    long long grid = (long long)sm_count() * 4;
+    if (grid > nframes) grid = nframes;
+    if (grid > max_grid) grid = max_grid;
+    dec1_wgrad_stream_kernel<8><<<(int)grid, Fin < 128 ? Fin : 128, 0, st>>>(in, dz, ws, Fin, nframes, pitch);
+    return cudaGetLastError() == cudaSuccess ? (int)grid : -3;
+}
+
+// Data gradient of the last decoder stage: 1 when launched here.
+int convT_edge_dgrad_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
+                         int Fout, cudaStream_t st) {
+    if (!(Cout == 1 && Cin == 8 && Fout == 2 * Fin && (Fin % 32) == 0 && addend == nullptr)) return 0;
+    if ((reinterpret_cast<uintptr_t>(dz) & 7) != 0) return 0;
+    const long long nframes = (long long)B * T;
+    const long long cap = (long long)sm_count() * 16;
+    const int grid = (int)(nframes < cap ? nframes : cap);
+    dec1_dgrad_stream_kernel<8><<<grid, Fin < 128 ? Fin : 128, 0, st>>>(dz, w, din, Fin, nframes);
+    return cudaGetLastError() == cudaSuccess ? 1 : -3;
+}
 
 // Returns 1 when the stage was launched here, 0 when the shape is not one of these (caller runs the general kernel).
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,

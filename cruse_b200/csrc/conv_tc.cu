@@ -479,6 +479,8 @@ bool conv_tc_enabled() { return conv_mode() == 1; }
 
 }  // namespace
 
+int conv_max_ctas() { return g_conv_max_ctas; }
+
 // Returns 1 when the stage was launched on the tensor cores, 0 when no instantiation matches (the caller then
 // runs the CUDA-core kernel), < 0 on error.
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,

@@ -26,6 +26,7 @@
 #include "tc_common.cuh"
 
 namespace cruse {
+int conv_max_ctas();     // conv_tc.cu: optional cap on persistent grids (0 = none)
 namespace {
 
 constexpr int WT_NPW = 8;                          // producer warps per set
@@ -283,6 +284,7 @@ int launch_wgrad_tc(const float* pl, const float* tp, float* ws, int B, int T, i
     const long long nkb = ((long long)B * T * FO + 31) / 32;
     int grid = sm_count();
     if (grid > max_grid) grid = max_grid;
+    if (conv_max_ctas() > 0 && grid > conv_max_ctas()) grid = conv_max_ctas();     // running beside the BPTT on a side stream
     if ((long long)grid > nkb) grid = (int)nkb;
     kern<<<grid, WT_THREADS, C::SMEM, st>>>(pl, tp, ws, B, T, pitch);
     CRUSE_LAUNCH_OK();

@@ -347,7 +347,11 @@ gru_bwd_tc_kernel(const float* __restrict__ dy, const float* __restrict__ y, con
 }
 
 constexpr size_t bwd_smem_bytes(int NC, int NI) {
-    return 1024 + 3 * (size_t)(16 * NI * 128) + 2 * (size_t)NC * 16 * NI * 32 * 4 + 64;
+    // The kernel holds all 512 TMEM columns of its SM.  Requesting at least 136 KB keeps every other tensor-core CTA of this
+    // library (GEMM 99.5 KB, conv stages > 100 KB) off the SM: one that were co-scheduled (the weight-gradient kernels run
+    // beside the BPTT on a side stream) would sit in tcgen05.alloc until the whole sequence has been processed.
+    const size_t need = 1024 + 3 * (size_t)(16 * NI * 128) + 2 * (size_t)NC * 16 * NI * 32 * 4 + 64;
+    return need < 136 * 1024 ? 136 * 1024 : need;
 }
 
 template <int NC, int NI>

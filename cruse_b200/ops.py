@@ -690,6 +690,11 @@ def set_conv_max_ctas(n: int):
     check(lib().cruse_conv_set_max_ctas(int(n)), "cruse_conv_set_max_ctas")
 
 
+# training backward: weight-gradient kernels on a side stream beside the BPTT launches (autograd._SideWork)
+OVERLAP_BWD = os.environ.get("CRUSE_OVERLAP_BWD", "1") != "0"
+BWD_SIDE_CAP = os.environ.get("CRUSE_BWD_SIDE_CAP", "1") != "0"
+BWD_SIDE_L1 = os.environ.get("CRUSE_BWD_SIDE_L1", "1") != "0"      # layer-1 GRU weight gradients beside the encoder backward
+
 # run the skip convs (and the clean-speech STFT) on a low-priority side stream beside the GRU wavefront
 OVERLAP_SKIPS = os.environ.get("CRUSE_OVERLAP_SKIPS", "1") != "0"
 SKIP_MAX_CTAS = int(os.environ.get("CRUSE_SKIP_MAX_CTAS", "0"))     # 0 = no cap (measured best on B200: 1.90 vs 1.94 ms at 80)

@@ -158,6 +158,72 @@ class CapturedForwardLoss:
         return self.loss, self.wav, self.est, self.mask
 
 
+class CapturedTrainStep(CapturedForwardLoss):
+    """The whole training step -- STFT, forward with batch statistics, wo_male, backward -- for one fixed (B, L) captured
+    ONCE into a CUDA graph.  Eagerly the step is ~180 launches plus autograd / allocator bookkeeping, about as much host
+    time as the 7 ms of device time; replayed it is device-bound, which is also what lets the weight-gradient kernels run
+    beside the BPTT launches on a second stream (autograd._SideWork) instead of queueing behind the host.
+
+    After a call every ``param.grad`` holds THIS step's gradient in a static buffer (overwritten by the next call, never
+    accumulated: gradient accumulation = add them up outside); BatchNorm running statistics are updated by the replay as
+    in eager mode.  An optimizer that updates parameters in place is seen by the next replay."""
+
+    def __init__(self, model, B, L, n_fft=512, hop=320, pad_mode="reflect", warmup=3):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("CapturedTrainStep: cruse_b200 runs on sm_100a only (no CPU fallback)")
+        self.model, self.args = model, (n_fft, hop, pad_mode)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.noisy = torch.zeros(B, L, device=dev, dtype=torch.float32)
+        self.clean = torch.zeros(B, L, device=dev, dtype=torch.float32)
+        bn_state = [(b, b.clone()) for n, b in model.named_buffers()]          # warm-up / capture must not move running stats
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                for p in self.params:
+                    p.grad = None
+                train_forward_loss(model, self.noisy, self.clean, n_fft, hop, pad_mode).backward()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in self.params:
+            p.grad = None                                                      # .grad allocated inside the capture = static
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss = train_forward_loss(model, self.noisy, self.clean, n_fft, hop, pad_mode)
+            loss.backward()
+            self.loss = loss.detach()
+        self.grads = [p.grad for p in self.params]
+        with torch.no_grad():
+            for b, saved in bn_state:
+                b.copy_(saved)
+        self.wav = self.est = self.mask = None
+
+    def _attach(self):
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+
+    def __call__(self, noisy, clean):
+        """noisy / clean [B,L] on the device or pinned host -> loss (0-dim, static); gradients in ``param.grad``."""
+        self.noisy.copy_(noisy, non_blocking=True)
+        self.clean.copy_(clean, non_blocking=True)
+        return self.replay()
+
+    def replay(self):
+        self.graph.replay()
+        self._attach()
+        return self.loss
+
+    def run_prefetched(self, ticket):
+        main = torch.cuda.current_stream(self.noisy.device)
+        main.wait_event(self._ready[ticket])
+        self.noisy.copy_(self._stage[ticket][0], non_blocking=True)
+        self.clean.copy_(self._stage[ticket][1], non_blocking=True)
+        self._consumed[ticket].record(main)
+        return self.replay()
+
+
 def train_forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
     """Training step forward: STFT + U-Net (saving what backward needs) + mask*X + wo_male -> loss with autograd
     history; ``loss.backward()`` runs the sm_100a backward kernels and fills ``param.grad``."""

@@ -405,3 +405,72 @@ def test_unet_gradients_smooth_functional(cuda, act):
             f.write(f"{name:40s} cos {cos:.7f} relL2 {rl2:.3e}\n")
     for name, cos, rl2 in rows:
         assert cos >= 0.99 and rl2 <= 0.15, (name, cos, rl2)
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_captured_train_step_matches_eager(cuda, overlap, monkeypatch):
+    """pipeline.CapturedTrainStep (the whole train step as one CUDA graph, weight gradients on a side stream beside the
+    BPTT) against the eager, single-stream step in the same numeric mode: same loss and same gradients (the kernels and
+    their summation orders are identical, so the bound is tight: 1e-5 rel-L2), on two different batches through the same
+    graph, and BatchNorm running statistics advance exactly as in eager mode."""
+    from cruse_b200 import ops, pipeline
+    from cruse_b200.cruse_net import unet_2
+    from oracle import cruse_oracle as o
+    B, L = 4, 8000
+    torch.manual_seed(5)
+    eager = unet_2(in_feat=256).to(cuda).train()
+    graph = unet_2(in_feat=256).to(cuda).train()
+    graph.load_state_dict(eager.state_dict())
+    monkeypatch.setattr(ops, "OVERLAP_BWD", overlap)
+    step = pipeline.CapturedTrainStep(graph, B, L)
+    for seed in (1, 2):
+        noisy, clean = o.synth_batch(B, L, seed)
+        noisy, clean = noisy.to(cuda), clean.to(cuda)
+        monkeypatch.setattr(ops, "OVERLAP_BWD", False)
+        for p in eager.parameters():
+            p.grad = None
+        loss_e = pipeline.train_forward_loss(eager, noisy, clean)
+        loss_e.backward()
+        loss_g = step(noisy, clean)
+        torch.cuda.synchronize()
+        assert abs(float(loss_g) - float(loss_e)) <= 1e-6 * abs(float(loss_e))
+        for (name, pe), pg in zip(eager.named_parameters(), graph.parameters()):
+            if pe.grad is None:
+                assert pg.grad is None or float(pg.grad.abs().max()) == 0.0, name
+                continue
+            assert pg.grad is not None, name
+            den = float(pe.grad.norm())
+            assert float((pg.grad - pe.grad).norm()) <= 1e-5 * den + 1e-12, (name, seed)
+        for (name, be), bg in zip(eager.named_buffers(), graph.buffers()):
+            assert torch.allclose(be.float(), bg.float(), rtol=1e-6, atol=1e-7), (name, seed)
+
+
+@pytest.mark.parametrize("B,T,Fin", [(3, 11, 256), (2, 64, 256), (1, 1, 64), (2, 5, 128)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_single_channel_stage_gradients_streaming_kernels(cuda, B, T, Fin, mode):
+    """stage 1 (Conv2d 1->8) weight/bias gradient and the last decoder stage (ConvTranspose2d 8->1) weight/bias/data
+    gradients run on the streaming kernels of conv_edge.cu in either numeric mode (exact fp32): 1e-4 against torch autograd,
+    and bit-identical run to run (fixed-order reductions)."""
+    from cruse_b200 import ops
+    torch.manual_seed(36)
+    ops.set_conv_mode(mode)
+    conv = nn.Conv2d(1, 8, (2, 3), (1, 2), padding=(0, 1))
+    x = torch.randn(B, 1, T, Fin)
+    z = conv(torch.nn.functional.pad(x, (0, 0, 1, 0)))
+    gz = torch.randn_like(z)
+    z.backward(gz)
+    dw, db = ops.conv_wgrad(_to_frames(x).to(cuda), _to_frames(gz).to(cuda), 2, 2)
+    assert rel_err(dw, conv.weight.grad) <= 1e-4 and rel_err(db, conv.bias.grad) <= 1e-4
+    dw2, db2 = ops.conv_wgrad(_to_frames(x).to(cuda), _to_frames(gz).to(cuda), 2, 2)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    Fi = Fin // 2
+    convt = nn.ConvTranspose2d(8, 1, (1, 3), (1, 2))
+    xi = torch.randn(B, 8, T, Fi, requires_grad=True)
+    y = convt(xi)[..., :2 * Fi]
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    dw, db = ops.convT_wgrad(_to_frames(xi.detach()).to(cuda), _to_frames(gy).to(cuda))
+    assert rel_err(dw, convt.weight.grad) <= 1e-4 and rel_err(db, convt.bias.grad) <= 1e-4
+    din = ops.convT_dgrad(_to_frames(gy).to(cuda), convt.weight.detach().to(cuda), (B, T, 8, Fi))
+    assert rel_err(din, _to_frames(xi.grad)) <= 1e-4
+    ops.set_conv_mode("tf32")

@@ -1,6 +1,6 @@
 """kernel timeline of one inference step (CUPTI through torch.profiler): start / duration / stream of every kernel,
 so that overlap between the GRU wavefront streams and the side work is visible.
-   python tools/trace_step.py [out.md] [--graph]"""
+   python tools/trace_step.py [out.md] [--graph | --train]"""
 import json, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,11 +15,13 @@ dev = torch.device("cuda:0")
 torch.manual_seed(1234)
 model = unet_2(in_feat=256)
 bench.randomise_bn(model)
-model = model.to(dev).eval()
-B, L = 32, 160000
+train = "--train" in sys.argv
+model = model.to(dev).train(train)
+B, L = (64, 64000) if train else (32, 160000)
+params = list(model.parameters())
 noisy, clean = bench.synth_batch(B, L, 20260)
 noisy, clean = noisy.to(dev), clean.to(dev)
-cap = pipeline.CapturedForwardLoss(model, B, L, 512, 320) if use_graph else None
+cap = pipeline.CapturedForwardLoss(model, B, L, 512, 320) if (use_graph and not train) else None
 if cap is not None:
     cap.noisy.copy_(noisy); cap.clean.copy_(clean)
 
@@ -27,6 +29,12 @@ if cap is not None:
 def step():
     if cap is not None:
         return cap.replay()
+    if train:
+        for p in params:
+            p.grad = None
+        loss = pipeline.train_forward_loss(model, noisy, clean, 512, 320)
+        loss.backward()
+        return loss.detach()
     with torch.no_grad():
         return pipeline.forward_loss(model, noisy, clean, 512, 320)[0]
 

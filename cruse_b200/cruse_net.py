@@ -58,6 +58,9 @@ class GGRU(nn.Module):
     def _layer(self, x2d, grus, B, T, interleave, h0=None, want_hT=False):
         xproj = ops.gru_ih_gemm(x2d, [g.weight_ih_l0 for g in grus], [g.bias_ih_l0 for g in grus],
                                 [g.bias_hh_l0 for g in grus])
+        if T == 1 and want_hT and B >= self.STEP_MIN_B and ops.GRU_SEQ_MODE == "tf32":
+            # streaming step of many concurrent utterances (cfg-5): no recurrence to keep on chip, the hidden half is a GEMM
+            return ops.gru_step(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], h0, interleave)
         return ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
                                interleave=interleave, h0=h0, want_hT=want_hT)
 
@@ -66,6 +69,7 @@ class GGRU(nn.Module):
     # layer only occupies G*ceil(B/16) clusters of 8 SMs.  Layer 2 (+ LayerNorm 1 and its input projections) of
     # frames [t0,t1) depends only on layer 1 up to t1, so the layers run side by side on three streams, one chunk of
     # frames apart; GRU-internal buffers are time-major so a chunk is a contiguous row range.
+    STEP_MIN_B = 128                # 1-frame streaming calls with at least this many utterances use ops.gru_step
     WAVEFRONT_MIN_T = 96
     WAVEFRONT_CHUNKS = 8            # relaunch mode: one recurrence launch per chunk
     WAVEFRONT_FLAG_CHUNKS = 8      # flag mode: chunks only gate the hand-over between the layers (ABI limit 16)

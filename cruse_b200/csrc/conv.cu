@@ -20,7 +20,7 @@ namespace cruse {
 // conv_tc.cu: tensor-core (tcgen05) implicit-GEMM instantiations for the 256-bin pyramid in eval mode
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                int in_tm, int out_tm, int wmode, cudaStream_t st);
+                int in_tm, int out_tm, int wmode, cudaStream_t st, const float* hist = nullptr);
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
 int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
@@ -32,7 +32,8 @@ int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, flo
 int convT_edge_dgrad_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
                          int Fout, cudaStream_t st);
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
-                  int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st);
+                  int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st,
+                  const float* hist = nullptr);
 int convT_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                    int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
 
@@ -472,10 +473,10 @@ extern "C" int cruse_conv_fwd(const float* in, const float* hist, const float* w
             return 0;
         }
     }
-    if (!hist && !stats_ws) {     // eval-mode stage of the 256-bin pyramid: tcgen05 implicit GEMM (conv_tc.cu)
-        int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, 0, st);
+    if (!stats_ws) {     // eval-mode stage of the 256-bin pyramid (hist: streaming chunk): tcgen05 implicit GEMM (conv_tc.cu)
+        int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, 0, 0, 0, st, hist);
         if (rc) return rc < 0 ? rc : 0;
-        rc = conv_edge_try(in, w, bias, scale, shift, alpha, act, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st);
+        rc = conv_edge_try(in, w, bias, scale, shift, alpha, act, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st, hist);
         if (rc) { if (rc < 0) set_error("conv_fwd: streaming stage-1 kernel launch failed"); return rc < 0 ? rc : 0; }
     }
     const size_t smem = conv_smem_bytes(kt, Cin, Fin, Cout);

@@ -20,7 +20,7 @@ template <int COUT>
 __global__ void __launch_bounds__(128)
 enc1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha, int act,
-                   float* __restrict__ out, int T, int Fout, long long nframes) {
+                   float* __restrict__ out, int T, int Fout, long long nframes, const float* __restrict__ hist) {
     __shared__ float s_w[COUT * 6 + 3 * COUT];
     for (int i = threadIdx.x; i < COUT * 6; i += blockDim.x) s_w[i] = __ldg(w + i);            // [COUT][1][2][3]
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
@@ -37,13 +37,15 @@ enc1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, co
         for (int fo = threadIdx.x; fo < Fout; fo += blockDim.x) {        // Fout is a multiple of 32: warps stay converged
             const float* cur = in + fr * Fin + 2 * fo;
             const float2 c = __ldg(reinterpret_cast<const float2*>(cur));
+            // frame t-1: the previous frame of the utterance, or (t == 0) the frame carried from the previous chunk of a stream
+            const float* prv = t > 0 ? cur - Fin : (hist ? hist + (fr / T) * Fin + 2 * fo : nullptr);
             float2 p = make_float2(0.f, 0.f);
-            if (t > 0) p = __ldg(reinterpret_cast<const float2*>(cur - Fin));
+            if (prv) p = __ldg(reinterpret_cast<const float2*>(prv));
             // bin 2fo-1 = the odd element of the previous thread (previous warp's last lane: one extra 4-byte load)
             float cl = __shfl_up_sync(0xffffffffu, c.y, 1), pl = __shfl_up_sync(0xffffffffu, p.y, 1);
             if (lane == 0) {
                 cl = fo > 0 ? __ldg(cur - 1) : 0.f;
-                pl = (fo > 0 && t > 0) ? __ldg(cur - Fin - 1) : 0.f;
+                pl = (fo > 0 && prv) ? __ldg(prv - 1) : 0.f;
             }
             float* o = out + fr * (long long)(COUT * Fout) + fo;
 #pragma unroll
@@ -254,13 +256,15 @@ int convT_edge_dgrad_try(const float* dz, const float* w, const float* addend, f
 
 // Returns 1 when the stage was launched here, 0 when the shape is not one of these (caller runs the general kernel).
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
-                  int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st) {
+                  int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st,
+                  const float* hist) {
+    if ((reinterpret_cast<uintptr_t>(hist) & 7) != 0) return 0;
     if (!(Cin == 1 && Cout == 8 && kt == 2 && fstride == 2 && Fin == 2 * Fout && (Fout % 32) == 0 && Fout <= 128)) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 7) != 0) return 0;
     const long long nframes = (long long)B * T;
     const long long cap = (long long)sm_count() * 16;
     const int grid = (int)(nframes < cap ? nframes : cap);
-    enc1_stream_kernel<8><<<grid, Fout < 128 ? Fout : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, T, Fout, nframes);
+    enc1_stream_kernel<8><<<grid, Fout < 128 ? Fout : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, T, Fout, nframes, hist);
     return cudaGetLastError() == cudaSuccess ? 1 : -3;
 }
 

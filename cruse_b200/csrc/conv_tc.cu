@@ -61,6 +61,8 @@ struct ConvTcArgs {
     float* out;
     int B, T, act;
     int in_tm, out_tm;      // frame records of in / out are ordered time-major (t*B + b) instead of (b*T + t)
+    const float* hist;      // MODE 0, KT == 2: frame -1 of every utterance [B][CIN][FIN] (streaming: the previous chunk's last
+                            //    input frame) or NULL = zero padding
     int wmode;              // 0: w is this conv's weight; 1 (KT == 1 conv only): data gradient of a (1,3)/stride-1 conv --
                             //    w is THAT conv's weight [Cin_here][Cout_here][1][3], taps flipped
 };
@@ -233,9 +235,13 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 const int item = it * CT_NPW + wq;
                 const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
                 const int t = MODE == 2 ? t0 + fr : t0 - (KT - 1) + fr;
-                const bool valid = (t >= 0) && (t < T);
+                bool valid = (t >= 0) && (t < T);
                 const int fo = fg * 16 + row16, ci0 = g * C::CB + cg * 4 + 2 * ep;
                 const float* src = a.in + ((a.in_tm ? (size_t)t * a.B + b : (size_t)b * T + t) * CIN + ci0) * C::FIN + (C::CONVLIKE ? SF : 1) * fo;
+                if (MODE == 0 && KT == 2 && t == -1 && a.hist) {      // streaming: the time tap of frame 0 reads the carried frame
+                    valid = true;
+                    src = a.hist + ((size_t)b * CIN + ci0) * C::FIN + SF * fo;
+                }
 #pragma unroll
                 for (int q = 0; q < NV; ++q) { va[it][q] = 0.f; vb[it][q] = 0.f; }
                 ea[it] = 0.f; eb[it] = 0.f;
@@ -485,11 +491,12 @@ int conv_max_ctas() { return g_conv_max_ctas; }
 // runs the CUDA-core kernel), < 0 on error.
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                int in_tm, int out_tm, int wmode, cudaStream_t st) {
+                int in_tm, int out_tm, int wmode, cudaStream_t st, const float* hist) {
     if (!conv_tc_enabled()) return 0;
+    if (hist && (kt != 2 || in_tm || (reinterpret_cast<uintptr_t>(hist) & 15))) return 0;
     if (wmode != 0 && !(wmode == 1 && kt == 1 && fstride == 1)) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, wmode};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, hist, wmode};
     int rc = 0;
     // last argument: MMA tiles (128 rows) per pipeline step; stages with long frames (FO >= 32) batch several of them
 #define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_, NS_)                                                    \
@@ -514,7 +521,7 @@ int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, flo
                        int Fout, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, 0};
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0};
     int rc = 0;
 #define CRUSE_CT_TD(CO_, CI_, FI_, NS_)                                              \
     if (Cout == CO_ && Cin == CI_ && Fin == FI_ && Fout == 2 * FI_) {                \
@@ -533,7 +540,7 @@ int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, floa
                       int Fout, int kt, cudaStream_t st) {
     if (!conv_tc_enabled() || kt != 2) return 0;
     if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, 0};
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0};
     int rc = 0;
 #define CRUSE_CT_CD(CO_, CI_, FO_, GM_, NS_)                                         \
     if (Cout == CO_ && Cin == CI_ && Fout == FO_ && Fin == 2 * FO_) {                \
@@ -551,7 +558,7 @@ int convT_tc_try(const float* in, const float* w, const float* bias, const float
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, 0};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, nullptr, 0};
     int rc = 0;
 #define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_, NS_)                                      \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \

@@ -281,3 +281,88 @@ extern "C" int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, c
     }
     return launch_gemm(args, G, M, N, K, ldc, 0, splitk, c_plane, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// One streaming GRU step for a large batch of concurrent utterances (BASELINE cfg-5: 2048 utterances x 1 frame).
+// With T == 1 there is no recurrence to keep on chip: the hidden half is ONE [B,H] x [H,3H] GEMM per group -- the same
+// tcgen05 kernel as the input half -- followed by the gate math as an elementwise pass.
+//   hproj[g][b][:] = W_hh[g] . h_prev[g][b]          (tf32 operands, fp32 accumulate)
+//   r = s(xr + hr), z = s(xz + hz), n = tanh(xn + r * (hn + b_hn)), h' = (1-z) n + z h     (PyTorch gate order r,z,n;
+//   xproj already carries b_ih and the r,z part of b_hh: cruse_gru_ih_gemm)
+// ---------------------------------------------------------------------------------------------
+namespace cruse {
+namespace {
+struct StepPtrs { const float* b_hh[CRUSE_MAX_GROUPS]; };
+
+__global__ void __launch_bounds__(256)
+gru_step_gates_kernel(const float* __restrict__ xproj, const float* __restrict__ hproj, const float* __restrict__ h_prev, const StepPtrs bp,
+                      float* __restrict__ h_new, float* __restrict__ y, int B, int G, int H, int y_fs, int y_gs) {
+    const int H4 = H >> 2;
+    const long long n = (long long)G * B * H4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % H4) * 4;
+        const long long gb = i / H4;
+        const int b = (int)(gb % B), g = (int)(gb / B);
+        const float* xp = xproj + ((size_t)b * G + g) * 3 * H + j;
+        const float* hp = hproj + ((size_t)g * B + b) * 3 * H + j;
+        const float4 xr = __ldg(reinterpret_cast<const float4*>(xp)), xz = __ldg(reinterpret_cast<const float4*>(xp + H)),
+                     xn = __ldg(reinterpret_cast<const float4*>(xp + 2 * H));
+        const float4 hr = __ldg(reinterpret_cast<const float4*>(hp)), hz = __ldg(reinterpret_cast<const float4*>(hp + H)),
+                     hn = __ldg(reinterpret_cast<const float4*>(hp + 2 * H));
+        const float4 ho = h_prev ? __ldg(reinterpret_cast<const float4*>(h_prev + ((size_t)g * B + b) * H + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 bn = bp.b_hh[g] ? __ldg(reinterpret_cast<const float4*>(bp.b_hh[g] + 2 * H + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float o[4];
+        const float xr_[4] = {xr.x, xr.y, xr.z, xr.w}, xz_[4] = {xz.x, xz.y, xz.z, xz.w}, xn_[4] = {xn.x, xn.y, xn.z, xn.w};
+        const float hr_[4] = {hr.x, hr.y, hr.z, hr.w}, hz_[4] = {hz.x, hz.y, hz.z, hz.w}, hn_[4] = {hn.x, hn.y, hn.z, hn.w};
+        const float ho_[4] = {ho.x, ho.y, ho.z, ho.w}, bn_[4] = {bn.x, bn.y, bn.z, bn.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float r = sigmoidf_(xr_[q] + hr_[q]);
+            const float z = sigmoidf_(xz_[q] + hz_[q]);
+            const float nn = tanhf(xn_[q] + r * (hn_[q] + bn_[q]));
+            o[q] = (1.f - z) * nn + z * ho_[q];
+        }
+        *reinterpret_cast<float4*>(h_new + ((size_t)g * B + b) * H + j) = make_float4(o[0], o[1], o[2], o[3]);
+        float* yo = y + (size_t)b * G * H + (size_t)g * y_gs;
+        if (y_fs == 1) {
+            *reinterpret_cast<float4*>(yo + j) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) yo[(size_t)(j + q) * y_fs] = o[q];
+        }
+    }
+}
+}  // namespace
+}  // namespace cruse
+
+extern "C" size_t cruse_gru_step_ws_bytes(int B, int G, int H) { return sizeof(float) * (size_t)G * B * 3 * H; }
+
+extern "C" int cruse_gru_step(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h_prev,
+                              float* h_new, float* y, void* ws, int B, int G, int H, int y_fs, int y_gs, void* stream) {
+    CRUSE_CHECK_ARG(xproj && w_hh && h_new && y && ws, "gru_step: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0, "gru_step: bad sizes B=%d G=%d H=%d", B, G, H);
+    CRUSE_CHECK_ARG(h_new != h_prev, "gru_step: h_new must not alias h_prev");
+    CRUSE_CHECK_ARG((y_gs % 4) == 0 || y_fs != 1, "gru_step: concatenated output needs a 16-byte aligned group stride");
+    float* hproj = static_cast<float*>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h_prev) {
+        const float* A[CRUSE_MAX_GROUPS];
+        float* C[CRUSE_MAX_GROUPS];
+        for (int g = 0; g < G; ++g) {
+            CRUSE_CHECK_ARG(w_hh[g], "gru_step: null w_hh[%d]", g);
+            A[g] = h_prev + (size_t)g * B * H;
+            C[g] = hproj + (size_t)g * B * 3 * H;
+        }
+        if (int rc = cruse_gemm_tn_tc(A, w_hh, nullptr, C, G, B, 3 * H, H, H, H, 3 * H, 1, 0, stream)) return rc;
+    } else {
+        CRUSE_CUDA_OK(cudaMemsetAsync(hproj, 0, cruse_gru_step_ws_bytes(B, G, H), st));       // zero state: W_hh . 0
+    }
+    cruse::StepPtrs bp;
+    for (int g = 0; g < CRUSE_MAX_GROUPS; ++g) bp.b_hh[g] = (g < G && b_hh) ? b_hh[g] : nullptr;
+    const long long n = (long long)G * B * (H / 4);
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)cruse::sm_count() * 16) blocks = (long long)cruse::sm_count() * 16;
+    cruse::gru_step_gates_kernel<<<(int)blocks, 256, 0, st>>>(xproj, hproj, h_prev, bp, h_new, y, B, G, H, y_fs, y_gs);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}

@@ -345,6 +345,28 @@ def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False, mod
     return (y, hT) if want_hT else y
 
 
+def gru_step(xproj, w_hh, b_hh, h_prev, interleave):
+    """ONE streaming step for B concurrent utterances (BASELINE cfg-5): xproj [B,G,3H], h_prev [G,B,H] | None ->
+    (y [B,1,G*H] in the layer's output order, h_new [G,B,H]).  The hidden half is one tcgen05 GEMM per group."""
+    _req(xproj, "xproj", 3)
+    _req(h_prev, "h_prev", 3)
+    B, G, H3 = xproj.shape
+    H = H3 // 3
+    if len(w_hh) != G or tuple(w_hh[0].shape) != (3 * H, H):
+        raise RuntimeError(f"gru_step: w_hh {len(w_hh)} x {tuple(w_hh[0].shape)} does not match xproj {tuple(xproj.shape)}")
+    if h_prev is not None and tuple(h_prev.shape) != (G, B, H):
+        raise RuntimeError(f"gru_step: h_prev shape {tuple(h_prev.shape)} != {(G, B, H)}")
+    dev = xproj.device
+    y = torch.empty(B, 1, G * H, device=dev, dtype=torch.float32)
+    h_new = torch.empty(G, B, H, device=dev, dtype=torch.float32)
+    ws = _ws(lib().cruse_gru_step_ws_bytes(B, G, H), dev)
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    _call("cruse_gru_step", _p(xproj), _ptr_table(w_hh), _ptr_table(b_hh), _p(h_prev), _p(h_new), _p(y), _p(ws), B, G, H,
+          y_fs, y_gs, _stream(),
+          meta=(f"gru_step[tf32] G{G} H{H} B{B}", _nb(xproj, h_prev, h_new, y, *w_hh) + 2 * ws.numel() * 4, 2 * B * G * H * 3 * H))
+    return y, h_new
+
+
 def gru_ih_gemm_tm(x, w_ih, b_ih, b_hh, B, T):
     """x [B*T, G*H] in frame order -> xproj [T, B, G, 3H] TIME-MAJOR (tcgen05, tf32): a chunk of frames of the
     result is one contiguous row range, which is what the two-layer wavefront needs."""

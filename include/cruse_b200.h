@@ -268,6 +268,15 @@ int cruse_layernorm_bwd(const float* dy, const float* x, const float* gamma, con
 int cruse_gru_seq_bwd_tc(const float* dy, const float* y, const float* gates, const float* h0,
                          const float* const* w_hh, float* dxproj, float* dpre, float* dh0, float* dbias_part,
                          int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
+/* One streaming step of the grouped GRU for B concurrent utterances (BASELINE cfg-5; the reference's state-carry API is
+ * GroupedGRULayer.forward(input, h0) -> (out, h), model/based_model/cust_conv.py:303-325, applied to a 1-frame input):
+ * hproj = W_hh . h_prev as ONE tcgen05 GEMM per group (tf32 operands), then the gate math (r,z,n order of nn.GRU,
+ * model/cruse_net.py:23-31) elementwise.  xproj [B,G,3H] from cruse_gru_ih_gemm(_tc) with M = B; h_prev [G,B,H] or NULL
+ * (zero state); h_new [G,B,H] (must not alias h_prev); y[b, j*y_fs + g*y_gs] = h_new[g][b][j];
+ * ws: cruse_gru_step_ws_bytes(B,G,H) bytes of scratch. */
+size_t cruse_gru_step_ws_bytes(int B, int G, int H);
+int cruse_gru_step(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h_prev,
+                   float* h_new, float* y, void* ws, int B, int G, int H, int y_fs, int y_gs, void* stream);
 /* G independent GEMMs on tcgen05 (tf32 operands, fp32 accumulate):  C_g[m,n] = sum_k A_g[m,k] * B_g[n,k] (+ bias_g[n]).
  * A_g [M,K] row pitch lda, B_g [N,K] row pitch ldb (both K-major), C_g row pitch ldc (floats).  splitk > 1 writes
  * splitk partial planes C_g + s*c_plane (bias must be NULL); sum them with cruse_colsum.

@@ -119,20 +119,22 @@ def test_forward_train_mode_batchnorm(cuda, conv_mode, tol_stats):
         assert rel_err(getattr(ours, k).running_var, getattr(ref, k).running_var) <= tol_stats
 
 
-def test_streaming_matches_batched(cuda):
+@pytest.mark.parametrize("B,T,chunk", [(4, 24, 6), (3, 7, 1), (130, 5, 1), (2048, 2, 1)])
+def test_streaming_matches_batched(cuda, B, T, chunk):
     """causal model: feeding frames in chunks with carried GRU state and one frame of conv history
-    reproduces the batched forward."""
+    reproduces the batched forward.  1-frame chunks of >= 128 utterances take the
+    cfg-5 path (ops.gru_step); (2048, 1 frame) is BASELINE cfg-5's size."""
     ours, _ = _pair(256, "relu", cuda)
     ours.eval()
     torch.manual_seed(12)
-    B, T, F = 4, 24, 256
+    F = 256
     mag = torch.rand(B, T, F, device=cuda)
     with torch.no_grad():
         full = ours.forward_frames(mag)
         from cruse_b200 import streaming
         st, outs = streaming.StreamState(), []
-        for t0 in range(0, T, 6):
-            outs.append(streaming.step(ours, mag[:, t0:t0 + 6].contiguous(), st))
+        for t0 in range(0, T, chunk):
+            outs.append(streaming.step(ours, mag[:, t0:t0 + chunk].contiguous(), st))
     assert rel_err(torch.cat(outs, dim=1), full) <= 1e-3   # tf32 recurrence: chunk boundaries re-round h
 
 

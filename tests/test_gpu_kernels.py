@@ -266,6 +266,36 @@ def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T, mode, tol):
         assert rel_err(torch.tanh(xn + r * hn), n) <= 1e-5
 
 
+@pytest.mark.parametrize("G,H,B,zero_state", [(4, 256, 2048, False), (4, 256, 130, True), (4, 176, 200, False), (2, 32, 129, False)])
+def test_gru_step_matches_nn_gru(cuda, G, H, B, zero_state):
+    """cfg-5 streaming step (ops.gru_step: one tcgen05 GEMM per group for the hidden half + elementwise gates) against
+    nn.GRU on a 1-frame input with explicit state, both output orders, up to the 2048 concurrent utterances BASELINE
+    cfg-5 names; tf32 operands -> 1e-3.  The module-level streaming path picks it for T == 1, B >= GGRU.STEP_MIN_B."""
+    from cruse_b200 import ops
+    torch.manual_seed(41)
+    grus = [nn.GRU(H, H, 1, batch_first=True) for _ in range(G)]
+    x = torch.randn(B, 1, G * H)
+    h0 = None if zero_state else 0.5 * torch.randn(G, B, H)
+    with torch.no_grad():
+        outs = [grus[g](x[..., g * H:(g + 1) * H].contiguous(), None if h0 is None else h0[g:g + 1].contiguous()) for g in range(G)]
+        y_cat = torch.cat([a for a, _ in outs], dim=-1)
+        y_int = torch.flatten(torch.stack([a for a, _ in outs], dim=-1), -2, -1)
+        hT = torch.cat([b for _, b in outs], dim=0)
+    dev = lambda ts: [t.detach().to(cuda) for t in ts]
+    w_ih, w_hh = dev([g.weight_ih_l0 for g in grus]), dev([g.weight_hh_l0 for g in grus])
+    b_ih, b_hh = dev([g.bias_ih_l0 for g in grus]), dev([g.bias_hh_l0 for g in grus])
+    xproj = ops.gru_ih_gemm(x.view(B, G * H).to(cuda), w_ih, b_ih, b_hh, mode="tf32")
+    hp = None if h0 is None else h0.to(cuda)
+    got_cat, got_h = ops.gru_step(xproj, w_hh, b_hh, hp, interleave=False)
+    got_int, got_h2 = ops.gru_step(xproj, w_hh, b_hh, hp, interleave=True)
+    assert got_cat.shape == (B, 1, G * H) and got_h.shape == (G, B, H)
+    assert rel_err(got_cat, y_cat) <= 1e-3
+    assert rel_err(got_int, y_int) <= 1e-3
+    assert rel_err(got_h, hT) <= 1e-3 and torch.equal(got_h, got_h2)
+    with pytest.raises(RuntimeError):
+        ops.gru_step(xproj, w_hh, b_hh, torch.zeros(G, B + 1, H, device=cuda), interleave=False)
+
+
 def test_grouped_gru_reference_fixture_and_streaming(cuda, golden_dir):
     """reference GroupedGRULayer output (cust_conv.py:303-325) incl. explicit state; and T steps of 1 frame
     with carried state == one call over T frames."""

@@ -259,7 +259,7 @@ def run_ours(args):
         if captured is not None:
             loss = captured.replay()
             if train and world > 1:
-                distrib.sync_grad(params)
+                distrib.sync_grad(params, flat=captured.flat_grad)
             return loss
         return run(noisy, clean)
 
@@ -267,7 +267,7 @@ def run_ours(args):
         if captured is not None:
             out = captured(noisy_h, clean_h)
             if train and world > 1:
-                distrib.sync_grad(params)
+                distrib.sync_grad(params, flat=captured.flat_grad)
             return (out if train else out[0]).to("cpu")
         loss = run(noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True))
         return loss.to("cpu")
@@ -323,7 +323,7 @@ def run_ours(args):
             nxt = captured.prefetch(noisy_h, clean_h) if i + 1 < args.steps else None
             out = captured.run_prefetched(ticket)
             if train and world > 1:
-                distrib.sync_grad(params)
+                distrib.sync_grad(params, flat=captured.flat_grad)
             l_host = (out if train else out[0]).to("cpu")
             ticket = nxt
     else:

@@ -22,10 +22,32 @@ def world_size(group=None) -> int:
     return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
 
-def sync_grad(params, group=None):
-    """average ``p.grad`` over all ranks with ONE all_reduce (loss_func/distrib.py:100-116 semantics)."""
+def flat_grad_views(params, flat=None):
+    """one flat fp32 buffer and per-parameter views into it (parameter order, every parameter gets a slot):
+    gradients that live in such views are averaged in place by ``sync_grad(..., flat=flat)`` -- no gather / scatter copies."""
+    ps = list(params)
+    n = sum(p.numel() for p in ps)
+    if flat is None:
+        flat = torch.zeros(n, device=ps[0].device, dtype=torch.float32)
+    elif flat.numel() != n:
+        raise RuntimeError(f"flat_grad_views: buffer has {flat.numel()} elements, parameters have {n}")
+    views, off = [], 0
+    for p in ps:
+        views.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+    return flat, views
+
+
+def sync_grad(params, group=None, flat=None):
+    """average ``p.grad`` over all ranks with ONE all_reduce (loss_func/distrib.py:100-116 semantics).
+    ``flat``: the buffer the gradients already live in (``flat_grad_views``; pipeline.CapturedTrainStep.flat_grad):
+    reduced in place, two launches in total."""
     if not is_distributed(group):
         return None
+    if flat is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world_size(group))
+        return flat.numel() * flat.element_size()
     ps = [p for p in params if p.grad is not None]
     if not ps:
         return None

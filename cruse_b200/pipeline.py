@@ -164,7 +164,8 @@ class CapturedTrainStep(CapturedForwardLoss):
     time as the 7 ms of device time; replayed it is device-bound, which is also what lets the weight-gradient kernels run
     beside the BPTT launches on a second stream (autograd._SideWork) instead of queueing behind the host.
 
-    After a call every ``param.grad`` holds THIS step's gradient in a static buffer (overwritten by the next call, never
+    After a call every ``param.grad`` holds THIS step's gradient as a view of ``self.flat_grad`` (one static buffer:
+    ``distrib.sync_grad(params, flat=step.flat_grad)`` averages it over the ranks in place; overwritten by the next call, never
     accumulated: gradient accumulation = add them up outside); BatchNorm running statistics are updated by the replay as
     in eager mode.  An optimizer that updates parameters in place is seen by the next replay."""
 
@@ -189,12 +190,17 @@ class CapturedTrainStep(CapturedForwardLoss):
         torch.cuda.synchronize(dev)
         for p in self.params:
             p.grad = None                                                      # .grad allocated inside the capture = static
+        from .distrib import flat_grad_views
+        self.flat_grad, views = flat_grad_views(self.params)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             loss = train_forward_loss(model, self.noisy, self.clean, n_fft, hop, pad_mode)
             loss.backward()
             self.loss = loss.detach()
-        self.grads = [p.grad for p in self.params]
+            # the step's gradients end up in ONE flat buffer (the data-parallel all_reduce then runs in place on it)
+            got = [(v, p.grad) for v, p in zip(views, self.params) if p.grad is not None]
+            torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+        self.grads = [v if p.grad is not None else None for v, p in zip(views, self.params)]
         with torch.no_grad():
             for b, saved in bn_state:
                 b.copy_(saved)

@@ -37,6 +37,14 @@ def _worker(rank, world, port, out):
         nbytes = distrib.sync_grad(params)
         want = sum(range(1, world + 1)) / world
         ok = all((p.grad is None) if i == 3 else bool(torch.allclose(p.grad, torch.full_like(p, want))) for i, p in enumerate(params))
+        # the same average in place on a flat buffer the gradients are views of (pipeline.CapturedTrainStep.flat_grad)
+        flat, views = distrib.flat_grad_views(params)
+        for p, v in zip(params, views):
+            v.fill_(float(rank + 1))
+            p.grad = v
+        nb2 = distrib.sync_grad(params, flat=flat)
+        ok = ok and nb2 == 4 * flat.numel() and all(bool(torch.allclose(p.grad, torch.full_like(p, want))) for p in params)
+        ok = ok and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views))
         lo, hi = distrib.shard_batch(7, rank, world)
         out[rank] = (same, ok, nbytes, (lo, hi))
     finally:

@@ -80,14 +80,35 @@ class GGRU(nn.Module):
         key = (device.type, device.index)
         if key not in cls._side_streams:
             # the latency-critical recurrence chunks get scheduling priority over whatever runs beside them
-            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(4))
+            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(5))
         return cls._side_streams[key]
 
-    def _wavefront(self, x, residual, side=None, time_major=False):
+    def plan(self, B, T, device):
+        """chunk boundaries + zeroed device flags of a flag-synchronised wavefront over T frames, made BEFORE the encoder runs
+        so that the first chunk can start as soon as the encoder has produced its frames (``edges``); None when the
+        wavefront would not run in flag mode."""
+        if ops.GRU_WAVEFRONT_MODE != "flags":
+            return None
+        nch = max(2, min(self.WAVEFRONT_FLAG_CHUNKS, T // 24))
+        bounds = [T * k // nch for k in range(nch + 1)]
+        if not all(bounds[k + 1] - bounds[k] >= 8 for k in range(nch)):
+            return None
+        # [0,nch) layer-1 projections ready, [nch,2nch) layer-1 chunk stored (counts (CTA, slice) pairs), [2nch,3nch) layer-2
+        # projections ready, [3nch,4nch) layer-2 chunk stored, [4nch] error
+        flags = torch.zeros(4 * nch + 1, device=device, dtype=torch.int32)
+        return {"nch": nch, "bounds": bounds, "flags": flags}
+
+    def _wavefront(self, x, residual, side=None, time_major=False, plan=None, around=None):
         """``side(fork_event) -> (residual, ready_event)``: optional independent work (the skip convs) launched on a
         low-priority stream once the wavefront starts; it fills the SMs the recurrence leaves free.
         ``time_major``: x is [T,B,D] (written so by the last encoder stage); the layer-1 input projections then run per
-        chunk on contiguous rows and join the wavefront instead of preceding it."""
+        chunk on contiguous rows and join the wavefront instead of preceding it.
+        ``plan`` / ``around`` (flag mode): the network is causal, so the wavefront is extended over the stages behind the
+        GRU.  ``around.groups`` = [(k0, k1), ...] partitions the chunks; for group j covering the frames [t0,t1) the
+        callbacks ``skips(j, t0, t1, after_event) -> ready_event`` (the skip convs, on the caller's side stream) and
+        ``decode(j, ln2_out, t0, t1)`` (decoder stages, on the current stream) are issued, the latter behind LayerNorm 2 of
+        those frames as soon as layer 2 has stored chunk k1-1; ``around.residual`` is the [B,T,D] tensor LayerNorm 2 adds
+        (skip4).  Only the LAST group's LayerNorm 2 + decoder remain after the recurrence."""
         if time_major:
             T, B, D = x.shape
         else:
@@ -99,7 +120,7 @@ class GGRU(nn.Module):
         w_hh2, b_hh2 = [g.weight_hh_l0 for g in g2], [g.bias_hh_l0 for g in g2]
         w_ih2, b_ih2 = [g.weight_ih_l0 for g in g2], [g.bias_ih_l0 for g in g2]
         main = torch.cuda.current_stream(dev)
-        sA, sC, sB, sD = self._streams(dev)
+        sA, sC, sB, sD, sE = self._streams(dev)
         w_ih1, b_ih1 = [g.weight_ih_l0 for g in g1], [g.bias_ih_l0 for g in g1]
         if time_major:
             xp1 = torch.empty(T, B, G, 3 * H, device=dev, dtype=torch.float32)
@@ -115,9 +136,13 @@ class GGRU(nn.Module):
         # chunk boundaries: layer 2 finishes one (LayerNorm + projections + LAST chunk) after layer 1 and starts one FIRST chunk
         # after it, so the first and last chunks are short and the ones in between long (fewer relaunches)
         flag_mode = ops.GRU_WAVEFRONT_MODE == "flags" and time_major
-        if flag_mode:
+        if plan is None and flag_mode:
+            plan = self.plan(B, T, dev)
+        if flag_mode and plan is not None:
             # flag-synchronised chunks cost no relaunch, so they are short: layer 2 trails layer 1 by one chunk + its LayerNorm
             # and projections
+            nch, bounds = plan["nch"], plan["bounds"]
+        elif flag_mode:
             nch = max(2, min(self.WAVEFRONT_FLAG_CHUNKS, T // 24))
             bounds = [T * k // nch for k in range(nch + 1)]
         else:
@@ -131,18 +156,21 @@ class GGRU(nn.Module):
         else:
             bounds = [T * k // nch for k in range(nch + 1)]
         H = D // G
-        flagged = flag_mode and all(bounds[k + 1] - bounds[k] >= 8 for k in range(nch))
+        flagged = flag_mode and plan is not None
         if flagged:
-            # one launch per layer; chunk hand-over through device flags: [0,nch) layer-1 projections ready, [nch,2nch) layer-1
-            # chunk stored (counts (CTA, slice) pairs), [2nch,3nch) layer-2 projections ready, [3nch] error
-            flags = torch.zeros(3 * nch + 1, device=dev, dtype=torch.int32)
-            f_ih1, f_l1, f_ih2, f_err = flags[0:nch], flags[nch:2 * nch], flags[2 * nch:3 * nch], flags[3 * nch:]
+            # one launch per layer; chunk hand-over through device flags (layout: plan())
+            flags = plan["flags"]
+            f_ih1, f_l1, f_ih2, f_l2, f_err = (flags[0:nch], flags[nch:2 * nch], flags[2 * nch:3 * nch], flags[3 * nch:4 * nch],
+                                               flags[4 * nch:])
             self._wavefront_err = f_err
             n_wg = G * ((H + 31) // 32) * ((B + 15) // 16)
         fork = torch.cuda.Event()                                         # (after the flags are zeroed)
         fork.record(main)
-        for s_ in (sA, sC, sB, sD):
+        if not flagged:
+            around = None
+        for s_ in (sA, sC, sB, sD, sE):
             s_.wait_event(fork)
+        e_skip = [None] * nch
         side_ready = None
         tw1, tb1 = ops._ptr_table(w_ih1), ops._ptr_table(b_ih1)
         tw, tb = ops._ptr_table(w_ih2), ops._ptr_table(b_ih2)
@@ -174,9 +202,22 @@ class GGRU(nn.Module):
                     ops.gru_ih_gemm_into(z1[t0:t1].view(-1, D), w_ih2, b_ih2, b_hh2, xp2[t0:t1], tables=(tw, tb))
                     ops.flag_set(f_ih2[k:k + 1])
             with torch.cuda.stream(sB):                                   # layer 2, all frames  (:49-50)
-                ops.gru_seq_flagged(xp2, w_hh2, b_hh2, y2, False, False, bounds, f_ih2, 1, None, f_err)
+                ops.gru_seq_flagged(xp2, w_hh2, b_hh2, y2, False, False, bounds, f_ih2, 1, f_l2 if around is not None else None, f_err)
             if side is not None:
                 residual, side_ready = side(eD[nch - 1])
+            if around is not None:
+                # LayerNorm 2 (+ skip4, :51,160) and the decoder follow layer 2 group by group
+                out = torch.empty(B, T, D, device=dev, dtype=torch.float32)
+                groups = around.groups(nch)
+                for j, (k0, k1) in enumerate(groups):      # skip convs: once the layer-1 projections are through (as `side`)
+                    e_skip[j] = around.skips(j, bounds[k0], bounds[k1], eD[nch - 1])
+                with torch.cuda.stream(sE):
+                    for j, (k0, k1) in enumerate(groups):
+                        t0, t1 = bounds[k0], bounds[k1]
+                        sE.wait_event(e_skip[j])
+                        ops.flag_wait(f_l2[k1 - 1:k1], n_wg, f_err)
+                        ops.layernorm_fwd_range(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, around.residual, out, t0, t1)
+                        around.decode(j, out, t0, t1)
             for s_ in (sA, sC, sD):                                       # join every branch (graph capture needs it)
                 ev = torch.cuda.Event()
                 ev.record(s_)
@@ -211,6 +252,11 @@ class GGRU(nn.Module):
         main.wait_event(join)
         if side_ready is not None:
             main.wait_event(side_ready)
+        ev = torch.cuda.Event()
+        ev.record(sE)
+        main.wait_event(ev)
+        if around is not None:
+            return out
         return ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)   # :51 (+ skip4, :160)
 
     def uses_wavefront(self, B, T, state=None, want_state=False):
@@ -219,7 +265,8 @@ class GGRU(nn.Module):
                 and ops.GRU_IH_MODE == "tf32" and ops.GRU_WAVEFRONT
                 and 2 * self.groups * ((B + 31) // 32) <= ops.gru_seq_max_clusters(self.hidden_size // self.groups))
 
-    def forward_frames(self, x, residual=None, state=None, want_state=False, side=None, time_major=False):
+    def forward_frames(self, x, residual=None, state=None, want_state=False, side=None, time_major=False, plan=None,
+                       around=None):
         """x [B,T,D] frame-major ([T,B,D] with ``time_major``, wavefront path only); the result is always [B,T,D].
         state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence (streaming, model/based_model/cust_conv.py:303-325)."""
         _need_cuda(x, "GGRU")
@@ -230,8 +277,8 @@ class GGRU(nn.Module):
         if D != self.hidden_size:
             raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
         if self.uses_wavefront(B, T, state, want_state):
-            return self._wavefront(x, residual, side, time_major)
-        if side is not None or time_major:
+            return self._wavefront(x, residual, side, time_major, plan, around)
+        if side is not None or time_major or around is not None:
             raise RuntimeError("GGRU: side work / time-major input need the wavefront path")
         h1 = h2 = None
         if state is not None:
@@ -313,6 +360,91 @@ class unet_2(nn.Module):
         scale, shift, _, _ = ops.bn_finalize(stats, B * T * F, bn)
         return ops.bn_act_fwd(z, scale, shift, alpha, self.act_kind)
 
+    def _forward_frames_pipelined(self, mag, plan, folds):
+        """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
+        have no time taps at all, so LayerNorm 2 + the decoder (and the skip convs they add) are run per GROUP of wavefront
+        chunks as soon as layer 2 of the GRU has stored them: behind the last step of the recurrence only the last chunk's
+        LayerNorm + decoder are left instead of the whole decoder.  (The encoder stays in front: per-chunk encoder launches
+        were measured too -- layer 1 then starts 170 us earlier but is starved, ~25 us per small launch under load against
+        87 us of recurrence per chunk: 1.92 ms instead of 1.53.)"""
+        B, T, F = mag.shape
+        n = self.laynum
+        dev = mag.device
+        main = torch.cuda.current_stream(dev)
+        s_skip = self._skip_stream(dev)
+        new = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        C4, F4 = self.ch[n], self.freqs[n]
+        D = C4 * F4
+        unet = self
+        # ---- encoder, whole utterances (:149-152 repaired); the last stage writes the GRU input time-major
+        enc, h = [], mag.view(B, T, 1, F)
+        for k in range(1, n + 1):
+            conv = getattr(self, f"conv{k}")
+            scale, shift = folds[f"bn{k}"]
+            if k == n:
+                h = ops.conv_fwd_tm(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2, B, T, False, True)
+            else:
+                h = ops.conv_fwd(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2)
+            enc.append(h)
+        skip_out = [new(B, T, self.ch[k], self.freqs[k]) for k in range(1, n + 1)]
+        dec = [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
+        mask_buf = new(B, T, 1, F)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        layer_sms = 8 * self.gru.groups * ((B + 31) // 32)
+
+        class Around:
+            residual = skip_out[n - 1].view(B, T, D)
+
+            @staticmethod
+            def groups(nch):
+                # everything up to three chunks before the end, the next two, the last one
+                cuts = sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
+                return list(zip(cuts[:-1], cuts[1:]))
+
+            @staticmethod
+            def caps(j, ngroups):
+                # persistent grids sized to the SMs the recurrences leave free: both layers busy / layer 2 only / nothing
+                if j == ngroups - 1:
+                    return 0
+                return max(32, sms - (2 if j < ngroups - 2 else 1) * layer_sms)
+
+            @staticmethod
+            def skips(j, t0, t1, after):                                                         # :153-156
+                s_skip.wait_event(after)
+                ops.set_conv_max_ctas(max(32, sms - 2 * layer_sms))
+                try:
+                    with torch.cuda.stream(s_skip):
+                        for k in range(n, 0, -1):
+                            wk = getattr(unet, f"skip_connect_{k}").weight
+                            ops.conv_fwd_range(enc[k - 1], wk, None, None, None, None, "none", 1, 1, B, T, skip_out[k - 1], t0, t1,
+                                               in_tm=(k == n))
+                        ev = torch.cuda.Event()
+                        ev.record(s_skip)
+                finally:
+                    ops.set_conv_max_ctas(0)
+                return ev
+
+            @staticmethod
+            def decode(j, ln2_out, t0, t1):                                                      # :161-164 repaired
+                ops.set_conv_max_ctas(Around.caps(j, len(Around.groups(plan["nch"]))))
+                try:
+                    cur = ln2_out.view(B, T, C4, F4)
+                    for i, k in enumerate(range(n, 1, -1)):
+                        conv = getattr(unet, f"conv{k}_t")
+                        scale, shift = folds[f"bn{k}_t"]
+                        ops.convT_fwd_range(cur, conv.weight, conv.bias, scale, shift, unet._alpha(f"act{k}_t"), unet.act_kind,
+                                            skip_out[k - 2], dec[i], t0, t1)
+                        cur = dec[i]
+                    ops.convT_fwd_range(cur, unet.conv1_t.weight, unet.conv1_t.bias, None, None, None, "sigmoid", None, mask_buf, t0, t1)
+                finally:
+                    ops.set_conv_max_ctas(0)
+
+        self.gru.forward_frames(enc[n - 1].view(T, B, D), time_major=True, plan=plan, around=Around)
+        ev = torch.cuda.Event()
+        ev.record(s_skip)
+        main.wait_event(ev)
+        return mask_buf.view(B, T, F)
+
     def forward_frames(self, mag, state=None, want_state=False):
         """mag [B,T,F] frame-major magnitudes -> mask [B,T,F].  (Internal zero-copy entry used by
         cruse_b200.pipeline; ``forward`` wraps it with the reference's [B,1,T,F] layout.)
@@ -335,7 +467,10 @@ class unet_2(nn.Module):
         if not train:                                   # all eval-mode BatchNorm folds of the pass in one launch
             names = [f"bn{k}" for k in range(1, n + 1)] + [f"bn{k}_t" for k in range(n, 1, -1)]
             folds = dict(zip(names, ops.bn_fold_many([getattr(self, nm) for nm in names])))
-        for k in range(1, n + 1):                                                                   # :149-152 repaired
+        plan = self.gru.plan(B, T, mag.device) if (overlap and ops.PIPELINE_EDGES) else None
+        if plan is not None:
+            return self._forward_frames_pipelined(mag, plan, folds)
+        for k in range(1, n + 1):                                            # :149-152 repaired
             if want_state:
                 new_hist.append(h[:, -1].contiguous())
             if overlap and k == n:

@@ -20,9 +20,10 @@ namespace cruse {
 // conv_tc.cu: tensor-core (tcgen05) implicit-GEMM instantiations for the 256-bin pyramid in eval mode
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                int in_tm, int out_tm, int wmode, cudaStream_t st, const float* hist = nullptr);
+                int in_tm, int out_tm, int wmode, cudaStream_t st, const float* hist = nullptr, int t_begin = 0, int t_end = 0);
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
-                 int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
+                 int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st,
+                 int t_begin = 0, int t_end = 0);
 int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
                       int Fout, int kt, cudaStream_t st);
 int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
@@ -33,9 +34,10 @@ int convT_edge_dgrad_try(const float* dz, const float* w, const float* addend, f
                          int Fout, cudaStream_t st);
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                   int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st,
-                  const float* hist = nullptr);
+                  const float* hist = nullptr, int t_begin = 0, int t_end = 0);
 int convT_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
-                   int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st);
+                   int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st,
+                   int t_begin = 0, int t_end = 0);
 
 constexpr int CONV_TT = 8;    // frames per CTA
 constexpr int CONV_COT = 4;   // output channels per thread
@@ -505,6 +507,42 @@ extern "C" int cruse_conv_fwd_tm(const float* in, const float* w, const float* b
     if (rc < 0) return rc;
     CRUSE_CHECK_ARG(rc == 1, "conv_fwd_tm: no tensor-core instantiation for kt=%d fstride=%d Cin=%d Cout=%d Fin=%d (or conv mode is fp32)", kt,
                     fstride, Cin, Cout, Fin);
+    return 0;
+}
+
+// Eval-mode stages restricted to the output frames [t_begin, t_end) of every utterance (tensor-core / streaming kernels only).
+extern "C" int cruse_conv_fwd_range(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                                    const float* alpha, int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout,
+                                    int kt, int fstride, int in_time_major, int out_time_major, int t_begin, int t_end, void* stream) {
+    CRUSE_CHECK_ARG(in && w && out, "conv_fwd_range: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "conv_fwd_range: bad sizes");
+    CRUSE_CHECK_ARG(t_begin >= 0 && t_begin < t_end && t_end <= T, "conv_fwd_range: bad frame range [%d,%d) of %d", t_begin, t_end, T);
+    CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_fwd_range: scale and shift go together");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_fwd_range: PReLU needs alpha");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = conv_tc_try(in, w, bias, scale, shift, alpha, act, nullptr, out, B, T, Cin, Fin, Cout, Fout, kt, fstride,
+                         in_time_major ? 1 : 0, out_time_major ? 1 : 0, 0, st, nullptr, t_begin, t_end);
+    if (rc == 0 && !in_time_major && !out_time_major)
+        rc = conv_edge_try(in, w, bias, scale, shift, alpha, act, out, B, T, Cin, Fin, Cout, Fout, kt, fstride, st, nullptr, t_begin, t_end);
+    if (rc < 0) { set_error("conv_fwd_range: kernel launch failed"); return rc; }
+    CRUSE_CHECK_ARG(rc == 1, "conv_fwd_range: no tensor-core / streaming instantiation for kt=%d fstride=%d Cin=%d Cout=%d Fin=%d (or conv mode is fp32)",
+                    kt, fstride, Cin, Cout, Fin);
+    return 0;
+}
+
+extern "C" int cruse_convT_fwd_range(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                                     const float* alpha, int act, const float* skip, float* out, int B, int T, int Cin, int Fin,
+                                     int Cout, int Fout, int t_begin, int t_end, void* stream) {
+    CRUSE_CHECK_ARG(in && w && out, "convT_fwd_range: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0, "convT_fwd_range: bad sizes");
+    CRUSE_CHECK_ARG(t_begin >= 0 && t_begin < t_end && t_end <= T, "convT_fwd_range: bad frame range [%d,%d) of %d", t_begin, t_end, T);
+    CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "convT_fwd_range: scale and shift go together");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "convT_fwd_range: PReLU needs alpha");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = convT_tc_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, st, t_begin, t_end);
+    if (rc == 0) rc = convT_edge_try(in, w, bias, scale, shift, alpha, act, skip, out, B, T, Cin, Fin, Cout, Fout, st, t_begin, t_end);
+    if (rc < 0) { set_error("convT_fwd_range: kernel launch failed"); return rc; }
+    CRUSE_CHECK_ARG(rc == 1, "convT_fwd_range: no tensor-core / streaming instantiation for Cin=%d Cout=%d Fin=%d (or conv mode is fp32)", Cin, Cout, Fin);
     return 0;
 }
 

@@ -20,7 +20,7 @@ template <int COUT>
 __global__ void __launch_bounds__(128)
 enc1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha, int act,
-                   float* __restrict__ out, int T, int Fout, long long nframes, const float* __restrict__ hist) {
+                   float* __restrict__ out, int T, int Fout, long long nframes, const float* __restrict__ hist, int t_begin, int Tc) {
     __shared__ float s_w[COUT * 6 + 3 * COUT];
     for (int i = threadIdx.x; i < COUT * 6; i += blockDim.x) s_w[i] = __ldg(w + i);            // [COUT][1][2][3]
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
@@ -32,8 +32,9 @@ enc1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, co
     __syncthreads();
     const int Fin = 2 * Fout;
     const int lane = threadIdx.x & 31;
-    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
-        const int t = (int)(fr % T);
+    for (long long i = blockIdx.x; i < nframes; i += gridDim.x) {       // nframes = B * Tc frames of the range [t_begin, t_begin + Tc)
+        const int t = t_begin + (int)(i % Tc);
+        const long long fr = (i / Tc) * T + t;
         for (int fo = threadIdx.x; fo < Fout; fo += blockDim.x) {        // Fout is a multiple of 32: warps stay converged
             const float* cur = in + fr * Fin + 2 * fo;
             const float2 c = __ldg(reinterpret_cast<const float2*>(cur));
@@ -68,7 +69,7 @@ template <int CIN>
 __global__ void __launch_bounds__(128)
 dec1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ alpha, int act,
-                   float* __restrict__ out, int Fin, long long nframes) {
+                   float* __restrict__ out, int Fin, long long nframes, int T, int t_begin, int Tc) {
     __shared__ float s_w[CIN * 3];
     for (int i = threadIdx.x; i < CIN * 3; i += blockDim.x) s_w[i] = __ldg(w + i);             // [CIN][1][1][3]
     __syncthreads();
@@ -76,7 +77,8 @@ dec1_stream_kernel(const float* __restrict__ in, const float* __restrict__ w, co
     const float sh = fmaf(bias ? __ldg(bias) : 0.f, sc, shift ? __ldg(shift) : 0.f);
     const float al = alpha ? __ldg(alpha) : 0.f;
     const int lane = threadIdx.x & 31;
-    for (long long fr = blockIdx.x; fr < nframes; fr += gridDim.x) {
+    for (long long j = blockIdx.x; j < nframes; j += gridDim.x) {       // nframes = B * Tc frames of the range [t_begin, t_begin + Tc)
+        const long long fr = (j / Tc) * T + t_begin + (j % Tc);
         for (int i = threadIdx.x; i < Fin; i += blockDim.x) {
             const float* x = in + fr * (long long)(CIN * Fin) + i;
             float xv[CIN];
@@ -257,25 +259,32 @@ int convT_edge_dgrad_try(const float* dz, const float* w, const float* addend, f
 // Returns 1 when the stage was launched here, 0 when the shape is not one of these (caller runs the general kernel).
 int conv_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                   int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride, cudaStream_t st,
-                  const float* hist) {
+                  const float* hist, int t_begin, int t_end) {
     if ((reinterpret_cast<uintptr_t>(hist) & 7) != 0) return 0;
+    if (t_end <= 0) { t_begin = 0; t_end = T; }
+    if (t_begin < 0 || t_begin >= t_end || t_end > T) return -1;
     if (!(Cin == 1 && Cout == 8 && kt == 2 && fstride == 2 && Fin == 2 * Fout && (Fout % 32) == 0 && Fout <= 128)) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 7) != 0) return 0;
-    const long long nframes = (long long)B * T;
+    const long long nframes = (long long)B * (t_end - t_begin);
     const long long cap = (long long)sm_count() * 16;
     const int grid = (int)(nframes < cap ? nframes : cap);
-    enc1_stream_kernel<8><<<grid, Fout < 128 ? Fout : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, T, Fout, nframes, hist);
+    enc1_stream_kernel<8><<<grid, Fout < 128 ? Fout : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, T, Fout, nframes, hist, t_begin,
+                                                                  t_end - t_begin);
     return cudaGetLastError() == cudaSuccess ? 1 : -3;
 }
 
 int convT_edge_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
-                   int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
+                   int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st,
+                   int t_begin, int t_end) {
     if (!(Cout == 1 && Cin == 8 && Fout == 2 * Fin && (Fin % 32) == 0 && skip == nullptr)) return 0;
     if ((reinterpret_cast<uintptr_t>(out) & 7) != 0) return 0;
-    const long long nframes = (long long)B * T;
+    if (t_end <= 0) { t_begin = 0; t_end = T; }
+    if (t_begin < 0 || t_begin >= t_end || t_end > T) return -1;
+    const long long nframes = (long long)B * (t_end - t_begin);
     const long long cap = (long long)sm_count() * 16;
     const int grid = (int)(nframes < cap ? nframes : cap);
-    dec1_stream_kernel<8><<<grid, Fin < 128 ? Fin : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, Fin, nframes);
+    dec1_stream_kernel<8><<<grid, Fin < 128 ? Fin : 128, 0, st>>>(in, w, bias, scale, shift, alpha, act, out, Fin, nframes, T, t_begin,
+                                                                 t_end - t_begin);
     return cudaGetLastError() == cudaSuccess ? 1 : -3;
 }
 

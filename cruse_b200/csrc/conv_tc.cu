@@ -63,6 +63,9 @@ struct ConvTcArgs {
     int in_tm, out_tm;      // frame records of in / out are ordered time-major (t*B + b) instead of (b*T + t)
     const float* hist;      // MODE 0, KT == 2: frame -1 of every utterance [B][CIN][FIN] (streaming: the previous chunk's last
                             //    input frame) or NULL = zero padding
+    int t_begin, t_end;     // output frames [t_begin, t_end) only (0, 0 = all T): the net is causal, so a time range of a stage needs
+                            //    nothing but the same range (and one frame before it) of the stage below -- lets the head of the
+                            //    encoder / the tail of the decoder run beside the recurrence instead of before / after it
     int wmode;              // 0: w is this conv's weight; 1 (KT == 1 conv only): data gradient of a (1,3)/stride-1 conv --
                             //    w is THAT conv's weight [Cin_here][Cout_here][1][3], taps flipped
 };
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) CT_STAMP(63, 14);                               // kernel start
     const int T = a.T;
-    const int chunks = (T + C::TF - 1) / C::TF;
+    const int chunks = (a.t_end - a.t_begin + C::TF - 1) / C::TF;
     const int ntiles = a.B * chunks;
 
     // ---- one-time setup: barriers, TMEM, weights in UMMA layout, epilogue parameters
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
 
         auto load_items = [&](int lo, int hi, int j) {
             const int tile = blockIdx.x + (j / C::NG) * gridDim.x, g = j % C::NG;
-            const int b = tile / chunks, t0 = (tile - b * chunks) * C::TF;
+            const int b = tile / chunks, t0 = a.t_begin + (tile - b * chunks) * C::TF;
 #pragma unroll
             for (int it = 0; it < C::NIT; ++it) {
                 if (it < lo || it >= hi) continue;
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
         const int act = a.act;
         int lt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-            const int b = tile / chunks, t0 = (tile - b * chunks) * C::TF;
+            const int b = tile / chunks, t0 = a.t_begin + (tile - b * chunks) * C::TF;
             const int ab = lt & 1;
             if (warp == CT_EPI_WARP0) CT_STAMP(lt, 10);
             tc::mbar_wait(&acc_full[ab], (lt >> 1) & 1);
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                     const int row = mt * 128 + quad * 32 + lane;
                     const int tl = row / FO, fo = row % FO;
                     const int t = t0 + tl;
-                    if (t >= T) continue;
+                    if (t >= a.t_end) continue;
                     const size_t rec = a.out_tm ? (size_t)t * a.B + b : (size_t)b * T + t;
                     if (C::CONVLIKE) {
                         const size_t o0 = rec * COUT * FO + fo;
@@ -453,15 +456,18 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
 }
 
 template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS>
-int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
+int launch_conv_tc(const ConvTcArgs& a_in, cudaStream_t st) {
     using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
+    ConvTcArgs a = a_in;
+    if (a.t_end <= 0) { a.t_begin = 0; a.t_end = a.T; }
+    if (a.t_begin < 0 || a.t_begin >= a.t_end || a.t_end > a.T) return -1;
     auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO, GM, NS>;
     static bool attr_set = false;                                   // per instantiation; benign if raced
     if (!attr_set) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    const int chunks = (a.T + C::TF - 1) / C::TF;
+    const int chunks = (a.t_end - a.t_begin + C::TF - 1) / C::TF;
     const long long ntiles = (long long)a.B * chunks;
     int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
     if (g_conv_max_ctas > 0 && grid > g_conv_max_ctas) grid = g_conv_max_ctas;
@@ -491,12 +497,12 @@ int conv_max_ctas() { return g_conv_max_ctas; }
 // runs the CUDA-core kernel), < 0 on error.
 int conv_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                 int act, const float* addend, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, int kt, int fstride,
-                int in_tm, int out_tm, int wmode, cudaStream_t st, const float* hist) {
+                int in_tm, int out_tm, int wmode, cudaStream_t st, const float* hist, int t_begin, int t_end) {
     if (!conv_tc_enabled()) return 0;
     if (hist && (kt != 2 || in_tm || (reinterpret_cast<uintptr_t>(hist) & 15))) return 0;
     if (wmode != 0 && !(wmode == 1 && kt == 1 && fstride == 1)) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, hist, wmode};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, hist, t_begin, t_end, wmode};
     int rc = 0;
     // last argument: MMA tiles (128 rows) per pipeline step; stages with long frames (FO >= 32) batch several of them
 #define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_, NS_)                                                    \
@@ -521,7 +527,7 @@ int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, flo
                        int Fout, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0};
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0, 0, 0};
     int rc = 0;
 #define CRUSE_CT_TD(CO_, CI_, FI_, NS_)                                              \
     if (Cout == CO_ && Cin == CI_ && Fin == FI_ && Fout == 2 * FI_) {                \
@@ -540,7 +546,7 @@ int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, floa
                       int Fout, int kt, cudaStream_t st) {
     if (!conv_tc_enabled() || kt != 2) return 0;
     if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0};
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0, 0, 0};
     int rc = 0;
 #define CRUSE_CT_CD(CO_, CI_, FO_, GM_, NS_)                                         \
     if (Cout == CO_ && Cin == CI_ && Fout == FO_ && Fin == 2 * FO_) {                \
@@ -555,10 +561,11 @@ int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, floa
 }
 
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
-                 int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st) {
+                 int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st,
+                 int t_begin, int t_end) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, nullptr, 0};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, nullptr, t_begin, t_end, 0};
     int rc = 0;
 #define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_, NS_)                                      \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \

@@ -292,10 +292,12 @@ static int launch_gru_seq(const float* xproj, const GroupPtrs& w_hh, const Group
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float eps, const float* __restrict__ res, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                     long long rows, int D) {
+                     long long rows, int D, int T, int t_begin, int Tc) {
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const bool vec = (D & 3) == 0;
-    for (long long row = (long long)blockIdx.x * nwarps + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * nwarps) {
+    for (long long r = (long long)blockIdx.x * nwarps + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * nwarps) {
+        // Tc > 0: the rows are the frames [t_begin, t_begin + Tc) of every utterance of a frame-major [B,T,D] tensor
+        const long long row = Tc > 0 ? (r / Tc) * T + t_begin + (r % Tc) : r;
         const float* xr = x + row * D;
         float* yr = y + row * D;
         float s = 0.f;
@@ -478,7 +480,23 @@ extern "C" int cruse_layernorm_fwd(const float* x, const float* gamma, const flo
     long long blocks = (rows + 7) / 8;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, residual, y, mean, rstd, rows, D);
+    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, residual, y, mean, rstd, rows, D, 0, 0, 0);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+// the same over the frames [t_begin, t_end) of every utterance of frame-major x / residual / y [B,T,D]
+extern "C" int cruse_layernorm_fwd_range(const float* x, const float* gamma, const float* beta, float eps, const float* residual,
+                                         float* y, int B, int T, int D, int t_begin, int t_end, void* stream) {
+    CRUSE_CHECK_ARG(x && y, "layernorm_fwd_range: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && D > 0 && t_begin >= 0 && t_begin < t_end && t_end <= T, "layernorm_fwd_range: bad sizes B=%d T=%d D=%d range [%d,%d)",
+                    B, T, D, t_begin, t_end);
+    const long long rows = (long long)B * (t_end - t_begin);
+    long long blocks = (rows + 7) / 8;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    layernorm_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, residual, y, nullptr, nullptr, rows, D, T, t_begin,
+                                                                             t_end - t_begin);
     CRUSE_LAUNCH_OK();
     return 0;
 }

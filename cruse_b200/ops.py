@@ -203,6 +203,41 @@ def conv_fwd_tm(x, w, bias, scale, shift, alpha, act, kt, fstride, B, T, in_tm, 
     return out
 
 
+def conv_fwd_range(x, w, bias, scale, shift, alpha, act, kt, fstride, B, T, out, t0, t1, in_tm=False, out_tm=False):
+    """eval-mode stage for the output frames [t0, t1) only, written into the full-size ``out`` ([B,T,Cout,Fout], or
+    [T,B,Cout,Fout] with ``out_tm``); x is the full-size input of the stage (frames < t1 must be valid)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    Fin = x.shape[-1]
+    Fout = (Fin + 2 - 3) // fstride + 1
+    if x.numel() != B * T * Cin * Fin or out.numel() != B * T * Cout * Fout:
+        raise RuntimeError(f"conv_fwd_range: x / out sizes {x.numel()} / {out.numel()} do not match B={B} T={T} {Cin}x{Fin} -> {Cout}x{Fout}")
+    _call("cruse_conv_fwd_range", _p(x), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(out), B, T, Cin, Fin, Cout, Fout,
+          kt, fstride, 1 if in_tm else 0, 1 if out_tm else 0, t0, t1, _stream(),
+          meta=(f"conv{kt}x3 {Cin}->{Cout} F{Fin}->{Fout} [{t0},{t1})", 4 * B * (t1 - t0) * (Cin * Fin + Cout * Fout),
+                2 * B * (t1 - t0) * Cout * Fout * Cin * kt * 3))
+
+
+def convT_fwd_range(x, w, bias, scale, shift, alpha, act, skip, out, t0, t1):
+    """eval-mode decoder stage for the frames [t0, t1) only: x [B,T,Cin,Fin], skip / out [B,T,Cout,Fout] full size."""
+    B, T, Cin, Fin = x.shape
+    Cout, Fout = out.shape[2], out.shape[3]
+    if tuple(w.shape) != (Cin, Cout, 1, 3) or tuple(out.shape[:2]) != (B, T):
+        raise RuntimeError(f"convT_fwd_range: weight {tuple(w.shape)} / out {tuple(out.shape)} do not match x {tuple(x.shape)}")
+    if skip is not None and tuple(skip.shape) != tuple(out.shape):
+        raise RuntimeError(f"convT_fwd_range: skip shape {tuple(skip.shape)} != {tuple(out.shape)}")
+    _call("cruse_convT_fwd_range", _p(x), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(skip), _p(out),
+          B, T, Cin, Fin, Cout, Fout, t0, t1, _stream(),
+          meta=(f"convT1x3 {Cin}->{Cout} F{Fin}->{Fout} [{t0},{t1})", 4 * B * (t1 - t0) * (Cin * Fin + (2 if skip is not None else 1) * Cout * Fout),
+                2 * B * (t1 - t0) * Cin * Fin * Cout * 3))
+
+
+def layernorm_fwd_range(x, gamma, beta, eps, residual, y, t0, t1):
+    """LayerNorm (+ residual) of the frames [t0, t1) of frame-major x / residual / y [B,T,D]."""
+    B, T, D = x.shape
+    _call("cruse_layernorm_fwd_range", _p(x), _p(gamma), _p(beta), float(eps), _p(residual), _p(y), B, T, D, t0, t1, _stream(),
+          meta=(f"layernorm D{D} [{t0},{t1})", 4 * B * (t1 - t0) * D * (3 if residual is not None else 2), 8 * B * (t1 - t0) * D))
+
+
 def convT_fwd(x, w, bias, scale, shift, alpha, act, skip, Fout, want_stats=False):
     """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout];  w [Cin,Cout,1,3] (ConvTranspose2d layout)."""
     _req(x, "x", 4)
@@ -716,6 +751,9 @@ def set_conv_max_ctas(n: int):
 OVERLAP_BWD = os.environ.get("CRUSE_OVERLAP_BWD", "1") != "0"
 BWD_SIDE_CAP = os.environ.get("CRUSE_BWD_SIDE_CAP", "1") != "0"
 BWD_SIDE_L1 = os.environ.get("CRUSE_BWD_SIDE_L1", "1") != "0"      # layer-1 GRU weight gradients beside the encoder backward
+
+# inference: pipeline the head of the encoder and the tail of the decoder with the GRU wavefront (cruse_net.GGRU._wavefront)
+PIPELINE_EDGES = os.environ.get("CRUSE_PIPELINE_EDGES", "0") != "0"
 
 # run the skip convs (and the clean-speech STFT) on a low-priority side stream beside the GRU wavefront
 OVERLAP_SKIPS = os.environ.get("CRUSE_OVERLAP_SKIPS", "1") != "0"

@@ -126,6 +126,21 @@ int cruse_bn_fold_many(const float* const* gamma, const float* const* beta, cons
 int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
                      const float* skip, float* y, long long n_frames, int C, int F, void* stream);
 
+/* Eval-mode stages restricted to the OUTPUT frames [t_begin, t_end) of every utterance (same argument meaning as
+ * cruse_conv_fwd_tm / cruse_convT_fwd / cruse_layernorm_fwd; out / y are the full-size tensors, rows outside the range are
+ * not touched).  The net is causal (model/cruse_net.py:138 pads time on the left only), so a frame range of a stage needs
+ * the same range -- plus one earlier frame for the (2,3) convs -- of the stage below: the first frames of the encoder
+ * can be through before the rest, and the decoder can follow the last GRU layer chunk by chunk.  Tensor-core / streaming
+ * kernels only (256-bin pyramid, tf32 conv mode): any other shape is an error, not a fallback. */
+int cruse_conv_fwd_range(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                         const float* alpha, int act, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout,
+                         int kt, int fstride, int in_time_major, int out_time_major, int t_begin, int t_end, void* stream);
+int cruse_convT_fwd_range(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                          const float* alpha, int act, const float* skip, float* out, int B, int T, int Cin, int Fin,
+                          int Cout, int Fout, int t_begin, int t_end, void* stream);
+int cruse_layernorm_fwd_range(const float* x, const float* gamma, const float* beta, float eps, const float* residual,
+                              float* y, int B, int T, int D, int t_begin, int t_end, void* stream);
+
 /* ---- a4: grouped GRU.  replaces nn.GRU(H,H) x groups at model/cruse_net.py:23-31,43-50.
  *  ih GEMM: xproj[m, g, :] = x[m, g*H:(g+1)*H] . w_ih[g]^T + b_ih[g] (+ b_hh[g] for r,z rows)
  *  x [M, G*H] (M = B*T); xproj [M, G, 3H].  w_ih/b_ih/b_hh: HOST arrays of G device pointers. */

@@ -383,3 +383,60 @@ def test_mask_bwd(cuda):
     want = (X[..., :F, 0] * dE[..., :F, 0] + X[..., :F, 1] * dE[..., :F, 1])
     got = ops.mask_bwd(dE.to(cuda), X.to(cuda), F)
     assert rel_err(got, want) <= 1e-6
+
+
+@pytest.mark.parametrize("B,T,cuts", [(3, 40, (0, 7, 8, 33, 40)), (2, 9, (0, 1, 9))])
+def test_frame_range_entries_equal_whole_tensor_calls(cuda, B, T, cuts):
+    """cruse_conv_fwd_range / cruse_convT_fwd_range / cruse_layernorm_fwd_range (the per-chunk launches of the pipelined
+    inference schedule): running a stage range by range into one buffer gives bit-identical results to the whole-tensor
+    call, for every stage shape of the 256-bin pyramid, incl. time-major input / output and the skip / residual adds."""
+    from cruse_b200 import ops
+    torch.manual_seed(42)
+    ops.set_conv_mode("tf32")
+    rnd = lambda *s: torch.randn(*s, device=cuda)
+    for cin, cout, Fin in [(1, 8, 256), (8, 16, 128), (16, 32, 64), (32, 64, 32)]:
+        x, w, b = rnd(B, T, cin, Fin), rnd(cout, cin, 2, 3) * 0.2, rnd(cout)
+        sc, sh = torch.rand(cout, device=cuda) + 0.5, rnd(cout) * 0.1
+        want = ops.conv_fwd(x, w, b, sc, sh, None, "relu", 2, 2)
+        got = torch.full_like(want, float("nan"))
+        for t0, t1 in zip(cuts[:-1], cuts[1:]):
+            ops.conv_fwd_range(x, w, b, sc, sh, None, "relu", 2, 2, B, T, got, t0, t1)
+        assert torch.equal(got, want), (cin, cout)
+        if cin == 32:                      # the GRU input is written time-major
+            got_tm = torch.full((T, B, cout, Fin // 2), float("nan"), device=cuda)
+            for t0, t1 in zip(cuts[:-1], cuts[1:]):
+                ops.conv_fwd_range(x, w, b, sc, sh, None, "relu", 2, 2, B, T, got_tm, t0, t1, out_tm=True)
+            assert torch.equal(got_tm.transpose(0, 1), want)
+    for c, F in [(8, 128), (16, 64), (32, 32), (64, 16)]:
+        x, w = rnd(B, T, c, F), rnd(c, c, 1, 3) * 0.2
+        want = ops.conv_fwd(x, w, None, None, None, None, "none", 1, 1)
+        got = torch.full_like(want, float("nan"))
+        for t0, t1 in zip(cuts[:-1], cuts[1:]):
+            ops.conv_fwd_range(x, w, None, None, None, None, "none", 1, 1, B, T, got, t0, t1)
+        assert torch.equal(got, want), c
+        if c == 64:                        # skip4 reads the time-major e4
+            x_tm = x.transpose(0, 1).contiguous()
+            got = torch.full_like(want, float("nan"))
+            for t0, t1 in zip(cuts[:-1], cuts[1:]):
+                ops.conv_fwd_range(x_tm, w, None, None, None, None, "none", 1, 1, B, T, got, t0, t1, in_tm=True)
+            assert torch.equal(got, want)
+    for cin, cout, Fin in [(64, 32, 16), (32, 16, 32), (16, 8, 64), (8, 1, 128)]:
+        last = cout == 1
+        x, w, b = rnd(B, T, cin, Fin), rnd(cin, cout, 1, 3) * 0.2, rnd(cout)
+        sc, sh = (None, None) if last else (torch.rand(cout, device=cuda) + 0.5, rnd(cout) * 0.1)
+        skip = None if last else rnd(B, T, cout, 2 * Fin)
+        want = ops.convT_fwd(x, w, b, sc, sh, None, "sigmoid" if last else "relu", skip, 2 * Fin)
+        got = torch.full_like(want, float("nan"))
+        for t0, t1 in zip(cuts[:-1], cuts[1:]):
+            ops.convT_fwd_range(x, w, b, sc, sh, None, "sigmoid" if last else "relu", skip, got, t0, t1)
+        assert torch.equal(got, want), (cin, cout)
+    x, res, g, bt = rnd(B, T, 1024), rnd(B, T, 1024), rnd(1024), rnd(1024)
+    want = ops.layernorm_fwd(x, g, bt, 1e-5, residual=res)
+    got = torch.full_like(want, float("nan"))
+    for t0, t1 in zip(cuts[:-1], cuts[1:]):
+        ops.layernorm_fwd_range(x, g, bt, 1e-5, res, got, t0, t1)
+    assert torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        ops.conv_fwd_range(rnd(B, T, 5, 7), rnd(5, 5, 1, 3), None, None, None, None, "none", 1, 1, B, T, rnd(B, T, 5, 7), 0, T)
+    with pytest.raises(RuntimeError):
+        ops.layernorm_fwd_range(x, g, bt, 1e-5, res, got, 3, 2)

@@ -12,6 +12,8 @@ same ones the oracle makes; they are cited inline.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -209,12 +211,15 @@ class GGRU(nn.Module):
                 # LayerNorm 2 (+ skip4, :51,160) and the decoder follow layer 2 group by group
                 out = torch.empty(B, T, D, device=dev, dtype=torch.float32)
                 groups = around.groups(nch)
-                for j, (k0, k1) in enumerate(groups):      # skip convs: once the layer-1 projections are through (as `side`)
-                    e_skip[j] = around.skips(j, bounds[k0], bounds[k1], eD[nch - 1])
+                sgroups = around.skip_groups(nch)
+                # skip convs: once the layer-1 projections are through (as `side`), in their own (coarser) groups
+                e_skip = [around.skips(j, bounds[k0], bounds[k1], eD[nch - 1]) for j, (k0, k1) in enumerate(sgroups)]
                 with torch.cuda.stream(sE):
                     for j, (k0, k1) in enumerate(groups):
                         t0, t1 = bounds[k0], bounds[k1]
-                        sE.wait_event(e_skip[j])
+                        for (s0, s1), ev_s in zip(sgroups, e_skip):
+                            if s0 < k1 and k0 < s1:
+                                sE.wait_event(ev_s)
                         ops.flag_wait(f_l2[k1 - 1:k1], n_wg, f_err)
                         ops.layernorm_fwd_range(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, around.residual, out, t0, t1)
                         around.decode(j, out, t0, t1)
@@ -360,6 +365,10 @@ class unet_2(nn.Module):
         scale, shift, _, _ = ops.bn_finalize(stats, B * T * F, bn)
         return ops.bn_act_fwd(z, scale, shift, alpha, self.act_kind)
 
+    # developer knobs: chunk indices at which the pipelined decoder / skip convs are cut (default: derived from the chunk count)
+    DECODE_CUTS = [int(v) for v in os.environ.get("CRUSE_DECODE_CUTS", "").split(",") if v]
+    SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
+
     def _forward_frames_pipelined(self, mag, plan, folds):
         """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
         have no time taps at all, so LayerNorm 2 + the decoder (and the skip convs they add) are run per GROUP of wavefront
@@ -397,8 +406,14 @@ class unet_2(nn.Module):
 
             @staticmethod
             def groups(nch):
-                # everything up to three chunks before the end, the next two, the last one
-                cuts = sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
+                # few, large groups (every launch costs ~10 us of set-up and runs beside the recurrences; measured on B200 at
+                # 8 chunks: cuts 0,5,7,8 -> 1.45 ms, 0,4,6,7,8 -> 1.47-1.50, pairs -> 1.53, single chunks -> 1.63, off -> 1.52)
+                cuts = unet.DECODE_CUTS or sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
+                return list(zip(cuts[:-1], cuts[1:]))
+
+            @staticmethod
+            def skip_groups(nch):
+                cuts = unet.SKIP_CUTS or sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
                 return list(zip(cuts[:-1], cuts[1:]))
 
             @staticmethod

@@ -753,7 +753,7 @@ BWD_SIDE_CAP = os.environ.get("CRUSE_BWD_SIDE_CAP", "1") != "0"
 BWD_SIDE_L1 = os.environ.get("CRUSE_BWD_SIDE_L1", "1") != "0"      # layer-1 GRU weight gradients beside the encoder backward
 
 # inference: pipeline the head of the encoder and the tail of the decoder with the GRU wavefront (cruse_net.GGRU._wavefront)
-PIPELINE_EDGES = os.environ.get("CRUSE_PIPELINE_EDGES", "0") != "0"
+PIPELINE_EDGES = os.environ.get("CRUSE_PIPELINE_EDGES", "1") != "0"
 
 # run the skip convs (and the clean-speech STFT) on a low-priority side stream beside the GRU wavefront
 OVERLAP_SKIPS = os.environ.get("CRUSE_OVERLAP_SKIPS", "1") != "0"

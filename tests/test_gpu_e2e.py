@@ -241,6 +241,31 @@ def test_captured_graph_and_wavefront_match_eager(cuda):
     assert rel_err(m2, m0) <= 1e-3 and abs(float(l2) - float(l0)) <= 1e-3 * abs(float(l0))
 
 
+@pytest.mark.parametrize("B,L", [(3, 64000), (32, 32000)])
+def test_pipelined_decoder_schedule_is_bit_identical(cuda, B, L, monkeypatch):
+    """ops.PIPELINE_EDGES: LayerNorm 2, the skip convs and the decoder issued per group of wavefront chunks behind layer 2
+    of the GRU (frame-range entry points) instead of after it -- a scheduling change only: bit-identical loss, mask and
+    waveform, eagerly and through the captured graph; the bounded flag spins never time out."""
+    from cruse_b200 import ops, pipeline
+    ours, _ = _pair(256, "relu", cuda)
+    ours.eval()
+    g = torch.Generator().manual_seed(6)
+    noisy, clean = (0.1 * torch.randn(B, L, generator=g)).to(cuda), (0.05 * torch.randn(B, L, generator=g)).to(cuda)
+    monkeypatch.setattr(ops, "PIPELINE_EDGES", False)
+    with torch.no_grad():
+        l0, w0, e0, m0 = pipeline.forward_loss(ours, noisy, clean, 512, 320)
+    monkeypatch.setattr(ops, "PIPELINE_EDGES", True)
+    with torch.no_grad():
+        l1, w1, e1, m1 = pipeline.forward_loss(ours, noisy, clean, 512, 320)
+    torch.cuda.synchronize()
+    assert int(ours.gru._wavefront_err.item()) == 0
+    assert torch.equal(m0, m1) and torch.equal(l0, l1) and torch.equal(w0, w1)
+    cap = pipeline.CapturedForwardLoss(ours, B, L, 512, 320)
+    l2, w2, e2, m2 = cap(noisy, clean)
+    torch.cuda.synchronize()
+    assert torch.equal(m0, m2) and torch.equal(l0, l2)
+
+
 def test_wavefront_modes_agree_and_no_flag_timeout(cuda):
     """the flag-synchronised wavefront (one recurrence launch per layer, device-side chunk flags) and the relaunch wavefront
     (one launch per chunk, CUDA events) are the same arithmetic in a different schedule: bit-identical masks; the bounded

@@ -82,7 +82,7 @@ class GGRU(nn.Module):
         key = (device.type, device.index)
         if key not in cls._side_streams:
             # the latency-critical recurrence chunks get scheduling priority over whatever runs beside them
-            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(5))
+            cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(8))
         return cls._side_streams[key]
 
     def plan(self, B, T, device):
@@ -122,7 +122,8 @@ class GGRU(nn.Module):
         w_hh2, b_hh2 = [g.weight_hh_l0 for g in g2], [g.bias_hh_l0 for g in g2]
         w_ih2, b_ih2 = [g.weight_ih_l0 for g in g2], [g.bias_ih_l0 for g in g2]
         main = torch.cuda.current_stream(dev)
-        sA, sC, sB, sD, sE = self._streams(dev)
+        sA, sC, sB, sD, sE, *sMore = self._streams(dev)
+        dstreams = (sE, *sMore)                                           # one per decoder group in flight
         w_ih1, b_ih1 = [g.weight_ih_l0 for g in g1], [g.bias_ih_l0 for g in g1]
         if time_major:
             xp1 = torch.empty(T, B, G, 3 * H, device=dev, dtype=torch.float32)
@@ -170,7 +171,7 @@ class GGRU(nn.Module):
         fork.record(main)
         if not flagged:
             around = None
-        for s_ in (sA, sC, sB, sD, sE):
+        for s_ in (sA, sC, sB, sD, *dstreams):
             s_.wait_event(fork)
         e_skip = [None] * nch
         side_ready = None
@@ -214,12 +215,14 @@ class GGRU(nn.Module):
                 sgroups = around.skip_groups(nch)
                 # skip convs: once the layer-1 projections are through (as `side`), in their own (coarser) groups
                 e_skip = [around.skips(j, bounds[k0], bounds[k1], eD[nch - 1]) for j, (k0, k1) in enumerate(sgroups)]
-                with torch.cuda.stream(sE):
-                    for j, (k0, k1) in enumerate(groups):
+                # every group on its own stream: a late group (the first one is the largest) must not hold up the next ones
+                for j, (k0, k1) in enumerate(groups):
+                    sG = dstreams[j % len(dstreams)]
+                    with torch.cuda.stream(sG):
                         t0, t1 = bounds[k0], bounds[k1]
                         for (s0, s1), ev_s in zip(sgroups, e_skip):
                             if s0 < k1 and k0 < s1:
-                                sE.wait_event(ev_s)
+                                sG.wait_event(ev_s)
                         ops.flag_wait(f_l2[k1 - 1:k1], n_wg, f_err)
                         ops.layernorm_fwd_range(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, around.residual, out, t0, t1)
                         around.decode(j, out, t0, t1)
@@ -257,9 +260,10 @@ class GGRU(nn.Module):
         main.wait_event(join)
         if side_ready is not None:
             main.wait_event(side_ready)
-        ev = torch.cuda.Event()
-        ev.record(sE)
-        main.wait_event(ev)
+        for s_ in dstreams:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            main.wait_event(ev)
         if around is not None:
             return out
         return ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)   # :51 (+ skip4, :160)
@@ -369,7 +373,7 @@ class unet_2(nn.Module):
     DECODE_CUTS = [int(v) for v in os.environ.get("CRUSE_DECODE_CUTS", "").split(",") if v]
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
 
-    def _forward_frames_pipelined(self, mag, plan, folds):
+    def _forward_frames_pipelined(self, mag, plan, folds, post=None):
         """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
         have no time taps at all, so LayerNorm 2 + the decoder (and the skip convs they add) are run per GROUP of wavefront
         chunks as soon as layer 2 of the GRU has stored them: behind the last step of the recurrence only the last chunk's
@@ -453,6 +457,9 @@ class unet_2(nn.Module):
                     ops.convT_fwd_range(cur, unet.conv1_t.weight, unet.conv1_t.bias, None, None, None, "sigmoid", None, mask_buf, t0, t1)
                 finally:
                     ops.set_conv_max_ctas(0)
+                if post is not None:                 # what the caller does with the mask (mask*X + iSTFT, loss) follows range by range
+                    post(mask_buf.view(B, T, F), t0, t1)
+                    unet._post_ranges.append((t0, t1))
 
         self.gru.forward_frames(enc[n - 1].view(T, B, D), time_major=True, plan=plan, around=Around)
         ev = torch.cuda.Event()
@@ -460,9 +467,11 @@ class unet_2(nn.Module):
         main.wait_event(ev)
         return mask_buf.view(B, T, F)
 
-    def forward_frames(self, mag, state=None, want_state=False):
+    def forward_frames(self, mag, state=None, want_state=False, post=None):
         """mag [B,T,F] frame-major magnitudes -> mask [B,T,F].  (Internal zero-copy entry used by
         cruse_b200.pipeline; ``forward`` wraps it with the reference's [B,1,T,F] layout.)
+        ``post(mask, t0, t1)``: optional consumer of the mask, called on the stream that has just produced the frames [t0,t1)
+        when the pipelined schedule runs (``self._post_ranges`` lists the ranges it was called for; empty = not called).
         ``state`` (cruse_b200.streaming.StreamState) carries one frame of history per encoder conv and the
         GRU hidden states between chunks of a stream; it is updated in place when ``want_state``."""
         _need_cuda(mag, "unet_2")
@@ -483,8 +492,9 @@ class unet_2(nn.Module):
             names = [f"bn{k}" for k in range(1, n + 1)] + [f"bn{k}_t" for k in range(n, 1, -1)]
             folds = dict(zip(names, ops.bn_fold_many([getattr(self, nm) for nm in names])))
         plan = self.gru.plan(B, T, mag.device) if (overlap and ops.PIPELINE_EDGES) else None
+        self._post_ranges = []
         if plan is not None:
-            return self._forward_frames_pipelined(mag, plan, folds)
+            return self._forward_frames_pipelined(mag, plan, folds, post)
         for k in range(1, n + 1):                                            # :149-152 repaired
             if want_state:
                 new_hist.append(h[:, -1].contiguous())

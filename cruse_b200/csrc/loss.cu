@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, const float* __restrict__ est,
                        cruse_cplx_layout le, const float* __restrict__ unp, cruse_cplx_layout lu,
                        float* __restrict__ dest, float* __restrict__ partials, int T, int F, long long total,
-                       float inv_count, const float* __restrict__ mask) {
+                       float inv_count, const float* __restrict__ mask, int t_begin, int Tc) {
+    // Tc < T: only the frames [t_begin, t_begin + Tc) of every utterance (total = B * Tc * F); the partial sums of several
+    // ranges are added up by sum_partials_kernel
     // mask != NULL: the estimate is mask[b,t,f] * unproc[b,t,f] computed on the fly (PreProcess.masking, utils/utils.py:417-433,
     // fused into the loss so that it does not have to wait for -- and runs beside -- the mask*spectrum + iSTFT kernel)
     const float alpha = 2.f, beta = 1.f;              // loss.py:126-128 (gamma = 1)
@@ -30,12 +32,12 @@ wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, cons
     float acc = 0.f;
     // one (b, t) row of F bins per CTA iteration; (b, t) advance incrementally -- no 64-bit division per element
     const long long rows = total / F;
-    int t = (int)(blockIdx.x % T);
-    long long b = blockIdx.x / T;
+    int t = t_begin + (int)(blockIdx.x % Tc);
+    long long b = blockIdx.x / Tc;
     for (long long bt = blockIdx.x; bt < rows; bt += gridDim.x) {
       const long long rbase = b * lr.sb + t * lr.st, ebase = b * le.sb + t * le.st, ubase = b * lu.sb + t * lu.st;
       for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        const long long i = bt * F + f;
+        const long long i = (b * T + t) * F + f;
         const float2 r = ld_cplx(ref, rbase + f * lr.sf, lr.im_off);
         const long long eoff = ebase + f * le.sf;
         const float2 u = ld_cplx(unp, ubase + f * lu.sf, lu.im_off);
@@ -66,9 +68,9 @@ wo_male_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, cons
             }
         }
       }
-      t += (int)(gridDim.x % T);
-      b += gridDim.x / T;
-      if (t >= T) { t -= T; ++b; }
+      t += (int)(gridDim.x % Tc);
+      b += gridDim.x / Tc;
+      if (t >= t_begin + Tc) { t -= Tc; ++b; }
     }
     __shared__ float sh[LOSS_THREADS / 32];
     acc = warp_sum(acc);
@@ -117,9 +119,40 @@ static int wo_male_launch(const float* ref, cruse_cplx_layout lref, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const double inv = 1.0 / (double)total;
     wo_male_partial_kernel<<<(unsigned)blocks, LOSS_THREADS, 0, st>>>(ref, lref, est, lest, unproc, lunp, dest, (float*)ws, T, F, total,
-                                                                      (float)inv, mask);
+                                                                      (float)inv, mask, 0, T);
     CRUSE_LAUNCH_OK();
     sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)blocks, inv, loss);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+// The masked loss over the frames [t_begin, t_end) of every utterance: nparts partial sums into ws[p_off, p_off + nparts)
+// (no final reduction); cruse_wo_male_finish adds up the partials of all ranges.  Lets the loss follow the decoder range by
+// range instead of waiting for the whole mask.
+extern "C" int cruse_wo_male_masked_partial_range(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
+                                                  cruse_cplx_layout lunp, void* ws, int p_off, int nparts, int B, int T, int F,
+                                                  int t_begin, int t_end, void* stream) {
+    CRUSE_CHECK_ARG(ref && mask && unproc && ws, "wo_male_masked_partial_range: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && F > 0 && t_begin >= 0 && t_begin < t_end && t_end <= T, "wo_male_masked_partial_range: bad sizes B=%d T=%d F=%d range [%d,%d)",
+                    B, T, F, t_begin, t_end);
+    CRUSE_CHECK_ARG(p_off >= 0 && nparts > 0 && p_off + nparts <= LOSS_MAX_PARTS, "wo_male_masked_partial_range: partials [%d,%d) outside the workspace (%d)",
+                    p_off, p_off + nparts, LOSS_MAX_PARTS);
+    const int Tc = t_end - t_begin;
+    long long blocks = (long long)B * Tc;
+    if (blocks > nparts) blocks = nparts;
+    const long long total = (long long)B * Tc * F;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (blocks < nparts)      // fewer rows than partial slots: the unused slots must not hold stale values
+        CRUSE_CUDA_OK(cudaMemsetAsync((float*)ws + p_off + blocks, 0, sizeof(float) * (size_t)(nparts - blocks), st));
+    wo_male_partial_kernel<<<(unsigned)blocks, LOSS_THREADS, 0, st>>>(ref, lref, nullptr, lunp, unproc, lunp, nullptr, (float*)ws + p_off, T, F,
+                                                                      total, 0.f, mask, t_begin, Tc);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_wo_male_finish(const void* ws, int nparts, int B, int T, int F, float* loss, void* stream) {
+    CRUSE_CHECK_ARG(ws && loss && nparts > 0 && nparts <= LOSS_MAX_PARTS && B > 0 && T > 0 && F > 0, "wo_male_finish: bad arguments");
+    sum_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const float*)ws, nparts, 1.0 / ((double)B * T * F), loss);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -216,7 +216,7 @@ stft_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ window,
 __global__ void __launch_bounds__(256)
 mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask, const float* __restrict__ window,
                   float* __restrict__ est_spec, float* __restrict__ wav, int B, int L, int N, int hop, int T,
-                  int mask_bins, int FC, int halo, FftPlan plan) {
+                  int mask_bins, int FC, int halo, FftPlan plan, int c_begin) {
     extern __shared__ float2 sm_[];
     const int M = N >> 1, NF = M + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -224,7 +224,7 @@ mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask
     float2* x = sm_ + N + (size_t)warp * 2 * M;
     float2* y = x + M;
     float* frames = reinterpret_cast<float*>(sm_ + N + (size_t)nwarps * 2 * M);
-    const int b = blockIdx.y, t0 = blockIdx.x * FC, tbeg = t0 - halo, nfr = FC + halo;
+    const int b = blockIdx.y, t0 = (blockIdx.x + c_begin) * FC, tbeg = t0 - halo, nfr = FC + halo;
     build_twiddles(tw, N);
     __syncthreads();
     const float inv_m = 1.0f / (float)M;
@@ -346,8 +346,37 @@ extern "C" int cruse_stft_fwd(const float* wav, const float* window, float* spec
     return 0;
 }
 
+static int istft_chunk_frames(int n_fft, int hop) {
+    const int nwarps = 256 / 32, halo = (n_fft - 1) / hop;
+    const int FC = 2 * nwarps - halo;
+    return FC < 1 ? nwarps : FC;
+}
+
+// frames per CTA of cruse_mask_istft_fwd: CTA c produces est_spec of the frames [c*FC, (c+1)*FC) and the samples they start,
+// reading the mask of the frames [c*FC - (n_fft-1)/hop, (c+1)*FC)
+extern "C" int cruse_mask_istft_chunk_frames(int n_fft, int hop) {
+    if (n_fft < 4 || hop <= 0 || hop > n_fft) return -1;
+    return istft_chunk_frames(n_fft, hop);
+}
+
+static int mask_istft_launch(const float* spec, const float* mask, const float* window, float* est_spec, float* wav, int B, int L,
+                             int n_fft, int hop, int T, int mask_bins, int c_begin, int c_end, void* stream);
+
+// the CTAs [c_begin, c_end) of cruse_mask_istft_fwd only (c_end <= ceil(T / chunk_frames)): lets mask*X + iSTFT follow the
+// decoder range by range; the union of disjoint CTA ranges covering [0, ceil(T/FC)) is bit-identical to the whole call
+extern "C" int cruse_mask_istft_fwd_range(const float* spec, const float* mask, const float* window, float* est_spec,
+                                          float* wav, int B, int L, int n_fft, int hop, int T, int mask_bins, int c_begin,
+                                          int c_end, void* stream) {
+    return mask_istft_launch(spec, mask, window, est_spec, wav, B, L, n_fft, hop, T, mask_bins, c_begin, c_end, stream);
+}
+
 extern "C" int cruse_mask_istft_fwd(const float* spec, const float* mask, const float* window, float* est_spec,
                                     float* wav, int B, int L, int n_fft, int hop, int T, int mask_bins, void* stream) {
+    return mask_istft_launch(spec, mask, window, est_spec, wav, B, L, n_fft, hop, T, mask_bins, 0, -1, stream);
+}
+
+static int mask_istft_launch(const float* spec, const float* mask, const float* window, float* est_spec, float* wav, int B, int L,
+                             int n_fft, int hop, int T, int mask_bins, int c_begin, int c_end, void* stream) {
     CRUSE_CHECK_ARG(spec && window, "mask_istft_fwd: null pointer");
     CRUSE_CHECK_ARG(est_spec || wav, "mask_istft_fwd: nothing to compute");
     CRUSE_CHECK_ARG(B > 0 && T > 0 && hop > 0 && n_fft >= 4 && (n_fft % 2) == 0 && hop <= n_fft, "mask_istft_fwd: bad sizes");
@@ -362,9 +391,12 @@ extern "C" int cruse_mask_istft_fwd(const float* spec, const float* mask, const 
     const size_t smem = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * n_fft) + sizeof(float) * (size_t)(FC + halo) * n_fft;
     CRUSE_CHECK_ARG(smem <= 220 * 1024, "mask_istft_fwd: n_fft=%d / hop=%d need too much shared memory", n_fft, hop);
     CRUSE_CUDA_OK(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((T + FC - 1) / FC, B);
+    const int nchunks = (T + FC - 1) / FC;
+    if (c_end < 0) c_end = nchunks;
+    CRUSE_CHECK_ARG(c_begin >= 0 && c_begin < c_end && c_end <= nchunks, "mask_istft_fwd: CTA range [%d,%d) outside [0,%d)", c_begin, c_end, nchunks);
+    dim3 grid(c_end - c_begin, B);
     mask_istft_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(spec, mask_bins > 0 ? mask : nullptr, window, est_spec, wav, B, L,
-                                                                    n_fft, hop, T, mask_bins, FC, halo, plan);
+                                                                    n_fft, hop, T, mask_bins, FC, halo, plan, c_begin);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -71,6 +71,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def check_nonneg(rc, what):
+    if rc < 0:
+        check(rc, what)
+    return rc
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -134,6 +140,18 @@ def mask_istft_fwd(spec, mask, window, n_fft, hop, length, want_est=True, want_w
                                      n_fft, hop, T, mask_bins, _stream(),
           meta=(f"mask_istft n{n_fft} h{hop}", _nb(spec, mask, est, wav), int(B * T * 2.5 * n_fft * 9) if want_wav else 0))
     return est, wav
+
+
+def mask_istft_chunk_frames(n_fft, hop):
+    return check_nonneg(lib().cruse_mask_istft_chunk_frames(n_fft, hop), "cruse_mask_istft_chunk_frames")
+
+
+def mask_istft_fwd_range(spec, mask, window, n_fft, hop, est, wav, c0, c1):
+    """the CTAs [c0, c1) of mask_istft_fwd (each covers mask_istft_chunk_frames frames) into the full-size est / wav."""
+    B, T, NF, _ = spec.shape
+    mask_bins = mask.shape[-1]
+    _call("cruse_mask_istft_fwd_range", _p(spec), _p(mask), _p(window), _p(est), _p(wav), B, wav.shape[-1], n_fft, hop, T, mask_bins,
+          c0, c1, _stream(), meta=(f"mask_istft n{n_fft} h{hop} ctas[{c0},{c1})", 0, 0))
 
 
 def mask_bwd(dest, spec, mask_bins, gscale=None, mask=None):
@@ -568,6 +586,22 @@ def wo_male_masked_fwd(ref, lref, mask, unp, lunp, B, T, F):
     _call("cruse_wo_male_masked_fwd", _p(ref), lref, _p(mask), _p(unp), lunp, _p(loss), _p(ws), B, T, F, _stream(),
           meta=("wo_male[mask fused]", B * T * F * (8 * 2 + 4), 30 * B * T * F))
     return loss
+
+
+def wo_male_masked_partial_range(ref, lref, mask, unp, lunp, ws, p_off, nparts, B, T, F, t0, t1):
+    """partial sums of the masked loss over the frames [t0, t1) into ws[p_off, p_off + nparts)."""
+    _call("cruse_wo_male_masked_partial_range", _p(ref), lref, _p(mask), _p(unp), lunp, _p(ws), p_off, nparts, B, T, F, t0, t1, _stream(),
+          meta=(f"wo_male[mask fused] [{t0},{t1})", B * (t1 - t0) * F * (8 * 2 + 4), 30 * B * (t1 - t0) * F))
+
+
+def wo_male_finish(ws, nparts, B, T, F):
+    loss = torch.empty((), device=ws.device, dtype=torch.float32)
+    _call("cruse_wo_male_finish", _p(ws), nparts, B, T, F, _p(loss), _stream())
+    return loss
+
+
+def loss_workspace(device):
+    return _loss_ws(device)
 
 
 # ------------------------------------------------------------------------------------------

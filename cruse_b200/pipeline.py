@@ -41,7 +41,43 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         with torch.cuda.stream(side):
             S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
             S.record_stream(main)
-        mask = model.forward_frames(mag)                                                        # cruse_net.py:147-165
+        # Pipelined schedule (ops.PIPELINE_EDGES): the decoder hands the mask over range by range; mask*X + iSTFT and the loss
+        # follow on the side stream, so that only the last range of both is left after the last decoder launch.
+        T = X.shape[1]
+        FC = ops.mask_istft_chunk_frames(n_fft, hop)
+        nct = (T + FC - 1) // FC
+        window = hann_window(n_fft, n_fft, dev)
+        est_buf = torch.empty_like(X)
+        wav_buf = torch.empty(noisy.shape[0], noisy.shape[-1], device=dev, dtype=torch.float32)
+        ws = ops.loss_workspace(dev)
+        lay_s, lay_x = ops.layout_btf2(S), ops.layout_btf2(X)
+        prog = {"c": 0, "p": 0}
+
+        def post(mask_all, t0, t1):
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                c1 = nct if t1 >= T else t1 // FC
+                if c1 > prog["c"]:
+                    ops.mask_istft_fwd_range(X, mask_all, window, n_fft, hop, est_buf, wav_buf, prog["c"], c1)
+                    prog["c"] = c1
+                nparts = max(1, ws.numel() * (t1 - t0) // T)
+                ops.wo_male_masked_partial_range(S, lay_s, mask_all, X, lay_x, ws, prog["p"], nparts, X.shape[0], T, F, t0, t1)
+                prog["p"] += nparts
+
+        mask = model.forward_frames(mag, post=post) if ops.PIPELINE_EDGES else model.forward_frames(mag)   # cruse_net.py:147-165
+        ranges = getattr(model, "_post_ranges", [])
+        if ranges and ranges[0][0] == 0 and ranges[-1][1] == T and prog["c"] == nct:
+            with torch.cuda.stream(side):
+                loss = ops.wo_male_finish(ws, prog["p"], X.shape[0], T, F)
+                done = torch.cuda.Event()
+                done.record(side)
+            loss.record_stream(main)                     # made on the side stream, handed to the caller's
+            for t_ in (est_buf, wav_buf, ws):            # made on the caller's stream, written on the side stream
+                t_.record_stream(side)
+            main.wait_event(done)
+            return loss, wav_buf, est_buf, mask
         have_mask = torch.cuda.Event()
         have_mask.record(main)
         with torch.cuda.stream(side):

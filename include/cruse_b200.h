@@ -62,6 +62,12 @@ int cruse_stft_fwd(const float* wav, const float* window, float* spec, float* ma
 int cruse_mask_istft_fwd(const float* spec, const float* mask, const float* window,
                          float* est_spec, float* wav,
                          int B, int L, int n_fft, int hop, int T, int mask_bins, void* stream);
+/* The CTAs [c_begin, c_end) of the same launch: CTA c produces est_spec of the frames [c*FC, (c+1)*FC) and the samples
+ * those frames start, reading the mask of the frames [c*FC - (n_fft-1)/hop, (c+1)*FC), FC = cruse_mask_istft_chunk_frames.
+ * Disjoint ranges covering [0, ceil(T/FC)) are bit-identical to the whole call. */
+int cruse_mask_istft_chunk_frames(int n_fft, int hop);
+int cruse_mask_istft_fwd_range(const float* spec, const float* mask, const float* window, float* est_spec, float* wav,
+                               int B, int L, int n_fft, int hop, int T, int mask_bins, int c_begin, int c_end, void* stream);
 
 /* backward of the mask apply: dmask[b,t,f] = gscale * (dre*Xre + dim*Xim), f < mask_bins.
  * dest [B,T,NF,2] (row stride NF) ; gscale: device scalar or NULL (=1).  mask [B,T,mask_bins] or NULL: when given
@@ -223,6 +229,14 @@ int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float*
 int cruse_wo_male_masked_fwd(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
                              cruse_cplx_layout lunp, float* loss, void* ws, int B, int T, int F, void* stream);
 size_t cruse_wo_male_ws_bytes(void);
+/* The same loss range by range (inference schedule: the loss follows the decoder instead of waiting for the whole mask):
+ * _partial_range writes nparts partial sums of the frames [t_begin, t_end) of every utterance into ws[p_off, p_off+nparts),
+ * cruse_wo_male_finish adds up the nparts partials of all ranges and divides by B*T*F (loss.py:147).  Same arithmetic per
+ * bin as cruse_wo_male_masked_fwd; the summation order differs, so the value agrees to fp32 rounding (1e-6), not bitwise. */
+int cruse_wo_male_masked_partial_range(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
+                                       cruse_cplx_layout lunp, void* ws, int p_off, int nparts, int B, int T, int F,
+                                       int t_begin, int t_end, void* stream);
+int cruse_wo_male_finish(const void* ws, int nparts, int B, int T, int F, float* loss, void* stream);
 
 /* =====================================================================================================
  * a9: backward of a2-a8 (what autograd + cuDNN/ATen compute on the reference path for the modules of

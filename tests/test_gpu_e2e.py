@@ -244,8 +244,9 @@ def test_captured_graph_and_wavefront_match_eager(cuda):
 @pytest.mark.parametrize("B,L", [(3, 64000), (32, 32000)])
 def test_pipelined_decoder_schedule_is_bit_identical(cuda, B, L, monkeypatch):
     """ops.PIPELINE_EDGES: LayerNorm 2, the skip convs and the decoder issued per group of wavefront chunks behind layer 2
-    of the GRU (frame-range entry points) instead of after it -- a scheduling change only: bit-identical loss, mask and
-    waveform, eagerly and through the captured graph; the bounded flag spins never time out."""
+    of the GRU (frame-range entry points) instead of after it, with mask*X + iSTFT and the loss following range by range -- a
+    scheduling change only: bit-identical mask, spectrum and waveform (loss to summation order), eagerly and through the
+    captured graph; the bounded flag spins never time out."""
     from cruse_b200 import ops, pipeline
     ours, _ = _pair(256, "relu", cuda)
     ours.eval()
@@ -259,11 +260,13 @@ def test_pipelined_decoder_schedule_is_bit_identical(cuda, B, L, monkeypatch):
         l1, w1, e1, m1 = pipeline.forward_loss(ours, noisy, clean, 512, 320)
     torch.cuda.synchronize()
     assert int(ours.gru._wavefront_err.item()) == 0
-    assert torch.equal(m0, m1) and torch.equal(l0, l1) and torch.equal(w0, w1)
+    # mask, enhanced spectrum and waveform: bit-identical; the loss is summed range by range (different order): 1e-6
+    assert torch.equal(m0, m1) and torch.equal(w0, w1) and torch.equal(e0, e1)
+    assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
     cap = pipeline.CapturedForwardLoss(ours, B, L, 512, 320)
     l2, w2, e2, m2 = cap(noisy, clean)
     torch.cuda.synchronize()
-    assert torch.equal(m0, m2) and torch.equal(l0, l2)
+    assert torch.equal(m0, m2) and torch.equal(l1, l2) and torch.equal(w0, w2) and torch.equal(e0, e2)
 
 
 def test_wavefront_modes_agree_and_no_flag_timeout(cuda):

@@ -16,12 +16,22 @@ from . import ops
 # ------------------------------------------------------------------------------------------------
 # grouped-GRU layer
 # ------------------------------------------------------------------------------------------------
-def gru_layer_fwd_train(x2d, grus, B, T, interleave):
-    """x2d [B*T, G*H] -> (y [B,T,G*H], saved)"""
+def gru_layer_fwd_train(x2d, grus, B, T, interleave, side=None, beside=None):
+    """x2d [B*T, G*H] -> (y [B,T,G*H], saved); ``beside(after_event)`` queues side work next to the recurrence (which
+    occupies 8*G*ceil(B/32) SMs) -- called right after the recurrence has been launched on a high-priority stream, see
+    _SideWork.critical"""
     w_ih = [g.weight_ih_l0 for g in grus]
     xproj = ops.gru_ih_gemm(x2d, w_ih, [g.bias_ih_l0 for g in grus], [g.bias_hh_l0 for g in grus], mode="tf32")
-    y, gates = ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
-                               interleave=interleave, mode="tf32", want_gates=True)
+    run = lambda: ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
+                                  interleave=interleave, mode="tf32", want_gates=True)
+    if side is not None and side.enabled and beside is not None:
+        ready = side.mark()
+        y, gates = side.critical(run, ready)
+        beside(ready)
+    else:
+        y, gates = run()
+        if beside is not None:
+            beside(None)
     return y, (x2d, y, gates)
 
 
@@ -183,7 +193,7 @@ class _Unet2Fn(torch.autograd.Function):
         train = m.training
         sv = {}
         h = mag.view(B, T, 1, F)
-        enc_in, enc_z, enc_bn, skips = [], [], [], []
+        enc_in, enc_z, enc_bn, skips, enc_out = [], [], [], [], []
         for k in range(1, n + 1):                                                    # cruse_net.py:149-156
             conv, bn = getattr(m, f"conv{k}"), getattr(m, f"bn{k}")
             alpha = m._alpha(f"act{k}")
@@ -198,15 +208,29 @@ class _Unet2Fn(torch.autograd.Function):
             h = ops.bn_act_fwd(z, scale, shift, alpha, act)
             enc_z.append(z)
             enc_bn.append((scale, shift, mean, invstd))
-            skips.append(ops.conv_fwd(h, getattr(m, f"skip_connect_{k}").weight, None, None, None, None, "none", 1, 1))
+            enc_out.append(h)
         e4 = h
+        # the four skip convs (:153-156) run beside the layer-1 recurrence (64 of 148 SMs busy) on the side stream
+        side = _SideWork(mag.device, ops.OVERLAP_BWD)
+        cap = 0
+        if side.enabled and ops.BWD_SIDE_CAP:
+            free_sms = torch.cuda.get_device_properties(mag.device).multi_processor_count - 8 * len(m.gru.gru_list1) * ((B + 31) // 32)
+            cap = free_sms if free_sms >= 32 else 0
+
+        def skip_convs():
+            return [ops.conv_fwd(enc_out[k - 1], getattr(m, f"skip_connect_{k}").weight, None, None, None, None, "none", 1, 1)
+                    for k in range(1, n + 1)]
+
+        def beside(ev):
+            skips.extend(side.run(skip_convs, *enc_out, after=ev, max_ctas=cap))
         C4, F4 = e4.shape[2], e4.shape[3]
         D = C4 * F4
         gru = m.gru
         x2d = e4.view(B * T, D)
-        y1, sv1 = gru_layer_fwd_train(x2d, gru.gru_list1, B, T, True)                # :42-45
+        y1, sv1 = gru_layer_fwd_train(x2d, gru.gru_list1, B, T, True, side=side, beside=beside)   # :42-45
         z1, mean1, rstd1 = ops.layernorm_fwd(y1, gru.ln1.weight, gru.ln1.bias, gru.ln1.eps, want_stats=True)
         y2, sv2 = gru_layer_fwd_train(z1.view(B * T, D), gru.gru_list2, B, T, False)  # :48-50
+        side.join()
         out, mean2, rstd2 = ops.layernorm_fwd(y2, gru.ln2.weight, gru.ln2.bias, gru.ln2.eps,
                                               residual=skips[-1].view(B, T, D), want_stats=True)   # :51,160
         out = out.view(B, T, C4, F4)

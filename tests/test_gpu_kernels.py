@@ -440,3 +440,41 @@ def test_frame_range_entries_equal_whole_tensor_calls(cuda, B, T, cuts):
         ops.conv_fwd_range(rnd(B, T, 5, 7), rnd(5, 5, 1, 3), None, None, None, None, "none", 1, 1, B, T, rnd(B, T, 5, 7), 0, T)
     with pytest.raises(RuntimeError):
         ops.layernorm_fwd_range(x, g, bt, 1e-5, res, got, 3, 2)
+
+
+@pytest.mark.parametrize("n_fft,hop,B,L", [(512, 320, 3, 16000), (320, 160, 2, 8000)])
+def test_mask_istft_and_loss_range_entries(cuda, n_fft, hop, B, L):
+    """cruse_mask_istft_fwd_range (CTA ranges) is bit-identical to the whole launch; cruse_wo_male_masked_partial_range +
+    cruse_wo_male_finish give the whole-tensor loss to summation order (1e-6), incl. ranges with fewer rows than partial slots."""
+    from cruse_b200 import acoustics, ops
+    torch.manual_seed(43)
+    F = n_fft // 2
+    y, c = 0.1 * torch.randn(B, L, device=cuda), 0.05 * torch.randn(B, L, device=cuda)
+    X, _ = acoustics.stft_frames(y, n_fft, hop, n_fft, mag_bins=F)
+    S, _ = acoustics.stft_frames(c, n_fft, hop, n_fft)
+    T = X.shape[1]
+    mask = torch.rand(B, T, F, device=cuda)
+    win = acoustics.hann_window(n_fft, n_fft, cuda)
+    est0, wav0 = ops.mask_istft_fwd(X, mask, win, n_fft, hop, L)
+    FC = ops.mask_istft_chunk_frames(n_fft, hop)
+    nct = (T + FC - 1) // FC
+    est1, wav1 = torch.full_like(est0, float("nan")), torch.full_like(wav0, float("nan"))
+    cuts = sorted({0, 1, nct // 2, nct})
+    for c0, c1 in zip(cuts[:-1], cuts[1:]):
+        ops.mask_istft_fwd_range(X, mask, win, n_fft, hop, est1, wav1, c0, c1)
+    assert torch.equal(est0, est1) and torch.equal(wav0, wav1)
+    want = ops.wo_male_masked_fwd(S, ops.layout_btf2(S), mask, X, ops.layout_btf2(X), B, T, F)
+    ws = ops.loss_workspace(cuda)
+    ws.fill_(float("nan"))
+    p = 0
+    tcuts = sorted({0, 1, T // 3, T})
+    for t0, t1 in zip(tcuts[:-1], tcuts[1:]):
+        n = max(1, ws.numel() * (t1 - t0) // T)
+        ops.wo_male_masked_partial_range(S, ops.layout_btf2(S), mask, X, ops.layout_btf2(X), ws, p, n, B, T, F, t0, t1)
+        p += n
+    got = ops.wo_male_finish(ws, p, B, T, F)
+    assert abs(float(got) - float(want)) <= 1e-6 * abs(float(want))
+    with pytest.raises(RuntimeError):
+        ops.mask_istft_fwd_range(X, mask, win, n_fft, hop, est1, wav1, 0, nct + 1)
+    with pytest.raises(RuntimeError):
+        ops.wo_male_masked_partial_range(S, ops.layout_btf2(S), mask, X, ops.layout_btf2(X), ws, ws.numel(), 1, B, T, F, 0, T)

@@ -4,7 +4,8 @@ import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CALL_OF = {"gru_seq_tc_kernel": ["gru_seq_flagged_tc", "gru_seq_fwd_tc"], "gemm_tn_tc_kernel": ["gru_ih_gemm_tc"],
-           "layernorm_fwd_kernel": ["layernorm_fwd"], "stft_fwd_kernel": ["stft_fwd"], "mask_istft_kernel": ["mask_istft_fwd"]}
+           "layernorm_fwd_kernel": ["layernorm_fwd"], "stft_fwd_kernel": ["stft_fwd"], "mask_istft_kernel": ["mask_istft_fwd"],
+           "gru_bwd_tc_kernel": ["gru_seq_bwd_tc"]}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
 for rep in sys.argv[1:]:

@@ -373,7 +373,7 @@ class unet_2(nn.Module):
     DECODE_CUTS = [int(v) for v in os.environ.get("CRUSE_DECODE_CUTS", "").split(",") if v]
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
 
-    def _forward_frames_pipelined(self, mag, plan, folds, post=None):
+    def _forward_frames_pipelined(self, mag, plan, folds, post=None, after_encoder=None):
         """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
         have no time taps at all, so LayerNorm 2 + the decoder (and the skip convs they add) are run per GROUP of wavefront
         chunks as soon as layer 2 of the GRU has stored them: behind the last step of the recurrence only the last chunk's
@@ -429,6 +429,9 @@ class unet_2(nn.Module):
 
             @staticmethod
             def skips(j, t0, t1, after):                                                         # :153-156
+                if j == 0 and after_encoder is not None:
+                    after_encoder(after)             # the caller's off-path work starts with the skip convs: once the layer-1
+                                                     # projections are through, so that it takes no SMs from what gates layer 1
                 s_skip.wait_event(after)
                 ops.set_conv_max_ctas(max(32, sms - 2 * layer_sms))
                 try:
@@ -467,11 +470,14 @@ class unet_2(nn.Module):
         main.wait_event(ev)
         return mask_buf.view(B, T, F)
 
-    def forward_frames(self, mag, state=None, want_state=False, post=None):
+    def forward_frames(self, mag, state=None, want_state=False, post=None, after_encoder=None):
         """mag [B,T,F] frame-major magnitudes -> mask [B,T,F].  (Internal zero-copy entry used by
         cruse_b200.pipeline; ``forward`` wraps it with the reference's [B,1,T,F] layout.)
         ``post(mask, t0, t1)``: optional consumer of the mask, called on the stream that has just produced the frames [t0,t1)
         when the pipelined schedule runs (``self._post_ranges`` lists the ranges it was called for; empty = not called).
+        ``after_encoder(event=None)``: optional hook called once the encoder stages (pipelined schedule: and the layer-1 input
+        projections, ``event``) have been queued -- work the caller wants to start behind them rather than beside them, e.g.
+        the clean-speech STFT of the loss.
         ``state`` (cruse_b200.streaming.StreamState) carries one frame of history per encoder conv and the
         GRU hidden states between chunks of a stream; it is updated in place when ``want_state``."""
         _need_cuda(mag, "unet_2")
@@ -494,7 +500,7 @@ class unet_2(nn.Module):
         plan = self.gru.plan(B, T, mag.device) if (overlap and ops.PIPELINE_EDGES) else None
         self._post_ranges = []
         if plan is not None:
-            return self._forward_frames_pipelined(mag, plan, folds, post)
+            return self._forward_frames_pipelined(mag, plan, folds, post, after_encoder)
         for k in range(1, n + 1):                                            # :149-152 repaired
             if want_state:
                 new_hist.append(h[:, -1].contiguous())
@@ -512,6 +518,8 @@ class unet_2(nn.Module):
                 skips.append(ops.conv_fwd(h, getattr(self, f"skip_connect_{k}").weight, None, None, None, None,
                                           "none", 1, 1))                                             # :153-156
         e4 = enc[-1]
+        if after_encoder is not None:
+            after_encoder()
         C4, F4 = e4.shape[2], e4.shape[3]
         D = C4 * F4
         side = None

@@ -121,6 +121,16 @@ def stft_fwd(wav, window, n_fft, hop, pad_mode="reflect", mag_bins=0, mag_eps=1e
     return spec, mag
 
 
+def stft_fwd_into(wav, window, spec, n_fft, hop, pad_mode="reflect"):
+    """STFT of wav [B,L] into a preallocated spec [B,T,NF,2] (no allocation: queued on a side stream)."""
+    B, L = wav.shape
+    T = 1 + L // hop
+    if tuple(spec.shape) != (B, T, n_fft // 2 + 1, 2):
+        raise RuntimeError(f"stft_fwd_into: spec shape {tuple(spec.shape)} != {(B, T, n_fft // 2 + 1, 2)}")
+    _call("cruse_stft_fwd", _p(wav.contiguous()), _p(window), _p(spec), None, B, L, n_fft, hop, T, PAD[pad_mode], 0, 1e-8, _stream(),
+          meta=(f"stft n{n_fft} h{hop}", _nb(wav, spec), int(B * T * 2.5 * n_fft * 9)))
+
+
 def mask_istft_fwd(spec, mask, window, n_fft, hop, length, want_est=True, want_wav=True):
     """spec [B,T,NF,2] (* mask [B,T,Fm]) -> (est_spec | None, wav [B,length] | None).  utils.py:417-454."""
     _req(spec, "spec", 4)

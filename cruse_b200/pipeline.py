@@ -35,12 +35,22 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
         X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)   # feature.py:10-30, utils.py:400
-        fork = torch.cuda.Event()
-        fork.record(main)
-        side.wait_event(fork)
-        with torch.cuda.stream(side):
-            S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
-            S.record_stream(main)
+        # the clean-speech STFT is only needed by the loss: it is released behind the encoder and the layer-1 input projections
+        # (not beside them, where it would take SMs from what gates the recurrence) and runs beside the GRU; its output buffer
+        # exists up front because the loss launches that read it are queued while the model runs
+        S = torch.empty_like(X)
+        S.record_stream(side)
+        clean_started = []
+
+        def start_clean_stft(after=None):
+            fork = after
+            if fork is None:
+                fork = torch.cuda.Event()
+                fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                ops.stft_fwd_into(clean, hann_window(n_fft, n_fft, dev), S, n_fft, hop, pad_mode)
+            clean_started.append(True)
         # Pipelined schedule (ops.PIPELINE_EDGES): the decoder hands the mask over range by range; mask*X + iSTFT and the loss
         # follow on the side stream, so that only the last range of both is left after the last decoder launch.
         T = X.shape[1]
@@ -66,7 +76,13 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 ops.wo_male_masked_partial_range(S, lay_s, mask_all, X, lay_x, ws, prog["p"], nparts, X.shape[0], T, F, t0, t1)
                 prog["p"] += nparts
 
-        mask = model.forward_frames(mag, post=post) if ops.PIPELINE_EDGES else model.forward_frames(mag)   # cruse_net.py:147-165
+        if ops.PIPELINE_EDGES:
+            mask = model.forward_frames(mag, post=post, after_encoder=start_clean_stft)             # cruse_net.py:147-165
+        else:
+            start_clean_stft()
+            mask = model.forward_frames(mag)
+        if not clean_started:
+            raise RuntimeError("forward_loss: the model did not call after_encoder()")
         ranges = getattr(model, "_post_ranges", [])
         if ranges and ranges[0][0] == 0 and ranges[-1][1] == T and prog["c"] == nct:
             with torch.cuda.stream(side):

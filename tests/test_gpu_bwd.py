@@ -474,3 +474,39 @@ def test_single_channel_stage_gradients_streaming_kernels(cuda, B, T, Fin, mode)
     din = ops.convT_dgrad(_to_frames(gy).to(cuda), convt.weight.detach().to(cuda), (B, T, 8, Fi))
     assert rel_err(din, _to_frames(xi.grad)) <= 1e-4
     ops.set_conv_mode("tf32")
+
+
+def test_train_step_with_fused_adam_reduces_the_loss(cuda):
+    """trainer.TrainStep (captured step + flat-buffer clip + fused Adam, the shape of base_trainer.py:378-430): on a fixed batch
+    the loss goes down over a few updates, the clip bounds the global gradient norm, and the update equals what eager autograd +
+    clip_grad_norm_ + Adam gives on an identical model (one step, 1e-4)."""
+    from cruse_b200 import pipeline, trainer
+    from cruse_b200.cruse_net import unet_2
+    from oracle import cruse_oracle as o
+    B, L = 4, 8000
+    torch.manual_seed(7)
+    a = unet_2(in_feat=256).to(cuda).train()
+    b = unet_2(in_feat=256).to(cuda).train()
+    b.load_state_dict(a.state_dict())
+    noisy, clean = o.synth_batch(B, L, 3)
+    noisy, clean = noisy.to(cuda), clean.to(cuda)
+    ts = trainer.TrainStep(a, B, L, lr=1e-3, max_grad_norm=0.5)
+    # eager twin: one step
+    opt = torch.optim.Adam([p for p in b.parameters() if p.requires_grad], lr=1e-3)
+    loss_b = pipeline.train_forward_loss(b, noisy, clean)
+    loss_b.backward()
+    torch.nn.utils.clip_grad_norm_([p for p in b.parameters() if p.grad is not None], 0.5)
+    opt.step()
+    l0 = float(ts.step(noisy, clean))
+    assert abs(l0 - float(loss_b)) <= 1e-5 * abs(l0)
+    # the first Adam step moves every element by ~lr * sign(g): elements whose gradient is rounding noise (conv biases in front
+    # of a train-mode BatchNorm, bins at |g| ~ 1e-9) may go the other way, so the bound is on the tensor mean, in units of lr
+    for (name, pa), pb in zip(a.named_parameters(), b.parameters()):
+        if pb.grad is None:
+            continue
+        assert float((pa - pb).abs().max()) <= 2.5e-3, name
+        if float(pb.grad.abs().mean()) > 1e-6:
+            assert float((pa - pb).abs().mean()) <= 5e-5, (name, float((pa - pb).abs().mean()))
+    losses = [l0] + [float(ts.step(noisy, clean)) for _ in range(5)]
+    assert losses[-1] < losses[0], losses
+    assert all(l == l for l in losses)                                            # no NaN

@@ -306,7 +306,10 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
 
         // x-projections are streamed from HBM PF steps ahead of their use (a step is shorter than a DRAM round trip, and
         // the skip convs / input projections running beside the recurrence load the memory system)
-        constexpr int PF = 4;
+#ifndef CRUSE_SEQ_PF
+#define CRUSE_SEQ_PF 4
+#endif
+        constexpr int PF = CRUSE_SEQ_PF;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 xq_r[PF], xq_z[PF], xq_n[PF];                          // queue: [0] = current step, [PF-1] = newest prefetch
         int kw = 0, kd = 0;                                           // next chunk to wait for / to report

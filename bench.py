@@ -313,6 +313,10 @@ def run_ours(args):
     # ---- e2e: host buffers in, loss out, copies inside the timed region
     for _ in range(2):
         step_host()
+    if captured is not None:              # the prefetch path captures one graph per staging pair on first use: outside the timed region
+        for _ in range(2):
+            out = captured.run_prefetched(captured.prefetch(noisy_h, clean_h))
+        (out if train else out[0]).to("cpu")
     barrier()
     t0 = time.perf_counter()
     if captured is not None:
@@ -337,7 +341,7 @@ def run_ours(args):
     e2e = {"value": frames * world * args.steps / float(t.item()), "unit": "frames/s",
            "h2d_bytes_per_step": int(noisy_h.numel() * 4 + clean_h.numel() * 4), "d2h_bytes_per_step": 4,
            "ms_per_step": 1e3 * float(t.item()) / args.steps,
-           "how": ("pipeline.CapturedForwardLoss.prefetch/run_prefetched: pinned H2D of step i+1 on a copy stream under the replay of step i, loss .to(cpu) every step"
+           "how": ("pipeline.CapturedForwardLoss.prefetch/run_prefetched: pinned H2D of step i+1 on a copy stream (into the staging pair the next replay reads in place) under the replay of step i, loss .to(cpu) every step"
                    if captured is not None else "forward_loss_host: H2D, launches, loss .to(cpu) back to back")}
 
     # ---- per-kernel device times of one step (CUDA events on the launching stream) -> roofline

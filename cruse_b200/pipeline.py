@@ -200,14 +200,37 @@ class CapturedForwardLoss:
             self._ready[i].record(st)
         return i
 
+    def _stage_graph(self, ticket):
+        """a second / third capture of the same step that reads staging pair ``ticket`` in place (no device-to-device copy of
+        the inputs per step); shares the memory pool of the first graph -- the graphs never run concurrently"""
+        if not hasattr(self, "_stage_graphs"):
+            self._stage_graphs = {}
+        if ticket not in self._stage_graphs:
+            n_fft, hop, pad_mode = self.args
+            nz, cl = self._stage[ticket]
+            torch.cuda.synchronize(self.noisy.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.graph.pool()), torch.no_grad():
+                outs = forward_loss(self.model, nz, cl, n_fft, hop, pad_mode)
+            self._stage_graphs[ticket] = (g, outs)
+        return self._stage_graphs[ticket]
+
     def run_prefetched(self, ticket):
         main = torch.cuda.current_stream(self.noisy.device)
+        if type(self) is CapturedForwardLoss and self.IN_PLACE_STAGING:
+            g, outs = self._stage_graph(ticket)                          # (captured on first use, outside any timed region)
+            main.wait_event(self._ready[ticket])
+            g.replay()
+            self._consumed[ticket].record(main)
+            return outs
         main.wait_event(self._ready[ticket])
         self.noisy.copy_(self._stage[ticket][0], non_blocking=True)     # device-to-device, ~30 us for 2 x 20 MB
         self.clean.copy_(self._stage[ticket][1], non_blocking=True)
         self._consumed[ticket].record(main)
         self.graph.replay()
         return self.loss, self.wav, self.est, self.mask
+
+    IN_PLACE_STAGING = True
 
 
 class CapturedTrainStep(CapturedForwardLoss):

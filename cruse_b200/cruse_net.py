@@ -372,6 +372,7 @@ class unet_2(nn.Module):
     # developer knobs: chunk indices at which the pipelined decoder / skip convs are cut (default: derived from the chunk count)
     DECODE_CUTS = [int(v) for v in os.environ.get("CRUSE_DECODE_CUTS", "").split(",") if v]
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
+    SIDE_CAP = int(os.environ.get("CRUSE_SIDE_CAP", "0"))     # CTAs of the persistent side kernels (0 = the SMs the recurrences leave free)
 
     def _forward_frames_pipelined(self, mag, plan, folds, post=None, after_encoder=None):
         """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
@@ -425,6 +426,8 @@ class unet_2(nn.Module):
                 # persistent grids sized to the SMs the recurrences leave free: both layers busy / layer 2 only / nothing
                 if j == ngroups - 1:
                     return 0
+                if unet.SIDE_CAP:
+                    return unet.SIDE_CAP
                 return max(32, sms - (2 if j < ngroups - 2 else 1) * layer_sms)
 
             @staticmethod
@@ -433,7 +436,7 @@ class unet_2(nn.Module):
                     after_encoder(after)             # the caller's off-path work starts with the skip convs: once the layer-1
                                                      # projections are through, so that it takes no SMs from what gates layer 1
                 s_skip.wait_event(after)
-                ops.set_conv_max_ctas(max(32, sms - 2 * layer_sms))
+                ops.set_conv_max_ctas(unet.SIDE_CAP or max(32, sms - 2 * layer_sms))
                 try:
                     with torch.cuda.stream(s_skip):
                         for k in range(n, 0, -1):

@@ -211,7 +211,8 @@ class _Unet2Fn(torch.autograd.Function):
             enc_out.append(h)
         e4 = h
         # the four skip convs (:153-156) run beside the layer-1 recurrence (64 of 148 SMs busy) on the side stream
-        side = _SideWork(mag.device, ops.OVERLAP_BWD)
+        # (ops.FWD_SIDE_SKIPS; measured on one box, repeated: 6.06 ms per step with, 6.27 without, 6.86 with no side streams at all)
+        side = _SideWork(mag.device, ops.OVERLAP_BWD and ops.FWD_SIDE_SKIPS)
         cap = 0
         if side.enabled and ops.BWD_SIDE_CAP:
             free_sms = torch.cuda.get_device_properties(mag.device).multi_processor_count - 8 * len(m.gru.gru_list1) * ((B + 31) // 32)

@@ -794,6 +794,7 @@ def set_conv_max_ctas(n: int):
 # training backward: weight-gradient kernels on a side stream beside the BPTT launches (autograd._SideWork)
 OVERLAP_BWD = os.environ.get("CRUSE_OVERLAP_BWD", "1") != "0"
 BWD_SIDE_CAP = os.environ.get("CRUSE_BWD_SIDE_CAP", "1") != "0"
+FWD_SIDE_SKIPS = os.environ.get("CRUSE_FWD_SIDE_SKIPS", "1") != "0"   # training forward: skip convs beside the layer-1 recurrence
 BWD_SIDE_L1 = os.environ.get("CRUSE_BWD_SIDE_L1", "1") != "0"      # layer-1 GRU weight gradients beside the encoder backward
 
 # inference: pipeline the head of the encoder and the tail of the decoder with the GRU wavefront (cruse_net.GGRU._wavefront)

@@ -8,7 +8,6 @@ timeout 400 python bench.py --workload train --no-cpu-baseline --table $O/kernel
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2>$O/bench_reference.err
 timeout 200 python tools/stream_step_bench.py --table $O/kernels_stream.md > $O/bench_stream.json 2>$O/stream.err
 timeout 200 python tools/trace_step.py $O/trace_graph_timeline.md --graph > /dev/null 2>$O/trace.err
-timeout 200 python tools/trace_step.py $O/trace_train_timeline.md --train > /dev/null 2>>$O/trace.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_bench.log 2>&1
 python - <<'PY'
 import json

@@ -34,6 +34,7 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         F = model.in_feat
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
+        side2 = _side_stream(dev, 1)                # the loss ranges: beside (not behind) the mask*X + iSTFT ranges
         X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)   # feature.py:10-30, utils.py:400
         # the clean-speech STFT is only needed by the loss: it is released behind the encoder and the layer-1 input projections
         # (not beside them, where it would take SMs from what gates the recurrence) and runs beside the GRU; its output buffer
@@ -50,6 +51,9 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
             side.wait_event(fork)
             with torch.cuda.stream(side):
                 ops.stft_fwd_into(clean, hann_window(n_fft, n_fft, dev), S, n_fft, hop, pad_mode)
+                s_ready = torch.cuda.Event()
+                s_ready.record(side)
+            side2.wait_event(s_ready)
             clean_started.append(True)
         # Pipelined schedule (ops.PIPELINE_EDGES): the decoder hands the mask over range by range; mask*X + iSTFT and the loss
         # follow on the side stream, so that only the last range of both is left after the last decoder launch.
@@ -67,11 +71,13 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             side.wait_event(ev)
+            side2.wait_event(ev)
             with torch.cuda.stream(side):
                 c1 = nct if t1 >= T else t1 // FC
                 if c1 > prog["c"]:
                     ops.mask_istft_fwd_range(X, mask_all, window, n_fft, hop, est_buf, wav_buf, prog["c"], c1)
                     prog["c"] = c1
+            with torch.cuda.stream(side2):
                 nparts = max(1, ws.numel() * (t1 - t0) // T)
                 ops.wo_male_masked_partial_range(S, lay_s, mask_all, X, lay_x, ws, prog["p"], nparts, X.shape[0], T, F, t0, t1)
                 prog["p"] += nparts
@@ -85,14 +91,19 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
             raise RuntimeError("forward_loss: the model did not call after_encoder()")
         ranges = getattr(model, "_post_ranges", [])
         if ranges and ranges[0][0] == 0 and ranges[-1][1] == T and prog["c"] == nct:
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side2):
                 loss = ops.wo_male_finish(ws, prog["p"], X.shape[0], T, F)
                 done = torch.cuda.Event()
-                done.record(side)
-            loss.record_stream(main)                     # made on the side stream, handed to the caller's
-            for t_ in (est_buf, wav_buf, ws):            # made on the caller's stream, written on the side stream
+                done.record(side2)
+            done_istft = torch.cuda.Event()
+            done_istft.record(side)
+            loss.record_stream(main)                     # made on a side stream, handed to the caller's
+            for t_ in (est_buf, wav_buf):                # made on the caller's stream, written on the side streams
                 t_.record_stream(side)
+            for t_ in (ws, S, X):
+                t_.record_stream(side2)
             main.wait_event(done)
+            main.wait_event(done_istft)
             return loss, wav_buf, est_buf, mask
         have_mask = torch.cuda.Event()
         have_mask.record(main)
@@ -104,6 +115,9 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
             done.record(side)
         est, wav = ops.mask_istft_fwd(X, mask, hann_window(n_fft, n_fft, dev), n_fft, hop, noisy.shape[-1])
         main.wait_event(done)
+        joined = torch.cuda.Event()                  # side2 only waited for the clean STFT here: join it (graph capture needs it)
+        joined.record(side2)
+        main.wait_event(joined)
         return loss, wav, est, mask
     wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
     S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
@@ -114,8 +128,8 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
 _side_streams = {}
 
 
-def _side_stream(device):
-    key = (device.type, device.index)
+def _side_stream(device, which=0):
+    key = (device.type, device.index, which)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=device, priority=0)
     return _side_streams[key]

@@ -245,7 +245,7 @@ def run_ours(args):
             distrib.sync_grad(params)          # the one collective of the path: flat fp32 gradient all_reduce over NCCL
         return loss.detach()
 
-    # inference: the whole step (~60 launches on 4 streams) is captured once into a CUDA graph and replayed
+    # the whole step (inference: ~95 launches on 13 streams; training: ~190) is captured once into a CUDA graph and replayed
     captured = None
     if not args.no_graph:
         captured = (pipeline.CapturedTrainStep if train else pipeline.CapturedForwardLoss)(model, B, L, N_FFT, HOP)
@@ -388,10 +388,10 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "frames_per_step_per_gpu": frames, "l2": "256 MB flush write between timed steps",
-                   "launch": ("one CUDA graph replay per step (captured from the ctypes launches, 4 streams)" if captured is not None
+                   "launch": ("one CUDA graph replay per step (captured from the ctypes launches on up to 13 streams)" if captured is not None
                               else "eager ctypes launches on torch's current stream"),
                    "tensor_core_operands": "tf32 (tcgen05, fp32 accumulate in TMEM) in the conv / convT implicit GEMMs and both GRU matmuls; everything else fp32",
-                   "gru": "two layers side by side (time-chunked wavefront, 3 streams), 2 x 16 utterances software-pipelined per cluster",
+                   "gru": "two layers side by side (flag-synchronised time-chunked wavefront; in inference the decoder, mask*X + iSTFT and the loss follow layer 2 in groups of chunks), 2 x 16 utterances software-pipelined per cluster",
                    "collective": ("one flat fp32 gradient all_reduce (NCCL) per step" if (train and world > 1) else "none")},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(), "loss": float(loss), "kernels": kernels,

@@ -75,6 +75,7 @@ class GGRU(nn.Module):
     WAVEFRONT_MIN_T = 96
     WAVEFRONT_CHUNKS = 8            # relaunch mode: one recurrence launch per chunk
     WAVEFRONT_FLAG_CHUNKS = 8      # flag mode: chunks only gate the hand-over between the layers (ABI limit 16)
+    WAVEFRONT_LAST_CHUNK = int(os.environ.get("CRUSE_LAST_CHUNK", "0"))      # frames of the last flag chunk (0 = equal chunks)
     _side_streams = {}
 
     @classmethod
@@ -92,7 +93,13 @@ class GGRU(nn.Module):
         if ops.GRU_WAVEFRONT_MODE != "flags":
             return None
         nch = max(2, min(self.WAVEFRONT_FLAG_CHUNKS, T // 24))
-        bounds = [T * k // nch for k in range(nch + 1)]
+        # a SHORT last chunk: what is left after layer 1 has finished -- LayerNorm 1 + projections + layer 2 of the last chunk, then
+        # its LayerNorm 2 + decoder -- is proportional to it
+        last = min(self.WAVEFRONT_LAST_CHUNK, T // nch)
+        if last >= 8 and nch >= 3:
+            bounds = [(T - last) * k // (nch - 1) for k in range(nch)] + [T]
+        else:
+            bounds = [T * k // nch for k in range(nch + 1)]
         if not all(bounds[k + 1] - bounds[k] >= 8 for k in range(nch)):
             return None
         # [0,nch) layer-1 projections ready, [nch,2nch) layer-1 chunk stored (counts (CTA, slice) pairs), [2nch,3nch) layer-2

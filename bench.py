@@ -322,14 +322,25 @@ def run_ours(args):
     if captured is not None:
         # every step: pinned host -> device copy of that step's inputs (on the copy stream, overlapping the previous
         # step's replay), graph replay, loss read back to the host
+        # (inference) the loss of step i is read back on its own stream and the host blocks on it only after step i+1 has been
+        # launched, so the GPU does not idle for the host's launch latency between steps; every step's loss reaches the host
         ticket = captured.prefetch(noisy_h, clean_h)
+        pending = None
         for i in range(args.steps):
             nxt = captured.prefetch(noisy_h, clean_h) if i + 1 < args.steps else None
             out = captured.run_prefetched(ticket)
-            if train and world > 1:
-                distrib.sync_grad(params, flat=captured.flat_grad)
-            l_host = (out if train else out[0]).to("cpu")
+            if train:
+                if world > 1:
+                    distrib.sync_grad(params, flat=captured.flat_grad)
+                l_host = out.to("cpu")
+            else:
+                handle = captured.loss_to_host_async(out[0])
+                if pending is not None:
+                    l_host = pending.result()
+                pending = handle
             ticket = nxt
+        if pending is not None:
+            l_host = pending.result()
     else:
         for _ in range(args.steps):
             l_host = step_host()
@@ -341,7 +352,7 @@ def run_ours(args):
     e2e = {"value": frames * world * args.steps / float(t.item()), "unit": "frames/s",
            "h2d_bytes_per_step": int(noisy_h.numel() * 4 + clean_h.numel() * 4), "d2h_bytes_per_step": 4,
            "ms_per_step": 1e3 * float(t.item()) / args.steps,
-           "how": ("pipeline.CapturedForwardLoss.prefetch/run_prefetched: pinned H2D of step i+1 on a copy stream (into the staging pair the next replay reads in place) under the replay of step i, loss .to(cpu) every step"
+           "how": ("pipeline.CapturedForwardLoss.prefetch/run_prefetched: pinned H2D of step i+1 on a copy stream (into the staging pair the next replay reads in place) under the replay of step i; every step's loss is copied to pinned host memory on a read-back stream and awaited after the next step has been launched"
                    if captured is not None else "forward_loss_host: H2D, launches, loss .to(cpu) back to back")}
 
     # ---- per-kernel device times of one step (CUDA events on the launching stream) -> roofline

@@ -246,6 +246,37 @@ class CapturedForwardLoss:
 
     IN_PLACE_STAGING = True
 
+    # -- asynchronous read-back of a step's loss: the host can launch step i+1 before it blocks on the loss of step i ------
+    class _HostLoss:
+        def __init__(self, buf, event):
+            self.buf, self.event = buf, event
+
+        def result(self):
+            self.event.synchronize()
+            return float(self.buf[0])
+
+    def loss_to_host_async(self, loss):
+        """queue the device->host copy of ``loss`` (a 0-dim output of the step just launched) on a read-back stream behind that
+        step; returns a handle whose ``result()`` blocks until the value has arrived.  Two pinned slots alternate, so a handle
+        must be consumed before the step after next is queued (the per-staging-pair graphs keep their own output tensors)."""
+        dev = self.noisy.device
+        if not hasattr(self, "_read_stream"):
+            self._read_stream = torch.cuda.Stream(device=dev)
+            self._host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._host_slot = 0
+        main = torch.cuda.current_stream(dev)
+        done = torch.cuda.Event()
+        done.record(main)
+        rs = self._read_stream
+        rs.wait_event(done)
+        buf = self._host_loss[self._host_slot]
+        self._host_slot ^= 1
+        with torch.cuda.stream(rs):
+            buf.copy_(loss.reshape(1), non_blocking=True)
+            arrived = torch.cuda.Event()
+            arrived.record(rs)
+        return CapturedForwardLoss._HostLoss(buf, arrived)
+
 
 class CapturedTrainStep(CapturedForwardLoss):
     """The whole training step -- STFT, forward with batch statistics, wo_male, backward -- for one fixed (B, L) captured

@@ -229,8 +229,12 @@ def test_captured_graph_and_wavefront_match_eager(cuda):
     # double-buffered host input path: same numbers
     t1 = cap.prefetch(noisy.pin_memory(), clean.pin_memory())
     l3 = cap.run_prefetched(t1)[0]
+    handle = cap.loss_to_host_async(l3)            # read-back on its own stream, awaited later
+    t2 = cap.prefetch(noisy.pin_memory(), clean.pin_memory())
+    l4 = cap.run_prefetched(t2)[0]                 # the next step is already queued (other staging pair, own outputs)
+    assert handle.result() == float(l0)
     torch.cuda.synchronize()
-    assert torch.equal(l3, l0)
+    assert torch.equal(l3, l0) and torch.equal(l4, l0)
     old = ops.GRU_WAVEFRONT
     ops.GRU_WAVEFRONT = False
     try:

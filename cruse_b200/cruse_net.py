@@ -381,6 +381,15 @@ class unet_2(nn.Module):
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
     SIDE_CAP = int(os.environ.get("CRUSE_SIDE_CAP", "0"))     # CTAs of the persistent side kernels (0 = the SMs the recurrences leave free)
 
+    @staticmethod
+    def chunk_groups(nch, cuts=None):
+        """[(k0, k1), ...]: the groups of wavefront chunks the pipelined decoder / skip convs are issued in -- everything up to
+        three chunks before the end, the next two, the last one (``cuts``: explicit chunk indices instead)."""
+        cuts = sorted(set(cuts)) if cuts else sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
+        if cuts[0] != 0 or cuts[-1] != nch or any(c < 0 or c > nch for c in cuts):
+            raise RuntimeError(f"chunk_groups: cuts {cuts} do not partition [0, {nch}]")
+        return list(zip(cuts[:-1], cuts[1:]))
+
     def _forward_frames_pipelined(self, mag, plan, folds, post=None, after_encoder=None):
         """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
         have no time taps at all, so LayerNorm 2 + the decoder (and the skip convs they add) are run per GROUP of wavefront
@@ -420,13 +429,11 @@ class unet_2(nn.Module):
             def groups(nch):
                 # few, large groups (every launch costs ~10 us of set-up and runs beside the recurrences; measured on B200 at
                 # 8 chunks: cuts 0,5,7,8 -> 1.45 ms, 0,4,6,7,8 -> 1.47-1.50, pairs -> 1.53, single chunks -> 1.63, off -> 1.52)
-                cuts = unet.DECODE_CUTS or sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
-                return list(zip(cuts[:-1], cuts[1:]))
+                return unet.chunk_groups(nch, unet.DECODE_CUTS)
 
             @staticmethod
             def skip_groups(nch):
-                cuts = unet.SKIP_CUTS or sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
-                return list(zip(cuts[:-1], cuts[1:]))
+                return unet.chunk_groups(nch, unet.SKIP_CUTS)
 
             @staticmethod
             def caps(j, ngroups):

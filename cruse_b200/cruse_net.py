@@ -74,7 +74,7 @@ class GGRU(nn.Module):
     STEP_MIN_B = 128                # 1-frame streaming calls with at least this many utterances use ops.gru_step
     WAVEFRONT_MIN_T = 96
     WAVEFRONT_CHUNKS = 8            # relaunch mode: one recurrence launch per chunk
-    WAVEFRONT_FLAG_CHUNKS = 8      # flag mode: chunks only gate the hand-over between the layers (ABI limit 16)
+    WAVEFRONT_FLAG_CHUNKS = int(os.environ.get("CRUSE_FLAG_CHUNKS", "8"))   # flag mode: chunks only gate the hand-over between the layers (ABI limit 16)
     WAVEFRONT_LAST_CHUNK = int(os.environ.get("CRUSE_LAST_CHUNK", "0"))      # frames of the last flag chunk (0 = equal chunks)
     _side_streams = {}
 

@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) CT_STAMP(63, 14);                               // kernel start
+    // programmatic dependent launch: the next kernel of the stream may start its own set-up (weights, TMEM, barriers) on SMs this
+    // grid has left; everything that touches activations sits behind griddepcontrol.wait below
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int T = a.T;
     const int chunks = (a.t_end - a.t_begin + C::TF - 1) / C::TF;
     const int ntiles = a.B * chunks;
@@ -211,6 +214,9 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    // the set-up above read parameters only; the upstream grid (which produced this stage's input / skip tensors) must have
+    // completed and flushed before any activation is read or written (no-op when launched without the PDL attribute)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp == 0) CT_STAMP(63, 13);                               // setup done
 
     if (warp < CT_PROD_WARPS) {
@@ -455,6 +461,18 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
     if (warp == CT_MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
+// programmatic dependent launch of the conv stages: OFF by default (CRUSE_CONV_PDL=1 turns it on).  Measured on B200 with the set-up
+// of kernel N+1 overlapping the tail of kernel N: inference 1.565 vs 1.48 ms per step, training 6.29 vs 6.07 ms -- the early-resident
+// dependent CTAs (200 KB of shared memory each) sit in griddepcontrol.wait on SMs that the other streams of the step would have used.
+inline bool conv_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CRUSE_CONV_PDL");
+        v = (e && strcmp(e, "1") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS>
 int launch_conv_tc(const ConvTcArgs& a_in, cudaStream_t st) {
     using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
@@ -471,6 +489,20 @@ int launch_conv_tc(const ConvTcArgs& a_in, cudaStream_t st) {
     const long long ntiles = (long long)a.B * chunks;
     int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
     if (g_conv_max_ctas > 0 && grid > g_conv_max_ctas) grid = g_conv_max_ctas;
+    if (conv_pdl_enabled()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(ct_threads(NS));
+        cfg.dynamicSmemBytes = C::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CRUSE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
+        return 0;
+    }
     kern<<<grid, ct_threads(NS), C::SMEM, st>>>(a);
     CRUSE_LAUNCH_OK();
     return 0;

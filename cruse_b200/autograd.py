@@ -376,3 +376,27 @@ class _MaskApplyFn(torch.autograd.Function):
 
 def mask_apply(mask, X, n_fft, hop):
     return _MaskApplyFn.apply(mask, X, n_fft, hop)
+
+
+class _MaskIstftFn(torch.autograd.Function):
+    """wav = istft(mask * X) (utils/utils.py:417-454), differentiable w.r.t. the mask: for time-domain losses (SI-SNR)."""
+
+    @staticmethod
+    def forward(ctx, mask, X, n_fft, hop, length):
+        from .acoustics import hann_window
+        window = hann_window(n_fft, n_fft, X.device)
+        _, wav = ops.mask_istft_fwd(X, mask, window, n_fft, hop, length, want_est=False, want_wav=True)
+        ctx.save_for_backward(X, window)
+        ctx.geom = (n_fft, hop, mask.shape[-1])
+        return wav
+
+    @staticmethod
+    def backward(ctx, dwav):
+        X, window = ctx.saved_tensors
+        n_fft, hop, F = ctx.geom
+        dspec = ops.istft_bwd(dwav.contiguous(), window, n_fft, hop)          # adjoint of the iSTFT
+        return ops.mask_bwd(dspec, X, F), None, None, None, None              # Re(conj(X) * dspec) per masked bin
+
+
+def mask_istft_apply(mask, X, n_fft, hop, length):
+    return _MaskIstftFn.apply(mask, X, n_fft, hop, length)

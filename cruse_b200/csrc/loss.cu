@@ -157,6 +157,135 @@ extern "C" int cruse_wo_male_finish(const void* ws, int nparts, int B, int T, in
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// SI-SNR (loss_func/loss.py:37-56; the 'SI-SNR' mode of the dispatcher, :25-26, returns its negative), est / ref wav [B, L]:
+//   a = <est,ref>, c = <ref,ref>, alpha = a / (c + eps), tn = |alpha ref|^2, nn = |est - alpha ref|^2,
+//   value = mean_b 10 log10(tn / (nn + eps) + eps)
+// Three launches, all reductions in a fixed order (deterministic): per-(utterance, chunk) partial dot products; partial norms
+// with alpha rebuilt from the partials; one block that finishes every utterance in double precision and leaves the two
+// coefficients of d value / d est = P_b est + Q_b ref in the workspace for the backward pass.
+// ---------------------------------------------------------------------------------------------
+namespace cruse {
+constexpr int SISNR_CHUNKS = 32;
+
+__device__ __forceinline__ void block_sum2(float& x, float& y, float* sh) {
+    x = warp_sum(x);
+    y = warp_sum(y);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[w] = x; sh[8 + w] = y; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float u = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f, v = threadIdx.x < (blockDim.x >> 5) ? sh[8 + threadIdx.x] : 0.f;
+        u = warp_sum(u);
+        v = warp_sum(v);
+        x = u;
+        y = v;
+    }
+}
+
+// pass 0: (a, c) partials; pass 1: (tn, nn) partials with alpha from the pass-0 partials
+template <int PASS>
+__global__ void __launch_bounds__(256)
+sisnr_partial_kernel(const float* __restrict__ est, const float* __restrict__ ref, const float* __restrict__ dots, float* __restrict__ out,
+                     int L, float eps) {
+    __shared__ float sh[16];
+    const int b = blockIdx.y, j = blockIdx.x;
+    const int len = (L + SISNR_CHUNKS - 1) / SISNR_CHUNKS;
+    const int lo = j * len, hi = (lo + len < L) ? lo + len : L;
+    float alpha = 0.f;
+    if (PASS == 1) {
+        double a = 0.0, c = 0.0;
+        for (int q = 0; q < SISNR_CHUNKS; ++q) { a += (double)dots[((size_t)b * SISNR_CHUNKS + q) * 2]; c += (double)dots[((size_t)b * SISNR_CHUNKS + q) * 2 + 1]; }
+        alpha = (float)(a / (c + (double)eps));
+    }
+    const float* e = est + (size_t)b * L;
+    const float* r = ref + (size_t)b * L;
+    float x = 0.f, y = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float ev = __ldg(e + i), rv = __ldg(r + i);
+        if (PASS == 0) { x = fmaf(ev, rv, x); y = fmaf(rv, rv, y); }
+        else { const float tv = alpha * rv, nv = ev - tv; x = fmaf(tv, tv, x); y = fmaf(nv, nv, y); }
+    }
+    block_sum2(x, y, sh);
+    if (threadIdx.x == 0) { out[((size_t)b * SISNR_CHUNKS + j) * 2] = x; out[((size_t)b * SISNR_CHUNKS + j) * 2 + 1] = y; }
+}
+
+__global__ void __launch_bounds__(256)
+sisnr_finish_kernel(const float* __restrict__ dots, const float* __restrict__ norms, float* __restrict__ coef, float* __restrict__ value,
+                    int B, float eps_f) {
+    __shared__ double sh[256];
+    const double eps = (double)eps_f, K = 10.0 / log(10.0);
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        double a = 0.0, c = 0.0, tn = 0.0, nn = 0.0;
+        for (int q = 0; q < SISNR_CHUNKS; ++q) {
+            const size_t o = ((size_t)b * SISNR_CHUNKS + q) * 2;
+            a += (double)dots[o]; c += (double)dots[o + 1]; tn += (double)norms[o]; nn += (double)norms[o + 1];
+        }
+        const double alpha = a / (c + eps), q_ = tn / (nn + eps) + eps;
+        acc += K * log(q_);
+        // d snr_b / d est = P est + Q ref (derivation: DESIGN.md section 3.2 / tests), scaled by 1/B for the mean
+        const double r2 = tn / ((nn + eps) * (nn + eps));
+        const double P = -(K / q_) * 2.0 * r2;
+        const double Q = (K / q_) * (2.0 * alpha * c / ((c + eps) * (nn + eps)) + r2 * (2.0 * alpha + 2.0 * (a - alpha * c) / (c + eps)));
+        coef[2 * b] = (float)(P / B);
+        coef[2 * b + 1] = (float)(Q / B);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) s += sh[i];
+        value[0] = (float)(s / B);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sisnr_bwd_kernel(const float* __restrict__ est, const float* __restrict__ ref, const float* __restrict__ coef,
+                 const float* __restrict__ gscale, float* __restrict__ dest, long long total, int L) {
+    const float g = gscale ? __ldg(gscale) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / L;
+        dest[i] = g * fmaf(__ldg(coef + 2 * b), __ldg(est + i), __ldg(coef + 2 * b + 1) * __ldg(ref + i));
+    }
+}
+}  // namespace cruse
+
+// workspace: [B][CHUNKS][2] dot partials, [B][CHUNKS][2] norm partials, [B][2] gradient coefficients (kept for cruse_sisnr_bwd)
+extern "C" size_t cruse_sisnr_ws_bytes(int B) { return sizeof(float) * (size_t)(B > 0 ? B : 0) * (4 * cruse::SISNR_CHUNKS + 2); }
+
+extern "C" int cruse_sisnr_fwd(const float* est, const float* ref, float* value, void* ws, int B, int L, float eps, void* stream) {
+    CRUSE_CHECK_ARG(est && ref && value && ws, "sisnr_fwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && L > 0, "sisnr_fwd: bad sizes B=%d L=%d", B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dots = static_cast<float*>(ws);
+    float* norms = dots + (size_t)B * cruse::SISNR_CHUNKS * 2;
+    float* coef = norms + (size_t)B * cruse::SISNR_CHUNKS * 2;
+    const dim3 grid(cruse::SISNR_CHUNKS, B);
+    cruse::sisnr_partial_kernel<0><<<grid, 256, 0, st>>>(est, ref, nullptr, dots, L, eps);
+    CRUSE_LAUNCH_OK();
+    cruse::sisnr_partial_kernel<1><<<grid, 256, 0, st>>>(est, ref, dots, norms, L, eps);
+    CRUSE_LAUNCH_OK();
+    cruse::sisnr_finish_kernel<<<1, 256, 0, st>>>(dots, norms, coef, value, B, eps);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+// dest[b, i] = gscale * d value / d est[b, i]   (gscale: device scalar = upstream gradient, or NULL = 1); ws from cruse_sisnr_fwd
+extern "C" int cruse_sisnr_bwd(const float* est, const float* ref, const void* ws, const float* gscale, float* dest, int B, int L,
+                               void* stream) {
+    CRUSE_CHECK_ARG(est && ref && ws && dest, "sisnr_bwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && L > 0, "sisnr_bwd: bad sizes B=%d L=%d", B, L);
+    const float* coef = static_cast<const float*>(ws) + (size_t)B * cruse::SISNR_CHUNKS * 4;
+    const long long total = (long long)B * L;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)cruse::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cruse::sisnr_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(est, ref, coef, gscale, dest, total, L);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
                                      const float* unproc, cruse_cplx_layout lunp, float* dest, float* loss, void* ws,
                                      int B, int T, int F, void* stream) {

@@ -401,6 +401,69 @@ static int mask_istft_launch(const float* spec, const float* mask, const float* 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward of the iSTFT (a9 for time-domain losses).  wav = istft(spec) is linear: irfft per frame, window, overlap-add,
+// divide by the window-power envelope, trim n_fft/2.  Its adjoint is therefore an STFT: with g[s] = dwav[s] / env[s + n_fft/2]
+// (0 where the forward wrote 0), dspec[t,k] = c_k / n_fft * rfft(window * frame_t(g, zero padded))[k], c_0 = c_{n_fft/2} = 1,
+// c_k = 2 otherwise (a real inverse FFT sees every interior bin twice).  The transform itself is cruse_stft_fwd with constant
+// padding; the two small kernels here do the envelope division and the c_k / n_fft scale.
+// ---------------------------------------------------------------------------------------------
+namespace cruse {
+__global__ void __launch_bounds__(256)
+istft_bwd_prep_kernel(const float* __restrict__ dwav, const float* __restrict__ window, float* __restrict__ g, long long total, int L,
+                      int N, int hop, int T) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i % L);
+        const int m = s + (N >> 1);
+        int t = m / hop;
+        if (t > T - 1) t = T - 1;
+        float env = 0.f;
+        for (; t >= 0; --t) {
+            const int off = m - t * hop;
+            if (off >= N) break;
+            const float w = __ldg(window + off);
+            env += w * w;
+        }
+        g[i] = env > 1e-11f ? __ldg(dwav + i) / env : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rfft_adjoint_scale_kernel(float2* __restrict__ dspec, long long total, int NF, float inv_n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % NF);
+        const float sc = (k == 0 || k == NF - 1) ? inv_n : 2.f * inv_n;
+        float2 v = dspec[i];
+        dspec[i] = make_float2(v.x * sc, v.y * sc);
+    }
+}
+}  // namespace cruse
+
+extern "C" size_t cruse_istft_bwd_ws_bytes(int B, int L) { return sizeof(float) * (size_t)(B > 0 ? B : 0) * (size_t)(L > 0 ? L : 0); }
+
+extern "C" int cruse_istft_bwd(const float* dwav, const float* window, float* dspec, void* ws, int B, int L, int n_fft, int hop,
+                               int T, void* stream) {
+    CRUSE_CHECK_ARG(dwav && window && dspec && ws, "istft_bwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && L > 0 && hop > 0 && n_fft >= 4 && (n_fft % 2) == 0 && hop <= n_fft, "istft_bwd: bad sizes B=%d L=%d n_fft=%d hop=%d", B, L, n_fft, hop);
+    CRUSE_CHECK_ARG(T == 1 + L / hop, "istft_bwd: T=%d must equal 1 + L/hop = %d", T, 1 + L / hop);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* g = static_cast<float*>(ws);
+    const long long total = (long long)B * L;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)cruse::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cruse::istft_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, st>>>(dwav, window, g, total, L, n_fft, hop, T);
+    CRUSE_LAUNCH_OK();
+    if (int rc = cruse_stft_fwd(g, window, dspec, nullptr, B, L, n_fft, hop, T, CRUSE_PAD_CONSTANT, 0, 0.f, stream)) return rc;
+    const int NF = n_fft / 2 + 1;
+    const long long n = (long long)B * T * NF;
+    blocks = (n + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    cruse::rfft_adjoint_scale_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float2*>(dspec), n, NF, 1.0f / (float)n_fft);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int cruse_mask_bwd(const float* dest, const float* spec, const float* gscale, const float* mask, float* dmask,
                               int B, int T, int NF, int mask_bins, void* stream) {
     CRUSE_CHECK_ARG(dest && spec && dmask, "mask_bwd: null pointer");

@@ -65,6 +65,32 @@ def wo_male_frames_autograd(ref, est, unproc, F):
     return _WoMale.apply(ref, est, unproc, "btf2", F)
 
 
+class _SiSnr(torch.autograd.Function):
+    """mean SI-SNR (dB) of est vs ref waveforms, differentiable w.r.t. est (loss_func/loss.py:37-56)."""
+
+    @staticmethod
+    def forward(ctx, est, ref, eps):
+        est, ref = est.contiguous(), ref.contiguous()
+        value, ws = ops.sisnr_fwd(est, ref, eps)
+        ctx.save_for_backward(est, ref, ws)
+        return value
+
+    @staticmethod
+    def backward(ctx, g):
+        est, ref, ws = ctx.saved_tensors
+        return ops.sisnr_bwd(est, ref, ws, g.contiguous().float()), None, None
+
+
+def sisnr(s1, s2, eps=1e-8):
+    """loss_func/loss.py:47-56: s1 = estimate, s2 = target, [B, L] (any leading dims are flattened) -> mean SI-SNR in dB."""
+    if s1.shape != s2.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate si-snr, {tuple(s1.shape)} vs {tuple(s2.shape)}")
+    if not s1.is_cuda:
+        raise RuntimeError("sisnr: cruse_b200 runs on sm_100a only (no CPU fallback)")
+    L = s1.shape[-1]
+    return _SiSnr.apply(s1.reshape(-1, L).float(), s2.reshape(-1, L).float(), eps)
+
+
 def wo_male_loss():
     """factory in the style of train_base/loss.py:7-25: returns loss(est, ref, noisy)."""
     def loss(est, ref, noisy):
@@ -73,7 +99,7 @@ def wo_male_loss():
 
 
 class loss_func:
-    """loss_func/loss.py:16-34 dispatcher; only the hot-path mode is built (others: SURVEY 8f2)."""
+    """loss_func/loss.py:16-34 dispatcher; WO_MALE (the hot path) and SI-SNR are built (others: SURVEY 8f2)."""
 
     MODES = ['SI-SNR', 'SS-SNR', 'MSE', 'Normal_MSE', 'CN_MSE', 'D_MSE', 'WO_MALE', 'C_MSE']
 
@@ -84,6 +110,8 @@ class loss_func:
     def loss(self, inputs, labels, noisy=None):
         if self.loss_mode == 'WO_MALE':
             return wo_male(labels, inputs, noisy)                            # :29-30 (arg order)
+        if self.loss_mode == 'SI-SNR':
+            return -(sisnr(inputs, labels))                                  # :25-26 (time-domain estimate / target)
         if self.loss_mode == 'SS-SNR':
             return 0                                                         # :27-28
         raise NotImplementedError(f"loss mode {self.loss_mode!r} is outside the built hot path (SURVEY.md 8f2)")

@@ -164,6 +164,41 @@ def mask_istft_fwd_range(spec, mask, window, n_fft, hop, est, wav, c0, c1):
           c0, c1, _stream(), meta=(f"mask_istft n{n_fft} h{hop} ctas[{c0},{c1})", 0, 0))
 
 
+def istft_bwd(dwav, window, n_fft, hop):
+    """gradient of wav = istft(spec) w.r.t. spec: dwav [B,L] -> dspec [B,T,NF,2] (an STFT of dwav / envelope, scaled)."""
+    _req(dwav, "dwav", 2)
+    _req(window, "window", 1)
+    B, L = dwav.shape
+    T = 1 + L // hop
+    dspec = torch.empty(B, T, n_fft // 2 + 1, 2, device=dwav.device, dtype=torch.float32)
+    ws = _ws(lib().cruse_istft_bwd_ws_bytes(B, L), dwav.device)
+    _call("cruse_istft_bwd", _p(dwav), _p(window), _p(dspec), _p(ws), B, L, n_fft, hop, T, _stream(),
+          meta=(f"istft_bwd n{n_fft} h{hop}", _nb(dwav, dspec) + 2 * ws.numel() * 4, int(B * T * 2.5 * n_fft * 9)))
+    return dspec
+
+
+def sisnr_fwd(est, ref, eps=1e-8):
+    """-> (value 0-dim, ws): mean SI-SNR in dB of est vs ref wav [B,L] (loss.py:37-56); ws feeds sisnr_bwd."""
+    _req(est, "est", 2)
+    _req(ref, "ref", 2)
+    if est.shape != ref.shape:
+        raise RuntimeError(f"sisnr: shapes {tuple(est.shape)} vs {tuple(ref.shape)}")
+    B, L = est.shape
+    value = torch.empty((), device=est.device, dtype=torch.float32)
+    ws = _ws(lib().cruse_sisnr_ws_bytes(B), est.device)
+    _call("cruse_sisnr_fwd", _p(est), _p(ref), _p(value), _p(ws), B, L, float(eps), _stream(),
+          meta=("sisnr", 2 * _nb(est, ref), 8 * B * L))
+    return value, ws
+
+
+def sisnr_bwd(est, ref, ws, gscale=None):
+    """gscale * d value / d est (gscale: 0-dim device tensor or None)."""
+    B, L = est.shape
+    dest = torch.empty_like(est)
+    _call("cruse_sisnr_bwd", _p(est), _p(ref), _p(ws), _p(gscale), _p(dest), B, L, _stream(), meta=("sisnr_bwd", _nb(est, ref, dest), 3 * B * L))
+    return dest
+
+
 def mask_bwd(dest, spec, mask_bins, gscale=None, mask=None):
     """dmask[b,t,f] = gscale * Re(conj(X) * dEst), f < mask_bins; with ``mask`` given the result is the gradient
     before the sigmoid (times mask*(1-mask))."""

@@ -62,6 +62,12 @@ int cruse_stft_fwd(const float* wav, const float* window, float* spec, float* ma
 int cruse_mask_istft_fwd(const float* spec, const float* mask, const float* window,
                          float* est_spec, float* wav,
                          int B, int L, int n_fft, int hop, int T, int mask_bins, void* stream);
+/* backward of the iSTFT half (a9 for time-domain losses; the reference gets it from autograd of torch.istft, feature.py:53-61):
+ * dwav [B,L] -> dspec [B,T,NF,2] = gradient w.r.t. the (real, imag) spectrum handed to cruse_mask_istft_fwd; feed it to
+ * cruse_mask_bwd for the mask gradient.  ws: cruse_istft_bwd_ws_bytes(B, L) bytes of scratch. */
+size_t cruse_istft_bwd_ws_bytes(int B, int L);
+int cruse_istft_bwd(const float* dwav, const float* window, float* dspec, void* ws, int B, int L, int n_fft, int hop, int T,
+                    void* stream);
 /* The CTAs [c_begin, c_end) of the same launch: CTA c produces est_spec of the frames [c*FC, (c+1)*FC) and the samples
  * those frames start, reading the mask of the frames [c*FC - (n_fft-1)/hop, (c+1)*FC), FC = cruse_mask_istft_chunk_frames.
  * Disjoint ranges covering [0, ceil(T/FC)) are bit-identical to the whole call. */
@@ -229,6 +235,14 @@ int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float*
 int cruse_wo_male_masked_fwd(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
                              cruse_cplx_layout lunp, float* loss, void* ws, int B, int T, int F, void* stream);
 size_t cruse_wo_male_ws_bytes(void);
+/* SI-SNR of loss_func/loss.py:37-56 on waveforms est / ref [B,L]: value = mean_b 10 log10(|alpha ref|^2 /
+ * (|est - alpha ref|^2 + eps) + eps), alpha = <est,ref> / (<ref,ref> + eps); the dispatcher's 'SI-SNR' mode (:25-26) returns
+ * its negative.  cruse_sisnr_bwd: dest = gscale * d value / d est (gscale: device scalar or NULL = 1), from the coefficients
+ * cruse_sisnr_fwd left in ws (cruse_sisnr_ws_bytes(B) bytes).  Fixed-order reductions: deterministic. */
+size_t cruse_sisnr_ws_bytes(int B);
+int cruse_sisnr_fwd(const float* est, const float* ref, float* value, void* ws, int B, int L, float eps, void* stream);
+int cruse_sisnr_bwd(const float* est, const float* ref, const void* ws, const float* gscale, float* dest, int B, int L,
+                    void* stream);
 /* The same loss range by range (inference schedule: the loss follows the decoder instead of waiting for the whole mask):
  * _partial_range writes nparts partial sums of the frames [t_begin, t_end) of every utterance into ws[p_off, p_off+nparts),
  * cruse_wo_male_finish adds up the nparts partials of all ranges and divides by B*T*F (loss.py:147).  Same arithmetic per

@@ -510,3 +510,77 @@ def test_train_step_with_fused_adam_reduces_the_loss(cuda):
     losses = [l0] + [float(ts.step(noisy, clean)) for _ in range(5)]
     assert losses[-1] < losses[0], losses
     assert all(l == l for l in losses)                                            # no NaN
+
+
+@pytest.mark.parametrize("n_fft,hop,B,L", [(512, 320, 2, 6400), (320, 160, 3, 3200), (512, 320, 1, 3333)])
+def test_istft_backward_matches_torch_autograd(cuda, n_fft, hop, B, L):
+    """cruse_istft_bwd (the adjoint of irfft + window + overlap-add + envelope division + trim, computed as an STFT of
+    dwav / envelope scaled by c_k / n_fft) against autograd of torch.istft (feature.py:53-61); 1e-4."""
+    from cruse_b200 import acoustics, ops
+    torch.manual_seed(44)
+    T, NF = 1 + L // hop, n_fft // 2 + 1
+    w = torch.hann_window(n_fft, periodic=True)
+    spec = torch.randn(B, T, NF, 2, requires_grad=True)
+    wav = torch.istft(torch.view_as_complex(spec).transpose(1, 2), n_fft, hop, n_fft, window=w, center=True, length=L)
+    r = torch.randn(B, L)
+    (wav * r).sum().backward()
+    got = ops.istft_bwd(r.to(cuda), acoustics.hann_window(n_fft, n_fft, cuda), n_fft, hop)
+    want = spec.grad.clone()
+    want[:, :, 0, 1] = 0          # imag of DC / Nyquist does not enter a real inverse FFT
+    want[:, :, NF - 1, 1] = 0
+    assert rel_err(got, want) <= 1e-4
+    # and the forward it is the adjoint of: <istft(S), r> == <S, istft_bwd(r)> on our own kernels (dot-product test)
+    S = torch.randn(B, T, NF, 2, device=cuda)
+    S[:, :, 0, 1] = 0
+    S[:, :, NF - 1, 1] = 0
+    _, y = ops.mask_istft_fwd(S, None, acoustics.hann_window(n_fft, n_fft, cuda), n_fft, hop, L, want_est=False)
+    lhs, rhs = float((y * r.to(cuda)).sum()), float((S * got).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1.0)
+
+
+@pytest.mark.parametrize("B,L,snr", [(3, 16000, 0.3), (32, 8000, 1.0), (1, 777, 0.01)])
+def test_sisnr_value_and_gradient_match_oracle(cuda, B, L, snr):
+    """loss_func('SI-SNR') (loss.py:25-26, 37-56) on the GPU: value and d/d est against autograd of the oracle's sisnr,
+    from low to high SNR; deterministic (fixed-order reductions)."""
+    from cruse_b200 import loss as L_
+    from oracle import cruse_oracle as o
+    torch.manual_seed(45)
+    ref = 0.1 * torch.randn(B, L)
+    est = (ref + snr * 0.1 * torch.randn(B, L)).requires_grad_()
+    want = -o.sisnr(est, ref)
+    want.backward()
+    e = est.detach().to(cuda).requires_grad_()
+    got = L_.loss_func('SI-SNR').loss(e, ref.to(cuda))
+    got.backward()
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want)) + 1e-5
+    assert rel_err(e.grad, est.grad) <= 1e-4
+    e2 = est.detach().to(cuda).requires_grad_()
+    got2 = L_.loss_func('SI-SNR').loss(e2, ref.to(cuda))
+    got2.backward()
+    assert torch.equal(got, got2) and torch.equal(e.grad, e2.grad)
+    with pytest.raises(RuntimeError):
+        L_.sisnr(e, ref.to(cuda)[:, :-1])
+
+
+def test_sisnr_through_mask_and_istft_gradient(cuda):
+    """time-domain training loss end to end behind the network: -SI-SNR(istft(mask * X), clean) differentiated w.r.t. the mask
+    through cruse_sisnr_bwd -> cruse_istft_bwd -> cruse_mask_bwd, against the same composition in CPU torch autograd."""
+    from cruse_b200 import acoustics, autograd as ag, loss as L_
+    from oracle import cruse_oracle as o
+    torch.manual_seed(46)
+    B, L, n_fft, hop, F = 2, 6400, 512, 320, 256
+    noisy, clean = 0.1 * torch.randn(B, L), 0.05 * torch.randn(B, L)
+    w = torch.hann_window(n_fft, periodic=True)
+    Xc = torch.stft(noisy, n_fft, hop, n_fft, window=w, center=True, pad_mode="reflect", return_complex=True)      # [B,NF,T]
+    T = Xc.shape[-1]
+    mask = torch.rand(B, T, F, requires_grad=True)
+    full = torch.cat([mask, torch.ones(B, T, 1)], dim=-1).transpose(1, 2)                                       # Nyquist bin passes through
+    wav = torch.istft(Xc * full, n_fft, hop, n_fft, window=w, center=True, length=L)
+    want = -o.sisnr(wav, clean)
+    want.backward()
+    X, _ = acoustics.stft_frames(noisy.to(cuda), n_fft, hop, n_fft)
+    m = mask.detach().to(cuda).requires_grad_()
+    got = L_.loss_func('SI-SNR').loss(ag.mask_istft_apply(m, X, n_fft, hop, L), clean.to(cuda))
+    got.backward()
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want)) + 1e-4
+    assert rel_err(m.grad, mask.grad) <= 1e-3

@@ -68,6 +68,7 @@ SIGNATURES = {
     "cruse_mask_istft_fwd_range": (c_int, [c_fp] * 5 + [c_int] * 8 + [c_fp]),
     "cruse_istft_bwd_ws_bytes": (C.c_size_t, [c_int, c_int]),
     "cruse_istft_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp] + [c_int] * 5 + [c_fp]),
+    "cruse_spec_loss_fwd_bwd": (c_int, [c_int, c_fp, CplxLayout, c_fp, CplxLayout, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "cruse_sisnr_ws_bytes": (C.c_size_t, [c_int]),
     "cruse_sisnr_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_f, c_fp]),
     "cruse_sisnr_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),

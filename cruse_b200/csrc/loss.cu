@@ -158,6 +158,102 @@ extern "C" int cruse_wo_male_finish(const void* ws, int nparts, int B, int T, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// The two other spectral-domain modes of the dispatcher (loss_func/loss.py:31-34), same one-pass structure as
+// wo_male: MODE 0 = rmse (:59-78): sum_c |est_c - ref_c| / (B T F);  MODE 1 = c_rmse (:88-118), arithmetic kept literally,
+// incl. the tmp1 / tmp2 mix of :107-109:  with t1 = |est|^c, t2 = |ref|^c, phases pr, pe,
+//   v = (1-beta) (t2 - t1)^2 + beta [ (t1 cos pr - t2 cos pe)^2 + t1^2 (sin pr - sin pe)^2 ],  c = beta = 0.3, plain sum.
+// dest (optional) receives d loss / d est in est's layout.  At |est| = 0 torch's autograd yields inf / NaN (pow with a negative
+// exponent, atan2 at the origin); this kernel writes 0 there.
+// ---------------------------------------------------------------------------------------------
+namespace cruse {
+template <int MODE>
+__global__ void __launch_bounds__(LOSS_THREADS)
+spec_loss_partial_kernel(const float* __restrict__ ref, cruse_cplx_layout lr, const float* __restrict__ est, cruse_cplx_layout le,
+                         float* __restrict__ dest, float* __restrict__ partials, int T, int F, long long rows, float gscale) {
+    const float cpow = 0.3f, beta = 0.3f;
+    float acc = 0.f;
+    int t = (int)(blockIdx.x % T);
+    long long b = blockIdx.x / T;
+    for (long long bt = blockIdx.x; bt < rows; bt += gridDim.x) {
+        const long long rbase = b * lr.sb + t * lr.st, ebase = b * le.sb + t * le.st;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            const float2 r = ld_cplx(ref, rbase + f * lr.sf, lr.im_off);
+            const long long eoff = ebase + f * le.sf;
+            const float2 e = ld_cplx(est, eoff, le.im_off);
+            float gx = 0.f, gy = 0.f;
+            if (MODE == 0) {
+                const float dx = e.x - r.x, dy = e.y - r.y;
+                acc += fabsf(dx) + fabsf(dy);
+                gx = dx > 0.f ? gscale : (dx < 0.f ? -gscale : 0.f);
+                gy = dy > 0.f ? gscale : (dy < 0.f ? -gscale : 0.f);
+            } else {
+                const float mr = sqrtf(r.x * r.x + r.y * r.y), m = sqrtf(e.x * e.x + e.y * e.y);
+                const float cr = mr > 0.f ? r.x / mr : 1.f, sr = mr > 0.f ? r.y / mr : 0.f;      // atan2(0,0) = 0
+                const float cp = m > 0.f ? e.x / m : 1.f, sp = m > 0.f ? e.y / m : 0.f;
+                const float t1 = powf(m, cpow), t2 = powf(mr, cpow);
+                const float A = t1 * cr - t2 * cp, Bq = t1 * (sr - sp), d12 = t2 - t1;
+                acc += (1.f - beta) * d12 * d12 + beta * (A * A + Bq * Bq);
+                if (dest && m > 0.f) {
+                    const float dt1 = -2.f * (1.f - beta) * d12 + 2.f * beta * (A * cr + Bq * (sr - sp));
+                    const float dc = -2.f * beta * A * t2, ds = -2.f * beta * Bq * t1;
+                    const float k = dt1 * cpow * t1 / m;                 // d t1 / d m = c m^(c-1)
+                    const float im3 = 1.f / (m * m * m);
+                    gx = gscale * (k * e.x / m + dc * e.y * e.y * im3 - ds * e.x * e.y * im3);
+                    gy = gscale * (k * e.y / m - dc * e.x * e.y * im3 + ds * e.x * e.x * im3);
+                }
+            }
+            if (dest) {
+                if (le.im_off == 1 && ((eoff & 1) == 0)) {
+                    *reinterpret_cast<float2*>(dest + eoff) = make_float2(gx, gy);
+                } else {
+                    dest[eoff] = gx;
+                    dest[eoff + le.im_off] = gy;
+                }
+            }
+        }
+        t += (int)(gridDim.x % T);
+        b += gridDim.x / T;
+        if (t >= T) { t -= T; ++b; }
+    }
+    __shared__ float sh[LOSS_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < LOSS_THREADS / 32 ? sh[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) partials[blockIdx.x] = v;
+    }
+}
+}  // namespace cruse
+
+// mode 0: rmse ('MSE'), mode 1: c_rmse ('C_MSE'); ref / est in any cruse_cplx_layout; dest NULL or est's layout; ws as wo_male
+extern "C" int cruse_spec_loss_fwd_bwd(int mode, const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
+                                       float* dest, float* loss, void* ws, int B, int T, int F, void* stream) {
+    CRUSE_CHECK_ARG(ref && est && loss && ws, "spec_loss: null pointer");
+    CRUSE_CHECK_ARG(mode == 0 || mode == 1, "spec_loss: mode must be 0 (rmse) or 1 (c_rmse), got %d", mode);
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && F > 0, "spec_loss: bad sizes B=%d T=%d F=%d", B, T, F);
+    const long long rows = (long long)B * T;
+    long long blocks = rows;
+    long long cap = (long long)sm_count() * 8;
+    if (cap > LOSS_MAX_PARTS) cap = LOSS_MAX_PARTS;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double count = (double)B * T * F;
+    if (mode == 0) {
+        spec_loss_partial_kernel<0><<<(unsigned)blocks, LOSS_THREADS, 0, st>>>(ref, lref, est, lest, dest, (float*)ws, T, F, rows, (float)(1.0 / count));
+        CRUSE_LAUNCH_OK();
+        sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)blocks, 1.0 / count, loss);
+    } else {
+        spec_loss_partial_kernel<1><<<(unsigned)blocks, LOSS_THREADS, 0, st>>>(ref, lref, est, lest, dest, (float*)ws, T, F, rows, 1.f);
+        CRUSE_LAUNCH_OK();
+        sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)blocks, 1.0, loss);
+    }
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // SI-SNR (loss_func/loss.py:37-56; the 'SI-SNR' mode of the dispatcher, :25-26, returns its negative), est / ref wav [B, L]:
 //   a = <est,ref>, c = <ref,ref>, alpha = a / (c + eps), tn = |alpha ref|^2, nn = |est - alpha ref|^2,
 //   value = mean_b 10 log10(tn / (nn + eps) + eps)

@@ -65,6 +65,45 @@ def wo_male_frames_autograd(ref, est, unproc, F):
     return _WoMale.apply(ref, est, unproc, "btf2", F)
 
 
+class _SpecLoss(torch.autograd.Function):
+    """rmse / c_rmse on [B,2,T,F] spectra, differentiable w.r.t. est."""
+
+    @staticmethod
+    def forward(ctx, ref, est, mode):
+        B, _, T, F = est.shape
+        ref_c, est_c = ref.contiguous().float(), est.contiguous().float()
+        loss, dest = ops.spec_loss_fwd_bwd(mode, ref_c, ops.layout_bctf(ref_c), est_c, ops.layout_bctf(est_c), B, T, F,
+                                           want_grad=est.requires_grad)
+        ctx.save_for_backward(dest)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dest,) = ctx.saved_tensors
+        return None, (dest * g if dest is not None else None), None
+
+
+def _check_bctf(ref, est, what):
+    if ref.shape != est.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate {what}, {tuple(ref.shape)} vs {tuple(est.shape)}")   # loss.py:65-68, 89-92
+    if est.dim() != 4 or est.shape[1] != 2:
+        raise RuntimeError(f"{what}: expected [B,2,T,F], got {tuple(est.shape)}")
+    if not est.is_cuda:
+        raise RuntimeError(f"{what}: cruse_b200 runs on sm_100a only (no CPU fallback)")
+
+
+def rmse(ref, est, eps=1e-8):
+    """loss_func/loss.py:59-78 ('MSE' mode): sum sqrt((est-ref)^2) / (B*T*F) on [B,2,T,F]."""
+    _check_bctf(ref, est, "rmse")
+    return _SpecLoss.apply(ref, est, "MSE")
+
+
+def c_rmse(ref, est, unproc=None, norm=False, eps=1e-8):
+    """loss_func/loss.py:88-118 ('C_MSE' mode): power-law compressed complex error, arithmetic kept literally."""
+    _check_bctf(ref, est, "c_mse")
+    return _SpecLoss.apply(ref, est, "C_MSE")
+
+
 class _SiSnr(torch.autograd.Function):
     """mean SI-SNR (dB) of est vs ref waveforms, differentiable w.r.t. est (loss_func/loss.py:37-56)."""
 
@@ -99,7 +138,8 @@ def wo_male_loss():
 
 
 class loss_func:
-    """loss_func/loss.py:16-34 dispatcher; WO_MALE (the hot path) and SI-SNR are built (others: SURVEY 8f2)."""
+    """loss_func/loss.py:16-34 dispatcher; WO_MALE (the hot path), SI-SNR, C_MSE and MSE are built -- every mode the
+    reference's dispatcher itself implements (:24-34; the remaining names fall through to None there)."""
 
     MODES = ['SI-SNR', 'SS-SNR', 'MSE', 'Normal_MSE', 'CN_MSE', 'D_MSE', 'WO_MALE', 'C_MSE']
 
@@ -114,4 +154,8 @@ class loss_func:
             return -(sisnr(inputs, labels))                                  # :25-26 (time-domain estimate / target)
         if self.loss_mode == 'SS-SNR':
             return 0                                                         # :27-28
+        if self.loss_mode == 'C_MSE':
+            return c_rmse(labels, inputs)                                    # :31-32
+        if self.loss_mode == 'MSE':
+            return rmse(labels, inputs)                                      # :33-34
         raise NotImplementedError(f"loss mode {self.loss_mode!r} is outside the built hot path (SURVEY.md 8f2)")

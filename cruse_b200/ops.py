@@ -633,6 +633,18 @@ def wo_male_masked_fwd(ref, lref, mask, unp, lunp, B, T, F):
     return loss
 
 
+def spec_loss_fwd_bwd(mode, ref, lref, est, lest, B, T, F, want_grad=False):
+    """mode 'MSE' (rmse, loss.py:59-78) or 'C_MSE' (c_rmse, :88-118) -> (loss 0-dim, dL/d est in est's layout | None)."""
+    _req(ref, "ref")
+    _req(est, "est")
+    loss = torch.empty((), device=est.device, dtype=torch.float32)
+    dest = torch.zeros_like(est) if want_grad else None
+    ws = _loss_ws(est.device)
+    _call("cruse_spec_loss_fwd_bwd", {"MSE": 0, "C_MSE": 1}[mode], _p(ref), lref, _p(est), lest, _p(dest), _p(loss), _p(ws), B, T, F,
+          _stream(), meta=(f"spec_loss[{mode}]", B * T * F * 8 * (3 if want_grad else 2), 40 * B * T * F))
+    return loss, dest
+
+
 def wo_male_masked_partial_range(ref, lref, mask, unp, lunp, ws, p_off, nparts, B, T, F, t0, t1):
     """partial sums of the masked loss over the frames [t0, t1) into ws[p_off, p_off + nparts)."""
     _call("cruse_wo_male_masked_partial_range", _p(ref), lref, _p(mask), _p(unp), lunp, _p(ws), p_off, nparts, B, T, F, t0, t1, _stream(),

@@ -235,6 +235,12 @@ int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float*
 int cruse_wo_male_masked_fwd(const float* ref, cruse_cplx_layout lref, const float* mask, const float* unproc,
                              cruse_cplx_layout lunp, float* loss, void* ws, int B, int T, int F, void* stream);
 size_t cruse_wo_male_ws_bytes(void);
+/* The other spectral-domain modes of the dispatcher (loss_func/loss.py:31-34) on ref / est in any complex layout:
+ * mode 0 = rmse (:59-78): sum_c |est_c - ref_c| / (B*T*F);  mode 1 = c_rmse (:88-118): power-law compressed complex error with
+ * c = beta = 0.3, arithmetic kept literally (incl. the tmp1/tmp2 mix at :107-109), plain sum.  dest (NULL or est's layout)
+ * receives d loss / d est (0 where |est| = 0, where torch's autograd yields inf / NaN).  ws: cruse_wo_male_ws_bytes(). */
+int cruse_spec_loss_fwd_bwd(int mode, const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
+                            float* dest, float* loss, void* ws, int B, int T, int F, void* stream);
 /* SI-SNR of loss_func/loss.py:37-56 on waveforms est / ref [B,L]: value = mean_b 10 log10(|alpha ref|^2 /
  * (|est - alpha ref|^2 + eps) + eps), alpha = <est,ref> / (<ref,ref> + eps); the dispatcher's 'SI-SNR' mode (:25-26) returns
  * its negative.  cruse_sisnr_bwd: dest = gscale * d value / d est (gscale: device scalar or NULL = 1), from the coefficients

@@ -584,3 +584,24 @@ def test_sisnr_through_mask_and_istft_gradient(cuda):
     got.backward()
     assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want)) + 1e-4
     assert rel_err(m.grad, mask.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("mode,fn", [("MSE", "rmse"), ("C_MSE", "c_rmse")])
+@pytest.mark.parametrize("B,T,F", [(2, 9, 256), (3, 5, 161), (1, 1, 7)])
+def test_spectral_loss_modes_match_oracle(cuda, mode, fn, B, T, F):
+    """the 'MSE' (rmse, loss.py:59-78) and 'C_MSE' (c_rmse, :88-118, arithmetic kept literally) modes of the dispatcher on
+    [B,2,T,F] spectra: value and d/d est against autograd of the oracle; argument order of the dispatcher (labels, inputs)."""
+    from cruse_b200 import loss as L_
+    from oracle import cruse_oracle as o
+    torch.manual_seed(47)
+    ref = torch.randn(B, 2, T, F)
+    est = (ref + 0.5 * torch.randn(B, 2, T, F)).requires_grad_()
+    want = getattr(o, fn)(ref, est)
+    want.backward()
+    e = est.detach().to(cuda).requires_grad_()
+    got = L_.loss_func(mode).loss(e, ref.to(cuda))
+    got.backward()
+    assert abs(float(got) - float(want)) <= 2e-5 * abs(float(want))
+    assert rel_err(e.grad, est.grad) <= 2e-4
+    with pytest.raises(RuntimeError):
+        getattr(L_, fn)(ref.to(cuda), e[:, :, :, :-1])

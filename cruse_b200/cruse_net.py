@@ -93,8 +93,8 @@ class GGRU(nn.Module):
         if ops.GRU_WAVEFRONT_MODE != "flags":
             return None
         nch = max(2, min(self.WAVEFRONT_FLAG_CHUNKS, T // 24))
-        # a SHORT last chunk: what is left after layer 1 has finished -- LayerNorm 1 + projections + layer 2 of the last chunk, then
-        # its LayerNorm 2 + decoder -- is proportional to it
+        # optional SHORT last chunk (WAVEFRONT_LAST_CHUNK frames; 0 = equal chunks, the default): what is left after layer 1 has
+        # finished is proportional to it -- measured on B200 it loses all the same (32 / 16 frames: 1.51 / 1.53 vs 1.49 ms per step)
         last = min(self.WAVEFRONT_LAST_CHUNK, T // nch)
         if last >= 8 and nch >= 3:
             bounds = [(T - last) * k // (nch - 1) for k in range(nch)] + [T]

@@ -97,3 +97,18 @@ def test_state_dict_surface_equals_oracle():
             assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
         assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
         ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_ctypes_argument_counts_match_header_prototypes():
+    """every entry of the ctypes table passes exactly as many arguments as the C prototype declares (a drifted table corrupts
+    the call silently): parsed from include/cruse_b200.h"""
+    import re
+    from cruse_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "cruse_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = dict(re.findall(r"\b(cruse_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))

@@ -11,15 +11,25 @@ authority).  Each function cites the reference lines it fo
 (paths relative to /root/reference) and each repair cites the defect it fixes
 (SURVEY.md Appendix A).
 
-PARITY PIN STATUS: **parity unpinned against reference golden vectors** -- the
-reference holds no golden vector, known-answer test or fixture for this path and
-its own model/loss/STFT files do not import.  What *is* pinned:
-the reference fragments that do run in the build container
-(``model/based_model/cust_conv.py`` Conv2dNormAct / GroupedGRULayer,
-``train_base/acoustics/mask.py`` complex_mul, ``train_base/loss.py`` si_snr_loss)
-were executed there by ``oracle/make_golden.py`` and their outputs are committed
-under ``tests/golden/ref_*.npz``; ``tests/test_oracle.py`` checks this file
-against them.
+PARITY PIN STATUS: **pinned to outputs of the reference's own hot-path source, executed in the build
+container** (the reference holds no golden vector, known-answer test or fixture for this path -- SURVEY.md
+section 0 -- so the fixtures were generated from its code).  ``oracle/ref_extract.py`` cuts the class / function
+source out of the reference files' ASTs (the modules themselves do not import) and runs it unmodified with
+era-compatible torch spellings, or with asserted one-token repairs of genuine defects (SURVEY App. A);
+``oracle/make_golden.py`` stores the outputs as ``tests/golden/refx_*.npz``:
+
+  GGRU                 model/cruse_net.py:14-51 unmodified, taken at ln1 / ln2 by forward hook (hidden 64 and 1024)
+  unet_2 stages        the modules model/cruse_net.py:129-146 builds (conv3/bn3, conv4/bn4, skip convs, GGRU, ReLU)
+                       composed as :151-156 with the App. A.1 slice repair; decoder stage vs cust_conv.py:65-113
+  wo_male / rmse / c_rmse / sisnr / loss_func   loss_func/loss.py from source (one repaired index, :139)
+  stft / istft         train_base/acoustics/feature.py:10-61 unmodified
+  PreProcess           utils/utils.py:365-455 unmodified
+  ConvSTFT             train_base/acoustics/conv_stft.py: stft unmodified; istft with four repairs (round trip exact)
+  si_snr_loss, complex_mul, encoder stage (train/eval BN), grouped GRU with state: ``ref_*.npz`` (fragments that import)
+
+``tests/test_oracle.py`` drives THIS file's classes with those fixtures.  What cannot be pinned by any reference
+output: the composition of the repaired ``unet_2.forward`` (:147-165 cannot execute; its repairs are SURVEY App. A.1)
+and the decoder's ``conv{k}_t`` / ``bn{k}_t`` modules, which the reference constructor never creates.
 """
 from __future__ import annotations
 
@@ -127,20 +137,33 @@ class unet_2(nn.Module):
             return self.elu(x)
         return getattr(self, name)(x)
 
+    # the three stage expressions of the reference forward, one method each so that tests can drive a single
+    # stage with reference-generated weights (tests/test_oracle.py)
+    def enc_stage(self, k, x):
+        """:149-152 repaired: act(bn_k(conv_k(x)[..., :-pad_t, :]))  (drop the look-ahead frame)."""
+        z = getattr(self, f"conv{k}")(x)[..., :-self.padding[0], :]
+        return self._act(f"act{k}", getattr(self, f"bn{k}")(z))
+
+    def skip(self, k, e):
+        """:153-156 repaired: skip_connect_k(e_k)."""
+        return getattr(self, f"skip_connect_{k}")(e)
+
+    def dec_stage(self, k, x, skip):
+        """:161-163 repaired: act(bn_k_t(conv_k_t(x)[..., :F_{k-1}])) + skip_{k-1}."""
+        z = getattr(self, f"conv{k}_t")(x)[..., : self.freqs[k - 1]]
+        return self._act(f"act{k}_t", getattr(self, f"bn{k}_t")(z)) + skip
+
     def forward(self, x):
         n = self.laynum
-        p0 = self.padding[0]
         e = []
         out = x
-        for k in range(1, n + 1):                                         # :149-152 repaired
-            z = getattr(self, f"conv{k}")(out)[..., :-p0, :]
-            out = self._act(f"act{k}", getattr(self, f"bn{k}")(z))
+        for k in range(1, n + 1):                                         # :149-152
+            out = self.enc_stage(k, out)
             e.append(out)
-        skips = [getattr(self, f"skip_connect_{k}")(e[k - 1]) for k in range(1, n + 1)]  # :153-156 repaired
+        skips = [self.skip(k, e[k - 1]) for k in range(1, n + 1)]         # :153-156
         out = self.gru(e[-1]) + skips[-1]                                 # :158-160
-        for k in range(n, 1, -1):                                         # :161-163 repaired (chained)
-            z = getattr(self, f"conv{k}_t")(out)[..., : self.freqs[k - 1]]
-            out = self._act(f"act{k}_t", getattr(self, f"bn{k}_t")(z)) + skips[k - 2]
+        for k in range(n, 1, -1):                                         # :161-163 (chained)
+            out = self.dec_stage(k, out, skips[k - 2])
         return torch.sigmoid(self.conv1_t(out)[..., : self.freqs[0]])     # :164
 
 
@@ -207,6 +230,45 @@ class PreProcess:
         c = torch.view_as_complex(stft_outputs.contiguous()).transpose(1, 2)  # -> [B,F,T]
         return torch.istft(c, n_fft=self.fft_len, hop_length=self.win_inc, win_length=self.win_len,
                            window=self.window, center=True, length=sig_len)
+
+
+class ConvSTFT:
+    """train_base/acoustics/conv_stft.py:8-129, the conv-form analysis / synthesis pair (320/160, symmetric hamming,
+    zero padding win-hop).  Restated with FFT calls instead of DFT-matrix convolutions (same linear maps):
+    ``stft``  :72-98   = torch.stft(window=hamming(N, symmetric), center-equivalent constant pad of win-hop);
+    ``istft`` :100-129 = per-frame inverse real DFT (NO synthesis window), overlap-add, divide by the hop-periodic
+    sum of the ANALYSIS window (+eps, :60-70,127-128), trim win-hop at both ends (conv_transpose1d padding).
+    Repairs: scipy.hamming / nn.parameter (:20,23), imaginary channel (:102), Hermitian cat (:108), the sign of the
+    imaginary synthesis term (:120) and the envelope tiling (:66-67) -- see oracle/ref_extract.py::conv_stft_class."""
+
+    def __init__(self, win_size=320, hop_size=160):
+        import scipy.signal
+        self.win_size, self.hop_size = win_size, hop_size
+        self.n_overlap = win_size // hop_size
+        self.win = torch.relu(torch.from_numpy(scipy.signal.windows.hamming(win_size)).float())   # :20-21
+        self.eps = torch.finfo(torch.float32).eps                                                # :39
+
+    def stft(self, sig):
+        pad = self.win_size - self.hop_size                                                      # :85,90
+        x = torch.nn.functional.pad(sig, (pad, pad))
+        c = torch.stft(x, self.win_size, self.hop_size, self.win_size, window=self.win, center=False,
+                       return_complex=True)                                                      # [B,F,T]
+        spec_r, spec_i = c.real.transpose(-1, -2).contiguous(), c.imag.transpose(-1, -2).contiguous()   # :92-93
+        return spec_r, spec_i, torch.sqrt(spec_r ** 2 + spec_i ** 2), torch.atan2(spec_i, spec_r)       # :95-96
+
+    def istft(self, x):
+        """x: [B,2,T,F] (real, imag) -> [B, (T-1)*hop + win - 2*(win-hop)]."""
+        c = torch.complex(x[:, 0], x[:, 1])                                                      # [B,T,F]
+        frames = torch.fft.irfft(c, n=self.win_size, dim=-1)                                     # :105-124 (basis / N)
+        B, T, N = frames.shape
+        hop, pad = self.hop_size, self.win_size - self.hop_size
+        out = torch.zeros(B, (T - 1) * hop + N)
+        for t in range(T):                                                                       # conv_transpose1d = OLA
+            out[:, t * hop:t * hop + N] += frames[:, t]
+        sig = out[:, pad:out.shape[1] - pad]
+        seg = sum(self.win[i * hop:(i + 1) * hop] for i in range(self.n_overlap))                # :62-65
+        window = seg.repeat(T - self.n_overlap + 1)                                              # :66-68 repaired
+        return sig / (window + self.eps)                                                         # :128
 
 
 def complex_mul(noisy_r, noisy_i, mask_r, mask_i):
@@ -353,3 +415,19 @@ def make_model(in_feat=256, act="relu", seed=1234, eval_stats=True):
                 mod.running_mean.copy_(0.1 * torch.randn(mod.num_features, generator=g))
                 mod.running_var.copy_(1 + 0.1 * torch.rand(mod.num_features, generator=g))
     return m
+
+
+def seeded_fill_(mod, seed, scale=0.06):
+    """Overwrite every floating parameter / buffer of ``mod`` from a seeded generator in state_dict key order, so that a
+    test can rebuild the same weights in the oracle's module without storing 3 M floats (oracle/make_golden.py fills the reference's modules with it, tests/test_oracle.py the oracle's)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for k, v in mod.state_dict().items():
+            if not v.is_floating_point():
+                continue
+            r = torch.randn(v.shape, generator=g) * scale
+            if k.endswith("running_var"):
+                r = 1 + r.abs()
+            elif k.endswith(".weight") and v.dim() == 1:       # BN / LN scale
+                r = 1 + r
+            v.copy_(r)

@@ -1,12 +1,19 @@
-"""CPU: pin oracle/cruse_oracle.py against (i) outputs of the reference fragments that run
-(tests/golden/ref_*.npz, generated by oracle/make_golden.py from /root/reference) and (ii) its own
-committed end-to-end vectors (drift guard).  The oracle is test infrastructure."""
+"""CPU: pin oracle/cruse_oracle.py against reference-generated fixtures.
+
+(i)   tests/golden/refx_*.npz -- outputs of the reference's HOT-PATH files themselves (GGRU and the modules unet_2's
+      constructor builds, loss_func/loss.py, feature.py stft/istft, utils.py PreProcess, conv_stft.py), executed in the
+      build container by oracle/make_golden.py through oracle/ref_extract.py (AST-cut source, unmodified or with the
+      asserted one-token repairs of SURVEY App. A);
+(ii)  tests/golden/ref_*.npz  -- the adjacent reference fragments that import as they are (cust_conv.py, mask.py,
+      train_base/loss.py);
+(iii) the oracle's own committed end-to-end vectors (drift guard).
+Every test below drives the ORACLE'S OWN classes / functions (o.unet_2.enc_stage / skip / dec_stage, o.GGRU, o.stft ...)
+with the fixture's weights -- no hand-built stand-ins.  The oracle is test infrastructure."""
 import os
 
 import numpy as np
 import pytest
 import torch
-import torch.nn as nn
 
 from oracle import cruse_oracle as o
 
@@ -15,63 +22,200 @@ def _load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name))
 
 
-def _oracle_stage(cin, cout, F, sd, train):
-    """One encoder stage exactly as oracle.unet_2 builds it (conv (2,3)/s(1,2)/p(1,1), drop last frame, BN, ReLU)."""
-    conv = nn.Conv2d(cin, cout, (2, 3), (1, 2), [1, 1])
-    bn = nn.BatchNorm2d(cout)
-    # reference Conv2dNormAct = ConstantPad2d -> Conv2d -> BatchNorm2d -> ReLU  (cust_conv.py:15-62)
-    conv.weight.data.copy_(torch.from_numpy(sd["sd.1.weight"]))
-    conv.bias.data.copy_(torch.from_numpy(sd["sd.1.bias"]))
-    bn.weight.data.copy_(torch.from_numpy(sd["sd.2.weight"]))
-    bn.bias.data.copy_(torch.from_numpy(sd["sd.2.bias"]))
-    if "sd.2.running_mean" in sd:
-        bn.running_mean.copy_(torch.from_numpy(sd["sd.2.running_mean"]))
-        bn.running_var.copy_(torch.from_numpy(sd["sd.2.running_var"]))
-    conv.train(train)
-    bn.train(train)
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
 
-    def f(x):
-        return torch.relu(bn(conv(x)[..., :-1, :]))
-    return f
+
+def _stage_net(cin, cout, k, sd, train, in_feat=256):
+    """o.unet_2 whose stage k is (cin -> cout) and carries the reference Conv2dNormAct's weights
+    (cust_conv.py:15-62 = ConstantPad2d -> Conv2d -> BatchNorm2d -> ReLU; Sequential indices 1 and 2)."""
+    ch = [1, 1, 1, 1, 1]
+    ch[k - 1], ch[k] = cin, cout
+    net = o.unet_2(in_feat=in_feat, ch=tuple(ch))
+    conv, bn = getattr(net, f"conv{k}"), getattr(net, f"bn{k}")
+    conv.weight.data.copy_(_t(sd["sd.1.weight"]))
+    conv.bias.data.copy_(_t(sd["sd.1.bias"]))
+    bn.weight.data.copy_(_t(sd["sd.2.weight"]))
+    bn.bias.data.copy_(_t(sd["sd.2.bias"]))
+    if "sd.2.running_mean" in sd:
+        bn.running_mean.copy_(_t(sd["sd.2.running_mean"]))
+        bn.running_var.copy_(_t(sd["sd.2.running_var"]))
+    return net.train(train)
 
 
 @pytest.mark.parametrize("name,cin,cout", [("a", 1, 8), ("b", 8, 16)])
-def test_encoder_stage_matches_reference_conv2dnormact_train(golden_dir, name, cin, cout):
+def test_enc_stage_matches_reference_conv2dnormact_train(golden_dir, name, cin, cout):
     g = _load(golden_dir, f"ref_conv2dnormact_train_{name}.npz")
-    x = torch.from_numpy(g["x"])
+    x = _t(g["x"])
     with torch.no_grad():
-        y = _oracle_stage(cin, cout, x.shape[-1], g, train=True)(x)
+        y = _stage_net(cin, cout, 2, g, train=True).enc_stage(2, x)
     np.testing.assert_allclose(y.numpy(), g["y_train"], rtol=1e-5, atol=1e-5)
 
 
-def test_encoder_stage_matches_reference_conv2dnormact_eval(golden_dir):
+def test_enc_stage_matches_reference_conv2dnormact_eval(golden_dir):
     g = _load(golden_dir, "ref_conv2dnormact_eval.npz")
-    x = torch.from_numpy(g["x"])
     with torch.no_grad():
-        y = _oracle_stage(1, 8, 161, g, train=False)(x)
+        y = _stage_net(1, 8, 1, g, train=False).enc_stage(1, _t(g["x"]))
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-5, atol=1e-5)
 
 
-def test_grouped_gru_matches_reference_groupedgrulayer(golden_dir):
-    """reference GroupedGRULayer (cust_conv.py:250-325) == per-group nn.GRU on chunks + cat, the building
-    block the oracle's GGRU uses (cruse_net.py:42-50), including the explicit-state (streaming) call."""
+def test_unet2_stages_match_modules_built_by_reference_constructor(golden_dir):
+    """model/cruse_net.py:129-146 executed unmodified: the encoder stages whose modules survive the naming bug (conv3/bn3,
+    conv4/bn4), the skip convs and the GGRU it builds, filled from the same seeded stream, against o.unet_2's own stage methods."""
+    g = _load(golden_dir, "refx_unet2_ctor.npz")
+    keys = [str(k) for k in g["keys"]]
+    # what the reference constructor really creates (documents the defect the oracle repairs)
+    assert "conv4_t.weight" not in keys and "bn1_t.weight" in keys and "skip_connect_4.weight" in keys
+    assert dict(zip(keys, (str(s) for s in g["shapes"])))["gru.ln1.weight"] == "(1024,)"
+    assert list(g["padding"]) == [1, 1]
+    net = o.unet_2(in_feat=256).eval()
+    assert net.padding == [1, 1]
+    # the GGRU: same seeded fill as make_golden applied to the reference's module, restricted to the gru.* keys in order
+    ref_sd_order = [k for k in keys]
+    gen = torch.Generator(device="cpu").manual_seed(int(g["fill_seed"]))
+    shapes = dict(zip(keys, (eval(str(s)) for s in g["shapes"])))
+    sd = net.state_dict()
+    with torch.no_grad():
+        for k in ref_sd_order:                      # replay the generator stream over the REFERENCE's key order
+            if k.endswith("num_batches_tracked"):
+                continue
+            r = torch.randn(shapes[k], generator=gen) * 0.06
+            if k.endswith("running_var"):
+                r = 1 + r.abs()
+            elif k.endswith(".weight") and len(shapes[k]) == 1:
+                r = 1 + r
+            if k.startswith("gru."):
+                sd[k].copy_(r)
+        for k in ("conv3", "bn3", "conv4", "bn4", "skip_connect_3", "skip_connect_4"):
+            for name in [n for n in g.files if n.startswith(f"sd.{k}.")]:
+                t = sd[name[3:]]
+                t.copy_(_t(g[name]).reshape(t.shape))
+        x3 = _t(g["x3"])
+        e3 = net.enc_stage(3, x3)
+        e4 = net.enc_stage(4, e3)
+        s3, s4 = net.skip(3, e3), net.skip(4, e4)
+        gr = net.gru(e4)                                         # [B,C,T,F'] -> back to the ln2 layout [B,T,C*F']
+    np.testing.assert_allclose(e3.numpy(), g["e3"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(e4.numpy(), g["e4"], rtol=1e-5, atol=1e-5)
+    # the reference builds the skip convs without padding (F-2 bins, App. A.1); the oracle's pad (0,1) keeps F: interior equal
+    np.testing.assert_allclose(s3[..., 1:-1].numpy(), g["s3"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(s4[..., 1:-1].numpy(), g["s4"], rtol=1e-5, atol=1e-5)
+    ln2 = gr.transpose(1, 2).reshape(gr.shape[0], gr.shape[2], -1)
+    np.testing.assert_allclose(ln2.numpy(), g["gru_ln2"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["small", "cfgB"])
+def test_ggru_matches_reference_ggru_at_ln2(golden_dir, tag):
+    """model/cruse_net.py:14-51 executed unmodified (forward hook on ln1 / ln2; :53 then raises) vs o.GGRU."""
+    g = _load(golden_dir, f"refx_ggru_{tag}.npz")
+    m = o.GGRU(hidden_size=int(g["hidden"]), groups=int(g["groups"]))
+    assert list(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    o.seeded_fill_(m, int(g["fill_seed"]))
+    got = {}
+    m.ln1.register_forward_hook(lambda mod, i, out: got.__setitem__("ln1", out.detach()))
+    x = _t(g["x"])
+    with torch.no_grad():
+        y = m(x)
+    np.testing.assert_allclose(got["ln1"].numpy(), g["ln1"], rtol=1e-4, atol=2e-5)
+    ln2 = y.transpose(1, 2).reshape(y.shape[0], y.shape[2], -1)
+    np.testing.assert_allclose(ln2.numpy(), g["ln2"], rtol=1e-4, atol=2e-5)
+    assert y.shape == x.shape
+
+
+def test_dec_stage_matches_reference_convtranspose2dnormact(golden_dir):
+    """cust_conv.py:65-113 ConvTranspose2dNormAct((1,3), fstride 2, fpad False) = ConvT + BN + ReLU, eval; the oracle crops to
+    2F bins before BN (pointwise in eval, so the crop commutes) and adds the skip."""
+    g = _load(golden_dir, "refx_convT_stage.npz")
+    net = o.unet_2(in_feat=256, ch=(1, 8, 16, 32, 64)).eval()
+    # the fixture's stage is 32 -> 16 channels on 32 bins = the oracle's decoder stage 3 (conv3_t, bn3_t: 32 bins -> 64)
+    net.conv3_t.weight.data.copy_(_t(g["sd.0.weight"]))
+    net.conv3_t.bias.data.copy_(_t(g["sd.0.bias"]))
+    for k in ("weight", "bias", "running_mean", "running_var"):
+        getattr(net.bn3_t, k).data.copy_(_t(g[f"sd.1.{k}"]))
+    with torch.no_grad():
+        y = net.dec_stage(3, _t(g["x"]), torch.zeros(2, 16, 5, 64))
+    np.testing.assert_allclose(y.numpy(), g["y"][..., :64], rtol=1e-5, atol=1e-5)
+
+
+def test_grouped_gru_state_carry_matches_reference_groupedgrulayer(golden_dir):
+    """reference GroupedGRULayer (cust_conv.py:250-325) with explicit h0 (the streaming call) == the oracle GGRU's layer-2
+    arithmetic (chunk -> per-group nn.GRU -> cat, cruse_net.py:48-50) run on the oracle's own gru_list2 modules."""
     g = _load(golden_dir, "ref_groupedgru.npz")
     G, H = 4, 8
-    x, h0 = torch.from_numpy(g["x"]), torch.from_numpy(g["h0"])
-    grus = []
+    m = o.GGRU(hidden_size=G * H, groups=G)
     for i in range(G):
-        m = nn.GRU(H, H, 1, batch_first=True)
         for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
-            getattr(m, k).data.copy_(torch.from_numpy(g[f"sd.layers.{i}.{k}"]))
-        grus.append(m)
+            getattr(m.gru_list2[i], k).data.copy_(_t(g[f"sd.layers.{i}.{k}"]))
+    x, h0 = _t(g["x"]), _t(g["h0"])
     with torch.no_grad():
-        outs = [grus[i](x[..., i * H:(i + 1) * H], h0[i:i + 1]) for i in range(G)]
+        outs = [m.gru_list2[i](c, h0[i:i + 1]) for i, c in enumerate(torch.chunk(x, G, dim=-1))]
         y = torch.cat([a for a, _ in outs], dim=-1)
         h = torch.cat([b for _, b in outs], dim=0)
-        y0 = torch.cat([grus[i](x[..., i * H:(i + 1) * H])[0] for i in range(G)], dim=-1)
+        y0 = torch.cat([m.gru_list2[i](c)[0] for i, c in enumerate(torch.chunk(x, G, dim=-1))], dim=-1)
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(h.numpy(), g["h"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(y0.numpy(), g["y_zero"], rtol=1e-5, atol=1e-6)
+
+
+def test_losses_match_reference_loss_py(golden_dir):
+    """loss_func/loss.py executed from its own source (one repaired line, :139): wo_male, rmse, c_rmse, sisnr and the
+    dispatcher's argument order (:24-34)."""
+    g = _load(golden_dir, "refx_loss.npz")
+    ref, est, unp, s1, s2 = (_t(g[k]) for k in ("ref", "est", "unproc", "s1", "s2"))
+    np.testing.assert_allclose(o.wo_male(ref, est, unp).numpy(), g["wo_male"], rtol=1e-6)
+    np.testing.assert_allclose(o.rmse(ref, est).numpy(), g["rmse"], rtol=1e-6)
+    np.testing.assert_allclose(o.c_rmse(ref, est).numpy(), g["c_rmse"], rtol=1e-5)
+    np.testing.assert_allclose(o.sisnr(s1, s2).numpy(), g["sisnr"], rtol=1e-6)
+    np.testing.assert_allclose(o.loss_func("WO_MALE").loss(est, ref, unp).numpy(), g["disp_WO_MALE"], rtol=1e-6)
+    np.testing.assert_allclose(o.loss_func("MSE").loss(est, ref).numpy(), g["disp_MSE"], rtol=1e-6)
+    np.testing.assert_allclose(o.loss_func("C_MSE").loss(est, ref).numpy(), g["disp_C_MSE"], rtol=1e-5)
+    np.testing.assert_allclose(o.loss_func("SI-SNR").loss(s1, s2).numpy(), g["disp_SI_SNR"], rtol=1e-6)
+    with pytest.raises(RuntimeError):
+        o.wo_male(ref, est[:, :, :-1], unp)
+
+
+@pytest.mark.parametrize("tag,n_fft,hop", [("B", 512, 320), ("R", 320, 160)])
+def test_stft_istft_match_reference_feature_py(golden_dir, tag, n_fft, hop):
+    """train_base/acoustics/feature.py:10-61 executed unmodified."""
+    g = _load(golden_dir, "refx_feature.npz")
+    y = _t(g[f"{tag}_y"])
+    c = o.stft(y, n_fft, hop, n_fft)
+    np.testing.assert_allclose(torch.view_as_real(c).numpy(), g[f"{tag}_spec"], rtol=1e-5, atol=1e-5)
+    L = y.shape[-1]
+    np.testing.assert_allclose(o.istft(_t(g[f"{tag}_spec"]), n_fft, hop, n_fft, length=L).numpy(), g[f"{tag}_wav"], atol=1e-6)
+    ms = _t(g[f"{tag}_masked_spec"])
+    np.testing.assert_allclose(o.istft(ms, n_fft, hop, n_fft, length=L).numpy(), g[f"{tag}_masked_wav"], atol=1e-6)
+    np.testing.assert_allclose(o.istft((c.abs(), c.angle()), n_fft, hop, n_fft, length=L, use_mag_phase=True).numpy(),
+                               g[f"{tag}_wav_magphase"], atol=1e-5)
+
+
+def test_preprocess_matches_reference_utils_py(golden_dir):
+    """utils/utils.py:365-455 PreProcess executed unmodified (era torch.stft / istft spellings)."""
+    g = _load(golden_dir, "refx_preprocess.npz")
+    pp = o.PreProcess(512, 320, 512, "hanning", "mag_mapping", "freq")
+    stft_inputs, real, imag, mags, phase = pp.pre_stft(_t(g["y"]))
+    for a, k in ((stft_inputs, "stft_inputs"), (real, "real"), (imag, "imag"), (mags, "mags")):
+        np.testing.assert_allclose(a.numpy(), g[k], rtol=1e-5, atol=1e-5)
+    dphi = np.angle(np.exp(1j * (phase.numpy() - g["phase"])))
+    assert np.abs(dphi[g["mags"] > 1e-2]).max() < 1e-3
+    spec = pp.masking(_t(g["mask"]))
+    np.testing.assert_allclose(spec.numpy(), g["masked"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(pp.reconstruction(spec, sig_len=3200).numpy(), g["wav"], atol=1e-6)
+    with pytest.raises(ValueError):
+        o.PreProcess(512, 320, 512, "hamming", "mag_mapping", "freq")
+
+
+def test_conv_stft_matches_reference_conv_stft_py(golden_dir):
+    """train_base/acoustics/conv_stft.py: stft executed unmodified, istft with the repairs listed in oracle/ref_extract.py."""
+    g = _load(golden_dir, "refx_conv_stft.npz")
+    S = o.ConvSTFT()
+    np.testing.assert_allclose(S.win.numpy(), g["win"], atol=1e-7)
+    r, i, mag, pha = S.stft(_t(g["y"]))
+    np.testing.assert_allclose(r.numpy(), g["spec_r"], atol=5e-5)
+    np.testing.assert_allclose(i.numpy(), g["spec_i"], atol=5e-5)
+    np.testing.assert_allclose(mag.numpy(), g["mag"], atol=5e-5)
+    np.testing.assert_allclose(S.istft(_t(g["masked"])).numpy(), g["masked_wav"], atol=2e-6)
+    np.testing.assert_allclose(S.istft(torch.stack([r, i], 1)).numpy(), g["y"], atol=1e-5)
 
 
 def test_misc_reference_fragments(golden_dir):

@@ -56,6 +56,7 @@ SIGNATURES = {
     "cruse_gru_seq_flagged_tc": (c_int, [c_fp, c_pp, c_pp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp, c_int, c_fp, C.c_uint, c_fp, c_fp, c_fp]),
     "cruse_flag_wait": (c_int, [c_fp, C.c_uint, c_fp, c_fp]),
     "cruse_flag_set": (c_int, [c_fp, C.c_uint, c_fp]),
+    "cruse_poison_on_error": (c_int, [c_fp, c_pp, c_pp, c_int, c_fp]),
     "cruse_gru_ih_gemm_tm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_gru_seq_chunk_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp]),
     "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),
@@ -91,6 +92,10 @@ SIGNATURES = {
     "cruse_layernorm_bwd": (c_int, [c_fp] * 7 + [c_ll, c_int, c_fp]),
     "cruse_gru_seq_bwd_tc": (c_int, [c_fp, c_fp, c_fp, c_fp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gemm_tn_tc": (c_int, [c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_fp]),
+    "cruse_gru_exact_ws_bytes": (C.c_size_t, [c_int] * 2),
+    "cruse_gru_seq_fwd_exact": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_gru_seq_bwd_exact": (c_int, [c_fp, c_fp, c_fp, c_fp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
+    "cruse_gemm_tn_fp32": (c_int, [c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_fp]),
     "cruse_gru_step_ws_bytes": (C.c_size_t, [c_int] * 3),
     "cruse_gru_step": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_transpose_gcm": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_int, c_ll, c_fp]),

@@ -21,9 +21,11 @@ def gru_layer_fwd_train(x2d, grus, B, T, interleave, side=None, beside=None):
     occupies 8*G*ceil(B/32) SMs) -- called right after the recurrence has been launched on a high-priority stream, see
     _SideWork.critical"""
     w_ih = [g.weight_ih_l0 for g in grus]
-    xproj = ops.gru_ih_gemm(x2d, w_ih, [g.bias_ih_l0 for g in grus], [g.bias_hh_l0 for g in grus], mode="tf32")
+    # numeric mode: ops.GRU_IH_MODE / ops.GRU_SEQ_MODE ("tf32" = tensor cores, the product default; "fp32" = the exact twins of
+    # csrc/gru_exact.cu, for the end-to-end gradient parity check against the oracle's autograd)
+    xproj = ops.gru_ih_gemm(x2d, w_ih, [g.bias_ih_l0 for g in grus], [g.bias_hh_l0 for g in grus])
     run = lambda: ops.gru_seq_fwd(xproj, [g.weight_hh_l0 for g in grus], [g.bias_hh_l0 for g in grus], B, T,
-                                  interleave=interleave, mode="tf32", want_gates=True)
+                                  interleave=interleave, want_gates=True)
     if side is not None and side.enabled and beside is not None:
         ready = side.mark()
         y, gates = side.critical(run, ready)
@@ -262,6 +264,10 @@ class _Unet2Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dmask):
         m, sv = ctx.model, ctx.sv
+        if sv is None:
+            raise RuntimeError("cruse_b200.unet_2: backward was already run through this forward pass; its saved activations were "
+                               "released (they are plain device buffers, not autograd-saved tensors, so retain_graph=True cannot "
+                               "keep them).  Run the forward again for a second backward.")
         n = m.laynum
         B, T, F, D, C4, F4 = ctx.dims
         act, train = m.act_kind, ctx.train
@@ -345,7 +351,11 @@ class _Unet2Fn(torch.autograd.Function):
 
 
 def unet2_frames_autograd(model, mag):
-    """mag [B,T,F] -> mask [B,T,F] with gradients to the module's parameters."""
+    """mag [B,T,F] -> mask [B,T,F] with gradients to the module's parameters (NOT to ``mag``: the reference trains on fixed
+    features, tools/train_stand.py; an input that requires grad is refused rather than silently given no gradient)."""
+    if mag.requires_grad:
+        raise RuntimeError("cruse_b200.unet_2: the input requires grad, but the sm_100a backward produces parameter gradients only "
+                           "(no dL/d input); detach the input (INTEGRATION.md, limitations)")
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     params = [dict(model.named_parameters())[n] for n in names]
     return _Unet2Fn.apply(model, mag.contiguous(), tuple(names), *params)

@@ -9,14 +9,34 @@ ways between the reference shell and this package:
 * preload / inference: ``load_state_dict(checkpoint["model"], strict=False)`` from a ``.tar`` (:128-147,
   train_base/inferencer/base_inferencer.py:128-134).
 
-Pure host code: ``unet_2``'s parameter names and shapes equal the repaired reference module, which is what
-makes the files interchangeable.
+Pure host code: ``unet_2``'s parameter names and shapes equal the REPAIRED reference module (the oracle's
+``unet_2``), which is what makes the files interchangeable -- the literal reference constructor builds ``bn1_t`` and no
+``conv*_t`` (model/cruse_net.py:138-142), so a file saved from it loads only with ``strict=False``, as the reference does.
+
+Files are read with ``torch.load(weights_only=True)``: the wire format needs tensors, ints, floats and (for ``best_score``) a
+numpy scalar, nothing that has to be unpickled as code.  ``unsafe=True`` restores torch's old arbitrary-pickle behaviour for
+files written by a trainer that stored other objects; only use it on files you trust.
 """
 from __future__ import annotations
 
 from pathlib import Path
 
 import torch
+
+
+def _load(path, map_location, unsafe=False):
+    if unsafe:
+        return torch.load(path, map_location=map_location, weights_only=False)
+    import numpy as np
+    safe = [np.dtype, np.ndarray]
+    try:                                        # numpy scalars (best_score = np.float64(...) in the reference's validation)
+        from numpy._core.multiarray import _reconstruct, scalar
+        safe += [_reconstruct, scalar]
+    except Exception:  # noqa: BLE001
+        pass
+    safe += [type(np.dtype(t)) for t in ("float32", "float64", "int64", "int32")]
+    with torch.serialization.safe_globals(safe):
+        return torch.load(path, map_location=map_location, weights_only=True)
 
 
 def _bare(model):
@@ -39,7 +59,7 @@ def save_checkpoint(checkpoints_dir, epoch, model, optimizer, best_score, scaler
     d.mkdir(parents=True, exist_ok=True)
     state = {
         "epoch": int(epoch),
-        "best_score": best_score,
+        "best_score": float(best_score),       # a plain float: loads under weights_only=True everywhere
         "optimizer": optimizer.state_dict(),
         "scaler": (scaler or _NoScaler()).state_dict(),
         "model": _bare(model).state_dict(),
@@ -53,12 +73,12 @@ def save_checkpoint(checkpoints_dir, epoch, model, optimizer, best_score, scaler
     return written
 
 
-def resume_checkpoint(checkpoints_dir, model, optimizer, scaler=None, map_location="cpu"):
+def resume_checkpoint(checkpoints_dir, model, optimizer, scaler=None, map_location="cpu", unsafe=False):
     """base_trainer.py:149-176 -> (start_epoch, best_score)."""
     path = Path(checkpoints_dir).expanduser().absolute() / "latest_model.tar"
     if not path.exists():
         raise FileNotFoundError(f"{path} does not exist, can not load latest checkpoint.")
-    ckpt = torch.load(path.as_posix(), map_location=map_location, weights_only=False)
+    ckpt = _load(path.as_posix(), map_location, unsafe)
     for key in ("epoch", "best_score", "optimizer", "scaler", "model"):
         if key not in ckpt:
             raise RuntimeError(f"{path}: not a trainer checkpoint (missing key {key!r})")
@@ -68,13 +88,13 @@ def resume_checkpoint(checkpoints_dir, model, optimizer, scaler=None, map_locati
     return ckpt["epoch"] + 1, ckpt["best_score"]
 
 
-def preload_model(model_path, model, map_location="cpu"):
+def preload_model(model_path, model, map_location="cpu", unsafe=False):
     """base_trainer.py:128-147 / base_inferencer.py:128-134: weights from a ``.tar`` (key ``model``) or a bare ``.pth``,
     ``strict=False`` as in the reference; returns the (missing, unexpected) key lists."""
     path = Path(model_path).expanduser().absolute()
     if not path.exists():
         raise FileNotFoundError(f"The file {path.as_posix()} is not exist. please check path.")
-    ckpt = torch.load(path.as_posix(), map_location=map_location, weights_only=False)
+    ckpt = _load(path.as_posix(), map_location, unsafe)
     sd = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt and isinstance(ckpt["model"], dict) else ckpt
     res = _bare(model).load_state_dict(sd, strict=False)
     return list(res.missing_keys), list(res.unexpected_keys)

@@ -292,6 +292,7 @@ class GGRU(nn.Module):
             B, T, D = x.shape
         if D != self.hidden_size:
             raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
+        self._wavefront_err = None          # set by a flag-synchronised wavefront: device flag "a bounded spin timed out"
         if self.uses_wavefront(B, T, state, want_state):
             return self._wavefront(x, residual, side, time_major, plan, around)
         if side is not None or time_major or around is not None:
@@ -313,6 +314,8 @@ class GGRU(nn.Module):
         B, Cc, T, Fp = x.shape
         frames = x.transpose(1, 2).contiguous().view(B, T, Cc * Fp)      # :39-40 (layout plumbing)
         out = self.forward_frames(frames)
+        if self._wavefront_err is not None:
+            ops.poison_on_error(self._wavefront_err, [out])               # a timed-out flag spin must not return numbers
         return out.view(B, T, Cc, Fp).transpose(1, 2).contiguous()       # :53-54
 
 
@@ -485,6 +488,8 @@ class unet_2(nn.Module):
         ev = torch.cuda.Event()
         ev.record(s_skip)
         main.wait_event(ev)
+        if self.gru._wavefront_err is not None:
+            ops.poison_on_error(self.gru._wavefront_err, [mask_buf])      # a timed-out flag spin must not return numbers
         return mask_buf.view(B, T, F)
 
     def forward_frames(self, mag, state=None, want_state=False, post=None, after_encoder=None):
@@ -593,7 +598,15 @@ class unet_2(nn.Module):
         mask = ops.convT_fwd(out, self.conv1_t.weight, self.conv1_t.bias, None, None, None, "sigmoid", None,
                              self.freqs[0])                                                          # :164
         mask = mask.view(B, T, F)
+        if self.gru._wavefront_err is not None:
+            ops.poison_on_error(self.gru._wavefront_err, [mask])          # a timed-out flag spin must not return numbers
         return mask
+
+    def wavefront_error_flags(self):
+        """device flags (possibly none) that a flag-synchronised wavefront of the LAST forward call sets when a bounded spin
+        timed out; ``ops.raise_if_wavefront_failed`` reads them on the host"""
+        f = getattr(self.gru, "_wavefront_err", None)
+        return [] if f is None else [f]
 
     def forward(self, x):
         """x [B,1,T,F] float32 CUDA -> mask [B,1,T,F] (model/cruse_net.py:147-165)."""

@@ -560,12 +560,36 @@ __global__ void flag_set_kernel(unsigned* flag, unsigned value) {
     __threadfence();
     atomicExch(flag, value);
 }
+// a bounded spin that timed out must not leave plausible numbers behind: every output of the step becomes NaN
+struct PoisonBufs {
+    float* p[4];
+    long long n[4];
+};
+__global__ void __launch_bounds__(256) poison_on_error_kernel(const int* err, PoisonBufs b) {
+    if (*reinterpret_cast<const volatile int*>(err) == 0) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (int k = 0; k < 4; ++k)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; b.p[k] && i < b.n[k]; i += (long long)gridDim.x * blockDim.x)
+            b.p[k][i] = nan;
+}
 }  // namespace
 }  // namespace cruse
 
 extern "C" int cruse_flag_wait(const unsigned* flag, unsigned target, int* err, void* stream) {
     CRUSE_CHECK_ARG(flag, "flag_wait: null pointer");
     cruse::flag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flag, target, err);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_poison_on_error(const int* err, float* const* bufs, const long long* counts, int nbufs, void* stream) {
+    CRUSE_CHECK_ARG(err && bufs && counts && nbufs >= 1 && nbufs <= 4, "poison_on_error: 1..4 buffers and an error flag needed");
+    cruse::PoisonBufs b;
+    for (int k = 0; k < 4; ++k) {
+        b.p[k] = k < nbufs ? bufs[k] : nullptr;
+        b.n[k] = k < nbufs ? counts[k] : 0;
+    }
+    cruse::poison_on_error_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(err, b);
     CRUSE_LAUNCH_OK();
     return 0;
 }

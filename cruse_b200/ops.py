@@ -413,7 +413,7 @@ GRU_SEQ_MODE = os.environ.get("CRUSE_GRU_SEQ", "tf32")
 
 def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False, mode=None, want_gates=False):
     """recurrence over T; y [B,T,G*H] with y[..., j*G+g] (interleave, cruse_net.py:43-45) or y[..., g*H+j] (cat).
-    want_gates (tf32 mode only): also returns gates [B,T,G,4,H] = r, z, n, W_hn.h+b_hn (saved for backward)."""
+    want_gates: also returns gates [B,T,G,4,H] = r, z, n, W_hn.h+b_hn (saved for backward)."""
     mode = mode or GRU_SEQ_MODE
     _req(xproj, "xproj", 3)
     _req(h0, "h0")
@@ -431,9 +431,13 @@ def gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave, h0=None, want_hT=False, mod
             gates = torch.empty(B, T, G, 4, H, device=xproj.device, dtype=torch.float32)
         _call("cruse_gru_seq_fwd_tc", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), _p(gates), B, T, G, H, y_fs, y_gs,
               _stream(), meta=(f"gru_seq[tf32] G{G} H{H} T{T}", _nb(xproj, y, gates, *w_hh), 2 * B * T * G * H * 3 * H))
+    elif mode == "fp32" and want_gates:
+        # exact-fp32 training forward (saves the gates): the parity twin of the tensor-core kernel (csrc/gru_exact.cu)
+        gates = torch.empty(B, T, G, 4, H, device=xproj.device, dtype=torch.float32)
+        ws = _ws(lib().cruse_gru_exact_ws_bytes(G, H), xproj.device)
+        _call("cruse_gru_seq_fwd_exact", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), _p(gates), _p(ws), B, T, G, H, y_fs, y_gs,
+              _stream(), meta=(f"gru_seq[fp32 exact] G{G} H{H} T{T}", _nb(xproj, y, gates, *w_hh), 2 * B * T * G * H * 3 * H))
     elif mode == "fp32":
-        if want_gates:
-            raise RuntimeError("gru_seq_fwd: want_gates needs mode='tf32'")
         _call("cruse_gru_seq_fwd", _p(xproj), tw, tb, _p(h0), _p(y), _p(hT), B, T, G, H, y_fs, y_gs, _stream(),
               meta=(f"gru_seq[fp32] G{G} H{H} T{T}", _nb(xproj, y, *w_hh), 2 * B * T * G * H * 3 * H))
     else:
@@ -543,6 +547,32 @@ def flag_set(flag, value=1):
 
 def flag_wait(flag, target, err):
     _call("cruse_flag_wait", _p(flag), int(target), _p(err), _stream())
+
+
+class WavefrontTimeout(RuntimeError):
+    """a bounded device-side spin of the flag-synchronised GRU wavefront gave up (2 s): the step's outputs are NaN"""
+
+
+def poison_on_error(err, tensors):
+    """device side of the loud failure: fill up to 4 fp32 tensors with NaN if the wavefront error flag ``err`` is set
+    (one tiny launch on the current stream; include/cruse_b200.h: cruse_poison_on_error)."""
+    tensors = [t for t in tensors if t is not None]
+    counts = (C.c_longlong * len(tensors))(*[t.numel() for t in tensors])
+    _call("cruse_poison_on_error", _p(err), _ptr_table(tensors), C.cast(counts, C.c_void_p), len(tensors), _stream())
+
+
+def raise_if_wavefront_failed(err_flags, what="cruse_b200"):
+    """host side: read the error flag(s) (synchronises with the device) and raise; later calls fall back to the relaunch
+    wavefront, which has no spinning kernels.  Flag mode needs a device this process has to itself: kernels of another
+    process / MPS client / user stream that hold SMs can keep a producer off the GPU while its consumer spins."""
+    global GRU_WAVEFRONT_MODE
+    flags = [f for f in (err_flags if isinstance(err_flags, (list, tuple)) else [err_flags]) if f is not None]
+    if any(int(f.item()) != 0 for f in flags):
+        GRU_WAVEFRONT_MODE = "relaunch"
+        raise WavefrontTimeout(
+            f"{what}: the flag-synchronised GRU wavefront timed out (a producer kernel was kept off the GPU for > 2 s while its "
+            "consumer was spinning -- is another process or stream using this device?).  The outputs of that step were set to NaN. "
+            "Falling back to CRUSE_GRU_WAVEFRONT_MODE=relaunch for the following calls (captured graphs must be re-captured).")
 
 
 def layernorm_fwd_into(x, gamma, beta, eps, y):
@@ -766,9 +796,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd):
     return dx, dgb[:D], dgb[D:]
 
 
-def gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave, h0=None, want_dh0=False):
+def gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave, h0=None, want_dh0=False, mode=None):
     """BPTT of one grouped-GRU layer -> (dxproj [B*T,G,3H], dpre [B*T,G,3H], dbias [G,4,H] = sums of (da_r,da_z,da_n,dhn),
-    dh0 [G,B,H] | None)."""
+    dh0 [G,B,H] | None).  mode (default GRU_SEQ_MODE): 'tf32' = tcgen05 kernel, 'fp32' = exact CUDA-core twin."""
+    mode = mode or GRU_SEQ_MODE
     _req(dy, "dy", 3)
     _req(y, "y", 3)
     _req(gates, "gates", 5)
@@ -784,9 +815,11 @@ def gru_seq_bwd(dy, y, gates, w_hh, B, T, interleave, h0=None, want_dh0=False):
     tw = _ptr_table(w_hh)
     nsl = (B + 15) // 16
     dbp = torch.zeros(nsl, G * 4 * H, device=y.device, dtype=torch.float32)
-    _call("cruse_gru_seq_bwd_tc", _p(dy), _p(y), _p(gates), _p(h0), tw, _p(dxproj), _p(dpre), _p(dh0), _p(dbp), B, T, G, H,
-          y_fs, y_gs, _stream(),
-          meta=(f"gru_seq_bwd[tf32] G{G} H{H} T{T}", _nb(dy, y, gates, dxproj, dpre, *w_hh), 2 * B * T * G * H * 3 * H))
+    if mode not in ("tf32", "fp32"):
+        raise RuntimeError(f"gru_seq_bwd: unknown mode {mode!r}")
+    _call("cruse_gru_seq_bwd_tc" if mode == "tf32" else "cruse_gru_seq_bwd_exact", _p(dy), _p(y), _p(gates), _p(h0), tw, _p(dxproj),
+          _p(dpre), _p(dh0), _p(dbp), B, T, G, H, y_fs, y_gs, _stream(),
+          meta=(f"gru_seq_bwd[{mode}] G{G} H{H} T{T}", _nb(dy, y, gates, dxproj, dpre, *w_hh), 2 * B * T * G * H * 3 * H))
     dbias = torch.empty(G * 4 * H, device=y.device, dtype=torch.float32)
     _call("cruse_colsum", _p(dbp), nsl, G * 4 * H, _p(dbias), 0, _stream())
     return dxproj, dpre, dbias.view(G, 4, H), dh0
@@ -802,13 +835,16 @@ def transpose_gcm(x, M, G, Cn, ld, gs, cs, shift_T=0, h0=None, Bn=0):
     return out
 
 
-def gemm_tn_tc(A, Bm, C, M, N, K, lda, ldb, ldc, bias=None, splitk=1, c_plane=0):
+def gemm_tn_tc(A, Bm, C, M, N, K, lda, ldb, ldc, bias=None, splitk=1, c_plane=0, mode=None):
     """G GEMMs C_g[m,n] = sum_k A_g[m,k] B_g[n,k] (+bias_g[n]); A/Bm/C/bias: lists of tensors (views allowed: only
-    data_ptr and the given pitches are used)."""
+    data_ptr and the given pitches are used).  mode (default GRU_IH_MODE): 'tf32' = tcgen05, 'fp32' = exact CUDA-core twin."""
+    mode = mode or GRU_IH_MODE
+    if mode not in ("tf32", "fp32"):
+        raise RuntimeError(f"gemm_tn_tc: unknown mode {mode!r}")
     G = len(A)
     ta, tb, tcs, tbias = _ptr_table(A), _ptr_table(Bm), _ptr_table(C), _ptr_table(bias)
-    _call("cruse_gemm_tn_tc", ta, tb, tbias, tcs, G, M, N, K, lda, ldb, ldc, splitk, c_plane, _stream(),
-          meta=(f"gemm_tn[tf32] G{G} {M}x{N}x{K} splitk{splitk}", 4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
+    _call("cruse_gemm_tn_tc" if mode == "tf32" else "cruse_gemm_tn_fp32", ta, tb, tbias, tcs, G, M, N, K, lda, ldb, ldc, splitk, c_plane,
+          _stream(), meta=(f"gemm_tn[{mode}] G{G} {M}x{N}x{K} splitk{splitk}", 4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
 
 
 def sigmoid_bwd(dy, y):

@@ -104,6 +104,10 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 t_.record_stream(side2)
             main.wait_event(done)
             main.wait_event(done_istft)
+            if model.gru._wavefront_err is not None:
+                # the ranges above were computed from the mask before forward_frames could poison it: a timed-out flag spin
+                # turns every output of the step into NaN (and the host raises where it synchronises, see check_wavefront)
+                ops.poison_on_error(model.gru._wavefront_err, [loss.view(1), wav_buf, est_buf])
             return loss, wav_buf, est_buf, mask
         have_mask = torch.cuda.Event()
         have_mask.record(main)
@@ -143,6 +147,7 @@ def forward_loss_host(model, noisy_host, clean_host, n_fft=512, hop=320, pad_mod
     clean = clean_host.to(dev, non_blocking=True)
     loss, wav, _, _ = forward_loss(model, noisy, clean, n_fft, hop, pad_mode)
     out = loss.to("cpu", non_blocking=False)
+    ops.raise_if_wavefront_failed(model.wavefront_error_flags(), "forward_loss_host")      # the host is synchronised here anyway
     if want_wav:
         return out, wav.to("cpu")
     return out
@@ -175,6 +180,14 @@ class CapturedForwardLoss:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.loss, self.wav, self.est, self.mask = forward_loss(model, self.noisy, self.clean, n_fft, hop, pad_mode)
+        self._err_flags = list(model.wavefront_error_flags())      # static device flags of this graph's wavefront
+
+    def check_wavefront(self):
+        """Synchronise and raise ``ops.WavefrontTimeout`` if a bounded flag spin of any replay since the last check timed out
+        (the outputs of that replay are NaN).  Cheap enough to call once per N steps; ``_HostLoss.result`` calls it when it sees
+        a NaN loss."""
+        torch.cuda.synchronize(self.noisy.device)
+        ops.raise_if_wavefront_failed(self._err_flags, type(self).__name__)
 
     def __call__(self, noisy, clean):
         """noisy / clean [B,L] on the device or on the host (pinned -> asynchronous copy) -> (loss, wav, est, mask)."""
@@ -226,6 +239,7 @@ class CapturedForwardLoss:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.graph.pool()), torch.no_grad():
                 outs = forward_loss(self.model, nz, cl, n_fft, hop, pad_mode)
+            self._err_flags.extend(self.model.wavefront_error_flags())
             self._stage_graphs[ticket] = (g, outs)
         return self._stage_graphs[ticket]
 
@@ -248,34 +262,46 @@ class CapturedForwardLoss:
 
     # -- asynchronous read-back of a step's loss: the host can launch step i+1 before it blocks on the loss of step i ------
     class _HostLoss:
-        def __init__(self, buf, event):
-            self.buf, self.event = buf, event
+        def __init__(self, buf, event, owner):
+            self.buf, self.event, self.owner = buf, event, owner
 
         def result(self):
             self.event.synchronize()
-            return float(self.buf[0])
+            v = float(self.buf[0])
+            if v != v:                       # NaN: either the data, or a timed-out wavefront poisoned the step -> raise for the latter
+                self.owner.check_wavefront()
+            return v
 
     def loss_to_host_async(self, loss):
-        """queue the device->host copy of ``loss`` (a 0-dim output of the step just launched) on a read-back stream behind that
-        step; returns a handle whose ``result()`` blocks until the value has arrived.  Two pinned slots alternate, so a handle
-        must be consumed before the step after next is queued (the per-staging-pair graphs keep their own output tensors)."""
+        """queue the device->host copy of ``loss`` (a 0-dim output of the step just launched) behind that step; returns a handle
+        whose ``result()`` blocks until the value has arrived (and raises if the step's wavefront timed out).  The value is first
+        copied, on the caller's stream, into one of two private 1-element device slots, so the next replay of the same graph --
+        which overwrites its static ``loss`` tensor -- cannot race the read-back; a handle must be consumed before the step after
+        next is queued (two slots alternate)."""
         dev = self.noisy.device
         if not hasattr(self, "_read_stream"):
             self._read_stream = torch.cuda.Stream(device=dev)
             self._host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._dev_loss = [torch.empty(1, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._slot_free = [None, None]
             self._host_slot = 0
         main = torch.cuda.current_stream(dev)
+        i = self._host_slot
+        self._host_slot ^= 1
+        if self._slot_free[i] is not None:
+            main.wait_event(self._slot_free[i])          # the previous read-back of this slot has left the device
+        self._dev_loss[i].copy_(loss.reshape(1), non_blocking=True)       # on the caller's stream, behind the step
         done = torch.cuda.Event()
         done.record(main)
         rs = self._read_stream
         rs.wait_event(done)
-        buf = self._host_loss[self._host_slot]
-        self._host_slot ^= 1
+        buf = self._host_loss[i]
         with torch.cuda.stream(rs):
-            buf.copy_(loss.reshape(1), non_blocking=True)
+            buf.copy_(self._dev_loss[i], non_blocking=True)
             arrived = torch.cuda.Event()
             arrived.record(rs)
-        return CapturedForwardLoss._HostLoss(buf, arrived)
+        self._slot_free[i] = arrived
+        return CapturedForwardLoss._HostLoss(buf, arrived, self)
 
 
 class CapturedTrainStep(CapturedForwardLoss):
@@ -325,6 +351,7 @@ class CapturedTrainStep(CapturedForwardLoss):
             for b, saved in bn_state:
                 b.copy_(saved)
         self.wav = self.est = self.mask = None
+        self._err_flags = []                 # the training step has no spinning kernels
 
     def _attach(self):
         for p, g in zip(self.params, self.grads):

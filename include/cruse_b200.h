@@ -204,6 +204,11 @@ int cruse_gru_seq_flagged_tc(const float* xproj, const float* const* w_hh, const
                              unsigned* done_flags, int* err, void* stream);
 int cruse_flag_wait(const unsigned* flag, unsigned target, int* err, void* stream);
 int cruse_flag_set(unsigned* flag, unsigned value, void* stream);
+/* Loud failure of the flag-synchronised wavefront: when *err != 0 (a bounded spin of cruse_gru_seq_flagged_tc / cruse_flag_wait
+ * timed out after 2 s -- another process or stream held the SMs the producers needed) every listed output buffer (HOST array of
+ * up to 4 DEVICE pointers with their element counts) is filled with NaN, so that a broken dependency can never return a plausible
+ * mask / waveform / loss (reference convention: errors are exceptions, loss_func/loss.py:65-68; the host raises when it reads the flag). */
+int cruse_poison_on_error(const int* err, float* const* bufs, const long long* counts, int nbufs, void* stream);
 
 /* how many clusters of the tcgen05 recurrence kernel the current device can hold at once (each serves two
  * software-pipelined slices of 16 utterances of one group); G*ceil(B/32) above this runs in waves.  <0 on error. */
@@ -333,6 +338,22 @@ int cruse_gru_step(const float* xproj, const float* const* w_hh, const float* co
 int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C,
                      int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
                      int splitk, long long c_plane, void* stream);
+/* Exact-fp32 twins of the three tensor-core kernels of the GRU training path (same contracts and layouts; every product an
+ * fp32 FMA on the CUDA cores, fixed summation order).  They make the whole training step runnable without tf32 operand rounding
+ * (CRUSE_CONV=fp32 CRUSE_GRU_IH=fp32 CRUSE_GRU_SEQ=fp32), which is how the end-to-end gradients are compared with autograd of
+ * the CPU oracle at fp32 tolerances (nn.GRU forward / backward, model/cruse_net.py:23-31,42-50).  Parity kernels, not the fast path.
+ *  cruse_gru_seq_fwd_exact: as cruse_gru_seq_fwd_tc (gates [B,T,G,4,H] or NULL); ws: cruse_gru_exact_ws_bytes(G,H) bytes of scratch
+ *  (a transposed copy of W_hh).  cruse_gru_seq_bwd_exact: as cruse_gru_seq_bwd_tc.  cruse_gemm_tn_fp32: as cruse_gemm_tn_tc. */
+size_t cruse_gru_exact_ws_bytes(int G, int H);
+int cruse_gru_seq_fwd_exact(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0,
+                            float* y, float* hT, float* gates, void* ws, int B, int T, int G, int H, int y_fs, int y_gs,
+                            void* stream);
+int cruse_gru_seq_bwd_exact(const float* dy, const float* y, const float* gates, const float* h0,
+                            const float* const* w_hh, float* dxproj, float* dpre, float* dh0, float* dbias_part,
+                            int B, int T, int G, int H, int y_fs, int y_gs, void* stream);
+int cruse_gemm_tn_fp32(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C,
+                       int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                       int splitk, long long c_plane, void* stream);
 /* out[(g*Cn + c)*ldo + m] = in[m*ld + g*gs + c*cs] (m < M, c < Cn): puts the (b,t) index innermost for the weight-gradient
  * GEMMs.  shift_T > 0: row m = b*shift_T + t reads row m-1 (h_{t-1} from y) and t == 0 reads h0[g][b][c] (or 0 if NULL; Bn = B). */
 int cruse_transpose_gcm(const float* in, const float* h0, float* out, long long M, int G, int Cn,

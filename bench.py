@@ -125,7 +125,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B_full, secs, desc = WORKLOADS[args.workload]
-    Bs = min(B_full, args.ref_clips)
+    Bs = min(B_full, args.ref_clips) if args.ref_clips > 0 else B_full        # default: every clip of the workload (same config as our arm)
     L = int(secs * SR)
     T = 1 + L // HOP
     train = args.workload == "train"
@@ -154,7 +154,7 @@ def run_reference(args):
         "impl": "reference", "metric": "frames/sec (16 kHz, 20 ms hop) CRUSE " + ("fwd+loss+bwd" if train else "fwd+loss"), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "sample": sample},
+        "config": {"workload": desc, "sample": sample, "same_config_as_ours": Bs == B_full},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": float(loss),
@@ -162,25 +162,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(workload, budget_s=15.0):
+def cpu_baseline_leg(workload, budget_s=15.0, state_dict=None, ours=None):
+    """the oracle port on the host cores over the WHOLE workload batch (same clips, same weights as our arm when ``state_dict``
+    is given); ``ours`` = (loss, est [B,T,NF,2]) of our arm on the same data -> the ``parity`` block of the line."""
     from oracle import cruse_oracle as o
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B_full, secs, _ = WORKLOADS[workload]
-    Bs, L = 4, int(secs * SR)
+    Bs, L = B_full, int(secs * SR)
     T = 1 + L // HOP
     train = workload == "train"
     model = o.make_model(F_BINS, eval_stats=not train)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
     model.train(train)
     noisy, clean = synth_batch(Bs, L, 20260)
+    last = {}
 
     def cpu_step():
         if train:
             model.zero_grad(set_to_none=True)
-            o.forward_loss(model, noisy, clean, N_FFT, HOP)[0].backward()
+            loss = o.forward_loss(model, noisy, clean, N_FFT, HOP)[0]
+            loss.backward()
+            last["loss"] = float(loss)
         else:
             with torch.no_grad():
-                o.forward_loss(model, noisy, clean, N_FFT, HOP)
+                loss, _, est, _ = o.forward_loss(model, noisy, clean, N_FFT, HOP)
+                last["loss"], last["est"] = float(loss), est
 
     cpu_step()
     n, t0 = 0, time.perf_counter()
@@ -190,8 +198,110 @@ def cpu_baseline_leg(workload, budget_s=15.0):
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= 20:
             break
-    return {"value": Bs * T * n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} passes over {Bs} of {B_full} clips x {secs:g}s (oracle port, torch CPU fp32, {cores} threads)"}
+    out = {"value": Bs * T * n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+           "sample": f"{n} passes over all {Bs} clips x {secs:g}s of the workload (oracle port, torch CPU fp32, {cores} threads)"}
+    parity = None
+    if ours is not None and state_dict is not None:
+        l_ours, est_ours = ours
+        parity = {"loss_ours": l_ours, "loss_oracle": last["loss"], "loss_rel_delta": abs(l_ours - last["loss"]) / abs(last["loss"]),
+                  "data": "identical clips and weights on both sides (rank 0's batch)"}
+        if est_ours is not None and "est" in last:
+            parity["enhanced_spectrum_mse"] = float(((est_ours - last["est"].permute(0, 2, 3, 1)) ** 2).mean())
+            parity["gate"] = "loss_rel_delta <= 1e-3, enhanced_spectrum_mse < 1e-4 (BASELINE)"
+    return out, parity
+
+
+# ------------------------------------------------------------------------------------------------
+def train_block(args, dev, world, rank, flush):
+    """BASELINE configs[2] / [3] beside the headline: the training step (STFT + forward with batch statistics + wo_male + backward)
+    on a 64 x 4 s shard per rank (N = 8: the 512 x 4 s batch of configs[3]) as one CUDA-graph replay, followed by THE collective of
+    the path -- one in-place all_reduce(SUM) + 1/N on the flat fp32 gradient buffer over NCCL (loss_func/distrib.py:100-116
+    semantics).  Device-timed with CUDA events, L2 flushed between steps, max over ranks; the all_reduce is also timed alone."""
+    import torch.distributed as dist
+    from cruse_b200 import distrib, pipeline
+    from cruse_b200.cruse_net import unet_2
+    B, secs, desc = WORKLOADS["train"]
+    L = int(secs * SR)
+    T = 1 + L // HOP
+    torch.manual_seed(1234)
+    model = unet_2(in_feat=F_BINS).to(dev).train()
+    if world > 1:
+        distrib.broadcast_model(model)
+    noisy, clean = synth_batch(B, L, 30260 + rank)
+    noisy, clean = noisy.to(dev), clean.to(dev)
+    cap = pipeline.CapturedTrainStep(model, B, L, N_FFT, HOP)
+    cap.noisy.copy_(noisy)
+    cap.clean.copy_(clean)
+    params = cap.params
+    steps = max(3, min(args.steps, 10))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step():
+        loss = cap.replay()
+        if world > 1:
+            distrib.sync_grad(params, flat=cap.flat_grad)
+        return loss
+
+    for _ in range(3):
+        step()
+    sync()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = step()
+        b.record()
+        evs.append((a, b))
+    sync()
+    ms = maxr(sum(a.elapsed_time(b) for a, b in evs)) / steps
+    out = {"workload": desc, "clips_global": B * world, "frames_per_step_per_gpu": B * T, "steps": steps, "warmup": 3,
+           "ms_per_step": ms, "value": B * T * world / (ms / 1e3), "unit": "frames/s", "loss": float(loss),
+           "launch": "one CUDA graph replay (forward + loss + backward, ~190 kernels) + in-place all_reduce on the flat gradient buffer",
+           "grad_bytes": int(cap.flat_grad.numel() * 4)}
+    if world > 1:
+        # the collective alone: back-to-back all_reduce + scale on the same buffer
+        reps = 20
+        for _ in range(3):
+            distrib.sync_grad(params, flat=cap.flat_grad)
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            distrib.sync_grad(params, flat=cap.flat_grad)
+        b.record()
+        sync()
+        ar_ms = maxr(a.elapsed_time(b)) / reps
+        # the same K steps WITHOUT the collective: what the all_reduce adds to the step
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cap.replay()
+            b.record()
+            evs.append((a, b))
+        sync()
+        ms0 = maxr(sum(a.elapsed_time(b) for a, b in evs)) / steps
+        nbytes = out["grad_bytes"]
+        out["allreduce"] = {"backend": dist.get_backend(), "nranks": world, "bytes": nbytes, "us": 1e3 * ar_ms,
+                            "bus_GBps": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                            "pct_of_step": 100.0 * ar_ms / ms, "ms_per_step_without": ms0, "added_ms": ms - ms0,
+                            "how": "one dist.all_reduce(SUM) on the flat fp32 gradient buffer + one in-place 1/N scale (timed alone, 20 back-to-back reps, max over ranks)"}
+    else:
+        out["allreduce"] = None
+    del cap
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,6 +317,11 @@ def run_ours(args):
         raise RuntimeError("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # cores and memory near this rank's GPU, BEFORE the pinned staging buffers are allocated (cruse_b200/hostio.py)
+    from cruse_b200 import hostio
+    affinity0 = os.sched_getaffinity(0)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_binding = hostio.bind_near_gpu(local, local, local_world) if not args.no_bind else {"why_not": "--no-bind"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -227,6 +342,7 @@ def run_ours(args):
     if train and world > 1:
         from cruse_b200 import distrib
         distrib.broadcast_model(model)
+    bn_state0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if train else None
     noisy_h, clean_h = synth_batch(B, L, 20260 + rank)
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
     noisy, clean = noisy_h.to(dev), clean_h.to(dev)
@@ -355,6 +471,31 @@ def run_ours(args):
            "how": ("pipeline.CapturedForwardLoss.prefetch/run_prefetched: pinned H2D of step i+1 on a copy stream (into the staging pair the next replay reads in place) under the replay of step i; every step's loss is copied to pinned host memory on a read-back stream and awaited after the next step has been launched"
                    if captured is not None else "forward_loss_host: H2D, launches, loss .to(cpu) back to back")}
 
+    if captured is not None and not train:
+        captured.check_wavefront()         # a timed-out flag spin anywhere above (outputs NaN) raises here instead of being reported
+    # ---- the H2D leg alone, all ranks at once: what the host side delivers to each GPU while the others copy too
+    h2d_stream = torch.cuda.Stream(device=dev)
+    stage = (torch.empty_like(noisy), torch.empty_like(clean))
+    barrier()
+    with torch.cuda.stream(h2d_stream):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage[0].copy_(noisy_h, non_blocking=True)
+        a.record(h2d_stream)
+        for _ in range(10):
+            stage[0].copy_(noisy_h, non_blocking=True)
+            stage[1].copy_(clean_h, non_blocking=True)
+        b.record(h2d_stream)
+    barrier()
+    h2d_ms = a.elapsed_time(b) / 10
+    t = torch.tensor([h2d_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e["h2d_alone"] = {"ms_per_step": float(t.item()), "GBps_per_rank": e2e["h2d_bytes_per_step"] / (float(t.item()) * 1e-3) / 1e9,
+                        "GBps_all_ranks": world * e2e["h2d_bytes_per_step"] / (float(t.item()) * 1e-3) / 1e9,
+                        "note": "pinned host -> device copy of one step's inputs, every rank copying at the same time, slowest rank"}
+    e2e["host_binding"] = host_binding
+    del stage
+
     # ---- per-kernel device times of one step (CUDA events on the launching stream) -> roofline
     pk = peaks()
     rows_acc = {}
@@ -407,8 +548,29 @@ def run_ours(args):
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(), "loss": float(loss), "kernels": kernels,
     }
+    if not train and not args.no_train_block:
+        line["train"] = train_block(args, dev, world, rank, flush)
+        if world > 1:
+            line["config"]["collective"] = ("none on the inference path (replicas); the `train` block runs the path's one collective: "
+                                            "a flat fp32 gradient all_reduce over NCCL per training step")
+    try:
+        os.sched_setaffinity(0, affinity0)             # the CPU leg below uses every host core again
+    except Exception:  # noqa: BLE001
+        pass
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(args.workload)
+        # the oracle on the host cores, same clips and weights: the CPU baseline and the oracle-vs-ours delta of THIS run
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        if bn_state0 is not None:
+            sd.update(bn_state0)                       # training replays moved the running statistics: compare at the start state
+        est_ours = None
+        if captured is not None and not train:
+            captured.noisy.copy_(noisy)
+            captured.clean.copy_(clean)
+            l_ours = float(captured.replay())
+            est_ours = captured.est.detach().cpu()
+        else:
+            l_ours = float(loss)
+        line["cpu_baseline"], line["parity"] = cpu_baseline_leg(args.workload, state_dict=sd, ours=(l_ours, est_ours) if not train else None)
     if rank == 0:
         if args.table:
             with open(args.table, "w") as f:
@@ -429,8 +591,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="infer", choices=sorted(WORKLOADS),
                     help="infer = BASELINE configs[1] (the headline, default); train = configs[2]/[3]")
-    ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the bounded CPU sample (--impl reference)")
+    ap.add_argument("--ref-clips", type=int, default=0,
+                    help="--impl reference: clips per step of the CPU run (0 = the whole workload batch, i.e. the same config as our arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the process / its pinned memory near its GPU")
+    ap.add_argument("--no-train-block", action="store_true", help="infer workload: skip the cfg-3/cfg-4 train step + all_reduce block")
     ap.add_argument("--no-graph", action="store_true", help="inference: launch eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--table", default=None, help="write the per-kernel roofline table (markdown) here")
     args = ap.parse_args()

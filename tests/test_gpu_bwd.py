@@ -314,14 +314,15 @@ def test_grouped_gru_layer_backward(cuda, G, H, B, T, interleave):
 @pytest.mark.parametrize("F,n_fft,hop,act,B,L", [(256, 512, 320, "relu", 3, 6400), (256, 512, 320, "prelu", 2, 4800),
                                                  (161, 320, 160, "relu", 2, 3200)])
 def test_full_model_gradients_match_oracle_autograd(cuda, F, n_fft, hop, act, B, L):
-    """End-to-end gradients vs autograd of the oracle: STFT -> unet_2 (train-mode BN) -> mask*X -> wo_male.
-    Stated tolerance per parameter tensor: cosine >= 0.98, rel-L2 <= 0.2 -- a sanity gate, deliberately loose: wo_male is an
-    L1-type loss, its gradient is sign(log-error) per bin, and on these tiny batches (16 k bins, BatchNorm over 63 frames) a
-    relative 2^-11 perturbation of the GRU weights already moves the ORACLE's own gradients by 2.7e-2 rel-L2
-    (tools/grad_conditioning.py, profiles/grad_conditioning_r1.log).  Two of OUR OWN runs differ by up to 9e-2 on single
-    tensors (tools/determinism_check.py: the per-CTA BatchNorm partial sums are combined with shared-memory atomics, a 1e-7
-    reordering difference that flips a few signs).  The kernels themselves are checked tightly above (1e-4 conv/BN/LN, 2e-3 GRU
-    layer), and test_unet_gradients_smooth_functional below checks the whole backward chain on a smooth functional."""
+    """End-to-end gradients vs autograd of the oracle in the DEFAULT tf32 mode: STFT -> unet_2 (train-mode BN) -> mask*X -> wo_male.
+    Stated tolerance per parameter tensor here: cosine >= 0.98, rel-L2 <= 0.2 -- a sanity gate for tiny batches.  The tight gate
+    of SURVEY 8d (cos >= 0.9999, rel-L2 <= 1e-3) is asserted in the exact-fp32 mode by
+    tests/test_gpu_bench_shapes.py::test_exact_mode_end_to_end_gradients_meet_the_stated_gate, and at the cfg-3 size in both modes
+    by ::test_cfg3_train_step_64x4s_through_bench_entry_vs_oracle_autograd.  Why tf32 is far from 1e-3 here although every kernel
+    alone is within 2e-3: this network's backward amplifies operand perturbations ~50x linearly -- a relative 2^-11 noise on the
+    GRU weights alone moves the ORACLE's own gradients by 2.7e-2 rel-L2 on this batch and by ~1e-2 at 16 x 4 s
+    (tools/grad_conditioning.py, profiles/grad_conditioning_r2.log).  The step itself is bit-reproducible run to run
+    (tools/determinism_check.py: every reduction has a fixed order)."""
     from cruse_b200 import pipeline
     from cruse_b200.cruse_net import unet_2
     from oracle import cruse_oracle as o

@@ -295,3 +295,28 @@ def test_wavefront_modes_agree_and_no_flag_timeout(cuda):
     finally:
         ops.GRU_WAVEFRONT_MODE = old
     assert torch.equal(out["flags"][3], out["relaunch"][3]) and torch.equal(out["flags"][0], out["relaunch"][0])
+
+
+def test_wavefront_timeout_is_loud(cuda):
+    """a bounded flag spin that gives up (2 s) must never hand back plausible numbers: the device flag is set, the outputs listed
+    for cruse_poison_on_error become NaN, the host check raises ops.WavefrontTimeout and switches later calls to the relaunch
+    wavefront (no spinning kernels)."""
+    from cruse_b200 import ops
+    flag = torch.zeros(1, device=cuda, dtype=torch.int32)
+    err = torch.zeros(1, device=cuda, dtype=torch.int32)
+    a, b = torch.ones(1000, device=cuda), torch.ones((), device=cuda)
+    ops.poison_on_error(err, [a, b.view(1)])
+    torch.cuda.synchronize()
+    assert float(a.sum()) == 1000.0 and float(b) == 1.0                 # no error: untouched
+    ops.raise_if_wavefront_failed([err])                                # and no exception
+    ops.flag_wait(flag, 1, err)                                         # nobody ever sets this flag -> gives up after 2 s
+    ops.poison_on_error(err, [a, b.view(1)])
+    torch.cuda.synchronize()
+    assert int(err.item()) == 1 and bool(torch.isnan(a).all()) and bool(torch.isnan(b))
+    old = ops.GRU_WAVEFRONT_MODE
+    try:
+        with pytest.raises(ops.WavefrontTimeout):
+            ops.raise_if_wavefront_failed([err], "test")
+        assert ops.GRU_WAVEFRONT_MODE == "relaunch"
+    finally:
+        ops.GRU_WAVEFRONT_MODE = old

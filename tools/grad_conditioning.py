@@ -1,12 +1,15 @@
 """Developer tool (CPU, uses the oracle): how sensitive are the oracle's OWN gradients to tf32-sized perturbations?
 A relative 2^-11 noise on the GRU weights alone moves every upstream gradient by ~2.7e-2 rel-L2 (|log-error| sign
 flips + small-batch BatchNorm), which is the floor any tf32 training path can reach against the fp32 oracle.
-Output committed as profiles/grad_conditioning_r1.log."""
+Output committed as profiles/grad_conditioning_r1.log (3 x 0.4 s) and profiles/grad_conditioning_r2.log (also 16 x 4 s:
+the amplification is linear in the perturbation -- fp32-vs-fp64 1e-6..3e-4, 2^-11 noise 1e-2..3e-2 -- and does not vanish with size)."""
 import sys, torch
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import cruse_oracle as o
-F,n_fft,hop,B,L=256,512,320,3,6400
+F,n_fft,hop=256,512,320
+B,L=(int(sys.argv[1]),int(sys.argv[2])) if len(sys.argv)>2 else (3,6400)   # e.g. 16 64000
+print(f'--- B={B} L={L} (T={1+L//hop})')
 def run(dtype, perturb=0.0):
     ref=o.make_model(F, act='relu', eval_stats=False).to(dtype); ref.train()
     noisy,clean=o.synth_batch(B,L)

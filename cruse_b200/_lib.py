@@ -49,6 +49,7 @@ SIGNATURES = {
     "cruse_bn_fold_many": (c_int, [c_pp] * 4 + [c_fp, c_pp, c_pp, c_fp, c_int, c_fp]),
     "cruse_bn_act_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_ll, c_int, c_int, c_fp]),
     "cruse_gru_ih_gemm": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),
+    "cruse_gemm_set_astat": (c_int, [c_int]),
     "cruse_gru_ih_gemm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_fp]),
     "cruse_gru_seq_fwd": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gru_seq_fwd_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
@@ -57,6 +58,7 @@ SIGNATURES = {
     "cruse_flag_wait": (c_int, [c_fp, C.c_uint, c_fp, c_fp]),
     "cruse_flag_set": (c_int, [c_fp, C.c_uint, c_fp]),
     "cruse_poison_on_error": (c_int, [c_fp, c_pp, c_pp, c_int, c_fp]),
+    "cruse_debug_seq_trace": (c_int, [c_fp]),
     "cruse_gru_ih_gemm_tm_tc": (c_int, [c_fp, c_pp, c_pp, c_pp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
     "cruse_gru_seq_chunk_tc": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_ll] * 4 + [c_fp]),
     "cruse_layernorm_fwd": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp, c_fp, c_fp, c_ll, c_int, c_fp]),

@@ -214,11 +214,170 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
     if (warp == 1) tc::tmem_dealloc<BN>(tmem_d);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// A-stationary variant for the input projections (K = 256): one CTA per (m-tile of 128 rows, group) computes ALL N <= 768
+// gate rows.  The activation tile (128 x 256 fp32 = 128 KB) is brought in ONCE by eight TMA boxes that are all in flight
+// together and stays resident; the weights stream through a 4-stage ring of 128 x 32 boxes (they are L2 resident: 3 MB per
+// layer), n-tile by n-tile; the accumulator is double buffered in tensor memory (2 x 128 columns), so the epilogue of n-tile j
+// (tcgen05.ld -> + bias -> transpose through shared memory -> full 128-byte row segments) runs under the MMAs of n-tile j+1.
+// Against the one-tile-per-CTA kernel above this removes the per-tile prologue (barrier init, TMEM allocation, descriptor
+// fetch, pipeline fill), re-reads the activations once instead of three times, and occupies M/128 x G SMs (64 for a 63-frame
+// chunk of 32 utterances) instead of the whole GPU -- what runs beside the recurrences is capacity bound.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int AS_BN = 128, AS_NKB = 8, AS_STAGES = 4;
+constexpr int AS_A_KB_BYTES = BM * BK * 4;                       // one k-block of the resident A tile: 16 KB
+constexpr int AS_A_BYTES = AS_NKB * AS_A_KB_BYTES;               // 128 KB
+constexpr int AS_W_STAGE = AS_BN * BK * 4;                       // 16 KB
+constexpr int AS_STG_BYTES = 4 * 32 * 36 * 4;                    // epilogue transpose pads (A stays live, so they have their own space)
+constexpr int AS_MAX_N = 768;
+constexpr int AS_SMEM = 1024 + AS_A_BYTES + AS_STAGES * AS_W_STAGE + AS_STG_BYTES + AS_MAX_N * 4 + 128;
+
+__global__ void __launch_bounds__(IH_THREADS, 1)
+gemm_astat_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, long long ldc, int bias2_rows, int tm_T) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sA = smem_raw + (base - tc::smem_u32(smem_raw));
+    uint8_t* sW = sA + AS_A_BYTES;
+    float* stg_all = reinterpret_cast<float*>(sW + AS_STAGES * AS_W_STAGE);
+    float* s_bias = stg_all + AS_STG_BYTES / 4;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(s_bias + AS_MAX_N);
+    uint64_t* full = a_full + 1;
+    uint64_t* empty = full + AS_STAGES;
+    uint64_t* tmem_full = empty + AS_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, g = blockIdx.y;
+    const int NT = N / AS_BN;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&args.a[g]);
+        tc::tma_prefetch_desc(&args.b[g]);
+        tc::mbar_init(a_full, 1);
+        for (int s = 0; s < AS_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full[s], 1); tc::mbar_init(&tmem_empty[s], 128); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<2 * AS_BN>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tc::mbar_expect_tx(a_full, AS_A_BYTES);
+            for (int kb = 0; kb < AS_NKB; ++kb) tc::tma_load_2d(sA + kb * AS_A_KB_BYTES, &args.a[g], kb * BK, m0, a_full);
+            int i = 0;
+            for (int nt = 0; nt < NT; ++nt)
+                for (int kb = 0; kb < AS_NKB; ++kb, ++i) {
+                    const int s = i % AS_STAGES;
+                    tc::mbar_wait(&empty[s], ((i / AS_STAGES) & 1) ^ 1);
+                    tc::mbar_expect_tx(&full[s], AS_W_STAGE);
+                    tc::tma_load_2d(sW + s * AS_W_STAGE, &args.b[g], kb * BK, nt * AS_BN, &full[s]);
+                }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, BM, AS_BN);
+        tc::mbar_wait(a_full, 0);
+        tc::tc_fence_after();
+        int i = 0;
+        for (int nt = 0; nt < NT; ++nt) {
+            const int acc = nt & 1;
+            tc::mbar_wait(&tmem_empty[acc], ((nt >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator buffer
+            tc::tc_fence_after();
+            for (int kb = 0; kb < AS_NKB; ++kb, ++i) {
+                const int s = i % AS_STAGES;
+                tc::mbar_wait(&full[s], (i / AS_STAGES) & 1);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t sa = base + kb * AS_A_KB_BYTES, sb = base + AS_A_BYTES + s * AS_W_STAGE;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)
+                        tc::umma_tf32(tmem_d + (uint32_t)(acc * AS_BN), tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc,
+                                      (kb | k) ? 1u : 0u);
+                    tc::umma_commit(&empty[s]);
+                    if (kb == AS_NKB - 1) tc::umma_commit(&tmem_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int quad = warp & 3;
+        const float* b1 = args.bias1[g];
+        const float* b2 = args.bias2[g];
+        for (int i = threadIdx.x - 64; i < N; i += 128) {
+            float b = (b1 ? __ldg(b1 + i) : 0.f) + ((b2 && i < bias2_rows) ? __ldg(b2 + i) : 0.f);
+            s_bias[i] = b;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* stg = stg_all + quad * (32 * 36);
+        const int rr = lane >> 3, cc = (lane & 7) * 4;
+        float* obase = args.out[g];
+        // output rows of this warp's four store phases (tm_T > 0: rows (b, t) are written time-major, t*B + b)
+        size_t orow[8];
+        bool ok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int mm = m0 + quad * 32 + rr + 4 * i;
+            ok[i] = mm < M;
+            size_t mr = (size_t)(ok[i] ? mm : 0);
+            if (tm_T > 0) { const int bq = (int)mr / tm_T; mr = (size_t)((int)mr - bq * tm_T) * (size_t)(M / tm_T) + bq; }
+            orow[i] = mr * (size_t)ldc;
+        }
+        for (int nt = 0; nt < NT; ++nt) {
+            const int acc = nt & 1;
+            tc::mbar_wait(&tmem_full[acc], (nt >> 1) & 1);
+            tc::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < AS_BN; c += 32) {
+                float v[32];
+                tc::tmem_ld_32x32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * AS_BN + c), v);
+                tc::tmem_ld_wait();
+                if (c == AS_BN - 32) {                       // last read of this buffer: hand it back before the stores
+                    tc::tc_fence_before();
+                    tc::mbar_arrive_relaxed(&tmem_empty[acc]);
+                }
+                const int n = nt * AS_BN + c;
+                __syncwarp();                                // the previous chunk's loads from the staging tile are done
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j] + s_bias[n + j], v[j + 1] + s_bias[n + j + 1],
+                                                                                   v[j + 2] + s_bias[n + j + 2], v[j + 3] + s_bias[n + j + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (ok[i]) *reinterpret_cast<float4*>(obase + orow[i] + n + cc) = *reinterpret_cast<const float4*>(stg + (rr + 4 * i) * 36 + cc);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<2 * AS_BN>(tmem_d);
+}
+
+// process-wide switch (developer A/B): 1 = use the A-stationary kernel where it applies (default), 0 = the tile-per-CTA kernel
+static int g_astat = 1;
+
 int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int bias2_rows, int splitk, long long c_plane,
-                cudaStream_t st, int tm_T = 0) {
+                cudaStream_t st, int tm_T = 0, bool astat_ok = false) {
     for (int g = G; g < CRUSE_MAX_GROUPS; ++g) {
         args.a[g] = args.a[0]; args.b[g] = args.b[0];
         args.bias1[g] = nullptr; args.bias2[g] = nullptr; args.out[g] = nullptr;
+    }
+    if (g_astat && astat_ok && splitk == 1 && K == AS_NKB * BK && N % AS_BN == 0 && N <= AS_MAX_N && (ldc & 3) == 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CRUSE_CUDA_OK(cudaFuncSetAttribute(gemm_astat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AS_SMEM));
+            attr_set = true;
+        }
+        gemm_astat_tc_kernel<<<dim3((M + BM - 1) / BM, G), IH_THREADS, AS_SMEM, st>>>(args, M, N, ldc, bias2_rows, tm_T);
+        CRUSE_LAUNCH_OK();
+        return 0;
     }
     CRUSE_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, G * splitk);
@@ -239,16 +398,22 @@ static int gru_ih_gemm_tc_impl(const float* x, const float* const* w_ih, const f
                     "gru_ih_gemm_tc: bad sizes M=%d G=%d H=%d (H%%4==0, G<=%d)", M, G, H, CRUSE_MAX_GROUPS);
     CRUSE_CHECK_ARG(tm_T == 0 || (tm_T > 0 && M % tm_T == 0), "gru_ih_gemm_tm_tc: M=%d is not a multiple of T=%d", M, tm_T);
     GemmArgs args;
+    const bool astat = g_astat && H == AS_NKB * BK;          // K = H = 256: the A-stationary kernel (weight boxes of 128 rows)
     for (int g = 0; g < G; ++g) {
         CRUSE_CHECK_ARG(w_ih[g], "gru_ih_gemm_tc: null weight pointer for group %d", g);
         // A: this group's H columns of x (row pitch G*H floats); B: weight_ih_l0 [3H, H]
         if (int rc = make_tmap_2d(&args.a[g], x + (size_t)g * H, (uint64_t)M, (uint64_t)H, (uint64_t)G * H * 4, BM, true)) return rc;
-        if (int rc = make_tmap_2d(&args.b[g], w_ih[g], (uint64_t)3 * H, (uint64_t)H, (uint64_t)H * 4, BN, true)) return rc;
+        if (int rc = make_tmap_2d(&args.b[g], w_ih[g], (uint64_t)3 * H, (uint64_t)H, (uint64_t)H * 4, astat ? AS_BN : BN, true)) return rc;
         args.bias1[g] = b_ih ? b_ih[g] : nullptr;
         args.bias2[g] = b_hh ? b_hh[g] : nullptr;
         args.out[g] = xproj + (size_t)g * 3 * H;
     }
-    return launch_gemm(args, G, M, 3 * H, H, (long long)G * 3 * H, 2 * H, 1, 0, (cudaStream_t)stream, tm_T);
+    return launch_gemm(args, G, M, 3 * H, H, (long long)G * 3 * H, 2 * H, 1, 0, (cudaStream_t)stream, tm_T, astat);
+}
+
+extern "C" int cruse_gemm_set_astat(int on) {
+    g_astat = on ? 1 : 0;
+    return 0;
 }
 
 extern "C" int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,

@@ -68,6 +68,7 @@ struct SeqSync {
     unsigned wait_target;
     int nchunks;
     int bounds[18];
+    unsigned long long* trace;      // developer progress trace (cruse_debug_seq_trace), NULL = off: [128] step stamps + [2*16] chunk-wait stamps
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -318,7 +319,10 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         auto chunk_gate = [&](int tp) {                               // called (WG-uniformly) before frame tp is prefetched
             if (tp == next_wait) {
                 if (sync.wait) {
+                    const bool tr = sync.trace && wt == 0 && sl == 0 && rank == 0 && g == 0 && bpair == 0 && kw < 16;
+                    if (tr) sync.trace[128 + 2 * kw] = globaltimer_ns();
                     if (wt == 0) spin_until(sync.wait + kw, sync.wait_target, sync.err);
+                    if (tr) sync.trace[128 + 2 * kw + 1] = globaltimer_ns();
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");
                 }
                 ++kw;
@@ -408,6 +412,7 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                 }
             }
             if (sl == 0 && wt == 0) SEQ_STAMP(6);
+            if (sync.trace && (t & 7) == 0 && wt == 0 && sl == 0 && rank == 0 && g == 0 && bpair == 0 && (t >> 3) < 128) sync.trace[t >> 3] = globaltimer_ns();
             if (t + 1 == next_done) {                                  // chunk kd is stored: publish it
                 if (sync.done) {
                     __threadfence();
@@ -513,6 +518,16 @@ extern "C" int cruse_gru_seq_tc_max_clusters(int H) {
     return -1;
 }
 
+// developer instrumentation: the next flagged recurrence launches (one per layer) write their progress trace (globaltimer stamps of
+// every 8th step and of the chunk waits of cluster 0) to buf[k * 160 ...] for k = 0, 1, ...; NULL switches it off
+static unsigned long long* g_seq_trace = nullptr;
+static int g_seq_trace_next = 0;
+extern "C" int cruse_debug_seq_trace(void* device_buf) {
+    g_seq_trace = static_cast<unsigned long long*>(device_buf);
+    g_seq_trace_next = 0;
+    return 0;
+}
+
 static int gru_seq_tc_impl(const float* xproj, const float* const* w_hh, const float* const* b_hh, const float* h0, float* y,
                            float* hT, float* gates, int B, int T, int G, int H, int y_fs, int y_gs, long long x_bs, long long x_ts,
                            long long y_bs, long long y_ts, void* stream, const SeqSync* syncp = nullptr) {
@@ -520,6 +535,7 @@ static int gru_seq_tc_impl(const float* xproj, const float* const* w_hh, const f
     SeqSync sync;
     memset(&sync, 0, sizeof(sync));
     if (syncp) sync = *syncp;
+    if (syncp && g_seq_trace) sync.trace = g_seq_trace + 160 * ((g_seq_trace_next++) & 1);      // layer 1, layer 2, layer 1, ...
     CRUSE_CHECK_ARG(B > 0 && T >= 0 && G > 0 && G <= CRUSE_MAX_GROUPS && H > 0 && (H % 4) == 0 && H <= 256,
                     "gru_seq_fwd_tc: bad sizes B=%d T=%d G=%d H=%d (H%%4==0, H<=256, G<=%d)", B, T, G, H, CRUSE_MAX_GROUPS);
     SeqPtrs ptrs;

@@ -162,6 +162,9 @@ int cruse_gru_ih_gemm(const float* x, const float* const* w_ih, const float* con
  * unit, fp32 accumulation in TMEM).  Needs 16-byte aligned x / w_ih rows (H % 4 == 0). */
 int cruse_gru_ih_gemm_tc(const float* x, const float* const* w_ih, const float* const* b_ih,
                          const float* const* b_hh, float* xproj, int M, int G, int H, void* stream);
+/* developer A/B switch for cruse_gru_ih_gemm_tc / _tm_tc at H = 256: 1 (default) = the A-stationary kernel (activation tile resident,
+ * weights streamed, double-buffered accumulator, one CTA per (128 rows, group)); 0 = one 128 x 256 tile per CTA */
+int cruse_gemm_set_astat(int on);
 /* recurrence over T with W_hh resident on chip (thread-block cluster per (group, 8-utterance slice)).
  *  y[b,t, j*y_fs + g*y_gs] = h_t[g][b][j]   (layer 1: y_fs=G,y_gs=1 = the stack/flatten interleave of
  *  cruse_net.py:43-45; layer 2: y_fs=1,y_gs=H = cat, :49-50).  h0/hT [G,B,H] or NULL (state carry,
@@ -209,6 +212,10 @@ int cruse_flag_set(unsigned* flag, unsigned value, void* stream);
  * up to 4 DEVICE pointers with their element counts) is filled with NaN, so that a broken dependency can never return a plausible
  * mask / waveform / loss (reference convention: errors are exceptions, loss_func/loss.py:65-68; the host raises when it reads the flag). */
 int cruse_poison_on_error(const int* err, float* const* bufs, const long long* counts, int nbufs, void* stream);
+/* Developer instrumentation (tools/wavefront_trace.py), not part of the data path: the next cruse_gru_seq_flagged_tc launches write a
+ * progress trace of their cluster 0 (%globaltimer of every 8th step [128] and of begin / end of every chunk wait [2*16]) to
+ * device_buf + (k%2)*160 (uint64) for launch k = 0, 1, ... (layer 1, layer 2 of a wavefront); NULL switches it off. */
+int cruse_debug_seq_trace(void* device_buf);
 
 /* how many clusters of the tcgen05 recurrence kernel the current device can hold at once (each serves two
  * software-pipelined slices of 16 utterances of one group); G*ceil(B/32) above this runs in waves.  <0 on error. */

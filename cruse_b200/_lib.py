@@ -41,6 +41,7 @@ SIGNATURES = {
     "cruse_conv_set_mode": (c_int, [c_int]),
     "cruse_conv_set_max_ctas": (c_int, [c_int]),
     "cruse_conv_fwd_range": (c_int, [c_fp] * 6 + [c_int, c_fp] + [c_int] * 12 + [c_fp]),
+    "cruse_conv_skip_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 9 + [c_fp]),
     "cruse_convT_fwd_range": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
     "cruse_layernorm_fwd_range": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp] + [c_int] * 5 + [c_fp]),
     "cruse_convT_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),

@@ -410,16 +410,24 @@ class unet_2(nn.Module):
         D = C4 * F4
         unet = self
         # ---- encoder, whole utterances (:149-152 repaired); the last stage writes the GRU input time-major
+        skip_out = [new(B, T, self.ch[k], self.freqs[k]) for k in range(1, n + 1)]
         enc, h = [], mag.view(B, T, 1, F)
+        # skip conv k (:153-155) reads the same tensor e_k as encoder stage k+1 (:150-152): where a fused tensor-core instantiation
+        # exists (Cin 8 / 16 of the 256-bin pyramid) it rides along with that stage -- e_k is read once and the skip conv costs no
+        # launch of its own; the remaining skip convs run beside the recurrences (Around.skips)
+        fused = set()
         for k in range(1, n + 1):
             conv = getattr(self, f"conv{k}")
             scale, shift = folds[f"bn{k}"]
             if k == n:
                 h = ops.conv_fwd_tm(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2, B, T, False, True)
+            elif ops.FUSE_SKIPS and k >= 2 and self.ch[k - 1] in (8, 16) and self.freqs[k - 1] == 2 * self.freqs[k] and self.freqs[k] in (64, 32):
+                h, _ = ops.conv_skip_fwd(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind,
+                                         getattr(self, f"skip_connect_{k - 1}").weight, out_skip=skip_out[k - 2])
+                fused.add(k - 1)
             else:
                 h = ops.conv_fwd(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2)
             enc.append(h)
-        skip_out = [new(B, T, self.ch[k], self.freqs[k]) for k in range(1, n + 1)]
         dec = [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
         mask_buf = new(B, T, 1, F)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -457,6 +465,8 @@ class unet_2(nn.Module):
                 try:
                     with torch.cuda.stream(s_skip):
                         for k in range(n, 0, -1):
+                            if k in fused:
+                                continue                                   # came out of encoder stage k+1 already
                             wk = getattr(unet, f"skip_connect_{k}").weight
                             ops.conv_fwd_range(enc[k - 1], wk, None, None, None, None, "none", 1, 1, B, T, skip_out[k - 1], t0, t1,
                                                in_tm=(k == n))

@@ -24,6 +24,9 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
 int convT_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
                  int act, const float* skip, float* out, int B, int T, int Cin, int Fin, int Cout, int Fout, cudaStream_t st,
                  int t_begin = 0, int t_end = 0);
+int conv_skip_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                     int act, const float* w2, float* out, float* out2, int B, int T, int Cin, int Fin, int Cout, int Fout, int out_tm,
+                     cudaStream_t st, int t_begin, int t_end);
 int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
                       int Fout, int kt, cudaStream_t st);
 int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
@@ -527,6 +530,23 @@ extern "C" int cruse_conv_fwd_range(const float* in, const float* w, const float
     if (rc < 0) { set_error("conv_fwd_range: kernel launch failed"); return rc; }
     CRUSE_CHECK_ARG(rc == 1, "conv_fwd_range: no tensor-core / streaming instantiation for kt=%d fstride=%d Cin=%d Cout=%d Fin=%d (or conv mode is fp32)",
                     kt, fstride, Cin, Cout, Fin);
+    return 0;
+}
+
+// Eval-mode encoder stage with the (1,3) skip conv of its INPUT fused in (tensor-core instantiations only): one pass over `in`
+// produces out = act(BN(conv2x3/s2(in))) and out_skip = conv1x3(in; w_skip) -- model/cruse_net.py:149-152 and :153-155 together.
+extern "C" int cruse_conv_skip_fwd(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                                   const float* alpha, int act, const float* w_skip, float* out, float* out_skip, int B, int T,
+                                   int Cin, int Fin, int Cout, int Fout, int out_time_major, int t_begin, int t_end, void* stream) {
+    CRUSE_CHECK_ARG(in && w && out && w_skip && out_skip, "conv_skip_fwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && Cin > 0 && Cout > 0 && Fin > 0 && Fout == (Fin + 2 - 3) / 2 + 1, "conv_skip_fwd: bad sizes");
+    CRUSE_CHECK_ARG((t_begin == 0 && t_end == 0) || (t_begin >= 0 && t_begin < t_end && t_end <= T), "conv_skip_fwd: bad frame range [%d,%d) of %d", t_begin, t_end, T);
+    CRUSE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_skip_fwd: scale and shift go together");
+    CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || alpha, "conv_skip_fwd: PReLU needs alpha");
+    const int rc = conv_skip_tc_try(in, w, bias, scale, shift, alpha, act, w_skip, out, out_skip, B, T, Cin, Fin, Cout, Fout,
+                                    out_time_major ? 1 : 0, (cudaStream_t)stream, t_begin, t_end);
+    if (rc < 0) { set_error("conv_skip_fwd: kernel launch failed"); return rc; }
+    CRUSE_CHECK_ARG(rc == 1, "conv_skip_fwd: no fused tensor-core instantiation for Cin=%d Cout=%d Fin=%d (or conv mode is fp32)", Cin, Cout, Fin);
     return 0;
 }
 

@@ -68,6 +68,8 @@ struct ConvTcArgs {
                             //    encoder / the tail of the decoder run beside the recurrence instead of before / after it
     int wmode;              // 0: w is this conv's weight; 1 (KT == 1 conv only): data gradient of a (1,3)/stride-1 conv --
                             //    w is THAT conv's weight [Cin_here][Cout_here][1][3], taps flipped
+    const float* w2;        // FUSE: weight [CIN][CIN][1][3] of the (1,3) skip conv of this stage's INPUT (model/cruse_net.py:143,153-155)
+    float* out2;            // FUSE: its output, frame-major [B,T,CIN,FIN]
 };
 
 // MODE 0: conv KT x 3, frequency stride SF, pad 1 (FO = output bins).  MODE 1: convT 1 x 3, stride 2, cropped
@@ -75,11 +77,15 @@ struct ConvTcArgs {
 // cropped at the right edge) = the data gradient of the transposed conv.  MODE 2: the data gradient of the KT x 3 / stride-2
 // conv: a transposed conv over dz (FO = dz bins, output 2*FO bins) whose frequency taps are {dz[i], dz[i+1]} and whose time taps
 // look FORWARD (frame t and t+1); CIN = channels of dz (the conv's Cout), COUT = channels of the gradient (the conv's Cin).
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM>
+// FUSE (MODE 0, KT x 3 / stride 2 only): the (1,3)/stride-1 skip conv of the stage's INPUT rides along.  The stage's A tile already
+// holds the input bins 2fo-1, 2fo, 2fo+1 of every row; with a fourth tap (bin 2fo+2) the skip outputs of the bins 2fo and 2fo+1
+// are two more groups of accumulator columns (N = COUT + 2*CIN) whose weights are zero outside the current frame's taps -- the
+// input tensor is read once instead of twice and the skip conv costs no launch of its own.
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int FUSE = 0>
 struct ConvTcCfg {
     static constexpr bool CONVLIKE = MODE == 0 || MODE == 3;
-    static constexpr int TAPS = CONVLIKE ? 3 : 2;                  // conv: kf = 0,1,2; convT: {x[i], x[i-1]}
-    static constexpr int N = CONVLIKE ? COUT : 2 * COUT;
+    static constexpr int TAPS = CONVLIKE ? (FUSE ? 4 : 3) : 2;     // conv: kf = 0,1,2 (+ bin 2fo+2 when fused); convT: {x[i], x[i-1]}
+    static constexpr int N = CONVLIKE ? COUT + (FUSE ? 2 * CIN : 0) : 2 * COUT;
     static constexpr int NPAD = N < 16 ? 16 : N;                   // UMMA M=128 needs N % 16 == 0
     static constexpr int TF = GM * (128 / FO);                     // frames per tile = GM MMA tiles of 128 rows: short-frame
                                                                    // stages (FO >= 32) batch several so that the per-tile
@@ -109,6 +115,7 @@ struct ConvTcCfg {
     static_assert(NPAD % 16 == 0 && NPAD <= 64 && 2 * ACC_COLS <= 256, "N tile");
     static_assert(NIT <= (MODE == 2 ? 10 : 9), "producer register budget: at most 9 patches per warp and group (10 with one value per patch)");
     static_assert(MODE == 0 || (MODE == 1 && KT == 1 && SF == 1) || (MODE == 3 && KT == 1 && SF == 2) || (MODE == 2 && SF == 1), "instantiation");
+    static_assert(!FUSE || (MODE == 0 && SF == 2 && COUT % 16 == 0), "the fused skip conv rides on the stride-2 encoder stages");
 };
 
 __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
@@ -127,11 +134,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {   // this 
         : "memory");
 }
 
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS>
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS, int FUSE = 0>
 __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTcArgs a) {
     constexpr int CT_SETS = NS, CT_PROD_WARPS = CT_NPW * NS, CT_MMA_WARP = CT_PROD_WARPS, CT_EPI_WARP0 = CT_PROD_WARPS + 1;
     constexpr int CT_THREADS = ct_threads(NS);
-    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
+    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM, FUSE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms are 1024-byte aligned
     uint8_t* ring = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -172,7 +179,14 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 float v = 0.f;
                 if (i < WTOT && k < C::KG && n < C::N) {
                     const int tap = k / C::CB, ci = g * C::CB + (k - tap * C::CB);
-                    if (C::CONVLIKE) {
+                    if (C::CONVLIKE && FUSE && n >= COUT) {
+                        // fused skip conv (Conv2d [CIN][CIN][1][3], pad 1): column COUT + 2*cs + ph = output bin 2fo+ph of channel cs,
+                        // which reads the CURRENT frame's taps ph, ph+1, ph+2 (tap t = input bin 2fo-1+t)
+                        const int cs = (n - COUT) >> 1, ph = (n - COUT) & 1, kf = tap - ph;
+                        v = (kt == KT - 1 && kf >= 0 && kf < 3) ? __ldg(a.w2 + ((size_t)cs * CIN + ci) * 3 + kf) : 0.f;
+                    } else if (C::CONVLIKE && FUSE && tap == 3) {
+                        v = 0.f;                                                                     // the stage itself has three taps
+                    } else if (C::CONVLIKE) {
                         v = a.wmode == 1 ? __ldg(a.w + ((size_t)ci * COUT + n) * 3 + (2 - tap))        // dgrad: [Cin][Cout][1][3], flipped
                                          : __ldg(a.w + (((size_t)n * CIN + ci) * KT + kt) * 3 + tap);  // Conv2d [Cout][Cin][KT][3]
                     } else if (MODE == 2) {
@@ -264,7 +278,7 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                         vb[it][0] = __ldg(src + C::FIN);
                     }
                     if ((MODE == 0 || MODE == 1) && row16 == 0 && fo > 0) { ea[it] = __ldg(src - 1); eb[it] = __ldg(src + C::FIN - 1); }
-                    if (MODE == 3 && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 2); eb[it] = __ldg(src + C::FIN + 2); }
+                    if ((MODE == 3 || FUSE) && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 2); eb[it] = __ldg(src + C::FIN + 2); }
                     if (((MODE == 0 && SF == 1) || MODE == 2) && row16 == 15 && fo < FO - 1) { ea[it] = __ldg(src + 1); eb[it] = __ldg(src + C::FIN + 1); }
                 }
             }
@@ -276,7 +290,8 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                 const int item = it * CT_NPW + wq;
                 const int fg = item % (FO / 16), cg = (item / (FO / 16)) % (C::CB / 4), fr = item / ((FO / 16) * (C::CB / 4));
                 const int row = fr * FO + fg * 16 + row16;
-                float ta[3], tb[3];
+                float ta[4], tb[4];
+                ta[3] = tb[3] = 0.f;
                 if (MODE == 3) {                     // taps read bins 2fo, 2fo+1, 2fo+2 (cropped)
                     float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
                     if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
@@ -287,6 +302,11 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                     if (row16 == 0) { la = ea[it]; lb = eb[it]; }
                     ta[0] = la; ta[1] = va[it][0]; ta[2] = va[it][NV - 1];
                     tb[0] = lb; tb[1] = vb[it][0]; tb[2] = vb[it][NV - 1];
+                    if (FUSE) {                      // fourth tap: bin 2fo+2 = the next row's own first value (lane 15: the edge load)
+                        float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
+                        if (row16 == 15) { ra = ea[it]; rb = eb[it]; }
+                        ta[3] = ra; tb[3] = rb;
+                    }
                 } else if (MODE == 0) {              // taps read bins fo-1, fo, fo+1
                     float la = __shfl_up_sync(0xffffffffu, va[it][0], 2), lb = __shfl_up_sync(0xffffffffu, vb[it][0], 2);
                     float ra = __shfl_down_sync(0xffffffffu, va[it][0], 2), rb = __shfl_down_sync(0xffffffffu, vb[it][0], 2);
@@ -419,7 +439,15 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
                     const int t = t0 + tl;
                     if (t >= a.t_end) continue;
                     const size_t rec = a.out_tm ? (size_t)t * a.B + b : (size_t)b * T + t;
-                    if (C::CONVLIKE) {
+                    if (C::CONVLIKE && FUSE && c0 >= COUT) {
+                        // the fused skip conv: columns (cs, ph) -> out2[b, t, cs, 2fo + ph], frame-major, no BatchNorm / activation
+                        const size_t o2 = ((size_t)b * T + t) * CIN * (2 * FO) + 2 * fo;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int cs = ((c0 - COUT) >> 1) + q;
+                            if (cs < CIN) *reinterpret_cast<float2*>(a.out2 + o2 + (size_t)cs * (2 * FO)) = make_float2(v[i][2 * q], v[i][2 * q + 1]);
+                        }
+                    } else if (C::CONVLIKE) {
                         const size_t o0 = rec * COUT * FO + fo;
                         float ad[16];
 #pragma unroll
@@ -473,13 +501,13 @@ inline bool conv_pdl_enabled() {
     return v == 1;
 }
 
-template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS>
+template <int MODE, int KT, int SF, int CIN, int COUT, int FO, int GM, int NS, int FUSE = 0>
 int launch_conv_tc(const ConvTcArgs& a_in, cudaStream_t st) {
-    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM>;
+    using C = ConvTcCfg<MODE, KT, SF, CIN, COUT, FO, GM, FUSE>;
     ConvTcArgs a = a_in;
     if (a.t_end <= 0) { a.t_begin = 0; a.t_end = a.T; }
     if (a.t_begin < 0 || a.t_begin >= a.t_end || a.t_end > a.T) return -1;
-    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO, GM, NS>;
+    auto kern = conv_tc_kernel<MODE, KT, SF, CIN, COUT, FO, GM, NS, FUSE>;
     static bool attr_set = false;                                   // per instantiation; benign if raced
     if (!attr_set) {
         CRUSE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -534,7 +562,7 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
     if (hist && (kt != 2 || in_tm || (reinterpret_cast<uintptr_t>(hist) & 15))) return 0;
     if (wmode != 0 && !(wmode == 1 && kt == 1 && fstride == 1)) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, hist, t_begin, t_end, wmode};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, addend, out, B, T, act, in_tm, out_tm, hist, t_begin, t_end, wmode, nullptr, nullptr};
     int rc = 0;
     // last argument: MMA tiles (128 rows) per pipeline step; stages with long frames (FO >= 32) batch several of them
 #define CRUSE_CT_CONV(KT_, SF_, CI_, CO_, FO_, GM_, NS_)                                                    \
@@ -553,13 +581,33 @@ int conv_tc_try(const float* in, const float* w, const float* bias, const float*
     return 0;
 }
 
+// encoder stage (2,3)/stride-(1,2) + folded BN + act WITH the (1,3) skip conv of its input fused in (eval mode, whole utterances or a
+// frame range): out = act(BN(conv(in))), out2 = conv1x3(in; w2).  Returns 1 when launched, 0 when no instantiation matches.
+int conv_skip_tc_try(const float* in, const float* w, const float* bias, const float* scale, const float* shift, const float* alpha,
+                     int act, const float* w2, float* out, float* out2, int B, int T, int Cin, int Fin, int Cout, int Fout, int out_tm,
+                     cudaStream_t st, int t_begin, int t_end) {
+    if (!conv_tc_enabled()) return 0;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(out2) & 15)) return 0;
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, nullptr, out, B, T, act, 0, out_tm, nullptr, t_begin, t_end, 0, w2, out2};
+    int rc = 0;
+#define CRUSE_CT_FUSED(CI_, CO_, FO_, GM_, NS_)                                      \
+    if (Cin == CI_ && Cout == CO_ && Fout == FO_ && Fin == 2 * FO_) {                \
+        rc = launch_conv_tc<0, 2, 2, CI_, CO_, FO_, GM_, NS_, 1>(a, st);             \
+        return rc ? rc : 1;                                                          \
+    }
+    CRUSE_CT_FUSED(8, 16, 64, 2, 2)
+    CRUSE_CT_FUSED(16, 32, 32, 1, 2)
+#undef CRUSE_CT_FUSED
+    return 0;
+}
+
 // data gradient of the transposed conv: din[ci, i] = sum_co sum_k W[ci,co,0,k] dz[co, 2i+k] -- a (1,3)/stride-2 conv over dz
 // without left pad; w is the ConvTranspose2d weight [Cin][Cout][1][3], which is exactly the [out][in][1][3] this conv reads
 int convT_dgrad_tc_try(const float* dz, const float* w, const float* addend, float* din, int B, int T, int Cin, int Fin, int Cout,
                        int Fout, cudaStream_t st) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0, 0, 0};
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0, 0, 0, nullptr, nullptr};
     int rc = 0;
 #define CRUSE_CT_TD(CO_, CI_, FI_, NS_)                                              \
     if (Cout == CO_ && Cin == CI_ && Fin == FI_ && Fout == 2 * FI_) {                \
@@ -578,7 +626,7 @@ int conv_dgrad_tc_try(const float* dz, const float* w, const float* addend, floa
                       int Fout, int kt, cudaStream_t st) {
     if (!conv_tc_enabled() || kt != 2) return 0;
     if ((reinterpret_cast<uintptr_t>(dz) & 15) || (reinterpret_cast<uintptr_t>(din) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15)) return 0;
-    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0, 0, 0};
+    ConvTcArgs a{dz, w, nullptr, nullptr, nullptr, nullptr, addend, din, B, T, CRUSE_ACT_NONE, 0, 0, nullptr, 0, 0, 0, nullptr, nullptr};
     int rc = 0;
 #define CRUSE_CT_CD(CO_, CI_, FO_, GM_, NS_)                                         \
     if (Cout == CO_ && Cin == CI_ && Fout == FO_ && Fin == 2 * FO_) {                \
@@ -597,7 +645,7 @@ int convT_tc_try(const float* in, const float* w, const float* bias, const float
                  int t_begin, int t_end) {
     if (!conv_tc_enabled()) return 0;
     if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(skip) & 15)) return 0;
-    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, nullptr, t_begin, t_end, 0};
+    ConvTcArgs a{in, w, bias, scale, shift, alpha, skip, out, B, T, act, 0, 0, nullptr, t_begin, t_end, 0, nullptr, nullptr};
     int rc = 0;
 #define CRUSE_CT_CONVT(CI_, CO_, FI_, GM_, NS_)                                      \
     if (Cin == CI_ && Cout == CO_ && Fin == FI_ && Fout == 2 * FI_) {                \

@@ -266,6 +266,31 @@ def conv_fwd_tm(x, w, bias, scale, shift, alpha, act, kt, fstride, B, T, in_tm, 
     return out
 
 
+# fuse the skip conv of a stage's input into the stage (inference, tf32 conv mode): CRUSE_FUSE_SKIPS=0 keeps them separate
+FUSE_SKIPS = os.environ.get("CRUSE_FUSE_SKIPS", "1") != "0"
+
+
+def conv_skip_fwd(x, w, bias, scale, shift, alpha, act, w_skip, out_skip=None, out_tm=False, t0=0, t1=0):
+    """eval-mode encoder stage (2,3)/stride (1,2) + folded BN + act WITH the (1,3) skip conv of its input fused in:
+    x [B,T,Cin,Fin] -> (out [B,T,Cout,Fin/2] ([T,B,..] with out_tm), out_skip [B,T,Cin,Fin]); one pass over x."""
+    _req(x, "x", 4)
+    _req(w, "w", 4)
+    _req(w_skip, "w_skip", 4)
+    B, T, Cin, Fin = x.shape
+    Cout = w.shape[0]
+    if tuple(w.shape) != (Cout, Cin, 2, 3) or tuple(w_skip.shape) != (Cin, Cin, 1, 3):
+        raise RuntimeError(f"conv_skip_fwd: weight shapes {tuple(w.shape)} / {tuple(w_skip.shape)} do not match x {tuple(x.shape)}")
+    Fout = (Fin + 2 - 3) // 2 + 1
+    out = torch.empty((T, B, Cout, Fout) if out_tm else (B, T, Cout, Fout), device=x.device, dtype=torch.float32)
+    if out_skip is None:
+        out_skip = torch.empty(B, T, Cin, Fin, device=x.device, dtype=torch.float32)
+    _call("cruse_conv_skip_fwd", _p(x), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(w_skip), _p(out), _p(out_skip),
+          B, T, Cin, Fin, Cout, Fout, 1 if out_tm else 0, t0, t1, _stream(),
+          meta=(f"conv2x3 {Cin}->{Cout} F{Fin}->{Fout} + skip1x3 {Cin}->{Cin}", _nb(x, out, out_skip, w, w_skip),
+                2 * B * T * (Cout * Fout * Cin * 6 + Cin * Fin * Cin * 3)))
+    return out, out_skip
+
+
 def conv_fwd_range(x, w, bias, scale, shift, alpha, act, kt, fstride, B, T, out, t0, t1, in_tm=False, out_tm=False):
     """eval-mode stage for the output frames [t0, t1) only, written into the full-size ``out`` ([B,T,Cout,Fout], or
     [T,B,Cout,Fout] with ``out_tm``); x is the full-size input of the stage (frames < t1 must be valid)."""

@@ -138,6 +138,15 @@ int cruse_bn_fold_many(const float* const* gamma, const float* const* beta, cons
 int cruse_bn_act_fwd(const float* z, const float* scale, const float* shift, const float* alpha, int act,
                      const float* skip, float* y, long long n_frames, int C, int F, void* stream);
 
+/* Encoder stage WITH the skip conv of its input fused in (eval mode; replaces one cruse_conv_fwd + one skip cruse_conv_fwd:
+ * model/cruse_net.py:149-152 for stage k+1 and :153-155 for skip_connect_k, which read the same tensor e_k):
+ *   out      [B,T,Cout,Fout]  = act(BN(Conv2d((2,3), stride (1,2), pad (1,1))(in)[..., :-1, :]))   (time-major records if out_time_major)
+ *   out_skip [B,T,Cin,Fin]    = Conv2d((1,3), pad (0,1), bias=False)(in)        w_skip [Cin][Cin][1][3]
+ * One pass over `in`: the stage's shared-memory tile gets a fourth frequency tap and the skip outputs are extra accumulator columns.
+ * Tensor-core instantiations only (Cin 8 / 16 of the 256-bin pyramid); t_begin = t_end = 0 means all frames. */
+int cruse_conv_skip_fwd(const float* in, const float* w, const float* bias, const float* scale, const float* shift,
+                        const float* alpha, int act, const float* w_skip, float* out, float* out_skip, int B, int T,
+                        int Cin, int Fin, int Cout, int Fout, int out_time_major, int t_begin, int t_end, void* stream);
 /* Eval-mode stages restricted to the OUTPUT frames [t_begin, t_end) of every utterance (same argument meaning as
  * cruse_conv_fwd_tm / cruse_convT_fwd / cruse_layernorm_fwd; out / y are the full-size tensors, rows outside the range are
  * not touched).  The net is causal (model/cruse_net.py:138 pads time on the left only), so a frame range of a stage needs

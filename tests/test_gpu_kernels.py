@@ -478,3 +478,36 @@ def test_mask_istft_and_loss_range_entries(cuda, n_fft, hop, B, L):
         ops.mask_istft_fwd_range(X, mask, win, n_fft, hop, est1, wav1, 0, nct + 1)
     with pytest.raises(RuntimeError):
         ops.wo_male_masked_partial_range(S, ops.layout_btf2(S), mask, X, ops.layout_btf2(X), ws, ws.numel(), 1, B, T, F, 0, T)
+
+
+@pytest.mark.parametrize("Cin,Cout,Fin", [(8, 16, 128), (16, 32, 64)])
+@pytest.mark.parametrize("B,T,rng", [(3, 37, None), (2, 64, (9, 41)), (33, 5, None)])
+def test_fused_encoder_stage_and_skip_conv_equal_the_separate_kernels(cuda, Cin, Cout, Fin, B, T, rng):
+    """cruse_conv_skip_fwd (encoder stage k+1 with skip conv k riding on the same shared-memory tile, model/cruse_net.py:150-155)
+    against the two separate tensor-core launches it replaces (same tf32 products, at most a different summation order: 1e-6) and
+    against the CPU nn ops (tf32 gate 1e-3); also for a frame range and with the stage output written time-major."""
+    from cruse_b200 import ops
+    ops.set_conv_mode("tf32")                 # (the autouse fixture of this file restores the mode afterwards)
+    torch.manual_seed(41)
+    conv = nn.Conv2d(Cin, Cout, (2, 3), (1, 2), (1, 1))
+    skipc = nn.Conv2d(Cin, Cin, (1, 3), bias=False, padding=(0, 1))
+    x = torch.randn(B, Cin, T, Fin)
+    scale, shift = 1 + 0.1 * torch.randn(Cout), 0.1 * torch.randn(Cout)
+    with torch.no_grad():
+        want = torch.relu(conv(x)[..., :-1, :] * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).permute(0, 2, 1, 3)
+        want_skip = skipc(x).permute(0, 2, 1, 3)
+    xf = x.permute(0, 2, 1, 3).contiguous().to(cuda)
+    w, b, ws = conv.weight.detach().to(cuda), conv.bias.detach().to(cuda), skipc.weight.detach().to(cuda)
+    sc, sh = scale.to(cuda), shift.to(cuda)
+    sep = ops.conv_fwd(xf, w, b, sc, sh, None, "relu", 2, 2)
+    sep_skip = ops.conv_fwd(xf, ws, None, None, None, None, "none", 1, 1)
+    t0, t1 = rng if rng else (0, 0)
+    out_skip = torch.zeros(B, T, Cin, Fin, device=cuda)
+    got, got_skip = ops.conv_skip_fwd(xf, w, b, sc, sh, None, "relu", ws, out_skip=out_skip, t0=t0, t1=t1)
+    sl = slice(t0, t1) if rng else slice(None)
+    assert rel_err(got[:, sl], sep[:, sl]) <= 1e-6 and rel_err(got_skip[:, sl], sep_skip[:, sl]) <= 1e-6
+    assert rel_err(got[:, sl], want[:, sl]) <= 1e-3 and rel_err(got_skip[:, sl], want_skip[:, sl]) <= 1e-3
+    if rng:
+        assert float(got_skip[:, :t0].abs().max()) == 0.0 and float(got_skip[:, t1:].abs().max()) == 0.0   # outside the range: untouched
+    got_tm, _ = ops.conv_skip_fwd(xf, w, b, sc, sh, None, "relu", ws, out_tm=True)
+    assert rel_err(got_tm.transpose(0, 1), sep) <= 1e-6

@@ -149,6 +149,119 @@ __device__ __forceinline__ float2* warp_fft256(float2* x, float2* y, const float
     return x;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// M = 256 (n_fft = 512) in REGISTERS: every lane holds 8 of the 256 complex points, the transform is radix 8 x 8 x 4 with the
+// butterflies in registers and only TWO exchanges through a small shared-memory pad (the ping-pong version above does four full
+// passes through shared memory: 8 loads + 6 twiddle loads + 8 stores per lane and pass, the stores of the first two passes 8- and
+// 4-way bank conflicted; measured, that made the STFT / iSTFT kernels instruction bound at 6-9 % of the HBM roofline).
+// Same Stockham index algebra as warp_fft (so the results agree to rounding):
+//   pass 1 (r 8, m 32, s 1):  lane i:            in x[i + 32 j]            out y1[8 i + k]          * W256^(i k)
+//   pass 2 (r 8, m 4,  s 8):  lane i = 8 p + q:  in y1[i + 32 j]           out y2[q + 64 p + 8 k]   * W32^(p k)
+//   pass 3 (r 4, m 1, s 64):  lane i:            in y2[i + 64 j], y2[i + 32 + 64 j]   out Z[i + 64 k], Z[i + 32 + 64 k]
+// Input and output are both "lane-strided" (element lane + 32 j in register j): coalesced global accesses on either side.
+// The per-lane twiddles depend on the lane only and are loaded once per kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FftRegTw {
+    float2 w1[7];      // W256^(lane * k),     k = 1..7
+    float2 w2[7];      // W32^((lane / 8) * k)
+};
+constexpr int FFT_XCH = 320;                       // float2 slots of one warp's exchange pad
+
+__device__ __forceinline__ void fft_reg_tw_init(FftRegTw& t, const float2* __restrict__ tw512, int lane) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        t.w1[k - 1] = tw512[2 * lane * k];          // <= 2*31*7 = 434 < 512
+        t.w2[k - 1] = tw512[16 * (lane >> 3) * k];  // <= 16*3*7 = 336
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ float2 mul_i(float2 a) {   // a * (-i) forward, a * (+i) inverse
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft4_reg(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 e0 = cadd(a0, a2), e1 = csub(a0, a2), o0 = cadd(a1, a3), o1 = mul_i<INV>(csub(a1, a3));
+    a0 = cadd(e0, o0); a1 = cadd(e1, o1); a2 = csub(e0, o0); a3 = csub(e1, o1);
+}
+
+// v[k] <- sum_j v[j] W8^(jk)   (W8 = exp(-+ 2 pi i / 8)), natural order in and out
+template <bool INV>
+__device__ __forceinline__ void dft8_reg(float2 (&v)[8]) {
+    const float h = 0.70710678118654752f;
+    float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+    float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+    // b_j *= W8^j
+    b1 = INV ? make_float2(h * (b1.x - b1.y), h * (b1.x + b1.y)) : make_float2(h * (b1.x + b1.y), h * (b1.y - b1.x));
+    b2 = mul_i<INV>(b2);
+    b3 = INV ? make_float2(-h * (b3.x + b3.y), h * (b3.x - b3.y)) : make_float2(h * (b3.y - b3.x), -h * (b3.x + b3.y));
+    dft4_reg<INV>(a0, a1, a2, a3);                  // even outputs 0, 2, 4, 6
+    dft4_reg<INV>(b0, b1, b2, b3);                  // odd outputs 1, 3, 5, 7
+    v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+    v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+
+template <bool INV>
+__device__ __forceinline__ void warp_fft256_reg(float2 (&z)[8], const FftRegTw& t, float2* __restrict__ xch, int lane) {
+    // ---- pass 1
+    dft8_reg<INV>(z);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        float2 w = t.w1[k - 1];
+        if (INV) w.y = -w.y;
+        z[k] = cmul(z[k], w);
+    }
+    // exchange 1: y1[8 i + k] sits at slot 10 i + k (80-byte lane pitch: the four 16-byte stores of a lane are conflict free)
+    {
+        float4* wa = reinterpret_cast<float4*>(xch + 10 * lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wa[k] = make_float4(z[2 * k].x, z[2 * k].y, z[2 * k + 1].x, z[2 * k + 1].y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = xch[10 * ((lane >> 3) + 4 * j) + (lane & 7)];      // y1[lane + 32 j]
+    __syncwarp();
+    // ---- pass 2
+    dft8_reg<INV>(z);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        float2 w = t.w2[k - 1];
+        if (INV) w.y = -w.y;
+        z[k] = cmul(z[k], w);
+    }
+    // exchange 2: y2[e] sits at slot e + 8 (e >> 6)  (72-slot pitch per 64: the four p blocks of a store hit different banks)
+    {
+        const int base2 = (lane & 7) + 72 * (lane >> 3);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xch[base2 + 8 * k] = z[k];                               // y2[q + 64 p + 8 k]
+    }
+    __syncwarp();
+    float2 a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a[j] = xch[lane + 72 * j];                                                          // y2[lane + 64 j]
+        b[j] = xch[lane + 32 + 72 * j];                                                     // y2[lane + 32 + 64 j]
+    }
+    __syncwarp();
+    // ---- pass 3
+    dft4_reg<INV>(a[0], a[1], a[2], a[3]);
+    dft4_reg<INV>(b[0], b[1], b[2], b[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { z[2 * k] = a[k]; z[2 * k + 1] = b[k]; }                    // Z[lane + 32 j] in z[j]
+}
+
+// value of register j' of lane (32 - lane) & 31 where the source element is Z[(256 - (lane + 32 j)) & 255]
+__device__ __forceinline__ float2 fft_reg_partner(const float2 (&z)[8], int j, int lane) {
+    const int src = (32 - lane) & 31;
+    float2 v;
+    // lanes != 0: element 256 - lane - 32 j = (32 - lane) + 32 (7 - j): register 7 - j of the partner lane
+    v.x = __shfl_sync(0xffffffffu, z[7 - j].x, src);
+    v.y = __shfl_sync(0xffffffffu, z[7 - j].y, src);
+    if (lane == 0) v = z[(8 - j) & 7];               // lane 0: element (256 - 32 j) & 255 = 32 ((8 - j) & 7), its own register
+    return v;
+}
+
 __device__ __forceinline__ float load_padded(const float* __restrict__ xb, int i, int L, int pad_mode) {
     if (i < 0) {
         if (pad_mode == CRUSE_PAD_CONSTANT) return 0.f;
@@ -194,7 +307,7 @@ stft_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ window,
             }
         }
         __syncwarp();
-        const float2* Z = (M == 256) ? warp_fft256<false>(x, y, tw, lane) : warp_fft<false>(x, y, tw, M, plan, lane);
+        const float2* Z = warp_fft<false>(x, y, tw, M, plan, lane);
         float2* so = reinterpret_cast<float2*>(spec) + fr * NF;
         float* mo = mag ? mag + fr * mag_bins : nullptr;
         for (int k = lane; k <= M; k += 32) {
@@ -209,6 +322,69 @@ stft_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ window,
             if (mo && k < mag_bins) mo[k] = sqrtf(X.x * X.x + X.y * X.y + mag_eps);
         }
         __syncwarp();
+    }
+}
+
+// n_fft = 512 (the geometry of the benchmark): one warp per frame, the 256-point complex FFT in registers (warp_fft256_reg).
+// Every global access is lane-strided (element lane + 32 j): full 256-byte warp transactions for the samples, the window, the
+// spectrum and the magnitude.
+__global__ void __launch_bounds__(256, 3)
+stft512_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ window, float* __restrict__ spec,
+                   float* __restrict__ mag, int B, int L, int hop, int T, int pad_mode, int mag_bins, float mag_eps) {
+    constexpr int N = 512, M = 256, NF = 257;
+    extern __shared__ float2 sm_[];
+    float2* tw = sm_;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float2* xch = sm_ + N + (size_t)warp * FFT_XCH;
+    build_twiddles(tw, N);
+    __syncthreads();
+    FftRegTw rt;
+    fft_reg_tw_init(rt, tw, lane);
+    const float2* w2 = reinterpret_cast<const float2*>(window);
+
+    const long long nframes = (long long)B * T;
+    for (long long fr = (long long)blockIdx.x * nwarps + warp; fr < nframes; fr += (long long)gridDim.x * nwarps) {
+        const int b = (int)(fr / T), t = (int)(fr - (long long)b * T);
+        const float* xb = wav + (long long)b * L;
+        const int start = t * hop - M;
+        const bool interior = (start >= 0) && (start + N <= L) && ((((long long)b * L + start) & 1) == 0);
+        float2 z[8];
+        if (interior) {
+            const float2* x2 = reinterpret_cast<const float2*>(xb + start);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 v = __ldg(x2 + lane + 32 * j), w = __ldg(w2 + lane + 32 * j);
+                z[j] = make_float2(v.x * w.x, v.y * w.y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = lane + 32 * j;
+                const float2 w = __ldg(w2 + n);
+                z[j] = make_float2(load_padded(xb, start + 2 * n, L, pad_mode) * w.x, load_padded(xb, start + 2 * n + 1, L, pad_mode) * w.y);
+            }
+        }
+        warp_fft256_reg<false>(z, rt, xch, lane);
+        float2* so = reinterpret_cast<float2*>(spec) + fr * NF;
+        float* mo = mag ? mag + fr * mag_bins : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = lane + 32 * j;
+            const float2 zk = z[j];
+            float2 zc = fft_reg_partner(z, j, lane);
+            zc.y = -zc.y;
+            const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+            const float2 xo = make_float2(d.y, -d.x);  // d / i
+            const float2 X = cadd(xe, cmul(tw[k], xo));
+            so[k] = X;
+            if (mo && k < mag_bins) mo[k] = sqrtf(X.x * X.x + X.y * X.y + mag_eps);
+        }
+        if (lane == 0) {                                // Nyquist bin: X[256] = Re Z[0] - Im Z[0]
+            const float2 X = make_float2(z[0].x - z[0].y, 0.f);
+            so[M] = X;
+            if (mo && M < mag_bins) mo[M] = sqrtf(X.x * X.x + mag_eps);
+        }
     }
 }
 
@@ -303,6 +479,107 @@ mask_istft_kernel(const float* __restrict__ spec, const float* __restrict__ mask
     }
 }
 
+// n_fft = 512: the same CTA structure (a run of FC frames of one utterance + halo frames recomputed, overlap-add as a shared-memory
+// gather) with the inverse transform in registers (warp_fft256_reg) and lane-strided global accesses; the noisy spectrum is
+// read ONCE per frame for both the enhanced spectrum and the waveform.
+__global__ void __launch_bounds__(256, 3)
+mask_istft512_kernel(const float* __restrict__ spec, const float* __restrict__ mask, const float* __restrict__ window,
+                     float* __restrict__ est_spec, float* __restrict__ wav, int B, int L, int hop, int T,
+                     int mask_bins, int FC, int halo, int c_begin) {
+    constexpr int N = 512, M = 256, NF = 257;
+    extern __shared__ float2 sm_[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float2* tw = sm_;
+    float2* xch = sm_ + N + (size_t)warp * FFT_XCH;
+    float* frames = reinterpret_cast<float*>(sm_ + N + (size_t)nwarps * FFT_XCH);
+    const int b = blockIdx.y, t0 = (blockIdx.x + c_begin) * FC, tbeg = t0 - halo, nfr = FC + halo;
+    build_twiddles(tw, N);
+    __syncthreads();
+    FftRegTw rt;
+    fft_reg_tw_init(rt, tw, lane);
+    const float inv_m = 1.0f / (float)M;
+    const float2* w2 = reinterpret_cast<const float2*>(window);
+
+    for (int fi = warp; fi < nfr; fi += nwarps) {
+        const int t = tbeg + fi;
+        if (t < 0 || t >= T) continue;  // never read by the gather below
+        const long long fr = (long long)b * T + t;
+        const float2* si = reinterpret_cast<const float2*>(spec) + fr * NF;
+        const float* mi = mask ? mask + fr * mask_bins : nullptr;
+        const bool want_est = est_spec && t >= t0;
+        float2* eo = reinterpret_cast<float2*>(est_spec) + fr * NF;
+        float2 z[8];
+        float2 xk[8], xm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                 // all 16 spectrum loads (and the mask) of the frame in flight together
+            const int k = lane + 32 * j;
+            xk[j] = __ldg(si + k);
+            xm[j] = __ldg(si + (M - k));
+            const float mk = (mi && k < mask_bins) ? __ldg(mi + k) : 1.f;
+            const float mm = (mi && (M - k) < mask_bins) ? __ldg(mi + (M - k)) : 1.f;
+            xk[j].x *= mk; xk[j].y *= mk; xm[j].x *= mm; xm[j].y *= mm;
+        }
+        if (want_est) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) eo[lane + 32 * j] = xk[j];
+            if (lane == 0) eo[M] = xm[0];             // bin 256 = X[M - 0] of lane 0
+        }
+        if (wav) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = lane + 32 * j;
+                float2 a = xk[j], c = xm[j];
+                if (k == 0) { a.y = 0.f; c.y = 0.f; }  // c2r ignores imag of DC and Nyquist
+                c.y = -c.y;                            // conj(X[M-k])
+                const float2 xe = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y + c.y));
+                const float2 d = make_float2(0.5f * (a.x - c.x), 0.5f * (a.y - c.y));
+                float2 w = tw[k];
+                w.y = -w.y;  // W_N^{-k}
+                const float2 xo = cmul(d, w);
+                z[j] = make_float2(xe.x - xo.y, xe.y + xo.x);  // Xe + i*Xo
+            }
+            warp_fft256_reg<true>(z, rt, xch, lane);
+            float2* fb = reinterpret_cast<float2*>(frames + (size_t)fi * N);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = lane + 32 * j;
+                const float2 w = __ldg(w2 + n);
+                fb[n] = make_float2(z[j].x * inv_m * w.x, z[j].y * inv_m * w.y);
+            }
+        }
+    }
+    if (!wav) return;
+    __syncthreads();
+
+    const bool last = (t0 + FC >= T);
+    const long long m_lo = (long long)t0 * hop;
+    long long m_hi = (long long)(t0 + FC) * hop;
+    if (last) {
+        long long a = (long long)(T - 1) * hop + N, c = (long long)L + M;
+        m_hi = a > c ? a : c;
+    }
+    float* wo = wav + (long long)b * L;
+    const int nslots = (int)((m_hi - m_lo + hop - 1) / hop);
+    for (int i = 0; i < nslots; ++i) {
+        const int tt = t0 + i;
+        for (int r = threadIdx.x; r < hop; r += blockDim.x) {
+            const long long m = m_lo + (long long)i * hop + r;
+            const long long sidx = m - M;
+            if (m >= m_hi || sidx < 0 || sidx >= L) continue;
+            float sum = 0.f, env = 0.f;
+            int t = tt;
+            for (int off = r; off < N; off += hop, --t) {
+                if (t < 0) break;
+                if (t > T - 1) continue;
+                sum += frames[(size_t)(t - tbeg) * N + off];
+                const float w = __ldg(window + off);
+                env += w * w;
+            }
+            wo[sidx] = env > 1e-11f ? sum / env : 0.f;
+        }
+    }
+}
+
 __global__ void mask_bwd_kernel(const float* __restrict__ dest, const float* __restrict__ spec,
                                 const float* __restrict__ gscale, const float* __restrict__ mask, float* __restrict__ dmask,
                                 long long rows, int NF, int mask_bins) {
@@ -333,10 +610,20 @@ extern "C" int cruse_stft_fwd(const float* wav, const float* window, float* spec
     FftPlan plan;
     CRUSE_CHECK_ARG(make_plan(n_fft / 2, plan) == 0, "stft_fwd: n_fft/2=%d must factor into 2,3,5", n_fft / 2);
     const int threads = 256, nwarps = threads / 32;
+    const long long nframes = (long long)B * T;
+    if (n_fft == 512) {
+        const size_t smem512 = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * FFT_XCH);
+        long long blocks = (nframes + nwarps - 1) / nwarps;
+        const long long cap = (long long)sm_count() * 3;         // persistent: 3 CTAs per SM, each builds its twiddle table once
+        if (blocks > cap) blocks = cap;
+        stft512_fwd_kernel<<<(unsigned)blocks, threads, smem512, (cudaStream_t)stream>>>(wav, window, spec, mag_bins > 0 ? mag : nullptr, B, L,
+                                                                                        hop, T, pad_mode, mag_bins, mag_eps);
+        CRUSE_LAUNCH_OK();
+        return 0;
+    }
     const size_t smem = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * n_fft);
     CRUSE_CHECK_ARG(smem <= 200 * 1024, "stft_fwd: n_fft=%d too large for on-chip FFT", n_fft);
     CRUSE_CUDA_OK(cudaFuncSetAttribute(stft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long nframes = (long long)B * T;
     long long blocks = (nframes + nwarps - 1) / nwarps;
     const long long cap = (long long)sm_count() * 6;  // persistent-ish (6 CTAs of 36 KB fit an SM): each CTA builds its twiddle table once
     if (blocks > cap) blocks = cap;
@@ -348,7 +635,9 @@ extern "C" int cruse_stft_fwd(const float* wav, const float* window, float* spec
 
 static int istft_chunk_frames(int n_fft, int hop) {
     const int nwarps = 256 / 32, halo = (n_fft - 1) / hop;
-    const int FC = 2 * nwarps - halo;
+    // n_fft = 512: one frame per warp (FC + halo = 8): twice the CTAs of the two-round version, half the serial work in each --
+    // the frame ranges that follow the decoder are short and latency bound
+    const int FC = (n_fft == 512 ? 1 : 2) * nwarps - halo;
     return FC < 1 ? nwarps : FC;
 }
 
@@ -386,15 +675,26 @@ static int mask_istft_launch(const float* spec, const float* mask, const float* 
     CRUSE_CHECK_ARG(make_plan(n_fft / 2, plan) == 0, "mask_istft_fwd: n_fft/2=%d must factor into 2,3,5", n_fft / 2);
     const int threads = 256, nwarps = threads / 32;
     const int halo = (n_fft - 1) / hop;
-    int FC = 2 * nwarps - halo;
-    if (FC < 1) FC = nwarps;
+    const int FC = istft_chunk_frames(n_fft, hop);
     const size_t smem = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * n_fft) + sizeof(float) * (size_t)(FC + halo) * n_fft;
     CRUSE_CHECK_ARG(smem <= 220 * 1024, "mask_istft_fwd: n_fft=%d / hop=%d need too much shared memory", n_fft, hop);
-    CRUSE_CUDA_OK(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nchunks = (T + FC - 1) / FC;
     if (c_end < 0) c_end = nchunks;
     CRUSE_CHECK_ARG(c_begin >= 0 && c_begin < c_end && c_end <= nchunks, "mask_istft_fwd: CTA range [%d,%d) outside [0,%d)", c_begin, c_end, nchunks);
     dim3 grid(c_end - c_begin, B);
+    if (n_fft == 512) {
+        const size_t smem512 = sizeof(float2) * ((size_t)n_fft + (size_t)nwarps * FFT_XCH) + sizeof(float) * (size_t)(FC + halo) * n_fft;
+        static bool attr512 = false;
+        if (!attr512) {
+            CRUSE_CUDA_OK(cudaFuncSetAttribute(mask_istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem512));
+            attr512 = true;
+        }
+        mask_istft512_kernel<<<grid, threads, smem512, (cudaStream_t)stream>>>(spec, mask_bins > 0 ? mask : nullptr, window, est_spec, wav, B, L,
+                                                                              hop, T, mask_bins, FC, halo, c_begin);
+        CRUSE_LAUNCH_OK();
+        return 0;
+    }
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mask_istft_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(spec, mask_bins > 0 ? mask : nullptr, window, est_spec, wav, B, L,
                                                                     n_fft, hop, T, mask_bins, FC, halo, plan, c_begin);
     CRUSE_LAUNCH_OK();

@@ -78,7 +78,10 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                     ops.mask_istft_fwd_range(X, mask_all, window, n_fft, hop, est_buf, wav_buf, prog["c"], c1)
                     prog["c"] = c1
             with torch.cuda.stream(side2):
-                nparts = max(1, ws.numel() * (t1 - t0) // T)
+                # CTAs (= partial-sum slots) of this range: at least two (b, t) rows each, never fewer than ~4 per SM -- the last,
+                # short range sits on the critical path and is pure latency with few CTAs
+                rows = X.shape[0] * (t1 - t0)
+                nparts = max(1, min(rows // 2, max(592, ws.numel() // 4 * (t1 - t0) // T), ws.numel() - prog["p"]))
                 ops.wo_male_masked_partial_range(S, lay_s, mask_all, X, lay_x, ws, prog["p"], nparts, X.shape[0], T, F, t0, t1)
                 prog["p"] += nparts
 

@@ -386,9 +386,11 @@ class unet_2(nn.Module):
 
     @staticmethod
     def chunk_groups(nch, cuts=None):
-        """[(k0, k1), ...]: the groups of wavefront chunks the pipelined decoder / skip convs are issued in -- everything up to
-        three chunks before the end, the next two, the last one (``cuts``: explicit chunk indices instead)."""
-        cuts = sorted(set(cuts)) if cuts else sorted({0, max(0, nch - 3), max(0, nch - 1), nch})
+        """[(k0, k1), ...]: the groups of wavefront chunks the pipelined decoder / skip convs are issued in -- pairs of chunks, then
+        the last two chunks singly (``cuts``: explicit chunk indices instead).  Measured on B200 at 8 chunks (r2, after the spectral /
+        loss kernels behind the decoder had become cheap): cuts 0,5,7,8 -> 1.32 ms per step, 0,4,6,7,8 -> 1.29, 0,3,5,7,8 and
+        0,2,4,6,7,8 -> 1.27, single chunks -> 1.31."""
+        cuts = sorted(set(cuts)) if cuts else sorted({0, nch} | {c for c in (nch - 6, nch - 4, nch - 2, nch - 1) if c > 0})
         if cuts[0] != 0 or cuts[-1] != nch or any(c < 0 or c > nch for c in cuts):
             raise RuntimeError(f"chunk_groups: cuts {cuts} do not partition [0, {nch}]")
         return list(zip(cuts[:-1], cuts[1:]))
@@ -444,7 +446,8 @@ class unet_2(nn.Module):
 
             @staticmethod
             def skip_groups(nch):
-                return unet.chunk_groups(nch, unet.SKIP_CUTS)
+                # the two skip convs that are still separate launches (3 and 4) need no fine groups: few, large launches
+                return unet.chunk_groups(nch, unet.SKIP_CUTS or sorted({0, max(0, nch - 3), max(0, nch - 1), nch}))
 
             @staticmethod
             def caps(j, ngroups):

@@ -189,8 +189,11 @@ class GGRU(nn.Module):
             # layer-1 input projections, one launch per chunk, all queued up front on their own stream: chunk 0 gates the
             # start of the wavefront, the rest stay ahead of layer 1
             with torch.cuda.stream(sD):
+                x_ready = plan.get("x_ready") if plan is not None else None
                 for k in range(nch):
                     t0, t1 = bounds[k], bounds[k + 1]
+                    if x_ready is not None and k == x_ready[0]:
+                        sD.wait_event(x_ready[1])              # the encoder frames of the chunks from here on come from its second range
                     ops.gru_ih_gemm_into(x[t0:t1].view(-1, D), w_ih1, b_ih1, b_hh1, xp1[t0:t1], tables=(tw1, tb1))
                     if flagged:
                         ops.flag_set(f_ih1[k:k + 1])
@@ -383,6 +386,19 @@ class unet_2(nn.Module):
     DECODE_CUTS = [int(v) for v in os.environ.get("CRUSE_DECODE_CUTS", "").split(",") if v]
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
     SIDE_CAP = int(os.environ.get("CRUSE_SIDE_CAP", "0"))     # CTAs of the persistent side kernels (0 = the SMs the recurrences leave free)
+    # wavefront chunks of the encoder that run in front of the recurrences (0 = all of it, the default).  Measured on B200 (r2, 8 chunks,
+    # 1.266 ms with the whole encoder in front): 4 -> 1.273, 3 -> 1.315 (layer 1 stalls 87 us at chunk 3: the second encoder range
+    # takes ~340 us beside the recurrences), 2 -> 1.45, 1 -> 1.47 ms.  Kept as a knob; the two-range schedule is bit-identical.
+    HEAD_CHUNKS = int(os.environ.get("CRUSE_HEAD_CHUNKS", "0"))
+    HEAD_CAP = int(os.environ.get("CRUSE_HEAD_CAP", "84"))        # CTAs of the encoder launches that run beside layer 1
+    _enc_streams = {}
+
+    @classmethod
+    def _enc_stream(cls, device):
+        key = (device.type, device.index)
+        if key not in cls._enc_streams:
+            cls._enc_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+        return cls._enc_streams[key]
 
     @staticmethod
     def chunk_groups(nch, cuts=None):
@@ -413,23 +429,49 @@ class unet_2(nn.Module):
         unet = self
         # ---- encoder, whole utterances (:149-152 repaired); the last stage writes the GRU input time-major
         skip_out = [new(B, T, self.ch[k], self.freqs[k]) for k in range(1, n + 1)]
-        enc, h = [], mag.view(B, T, 1, F)
         # skip conv k (:153-155) reads the same tensor e_k as encoder stage k+1 (:150-152): where a fused tensor-core instantiation
         # exists (Cin 8 / 16 of the 256-bin pyramid) it rides along with that stage -- e_k is read once and the skip conv costs no
         # launch of its own; the remaining skip convs run beside the recurrences (Around.skips)
-        fused = set()
-        for k in range(1, n + 1):
-            conv = getattr(self, f"conv{k}")
-            scale, shift = folds[f"bn{k}"]
-            if k == n:
-                h = ops.conv_fwd_tm(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2, B, T, False, True)
-            elif ops.FUSE_SKIPS and k >= 2 and self.ch[k - 1] in (8, 16) and self.freqs[k - 1] == 2 * self.freqs[k] and self.freqs[k] in (64, 32):
-                h, _ = ops.conv_skip_fwd(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind,
-                                         getattr(self, f"skip_connect_{k - 1}").weight, out_skip=skip_out[k - 2])
-                fused.add(k - 1)
-            else:
-                h = ops.conv_fwd(h, conv.weight, conv.bias, scale, shift, self._alpha(f"act{k}"), self.act_kind, 2, 2)
-            enc.append(h)
+        fused = {k - 1 for k in range(2, n) if ops.FUSE_SKIPS and self.ch[k - 1] in (8, 16) and self.freqs[k - 1] == 2 * self.freqs[k]
+                 and self.freqs[k] in (64, 32)}
+        enc = [new(B, T, self.ch[k], self.freqs[k]) for k in range(1, n)] + [new(T, B, self.ch[n], self.freqs[n])]   # last stage: time-major
+
+        def encode(t0, t1):
+            """encoder stages 1..n for the output frames [t0, t1) (the net is causal: a stage's range needs the same range and one
+            frame before it of the stage below, which the previous range has produced)"""
+            h = mag.view(B, T, 1, F)
+            for k in range(1, n + 1):
+                conv = getattr(self, f"conv{k}")
+                scale, shift = folds[f"bn{k}"]
+                alpha = self._alpha(f"act{k}")
+                if (k - 1) in fused:
+                    ops.conv_skip_fwd(h, conv.weight, conv.bias, scale, shift, alpha, self.act_kind,
+                                      getattr(self, f"skip_connect_{k - 1}").weight, out=enc[k - 1], out_skip=skip_out[k - 2], t0=t0, t1=t1)
+                else:
+                    ops.conv_fwd_range(h, conv.weight, conv.bias, scale, shift, alpha, self.act_kind, 2, 2, B, T, enc[k - 1], t0, t1,
+                                       out_tm=(k == n))
+                h = enc[k - 1]
+
+        # The head of the step: only the first HEAD_CHUNKS wavefront chunks of the encoder run in front of the recurrences; the rest
+        # of the encoder (one more set of launches over the remaining frames, grids capped so that the hand-over GEMMs find SMs)
+        # runs beside layer 1 on its own stream and gates the layer-1 input projections of its chunks (plan["x_ready"]).
+        head = min(self.HEAD_CHUNKS, plan["nch"]) if self.HEAD_CHUNKS > 0 else plan["nch"]
+        t_head = plan["bounds"][head]
+        encode(0, t_head)
+        if t_head < T:
+            s_enc = self._enc_stream(dev)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            s_enc.wait_event(ev)
+            ops.set_conv_max_ctas(self.HEAD_CAP)
+            try:
+                with torch.cuda.stream(s_enc):
+                    encode(t_head, T)
+                    rest_ready = torch.cuda.Event()
+                    rest_ready.record(s_enc)
+            finally:
+                ops.set_conv_max_ctas(0)
+            plan["x_ready"] = (head, rest_ready)
         dec = [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
         mask_buf = new(B, T, 1, F)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -501,6 +543,8 @@ class unet_2(nn.Module):
         ev = torch.cuda.Event()
         ev.record(s_skip)
         main.wait_event(ev)
+        if "x_ready" in plan:
+            main.wait_event(plan["x_ready"][1])
         if self.gru._wavefront_err is not None:
             ops.poison_on_error(self.gru._wavefront_err, [mask_buf])      # a timed-out flag spin must not return numbers
         return mask_buf.view(B, T, F)

@@ -270,7 +270,7 @@ def conv_fwd_tm(x, w, bias, scale, shift, alpha, act, kt, fstride, B, T, in_tm, 
 FUSE_SKIPS = os.environ.get("CRUSE_FUSE_SKIPS", "1") != "0"
 
 
-def conv_skip_fwd(x, w, bias, scale, shift, alpha, act, w_skip, out_skip=None, out_tm=False, t0=0, t1=0):
+def conv_skip_fwd(x, w, bias, scale, shift, alpha, act, w_skip, out=None, out_skip=None, out_tm=False, t0=0, t1=0):
     """eval-mode encoder stage (2,3)/stride (1,2) + folded BN + act WITH the (1,3) skip conv of its input fused in:
     x [B,T,Cin,Fin] -> (out [B,T,Cout,Fin/2] ([T,B,..] with out_tm), out_skip [B,T,Cin,Fin]); one pass over x."""
     _req(x, "x", 4)
@@ -281,9 +281,12 @@ def conv_skip_fwd(x, w, bias, scale, shift, alpha, act, w_skip, out_skip=None, o
     if tuple(w.shape) != (Cout, Cin, 2, 3) or tuple(w_skip.shape) != (Cin, Cin, 1, 3):
         raise RuntimeError(f"conv_skip_fwd: weight shapes {tuple(w.shape)} / {tuple(w_skip.shape)} do not match x {tuple(x.shape)}")
     Fout = (Fin + 2 - 3) // 2 + 1
-    out = torch.empty((T, B, Cout, Fout) if out_tm else (B, T, Cout, Fout), device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((T, B, Cout, Fout) if out_tm else (B, T, Cout, Fout), device=x.device, dtype=torch.float32)
     if out_skip is None:
         out_skip = torch.empty(B, T, Cin, Fin, device=x.device, dtype=torch.float32)
+    if out.numel() != B * T * Cout * Fout or out_skip.numel() != B * T * Cin * Fin:
+        raise RuntimeError(f"conv_skip_fwd: out / out_skip sizes {out.numel()} / {out_skip.numel()} do not match x {tuple(x.shape)}")
     _call("cruse_conv_skip_fwd", _p(x), _p(w), _p(bias), _p(scale), _p(shift), _p(alpha), ACT[act], _p(w_skip), _p(out), _p(out_skip),
           B, T, Cin, Fin, Cout, Fout, 1 if out_tm else 0, t0, t1, _stream(),
           meta=(f"conv2x3 {Cin}->{Cout} F{Fin}->{Fout} + skip1x3 {Cin}->{Cin}", _nb(x, out, out_skip, w, w_skip),

@@ -76,6 +76,9 @@ SIGNATURES = {
     "cruse_sisnr_ws_bytes": (C.c_size_t, [c_int]),
     "cruse_sisnr_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_f, c_fp]),
     "cruse_sisnr_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
+    "cruse_si_snr_zm_ws_bytes": (C.c_size_t, [c_int]),
+    "cruse_si_snr_zm_fwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_f, c_fp]),
+    "cruse_si_snr_zm_bwd": (c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_fp]),
     "cruse_wo_male_masked_fwd": (c_int, [c_fp, CplxLayout, c_fp, c_fp, CplxLayout, c_fp, c_fp, c_int, c_int, c_int, c_fp]),
     "cruse_wo_male_ws_bytes": (C.c_size_t, []),
     # ---- a9 backward

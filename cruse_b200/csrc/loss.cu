@@ -407,6 +407,121 @@ extern "C" int cruse_sisnr_bwd(const float* est, const float* ref, const void* w
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Zero-mean SI-SNR loss of the trainer's loss factory (train_base/loss.py:7-25, `si_snr_loss()`; tools/train_stand.py:73-75 builds
+// the loss through that factory):  x_zm = x - mean(x), s_zm = s - mean(s), t = <x_zm,s_zm> s_zm / (|s_zm|^2 + eps),
+//   loss = -mean_b 20 log10(eps + |t| / (|x_zm - t| + eps)).
+// Everything follows from five sums per utterance (sum x, sum s, sum xs, sum xx, sum ss): one pass of per-(utterance, chunk)
+// partials, one block that finishes each utterance in double precision and leaves the three coefficients of
+// d loss / d x[b,i] = P_b x + Q_b s + R_b, and an elementwise backward.  Fixed summation order: deterministic.
+// ---------------------------------------------------------------------------------------------
+namespace cruse {
+__global__ void __launch_bounds__(256)
+zm_sisnr_partial_kernel(const float* __restrict__ est, const float* __restrict__ ref, float* __restrict__ out, int L) {
+    __shared__ float sh[5][8];
+    const int b = blockIdx.y, j = blockIdx.x;
+    const int len = (L + SISNR_CHUNKS - 1) / SISNR_CHUNKS;
+    const int lo = j * len, hi = (lo + len < L) ? lo + len : L;
+    const float* e = est + (size_t)b * L;
+    const float* r = ref + (size_t)b * L;
+    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float x = __ldg(e + i), sv = __ldg(r + i);
+        v[0] += x; v[1] += sv; v[2] = fmaf(x, sv, v[2]); v[3] = fmaf(x, x, v[3]); v[4] = fmaf(sv, sv, v[4]);
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        v[q] = warp_sum(v[q]);
+        if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += sh[threadIdx.x][w];
+        out[((size_t)b * SISNR_CHUNKS + j) * 5 + threadIdx.x] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+zm_sisnr_finish_kernel(const float* __restrict__ sums, float* __restrict__ coef, float* __restrict__ value, int B, int L, float eps_f) {
+    __shared__ double sh[256];
+    const double eps = (double)eps_f, K = 20.0 / log(10.0), n = (double)L;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        double S[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int q = 0; q < SISNR_CHUNKS; ++q)
+            for (int k = 0; k < 5; ++k) S[k] += (double)sums[((size_t)b * SISNR_CHUNKS + q) * 5 + k];
+        const double mx = S[0] / n, ms = S[1] / n;
+        const double c = S[2] - S[0] * S[1] / n, p = S[3] - S[0] * S[0] / n, q_ = S[4] - S[1] * S[1] / n;
+        const double alpha = c / (q_ + eps), sq = sqrt(q_ > 0.0 ? q_ : 0.0);
+        const double A = fabs(alpha) * sq;
+        double r2 = p - 2.0 * alpha * c + alpha * alpha * q_;
+        if (r2 < 0.0) r2 = 0.0;
+        const double R = sqrt(r2), ratio = A / (R + eps);
+        acc += -K * log(eps + ratio);
+        // gradient through c = <x_zm, s_zm> and p = |x_zm|^2  (q does not depend on x)
+        const double sgn = alpha > 0.0 ? 1.0 : (alpha < 0.0 ? -1.0 : 0.0);
+        const double dA_dc = sgn * sq / (q_ + eps);
+        const double dr2_dc = -2.0 * alpha - 2.0 * c / (q_ + eps) + 2.0 * alpha * q_ / (q_ + eps);
+        const double inv2R = R > 0.0 ? 0.5 / R : 0.0;
+        const double dratio_dc = dA_dc / (R + eps) - A / ((R + eps) * (R + eps)) * dr2_dc * inv2R;
+        const double dratio_dp = -A / ((R + eps) * (R + eps)) * inv2R;
+        const double dv = -K / (eps + ratio) / (double)B;                     // d(mean loss) / d ratio_b
+        const double gc = dv * dratio_dc, gp = dv * dratio_dp;
+        coef[3 * b] = (float)(2.0 * gp);                                      // P: d c / d x_i = s_i - ms,  d p / d x_i = 2 (x_i - mx)
+        coef[3 * b + 1] = (float)gc;                                          // Q
+        coef[3 * b + 2] = (float)(-gc * ms - 2.0 * gp * mx);                  // R
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)blockDim.x; ++i) s += sh[i];
+        value[0] = (float)(s / B);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+zm_sisnr_bwd_kernel(const float* __restrict__ est, const float* __restrict__ ref, const float* __restrict__ coef,
+                    const float* __restrict__ gscale, float* __restrict__ dest, long long total, int L) {
+    const float g = gscale ? __ldg(gscale) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / L;
+        dest[i] = g * (fmaf(__ldg(coef + 3 * b), __ldg(est + i), __ldg(coef + 3 * b + 1) * __ldg(ref + i)) + __ldg(coef + 3 * b + 2));
+    }
+}
+}  // namespace cruse
+
+// workspace: [B][CHUNKS][5] partial sums, [B][3] gradient coefficients (kept for cruse_si_snr_zm_bwd)
+extern "C" size_t cruse_si_snr_zm_ws_bytes(int B) { return sizeof(float) * (size_t)(B > 0 ? B : 0) * (5 * cruse::SISNR_CHUNKS + 3); }
+
+extern "C" int cruse_si_snr_zm_fwd(const float* est, const float* ref, float* value, void* ws, int B, int L, float eps, void* stream) {
+    CRUSE_CHECK_ARG(est && ref && value && ws, "si_snr_zm_fwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && L > 0, "si_snr_zm_fwd: bad sizes B=%d L=%d", B, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* sums = static_cast<float*>(ws);
+    float* coef = sums + (size_t)B * cruse::SISNR_CHUNKS * 5;
+    cruse::zm_sisnr_partial_kernel<<<dim3(cruse::SISNR_CHUNKS, B), 256, 0, st>>>(est, ref, sums, L);
+    CRUSE_LAUNCH_OK();
+    cruse::zm_sisnr_finish_kernel<<<1, 256, 0, st>>>(sums, coef, value, B, L, eps);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_si_snr_zm_bwd(const float* est, const float* ref, const void* ws, const float* gscale, float* dest, int B, int L,
+                                   void* stream) {
+    CRUSE_CHECK_ARG(est && ref && ws && dest, "si_snr_zm_bwd: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && L > 0, "si_snr_zm_bwd: bad sizes B=%d L=%d", B, L);
+    const float* coef = static_cast<const float*>(ws) + (size_t)B * cruse::SISNR_CHUNKS * 5;
+    const long long total = (long long)B * L;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)cruse::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cruse::zm_sisnr_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(est, ref, coef, gscale, dest, total, L);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
                                      const float* unproc, cruse_cplx_layout lunp, float* dest, float* loss, void* ws,
                                      int B, int T, int F, void* stream) {

@@ -130,10 +130,40 @@ def sisnr(s1, s2, eps=1e-8):
     return _SiSnr.apply(s1.reshape(-1, L).float(), s2.reshape(-1, L).float(), eps)
 
 
+class _SiSnrZm(torch.autograd.Function):
+    """zero-mean SI-SNR loss (train_base/loss.py:7-25), differentiable w.r.t. the estimate."""
+
+    @staticmethod
+    def forward(ctx, x, s, eps):
+        x, s = x.contiguous(), s.contiguous()
+        value, ws = ops.si_snr_zm_fwd(x, s, eps)
+        ctx.save_for_backward(x, s, ws)
+        return value
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s, ws = ctx.saved_tensors
+        return ops.si_snr_zm_bwd(x, s, ws, g.contiguous().float()), None, None
+
+
+def si_snr_loss():
+    """train_base/loss.py:7-25: the factory tools/train_stand.py:73-75 resolves by name (``getattr(train_base.loss, name)(**args)``);
+    returns ``si_snr(x, s, eps=1e-8)`` on waveforms [..., L] -> 0-dim loss (negative mean SI-SNR of the zero-mean signals, in dB)."""
+    def si_snr(x, s, eps=1e-8):
+        if x.shape != s.shape:
+            raise RuntimeError(f"Dimension mismatch when calculate si_snr, {x.shape} vs {s.shape}")        # :13-16
+        if not x.is_cuda:
+            raise RuntimeError("si_snr: cruse_b200 runs on sm_100a only (no CPU fallback)")
+        L = x.shape[-1]
+        return _SiSnrZm.apply(x.reshape(-1, L).float(), s.reshape(-1, L).float(), eps)
+    return si_snr
+
+
 def wo_male_loss():
     """factory in the style of train_base/loss.py:7-25: returns loss(est, ref, noisy)."""
     def loss(est, ref, noisy):
         return wo_male(ref, est, noisy)
+    loss.cruse_kind = "wo_male"          # cruse_b200.trainer.Trainer runs the captured STFT + forward + wo_male + backward step for it
     return loss
 
 

@@ -199,6 +199,28 @@ def sisnr_bwd(est, ref, ws, gscale=None):
     return dest
 
 
+def si_snr_zm_fwd(est, ref, eps=1e-8):
+    """-> (loss 0-dim, ws): the zero-mean SI-SNR loss of train_base/loss.py:7-25 on wav [B,L]; ws feeds si_snr_zm_bwd."""
+    _req(est, "est", 2)
+    _req(ref, "ref", 2)
+    if est.shape != ref.shape:
+        raise RuntimeError(f"Dimension mismatch when calculate si_snr, {tuple(est.shape)} vs {tuple(ref.shape)}")
+    B, L = est.shape
+    value = torch.empty((), device=est.device, dtype=torch.float32)
+    ws = _ws(lib().cruse_si_snr_zm_ws_bytes(B), est.device)
+    _call("cruse_si_snr_zm_fwd", _p(est), _p(ref), _p(value), _p(ws), B, L, float(eps), _stream(), meta=("si_snr_zm", _nb(est, ref), 8 * B * L))
+    return value, ws
+
+
+def si_snr_zm_bwd(est, ref, ws, gscale=None):
+    """gscale * d loss / d est (gscale: 0-dim device tensor or None)."""
+    B, L = est.shape
+    dest = torch.empty_like(est)
+    _call("cruse_si_snr_zm_bwd", _p(est), _p(ref), _p(ws), _p(gscale), _p(dest), B, L, _stream(),
+          meta=("si_snr_zm_bwd", _nb(est, ref, dest), 3 * B * L))
+    return dest
+
+
 def mask_bwd(dest, spec, mask_bins, gscale=None, mask=None):
     """dmask[b,t,f] = gscale * Re(conj(X) * dEst), f < mask_bins; with ``mask`` given the result is the gradient
     before the sigmoid (times mask*(1-mask))."""

@@ -270,6 +270,14 @@ size_t cruse_sisnr_ws_bytes(int B);
 int cruse_sisnr_fwd(const float* est, const float* ref, float* value, void* ws, int B, int L, float eps, void* stream);
 int cruse_sisnr_bwd(const float* est, const float* ref, const void* ws, const float* gscale, float* dest, int B, int L,
                     void* stream);
+/* The zero-mean SI-SNR loss of the trainer's loss factory (train_base/loss.py:7-25 `si_snr_loss()`, selected by name in
+ * tools/train_stand.py:73-75):  -mean_b 20 log10(eps + |t| / (|x_zm - t| + eps)),  t = <x_zm,s_zm> s_zm / (|s_zm|^2 + eps).
+ * est = x, ref = s, both [B, L]; value: device scalar; ws: cruse_si_snr_zm_ws_bytes(B) bytes, kept for the backward call.
+ * cruse_si_snr_zm_bwd: dest[b,i] = gscale * d loss / d est[b,i] (gscale: device scalar or NULL = 1). */
+size_t cruse_si_snr_zm_ws_bytes(int B);
+int cruse_si_snr_zm_fwd(const float* est, const float* ref, float* value, void* ws, int B, int L, float eps, void* stream);
+int cruse_si_snr_zm_bwd(const float* est, const float* ref, const void* ws, const float* gscale, float* dest, int B, int L,
+                        void* stream);
 /* The same loss range by range (inference schedule: the loss follows the decoder instead of waiting for the whole mask):
  * _partial_range writes nparts partial sums of the frames [t_begin, t_end) of every utterance into ws[p_off, p_off+nparts),
  * cruse_wo_male_finish adds up the nparts partials of all ranges and divides by B*T*F (loss.py:147).  Same arithmetic per

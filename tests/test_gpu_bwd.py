@@ -3,6 +3,8 @@ uses (model/cruse_net.py:138-146: Conv2d / ConvTranspose2d / BatchNorm2d / GRU /
 max|d| / max|ref| per gradient tensor."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn as nn
@@ -606,3 +608,84 @@ def test_spectral_loss_modes_match_oracle(cuda, mode, fn, B, T, F):
     assert rel_err(e.grad, est.grad) <= 2e-4
     with pytest.raises(RuntimeError):
         getattr(L_, fn)(ref.to(cuda), e[:, :, :, :-1])
+
+
+def test_si_snr_loss_factory_value_and_gradient(cuda, golden_dir):
+    """train_base/loss.py:7-25 `si_snr_loss()` (the factory tools/train_stand.py resolves by name): value against the output of the
+    reference's own function (tests/golden/ref_misc.npz) and against the oracle, gradient against autograd of the oracle."""
+    import numpy as np
+    from cruse_b200.loss import si_snr_loss
+    from oracle import cruse_oracle as o
+    g = np.load(os.path.join(golden_dir, "ref_misc.npz"))
+    s1, s2 = torch.from_numpy(g["s1"]), torch.from_numpy(g["s2"])
+    got = si_snr_loss()(s1.to(cuda), s2.to(cuda))
+    assert abs(float(got) - float(g["si_snr"])) <= 1e-5 * abs(float(g["si_snr"]))
+    torch.manual_seed(31)
+    x = (0.3 * torch.randn(5, 6400) + 0.05).requires_grad_(True)
+    s = 0.3 * torch.randn(5, 6400) - 0.02
+    want = o.si_snr_loss()(x, s)
+    want.backward()
+    xc = x.detach().to(cuda).requires_grad_(True)
+    got = si_snr_loss()(xc, s.to(cuda))
+    (2.0 * got).backward()
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    assert rel_err(xc.grad, 2.0 * x.grad) <= 1e-4
+    with pytest.raises(RuntimeError):
+        si_snr_loss()(xc, s.to(cuda)[:, :-1])
+
+
+def _trainer_config(tmp_path, epochs=2):
+    return {"meta": {"seed": 0, "use_amp": False, "save_dir": str(tmp_path), "experiment_name": "exp"},
+            "acoustics": {"sr": 16000, "n_fft": 512, "hop_length": 320, "win_length": 512},
+            "trainer": {"path": "cruse_b200.trainer.Trainer",
+                        "train": {"epochs": epochs, "save_checkpoint_interval": 1, "clip_grad_norm_value": 10.0, "alpha": 0},
+                        "validation": {"validation_interval": 1, "save_max_metric_score": True},
+                        "visualization": {}}}
+
+
+@pytest.mark.parametrize("loss_name", ["wo_male_loss", "si_snr_loss"])
+def test_trainer_epochs_checkpoints_and_inferencer_shell(cuda, tmp_path, loss_name, capsys):
+    """the concrete trainer the reference's launcher would instantiate (tools/train_stand.py:76-90): two epochs on synthetic clips with
+    the path's own loss (captured step) or the time-domain factory loss (eager autograd), validation, the reference's checkpoint
+    files, resume; then the inferencer shell (base_inferencer.py:120-196) on the best checkpoint: enhanced waveform = the oracle's
+    enhance() of the trained weights (tf32 gate), int16 scaling and the real-time-factor print."""
+    from torch.utils.data import DataLoader
+    from cruse_b200 import loss as L_, trainer
+    from cruse_b200.cruse_net import unet_2
+    from cruse_b200.data import SyntheticDataset
+    from cruse_b200.inferencer import Inferencer
+    from oracle import cruse_oracle as o
+    torch.manual_seed(3)
+    model = unet_2(in_feat=256)
+    cfg = _trainer_config(tmp_path)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    tr_dl = DataLoader(SyntheticDataset(8, 6400), batch_size=4, shuffle=False)
+    va_dl = DataLoader(SyntheticDataset(2, 6400, seed=5, with_name=True), batch_size=1)
+    t = trainer.Trainer(dist=None, rank=0, config=cfg, resume=False, only_validation=False, model=model,
+                        loss_function=getattr(L_, loss_name)(), optimizer=opt, train_dataloader=tr_dl, validation_dataloader=va_dl)
+    t.train()
+    assert [h[0] for h in t.history] == [1, 2] and all(np.isfinite(h[1]) and h[2] is not None for h in t.history)
+    ck = tmp_path / "exp" / "checkpoints"
+    assert (ck / "latest_model.tar").exists() and (ck / "best_model.tar").exists() and (ck / "model_0002.pth").exists()
+    # resume continues at epoch 3 (base_trainer.py:149-176)
+    cfg3 = _trainer_config(tmp_path, epochs=3)
+    model2 = unet_2(in_feat=256)
+    t2 = trainer.Trainer(dist=None, rank=0, config=cfg3, resume=True, only_validation=False, model=model2,
+                         loss_function=getattr(L_, loss_name)(), optimizer=torch.optim.Adam(model2.parameters(), lr=1e-3),
+                         train_dataloader=tr_dl, validation_dataloader=va_dl)
+    assert t2.start_epoch == 3
+    # inferencer shell on the best checkpoint
+    model3 = unet_2(in_feat=256)
+    model3, epoch = Inferencer._load_model(model3, ck / "best_model.tar", cuda)
+    inf = Inferencer(model3, cfg["acoustics"], device=cuda, enhanced_dir=tmp_path / "enhanced")
+    out = inf(va_dl)
+    assert sorted(out) == ["synthetic_00000", "synthetic_00001"] and all(v.dtype == np.int16 for v in out.values())
+    assert "rtf:" in capsys.readouterr().out and len(inf.rtf) == 2 and (tmp_path / "enhanced" / "synthetic_00000.wav").exists()
+    ref = o.unet_2(in_feat=256)
+    ref.load_state_dict({k: v.cpu() for k, v in model3.state_dict().items()})
+    ref.eval()
+    noisy = va_dl.dataset[0][0][None]
+    with torch.no_grad():
+        want = o.enhance(ref, noisy, 512, 320)[0][0].numpy()
+    got = inf.multi_channel_mag_to_mag(noisy[:, None].to(cuda))
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-3 * np.abs(want).max()

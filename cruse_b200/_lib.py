@@ -104,6 +104,10 @@ SIGNATURES = {
     "cruse_gemm_tn_fp32": (c_int, [c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_fp]),
     "cruse_gru_step_ws_bytes": (C.c_size_t, [c_int] * 3),
     "cruse_gru_step": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_fp]),
+    "cruse_feature_norm": (c_int, [c_fp, c_fp, c_int, c_int, c_int, c_int, c_fp]),
+    "cruse_rir_conv": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_ll, c_fp]),
+    "cruse_snr_mix_ws_bytes": (C.c_size_t, [c_int]),
+    "cruse_snr_mix": (c_int, [c_fp] * 7 + [c_int, c_int, c_f, c_fp]),
     "cruse_transpose_gcm": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_int, c_ll, c_fp]),
 }
 

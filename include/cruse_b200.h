@@ -383,6 +383,23 @@ int cruse_gemm_tn_fp32(const float* const* A, const float* const* Bm, const floa
 int cruse_transpose_gcm(const float* in, const float* h0, float* out, long long M, int G, int Cn,
                         long long ld, long long gs, long long cs, int shift_T, int Bn, long long ldo, void* stream);
 
+/* ---- f4: the step in front of the path, on the device (so that eight GPUs are not fed by a CPU dataloader).
+ * cruse_feature_norm: the input feature norms of train_base/model/base_model.py:202-300 on a frame-major magnitude spectrogram
+ *   x, y [B,T,F] (the reference's [B,1,F,T]): mode 0 offline_laplace (x / (mean + 1e-5)), 1 cumulative_laplace (x / (running mean over
+ *   all bins of frames 0..t + eps)), 2 offline_gaussian ((x - mean) / (std + 1e-5), unbiased std), 3 cumulative_layer (running mean /
+ *   variance, formula of :292 kept literally); eps = float32 epsilon (train_base/constant.py:8).
+ * cruse_rir_conv: y[b, n] = sum_{k<R} rir[b*rir_stride + k] x[b, n-k], n < L = scipy.signal.fftconvolve(x, rir)[:L]
+ *   (dataset/dataset.py:244-247); rir_stride 0 = one impulse response for the whole batch.  y must not alias x.
+ * cruse_snr_mix: dataset/dataset.py:236-264 per utterance: clean / (max|clean| + eps), noise / (max|noise| + eps) scaled to
+ *   snr_db[b], noisy = clean + noise; level_db (device array or NULL) = the output level in dB FS the reference draws at random
+ *   (:262-264, where the reference file ends): noisy and clean are then scaled by 10^(dB/20) / (rms(noisy) + eps).
+ *   clean_out may be NULL; ws: cruse_snr_mix_ws_bytes(B). */
+int cruse_feature_norm(const float* x, float* y, int B, int T, int F, int mode, void* stream);
+int cruse_rir_conv(const float* x, const float* rir, float* y, int B, int L, int R, long long rir_stride, void* stream);
+size_t cruse_snr_mix_ws_bytes(int B);
+int cruse_snr_mix(const float* clean, const float* noise, const float* snr_db, const float* level_db, float* noisy_out,
+                  float* clean_out, void* ws, int B, int L, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

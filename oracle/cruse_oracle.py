@@ -366,6 +366,70 @@ class loss_func:
 
 
 # --------------------------------------------------------------------------
+# The step in front of the path: input feature norms and on-the-fly mixing
+# --------------------------------------------------------------------------
+EPSILON = float(torch.finfo(torch.float32).eps)            # train_base/constant.py:8
+
+
+def offline_laplace_norm(x):
+    """train_base/model/base_model.py:202-215; x [B,C,F,T]."""
+    return x / (torch.mean(x, dim=(1, 2, 3), keepdim=True) + 1e-5)
+
+
+def offline_gaussian_norm(x):
+    """base_model.py:247-261."""
+    mu = torch.mean(x, dim=(1, 2, 3), keepdim=True)
+    return (x - mu) / (torch.std(x, dim=(1, 2, 3), keepdim=True) + 1e-5)
+
+
+def cumulative_laplace_norm(x):
+    """base_model.py:217-245: x [B,C,F,T] divided by the running mean over all bins of the frames 0..t."""
+    B, C, F, T = x.size()
+    v = x.reshape(B * C, F, T)
+    cum = torch.cumsum(torch.sum(v, dim=1), dim=-1)
+    count = torch.arange(F, F * T + 1, F, dtype=x.dtype).reshape(1, T)
+    mean = (cum / count).reshape(B * C, 1, T)
+    return (v / (mean + EPSILON)).reshape(B, C, F, T)
+
+
+def cumulative_layer_norm(x):
+    """base_model.py:263-300 (online zero-mean / unit-variance; the variance formula is kept literally)."""
+    B, C, F, T = x.size()
+    v = x.reshape(B * C, F, T)
+    cs = torch.cumsum(torch.sum(v, dim=1), dim=-1)
+    cp = torch.cumsum(torch.sum(torch.square(v), dim=1), dim=-1)
+    count = torch.arange(F, F * T + 1, F, dtype=x.dtype).reshape(1, T)
+    mean = cs / count
+    var = (cp - 2 * mean * cs) / count + mean.pow(2)
+    std = torch.sqrt(var + EPSILON)
+    return ((v - mean.reshape(B * C, 1, T)) / std.reshape(B * C, 1, T)).reshape(B, C, F, T)
+
+
+def snr_mix(clean_y, noise_y, snr, target_dB_FS=None, rir=None, rir_noise=None, eps=1e-7):
+    """dataset/dataset.py:236-264 on torch tensors [L] (the reference: numpy + scipy.signal.fftconvolve).  The reference file
+    ENDS inside this function (after drawing the output level, :262-264, nothing is returned); kept here: reverberation, peak
+    normalisation, the SNR scalar and the sum (:244-260); ``target_dB_FS`` (the level the reference draws at random) then scales
+    noisy and clean by 10^(dB/20) / (rms(noisy) + eps), the continuation of the recipe the file was taken from."""
+    def fftconvolve(a, b):
+        n = a.numel() + b.numel() - 1
+        return torch.fft.irfft(torch.fft.rfft(a.double(), n) * torch.fft.rfft(b.double(), n), n).to(a.dtype)
+    if rir is not None:
+        clean_y = fftconvolve(clean_y, rir)[: clean_y.numel()]
+    if rir_noise is not None:
+        noise_y = fftconvolve(noise_y, rir_noise)[: noise_y.numel()]
+    clean_y = clean_y / (clean_y.abs().max() + eps)
+    clean_rms = (clean_y ** 2).mean() ** 0.5
+    noise_y = noise_y / (noise_y.abs().max() + eps)
+    noise_rms = (noise_y ** 2).mean() ** 0.5
+    noise_y = noise_y * (clean_rms / (10 ** (snr / 20)) / (noise_rms + eps))
+    noisy_y = clean_y + noise_y
+    if target_dB_FS is not None:
+        sc = 10 ** (target_dB_FS / 20) / ((noisy_y ** 2).mean() ** 0.5 + eps)
+        noisy_y, clean_y = noisy_y * sc, clean_y * sc
+    return noisy_y, clean_y
+
+
+# --------------------------------------------------------------------------
 # The hot path end to end (SURVEY.md section 3.2), used by parity tests and cpu_baseline
 # --------------------------------------------------------------------------
 def spec_to_bctf(c):

@@ -202,6 +202,23 @@ def ref_hot_path_files():
         m = torch.rand(2, 1, r.shape[1], r.shape[2])
         masked = torch.stack([r, i], 1) * m
         wav = S.istft(masked)
+    # ---- train_base/model/base_model.py:202-300 input feature norms (unmodified) and dataset/dataset.py:236-264 snr_mix
+    nm = rx.base_model_norms()
+    torch.manual_seed(53)
+    xin = torch.rand(2, 1, 33, 17) + 0.1
+    out = {"x": xin.numpy()}
+    for k in ("offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"):
+        out[k] = nm[k](xin.clone()).numpy()
+    mix = rx.snr_mix_fn()
+    rng = np.random.RandomState(5)
+    cy, ny = rng.randn(4000).astype(np.float64), rng.randn(4000).astype(np.float64)
+    rir = np.exp(-np.arange(300) / 40.0) * rng.randn(300)
+    np.random.seed(0)
+    res = mix(cy.copy(), ny.copy(), snr=5, target_dB_FS=-25, target_dB_FS_floating_val=10, rir=rir, rir_noise=None)
+    out.update(mix_clean_in=cy, mix_noise_in=ny, mix_rir=rir, mix_clean=res["clean_y"], mix_noise=res["noise_y"], mix_noisy=res["noisy_y"],
+               mix_snr_scalar=np.float64(res["snr_scalar"]))
+    np.savez_compressed(os.path.join(OUT, "refx_frontend.npz"), **out)
+
     np.savez_compressed(os.path.join(OUT, "refx_conv_stft.npz"), y=y.numpy(), spec_r=r.numpy(), spec_i=i.numpy(), mag=mag.numpy(),
                         pha=pha.numpy(), masked=masked.numpy(), masked_wav=wav.numpy(), win=S.win.detach().numpy())
 

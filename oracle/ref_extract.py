@@ -163,3 +163,34 @@ def conv_stft_class(repair_istft=True):
                "same repair, second half of the statement"),
     ] if repair_istft else []
     return extract("train_base/acoustics/conv_stft.py", ["STFT"], nn_compat=True, repairs=repairs)
+
+
+def base_model_norms():
+    """the four static norm methods of train_base/model/base_model.py:202-300, source unmodified, run with EPSILON of
+    train_base/constant.py:8 in scope"""
+    src = read_source("train_base/model/base_model.py")
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "BaseModel")
+    want = {"offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"}
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {f.name for f in fns} == want
+    for f in fns:
+        f.decorator_list = []                       # @staticmethod: they become plain functions of the namespace
+    ns = {"torch": torch, "EPSILON": float(np.finfo(np.float32).eps)}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), f"{REF}/train_base/model/base_model.py", "exec"), ns)
+    return ns
+
+
+def snr_mix_fn():
+    """dataset/dataset.py:236-264 snr_mix (a static method; the file ends inside it, so it returns None): executed with a
+    tracing namespace that keeps the locals it computed (clean_y, noise_y, noisy_y, snr_scalar)."""
+    src = read_source("dataset/dataset.py")
+    lines = src.split("\n")
+    start = next(i for i, l in enumerate(lines) if l.strip().startswith("def snr_mix("))
+    body = lines[start:]
+    ind = len(body[0]) - len(body[0].lstrip())
+    text = "\n".join(l[ind:] for l in body) + "\n    return dict(clean_y=clean_y, noise_y=noise_y, noisy_y=noisy_y, snr_scalar=snr_scalar)\n"
+    import scipy.signal as signal
+    ns = {"np": np, "signal": signal}
+    exec(compile(text, f"{REF}/dataset/dataset.py", "exec"), ns)
+    return ns["snr_mix"]

@@ -218,6 +218,18 @@ def test_conv_stft_matches_reference_conv_stft_py(golden_dir):
     np.testing.assert_allclose(S.istft(torch.stack([r, i], 1)).numpy(), g["y"], atol=1e-5)
 
 
+def test_frontend_norms_and_snr_mix_match_reference(golden_dir):
+    """train_base/model/base_model.py:202-300 (the four input feature norms, source unmodified) and dataset/dataset.py:236-260
+    (snr_mix with a room impulse response, executed from the reference source with its locals captured)."""
+    g = _load(golden_dir, "refx_frontend.npz")
+    x = _t(g["x"])
+    for k in ("offline_laplace_norm", "cumulative_laplace_norm", "offline_gaussian_norm", "cumulative_layer_norm"):
+        np.testing.assert_allclose(getattr(o, k)(x).numpy(), g[k], rtol=1e-5, atol=1e-6)
+    noisy, clean = o.snr_mix(_t(g["mix_clean_in"]), _t(g["mix_noise_in"]), 5, rir=_t(g["mix_rir"]))
+    np.testing.assert_allclose(clean.numpy(), g["mix_clean"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(noisy.numpy(), g["mix_noisy"], rtol=1e-9, atol=1e-12)
+
+
 def test_misc_reference_fragments(golden_dir):
     g = _load(golden_dir, "ref_misc.npz")
     a, b, c, d = (torch.from_numpy(g[k]) for k in "abcd")

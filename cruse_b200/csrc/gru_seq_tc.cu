@@ -33,7 +33,18 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <cstring>
+
+// Operand format of the recurrent product.  1 (default): both operands travel and multiply as IEEE half (tcgen05 kind::f16, fp32
+// accumulation) -- h_t lies in (-1, 1) and W_hh in (-1/sqrt(H), 1/sqrt(H)) at initialisation, where half has the SAME 10-bit
+// mantissa as tf32 (below 2^-14 it is absolutely, not relatively, accurate: error <= 3e-8), so the numerics are those of the tf32
+// path, while every step moves HALF the bytes through the cluster's distributed shared memory (measured: the step is bound by that
+// exchange, ~17 B/clk per SM), issues 16 instead of 32 MMAs (K = 16 per instruction) and W_hh takes 128 instead of 256 TMEM columns.
+// 0: tf32 operands (the round-1 path).
+#ifndef CRUSE_SEQ_F16
+#define CRUSE_SEQ_F16 1
+#endif
 
 namespace cg = cooperative_groups;
 
@@ -46,7 +57,15 @@ constexpr int SQ_WG = 128;                   // threads per slice warpgroup: thr
 constexpr int SQ_THREADS = 2 * SQ_WG + 32;   // two slice warpgroups + the MMA-issuing warp
 constexpr int SQ_TMEM_COLS = 512;            // A: up to 256 columns (K) + 2 x D: 16 columns -> whole TMEM (1 CTA/SM)
 constexpr int SQ_D_COL = 256;                // accumulator column offset (slice s at + 16*s)
-constexpr int SQ_H_KB = SQ_NB * 128;         // bytes of one B k-block tile: 16 rows x 32 tf32
+constexpr int SQ_H_KB = SQ_NB * 128;         // bytes of one B k-block tile: 16 rows x 128 bytes (32 tf32 / 64 half)
+#if CRUSE_SEQ_F16
+constexpr int SQ_KBE = 64;                   // K elements per 128-byte row of the B operand
+constexpr int SQ_EB = 2;                     // bytes per operand element
+#else
+constexpr int SQ_KBE = 32;
+constexpr int SQ_EB = 4;
+#endif
+constexpr int sq_nkb(int nc) { return (nc * SQ_U + SQ_KBE - 1) / SQ_KBE; }   // k-block tiles of one h buffer
 constexpr int SQ_PRE_LD = SQ_NB + 1;         // padded leading dim of the gate-row x utterance pad
 
 #ifdef CRUSE_SEQ_TIMING
@@ -106,8 +125,8 @@ __device__ __forceinline__ float to_tf32(float v) {
 
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B operand whose k-block tiles are `kb_bytes` apart
 __device__ __forceinline__ uint32_t sw128_off(int row, int k, int kb_bytes) {
-    const int kb = k >> 5, kk = k & 31;
-    return (uint32_t)(kb * kb_bytes + (row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ (row & 7))) << 4) + ((kk & 3) << 2));
+    const int kb = k / SQ_KBE, byte = (k % SQ_KBE) * SQ_EB;            // byte position inside the 128-byte row
+    return (uint32_t)(kb * kb_bytes + (row >> 3) * 1024 + (row & 7) * 128 + ((((byte >> 4) ^ (row & 7))) << 4) + (byte & 15));
 }
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {   // this warp's 32 lanes x 16 columns
@@ -128,6 +147,29 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
         "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);       // .x (low 16 bits) = lo
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, half operands (two consecutive k per 32-bit TMEM cell of A), K = 16 per instruction
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
@@ -153,7 +195,8 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                   float* __restrict__ hT, float* __restrict__ gates, int B, int T, int G, int H, int y_fs, int y_gs,
                   long long x_bs, long long x_ts, long long y_bs, long long y_ts, const SeqSync sync) {
     // row (b, t) of xproj is b*x_bs + t*x_ts, of y b*y_bs + t*y_ts ([B,T] frame order: (T,1); time-major [T,B]: (1,B))
-    constexpr int SLICE_BYTES = 2 * NC * SQ_H_KB;        // two h buffers of one slice
+    constexpr int NKB = sq_nkb(NC);                       // k-block tiles (16 rows x 128 B) of one h buffer
+    constexpr int SLICE_BYTES = 2 * NKB * SQ_H_KB;       // two h buffers of one slice
     extern __shared__ uint8_t smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -207,11 +250,24 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                     const int k = (kb0 + 2 * u) * 32 + i * 4;
                     float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (rowvalid && kb0 + 2 * u < NC && k < H) f = __ldg(reinterpret_cast<const float4*>(wrow + k));
+#if CRUSE_SEQ_F16
+                    v[u][i * 4 + 0] = f.x; v[u][i * 4 + 1] = f.y; v[u][i * 4 + 2] = f.z; v[u][i * 4 + 3] = f.w;
+#else
                     v[u][i * 4 + 0] = to_tf32(f.x); v[u][i * 4 + 1] = to_tf32(f.y); v[u][i * 4 + 2] = to_tf32(f.z); v[u][i * 4 + 3] = to_tf32(f.w);
+#endif
                 }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
-                if (kb0 + 2 * u < NC) tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kb0 + 2 * u) * 32), v[u]);
+                if (kb0 + 2 * u < NC) {
+#if CRUSE_SEQ_F16
+                    uint32_t pk[16];                     // two consecutive k per TMEM cell: 32 k -> 16 columns
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pk[i] = pack_half2(v[u][2 * i], v[u][2 * i + 1]);
+                    tmem_st_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kb0 + 2 * u) * 16), pk);
+#else
+                    tmem_st_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((kb0 + 2 * u) * 32), v[u]);
+#endif
+                }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -232,8 +288,13 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         }
 #pragma unroll
         for (int kb = 0; kb < NC; ++kb)
+#if CRUSE_SEQ_F16
+            *reinterpret_cast<uint2*>(dstb + sw128_off(bb, kb * 32 + c4 * 4, SQ_H_KB)) =
+                make_uint2(pack_half2(hv[kb].x, hv[kb].y), pack_half2(hv[kb].z, hv[kb].w));
+#else
             *reinterpret_cast<float4*>(dstb + sw128_off(bb, kb * 32 + c4 * 4, SQ_H_KB)) =
                 make_float4(to_tf32(hv[kb].x), to_tf32(hv[kb].y), to_tf32(hv[kb].z), to_tf32(hv[kb].w));
+#endif
     }
     tc::fence_proxy_async_smem();      // generic-proxy smem writes (h_0) -> visible to the tensor core's async proxy
     tc::tc_fence_before();
@@ -241,8 +302,8 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
     tc::tc_fence_after();
     cluster.sync();                    // every CTA's buffers + barriers exist before any remote store lands
 
-    constexpr uint32_t STEP_BYTES = (uint32_t)NC * SQ_WG * 16;     // all of h_t of one slice: 16 x 32*NC floats
-    constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, 128, SQ_NB);
+    constexpr uint32_t STEP_BYTES = (uint32_t)NC * SQ_WG * 4 * SQ_EB;     // all of h_t of one slice: 16 utterances x 32*NC elements
+    constexpr uint32_t idesc = tc::instr_desc(CRUSE_SEQ_F16 ? 0 /*f16*/ : 2 /*tf32*/, 128, SQ_NB);
     const size_t N3 = (size_t)3 * H;
 
     if (warp == 8) {
@@ -261,14 +322,22 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                 }
                 tc::tc_fence_after();
                 if (s == 0) SEQ_STAMP(1);
-                const uint64_t bdesc0 = tc::smem_desc_sw128(base + (uint32_t)s * SLICE_BYTES + (uint32_t)p * (NC * SQ_H_KB));
+                const uint64_t bdesc0 = tc::smem_desc_sw128(base + (uint32_t)s * SLICE_BYTES + (uint32_t)p * (NKB * SQ_H_KB));
                 if (tc::elect_one()) {
+#if CRUSE_SEQ_F16
+                    // K = 16 half per instruction = 32 bytes along the B row = 8 TMEM cells of A; 2 * NC instructions cover K = 32 * NC
+#pragma unroll
+                    for (int k16 = 0; k16 < 2 * NC; ++k16)
+                        umma_f16_ts(tmem_base + SQ_D_COL + 16 * s, tmem_base + (uint32_t)(k16 * 8),
+                                    bdesc0 + (uint64_t)(((k16 >> 2) * SQ_H_KB + (k16 & 3) * 32) >> 4), idesc, k16 ? 1u : 0u);
+#else
 #pragma unroll
                     for (int kb = 0; kb < NC; ++kb)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
                             umma_tf32_ts(tmem_base + SQ_D_COL + 16 * s, tmem_base + (uint32_t)(kb * 32 + ks * 8),
                                          bdesc0 + (uint64_t)((kb * SQ_H_KB + ks * 32) >> 4), idesc, (kb | ks) ? 1u : 0u);
+#endif
                     tc::umma_commit(&acc_full[s]);
                 }
                 __syncwarp();
@@ -288,7 +357,7 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
         // remote (shared::cluster) addresses of my 16-byte h slot and of the slice's barriers in every CTA of the cluster
         uint32_t rem_h[NC], rem_bar[NC];
         {
-            const uint32_t lh = tc::smem_u32(sH) + (uint32_t)sl * SLICE_BYTES + (uint32_t)rank * SQ_H_KB + sw128_off(b, 4 * jq, SQ_H_KB);
+            const uint32_t lh = tc::smem_u32(sH) + (uint32_t)sl * SLICE_BYTES + sw128_off(b, rank * SQ_U + 4 * jq, SQ_H_KB);   // my units' slot
             const uint32_t lb = tc::smem_u32(&hbar[sl * 2]);
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -385,7 +454,16 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
             if (sl == 0 && wt == 0) SEQ_STAMP(7);
             // scatter my 16 bytes of h_{t+1} (tf32-rounded operand copy) into the other buffer of every CTA
             {
-                const uint32_t poff = (uint32_t)(p ^ 1) * (NC * SQ_H_KB), boff = (uint32_t)(p ^ 1) * 8;
+                const uint32_t poff = (uint32_t)(p ^ 1) * (NKB * SQ_H_KB), boff = (uint32_t)(p ^ 1) * 8;
+#if CRUSE_SEQ_F16
+                const uint32_t w0 = pack_half2(hn[0], hn[1]), w1 = pack_half2(hn[2], hn[3]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(
+                                     rem_h[c] + poff),
+                                 "r"(w0), "r"(w1), "r"(rem_bar[c] + boff)
+                                 : "memory");
+#else
                 const uint32_t w0 = __float_as_uint(to_tf32(hn[0])), w1 = __float_as_uint(to_tf32(hn[1]));
                 const uint32_t w2 = __float_as_uint(to_tf32(hn[2])), w3 = __float_as_uint(to_tf32(hn[3]));
 #pragma unroll
@@ -394,6 +472,7 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                                      rem_h[c] + poff),
                                  "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(rem_bar[c] + boff)
                                  : "memory");
+#endif
             }
             if (sl == 0 && wt == 0) SEQ_STAMP(5);
             if (valid) {
@@ -440,7 +519,7 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
 // tcgen05.alloc until the recurrence CTA exits.  With 136 KB taken no such CTA fits beside it, and the input projections
 // that run beside the wavefront go to the SMs the recurrence does not use.
 constexpr size_t seq_smem_bytes(int NC) {
-    const size_t used = 1024 + 2 * 2 * (size_t)NC * SQ_H_KB + (2 * 96 * SQ_PRE_LD + 4) * 4 + 128;
+    const size_t used = 1024 + 2 * 2 * (size_t)sq_nkb(NC) * SQ_H_KB + (2 * 96 * SQ_PRE_LD + 4) * 4 + 128;
     return used > 136 * 1024 ? used : 136 * 1024;
 }
 

@@ -294,7 +294,9 @@ def test_wavefront_modes_agree_and_no_flag_timeout(cuda):
                 assert int(ours.gru._wavefront_err.item()) == 0
     finally:
         ops.GRU_WAVEFRONT_MODE = old
-    assert torch.equal(out["flags"][3], out["relaunch"][3]) and torch.equal(out["flags"][0], out["relaunch"][0])
+    assert torch.equal(out["flags"][3], out["relaunch"][3])             # masks: bit-identical
+    # the loss is summed range by range behind the pipelined decoder in flag mode, in one launch otherwise: summation order only
+    assert abs(float(out["flags"][0]) - float(out["relaunch"][0])) <= 1e-6 * abs(float(out["relaunch"][0]))
 
 
 def test_wavefront_timeout_is_loud(cuda):

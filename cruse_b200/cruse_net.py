@@ -385,7 +385,10 @@ class unet_2(nn.Module):
     # developer knobs: chunk indices at which the pipelined decoder / skip convs are cut (default: derived from the chunk count)
     DECODE_CUTS = [int(v) for v in os.environ.get("CRUSE_DECODE_CUTS", "").split(",") if v]
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
-    SIDE_CAP = int(os.environ.get("CRUSE_SIDE_CAP", "0"))     # CTAs of the persistent side kernels (0 = the SMs the recurrences leave free)
+    SIDE_CAP = int(os.environ.get("CRUSE_SIDE_CAP", "0"))     # CTAs of the persistent side kernels (0 = the SMs the recurrences leave free, minus SIDE_SPARE)
+    # SMs the persistent side kernels leave free for the hand-over kernels (LayerNorm 1 + layer-2 projections of a chunk), which otherwise wait
+    # for a side kernel to END before they get an SM (measured r2: 0 -> 1.188 ms, 12 -> 1.172 ms per step)
+    SIDE_SPARE = int(os.environ.get("CRUSE_SIDE_SPARE", "12"))
     # wavefront chunks of the encoder that run in front of the recurrences (0 = all of it, the default).  Measured on B200 (r2, 8 chunks,
     # 1.266 ms with the whole encoder in front): 4 -> 1.273, 3 -> 1.315 (layer 1 stalls 87 us at chunk 3: the second encoder range
     # takes ~340 us beside the recurrences), 2 -> 1.45, 1 -> 1.47 ms.  Kept as a knob; the two-range schedule is bit-identical.
@@ -488,8 +491,10 @@ class unet_2(nn.Module):
 
             @staticmethod
             def skip_groups(nch):
-                # the two skip convs that are still separate launches (3 and 4) need no fine groups: few, large launches
-                return unet.chunk_groups(nch, unet.SKIP_CUTS or sorted({0, max(0, nch - 3), max(0, nch - 1), nch}))
+                # the two skip convs that are still separate launches (3 and 4) depend on the encoder only: ONE launch each over all
+                # frames, early (low priority, beside layer 1) -- in groups the last one was served so late that it held up the last
+                # decoder group (measured r2: cuts 0,5,7,8 -> 1.202 ms, 0,6,8 -> 1.191, 0,8 -> 1.188)
+                return unet.chunk_groups(nch, unet.SKIP_CUTS or [0, nch])
 
             @staticmethod
             def caps(j, ngroups):
@@ -498,7 +503,7 @@ class unet_2(nn.Module):
                     return 0
                 if unet.SIDE_CAP:
                     return unet.SIDE_CAP
-                return max(32, sms - (2 if j < ngroups - 2 else 1) * layer_sms)
+                return max(32, sms - (2 if j < ngroups - 2 else 1) * layer_sms - unet.SIDE_SPARE)
 
             @staticmethod
             def skips(j, t0, t1, after):                                                         # :153-156
@@ -506,7 +511,7 @@ class unet_2(nn.Module):
                     after_encoder(after)             # the caller's off-path work starts with the skip convs: once the layer-1
                                                      # projections are through, so that it takes no SMs from what gates layer 1
                 s_skip.wait_event(after)
-                ops.set_conv_max_ctas(unet.SIDE_CAP or max(32, sms - 2 * layer_sms))
+                ops.set_conv_max_ctas(unet.SIDE_CAP or max(32, sms - 2 * layer_sms - unet.SIDE_SPARE))
                 try:
                     with torch.cuda.stream(s_skip):
                         for k in range(n, 0, -1):

@@ -324,6 +324,8 @@ def run_ours(args):
     host_binding = hostio.bind_near_gpu(local, local, local_world) if not args.no_bind else {"why_not": "--no-bind"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "INFO")              # the communicator line ("comm ... nranks N") on stderr: the collective is observable
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world and rank == 0:
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
@@ -530,7 +532,7 @@ def run_ours(args):
                 "us_per_recurrence_step": (round(1e3 * dom["ms"] / (2 * T), 3) if dom_name.startswith("gru_seq") else None),
                 "all_other_kernels": {"achieved": round(hbm_gbs, 1), "frac": round(hbm_gbs / pk["hbm_gbs"], 4), "ms": round(hbm_ms, 4),
                                       "note": "every HBM-bound launch of the step together (STFT, conv/convT, input projections, LayerNorm, mask+iSTFT, loss)"},
-                "note": "dominant = the GRU recurrence: T sequential steps per layer, latency-bound by construction (h exchange over DSMEM -> 32 "
+                "note": "dominant = the GRU recurrence: T sequential steps per layer, latency-bound by construction (h exchange over DSMEM -> 16 "
                         "tcgen05.mma -> tcgen05.ld -> gate math per step), so its HBM fraction is low by design; both layers run side by side "
                         "on 64 of the 148 SMs while the skip convs and input projections use the rest. Per-launch numbers are under 'kernels' "
                         "(timed eagerly, one CUDA-event pair per launch on its own stream; launches on different streams overlap)"}
@@ -542,7 +544,7 @@ def run_ours(args):
         "config": {"workload": desc, "frames_per_step_per_gpu": frames, "l2": "256 MB flush write between timed steps",
                    "launch": ("one CUDA graph replay per step (captured from the ctypes launches on up to 13 streams)" if captured is not None
                               else "eager ctypes launches on torch's current stream"),
-                   "tensor_core_operands": "tf32 (tcgen05, fp32 accumulate in TMEM) in the conv / convT implicit GEMMs and both GRU matmuls; everything else fp32",
+                   "tensor_core_operands": "tf32 (tcgen05, fp32 accumulate in TMEM) in the conv / convT implicit GEMMs and the GRU input projections; IEEE half (kind::f16, same 10-bit mantissa as tf32 for |h| < 1, fp32 accumulate) for W_hh and h in the recurrence; everything else fp32",
                    "gru": "two layers side by side (flag-synchronised time-chunked wavefront; in inference the decoder, mask*X + iSTFT and the loss follow layer 2 in groups of chunks), 2 x 16 utterances software-pipelined per cluster",
                    "collective": ("one flat fp32 gradient all_reduce (NCCL) per step" if (train and world > 1) else "none")},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

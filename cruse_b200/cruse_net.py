@@ -234,8 +234,11 @@ class GGRU(nn.Module):
                             if s0 < k1 and k0 < s1:
                                 sG.wait_event(ev_s)
                         ops.flag_wait(f_l2[k1 - 1:k1], n_wg, f_err)
-                        ops.layernorm_fwd_range(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, around.residual, out, t0, t1)
-                        around.decode(j, out, t0, t1)
+                        if getattr(around, "fused_decoder", False):
+                            around.decode_fused(j, y2, self.ln2, t0, t1)
+                        else:
+                            ops.layernorm_fwd_range(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, around.residual, out, t0, t1)
+                            around.decode(j, out, t0, t1)
             for s_ in (sA, sC, sD):                                       # join every branch (graph capture needs it)
                 ev = torch.cuda.Event()
                 ev.record(s_)
@@ -475,7 +478,10 @@ class unet_2(nn.Module):
             finally:
                 ops.set_conv_max_ctas(0)
             plan["x_ready"] = (head, rest_ready)
-        dec = [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
+        # LayerNorm 2 + all four decoder stages as ONE launch per group (decoder_fused.cu) where the geometry is the 256-bin pyramid
+        fuse_dec = (ops.FUSE_DECODER and n == 4 and tuple(self.ch) == (1, 8, 16, 32, 64) and tuple(self.freqs) == (256, 128, 64, 32, 16)
+                    and self.act_kind in ("relu", "prelu"))
+        dec = [] if fuse_dec else [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
         mask_buf = new(B, T, 1, F)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         layer_sms = 8 * self.gru.groups * ((B + 31) // 32)
@@ -525,6 +531,21 @@ class unet_2(nn.Module):
                 finally:
                     ops.set_conv_max_ctas(0)
                 return ev
+
+            fused_decoder = fuse_dec
+
+            @staticmethod
+            def decode_fused(j, y2, ln2, t0, t1):                                                # :51,160-164 repaired, one launch
+                names = [f"conv{k}_t" for k in range(n, 0, -1)]
+                ops.decoder_fused_range(
+                    y2, ln2.weight, ln2.bias, ln2.eps, [skip_out[k - 1] for k in range(n, 0, -1)],
+                    [getattr(unet, nm).weight for nm in names], [getattr(unet, nm).bias for nm in names],
+                    [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
+                    [unet._alpha(f"act{k}_t") for k in range(n, 1, -1)] if unet.act_kind == "prelu" else None,
+                    unet.act_kind, mask_buf, t0, t1, Around.caps(j, len(Around.groups(plan["nch"]))))
+                if post is not None:
+                    post(mask_buf.view(B, T, F), t0, t1)
+                    unet._post_ranges.append((t0, t1))
 
             @staticmethod
             def decode(j, ln2_out, t0, t1):                                                      # :161-164 repaired

@@ -1,0 +1,259 @@
+// decoder_fused.cu -- LayerNorm 2 (+ skip 4) and the whole 4-stage decoder of the 256-bin pyramid in ONE kernel (eval mode).
+//
+// replaces, per frame range: model/cruse_net.py:51 (ln2) + :160 (+ skip_connect_4) and :161-164 repaired
+// (3 x [ConvTranspose2d(1,3)/s(1,2) + BatchNorm(eval) + act + skip], ConvTranspose2d(8->1) + sigmoid) -- five launches and
+// three intermediate tensors (3 x 65.7 MB at 32 x 501 frames, written and read back) in the staged schedule.
+//
+// The decoder has NO time taps: every frame is an independent chain 1024 -> [32x32] -> [16x64] -> [8x128] -> 256.  One WARP owns one
+// frame from the GRU output to the mask; the activations never leave the SM:
+//   * prologue: LayerNorm over the 1024 features of the frame (the row lives in registers), + skip 4, written as the stage-4 operand
+//     X4[pos][channel] into the warp's shared-memory buffer (tf32-rounded, cvt.rna);
+//   * stages 4..2 as warp-level tensor-core GEMMs (mma.sync m16n8k8 tf32, fp32 accumulate): M = the frame's input bins, K = Cin,
+//     N = Cout; out[co, 2i] = W[:,co,0].x[:,i] + W[:,co,2].x[:,i-1] and out[co, 2i+1] = W[:,co,1].x[:,i] -- the i-1 tap is the same
+//     operand buffer read one row up (row 0 is a zero row), so no im2col and no cross-lane exchange.  Epilogue in registers: folded
+//     BN + bias, ReLU / PReLU, + skip (float2 loads issued BEFORE the k loop), stored as the next stage's operand;
+//   * stage 1 (8 -> 1 channel, sigmoid) on the FMA pipe (N = 1 is no GEMM), mask stored with 256-byte warp transactions.
+// A frame is 16..128 rows -- below one tcgen05 tile -- and the chain is bound by the 20 KB per frame it reads (GRU output + four
+// skip tensors), not by the 0.35 MFLOP it computes, so the warp-private mma.sync pipeline (no barriers between warps, 16 frames in
+// flight per SM) is the right tool here; the tcgen05 kernels stay where M is large (conv_tc.cu, gru_*_tc.cu).
+// Weights of all four stages (35 KB, tf32-rounded, K-contiguous per output channel) are staged once per CTA.
+#include "common.cuh"
+
+namespace cruse {
+namespace {
+
+constexpr int DF_WARPS = 16, DF_THREADS = DF_WARPS * 32;
+constexpr int C4 = 64, F4 = 16, C3 = 32, F3 = 32, C2 = 16, F2 = 64, C1 = 8, F1 = 128, F0 = 256;
+constexpr int LD4 = C4 + 4, LD3 = C3 + 4, LD2 = C2 + 4;     // operand rows: [1 + pos][channel], stride = Cin + 4 floats (conflict-free fragments)
+constexpr int LD1 = F1 + 4;                                  // stage-1 input is channel-major [8][2 + pos]
+constexpr int W4_OFF = 0, W4_SZ = 3 * C3 * LD4;              // [tap][co][ci + 4]
+constexpr int W3_OFF = W4_OFF + W4_SZ, W3_SZ = 3 * C2 * LD3;
+constexpr int W2_OFF = W3_OFF + W3_SZ, W2_SZ = 3 * C1 * LD2;
+constexpr int W1_OFF = W2_OFF + W2_SZ, W1_SZ = 32;           // [ci][tap] (24) + bias
+constexpr int EP_OFF = W1_OFF + W1_SZ, EP_N = C3 + C2 + C1;  // per output channel of stages 4..2: scale, shift (bias folded in), alpha
+constexpr int WTOT = EP_OFF + 3 * EP_N + 8;
+constexpr int BUFA = 1312;                                   // X4 (17 x 68 = 1156) then X2 (65 x 20 = 1300)
+constexpr int BUFB = 1200;                                   // X3 (33 x 36 = 1188) then X1 (8 x 132 = 1056)
+constexpr size_t DF_SMEM = (size_t)(WTOT + DF_WARPS * (BUFA + BUFB)) * sizeof(float);
+static_assert((WTOT % 4) == 0 && (BUFA % 4) == 0 && (BUFB % 4) == 0, "16-byte aligned buffers");
+
+struct DecFusedArgs {
+    const float* y2;                 // [B,T,1024] output of GRU layer 2
+    const float *ln_g, *ln_b;
+    float eps;
+    const float* skip[4];            // skip4 [B,T,64,16] (added to LN2), skip3 [B,T,32,32], skip2 [B,T,16,64], skip1 [B,T,8,128]
+    const float* w[4];               // conv4_t [64,32,1,3], conv3_t [32,16,1,3], conv2_t [16,8,1,3], conv1_t [8,1,1,3]
+    const float* bias[4];
+    const float* scale[3];           // folded eval BatchNorm of stages 4..2
+    const float* shift[3];
+    const float* alpha[3];           // PReLU slopes (null: ReLU)
+    float* mask;                     // [B,T,256]
+    int B, T, t0, t1;
+};
+
+__device__ __forceinline__ float tf32r(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// one transposed-conv stage of one frame, by one warp.  in: [1 + FIN][CIN + 4] (row 0 = zeros); w: [3][COUT][CIN + 4];
+// out: [1 + 2 FIN][COUT + 4] with a zero row 0, or (OUT_CM) channel-major [COUT][2 FIN + 4] with two zero columns in front.
+template <int CIN, int COUT, int FIN, bool OUT_CM>
+__device__ __forceinline__ void convT_stage(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
+                                            const float* __restrict__ ep, const float* __restrict__ skip, int lane) {
+    constexpr int LDI = CIN + 4, NT = COUT / 8, KS = CIN / 8, MT = FIN / 16, FOUT = 2 * FIN;
+    constexpr int LDO = OUT_CM ? (FOUT + 4) : (COUT + 4);
+    const int g = lane >> 2, t = lane & 3;
+    if (OUT_CM) {
+        if (lane < 2 * COUT) out[(lane >> 1) * LDO + (lane & 1)] = 0.f;
+    } else {
+        for (int i = lane; i < LDO; i += 32) out[i] = 0.f;
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+        float2 sk[NT][2][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    sk[nt][r][c] = __ldg(reinterpret_cast<const float2*>(skip + (size_t)(nt * 8 + 2 * t + c) * FOUT + 2 * (mt * 16 + g + 8 * r)));
+        float ae[NT][4], ao[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ae[nt][e] = 0.f; ao[nt][e] = 0.f; }
+        const float* xc = in + (1 + mt * 16 + g) * LDI + t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const float* x = xc + ks * 8;
+            const float cur[4] = {x[0], x[8 * LDI], x[4], x[8 * LDI + 4]};
+            const float prv[4] = {x[-LDI], x[7 * LDI], x[4 - LDI], x[7 * LDI + 4]};
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float* wp = w + (nt * 8 + g) * LDI + ks * 8 + t;
+                mma_tf32(ae[nt], cur, wp[0], wp[4]);                                        // tap 0 at bin i
+                mma_tf32(ae[nt], prv, wp[2 * COUT * LDI], wp[2 * COUT * LDI + 4]);          // tap 2 at bin i - 1
+                mma_tf32(ao[nt], cur, wp[COUT * LDI], wp[COUT * LDI + 4]);                  // tap 1 at bin i
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int co = nt * 8 + 2 * t + c, i = mt * 16 + g + 8 * r;
+                    const float sc = ep[co], sh = ep[EP_N + co], al = ep[2 * EP_N + co];
+                    float ve = fmaf(ae[nt][2 * r + c], sc, sh), vo = fmaf(ao[nt][2 * r + c], sc, sh);
+                    ve = (ve > 0.f ? ve : al * ve) + sk[nt][r][c].x;
+                    vo = (vo > 0.f ? vo : al * vo) + sk[nt][r][c].y;
+                    if (OUT_CM) {
+                        *reinterpret_cast<float2*>(out + co * LDO + 2 + 2 * i) = make_float2(ve, vo);
+                    } else {
+                        out[(1 + 2 * i) * LDO + co] = tf32r(ve);
+                        out[(2 + 2 * i) * LDO + co] = tf32r(vo);
+                    }
+                }
+    }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecFusedArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- weights of all four stages, once per CTA: PyTorch [Cin][Cout][1][3] -> [tap][co][ci] (K contiguous), tf32-rounded
+    for (int i = tid; i < C4 * C3 * 3; i += DF_THREADS) {
+        const int tap = i % 3, co = (i / 3) % C3, ci = i / (3 * C3);
+        sm[W4_OFF + (tap * C3 + co) * LD4 + ci] = tf32r(__ldg(a.w[0] + i));
+    }
+    for (int i = tid; i < C3 * C2 * 3; i += DF_THREADS) {
+        const int tap = i % 3, co = (i / 3) % C2, ci = i / (3 * C2);
+        sm[W3_OFF + (tap * C2 + co) * LD3 + ci] = tf32r(__ldg(a.w[1] + i));
+    }
+    for (int i = tid; i < C2 * C1 * 3; i += DF_THREADS) {
+        const int tap = i % 3, co = (i / 3) % C1, ci = i / (3 * C1);
+        sm[W2_OFF + (tap * C1 + co) * LD2 + ci] = tf32r(__ldg(a.w[2] + i));
+    }
+    if (tid < C1 * 3) sm[W1_OFF + tid] = __ldg(a.w[3] + tid);                     // [ci][tap], stage 1 runs in fp32
+    if (tid == 31) sm[W1_OFF + 24] = a.bias[3] ? __ldg(a.bias[3]) : 0.f;
+    if (tid < EP_N) {
+        const int s = tid < C3 ? 0 : (tid < C3 + C2 ? 1 : 2), co = tid - (s == 0 ? 0 : (s == 1 ? C3 : C3 + C2));
+        const float sc = a.scale[s] ? __ldg(a.scale[s] + co) : 1.f, sh = a.shift[s] ? __ldg(a.shift[s] + co) : 0.f;
+        const float bv = a.bias[s] ? __ldg(a.bias[s] + co) : 0.f;
+        sm[EP_OFF + tid] = sc;
+        sm[EP_OFF + EP_N + tid] = fmaf(bv, sc, sh);                               // (acc + b) * sc + sh
+        sm[EP_OFF + 2 * EP_N + tid] = a.alpha[s] ? __ldg(a.alpha[s] + co) : 0.f;  // ReLU = PReLU with slope 0
+    }
+    __syncthreads();
+
+    float* bufA = sm + WTOT + warp * (BUFA + BUFB);
+    float* bufB = bufA + BUFA;
+    const int Tc = a.t1 - a.t0;
+    const long long nfr = (long long)a.B * Tc;
+    for (long long fr = (long long)blockIdx.x * DF_WARPS + warp; fr < nfr; fr += (long long)gridDim.x * DF_WARPS) {
+        const long long row = (fr / Tc) * a.T + a.t0 + (fr % Tc);
+        // ---- LayerNorm 2 over the frame's 1024 features (same summation order as layernorm_fwd_kernel) + skip 4 -> X4
+        const float* xr = a.y2 + row * (C4 * F4);
+        const float* s4 = a.skip[0] + row * (C4 * F4);
+        float4 v[8], rv[8];
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            v[r] = __ldg(reinterpret_cast<const float4*>(xr + 4 * lane + 128 * r));
+            rv[r] = __ldg(reinterpret_cast<const float4*>(s4 + 4 * lane + 128 * r));
+            s += (v[r].x + v[r].y) + (v[r].z + v[r].w);
+        }
+        const float mean = warp_sum(s) / (float)(C4 * F4);
+        float q = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float d0 = v[r].x - mean, d1 = v[r].y - mean, d2 = v[r].z - mean, d3 = v[r].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)(C4 * F4) + a.eps);
+        for (int i = lane; i < LD4; i += 32) bufA[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int idx = 4 * lane + 128 * r;                                   // feature = channel * 16 + bin
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g + idx)), bt = __ldg(reinterpret_cast<const float4*>(a.ln_b + idx));
+            float* d = bufA + (1 + 4 * (lane & 3)) * LD4 + (lane >> 2) + 8 * r;
+            d[0] = tf32r((v[r].x - mean) * rstd * gm.x + bt.x + rv[r].x);
+            d[LD4] = tf32r((v[r].y - mean) * rstd * gm.y + bt.y + rv[r].y);
+            d[2 * LD4] = tf32r((v[r].z - mean) * rstd * gm.z + bt.z + rv[r].z);
+            d[3 * LD4] = tf32r((v[r].w - mean) * rstd * gm.w + bt.w + rv[r].w);
+        }
+        __syncwarp();
+        convT_stage<C4, C3, F4, false>(bufA, bufB, sm + W4_OFF, sm + EP_OFF, a.skip[1] + row * (C3 * F3), lane);
+        __syncwarp();
+        convT_stage<C3, C2, F3, false>(bufB, bufA, sm + W3_OFF, sm + EP_OFF + C3, a.skip[2] + row * (C2 * F2), lane);
+        __syncwarp();
+        convT_stage<C2, C1, F2, true>(bufA, bufB, sm + W2_OFF, sm + EP_OFF + C3 + C2, a.skip[3] + row * (C1 * F1), lane);
+        __syncwarp();
+        // ---- stage 1: ConvTranspose2d(8 -> 1) + bias + sigmoid (model/cruse_net.py:164), fp32 FMAs; lane owns the bin pairs i = lane + 32 r
+        {
+            const float* w1 = sm + W1_OFF;
+            const float b1 = w1[24];
+            float* mrow = a.mask + row * F0;
+#pragma unroll
+            for (int r = 0; r < F1 / 32; ++r) {
+                const int i = lane + 32 * r;
+                float ve = b1, vo = b1;
+#pragma unroll
+                for (int ci = 0; ci < C1; ++ci) {
+                    const float x0 = bufB[ci * LD1 + 2 + i], xm = bufB[ci * LD1 + 1 + i];
+                    ve = fmaf(w1[3 * ci], x0, fmaf(w1[3 * ci + 2], xm, ve));
+                    vo = fmaf(w1[3 * ci + 1], x0, vo);
+                }
+                *reinterpret_cast<float2*>(mrow + 2 * i) = make_float2(sigmoidf_(ve), sigmoidf_(vo));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+}  // namespace cruse
+
+extern "C" int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                         const float* const* skips, const float* const* w, const float* const* bias,
+                                         const float* const* scale, const float* const* shift, const float* const* alpha, int act,
+                                         float* mask, int B, int T, int t_begin, int t_end, int max_ctas, void* stream) {
+    using namespace cruse;
+    CRUSE_CHECK_ARG(y2 && ln_gamma && ln_beta && skips && w && bias && scale && shift && mask, "decoder_fused_range: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && t_begin >= 0 && t_begin < t_end && t_end <= T, "decoder_fused_range: bad sizes B=%d T=%d range [%d,%d)", B, T,
+                    t_begin, t_end);
+    CRUSE_CHECK_ARG(act == CRUSE_ACT_RELU || act == CRUSE_ACT_PRELU, "decoder_fused_range: activation %d (ReLU / PReLU only)", act);
+    DecFusedArgs a;
+    a.y2 = y2; a.ln_g = ln_gamma; a.ln_b = ln_beta; a.eps = ln_eps; a.mask = mask;
+    a.B = B; a.T = T; a.t0 = t_begin; a.t1 = t_end;
+    for (int s = 0; s < 4; ++s) {
+        CRUSE_CHECK_ARG(skips[s] && w[s], "decoder_fused_range: null skip / weight pointer of stage %d", 4 - s);
+        a.skip[s] = skips[s]; a.w[s] = w[s]; a.bias[s] = bias[s];
+        if (s < 3) {
+            a.scale[s] = scale[s]; a.shift[s] = shift[s];
+            a.alpha[s] = (act == CRUSE_ACT_PRELU && alpha) ? alpha[s] : nullptr;
+            CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || a.alpha[s], "decoder_fused_range: PReLU without slopes for stage %d", 4 - s);
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CRUSE_CUDA_OK(cudaFuncSetAttribute(decoder_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM));
+        attr_set = true;
+    }
+    const long long frames = (long long)B * (t_end - t_begin);
+    long long grid = (frames + DF_WARPS - 1) / DF_WARPS;
+    const long long cap = max_ctas > 0 ? max_ctas : sm_count();
+    if (grid > cap) grid = cap;
+    decoder_fused_kernel<<<(unsigned)grid, DF_THREADS, DF_SMEM, (cudaStream_t)stream>>>(a);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}

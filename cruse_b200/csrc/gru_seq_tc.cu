@@ -188,6 +188,14 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // fast gate nonlinearities (MUFU ex2 / rcp): abs error ~1e-6, far below the tf32 operand rounding of this kernel
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+// one MUFU per gate (tanh.approx; sigmoid(x) = 0.5 tanh(x/2) + 0.5) instead of ex2 + rcp: two MUFU latencies less on the per-step
+// critical path (measured r2: 1.14 -> 1.04 us per step, cfg-2 parity unchanged: mask 1.99e-4 vs 1.9e-4 of full scale, loss 2.7e-6).
+// Used when no gates are saved (inference); the training forward keeps the ex2/rcp gates its backward was validated with.
+#ifndef CRUSE_SEQ_TANH
+#define CRUSE_SEQ_TANH 1
+#endif
+__device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 
 template <int NC>
 __global__ void __launch_bounds__(SQ_THREADS, 1)
@@ -445,9 +453,15 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                 const float pr = myPre[(0 * 32 + 4 * jq + e) * SQ_PRE_LD + b];
                 const float pz = myPre[(1 * 32 + 4 * jq + e) * SQ_PRE_LD + b];
                 ghn[e] = myPre[(2 * 32 + 4 * jq + e) * SQ_PRE_LD + b] + bhv[e];
-                gr[e] = sigmoid_fast(xrv[e] + pr);
-                gz[e] = sigmoid_fast(xzv[e] + pz);
-                gn[e] = tanh_fast(xnv[e] + gr[e] * ghn[e]);
+                if (CRUSE_SEQ_TANH && gp == nullptr) {
+                    gr[e] = sigmoid_mufu(xrv[e] + pr);
+                    gz[e] = sigmoid_mufu(xzv[e] + pz);
+                    gn[e] = tanh_mufu(xnv[e] + gr[e] * ghn[e]);
+                } else {
+                    gr[e] = sigmoid_fast(xrv[e] + pr);
+                    gz[e] = sigmoid_fast(xzv[e] + pz);
+                    gn[e] = tanh_fast(xnv[e] + gr[e] * ghn[e]);
+                }
                 hn[e] = valid ? ((1.f - gz[e]) * gn[e] + gz[e] * hov[e]) : 0.f;
             }
             hold = make_float4(hn[0], hn[1], hn[2], hn[3]);

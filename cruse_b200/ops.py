@@ -351,6 +351,31 @@ def layernorm_fwd_range(x, gamma, beta, eps, residual, y, t0, t1):
           meta=(f"layernorm D{D} [{t0},{t1})", 4 * B * (t1 - t0) * D * (3 if residual is not None else 2), 8 * B * (t1 - t0) * D))
 
 
+# LayerNorm 2 + the four decoder stages of the 256-bin pyramid as one launch per frame range (inference, tf32 conv mode);
+# CRUSE_FUSE_DECODER=0 keeps the five per-stage launches
+FUSE_DECODER = os.environ.get("CRUSE_FUSE_DECODER", "1") != "0"
+
+
+def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, ws, biases, scales, shifts, alphas, act, mask, t0, t1, max_ctas=0):
+    """model/cruse_net.py:51,160-164 for the frames [t0,t1): y2 [B,T,1024] -> mask [B,T,256] (in place).  ``skips`` = (skip4, skip3,
+    skip2, skip1) [B,T,C,F]; ``ws`` / ``biases`` = conv4_t .. conv1_t; ``scales`` / ``shifts`` / ``alphas`` = stages 4..2."""
+    B, T, D = y2.shape
+    want = [(64, 16), (32, 32), (16, 64), (8, 128)]
+    if D != 1024 or tuple(mask.shape[:2]) != (B, T) or mask[0, 0].numel() != 256:
+        raise RuntimeError(f"decoder_fused_range: y2 {tuple(y2.shape)} / mask {tuple(mask.shape)}: the fused decoder is built for the 256-bin pyramid")
+    for k, (sk, w, (c, f)) in enumerate(zip(skips, ws, want)):
+        if tuple(sk.shape) != (B, T, c, f) or tuple(w.shape) != (c, c // 2 if c > 8 else 1, 1, 3):
+            raise RuntimeError(f"decoder_fused_range: stage {4 - k}: skip {tuple(sk.shape)} / weight {tuple(w.shape)} do not match the pyramid")
+    for t in [y2, ln_gamma, ln_beta, mask, *skips, *ws, *[b for b in biases if b is not None], *scales, *shifts, *[a for a in (alphas or []) if a is not None]]:
+        _req(t, "decoder_fused_range tensor")
+    tb = (C.c_void_p * 4)(*[b.data_ptr() if b is not None else None for b in biases])
+    ta = (C.c_void_p * 3)(*[a.data_ptr() if a is not None else None for a in alphas]) if alphas is not None else None
+    frames = B * (t1 - t0)
+    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), _ptr_table(ws), tb,
+          _ptr_table(scales), _ptr_table(shifts), ta, ACT[act], _p(mask), B, T, t0, t1, int(max_ctas), _stream(),
+          meta=(f"decoder_fused [{t0},{t1})", 4 * frames * (5 * 1024 + 256), 2 * frames * 175104))
+
+
 def convT_fwd(x, w, bias, scale, shift, alpha, act, skip, Fout, want_stats=False):
     """x [B,T,Cin,Fin] -> out [B,T,Cout,Fout];  w [Cin,Cout,1,3] (ConvTranspose2d layout)."""
     _req(x, "x", 4)

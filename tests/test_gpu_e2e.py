@@ -245,17 +245,21 @@ def test_captured_graph_and_wavefront_match_eager(cuda):
     assert rel_err(m2, m0) <= 1e-3 and abs(float(l2) - float(l0)) <= 1e-3 * abs(float(l0))
 
 
+@pytest.mark.parametrize("fuse_decoder", [False, True])
 @pytest.mark.parametrize("B,L", [(3, 64000), (32, 32000)])
-def test_pipelined_decoder_schedule_is_bit_identical(cuda, B, L, monkeypatch):
+def test_pipelined_decoder_schedule_is_bit_identical(cuda, B, L, fuse_decoder, monkeypatch):
     """ops.PIPELINE_EDGES: LayerNorm 2, the skip convs and the decoder issued per group of wavefront chunks behind layer 2
     of the GRU (frame-range entry points) instead of after it, with mask*X + iSTFT and the loss following range by range -- a
     scheduling change only: bit-identical mask, spectrum and waveform (loss to summation order), eagerly and through the
-    captured graph; the bounded flag spins never time out."""
+    captured graph; the bounded flag spins never time out.  With ops.FUSE_DECODER the groups run LayerNorm 2 + the four decoder
+    stages as one kernel (decoder_fused.cu): the same tf32-rounded operands in a different summation order -- 5e-4 instead of
+    bit-identity against the staged schedule, bit-identity between the eager and the captured run."""
     from cruse_b200 import ops, pipeline
     ours, _ = _pair(256, "relu", cuda)
     ours.eval()
     g = torch.Generator().manual_seed(6)
     noisy, clean = (0.1 * torch.randn(B, L, generator=g)).to(cuda), (0.05 * torch.randn(B, L, generator=g)).to(cuda)
+    monkeypatch.setattr(ops, "FUSE_DECODER", fuse_decoder)
     monkeypatch.setattr(ops, "PIPELINE_EDGES", False)
     with torch.no_grad():
         l0, w0, e0, m0 = pipeline.forward_loss(ours, noisy, clean, 512, 320)
@@ -264,13 +268,17 @@ def test_pipelined_decoder_schedule_is_bit_identical(cuda, B, L, monkeypatch):
         l1, w1, e1, m1 = pipeline.forward_loss(ours, noisy, clean, 512, 320)
     torch.cuda.synchronize()
     assert int(ours.gru._wavefront_err.item()) == 0
-    # mask, enhanced spectrum and waveform: bit-identical; the loss is summed range by range (different order): 1e-6
-    assert torch.equal(m0, m1) and torch.equal(w0, w1) and torch.equal(e0, e1)
-    assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
+    if fuse_decoder:
+        assert rel_err(m1, m0) <= 5e-4 and rel_err(w1, w0) <= 5e-4 and rel_err(e1, e0) <= 5e-4 and not torch.equal(m0, m1)
+        assert abs(float(l0) - float(l1)) <= 1e-4 * abs(float(l0))
+    else:
+        # mask, enhanced spectrum and waveform: bit-identical; the loss is summed range by range (different order): 1e-6
+        assert torch.equal(m0, m1) and torch.equal(w0, w1) and torch.equal(e0, e1)
+        assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0))
     cap = pipeline.CapturedForwardLoss(ours, B, L, 512, 320)
     l2, w2, e2, m2 = cap(noisy, clean)
     torch.cuda.synchronize()
-    assert torch.equal(m0, m2) and torch.equal(l1, l2) and torch.equal(w0, w2) and torch.equal(e0, e2)
+    assert torch.equal(m1, m2) and torch.equal(l1, l2) and torch.equal(w1, w2) and torch.equal(e1, e2)
 
 
 def test_wavefront_modes_agree_and_no_flag_timeout(cuda):
@@ -283,18 +291,20 @@ def test_wavefront_modes_agree_and_no_flag_timeout(cuda):
     g = torch.Generator().manual_seed(5)
     noisy, clean = 0.1 * torch.randn(5, 96000, generator=g), 0.05 * torch.randn(5, 96000, generator=g)     # T = 301
     out = {}
-    old = ops.GRU_WAVEFRONT_MODE
+    old, old_fuse = ops.GRU_WAVEFRONT_MODE, ops.FUSE_DECODER
     try:
-        for mode in ("flags", "relaunch"):
-            ops.GRU_WAVEFRONT_MODE = mode
+        for mode in ("flags", "relaunch", "flags+fused_decoder"):
+            ops.GRU_WAVEFRONT_MODE = mode.split("+")[0]
+            ops.FUSE_DECODER = mode.endswith("fused_decoder")        # (the one-launch decoder only exists in the flag schedule)
             with torch.no_grad():
                 out[mode] = pipeline.forward_loss(ours, noisy.to(cuda), clean.to(cuda), 512, 320)
             torch.cuda.synchronize()
-            if mode == "flags":
+            if mode != "relaunch":
                 assert int(ours.gru._wavefront_err.item()) == 0
     finally:
-        ops.GRU_WAVEFRONT_MODE = old
+        ops.GRU_WAVEFRONT_MODE, ops.FUSE_DECODER = old, old_fuse
     assert torch.equal(out["flags"][3], out["relaunch"][3])             # masks: bit-identical
+    assert rel_err(out["flags+fused_decoder"][3], out["relaunch"][3]) <= 5e-4
     # the loss is summed range by range behind the pipelined decoder in flag mode, in one launch otherwise: summation order only
     assert abs(float(out["flags"][0]) - float(out["relaunch"][0])) <= 1e-6 * abs(float(out["relaunch"][0]))
 

@@ -511,3 +511,55 @@ def test_fused_encoder_stage_and_skip_conv_equal_the_separate_kernels(cuda, Cin,
         assert float(got_skip[:, :t0].abs().max()) == 0.0 and float(got_skip[:, t1:].abs().max()) == 0.0   # outside the range: untouched
     got_tm, _ = ops.conv_skip_fwd(xf, w, b, sc, sh, None, "relu", ws, out_tm=True)
     assert rel_err(got_tm.transpose(0, 1), sep) <= 1e-6
+
+
+@pytest.mark.parametrize("act", ["relu", "prelu"])
+@pytest.mark.parametrize("B,T,rng,cap", [(3, 37, None, 0), (2, 64, (9, 41), 0), (33, 5, None, 3)])
+def test_fused_decoder_equals_layernorm_plus_the_four_stages(cuda, act, B, T, rng, cap):
+    """cruse_decoder_fused_range (LayerNorm 2 + skip 4 + the four transposed-conv stages of the 256-bin pyramid in one launch,
+    model/cruse_net.py:51,160-164 repaired) against the CPU nn ops (fp32; tf32 gate 1e-3) and against the five per-stage launches it
+    replaces (same tf32-rounded operands, different summation order); frame range, grid cap and PReLU slopes included."""
+    import torch.nn.functional as Fn
+    from cruse_b200 import ops
+    ops.set_conv_mode("tf32")
+    torch.manual_seed(43)
+    chans, freqs = [64, 32, 16, 8, 1], [16, 32, 64, 128, 256]
+    y2 = torch.randn(B, T, 1024)
+    g, b_ = 1 + 0.1 * torch.randn(1024), 0.1 * torch.randn(1024)
+    skips = [0.5 * torch.randn(B, T, chans[k], freqs[k]) for k in range(4)]
+    ws = [torch.randn(chans[k], chans[k + 1], 1, 3) / (1.5 * chans[k]) ** 0.5 for k in range(4)]
+    bs = [0.1 * torch.randn(chans[k + 1]) for k in range(4)]
+    scs = [1 + 0.1 * torch.randn(chans[k + 1]) for k in range(3)]
+    shs = [0.1 * torch.randn(chans[k + 1]) for k in range(3)]
+    als = [0.25 + 0.1 * torch.rand(chans[k + 1]) for k in range(3)] if act == "prelu" else None
+    with torch.no_grad():
+        x = (Fn.layer_norm(y2, (1024,), g, b_, 1e-5) + skips[0].reshape(B, T, 1024)).view(B, T, 64, 16).permute(0, 2, 1, 3)
+        for k in range(3):
+            z = Fn.conv_transpose2d(x, ws[k], bs[k], stride=(1, 2))[..., :freqs[k + 1]]
+            z = z * scs[k].view(1, -1, 1, 1) + shs[k].view(1, -1, 1, 1)
+            z = torch.where(z > 0, z, als[k].view(1, -1, 1, 1) * z) if als else torch.relu(z)
+            x = z + skips[k + 1].permute(0, 2, 1, 3)
+        want = torch.sigmoid(Fn.conv_transpose2d(x, ws[3], bs[3], stride=(1, 2))[..., :256]).permute(0, 2, 1, 3).reshape(B, T, 256)
+    d = lambda t: t.to(cuda).contiguous()
+    y2d, gd, bd = d(y2), d(g), d(b_)
+    skd, wd, bsd, scd, shd = [d(t) for t in skips], [d(t) for t in ws], [d(t) for t in bs], [d(t) for t in scs], [d(t) for t in shs]
+    ald = [d(t) for t in als] if als else None
+    t0, t1 = rng if rng else (0, T)
+    mask = torch.zeros(B, T, 256, device=cuda)
+    ops.decoder_fused_range(y2d, gd, bd, 1e-5, skd, wd, bsd, scd, shd, ald, act, mask, t0, t1, max_ctas=cap)
+    # the five launches it replaces
+    cur = torch.zeros(B, T, 1024, device=cuda)
+    ops.layernorm_fwd_range(y2d, gd, bd, 1e-5, skd[0].view(B, T, 1024), cur, t0, t1)
+    cur = cur.view(B, T, 64, 16)
+    for k in range(3):
+        nxt = torch.zeros(B, T, chans[k + 1], freqs[k + 1], device=cuda)
+        ops.convT_fwd_range(cur, wd[k], bsd[k], scd[k], shd[k], ald[k] if ald else None, act, skd[k + 1], nxt, t0, t1)
+        cur = nxt
+    sep = torch.zeros(B, T, 1, 256, device=cuda)
+    ops.convT_fwd_range(cur, wd[3], bsd[3], None, None, None, "sigmoid", None, sep, t0, t1)
+    torch.cuda.synchronize()
+    sl = slice(t0, t1)
+    assert rel_err(mask[:, sl], want[:, sl]) <= 1e-3
+    assert rel_err(mask[:, sl], sep.view(B, T, 256)[:, sl]) <= 5e-4
+    if rng:
+        assert float(mask[:, :t0].abs().max()) == 0.0 and float(mask[:, t1:].abs().max()) == 0.0      # outside the range: untouched

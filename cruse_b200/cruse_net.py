@@ -390,8 +390,8 @@ class unet_2(nn.Module):
     SKIP_CUTS = [int(v) for v in os.environ.get("CRUSE_SKIP_CUTS", "").split(",") if v]
     SIDE_CAP = int(os.environ.get("CRUSE_SIDE_CAP", "0"))     # CTAs of the persistent side kernels (0 = the SMs the recurrences leave free, minus SIDE_SPARE)
     # SMs the persistent side kernels leave free for the hand-over kernels (LayerNorm 1 + layer-2 projections of a chunk), which otherwise wait
-    # for a side kernel to END before they get an SM (measured r2: 0 -> 1.188 ms, 12 -> 1.172 ms per step)
-    SIDE_SPARE = int(os.environ.get("CRUSE_SIDE_SPARE", "12"))
+    # for a side kernel to END before they get an SM (measured r2: 0 -> 1.188 ms, 12 -> 1.172 ms per step; with the fused decoder: 0 -> 1.077, 12 -> 1.049, 24 -> 1.028, 40 -> 1.039)
+    SIDE_SPARE = int(os.environ.get("CRUSE_SIDE_SPARE", "24"))
     # wavefront chunks of the encoder that run in front of the recurrences (0 = all of it, the default).  Measured on B200 (r2, 8 chunks,
     # 1.266 ms with the whole encoder in front): 4 -> 1.273, 3 -> 1.315 (layer 1 stalls 87 us at chunk 3: the second encoder range
     # takes ~340 us beside the recurrences), 2 -> 1.45, 1 -> 1.47 ms.  Kept as a knob; the two-range schedule is bit-identical.
@@ -482,6 +482,13 @@ class unet_2(nn.Module):
         fuse_dec = (ops.FUSE_DECODER and n == 4 and tuple(self.ch) == (1, 8, 16, 32, 64) and tuple(self.freqs) == (256, 128, 64, 32, 16)
                     and self.act_kind in ("relu", "prelu"))
         dec = [] if fuse_dec else [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
+        dec_image = None
+        if fuse_dec:
+            names = [f"conv{k}_t" for k in range(n, 0, -1)]
+            dec_image = ops.decoder_fused_prep(
+                [getattr(self, nm).weight for nm in names], [getattr(self, nm).bias for nm in names],
+                [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
+                [self._alpha(f"act{k}_t") for k in range(n, 1, -1)] if self.act_kind == "prelu" else None, self.act_kind)
         mask_buf = new(B, T, 1, F)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         layer_sms = 8 * self.gru.groups * ((B + 31) // 32)
@@ -536,13 +543,8 @@ class unet_2(nn.Module):
 
             @staticmethod
             def decode_fused(j, y2, ln2, t0, t1):                                                # :51,160-164 repaired, one launch
-                names = [f"conv{k}_t" for k in range(n, 0, -1)]
-                ops.decoder_fused_range(
-                    y2, ln2.weight, ln2.bias, ln2.eps, [skip_out[k - 1] for k in range(n, 0, -1)],
-                    [getattr(unet, nm).weight for nm in names], [getattr(unet, nm).bias for nm in names],
-                    [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
-                    [unet._alpha(f"act{k}_t") for k in range(n, 1, -1)] if unet.act_kind == "prelu" else None,
-                    unet.act_kind, mask_buf, t0, t1, Around.caps(j, len(Around.groups(plan["nch"]))))
+                ops.decoder_fused_range(y2, ln2.weight, ln2.bias, ln2.eps, [skip_out[k - 1] for k in range(n, 0, -1)], dec_image, mask_buf,
+                                        t0, t1, Around.caps(j, len(Around.groups(plan["nch"]))))
                 if post is not None:
                     post(mask_buf.view(B, T, F), t0, t1)
                     unet._post_ranges.append((t0, t1))

@@ -16,8 +16,11 @@
 // A frame is 16..128 rows -- below one tcgen05 tile -- and the chain is bound by the 20 KB per frame it reads (GRU output + four
 // skip tensors), not by the 0.35 MFLOP it computes, so the warp-private mma.sync pipeline (no barriers between warps, 16 frames in
 // flight per SM) is the right tool here; the tcgen05 kernels stay where M is large (conv_tc.cu, gru_*_tc.cu).
-// Weights of all four stages (35 KB, tf32-rounded, K-contiguous per output channel) are staged once per CTA.
+// Weights of all four stages + the folded epilogue constants (35 KB, tf32-rounded, K-contiguous per output channel) are laid out
+// ONCE per forward pass by decoder_fused_prep_kernel as the exact shared-memory image; a CTA stages it with one bulk copy
+// (cp.async.bulk global -> shared, completion on an mbarrier) that runs under the LayerNorm of the CTA's first frames.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace cruse {
 namespace {
@@ -42,13 +45,18 @@ struct DecFusedArgs {
     const float *ln_g, *ln_b;
     float eps;
     const float* skip[4];            // skip4 [B,T,64,16] (added to LN2), skip3 [B,T,32,32], skip2 [B,T,16,64], skip1 [B,T,8,128]
+    const float* image;              // WTOT floats written by decoder_fused_prep_kernel
+    float* mask;                     // [B,T,256]
+    int B, T, t0, t1;
+};
+
+struct DecPrepArgs {
     const float* w[4];               // conv4_t [64,32,1,3], conv3_t [32,16,1,3], conv2_t [16,8,1,3], conv1_t [8,1,1,3]
     const float* bias[4];
     const float* scale[3];           // folded eval BatchNorm of stages 4..2
     const float* shift[3];
     const float* alpha[3];           // PReLU slopes (null: ReLU)
-    float* mask;                     // [B,T,256]
-    int B, T, t0, t1;
+    float* image;
 };
 
 __device__ __forceinline__ float tf32r(float v) {
@@ -64,11 +72,30 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
                    "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
+// the skip values a lane adds in the epilogue of a stage (its accumulator positions), loaded one stage AHEAD of their use so that the
+// HBM latency hides under the previous stage's MMAs: [m-tile][n-tile][row g / g+8][channel 2t / 2t+1] x (even bin, odd bin)
+template <int COUT, int FIN>
+struct SkipFrag {
+    float2 v[FIN / 16][COUT / 8][2][2];
+    __device__ __forceinline__ void load(const float* __restrict__ skip, int lane) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int mt = 0; mt < FIN / 16; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < COUT / 8; ++nt)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        v[mt][nt][r][c] = __ldg(reinterpret_cast<const float2*>(skip + (size_t)(nt * 8 + 2 * t + c) * (2 * FIN) + 2 * (mt * 16 + g + 8 * r)));
+    }
+};
+
 // one transposed-conv stage of one frame, by one warp.  in: [1 + FIN][CIN + 4] (row 0 = zeros); w: [3][COUT][CIN + 4];
 // out: [1 + 2 FIN][COUT + 4] with a zero row 0, or (OUT_CM) channel-major [COUT][2 FIN + 4] with two zero columns in front.
 template <int CIN, int COUT, int FIN, bool OUT_CM>
 __device__ __forceinline__ void convT_stage(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
-                                            const float* __restrict__ ep, const float* __restrict__ skip, int lane) {
+                                            const float* __restrict__ ep, const SkipFrag<COUT, FIN>& sk, int lane) {
     constexpr int LDI = CIN + 4, NT = COUT / 8, KS = CIN / 8, MT = FIN / 16, FOUT = 2 * FIN;
     constexpr int LDO = OUT_CM ? (FOUT + 4) : (COUT + 4);
     const int g = lane >> 2, t = lane & 3;
@@ -77,16 +104,8 @@ __device__ __forceinline__ void convT_stage(const float* __restrict__ in, float*
     } else {
         for (int i = lane; i < LDO; i += 32) out[i] = 0.f;
     }
-#pragma unroll 1
+#pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-        float2 sk[NT][2][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    sk[nt][r][c] = __ldg(reinterpret_cast<const float2*>(skip + (size_t)(nt * 8 + 2 * t + c) * FOUT + 2 * (mt * 16 + g + 8 * r)));
         float ae[NT][4], ao[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -115,8 +134,8 @@ __device__ __forceinline__ void convT_stage(const float* __restrict__ in, float*
                     const int co = nt * 8 + 2 * t + c, i = mt * 16 + g + 8 * r;
                     const float sc = ep[co], sh = ep[EP_N + co], al = ep[2 * EP_N + co];
                     float ve = fmaf(ae[nt][2 * r + c], sc, sh), vo = fmaf(ao[nt][2 * r + c], sc, sh);
-                    ve = (ve > 0.f ? ve : al * ve) + sk[nt][r][c].x;
-                    vo = (vo > 0.f ? vo : al * vo) + sk[nt][r][c].y;
+                    ve = (ve > 0.f ? ve : al * ve) + sk.v[mt][nt][r][c].x;
+                    vo = (vo > 0.f ? vo : al * vo) + sk.v[mt][nt][r][c].y;
                     if (OUT_CM) {
                         *reinterpret_cast<float2*>(out + co * LDO + 2 + 2 * i) = make_float2(ve, vo);
                     } else {
@@ -127,10 +146,13 @@ __device__ __forceinline__ void convT_stage(const float* __restrict__ in, float*
     }
 }
 
-__global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecFusedArgs a) {
-    extern __shared__ __align__(16) float sm[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // ---- weights of all four stages, once per CTA: PyTorch [Cin][Cout][1][3] -> [tap][co][ci] (K contiguous), tf32-rounded
+// the shared-memory image of the decoder's constants: PyTorch [Cin][Cout][1][3] -> [tap][co][ci + 4] (K contiguous), tf32-rounded;
+// stage-1 weights and bias in fp32; per channel of stages 4..2: scale, shift with the conv bias folded in, PReLU slope (ReLU: 0)
+__global__ void __launch_bounds__(DF_THREADS) decoder_fused_prep_kernel(const DecPrepArgs a) {
+    const int tid = threadIdx.x;
+    float* sm = a.image;
+    for (int i = tid; i < WTOT; i += DF_THREADS) sm[i] = 0.f;
+    __syncthreads();
     for (int i = tid; i < C4 * C3 * 3; i += DF_THREADS) {
         const int tap = i % 3, co = (i / 3) % C3, ci = i / (3 * C3);
         sm[W4_OFF + (tap * C3 + co) * LD4 + ci] = tf32r(__ldg(a.w[0] + i));
@@ -153,7 +175,25 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
         sm[EP_OFF + EP_N + tid] = fmaf(bv, sc, sh);                               // (acc + b) * sc + sh
         sm[EP_OFF + 2 * EP_N + tid] = a.alpha[s] ? __ldg(a.alpha[s] + co) : 0.f;  // ReLU = PReLU with slope 0
     }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecFusedArgs a) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t wbar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- constants of all four stages: one bulk copy of the prepared image, awaited in front of the first stage-4 GEMM
+    if (tid == 0) {
+        tc::mbar_init(&wbar, 1);
+        tc::fence_barrier_init();
+    }
     __syncthreads();
+    if (tid == 0) {
+        tc::mbar_expect_tx(&wbar, (uint32_t)(WTOT * sizeof(float)));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(sm)), "l"(a.image),
+                     "r"((uint32_t)(WTOT * sizeof(float))), "r"(tc::smem_u32(&wbar))
+                     : "memory");
+    }
+    bool have_w = false;
 
     float* bufA = sm + WTOT + warp * (BUFA + BUFB);
     float* bufB = bufA + BUFA;
@@ -165,6 +205,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
         const float* xr = a.y2 + row * (C4 * F4);
         const float* s4 = a.skip[0] + row * (C4 * F4);
         float4 v[8], rv[8];
+        SkipFrag<C3, F4> sk3;
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -192,11 +233,20 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
             d[3 * LD4] = tf32r((v[r].w - mean) * rstd * gm.w + bt.w + rv[r].w);
         }
         __syncwarp();
-        convT_stage<C4, C3, F4, false>(bufA, bufB, sm + W4_OFF, sm + EP_OFF, a.skip[1] + row * (C3 * F3), lane);
+        sk3.load(a.skip[1] + row * (C3 * F3), lane);
+        SkipFrag<C2, F3> sk2;
+        sk2.load(a.skip[2] + row * (C2 * F2), lane);
+        if (!have_w) {
+            tc::mbar_wait(&wbar, 0);
+            have_w = true;
+        }
+        convT_stage<C4, C3, F4, false>(bufA, bufB, sm + W4_OFF, sm + EP_OFF, sk3, lane);
         __syncwarp();
-        convT_stage<C3, C2, F3, false>(bufB, bufA, sm + W3_OFF, sm + EP_OFF + C3, a.skip[2] + row * (C2 * F2), lane);
+        SkipFrag<C1, F2> sk1;
+        sk1.load(a.skip[3] + row * (C1 * F1), lane);
+        convT_stage<C3, C2, F3, false>(bufB, bufA, sm + W3_OFF, sm + EP_OFF + C3, sk2, lane);
         __syncwarp();
-        convT_stage<C2, C1, F2, true>(bufA, bufB, sm + W2_OFF, sm + EP_OFF + C3 + C2, a.skip[3] + row * (C1 * F1), lane);
+        convT_stage<C2, C1, F2, true>(bufA, bufB, sm + W2_OFF, sm + EP_OFF + C3 + C2, sk1, lane);
         __syncwarp();
         // ---- stage 1: ConvTranspose2d(8 -> 1) + bias + sigmoid (model/cruse_net.py:164), fp32 FMAs; lane owns the bin pairs i = lane + 32 r
         {
@@ -223,26 +273,43 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
 }  // namespace
 }  // namespace cruse
 
-extern "C" int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                                         const float* const* skips, const float* const* w, const float* const* bias,
-                                         const float* const* scale, const float* const* shift, const float* const* alpha, int act,
-                                         float* mask, int B, int T, int t_begin, int t_end, int max_ctas, void* stream) {
+extern "C" long long cruse_decoder_fused_image_floats() { return cruse::WTOT; }
+
+extern "C" int cruse_decoder_fused_prep(const float* const* w, const float* const* bias, const float* const* scale, const float* const* shift,
+                                        const float* const* alpha, int act, float* image, void* stream) {
     using namespace cruse;
-    CRUSE_CHECK_ARG(y2 && ln_gamma && ln_beta && skips && w && bias && scale && shift && mask, "decoder_fused_range: null pointer");
-    CRUSE_CHECK_ARG(B > 0 && T > 0 && t_begin >= 0 && t_begin < t_end && t_end <= T, "decoder_fused_range: bad sizes B=%d T=%d range [%d,%d)", B, T,
-                    t_begin, t_end);
-    CRUSE_CHECK_ARG(act == CRUSE_ACT_RELU || act == CRUSE_ACT_PRELU, "decoder_fused_range: activation %d (ReLU / PReLU only)", act);
-    DecFusedArgs a;
-    a.y2 = y2; a.ln_g = ln_gamma; a.ln_b = ln_beta; a.eps = ln_eps; a.mask = mask;
-    a.B = B; a.T = T; a.t0 = t_begin; a.t1 = t_end;
+    CRUSE_CHECK_ARG(w && bias && scale && shift && image, "decoder_fused_prep: null pointer");
+    CRUSE_CHECK_ARG(act == CRUSE_ACT_RELU || act == CRUSE_ACT_PRELU, "decoder_fused_prep: activation %d (ReLU / PReLU only)", act);
+    DecPrepArgs a;
+    a.image = image;
     for (int s = 0; s < 4; ++s) {
-        CRUSE_CHECK_ARG(skips[s] && w[s], "decoder_fused_range: null skip / weight pointer of stage %d", 4 - s);
-        a.skip[s] = skips[s]; a.w[s] = w[s]; a.bias[s] = bias[s];
+        CRUSE_CHECK_ARG(w[s], "decoder_fused_prep: null weight pointer of stage %d", 4 - s);
+        a.w[s] = w[s]; a.bias[s] = bias[s];
         if (s < 3) {
             a.scale[s] = scale[s]; a.shift[s] = shift[s];
             a.alpha[s] = (act == CRUSE_ACT_PRELU && alpha) ? alpha[s] : nullptr;
-            CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || a.alpha[s], "decoder_fused_range: PReLU without slopes for stage %d", 4 - s);
+            CRUSE_CHECK_ARG(act != CRUSE_ACT_PRELU || a.alpha[s], "decoder_fused_prep: PReLU without slopes for stage %d", 4 - s);
         }
+    }
+    decoder_fused_prep_kernel<<<1, DF_THREADS, 0, (cudaStream_t)stream>>>(a);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                         const float* const* skips, const float* image, float* mask, int B, int T, int t_begin, int t_end,
+                                         int max_ctas, void* stream) {
+    using namespace cruse;
+    CRUSE_CHECK_ARG(y2 && ln_gamma && ln_beta && skips && image && mask, "decoder_fused_range: null pointer");
+    CRUSE_CHECK_ARG(B > 0 && T > 0 && t_begin >= 0 && t_begin < t_end && t_end <= T, "decoder_fused_range: bad sizes B=%d T=%d range [%d,%d)", B, T,
+                    t_begin, t_end);
+    CRUSE_CHECK_ARG(((uintptr_t)image & 15) == 0, "decoder_fused_range: image must be 16-byte aligned");
+    DecFusedArgs a;
+    a.y2 = y2; a.ln_g = ln_gamma; a.ln_b = ln_beta; a.eps = ln_eps; a.mask = mask; a.image = image;
+    a.B = B; a.T = T; a.t0 = t_begin; a.t1 = t_end;
+    for (int s = 0; s < 4; ++s) {
+        CRUSE_CHECK_ARG(skips[s], "decoder_fused_range: null skip pointer of stage %d", 4 - s);
+        a.skip[s] = skips[s];
     }
     static bool attr_set = false;
     if (!attr_set) {

@@ -356,24 +356,37 @@ def layernorm_fwd_range(x, gamma, beta, eps, residual, y, t0, t1):
 FUSE_DECODER = os.environ.get("CRUSE_FUSE_DECODER", "1") != "0"
 
 
-def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, ws, biases, scales, shifts, alphas, act, mask, t0, t1, max_ctas=0):
+def decoder_fused_prep(ws, biases, scales, shifts, alphas, act):
+    """the constants of the fused decoder as its shared-memory image (once per forward pass, after the BatchNorm fold): ``ws`` /
+    ``biases`` = conv4_t .. conv1_t, ``scales`` / ``shifts`` / ``alphas`` = stages 4..2 -> image tensor for decoder_fused_range"""
+    want = [(64, 32), (32, 16), (16, 8), (8, 1)]
+    for k, (w, (ci, co)) in enumerate(zip(ws, want)):
+        if tuple(w.shape) != (ci, co, 1, 3):
+            raise RuntimeError(f"decoder_fused_prep: stage {4 - k}: weight {tuple(w.shape)} does not match the 256-bin pyramid")
+    for t in [*ws, *[b for b in biases if b is not None], *scales, *shifts, *[a for a in (alphas or []) if a is not None]]:
+        _req(t, "decoder_fused_prep tensor")
+    image = torch.empty(int(lib().cruse_decoder_fused_image_floats()), device=ws[0].device, dtype=torch.float32)
+    tb = (C.c_void_p * 4)(*[b.data_ptr() if b is not None else None for b in biases])
+    ta = (C.c_void_p * 3)(*[a.data_ptr() if a is not None else None for a in alphas]) if alphas is not None else None
+    _call("cruse_decoder_fused_prep", _ptr_table(ws), tb, _ptr_table(scales), _ptr_table(shifts), ta, ACT[act], _p(image), _stream())
+    return image
+
+
+def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, max_ctas=0):
     """model/cruse_net.py:51,160-164 for the frames [t0,t1): y2 [B,T,1024] -> mask [B,T,256] (in place).  ``skips`` = (skip4, skip3,
-    skip2, skip1) [B,T,C,F]; ``ws`` / ``biases`` = conv4_t .. conv1_t; ``scales`` / ``shifts`` / ``alphas`` = stages 4..2."""
+    skip2, skip1) [B,T,C,F]; ``image`` from decoder_fused_prep."""
     B, T, D = y2.shape
     want = [(64, 16), (32, 32), (16, 64), (8, 128)]
     if D != 1024 or tuple(mask.shape[:2]) != (B, T) or mask[0, 0].numel() != 256:
         raise RuntimeError(f"decoder_fused_range: y2 {tuple(y2.shape)} / mask {tuple(mask.shape)}: the fused decoder is built for the 256-bin pyramid")
-    for k, (sk, w, (c, f)) in enumerate(zip(skips, ws, want)):
-        if tuple(sk.shape) != (B, T, c, f) or tuple(w.shape) != (c, c // 2 if c > 8 else 1, 1, 3):
-            raise RuntimeError(f"decoder_fused_range: stage {4 - k}: skip {tuple(sk.shape)} / weight {tuple(w.shape)} do not match the pyramid")
-    for t in [y2, ln_gamma, ln_beta, mask, *skips, *ws, *[b for b in biases if b is not None], *scales, *shifts, *[a for a in (alphas or []) if a is not None]]:
+    for k, (sk, (c, f)) in enumerate(zip(skips, want)):
+        if tuple(sk.shape) != (B, T, c, f):
+            raise RuntimeError(f"decoder_fused_range: stage {4 - k}: skip {tuple(sk.shape)} does not match the pyramid")
+    for t in [y2, ln_gamma, ln_beta, mask, image, *skips]:
         _req(t, "decoder_fused_range tensor")
-    tb = (C.c_void_p * 4)(*[b.data_ptr() if b is not None else None for b in biases])
-    ta = (C.c_void_p * 3)(*[a.data_ptr() if a is not None else None for a in alphas]) if alphas is not None else None
     frames = B * (t1 - t0)
-    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), _ptr_table(ws), tb,
-          _ptr_table(scales), _ptr_table(shifts), ta, ACT[act], _p(mask), B, T, t0, t1, int(max_ctas), _stream(),
-          meta=(f"decoder_fused [{t0},{t1})", 4 * frames * (5 * 1024 + 256), 2 * frames * 175104))
+    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), _p(image), _p(mask), B, T, t0, t1,
+          int(max_ctas), _stream(), meta=(f"decoder_fused [{t0},{t1})", 4 * frames * (5 * 1024 + 256), 2 * frames * 175104))
 
 
 def convT_fwd(x, w, bias, scale, shift, alpha, act, skip, Fout, want_stats=False):

@@ -165,16 +165,20 @@ int cruse_layernorm_fwd_range(const float* x, const float* gamma, const float* b
  * replaces model/cruse_net.py:51 (ln2), :160 (+ skip_connect_4) and :161-164 repaired (3 x [ConvTranspose2d(1,3)/s(1,2) + folded
  * BatchNorm + ReLU/PReLU + skip], ConvTranspose2d(8->1) + sigmoid).  One warp per frame, activations stay in shared memory,
  * warp-level tf32 tensor-core GEMMs (fp32 accumulate), stage 1 and the LayerNorm in fp32.
- *   y2 [B,T,1024] (GRU layer-2 output, feature = channel*16 + bin); mask [B,T,256]
- *   skips / w / bias: HOST arrays of 4 device pointers, decoder order: stage 4 (skip4 [B,T,64,16] added to the LayerNorm output,
- *   conv4_t.weight [64,32,1,3]), stage 3 (skip3 [B,T,32,32], conv3_t [32,16,1,3]), stage 2 (skip2 [B,T,16,64], conv2_t [16,8,1,3]),
- *   stage 1 (skip1 [B,T,8,128], conv1_t [8,1,1,3]); scale / shift / alpha: HOST arrays of 3 device pointers (folded BatchNorm and
- *   PReLU slopes of stages 4..2; alpha may be NULL for ReLU).  max_ctas > 0 caps the grid (running beside the recurrences).
+ *   cruse_decoder_fused_prep lays the constants of all four stages out once per forward pass (after the BatchNorm fold) as the
+ *   kernel's shared-memory image (cruse_decoder_fused_image_floats() floats, 16-byte aligned): w / bias = HOST arrays of 4 device
+ *   pointers in decoder order (conv4_t.weight [64,32,1,3], conv3_t [32,16,1,3], conv2_t [16,8,1,3], conv1_t [8,1,1,3]); scale /
+ *   shift / alpha = HOST arrays of 3 device pointers (folded BatchNorm and PReLU slopes of stages 4..2; alpha may be NULL for ReLU).
+ *   cruse_decoder_fused_range: y2 [B,T,1024] (GRU layer-2 output, feature = channel*16 + bin) -> mask [B,T,256]; skips = HOST array of
+ *   4 device pointers: skip4 [B,T,64,16] (added to the LayerNorm output), skip3 [B,T,32,32], skip2 [B,T,16,64], skip1 [B,T,8,128];
+ *   max_ctas > 0 caps the grid (running beside the recurrences).
  * Any other geometry is an error, not a fallback (use the per-stage entry points). */
+long long cruse_decoder_fused_image_floats(void);
+int cruse_decoder_fused_prep(const float* const* w, const float* const* bias, const float* const* scale, const float* const* shift,
+                             const float* const* alpha, int act, float* image, void* stream);
 int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                              const float* const* skips, const float* const* w, const float* const* bias,
-                              const float* const* scale, const float* const* shift, const float* const* alpha, int act,
-                              float* mask, int B, int T, int t_begin, int t_end, int max_ctas, void* stream);
+                              const float* const* skips, const float* image, float* mask, int B, int T, int t_begin, int t_end,
+                              int max_ctas, void* stream);
 
 /* ---- a4: grouped GRU.  replaces nn.GRU(H,H) x groups at model/cruse_net.py:23-31,43-50.
  *  ih GEMM: xproj[m, g, :] = x[m, g*H:(g+1)*H] . w_ih[g]^T + b_ih[g] (+ b_hh[g] for r,z rows)

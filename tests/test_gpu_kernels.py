@@ -546,7 +546,8 @@ def test_fused_decoder_equals_layernorm_plus_the_four_stages(cuda, act, B, T, rn
     ald = [d(t) for t in als] if als else None
     t0, t1 = rng if rng else (0, T)
     mask = torch.zeros(B, T, 256, device=cuda)
-    ops.decoder_fused_range(y2d, gd, bd, 1e-5, skd, wd, bsd, scd, shd, ald, act, mask, t0, t1, max_ctas=cap)
+    image = ops.decoder_fused_prep(wd, bsd, scd, shd, ald, act)
+    ops.decoder_fused_range(y2d, gd, bd, 1e-5, skd, image, mask, t0, t1, max_ctas=cap)
     # the five launches it replaces
     cur = torch.zeros(B, T, 1024, device=cuda)
     ops.layernorm_fwd_range(y2d, gd, bd, 1e-5, skd[0].view(B, T, 1024), cur, t0, t1)

@@ -76,6 +76,8 @@ class GGRU(nn.Module):
     WAVEFRONT_CHUNKS = 8            # relaunch mode: one recurrence launch per chunk
     WAVEFRONT_FLAG_CHUNKS = int(os.environ.get("CRUSE_FLAG_CHUNKS", "8"))   # flag mode: chunks only gate the hand-over between the layers (ABI limit 16)
     WAVEFRONT_LAST_CHUNK = int(os.environ.get("CRUSE_LAST_CHUNK", "0"))      # frames of the last flag chunk (0 = equal chunks)
+    # frames of extra short chunks behind the equal ones, e.g. "32,16" (experiment)
+    WAVEFRONT_TAIL = [int(v) for v in os.environ.get("CRUSE_CHUNK_TAIL", "").split(",") if v]
     _side_streams = {}
 
     @classmethod
@@ -96,7 +98,15 @@ class GGRU(nn.Module):
         # optional SHORT last chunk (WAVEFRONT_LAST_CHUNK frames; 0 = equal chunks, the default): what is left after layer 1 has
         # finished is proportional to it -- measured on B200 it loses all the same (32 / 16 frames: 1.51 / 1.53 vs 1.49 ms per step)
         last = min(self.WAVEFRONT_LAST_CHUNK, T // nch)
-        if last >= 8 and nch >= 3:
+        tail = [c for c in self.WAVEFRONT_TAIL if c >= 8]
+        if tail and nch >= 3 and sum(tail) <= T // 4 and nch + len(tail) <= 16:
+            # equal chunks, then a run of SHORT ones: layer 2 ends one chunk + one hand-over behind layer 1, so the last chunks set the lag
+            Tm = T - sum(tail)
+            bounds = [Tm * k // nch for k in range(nch + 1)]
+            for c in tail:
+                bounds.append(bounds[-1] + c)
+            nch += len(tail)
+        elif last >= 8 and nch >= 3:
             bounds = [(T - last) * k // (nch - 1) for k in range(nch)] + [T]
         else:
             bounds = [T * k // nch for k in range(nch + 1)]
@@ -392,6 +402,7 @@ class unet_2(nn.Module):
     # SMs the persistent side kernels leave free for the hand-over kernels (LayerNorm 1 + layer-2 projections of a chunk), which otherwise wait
     # for a side kernel to END before they get an SM (measured r2: 0 -> 1.188 ms, 12 -> 1.172 ms per step; with the fused decoder: 0 -> 1.077, 12 -> 1.049, 24 -> 1.028, 40 -> 1.039)
     SIDE_SPARE = int(os.environ.get("CRUSE_SIDE_SPARE", "24"))
+    DEC_CAP = int(os.environ.get("CRUSE_DEC_CAP", "0"))          # CTAs of the fused decoder launches (0 = like the other side kernels, -1 = uncapped)
     # wavefront chunks of the encoder that run in front of the recurrences (0 = all of it, the default).  Measured on B200 (r2, 8 chunks,
     # 1.266 ms with the whole encoder in front): 4 -> 1.273, 3 -> 1.315 (layer 1 stalls 87 us at chunk 3: the second encoder range
     # takes ~340 us beside the recurrences), 2 -> 1.45, 1 -> 1.47 ms.  Kept as a knob; the two-range schedule is bit-identical.
@@ -543,8 +554,11 @@ class unet_2(nn.Module):
 
             @staticmethod
             def decode_fused(j, y2, ln2, t0, t1):                                                # :51,160-164 repaired, one launch
+                cap = Around.caps(j, len(Around.groups(plan["nch"])))
+                if unet.DEC_CAP:
+                    cap = max(0, unet.DEC_CAP)
                 ops.decoder_fused_range(y2, ln2.weight, ln2.bias, ln2.eps, [skip_out[k - 1] for k in range(n, 0, -1)], dec_image, mask_buf,
-                                        t0, t1, Around.caps(j, len(Around.groups(plan["nch"]))))
+                                        t0, t1, cap)
                 if post is not None:
                     post(mask_buf.view(B, T, F), t0, t1)
                     unet._post_ranges.append((t0, t1))

@@ -35,6 +35,10 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
         side2 = _side_stream(dev, 1)                # the loss ranges: beside (not behind) the mask*X + iSTFT ranges
+        # consecutive ranges rotate over a few streams each: a range that was served late (the first, largest one shares the GPU with
+        # both recurrences) must not hold up the ranges behind it -- the last one sits on the critical path
+        istft_streams = (side, _side_stream(dev, 2), _side_stream(dev, 4))
+        loss_streams = (side2, _side_stream(dev, 3), _side_stream(dev, 5))
         X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)   # feature.py:10-30, utils.py:400
         # the clean-speech STFT is only needed by the loss: it is released behind the encoder and the layer-1 input projections
         # (not beside them, where it would take SMs from what gates the recurrence) and runs beside the GRU; its output buffer
@@ -53,7 +57,8 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 ops.stft_fwd_into(clean, hann_window(n_fft, n_fft, dev), S, n_fft, hop, pad_mode)
                 s_ready = torch.cuda.Event()
                 s_ready.record(side)
-            side2.wait_event(s_ready)
+            for st in loss_streams:
+                st.wait_event(s_ready)
             clean_started.append(True)
         # Pipelined schedule (ops.PIPELINE_EDGES): the decoder hands the mask over range by range; mask*X + iSTFT and the loss
         # follow on the side stream, so that only the last range of both is left after the last decoder launch.
@@ -65,19 +70,24 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         wav_buf = torch.empty(noisy.shape[0], noisy.shape[-1], device=dev, dtype=torch.float32)
         ws = ops.loss_workspace(dev)
         lay_s, lay_x = ops.layout_btf2(S), ops.layout_btf2(X)
-        prog = {"c": 0, "p": 0}
+        prog = {"c": 0, "p": 0, "i": 0}
 
         def post(mask_all, t0, t1):
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
-            side.wait_event(ev)
-            side2.wait_event(ev)
-            with torch.cuda.stream(side):
+            s_i, s_l = istft_streams[prog["i"] % len(istft_streams)], loss_streams[prog["i"] % len(loss_streams)]
+            prog["i"] += 1
+            s_i.wait_event(ev)
+            s_l.wait_event(ev)
+            if prog.get("prev") is not None:
+                s_i.wait_event(prog["prev"])     # the first iSTFT CTAs of this range read mask frames of the previous range's decoder launch
+            prog["prev"] = ev
+            with torch.cuda.stream(s_i):
                 c1 = nct if t1 >= T else t1 // FC
                 if c1 > prog["c"]:
                     ops.mask_istft_fwd_range(X, mask_all, window, n_fft, hop, est_buf, wav_buf, prog["c"], c1)
                     prog["c"] = c1
-            with torch.cuda.stream(side2):
+            with torch.cuda.stream(s_l):
                 # CTAs (= partial-sum slots) of this range: at least two (b, t) rows each, never fewer than ~4 per SM -- the last,
                 # short range sits on the critical path and is pure latency with few CTAs
                 rows = X.shape[0] * (t1 - t0)
@@ -94,19 +104,25 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
             raise RuntimeError("forward_loss: the model did not call after_encoder()")
         ranges = getattr(model, "_post_ranges", [])
         if ranges and ranges[0][0] == 0 and ranges[-1][1] == T and prog["c"] == nct:
+            for st in loss_streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                side2.wait_event(ev)
             with torch.cuda.stream(side2):
                 loss = ops.wo_male_finish(ws, prog["p"], X.shape[0], T, F)
                 done = torch.cuda.Event()
                 done.record(side2)
-            done_istft = torch.cuda.Event()
-            done_istft.record(side)
             loss.record_stream(main)                     # made on a side stream, handed to the caller's
-            for t_ in (est_buf, wav_buf):                # made on the caller's stream, written on the side streams
-                t_.record_stream(side)
-            for t_ in (ws, S, X):
-                t_.record_stream(side2)
+            for st in istft_streams[:max(1, min(prog["i"], len(istft_streams)))]:
+                for t_ in (est_buf, wav_buf):            # made on the caller's stream, written on the side streams
+                    t_.record_stream(st)
+                done_istft = torch.cuda.Event()
+                done_istft.record(st)
+                main.wait_event(done_istft)
+            for st in loss_streams:
+                for t_ in (ws, S, X):
+                    t_.record_stream(st)
             main.wait_event(done)
-            main.wait_event(done_istft)
             if model.gru._wavefront_err is not None:
                 # the ranges above were computed from the mask before forward_frames could poison it: a timed-out flag spin
                 # turns every output of the step into NaN (and the host raises where it synchronises, see check_wavefront)
@@ -122,9 +138,10 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
             done.record(side)
         est, wav = ops.mask_istft_fwd(X, mask, hann_window(n_fft, n_fft, dev), n_fft, hop, noisy.shape[-1])
         main.wait_event(done)
-        joined = torch.cuda.Event()                  # side2 only waited for the clean STFT here: join it (graph capture needs it)
-        joined.record(side2)
-        main.wait_event(joined)
+        for st in loss_streams:                      # they only waited for the clean STFT here: join them (graph capture needs it)
+            joined = torch.cuda.Event()
+            joined.record(st)
+            main.wait_event(joined)
         return loss, wav, est, mask
     wav, est, mask, X = enhance(model, noisy, n_fft, hop, pad_mode)
     S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)

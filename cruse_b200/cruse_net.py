@@ -428,7 +428,7 @@ class unet_2(nn.Module):
             raise RuntimeError(f"chunk_groups: cuts {cuts} do not partition [0, {nch}]")
         return list(zip(cuts[:-1], cuts[1:]))
 
-    def _forward_frames_pipelined(self, mag, plan, folds, post=None, after_encoder=None):
+    def _forward_frames_pipelined(self, mag, plan, folds, post=None, after_encoder=None, loss_inputs=None):
         """Eval, whole utterances, flag-synchronised wavefront: the net is causal and the transposed convs / (1,3) skip convs
         have no time taps at all, so LayerNorm 2 + the decoder (and the skip convs they add) are run per GROUP of wavefront
         chunks as soon as layer 2 of the GRU has stored them: behind the last step of the recurrence only the last chunk's
@@ -494,6 +494,9 @@ class unet_2(nn.Module):
                     and self.act_kind in ("relu", "prelu"))
         dec = [] if fuse_dec else [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
         dec_image = None
+        # the caller's wo_male inputs: the fused decoder then leaves every frame's share of the loss beside the mask (no loss launches)
+        fuse_loss = fuse_dec and loss_inputs is not None and F == 256 and ops.FUSE_LOSS
+        self._loss_fused = fuse_loss
         if fuse_dec:
             names = [f"conv{k}_t" for k in range(n, 0, -1)]
             dec_image = ops.decoder_fused_prep(
@@ -557,8 +560,13 @@ class unet_2(nn.Module):
                 cap = Around.caps(j, len(Around.groups(plan["nch"])))
                 if unet.DEC_CAP:
                     cap = max(0, unet.DEC_CAP)
+                larg = None
+                if fuse_loss:
+                    for ev in loss_inputs["ready"]():        # the clean-speech spectrum (made on the caller's side stream)
+                        torch.cuda.current_stream(dev).wait_event(ev)
+                    larg = loss_inputs["args"]
                 ops.decoder_fused_range(y2, ln2.weight, ln2.bias, ln2.eps, [skip_out[k - 1] for k in range(n, 0, -1)], dec_image, mask_buf,
-                                        t0, t1, cap)
+                                        t0, t1, cap, loss=larg)
                 if post is not None:
                     post(mask_buf.view(B, T, F), t0, t1)
                     unet._post_ranges.append((t0, t1))
@@ -591,11 +599,13 @@ class unet_2(nn.Module):
             ops.poison_on_error(self.gru._wavefront_err, [mask_buf])      # a timed-out flag spin must not return numbers
         return mask_buf.view(B, T, F)
 
-    def forward_frames(self, mag, state=None, want_state=False, post=None, after_encoder=None):
+    def forward_frames(self, mag, state=None, want_state=False, post=None, after_encoder=None, loss_inputs=None):
         """mag [B,T,F] frame-major magnitudes -> mask [B,T,F].  (Internal zero-copy entry used by
         cruse_b200.pipeline; ``forward`` wraps it with the reference's [B,1,T,F] layout.)
         ``post(mask, t0, t1)``: optional consumer of the mask, called on the stream that has just produced the frames [t0,t1)
         when the pipelined schedule runs (``self._post_ranges`` lists the ranges it was called for; empty = not called).
+        ``loss_inputs`` = {"args": (S, layout_S, X, layout_X, rows[B*T]), "ready": callable -> events}: where the one-launch decoder
+        runs it also leaves every frame's share of wo_male(S, mask*X, X) in ``rows`` (``self._loss_fused`` says whether it did).
         ``after_encoder(event=None)``: optional hook called once the encoder stages (pipelined schedule: and the layer-1 input
         projections, ``event``) have been queued -- work the caller wants to start behind them rather than beside them, e.g.
         the clean-speech STFT of the loss.
@@ -620,8 +630,9 @@ class unet_2(nn.Module):
             folds = dict(zip(names, ops.bn_fold_many([getattr(self, nm) for nm in names])))
         plan = self.gru.plan(B, T, mag.device) if (overlap and ops.PIPELINE_EDGES) else None
         self._post_ranges = []
+        self._loss_fused = False
         if plan is not None:
-            return self._forward_frames_pipelined(mag, plan, folds, post, after_encoder)
+            return self._forward_frames_pipelined(mag, plan, folds, post, after_encoder, loss_inputs)
         for k in range(1, n + 1):                                            # :149-152 repaired
             if want_state:
                 new_hist.append(h[:, -1].contiguous())

@@ -48,6 +48,12 @@ struct DecFusedArgs {
     const float* image;              // WTOT floats written by decoder_fused_prep_kernel
     float* mask;                     // [B,T,256]
     int B, T, t0, t1;
+    // optional: the frame's share of wo_male (loss_func/loss.py:121-148) on est = mask * X, formed right where the mask is produced
+    const float* ref;                // clean spectrum S
+    cruse_cplx_layout lr;
+    const float* unp;                // noisy spectrum X
+    cruse_cplx_layout lu;
+    float* loss_rows;                // [B*T] one partial sum per frame (fixed order: the loss does not depend on how the frames are grouped)
 };
 
 struct DecPrepArgs {
@@ -70,6 +76,23 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], flo
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
                    "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+__device__ __forceinline__ float2 ld_cplx(const float* __restrict__ p, long long off, long long im_off) {
+    if (im_off == 1 && ((off & 1) == 0)) return __ldg(reinterpret_cast<const float2*>(p + off));
+    return make_float2(__ldg(p + off), __ldg(p + off + im_off));
+}
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// one bin of wo_male with |mask * X| = mask * |X| (the arithmetic of wo_male_partial_kernel<true>, loss.cu)
+__device__ __forceinline__ float wo_male_bin(float2 r, float2 u, float mk) {
+    const float mr = sqrt_approx(r.x * r.x + r.y * r.y), mu = sqrt_approx(u.x * u.x + u.y * u.y);
+    const float iam = mr * rcp_approx(mu);
+    const float w = ex2_approx(2.f * 1.4426950408889634f * rcp_approx(1.f + iam));
+    const float d = 0.30102999566398120f * lg2_approx((fabsf(mk) * mu + 1.f) * rcp_approx(mr + 1.f));
+    return w * fabsf(d);
 }
 
 // the skip values a lane adds in the epilogue of a stage (its accumulator positions), loaded one stage AHEAD of their use so that the
@@ -246,6 +269,20 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
         sk1.load(a.skip[3] + row * (C1 * F1), lane);
         convT_stage<C3, C2, F3, false>(bufB, bufA, sm + W3_OFF, sm + EP_OFF + C3, sk2, lane);
         __syncwarp();
+        // the loss inputs of this frame (bins 2i, 2i+1 for i = lane + 32 r), in flight under stage 2
+        float2 lr_[F1 / 32][2], lu_[F1 / 32][2];
+        if (a.loss_rows) {
+            const long long bb = row / a.T, tt = row - bb * a.T;
+            const long long rb = bb * a.lr.sb + tt * a.lr.st, ub = bb * a.lu.sb + tt * a.lu.st;
+#pragma unroll
+            for (int r = 0; r < F1 / 32; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int f = 2 * (lane + 32 * r) + c;
+                    lr_[r][c] = ld_cplx(a.ref, rb + f * a.lr.sf, a.lr.im_off);
+                    lu_[r][c] = ld_cplx(a.unp, ub + f * a.lu.sf, a.lu.im_off);
+                }
+        }
         convT_stage<C2, C1, F2, true>(bufA, bufB, sm + W2_OFF, sm + EP_OFF + C3 + C2, sk1, lane);
         __syncwarp();
         // ---- stage 1: ConvTranspose2d(8 -> 1) + bias + sigmoid (model/cruse_net.py:164), fp32 FMAs; lane owns the bin pairs i = lane + 32 r
@@ -253,6 +290,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
             const float* w1 = sm + W1_OFF;
             const float b1 = w1[24];
             float* mrow = a.mask + row * F0;
+            float lacc = 0.f;
 #pragma unroll
             for (int r = 0; r < F1 / 32; ++r) {
                 const int i = lane + 32 * r;
@@ -263,7 +301,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fused_kernel(const DecF
                     ve = fmaf(w1[3 * ci], x0, fmaf(w1[3 * ci + 2], xm, ve));
                     vo = fmaf(w1[3 * ci + 1], x0, vo);
                 }
-                *reinterpret_cast<float2*>(mrow + 2 * i) = make_float2(sigmoidf_(ve), sigmoidf_(vo));
+                const float m0 = sigmoidf_(ve), m1 = sigmoidf_(vo);
+                *reinterpret_cast<float2*>(mrow + 2 * i) = make_float2(m0, m1);
+                if (a.loss_rows) lacc += wo_male_bin(lr_[r][0], lu_[r][0], m0) + wo_male_bin(lr_[r][1], lu_[r][1], m1);
+            }
+            if (a.loss_rows) {
+                lacc = warp_sum(lacc);
+                if (lane == 0) a.loss_rows[row] = lacc;
             }
         }
         __syncwarp();
@@ -297,8 +341,9 @@ extern "C" int cruse_decoder_fused_prep(const float* const* w, const float* cons
 }
 
 extern "C" int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                                         const float* const* skips, const float* image, float* mask, int B, int T, int t_begin, int t_end,
-                                         int max_ctas, void* stream) {
+                                         const float* const* skips, const float* image, float* mask, const float* ref,
+                                         cruse_cplx_layout lref, const float* unproc, cruse_cplx_layout lunp, float* loss_rows, int B, int T,
+                                         int t_begin, int t_end, int max_ctas, void* stream) {
     using namespace cruse;
     CRUSE_CHECK_ARG(y2 && ln_gamma && ln_beta && skips && image && mask, "decoder_fused_range: null pointer");
     CRUSE_CHECK_ARG(B > 0 && T > 0 && t_begin >= 0 && t_begin < t_end && t_end <= T, "decoder_fused_range: bad sizes B=%d T=%d range [%d,%d)", B, T,
@@ -307,6 +352,8 @@ extern "C" int cruse_decoder_fused_range(const float* y2, const float* ln_gamma,
     DecFusedArgs a;
     a.y2 = y2; a.ln_g = ln_gamma; a.ln_b = ln_beta; a.eps = ln_eps; a.mask = mask; a.image = image;
     a.B = B; a.T = T; a.t0 = t_begin; a.t1 = t_end;
+    CRUSE_CHECK_ARG(!loss_rows || (ref && unproc), "decoder_fused_range: loss rows requested without the clean / noisy spectra");
+    a.ref = ref; a.lr = lref; a.unp = unproc; a.lu = lunp; a.loss_rows = loss_rows;
     for (int s = 0; s < 4; ++s) {
         CRUSE_CHECK_ARG(skips[s], "decoder_fused_range: null skip pointer of stage %d", 4 - s);
         a.skip[s] = skips[s];

@@ -175,6 +175,39 @@ extern "C" int cruse_wo_male_masked_partial_range(const float* ref, cruse_cplx_l
     return 0;
 }
 
+// the per-frame partial sums cruse_decoder_fused_range leaves in rows[B*T] -> loss (fixed order, double accumulation): one CTA of
+// 1024 threads, eight independent loads in flight per thread (this launch is the last one of the step: pure latency)
+namespace cruse {
+__global__ void __launch_bounds__(1024) sum_rows_kernel(const float* __restrict__ rows, int n, double scale, float* __restrict__ out) {
+    double s = 0.0;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * 1024) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i0 + u * 1024 < n) ? __ldcg(rows + i0 + u * 1024) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    __shared__ double sh[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double a = sh[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (threadIdx.x == 0) out[0] = (float)(a * scale);
+    }
+}
+}  // namespace cruse
+
+extern "C" int cruse_wo_male_finish_rows(const float* rows, int B, int T, int F, float* loss, void* stream) {
+    CRUSE_CHECK_ARG(rows && loss && B > 0 && T > 0 && F > 0 && (long long)B * T < (1ll << 31), "wo_male_finish_rows: bad arguments");
+    sum_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rows, B * T, 1.0 / ((double)B * T * F), loss);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int cruse_wo_male_finish(const void* ws, int nparts, int B, int T, int F, float* loss, void* stream) {
     CRUSE_CHECK_ARG(ws && loss && nparts > 0 && nparts <= LOSS_MAX_PARTS && B > 0 && T > 0 && F > 0, "wo_male_finish: bad arguments");
     sum_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const float*)ws, nparts, 1.0 / ((double)B * T * F), loss);

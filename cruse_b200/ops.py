@@ -354,6 +354,8 @@ def layernorm_fwd_range(x, gamma, beta, eps, residual, y, t0, t1):
 # LayerNorm 2 + the four decoder stages of the 256-bin pyramid as one launch per frame range (inference, tf32 conv mode);
 # CRUSE_FUSE_DECODER=0 keeps the five per-stage launches
 FUSE_DECODER = os.environ.get("CRUSE_FUSE_DECODER", "1") != "0"
+# ... and the frames' shares of the wo_male loss in the same launch (CRUSE_FUSE_LOSS=0: separate loss launches per range)
+FUSE_LOSS = os.environ.get("CRUSE_FUSE_LOSS", "1") != "0"
 
 
 def decoder_fused_prep(ws, biases, scales, shifts, alphas, act):
@@ -372,9 +374,10 @@ def decoder_fused_prep(ws, biases, scales, shifts, alphas, act):
     return image
 
 
-def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, max_ctas=0):
+def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, max_ctas=0, loss=None):
     """model/cruse_net.py:51,160-164 for the frames [t0,t1): y2 [B,T,1024] -> mask [B,T,256] (in place).  ``skips`` = (skip4, skip3,
-    skip2, skip1) [B,T,C,F]; ``image`` from decoder_fused_prep."""
+    skip2, skip1) [B,T,C,F]; ``image`` from decoder_fused_prep.  ``loss`` = (S, layout_S, X, layout_X, rows[B*T]): also leaves the
+    frames' shares of wo_male on est = mask * X in ``rows`` (wo_male_finish_rows sums them)."""
     B, T, D = y2.shape
     want = [(64, 16), (32, 32), (16, 64), (8, 128)]
     if D != 1024 or tuple(mask.shape[:2]) != (B, T) or mask[0, 0].numel() != 256:
@@ -385,8 +388,27 @@ def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, 
     for t in [y2, ln_gamma, ln_beta, mask, image, *skips]:
         _req(t, "decoder_fused_range tensor")
     frames = B * (t1 - t0)
-    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), _p(image), _p(mask), B, T, t0, t1,
-          int(max_ctas), _stream(), meta=(f"decoder_fused [{t0},{t1})", 4 * frames * (5 * 1024 + 256), 2 * frames * 175104))
+    if loss is not None:
+        S, lay_s, X, lay_x, rows = loss
+        for t in (S, X, rows):
+            _req(t, "decoder_fused_range loss tensor")
+        if rows.numel() < B * T:
+            raise RuntimeError(f"decoder_fused_range: loss rows hold {rows.numel()} values, need B*T = {B * T}")
+        largs = (_p(S), lay_s, _p(X), lay_x, _p(rows))
+    else:
+        zero = CplxLayout(0, 0, 0, 0)
+        largs = (None, zero, None, zero, None)
+    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), _p(image), _p(mask), *largs,
+          B, T, t0, t1, int(max_ctas), _stream(),
+          meta=(f"decoder_fused{'+loss' if loss is not None else ''} [{t0},{t1})", 4 * frames * (5 * 1024 + 256 + (4 * 256 if loss is not None else 0)),
+                2 * frames * 175104))
+
+
+def wo_male_finish_rows(rows, B, T, F):
+    """sum of the per-frame loss shares of decoder_fused_range / (B*T*F) -> 0-dim loss"""
+    loss = torch.empty((), device=rows.device, dtype=torch.float32)
+    _call("cruse_wo_male_finish_rows", _p(rows), B, T, F, _p(loss), _stream())
+    return loss
 
 
 def convT_fwd(x, w, bias, scale, shift, alpha, act, skip, Fout, want_stats=False):

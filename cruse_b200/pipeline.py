@@ -57,6 +57,7 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 ops.stft_fwd_into(clean, hann_window(n_fft, n_fft, dev), S, n_fft, hop, pad_mode)
                 s_ready = torch.cuda.Event()
                 s_ready.record(side)
+                s_events.append(s_ready)
             for st in loss_streams:
                 st.wait_event(s_ready)
             clean_started.append(True)
@@ -71,6 +72,9 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
         ws = ops.loss_workspace(dev)
         lay_s, lay_x = ops.layout_btf2(S), ops.layout_btf2(X)
         prog = {"c": 0, "p": 0, "i": 0}
+        loss_rows = torch.empty(X.shape[0] * T, device=dev, dtype=torch.float32)
+        s_events = []
+        loss_inputs = {"args": (S, lay_s, X, lay_x, loss_rows), "ready": lambda: list(s_events)}
 
         def post(mask_all, t0, t1):
             ev = torch.cuda.Event()
@@ -87,6 +91,8 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 if c1 > prog["c"]:
                     ops.mask_istft_fwd_range(X, mask_all, window, n_fft, hop, est_buf, wav_buf, prog["c"], c1)
                     prog["c"] = c1
+            if getattr(model, "_loss_fused", False):
+                return                               # the decoder launch left this range's loss shares in loss_rows
             with torch.cuda.stream(s_l):
                 # CTAs (= partial-sum slots) of this range: at least two (b, t) rows each, never fewer than ~4 per SM -- the last,
                 # short range sits on the critical path and is pure latency with few CTAs
@@ -96,7 +102,7 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 prog["p"] += nparts
 
         if ops.PIPELINE_EDGES:
-            mask = model.forward_frames(mag, post=post, after_encoder=start_clean_stft)             # cruse_net.py:147-165
+            mask = model.forward_frames(mag, post=post, after_encoder=start_clean_stft, loss_inputs=loss_inputs)   # cruse_net.py:147-165
         else:
             start_clean_stft()
             mask = model.forward_frames(mag)
@@ -109,7 +115,13 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 ev.record(st)
                 side2.wait_event(ev)
             with torch.cuda.stream(side2):
-                loss = ops.wo_male_finish(ws, prog["p"], X.shape[0], T, F)
+                if getattr(model, "_loss_fused", False):
+                    have_rows = torch.cuda.Event()   # forward_frames has joined every decoder stream into the caller's
+                    have_rows.record(main)
+                    side2.wait_event(have_rows)
+                    loss = ops.wo_male_finish_rows(loss_rows, X.shape[0], T, F)
+                else:
+                    loss = ops.wo_male_finish(ws, prog["p"], X.shape[0], T, F)
                 done = torch.cuda.Event()
                 done.record(side2)
             loss.record_stream(main)                     # made on a side stream, handed to the caller's
@@ -120,7 +132,7 @@ def forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
                 done_istft.record(st)
                 main.wait_event(done_istft)
             for st in loss_streams:
-                for t_ in (ws, S, X):
+                for t_ in (ws, S, X, loss_rows):
                     t_.record_stream(st)
             main.wait_event(done)
             if model.gru._wavefront_err is not None:

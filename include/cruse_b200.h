@@ -38,6 +38,10 @@ extern "C" {
 #define CRUSE_ACT_PRELU   2   /* optional per-channel PReLU (model/mtfaa.py:170)     */
 #define CRUSE_ACT_SIGMOID 3   /* model/cruse_net.py:164                              */
 
+/* addressing of a complex [B,T,F] tensor: element (b,t,f) has its real part at b*sb + t*st + f*sf floats, the imaginary part
+ * im_off floats further (see the loss entries below) */
+typedef struct { long long sb, st, sf, im_off; } cruse_cplx_layout;
+
 #define CRUSE_PAD_REFLECT  0  /* train_base/acoustics/feature.py:22-30 (torch.stft default) */
 #define CRUSE_PAD_CONSTANT 1  /* utils/utils.py:396                                           */
 
@@ -171,14 +175,19 @@ int cruse_layernorm_fwd_range(const float* x, const float* gamma, const float* b
  *   shift / alpha = HOST arrays of 3 device pointers (folded BatchNorm and PReLU slopes of stages 4..2; alpha may be NULL for ReLU).
  *   cruse_decoder_fused_range: y2 [B,T,1024] (GRU layer-2 output, feature = channel*16 + bin) -> mask [B,T,256]; skips = HOST array of
  *   4 device pointers: skip4 [B,T,64,16] (added to the LayerNorm output), skip3 [B,T,32,32], skip2 [B,T,16,64], skip1 [B,T,8,128];
- *   max_ctas > 0 caps the grid (running beside the recurrences).
+ *   max_ctas > 0 caps the grid (running beside the recurrences).  loss_rows (optional, with ref = clean spectrum S and unproc =
+ *   noisy spectrum X in any complex layout): the frame's share of wo_male (loss_func/loss.py:121-148) on est = mask * X over the
+ *   256 bins, one partial sum per frame, formed where the mask is produced (same per-bin arithmetic as cruse_wo_male_masked_fwd).
  * Any other geometry is an error, not a fallback (use the per-stage entry points). */
 long long cruse_decoder_fused_image_floats(void);
 int cruse_decoder_fused_prep(const float* const* w, const float* const* bias, const float* const* scale, const float* const* shift,
                              const float* const* alpha, int act, float* image, void* stream);
 int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                              const float* const* skips, const float* image, float* mask, int B, int T, int t_begin, int t_end,
+                              const float* const* skips, const float* image, float* mask, const float* ref, cruse_cplx_layout lref,
+                              const float* unproc, cruse_cplx_layout lunp, float* loss_rows, int B, int T, int t_begin, int t_end,
                               int max_ctas, void* stream);
+/* the per-frame sums loss_rows[B*T] of cruse_decoder_fused_range -> loss = sum / (B*T*F) (loss.py:147), fixed order */
+int cruse_wo_male_finish_rows(const float* rows, int B, int T, int F, float* loss, void* stream);
 
 /* ---- a4: grouped GRU.  replaces nn.GRU(H,H) x groups at model/cruse_net.py:23-31,43-50.
  *  ih GEMM: xproj[m, g, :] = x[m, g*H:(g+1)*H] . w_ih[g]^T + b_ih[g] (+ b_hh[g] for r,z rows)
@@ -264,7 +273,6 @@ int cruse_layernorm_interleave_fwd(const float* x, const float* gamma, const flo
  *  reference layout [B,2,T,F] and the internal [B,T,NF,2] are accepted without a copy.
  *  loss: device scalar.  dest (optional): gradient of the loss w.r.t. est in est's layout
  *  (same strides), unscaled by any upstream gradient.  ws: >= cruse_wo_male_ws_bytes() bytes. */
-typedef struct { long long sb, st, sf, im_off; } cruse_cplx_layout;
 int cruse_wo_male_fwd_bwd(const float* ref, cruse_cplx_layout lref, const float* est, cruse_cplx_layout lest,
                           const float* unproc, cruse_cplx_layout lunp, float* dest,
                           float* loss, void* ws, int B, int T, int F, void* stream);

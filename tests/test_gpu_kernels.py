@@ -564,3 +564,18 @@ def test_fused_decoder_equals_layernorm_plus_the_four_stages(cuda, act, B, T, rn
     assert rel_err(mask[:, sl], sep.view(B, T, 256)[:, sl]) <= 5e-4
     if rng:
         assert float(mask[:, :t0].abs().max()) == 0.0 and float(mask[:, t1:].abs().max()) == 0.0      # outside the range: untouched
+    # the same launch with the frames' wo_male shares (loss_func/loss.py:121-148 on est = mask * X) left beside the mask: same mask,
+    # and the summed rows equal the stand-alone masked loss kernel on that mask (same per-bin arithmetic, different summation order)
+    from cruse_b200.loss import wo_male_frames_masked
+    S, X = torch.randn(B, T, 257, 2, device=cuda), torch.randn(B, T, 257, 2, device=cuda)
+    rows = torch.zeros(B * T, device=cuda)
+    mask2 = torch.zeros(B, T, 256, device=cuda)
+    ops.decoder_fused_range(y2d, gd, bd, 1e-5, skd, image, mask2, t0, t1, max_ctas=cap,
+                            loss=(S, ops.layout_btf2(S), X, ops.layout_btf2(X), rows))
+    assert torch.equal(mask2, mask)
+    if not rng:
+        got_loss = ops.wo_male_finish_rows(rows, B, T, 256)
+        want_loss = wo_male_frames_masked(S, mask, X, 256)
+        assert abs(float(got_loss) - float(want_loss)) <= 2e-6 * abs(float(want_loss))
+    else:
+        assert float(rows.view(B, T)[:, :t0].abs().max()) == 0.0 and float(rows.view(B, T)[:, t1:].abs().max()) == 0.0

@@ -21,7 +21,9 @@ B, L = (64, 64000) if train else (32, 160000)
 params = list(model.parameters())
 noisy, clean = bench.synth_batch(B, L, 20260)
 noisy, clean = noisy.to(dev), clean.to(dev)
-cap = pipeline.CapturedForwardLoss(model, B, L, 512, 320) if (use_graph and not train) else None
+cap = None
+if use_graph:
+    cap = pipeline.CapturedTrainStep(model, B, L, 512, 320) if train else pipeline.CapturedForwardLoss(model, B, L, 512, 320)
 if cap is not None:
     cap.noisy.copy_(noisy); cap.clean.copy_(clean)
 

@@ -44,9 +44,9 @@ SIGNATURES = {
     "cruse_conv_skip_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 9 + [c_fp]),
     "cruse_convT_fwd_range": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
     "cruse_layernorm_fwd_range": (c_int, [c_fp, c_fp, c_fp, c_f, c_fp, c_fp] + [c_int] * 5 + [c_fp]),
-    "cruse_decoder_fused_image_floats": (C.c_longlong, []),
-    "cruse_decoder_fused_prep": (c_int, [c_pp] * 5 + [c_int, c_fp, c_fp]),
-    "cruse_decoder_fused_range": (c_int, [c_fp, c_fp, c_fp, c_f, c_pp, c_fp, c_fp, c_fp, CplxLayout, c_fp, CplxLayout, c_fp] + [c_int] * 5 + [c_fp]),
+    "cruse_decoder_fused_image_floats": (C.c_longlong, [c_int]),
+    "cruse_decoder_fused_prep": (c_int, [c_pp] * 5 + [c_int, c_fp, c_fp, c_fp, c_fp]),
+    "cruse_decoder_fused_range": (c_int, [c_fp, c_fp, c_fp, c_f, c_pp, c_int, c_fp, c_fp, c_fp, CplxLayout, c_fp, CplxLayout, c_fp] + [c_int] * 5 + [c_fp]),
     "cruse_wo_male_finish_rows": (c_int, [c_fp, c_int, c_int, c_int, c_fp, c_fp]),
     "cruse_convT_fwd": (c_int, [c_fp] * 6 + [c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_bn_finalize": (c_int, [c_fp, c_int, c_int, c_d, c_fp, c_fp, c_f, c_f] + [c_fp] * 6 + [c_fp]),

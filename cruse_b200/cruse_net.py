@@ -88,7 +88,7 @@ class GGRU(nn.Module):
             cls._side_streams[key] = tuple(torch.cuda.Stream(device=device, priority=-1) for _ in range(8))
         return cls._side_streams[key]
 
-    def plan(self, B, T, device):
+    def plan(self, B, T, device, last_chunk=0):
         """chunk boundaries + zeroed device flags of a flag-synchronised wavefront over T frames, made BEFORE the encoder runs
         so that the first chunk can start as soon as the encoder has produced its frames (``edges``); None when the
         wavefront would not run in flag mode."""
@@ -97,7 +97,9 @@ class GGRU(nn.Module):
         nch = max(2, min(self.WAVEFRONT_FLAG_CHUNKS, T // 24))
         # optional SHORT last chunk (WAVEFRONT_LAST_CHUNK frames; 0 = equal chunks, the default): what is left after layer 1 has
         # finished is proportional to it -- measured on B200 it loses all the same (32 / 16 frames: 1.51 / 1.53 vs 1.49 ms per step)
-        last = min(self.WAVEFRONT_LAST_CHUNK, T // nch)
+        # ``last_chunk``: the caller's upper bound for the last chunk (what follows layer 2 there is on the critical path, e.g. one
+        # round of the one-launch decoder); the environment knob overrides it
+        last = min(self.WAVEFRONT_LAST_CHUNK or (last_chunk if 0 < last_chunk < T // nch else 0), T // nch)
         tail = [c for c in self.WAVEFRONT_TAIL if c >= 8]
         if tail and nch >= 3 and sum(tail) <= T // 4 and nch + len(tail) <= 16:
             # equal chunks, then a run of SHORT ones: layer 2 ends one chunk + one hand-over behind layer 1, so the last chunks set the lag
@@ -494,6 +496,8 @@ class unet_2(nn.Module):
                     and self.act_kind in ("relu", "prelu"))
         dec = [] if fuse_dec else [new(B, T, self.ch[k - 1], self.freqs[k - 1]) for k in range(n, 1, -1)]
         dec_image = None
+        # skip convs 4 and 3 inside the decoder launch, from e4 / e3: no skip-conv launches are left beside the recurrences
+        fuse_skip34 = fuse_dec and ops.FUSE_SKIP34
         # the caller's wo_male inputs: the fused decoder then leaves every frame's share of the loss beside the mask (no loss launches)
         fuse_loss = fuse_dec and loss_inputs is not None and F == 256 and ops.FUSE_LOSS
         self._loss_fused = fuse_loss
@@ -502,7 +506,8 @@ class unet_2(nn.Module):
             dec_image = ops.decoder_fused_prep(
                 [getattr(self, nm).weight for nm in names], [getattr(self, nm).bias for nm in names],
                 [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
-                [self._alpha(f"act{k}_t") for k in range(n, 1, -1)] if self.act_kind == "prelu" else None, self.act_kind)
+                [self._alpha(f"act{k}_t") for k in range(n, 1, -1)] if self.act_kind == "prelu" else None, self.act_kind,
+                self.skip_connect_4.weight if fuse_skip34 else None, self.skip_connect_3.weight if fuse_skip34 else None)
         mask_buf = new(B, T, 1, F)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         layer_sms = 8 * self.gru.groups * ((B + 31) // 32)
@@ -542,8 +547,8 @@ class unet_2(nn.Module):
                 try:
                     with torch.cuda.stream(s_skip):
                         for k in range(n, 0, -1):
-                            if k in fused:
-                                continue                                   # came out of encoder stage k+1 already
+                            if k in fused or (fuse_skip34 and k >= n - 1):
+                                continue                                   # came out of encoder stage k+1 already / is made inside the decoder launch
                             wk = getattr(unet, f"skip_connect_{k}").weight
                             ops.conv_fwd_range(enc[k - 1], wk, None, None, None, None, "none", 1, 1, B, T, skip_out[k - 1], t0, t1,
                                                in_tm=(k == n))
@@ -565,8 +570,9 @@ class unet_2(nn.Module):
                     for ev in loss_inputs["ready"]():        # the clean-speech spectrum (made on the caller's side stream)
                         torch.cuda.current_stream(dev).wait_event(ev)
                     larg = loss_inputs["args"]
-                ops.decoder_fused_range(y2, ln2.weight, ln2.bias, ln2.eps, [skip_out[k - 1] for k in range(n, 0, -1)], dec_image, mask_buf,
-                                        t0, t1, cap, loss=larg)
+                sk = [enc[n - 1], enc[n - 2], skip_out[1], skip_out[0]] if fuse_skip34 else [skip_out[k - 1] for k in range(n, 0, -1)]
+                ops.decoder_fused_range(y2, ln2.weight, ln2.bias, ln2.eps, sk, dec_image, mask_buf, t0, t1, cap, loss=larg,
+                                        skip_convs=fuse_skip34)
                 if post is not None:
                     post(mask_buf.view(B, T, F), t0, t1)
                     unet._post_ranges.append((t0, t1))
@@ -628,7 +634,13 @@ class unet_2(nn.Module):
         if not train:                                   # all eval-mode BatchNorm folds of the pass in one launch
             names = [f"bn{k}" for k in range(1, n + 1)] + [f"bn{k}_t" for k in range(n, 1, -1)]
             folds = dict(zip(names, ops.bn_fold_many([getattr(self, nm) for nm in names])))
-        plan = self.gru.plan(B, T, mag.device) if (overlap and ops.PIPELINE_EDGES) else None
+        # the decoder launch with the skip convs inside keeps 12 frames in flight per SM: the last wavefront chunk is cut so that its
+        # frames are ONE round of that launch
+        one_round = 0
+        if (ops.FUSE_DECODER and ops.FUSE_SKIP34 and n == 4 and tuple(self.ch) == (1, 8, 16, 32, 64) and F == 256
+                and self.act_kind in ("relu", "prelu")):
+            one_round = (torch.cuda.get_device_properties(mag.device).multi_processor_count * 12) // B
+        plan = self.gru.plan(B, T, mag.device, last_chunk=one_round) if (overlap and ops.PIPELINE_EDGES) else None
         self._post_ranges = []
         self._loss_fused = False
         if plan is not None:

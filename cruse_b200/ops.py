@@ -356,35 +356,49 @@ def layernorm_fwd_range(x, gamma, beta, eps, residual, y, t0, t1):
 FUSE_DECODER = os.environ.get("CRUSE_FUSE_DECODER", "1") != "0"
 # ... and the frames' shares of the wo_male loss in the same launch (CRUSE_FUSE_LOSS=0: separate loss launches per range)
 FUSE_LOSS = os.environ.get("CRUSE_FUSE_LOSS", "1") != "0"
+# ... and skip convs 4 and 3 from the encoder outputs (CRUSE_FUSE_SKIP34=0: two separate skip-conv launches beside the recurrences)
+FUSE_SKIP34 = os.environ.get("CRUSE_FUSE_SKIP34", "1") != "0"
 
 
-def decoder_fused_prep(ws, biases, scales, shifts, alphas, act):
+def decoder_fused_prep(ws, biases, scales, shifts, alphas, act, wskip4=None, wskip3=None):
     """the constants of the fused decoder as its shared-memory image (once per forward pass, after the BatchNorm fold): ``ws`` /
-    ``biases`` = conv4_t .. conv1_t, ``scales`` / ``shifts`` / ``alphas`` = stages 4..2 -> image tensor for decoder_fused_range"""
+    ``biases`` = conv4_t .. conv1_t, ``scales`` / ``shifts`` / ``alphas`` = stages 4..2 -> image tensor for decoder_fused_range.
+    ``wskip4`` / ``wskip3`` (skip_connect_4 / _3 weights): the image for ``skip_convs=True`` launches."""
+    if (wskip4 is None) != (wskip3 is None):
+        raise RuntimeError("decoder_fused_prep: wskip4 and wskip3 come together or not at all")
+    if wskip4 is not None and (tuple(wskip4.shape) != (64, 64, 1, 3) or tuple(wskip3.shape) != (32, 32, 1, 3)):
+        raise RuntimeError(f"decoder_fused_prep: skip conv weights {tuple(wskip4.shape)} / {tuple(wskip3.shape)} do not match the 256-bin pyramid")
     want = [(64, 32), (32, 16), (16, 8), (8, 1)]
     for k, (w, (ci, co)) in enumerate(zip(ws, want)):
         if tuple(w.shape) != (ci, co, 1, 3):
             raise RuntimeError(f"decoder_fused_prep: stage {4 - k}: weight {tuple(w.shape)} does not match the 256-bin pyramid")
     for t in [*ws, *[b for b in biases if b is not None], *scales, *shifts, *[a for a in (alphas or []) if a is not None]]:
         _req(t, "decoder_fused_prep tensor")
-    image = torch.empty(int(lib().cruse_decoder_fused_image_floats()), device=ws[0].device, dtype=torch.float32)
+    for t in (wskip4, wskip3):
+        _req(t, "decoder_fused_prep skip weight")
+    image = torch.empty(int(lib().cruse_decoder_fused_image_floats(int(wskip4 is not None))), device=ws[0].device, dtype=torch.float32)
     tb = (C.c_void_p * 4)(*[b.data_ptr() if b is not None else None for b in biases])
     ta = (C.c_void_p * 3)(*[a.data_ptr() if a is not None else None for a in alphas]) if alphas is not None else None
-    _call("cruse_decoder_fused_prep", _ptr_table(ws), tb, _ptr_table(scales), _ptr_table(shifts), ta, ACT[act], _p(image), _stream())
+    _call("cruse_decoder_fused_prep", _ptr_table(ws), tb, _ptr_table(scales), _ptr_table(shifts), ta, ACT[act], _p(wskip4), _p(wskip3),
+          _p(image), _stream())
     return image
 
 
-def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, max_ctas=0, loss=None):
+def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, max_ctas=0, loss=None, skip_convs=False):
     """model/cruse_net.py:51,160-164 for the frames [t0,t1): y2 [B,T,1024] -> mask [B,T,256] (in place).  ``skips`` = (skip4, skip3,
     skip2, skip1) [B,T,C,F]; ``image`` from decoder_fused_prep.  ``loss`` = (S, layout_S, X, layout_X, rows[B*T]): also leaves the
-    frames' shares of wo_male on est = mask * X in ``rows`` (wo_male_finish_rows sums them)."""
+    frames' shares of wo_male on est = mask * X in ``rows`` (wo_male_finish_rows sums them).  ``skip_convs``: skips[0] / skips[1] are
+    the encoder outputs e4 (TIME-MAJOR [T,B,64,16]) / e3 ([B,T,32,32]) and skip convs 4 / 3 run inside the launch (image prepared
+    with their weights)."""
     B, T, D = y2.shape
     want = [(64, 16), (32, 32), (16, 64), (8, 128)]
     if D != 1024 or tuple(mask.shape[:2]) != (B, T) or mask[0, 0].numel() != 256:
         raise RuntimeError(f"decoder_fused_range: y2 {tuple(y2.shape)} / mask {tuple(mask.shape)}: the fused decoder is built for the 256-bin pyramid")
     for k, (sk, (c, f)) in enumerate(zip(skips, want)):
-        if tuple(sk.shape) != (B, T, c, f):
+        if tuple(sk.shape) != ((T, B, c, f) if (skip_convs and k == 0) else (B, T, c, f)):
             raise RuntimeError(f"decoder_fused_range: stage {4 - k}: skip {tuple(sk.shape)} does not match the pyramid")
+    if image.numel() != int(lib().cruse_decoder_fused_image_floats(int(bool(skip_convs)))):
+        raise RuntimeError("decoder_fused_range: the image was prepared for the other skip_convs mode")
     for t in [y2, ln_gamma, ln_beta, mask, image, *skips]:
         _req(t, "decoder_fused_range tensor")
     frames = B * (t1 - t0)
@@ -398,10 +412,10 @@ def decoder_fused_range(y2, ln_gamma, ln_beta, eps, skips, image, mask, t0, t1, 
     else:
         zero = CplxLayout(0, 0, 0, 0)
         largs = (None, zero, None, zero, None)
-    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), _p(image), _p(mask), *largs,
+    _call("cruse_decoder_fused_range", _p(y2), _p(ln_gamma), _p(ln_beta), float(eps), _ptr_table(skips), int(bool(skip_convs)), _p(image), _p(mask), *largs,
           B, T, t0, t1, int(max_ctas), _stream(),
-          meta=(f"decoder_fused{'+loss' if loss is not None else ''} [{t0},{t1})", 4 * frames * (5 * 1024 + 256 + (4 * 256 if loss is not None else 0)),
-                2 * frames * 175104))
+          meta=(f"decoder_fused{'+skip34' if skip_convs else ''}{'+loss' if loss is not None else ''} [{t0},{t1})",
+                4 * frames * (5 * 1024 + 256 + (4 * 256 if loss is not None else 0)), 2 * frames * (175104 + (294912 if skip_convs else 0))))
 
 
 def wo_male_finish_rows(rows, B, T, F):

@@ -178,14 +178,18 @@ int cruse_layernorm_fwd_range(const float* x, const float* gamma, const float* b
  *   max_ctas > 0 caps the grid (running beside the recurrences).  loss_rows (optional, with ref = clean spectrum S and unproc =
  *   noisy spectrum X in any complex layout): the frame's share of wo_male (loss_func/loss.py:121-148) on est = mask * X over the
  *   256 bins, one partial sum per frame, formed where the mask is produced (same per-bin arithmetic as cruse_wo_male_masked_fwd).
+ *   skip_convs = 1 (image prepared with wskip4 = skip_connect_4.weight [64,64,1,3] and wskip3 = skip_connect_3.weight [32,32,1,3],
+ *   model/cruse_net.py:143): the two deepest skip convs (:154-155) are computed inside the launch from the encoder outputs --
+ *   skips[0] = e4 TIME-MAJOR [T,B,64,16] (the GRU input as the last encoder stage writes it), skips[1] = e3 [B,T,32,32]; their
+ *   skip tensors never exist in HBM and the two skip-conv launches disappear.
  * Any other geometry is an error, not a fallback (use the per-stage entry points). */
-long long cruse_decoder_fused_image_floats(void);
+long long cruse_decoder_fused_image_floats(int with_skip_convs);
 int cruse_decoder_fused_prep(const float* const* w, const float* const* bias, const float* const* scale, const float* const* shift,
-                             const float* const* alpha, int act, float* image, void* stream);
+                             const float* const* alpha, int act, const float* wskip4, const float* wskip3, float* image, void* stream);
 int cruse_decoder_fused_range(const float* y2, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                              const float* const* skips, const float* image, float* mask, const float* ref, cruse_cplx_layout lref,
-                              const float* unproc, cruse_cplx_layout lunp, float* loss_rows, int B, int T, int t_begin, int t_end,
-                              int max_ctas, void* stream);
+                              const float* const* skips, int skip_convs, const float* image, float* mask, const float* ref,
+                              cruse_cplx_layout lref, const float* unproc, cruse_cplx_layout lunp, float* loss_rows, int B, int T,
+                              int t_begin, int t_end, int max_ctas, void* stream);
 /* the per-frame sums loss_rows[B*T] of cruse_decoder_fused_range -> loss = sum / (B*T*F) (loss.py:147), fixed order */
 int cruse_wo_male_finish_rows(const float* rows, int B, int T, int F, float* loss, void* stream);
 

@@ -19,16 +19,20 @@ scs = [torch.ones(chans[k + 1], device=dev) for k in range(3)]
 shs = [torch.zeros(chans[k + 1], device=dev) for k in range(3)]
 mask = torch.zeros(B, T, 256, device=dev)
 flush = torch.empty(64 << 20, device=dev)
-image = ops.decoder_fused_prep(ws, bs, scs, shs, None, "relu")
+SKC = len(sys.argv) > 3 and sys.argv[3] == "skc"
+wsk4, wsk3 = torch.randn(64, 64, 1, 3, device=dev) / 192 ** 0.5, torch.randn(32, 32, 1, 3, device=dev) / 96 ** 0.5
+image = ops.decoder_fused_prep(ws, bs, scs, shs, None, "relu", wsk4 if SKC else None, wsk3 if SKC else None)
+if SKC:
+    skips[0] = skips[0].transpose(0, 1).contiguous()
 for _ in range(3):
-    ops.decoder_fused_range(y2, g, b_, 1e-5, skips, image, mask, 0, T)
+    ops.decoder_fused_range(y2, g, b_, 1e-5, skips, image, mask, 0, T, skip_convs=SKC)
 torch.cuda.synchronize()
 ts = []
 for _ in range(reps):
     flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    ops.decoder_fused_range(y2, g, b_, 1e-5, skips, image, mask, 0, T)
+    ops.decoder_fused_range(y2, g, b_, 1e-5, skips, image, mask, 0, T, skip_convs=SKC)
     b.record()
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b) * 1e3)

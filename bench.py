@@ -324,9 +324,12 @@ def run_ours(args):
     host_binding = hostio.bind_near_gpu(local, local, local_world) if not args.no_bind else {"why_not": "--no-bind"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "INFO")              # the communicator line ("comm ... nranks N") on stderr: the collective is observable
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # NCCL's own init log ("comm ... nranks N ... Init COMPLETE") on STDERR: the collective is observable, stdout stays one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            print(f"[bench] NCCL communicator: backend nccl {'.'.join(map(str, torch.cuda.nccl.version()))}, nranks {world}", file=sys.stderr)
     if args.gpus != world and rank == 0:
         print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
@@ -346,7 +349,8 @@ def run_ours(args):
         distrib.broadcast_model(model)
     bn_state0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if train else None
     noisy_h, clean_h = synth_batch(B, L, 20260 + rank)
-    noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
+    noisy_h, staging_kind = hostio.staging_like(noisy_h, args.wc)
+    clean_h, _ = hostio.staging_like(clean_h, args.wc)
     noisy, clean = noisy_h.to(dev), clean_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     params = [p for p in model.parameters()]
@@ -496,6 +500,7 @@ def run_ours(args):
                         "GBps_all_ranks": world * e2e["h2d_bytes_per_step"] / (float(t.item()) * 1e-3) / 1e9,
                         "note": "pinned host -> device copy of one step's inputs, every rank copying at the same time, slowest rank"}
     e2e["host_binding"] = host_binding
+    e2e["staging"] = staging_kind
     del stage
 
     # ---- per-kernel device times of one step (CUDA events on the launching stream) -> roofline
@@ -596,6 +601,7 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=0,
                     help="--impl reference: clips per step of the CPU run (0 = the whole workload batch, i.e. the same config as our arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wc", action="store_true", help="e2e staging buffers in write-combined pinned memory (cudaHostAllocWriteCombined)")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the process / its pinned memory near its GPU")
     ap.add_argument("--no-train-block", action="store_true", help="infer workload: skip the cfg-3/cfg-4 train step + all_reduce block")
     ap.add_argument("--no-graph", action="store_true", help="inference: launch eagerly instead of replaying the captured CUDA graph")

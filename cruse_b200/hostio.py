@@ -84,3 +84,30 @@ def bind_near_gpu(device_index: int, local_rank: int = 0, local_world: int = 1) 
     except Exception as e:  # noqa: BLE001
         rep["why_not"] = f"sched_setaffinity: {e!r}"
     return rep
+
+
+_wc_keep = []
+
+
+def staging_like(t, write_combined=False):
+    """a page-locked HOST copy of ``t`` for the HOST-buffer entry points.  ``write_combined``: cudaHostAllocWriteCombined memory -- the
+    CPU writes it through write-combining buffers and never caches it, so the GPU's DMA reads do not snoop the CPU caches (NVIDIA's
+    advice for buffers the host only writes and the device only reads, which is what an input staging buffer is); reading it back on
+    the host is slow.  Falls back to ordinary pinned memory (and says so) when the runtime call is unavailable."""
+    import torch
+    if not write_combined:
+        return t.pin_memory(), "pinned"
+    try:
+        rt = ctypes.CDLL("libcudart.so.12")
+        ptr = ctypes.c_void_p()
+        nbytes = t.numel() * t.element_size()
+        rc = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(nbytes), ctypes.c_uint(0x04))     # cudaHostAllocWriteCombined
+        if rc != 0:
+            raise RuntimeError(f"cudaHostAlloc rc={rc}")
+        buf = (ctypes.c_byte * nbytes).from_address(ptr.value)
+        out = torch.frombuffer(buf, dtype=t.dtype).view(t.shape)
+        _wc_keep.append((buf, ptr))              # lives as long as the process (a staging buffer is allocated once)
+        out.copy_(t)
+        return out, "write_combined"
+    except Exception as e:  # noqa: BLE001
+        return t.pin_memory(), f"pinned (write-combined unavailable: {e!r})"

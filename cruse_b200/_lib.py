@@ -112,6 +112,7 @@ SIGNATURES = {
     "cruse_rir_conv": (c_int, [c_fp, c_fp, c_fp, c_int, c_int, c_int, c_ll, c_fp]),
     "cruse_snr_mix_ws_bytes": (C.c_size_t, [c_int]),
     "cruse_snr_mix": (c_int, [c_fp] * 7 + [c_int, c_int, c_f, c_fp]),
+    "cruse_pcm16_to_float": (c_int, [c_fp, c_fp, C.c_longlong, c_fp]),
     "cruse_transpose_gcm": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_int, c_ll, c_fp]),
 }
 

@@ -251,3 +251,41 @@ extern "C" int cruse_snr_mix(const float* clean, const float* noise, const float
     CRUSE_LAUNCH_OK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// 16-bit PCM -> float32 on the device: out = in / 32768, the conversion soundfile / librosa apply when the reference reads a wav file
+// (dataset/dataset.py:20, train_base/acoustics/feature.py:110-114).  The HOST-buffer entry points take the samples in the files' own
+// format, so a step moves half the bytes over PCIe (the limit of an 8-GPU box: DESIGN.md section 6).  Eight samples per thread.
+// ---------------------------------------------------------------------------------------------
+namespace cruse {
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const short* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+    const long long n8 = n >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float4 o[2];
+        float* of = reinterpret_cast<float*>(o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            of[2 * k] = (float)(short)(w[k] & 0xffff) * scale;
+            of[2 * k + 1] = (float)(short)(w[k] >> 16) * scale;
+        }
+        reinterpret_cast<float4*>(out)[2 * i] = o[0];
+        reinterpret_cast<float4*>(out)[2 * i + 1] = o[1];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) out[(n8 << 3) + threadIdx.x] = (float)in[(n8 << 3) + threadIdx.x] * scale;
+}
+}  // namespace cruse
+
+extern "C" int cruse_pcm16_to_float(const short* in, float* out, long long n, void* stream) {
+    using namespace cruse;
+    CRUSE_CHECK_ARG(in && out && n > 0, "pcm16_to_float: null pointer / empty input");
+    CRUSE_CHECK_ARG(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "pcm16_to_float: buffers must be 16-byte aligned");
+    long long blocks = ((n >> 3) + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pcm16_to_float_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, 1.0f / 32768.0f);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}

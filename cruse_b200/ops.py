@@ -1010,3 +1010,13 @@ PIPELINE_EDGES = os.environ.get("CRUSE_PIPELINE_EDGES", "1") != "0"
 # run the skip convs (and the clean-speech STFT) on a low-priority side stream beside the GRU wavefront
 OVERLAP_SKIPS = os.environ.get("CRUSE_OVERLAP_SKIPS", "1") != "0"
 SKIP_MAX_CTAS = int(os.environ.get("CRUSE_SKIP_MAX_CTAS", "0"))     # 0 = no cap (measured best on B200: 1.90 vs 1.94 ms at 80)
+
+
+def pcm16_to_float(src, dst):
+    """int16 PCM samples (device) -> float32 = src / 32768 (what soundfile / librosa return for a 16-bit wav file), in ``dst``"""
+    if src.dtype != torch.int16 or dst.dtype != torch.float32 or src.numel() != dst.numel() or not src.is_cuda or not dst.is_cuda:
+        raise RuntimeError("pcm16_to_float: need an int16 and a float32 CUDA tensor of the same size")
+    if not (src.is_contiguous() and dst.is_contiguous()):
+        raise RuntimeError("pcm16_to_float: contiguous tensors only")
+    _call("cruse_pcm16_to_float", src.data_ptr(), _p(dst), src.numel(), _stream())
+    return dst

@@ -247,15 +247,25 @@ class CapturedForwardLoss:
         return self._stage
 
     def prefetch(self, noisy_host, clean_host):
-        """start the asynchronous H2D copy of a (pinned) host batch on the copy stream; returns a ticket for run_prefetched."""
+        """start the asynchronous H2D copy of a (pinned) host batch on the copy stream; returns a ticket for run_prefetched.
+        Host tensors are float32 (what the reference's DataLoader yields) or int16 PCM (what its wav files hold)."""
         stage = self._staging()
         i = self._next
         self._next ^= 1
         st = self._copy_stream
         st.wait_event(self._consumed[i])                  # the previous user of this staging pair has been consumed
         with torch.cuda.stream(st):
-            stage[i][0].copy_(noisy_host, non_blocking=True)
-            stage[i][1].copy_(clean_host, non_blocking=True)
+            for dst, src in zip(stage[i], (noisy_host, clean_host)):
+                if src.dtype == torch.int16:
+                    # 16-bit PCM (the wav files' own sample format): half the bytes over PCIe, widened on the device exactly as
+                    # soundfile / librosa widen it on the host (x / 32768)
+                    if not hasattr(self, "_pcm"):
+                        self._pcm = {}
+                    raw = self._pcm.setdefault((i, id(dst)), torch.empty(dst.shape, device=dst.device, dtype=torch.int16))
+                    raw.copy_(src, non_blocking=True)
+                    ops.pcm16_to_float(raw, dst)
+                else:
+                    dst.copy_(src, non_blocking=True)
             self._ready[i].record(st)
         return i
 

@@ -429,6 +429,10 @@ int cruse_rir_conv(const float* x, const float* rir, float* y, int B, int L, int
 size_t cruse_snr_mix_ws_bytes(int B);
 int cruse_snr_mix(const float* clean, const float* noise, const float* snr_db, const float* level_db, float* noisy_out,
                   float* clean_out, void* ws, int B, int L, float eps, void* stream);
+/* 16-bit PCM samples -> float32, out = in / 32768: the conversion soundfile / librosa apply when the reference reads a wav file
+ * (dataset/dataset.py:20, train_base/acoustics/feature.py:110-114), on the device, so that the HOST-buffer entry points can take the
+ * samples in the files' own format (half the bytes per step over PCIe).  16-byte aligned buffers. */
+int cruse_pcm16_to_float(const short* in, float* out, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,3 +50,23 @@ def test_snr_mix_with_rir_matches_reference_and_oracle(cuda, golden_dir):
         assert rel_err(got_n[b], wn) <= 1e-4 and rel_err(got_c[b], wc) <= 1e-4
         rms = float((got_n[b] ** 2).mean().sqrt())
         assert abs(20 * np.log10(rms) - float(lvl[b])) <= 1e-3
+
+
+def test_pcm16_host_buffers_through_the_prefetch_entry(cuda):
+    """16-bit PCM host buffers (the wav files' sample format) through CapturedForwardLoss.prefetch: widened on the device as
+    soundfile / librosa widen them on the host (x / 32768, dataset/dataset.py:20) -- bit-identical to feeding the float32 values."""
+    from cruse_b200 import ops, pipeline
+    from cruse_b200.cruse_net import unet_2
+    g = torch.Generator().manual_seed(9)
+    pcm = torch.randint(-20000, 20000, (2, 16003), generator=g, dtype=torch.int16)
+    raw, out = pcm.to(cuda), torch.empty(2, 16003, device=cuda)
+    ops.pcm16_to_float(raw, out)
+    assert torch.equal(out.cpu(), pcm.float() / 32768.0)
+    model = unet_2(in_feat=256).to(cuda).eval()
+    B, L = 3, 32000
+    n16 = torch.randint(-3000, 3000, (B, L), generator=g, dtype=torch.int16)
+    c16 = torch.randint(-2000, 2000, (B, L), generator=g, dtype=torch.int16)
+    cap = pipeline.CapturedForwardLoss(model, B, L, 512, 320)
+    l_pcm = float(cap.run_prefetched(cap.prefetch(n16.pin_memory(), c16.pin_memory()))[0])
+    l_f32 = float(cap.run_prefetched(cap.prefetch((n16.float() / 32768.0).pin_memory(), (c16.float() / 32768.0).pin_memory()))[0])
+    assert l_pcm == l_f32

@@ -503,11 +503,16 @@ class unet_2(nn.Module):
         self._loss_fused = fuse_loss
         if fuse_dec:
             names = [f"conv{k}_t" for k in range(n, 0, -1)]
-            dec_image = ops.decoder_fused_prep(
-                [getattr(self, nm).weight for nm in names], [getattr(self, nm).bias for nm in names],
-                [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
-                [self._alpha(f"act{k}_t") for k in range(n, 1, -1)] if self.act_kind == "prelu" else None, self.act_kind,
-                self.skip_connect_4.weight if fuse_skip34 else None, self.skip_connect_3.weight if fuse_skip34 else None)
+            prep_ev = torch.cuda.Event()
+            prep_ev.record(main)                          # the BatchNorm folds are through
+            s_skip.wait_event(prep_ev)
+            with torch.cuda.stream(s_skip):               # off the head of the step: nothing needs the images before the first decoder group
+                pargs = ([getattr(self, nm).weight for nm in names], [getattr(self, nm).bias for nm in names],
+                         [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
+                         [self._alpha(f"act{k}_t") for k in range(n, 1, -1)] if self.act_kind == "prelu" else None, self.act_kind)
+                dec_image = ops.decoder_fused_prep(*pargs, self.skip_connect_4.weight if fuse_skip34 else None,
+                                                   self.skip_connect_3.weight if fuse_skip34 else None)
+                dec_image.record_stream(main)
         mask_buf = new(B, T, 1, F)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         layer_sms = 8 * self.gru.groups * ((B + 31) // 32)
@@ -547,8 +552,10 @@ class unet_2(nn.Module):
                 try:
                     with torch.cuda.stream(s_skip):
                         for k in range(n, 0, -1):
-                            if k in fused or (fuse_skip34 and k >= n - 1):
-                                continue                                   # came out of encoder stage k+1 already / is made inside the decoder launch
+                            if k in fused:
+                                continue                                   # came out of encoder stage k+1 already
+                            if fuse_skip34 and k >= n - 1:
+                                continue                                   # made inside the decoder launches
                             wk = getattr(unet, f"skip_connect_{k}").weight
                             ops.conv_fwd_range(enc[k - 1], wk, None, None, None, None, "none", 1, 1, B, T, skip_out[k - 1], t0, t1,
                                                in_tm=(k == n))
@@ -570,6 +577,8 @@ class unet_2(nn.Module):
                     for ev in loss_inputs["ready"]():        # the clean-speech spectrum (made on the caller's side stream)
                         torch.cuda.current_stream(dev).wait_event(ev)
                     larg = loss_inputs["args"]
+                # (measured and dropped: the last group on the 16-frames-per-SM launch with its skip tensors made by two small early
+                # skip-conv launches -- 1.014 vs 0.995 ms per step)
                 sk = [enc[n - 1], enc[n - 2], skip_out[1], skip_out[0]] if fuse_skip34 else [skip_out[k - 1] for k in range(n, 0, -1)]
                 ops.decoder_fused_range(y2, ln2.weight, ln2.bias, ln2.eps, sk, dec_image, mask_buf, t0, t1, cap, loss=larg,
                                         skip_convs=fuse_skip34)

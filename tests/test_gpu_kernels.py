@@ -258,7 +258,9 @@ def test_grouped_gru_layer_matches_nn_gru(cuda, G, H, B, T, mode, tol):
     assert rel_err(got_h, hT) <= tol
     if mode == "tf32":   # saved gates (for backward) are consistent with the outputs: h_t = (1-z) n + z h_{t-1}
         y2, gates = ops.gru_seq_fwd(xproj, w_hh, b_hh, B, T, interleave=False, h0=h0.to(cuda), mode=mode, want_gates=True)
-        assert torch.equal(y2, got_cat)
+        # (the launch that saves gates evaluates them with ex2 / rcp, the inference launch with one tanh.approx per gate: same
+        # recurrence to the gate functions' approximation error, gated like everything tf32 at 1e-3)
+        assert rel_err(y2, got_cat) <= 1e-3 and rel_err(y2, y_cat) <= tol
         r, z, n, hn = gates.unbind(3)                                               # [B,T,G,H] each
         hprev = torch.cat([h0.to(cuda).permute(1, 0, 2).unsqueeze(1), y2.view(B, T, G, H)[:, :-1]], dim=1)
         assert rel_err((1 - z) * n + z * hprev, y2.view(B, T, G, H)) <= 1e-6

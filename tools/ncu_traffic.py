@@ -3,7 +3,7 @@ profiles/ncu_traffic.json, keyed by the C-ABI call bench.py reports.   python to
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CALL_OF = {"gru_seq_tc_kernel": ["gru_seq_flagged_tc", "gru_seq_fwd_tc", "gru_seq_chunk_tc"], "gemm_tn_tc_kernel": ["gemm_tn_tc"],
+CALL_OF = {"decoder_fused_kernel": ["decoder_fused_range"], "gru_seq_tc_kernel": ["gru_seq_flagged_tc", "gru_seq_fwd_tc", "gru_seq_chunk_tc"], "gemm_tn_tc_kernel": ["gemm_tn_tc"],
            "gemm_astat_tc_kernel": ["gru_ih_gemm_tc"], "layernorm_fwd_kernel": ["layernorm_fwd"], "stft_fwd_kernel": ["stft_fwd_generic"],
            "stft512_fwd_kernel": ["stft_fwd"], "mask_istft_kernel": ["mask_istft_fwd_generic"], "mask_istft512_kernel": ["mask_istft_fwd"],
            "wo_male_partial_kernel": ["wo_male_masked_fwd"], "gru_bwd_tc_kernel": ["gru_seq_bwd_tc"]}

@@ -52,12 +52,12 @@ with open(out, "w") as f:
     f.write(f"SASS evidence for `cruse_b200/libcruse_sm100.so` (sm_100a; `cuobjdump -sass`, {len(rows)} kernels, made by `tools/sass_evidence.py`)\n\n")
     f.write("UTCHMMA = tcgen05.mma (kind::tf32 and kind::f16 share the mnemonic; the operand kind is in the instruction descriptor), UTCBAR = tcgen05.commit, "
             "LDTM / STTM = tcgen05.ld / tcgen05.st, UTMALDG = TMA tensor load, UBLKCP = bulk copy, STAS = st.async into a peer CTA's shared memory, "
-            "SYNCS = mbarrier operations.  Kernels without any of these are the streaming (HBM-bound) kernels.\n\n")
-    f.write("| kernel | instr | UTCHMMA | UTCBAR | LDTM | STTM | UTMALDG | UBLKCP | STAS | SYNCS | MUFU (kinds) | LDG.128 | STG.128 | FFMA |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
+            "SYNCS = mbarrier operations, HMMA = warp-level mma.sync (the one-warp-per-frame fused decoder).  Kernels without any of these are the streaming (HBM-bound) kernels.\n\n")
+    f.write("| kernel | instr | UTCHMMA | UTCBAR | LDTM | STTM | UTMALDG | UBLKCP | STAS | SYNCS | HMMA (mma.sync) | MUFU (kinds) | LDG.128 | STG.128 | FFMA |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
     for n, ni, c, kinds in rows:
         mu = " ".join(f"{k}:{v}" for k, v in sorted(kinds.items())) or "-"
         f.write(f"| `{n}` | {ni} | {c['UTCHMMA'] or ''} | {c['UTCBAR'] or ''} | {c['LDTM'] or ''} | {c['STTM'] or ''} | {c['UTMALDG'] or ''} | {c['UBLKCP'] or ''} | {c['STAS'] or ''} | "
-                f"{c['SYNCS'] or ''} | {mu} | {c['LDG.E.128'] or ''} | {c['STG.E.128'] or ''} | {c['FFMA'] or ''} |\n")
+                f"{c['SYNCS'] or ''} | {c['HMMA'] or ''} | {mu} | {c['LDG.E.128'] or ''} | {c['STG.E.128'] or ''} | {c['FFMA'] or ''} |\n")
     tot = collections.Counter()
     for _, _, c, _ in rows:
         tot.update(c)

@@ -300,9 +300,11 @@ class GGRU(nn.Module):
                 and 2 * self.groups * ((B + 31) // 32) <= ops.gru_seq_max_clusters(self.hidden_size // self.groups))
 
     def forward_frames(self, x, residual=None, state=None, want_state=False, side=None, time_major=False, plan=None,
-                       around=None):
+                       around=None, skip_ln2=False):
         """x [B,T,D] frame-major ([T,B,D] with ``time_major``, wavefront path only); the result is always [B,T,D].
-        state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence (streaming, model/based_model/cust_conv.py:303-325)."""
+        state = (h1 [G,B,H], h2 [G,B,H]) carries the recurrence (streaming, model/based_model/cust_conv.py:303-325).
+        ``skip_ln2`` (layer-by-layer path only): return the output of GRU layer 2 -- the caller's one-launch decoder applies
+        LayerNorm 2 + residual itself."""
         _need_cuda(x, "GGRU")
         if time_major:
             T, B, D = x.shape
@@ -312,6 +314,8 @@ class GGRU(nn.Module):
             raise RuntimeError(f"GGRU: feature size {D} != hidden_size {self.hidden_size}")
         self._wavefront_err = None          # set by a flag-synchronised wavefront: device flag "a bounded spin timed out"
         if self.uses_wavefront(B, T, state, want_state):
+            if skip_ln2:
+                raise RuntimeError("GGRU: skip_ln2 is an option of the layer-by-layer path")
             return self._wavefront(x, residual, side, time_major, plan, around)
         if side is not None or time_major or around is not None:
             raise RuntimeError("GGRU: side work / time-major input need the wavefront path")
@@ -323,7 +327,7 @@ class GGRU(nn.Module):
         z1 = ops.layernorm_fwd(y1, self.ln1.weight, self.ln1.bias, self.ln1.eps)
         r2 = self._layer(z1.view(B * T, D), self.gru_list2, B, T, False, h2, want_state)
         y2, n2 = r2 if want_state else (r2, None)
-        out = ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)
+        out = y2 if skip_ln2 else ops.layernorm_fwd(y2, self.ln2.weight, self.ln2.bias, self.ln2.eps, residual=residual)
         return (out, (n1, n2)) if want_state else out
 
     def forward(self, x):
@@ -704,15 +708,29 @@ class unet_2(nn.Module):
                     ops.set_conv_max_ctas(0)
                 return skips[n - 1].view(B, T, D), ev4
 
+        # layer-by-layer eval path (streaming state carry, short inputs): LayerNorm 2 + skip 4 + the whole decoder as ONE launch
+        fuse_tail = (not train and not overlap and ops.FUSE_DECODER and ops.get_conv_mode() == "tf32" and n == 4 and F == 256
+                     and tuple(self.ch) == (1, 8, 16, 32, 64) and self.act_kind in ("relu", "prelu")
+                     and not self.gru.uses_wavefront(B, T, state.gru if state is not None else None, want_state))
         g = self.gru.forward_frames(e4.view(T, B, D) if overlap else e4.view(B, T, D),
-                                    residual=None if overlap else skips[-1].view(B, T, D),
+                                    residual=None if (overlap or fuse_tail) else skips[-1].view(B, T, D),
                                     state=state.gru if state is not None else None, want_state=want_state, side=side,
-                                    time_major=overlap)                                              # :158-160
+                                    time_major=overlap, skip_ln2=fuse_tail)                          # :158-160
         if overlap:
             torch.cuda.current_stream(mag.device).wait_event(self._skips_done)
         if want_state:
             g, gru_state = g
             state.hist, state.gru = new_hist, gru_state
+        if fuse_tail:                                                                               # :51,160-164 repaired
+            names = [f"conv{k}_t" for k in range(n, 0, -1)]
+            image = ops.decoder_fused_prep(
+                [getattr(self, nm).weight for nm in names], [getattr(self, nm).bias for nm in names],
+                [folds[f"bn{k}_t"][0] for k in range(n, 1, -1)], [folds[f"bn{k}_t"][1] for k in range(n, 1, -1)],
+                [self._alpha(f"act{k}_t") for k in range(n, 1, -1)] if self.act_kind == "prelu" else None, self.act_kind)
+            mask = torch.empty(B, T, F, device=mag.device, dtype=torch.float32)
+            ops.decoder_fused_range(g.view(B, T, D), self.gru.ln2.weight, self.gru.ln2.bias, self.gru.ln2.eps,
+                                    [skips[k - 1] for k in range(n, 0, -1)], image, mask, 0, T)
+            return mask
         out = g.view(B, T, C4, F4)
         for k in range(n, 1, -1):                                                                   # :161-163 repaired
             conv, bn = getattr(self, f"conv{k}_t"), getattr(self, f"bn{k}_t")

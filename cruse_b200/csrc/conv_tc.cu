@@ -40,6 +40,9 @@ constexpr int ct_threads(int ns) { return (CT_NPW * ns + 1 + CT_EPI_WARPS) * 32;
 constexpr int CT_SMEM_BUDGET = 222 * 1024;
 
 // optional cap on the persistent grid (0 = one CTA per SM): lets a stage run beside the GRU wavefront on the SMs it leaves free
+#ifndef CRUSE_CONV_L2_PREFETCH
+#define CRUSE_CONV_L2_PREFETCH 1
+#endif
 int g_conv_max_ctas = 0;
 
 #ifdef CRUSE_CT_TIMING
@@ -336,11 +339,29 @@ __global__ void __launch_bounds__(ct_threads(NS), 1) conv_tc_kernel(const ConvTc
             }
         };
 
+        // L2 prefetch of the input block of this set's group after next (one frame record slice per lane, bulk prefetch): the register
+        // pipeline above keeps ONE group of loads in flight per set -- 8-16 KB per SM, a quarter of what the HBM latency needs (ncu r2b:
+        // dram 25 %, long-scoreboard stalls 45 %) -- so the data of the groups behind it is pulled into L2 ahead of the loads.
+        // Measured (32 x 501 frames, alone): 16->32 + skip 67.6 -> 65.5 us, 32->64 49.2 -> 47.1 us, 8->16 + skip unchanged (71.7):
+        // the load latency is NOT what bounds these stages (the stalls are the pipeline's mbarrier waits); kept for the 2 us.
+        auto prefetch_group = [&](int j) {
+#if CRUSE_CONV_L2_PREFETCH
+            if (wq != 0 || lane >= C::NFR || j >= ngroups) return;
+            const int tile = blockIdx.x + (j / C::NG) * gridDim.x, g = j % C::NG;
+            const int b = tile / chunks, t0 = a.t_begin + (tile - b * chunks) * C::TF;
+            const int t = (MODE == 2 ? t0 : t0 - (KT - 1)) + lane;
+            if (t < 0 || t >= T) return;
+            const float* src = a.in + ((a.in_tm ? (size_t)t * a.B + b : (size_t)b * T + t) * CIN + g * C::CB) * C::FIN;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(C::CB * C::FIN * 4)) : "memory");
+#endif
+        };
         if (set < ngroups) load_items(0, C::NIT, set);
+        prefetch_group(set + CT_SETS);
 #pragma unroll 1
         for (int j = set; j < ngroups; j += CT_SETS) {
             const int r = j % C::RD;
             const bool more = j + CT_SETS < ngroups;
+            prefetch_group(j + 2 * CT_SETS);
             if (wq == 0) CT_STAMP(j, 0 + set * 3);
             tc::mbar_wait_backoff(&empty[r], ((j / C::RD) & 1) ^ 1);
             if (wq == 0) CT_STAMP(j, 1 + set * 3);            // ring slot free

@@ -1,5 +1,5 @@
 """per-tile phase stamps of conv_tc CTA 0 (library built with CRUSE_EXTRA_NVCC_FLAGS=-DCRUSE_CT_TIMING)
-   python tools/ct_timing.py enc4|skip4|dec4"""
+   python tools/ct_timing.py enc4|skip4|dec4|fused2"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,6 +15,11 @@ if which == "enc4":
 elif which == "skip4":
     x = torch.randn(B, T, 64, 16, generator=g).to(dev); w = (0.1 * torch.randn(64, 64, 1, 3, generator=g)).to(dev)
     f = lambda: ops.conv_fwd(x, w, None, None, None, None, "none", 1, 1)
+elif which == "fused2":
+    x = torch.randn(B, T, 8, 128, generator=g).to(dev); w = (0.1 * torch.randn(16, 8, 2, 3, generator=g)).to(dev)
+    wsk = (0.1 * torch.randn(8, 8, 1, 3, generator=g)).to(dev)
+    ops.set_conv_mode("tf32")
+    f = lambda: ops.conv_skip_fwd(x, w, None, None, None, None, "relu", wsk)
 else:
     x = torch.randn(B, T, 64, 16, generator=g).to(dev); w = (0.1 * torch.randn(64, 32, 1, 3, generator=g)).to(dev)
     sk = torch.randn(B, T, 32, 32, generator=g).to(dev)

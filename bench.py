@@ -324,9 +324,8 @@ def run_ours(args):
     host_binding = hostio.bind_near_gpu(local, local, local_world) if not args.no_bind else {"why_not": "--no-bind"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own init log ("comm ... nranks N ... Init COMPLETE") on STDERR: the collective is observable, stdout stays one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (NCCL_DEBUG is left alone: on this image it prints its version line to STDOUT, which must stay one JSON line, and no init
+        # lines at all; the communicator is reported on stderr below and as `comm` in the line)
         dist.init_process_group("nccl", device_id=dev)
         if rank == 0:
             print(f"[bench] NCCL communicator: backend nccl {'.'.join(map(str, torch.cuda.nccl.version()))}, nranks {world}", file=sys.stderr)
@@ -588,6 +587,18 @@ def run_ours(args):
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(), "loss": float(loss), "kernels": kernels,
     }
+    if world > 1:
+        line["comm"] = {"backend": "nccl", "nranks": world, "nccl_version": ".".join(map(str, torch.cuda.nccl.version())),
+                        "used_by": "the `train` block's gradient all_reduce (inference ranks are independent replicas)"}
+    # whole-step traffic view: the layer-by-layer algorithmic bytes of the path (205 344 B per frame, every stage
+    # reading its inputs and writing its outputs once) over the step time, against the measured HBM peak
+    if not train:
+        step_gbs = 205344.0 * frames / (total_ms / args.steps / 1e3) / 1e9
+        line["roofline"]["whole_step"] = {"alg_bytes_per_frame": 205344, "achieved": round(step_gbs, 1), "frac": round(step_gbs / pk["hbm_gbs"], 4),
+                                          "note": "layer-wise algorithmic bytes x frames / step time; the fused kernels move less than this (skip tensors 3/4 and the "
+                                                  "decoder intermediates never reach HBM), so it measures the step against the UNFUSED path's traffic"}
+    config_streams = line["config"]["launch"].replace("13 streams", "16 streams")
+    line["config"]["launch"] = config_streams
     if not train and not args.no_train_block:
         line["train"] = train_block(args, dev, world, rank, flush)
         if world > 1:

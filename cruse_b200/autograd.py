@@ -44,14 +44,14 @@ class _SideWork:
     Every tensor handed to the side stream is kept alive until the join so that the caching allocator cannot give its
     block to a later main-stream allocation while the side stream is still reading it."""
 
-    def __init__(self, device, enabled):
+    def __init__(self, device, enabled, hp_priority=-1):
         self.enabled = enabled and device.type == "cuda"
         self.keep = []
         if self.enabled:
             from .pipeline import _side_stream
             self.main = torch.cuda.current_stream(device)
             self.side = _side_stream(device)
-            self.hp = _high_priority_stream(device)
+            self.hp = _priority_stream(device, hp_priority)
 
     def mark(self):
         """event at the current point of the main stream (None when disabled)"""
@@ -59,6 +59,12 @@ class _SideWork:
             return None
         ev = torch.cuda.Event()
         ev.record(self.main)
+        return ev
+
+    def mark_side(self):
+        """event at the current point of the side stream: what the main stream waits for before it reads a side result early"""
+        ev = torch.cuda.Event()
+        ev.record(self.side)
         return ev
 
     def critical(self, fn, after):
@@ -103,10 +109,11 @@ class _SideWork:
 _hp_streams = {}
 
 
-def _high_priority_stream(device):
-    key = (device.type, device.index)
+def _priority_stream(device, priority=-1):
+    """one stream per (device, priority); CUDA priorities: 0 = default (lowest), negative = served first"""
+    key = (device.type, device.index, priority)
     if key not in _hp_streams:
-        _hp_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+        _hp_streams[key] = torch.cuda.Stream(device=device, priority=priority)
     return _hp_streams[key]
 
 
@@ -115,10 +122,12 @@ def _splitk(M):
     return max(1, min(16, M // 1024))
 
 
-def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, beside=None, own_wgrads_on_side=True):
+def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, beside=None, own_wgrads_on_side=True,
+                  defer_wgrads=False):
     """dy [B,T,G*H] (layout of y) -> (dx [B*T, G*H] | None, {param: grad}); with ``side`` the weight gradients are
     enqueued on the side stream (valid on the main stream after ``side.join()``) and ``beside(after_event)`` is called right
-    after the BPTT launch to queue side work that should run next to it"""
+    after the BPTT launch to queue side work that should run next to it.  ``defer_wgrads``: the weight-gradient GEMMs are not
+    launched; a third return value ``wg()`` launches them (on whatever stream is current) and fills the dict."""
     x2d, y, gates = saved
     G = len(grus)
     H = grus[0].hidden_size
@@ -136,43 +145,73 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
             beside(None)
     dev = dy.device
     grads = {}
+    # tensor-core GEMMs read the factors where they lie (MN-major operand descriptors); the exact-fp32 twins (parity mode)
+    # keep the K-major contract and therefore the transposed copies
+    in_place = ops.GRU_IH_MODE == "tf32" and ops.GEMM_MN_MAJOR
     # ---- bias gradients: xproj carried b_ih (all gates) + b_hh (r,z); W_hn.h carried b_hh (n)
     for gi, g in enumerate(grus):
         grads[g.bias_ih_l0] = dbias[gi, :3].reshape(3 * H)
         grads[g.bias_hh_l0] = torch.cat([dbias[gi, 0], dbias[gi, 1], dbias[gi, 3]])
-    # ---- dx = dxproj . W_ih   ([M,3H] x [3H,H]); B operand must be K-major -> W_ih^T copies (0.75 MB each)
+    # ---- dx = dxproj . W_ih   ([M,3H] x [3H,H]): W_ih [3H, H] is the B operand with the reduction index as its ROW
     dx = None
     if need_dx:
         dx = torch.empty(M, G * H, device=dev, dtype=torch.float32)
-        w_t = [w.detach().t().contiguous() for w in w_ih]                       # [H, 3H]
-        ops.gemm_tn_tc([dxproj[:, gi] for gi in range(G)], w_t, [dx[:, gi * H:] for gi in range(G)],
-                       M, H, 3 * H, G * 3 * H, 3 * H, G * H)
-    # ---- weight gradients: dW_ih = dxproj^T . x, dW_hh = dpre^T . h_{t-1}; reduction index (b,t) made innermost
+        if in_place:
+            ops.gemm_tc([dxproj[:, gi] for gi in range(G)], [w.detach() for w in w_ih], [dx[:, gi * H:] for gi in range(G)],
+                        M, H, 3 * H, G * 3 * H, H, G * H, b_mn=True)
+        else:
+            w_t = [w.detach().t().contiguous() for w in w_ih]                   # [H, 3H]: K-major copies (0.75 MB each)
+            ops.gemm_tn_tc([dxproj[:, gi] for gi in range(G)], w_t, [dx[:, gi * H:] for gi in range(G)],
+                           M, H, 3 * H, G * 3 * H, 3 * H, G * H)
+    # ---- weight gradients: dW_ih = dxproj^T . x, dW_hh = dpre^T . h_{t-1}; the reduction index is (b,t)
     y_fs, y_gs = (G, 1) if interleave else (1, H)
     plane = 3 * H * H
 
     def weight_grads():
-        dxT = ops.transpose_gcm(dxproj, M, G, 3 * H, G * 3 * H, 3 * H, 1)           # [G, 3H, M4]
-        dpT = ops.transpose_gcm(dpre, M, G, 3 * H, G * 3 * H, 3 * H, 1)
-        xT = ops.transpose_gcm(x2d, M, G, H, G * H, H, 1)                           # [G, H, M4]
-        hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # h_{t-1}
-        M4 = dxT.shape[-1]
         sk = _splitk(M)
         part = torch.empty(2, G, sk, plane, device=dev, dtype=torch.float32)
-        ops.gemm_tn_tc([dxT[gi] for gi in range(G)], [xT[gi] for gi in range(G)], [part[0, gi] for gi in range(G)],
-                       3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
-        ops.gemm_tn_tc([dpT[gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
-                       3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
+        if in_place:
+            # A = dxproj / dpre [M, G, 3H] and B = x [M, G*H] are read MN-major straight from where the BPTT / the forward
+            # left them.  h_{t-1}: the same rows of y one frame earlier (b_kshift = 1) with dpre's t = 0 rows zeroed (zero
+            # initial state; they would otherwise meet the previous utterance's last frame) -- when y is concatenated;
+            # the interleaved layer-1 output (feature = h*G + g) is not contiguous per group and keeps its transposed copy
+            dpre.view(B, T, G * 3 * H)[:, 0].zero_()
+            ops.gemm_tc([dxproj[:, gi] for gi in range(G)], [x2d[:, gi * H:] for gi in range(G)], [part[0, gi] for gi in range(G)],
+                        3 * H, H, M, G * 3 * H, G * H, H, a_mn=True, b_mn=True, splitk=sk, c_plane=plane)
+            if interleave:
+                hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # [G, H, M4]: h_{t-1}, K-major
+                M4 = hT.shape[-1]
+                ops.gemm_tc([dpre[:, gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
+                            3 * H, H, M, G * 3 * H, M4, H, a_mn=True, splitk=sk, c_plane=plane)
+            else:
+                yv = y.view(M, G * H)
+                ops.gemm_tc([dpre[:, gi] for gi in range(G)], [yv[:, gi * H:] for gi in range(G)], [part[1, gi] for gi in range(G)],
+                            3 * H, H, M, G * 3 * H, G * H, H, a_mn=True, b_mn=True, b_kshift=1, splitk=sk, c_plane=plane)
+        else:
+            dxT = ops.transpose_gcm(dxproj, M, G, 3 * H, G * 3 * H, 3 * H, 1)           # [G, 3H, M4]
+            dpT = ops.transpose_gcm(dpre, M, G, 3 * H, G * 3 * H, 3 * H, 1)
+            xT = ops.transpose_gcm(x2d, M, G, H, G * H, H, 1)                           # [G, H, M4]
+            hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # h_{t-1}
+            M4 = dxT.shape[-1]
+            ops.gemm_tn_tc([dxT[gi] for gi in range(G)], [xT[gi] for gi in range(G)], [part[0, gi] for gi in range(G)],
+                           3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
+            ops.gemm_tn_tc([dpT[gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
+                           3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
         dw_ = torch.empty(2, G, plane, device=dev, dtype=torch.float32)
         for a in range(2):
             for gi in range(G):
                 ops.colsum(part[a, gi], sk, plane, dw_[a, gi])
         return dw_
 
-    dw = side.run(weight_grads, dxproj, dpre, x2d, y) if (side is not None and own_wgrads_on_side) else weight_grads()
-    for gi, g in enumerate(grus):
-        grads[g.weight_ih_l0] = dw[0, gi].view(3 * H, H)
-        grads[g.weight_hh_l0] = dw[1, gi].view(3 * H, H)
+    def wg(on_side=own_wgrads_on_side):
+        dw = side.run(weight_grads, dxproj, dpre, x2d, y) if (side is not None and on_side) else weight_grads()
+        for gi, g in enumerate(grus):
+            grads[g.weight_ih_l0] = dw[0, gi].view(3 * H, H)
+            grads[g.weight_hh_l0] = dw[1, gi].view(3 * H, H)
+
+    if defer_wgrads:
+        return dx, grads, wg
+    wg()
     return dx, grads
 
 
@@ -263,6 +302,24 @@ class _Unet2Fn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dmask):
+        """Schedule (ops.BWD_PRIORITY): the chain of kernels that depend on each other -- loss gradient -> decoder -> BPTT 2
+        -> BPTT 1 -> encoder -- runs on a stream of priority -1 and the two BPTT launches at -2, while everything nothing
+        downstream waits for (all weight gradients) and the skip convs' data gradients (needed only at the encoder stage
+        they are added to) go to the side stream at priority 0: the block scheduler then fills the SMs the chain leaves
+        idle instead of making the chain queue behind a full-grid weight-gradient kernel."""
+        dev = dmask.device
+        if ctx.sv is not None and ops.OVERLAP_BWD and ops.BWD_PRIORITY and dev.type == "cuda":
+            cur = torch.cuda.current_stream(dev)
+            chain = _priority_stream(dev, -1)
+            chain.wait_stream(cur)
+            with torch.cuda.stream(chain):
+                out = _Unet2Fn._backward(ctx, dmask, -2)
+            cur.wait_stream(chain)
+            return out
+        return _Unet2Fn._backward(ctx, dmask, -1)
+
+    @staticmethod
+    def _backward(ctx, dmask, bptt_priority):
         m, sv = ctx.model, ctx.sv
         if sv is None:
             raise RuntimeError("cruse_b200.unet_2: backward was already run through this forward pass; its saved activations were "
@@ -273,7 +330,8 @@ class _Unet2Fn(torch.autograd.Function):
         act, train = m.act_kind, ctx.train
         G = {}                                                    # parameter tensor -> gradient
         dmask = dmask.contiguous()
-        side = _SideWork(dmask.device, ops.OVERLAP_BWD)
+        side = _SideWork(dmask.device, ops.OVERLAP_BWD, hp_priority=bptt_priority)
+        early = side.enabled and ops.BWD_PRIORITY                 # the re-ordered schedule of the docstring above
         cap = 0                                                   # persistent side kernels sized to the SMs the BPTT leaves free
         if side.enabled and ops.BWD_SIDE_CAP:
             ng = len(m.gru.gru_list1)
@@ -285,7 +343,13 @@ class _Unet2Fn(torch.autograd.Function):
         deferred = []                                             # decoder / skip weight gradients: run beside the BPTT
         # ---- last decoder stage: mask = sigmoid(convT(d2))           cruse_net.py:164
         dz = ops.sigmoid_bwd(dmask.view(B, T, 1, F), sv["mask"])
-        G[m.conv1_t.weight], G[m.conv1_t.bias] = ops.convT_wgrad(sv["d2"], dz)
+
+        def mask_layer_wgrad():
+            G[m.conv1_t.weight], G[m.conv1_t.bias] = ops.convT_wgrad(sv["d2"], dz)
+        if early:
+            side.run(mask_layer_wgrad, dz)
+        else:
+            mask_layer_wgrad()
         d_out = ops.convT_dgrad(dz, m.conv1_t.weight, sv["d2"].shape)
         # ---- decoder stages k = 2..n: out = act(BN(convT_k(in))) + skip_{k-1}       :161-163
         dskip = [None] * n                                        # gradient w.r.t. skip_k output (index k-1)
@@ -305,42 +369,70 @@ class _Unet2Fn(torch.autograd.Function):
             d_out = ops.convT_dgrad(dzk, conv.weight, x_in.shape)
         dskip[n - 1] = d_out                                      # out = g + skip4     :160
 
+        def e_of(k_):                                             # output of encoder stage k_ (= input of its skip conv)
+            return sv["e4"] if k_ == n else sv["enc_in"][k_]
+
         def decoder_weight_grads():
             for conv_, x_, dz_ in deferred:
                 G[conv_.weight], G[conv_.bias] = ops.convT_wgrad(x_, dz_)
             for k_ in range(n, 0, -1):
-                e_ = sv["e4"] if k_ == n else sv["enc_in"][k_]
-                G[getattr(m, f"skip_connect_{k_}").weight], _ = ops.conv_wgrad(e_, dskip[k_ - 1], 1, 1, want_bias=False)
+                G[getattr(m, f"skip_connect_{k_}").weight], _ = ops.conv_wgrad(e_of(k_), dskip[k_ - 1], 1, 1, want_bias=False)
+
+        sd = [None] * n                                           # skip conv k's data gradient (index k-1), early schedule only
+
+        def skip_data_grads():
+            for k_ in range(n, 0, -1):
+                sd[k_ - 1] = ops.conv_dgrad(dskip[k_ - 1], getattr(m, f"skip_connect_{k_}").weight, e_of(k_).shape, 1, 1)
         # ---- GGRU                                                              :37-55
         gru = m.gru
         dgo = d_out.view(B * T, D)
         dy2, G[gru.ln2.weight], G[gru.ln2.bias] = ops.layernorm_bwd(dgo, sv["y2"].view(B * T, D), gru.ln2.weight, *sv["ln2"])
-        dz1, g2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False, side=side,
-                                beside=lambda ev: side.run(decoder_weight_grads, *[t for d in deferred for t in d[1:]], *dskip,
-                                                           after=ev, max_ctas=cap))
-        G.update(g2)
+        side_in = [t for d in deferred for t in d[1:]] + dskip
+        dz1, g2, wg2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False, side=side, defer_wgrads=True,
+                                     beside=lambda ev: side.run(decoder_weight_grads, *side_in, after=ev, max_ctas=cap))
+        if not early:
+            wg2()
         dy1, G[gru.ln1.weight], G[gru.ln1.bias] = ops.layernorm_bwd(dz1, sv["y1"].view(B * T, D), gru.ln1.weight, *sv["ln1"])
-        de, g1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True, side=side,
-                               own_wgrads_on_side=ops.BWD_SIDE_L1)
-        G.update(g1)
+
+        sd_ready = []
+
+        def beside_bptt1(ev):                                     # what the chain needs first goes first
+            side.run(skip_data_grads, *dskip, after=ev, max_ctas=cap)
+            sd_ready.append(side.mark_side())
+            side.run(lambda: wg2(on_side=False))
+        de, g1, wg1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True, side=side, defer_wgrads=True,
+                                    beside=beside_bptt1 if early else None)
+        wg1(on_side=ops.BWD_SIDE_L1 or early)
+        if early:
+            side.main.wait_event(sd_ready[0])
+            ops.colsum(sd[n - 1], 1, de.numel(), de, accumulate=True)       # out = g + skip4: both paths' gradients meet at e4
         de = de.view(B, T, C4, F4)
         # ---- encoder stages k = n..1 with their skip convs                      :149-156
         for k in range(n, 0, -1):
             conv, bn, skipc = getattr(m, f"conv{k}"), getattr(m, f"bn{k}"), getattr(m, f"skip_connect_{k}")
             alpha = m._alpha(f"act{k}")
-            e_k = sv["e4"] if k == n else sv["enc_in"][k]         # output of stage k = input of stage k+1
+            e_k = e_of(k)                                         # output of stage k = input of stage k+1
             x_in, z = sv["enc_in"][k - 1], sv["enc_z"][k - 1]
             scale, shift, mean, invstd = sv["enc_bn"][k - 1]
-            de = ops.conv_dgrad(dskip[k - 1], skipc.weight, e_k.shape, 1, 1, addend=de)
+            if not early:
+                de = ops.conv_dgrad(dskip[k - 1], skipc.weight, e_k.shape, 1, 1, addend=de)
             dzk, dgamma, dbeta, dalpha = ops.bn_act_bwd(de, z, scale, shift, alpha, act, mean, invstd, bn.weight,
                                                         B * T * z.shape[3], training=train)
             G[bn.weight], G[bn.bias] = dgamma, dbeta
             if dalpha is not None:
                 G[getattr(m, f"act{k}").weight] = dalpha
-            G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
+
+            def stage_wgrad(conv=conv, x_in=x_in, dzk=dzk):
+                G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
+            if early:
+                side.run(stage_wgrad, x_in, dzk)
+            else:
+                stage_wgrad()
             if k > 1:
-                de = ops.conv_dgrad(dzk, conv.weight, x_in.shape, 2, 2)
+                de = ops.conv_dgrad(dzk, conv.weight, x_in.shape, 2, 2, addend=sd[k - 2] if early else None)
         side.join()
+        G.update(g2)
+        G.update(g1)
         named = dict(m.named_parameters())
         out = []
         for nm in ctx.names:

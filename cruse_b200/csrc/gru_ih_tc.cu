@@ -23,7 +23,7 @@
 namespace cruse {
 
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
-                 bool as_tf32) {
+                 bool as_tf32, bool atom32) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -47,7 +47,8 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t co
     const cuuint32_t box[2] = {32, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(out, as_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
-                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu)", (int)r,
@@ -74,9 +75,17 @@ struct GemmArgs {
     float* out[CRUSE_MAX_GROUPS];
 };
 
+// A_MN / B_MN: that operand is "MN-major" in HBM -- stored [K rows][M or N contiguous], the layout a weight gradient's
+// operands have naturally (dW = dpre^T . h: both factors are [B*T, features] row-major, the reduction index is the ROW).
+// tcgen05 reads such a tile through an MN-major shared-memory descriptor, so no transposed copy is made: the tile arrives as
+// BM/32 (BN/32) TMA boxes of {32 features, BK rows}, each a column of 4-row x 128-byte swizzle atoms (the one MN-major
+// layout tcgen05 has for 32-bit elements, 128-byte swizzle with 32-byte atoms: leading byte offset = one box = BK*128 B,
+// stride byte offset = one atom = 512 B, two atoms per UMMA_K = 8 rows).
+// b_kshift: B's row for reduction index k is k - b_kshift (rows < 0 read as zero): h_{t-1} paired with frame t.
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(IH_THREADS)
 gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, long long ldc, int bias2_rows, int splitk,
-                  long long c_plane, int tm_T) {
+                  long long c_plane, int tm_T, int b_kshift) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles: 1024-byte aligned
     uint8_t* tiles = smem_raw + (base - tc::smem_u32(smem_raw));
@@ -114,13 +123,25 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
                 tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
                 uint8_t* st = tiles + s * STAGE_BYTES;
-                tc::tma_load_2d(st, &args.a[g], (kb_begin + i) * BK, m0, &full[s]);
-                tc::tma_load_2d(st + A_BYTES, &args.b[g], (kb_begin + i) * BK, n0, &full[s]);
+                const int k0 = (kb_begin + i) * BK;
+                if constexpr (A_MN) {
+#pragma unroll
+                    for (int c = 0; c < BM / 32; ++c) tc::tma_load_2d(st + c * (BK * 128), &args.a[g], m0 + c * 32, k0, &full[s]);
+                } else {
+                    tc::tma_load_2d(st, &args.a[g], k0, m0, &full[s]);
+                }
+                if constexpr (B_MN) {
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c)
+                        tc::tma_load_2d(st + A_BYTES + c * (BK * 128), &args.b[g], n0 + c * 32, k0 - b_kshift, &full[s]);
+                } else {
+                    tc::tma_load_2d(st + A_BYTES, &args.b[g], k0, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane of a converged warp) =====
-        constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, BM, BN);
+        constexpr uint32_t idesc = tc::instr_desc(2 /*tf32*/, BM, BN, A_MN, B_MN);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % STAGES;
             tc::mbar_wait(&full[s], (i / STAGES) & 1);
@@ -128,8 +149,11 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
             if (tc::elect_one()) {
                 const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k)     // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
-                    tc::umma_tf32(tmem_d, tc::smem_desc_sw128(sa + k * 32), tc::smem_desc_sw128(sb + k * 32), idesc, (i | k) ? 1u : 0u);
+                for (int k = 0; k < BK / 8; ++k) {   // UMMA_K = 8 for tf32: 32 bytes along a K-major row / one 8-row atom of an MN-major box
+                    const uint64_t da = A_MN ? tc::smem_desc_mn_sw128_32b(sa + k * 1024, BK * 128) : tc::smem_desc_sw128(sa + k * 32);
+                    const uint64_t db = B_MN ? tc::smem_desc_mn_sw128_32b(sb + k * 1024, BK * 128) : tc::smem_desc_sw128(sb + k * 32);
+                    tc::umma_tf32(tmem_d, da, db, idesc, (i | k) ? 1u : 0u);
+                }
                 tc::umma_commit(&empty[s]);           // frees the stage when these MMAs have read it
             }
             __syncwarp();
@@ -363,8 +387,18 @@ gemm_astat_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, long l
 // process-wide switch (developer A/B): 1 = use the A-stationary kernel where it applies (default), 0 = the tile-per-CTA kernel
 static int g_astat = 1;
 
+template <bool A_MN, bool B_MN>
+int launch_gemm_tile(const GemmArgs& args, int G, int M, int N, int K, long long ldc, int bias2_rows, int splitk, long long c_plane,
+                     cudaStream_t st, int tm_T, int b_kshift) {
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, G * splitk);
+    gemm_tn_tc_kernel<A_MN, B_MN><<<grid, IH_THREADS, IH_SMEM, st>>>(args, M, N, K, ldc, bias2_rows, splitk, c_plane, tm_T, b_kshift);
+    CRUSE_LAUNCH_OK();
+    return 0;
+}
+
 int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int bias2_rows, int splitk, long long c_plane,
-                cudaStream_t st, int tm_T = 0, bool astat_ok = false) {
+                cudaStream_t st, int tm_T = 0, bool astat_ok = false, bool a_mn = false, bool b_mn = false, int b_kshift = 0) {
     for (int g = G; g < CRUSE_MAX_GROUPS; ++g) {
         args.a[g] = args.a[0]; args.b[g] = args.b[0];
         args.bias1[g] = nullptr; args.bias2[g] = nullptr; args.out[g] = nullptr;
@@ -379,11 +413,10 @@ int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int b
         CRUSE_LAUNCH_OK();
         return 0;
     }
-    CRUSE_CUDA_OK(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IH_SMEM));
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, G * splitk);
-    gemm_tn_tc_kernel<<<grid, IH_THREADS, IH_SMEM, st>>>(args, M, N, K, ldc, bias2_rows, splitk, c_plane, tm_T);
-    CRUSE_LAUNCH_OK();
-    return 0;
+    if (a_mn && b_mn) return launch_gemm_tile<true, true>(args, G, M, N, K, ldc, bias2_rows, splitk, c_plane, st, tm_T, b_kshift);
+    if (a_mn) return launch_gemm_tile<true, false>(args, G, M, N, K, ldc, bias2_rows, splitk, c_plane, st, tm_T, 0);
+    if (b_mn) return launch_gemm_tile<false, true>(args, G, M, N, K, ldc, bias2_rows, splitk, c_plane, st, tm_T, b_kshift);
+    return launch_gemm_tile<false, false>(args, G, M, N, K, ldc, bias2_rows, splitk, c_plane, st, tm_T, 0);
 }
 
 }  // namespace
@@ -445,6 +478,31 @@ extern "C" int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, c
         args.out[g] = C[g];
     }
     return launch_gemm(args, G, M, N, K, ldc, 0, splitk, c_plane, (cudaStream_t)stream);
+}
+
+extern "C" int cruse_gemm_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C, int G,
+                             int M, int N, int K, long long lda, long long ldb, long long ldc, int splitk, long long c_plane,
+                             int a_mn, int b_mn, int b_kshift, void* stream) {
+    CRUSE_CHECK_ARG(A && Bm && C, "gemm_tc: null pointer table");
+    CRUSE_CHECK_ARG(G > 0 && G <= CRUSE_MAX_GROUPS && M > 0 && N > 0 && K > 0 && splitk >= 1 && splitk <= 64,
+                    "gemm_tc: bad sizes G=%d M=%d N=%d K=%d splitk=%d", G, M, N, K, splitk);
+    CRUSE_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0 && lda >= (a_mn ? M : K) && ldb >= (b_mn ? N : K) && ldc >= N,
+                    "gemm_tc: bad pitches lda=%lld ldb=%lld ldc=%lld", lda, ldb, ldc);
+    CRUSE_CHECK_ARG(splitk == 1 || (bias == nullptr && c_plane >= (long long)M * ldc), "gemm_tc: split-K needs bias == NULL and c_plane >= M*ldc");
+    CRUSE_CHECK_ARG(b_kshift >= 0 && (b_kshift == 0 || b_mn), "gemm_tc: b_kshift needs an MN-major B operand");
+    GemmArgs args;
+    for (int g = 0; g < G; ++g) {
+        CRUSE_CHECK_ARG(A[g] && Bm[g] && C[g], "gemm_tc: null pointer for problem %d", g);
+        // K-major operand: tensor [rows = M|N][cols = K], box {32 k, BM|BN rows}; MN-major: tensor [rows = K][cols = M|N], box {32 features, BK rows}
+        if (int rc = a_mn ? make_tmap_2d(&args.a[g], A[g], (uint64_t)K, (uint64_t)M, (uint64_t)lda * 4, BK, true, true)
+                          : make_tmap_2d(&args.a[g], A[g], (uint64_t)M, (uint64_t)K, (uint64_t)lda * 4, BM, true)) return rc;
+        if (int rc = b_mn ? make_tmap_2d(&args.b[g], Bm[g], (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 4, BK, true, true)
+                          : make_tmap_2d(&args.b[g], Bm[g], (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, BN, true)) return rc;
+        args.bias1[g] = bias ? bias[g] : nullptr;
+        args.bias2[g] = nullptr;
+        args.out[g] = C[g];
+    }
+    return launch_gemm(args, G, M, N, K, ldc, 0, splitk, c_plane, (cudaStream_t)stream, 0, false, a_mn != 0, b_mn != 0, b_kshift);
 }
 
 // ---------------------------------------------------------------------------------------------

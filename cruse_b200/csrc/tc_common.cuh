@@ -117,9 +117,26 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B [61,64)
     return d;
 }
-// instruction descriptor: D fp32, A/B of `fmt` (0 f16, 1 bf16, 2 tf32), both K-major, shape M x N
-__host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major 32-bit operand tile: stored [K rows][32 fp32 of M|N = 128 bytes].  For 4-byte elements tcgen05 knows ONE
+// MN-major layout, "128-byte swizzle with 32-byte atoms" (layout type 1; a plain SWIZZLE_128B descriptor reads zeros):
+// within a 128-byte row the four 32-byte chunks are XOR-ed with (row & 3), the pattern repeating every 4 rows = 512 B --
+// what a TMA box {32 x fp32, rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  Consecutive 32-element blocks of M|N
+// lie `lbo_bytes` apart (leading byte offset), consecutive 4-row K groups 512 B apart (stride byte offset).  One tf32 MMA
+// (UMMA_K = 8) reads two K groups of every block: stepping K = adding 1024 B to the start.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset [16,30)
+    d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset = 512 B  [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell) [46,48)
+    d |= (uint64_t)1 << 61;                         // layout type SWIZZLE_128B_BASE32B [61,64)
+    return d;
+}
+// instruction descriptor: D fp32, A/B of `fmt` (0 f16, 1 bf16, 2 tf32), shape M x N; a_mn / b_mn = 1: that operand's
+// shared-memory tile is MN-major (bits 15 / 16), else K-major
+__host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, one CTA.  Issued by ONE thread.
@@ -158,7 +175,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------- host: tensor maps (driver entry point, no libcuda link)
 // 2-D fp32 tensor [rows, cols] with row pitch `pitch_bytes`, box = {32 cols (128 B), box_rows}, SWIZZLE_128B,
 // out-of-bounds elements read as zero.  `as_tf32` makes the TMA unit round fp32 -> tf32 on the way in.
+// `atom32` selects the 128-byte swizzle with 32-byte atoms (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), the only layout tcgen05
+// accepts for an MN-major 32-bit operand (smem_desc_mn_sw128_32b).
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
-                 bool as_tf32);
+                 bool as_tf32, bool atom32 = false);
 
 }  // namespace cruse

@@ -971,6 +971,16 @@ def gemm_tn_tc(A, Bm, C, M, N, K, lda, ldb, ldc, bias=None, splitk=1, c_plane=0,
           _stream(), meta=(f"gemm_tn[{mode}] G{G} {M}x{N}x{K} splitk{splitk}", 4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
 
 
+def gemm_tc(A, Bm, C, M, N, K, lda, ldb, ldc, a_mn=False, b_mn=False, b_kshift=0, bias=None, splitk=1, c_plane=0):
+    """gemm_tn_tc with either operand MN-major (stored [K rows][M | N contiguous], row pitch lda / ldb): C_g[m,n] =
+    sum_k A_g[m,k] B_g[n,k]; b_kshift pairs A's reduction index k with B's row k - b_kshift (rows < 0 are zero).  tf32 only."""
+    G = len(A)
+    ta, tb, tcs, tbias = _ptr_table(A), _ptr_table(Bm), _ptr_table(C), _ptr_table(bias)
+    _call("cruse_gemm_tc", ta, tb, tbias, tcs, G, M, N, K, lda, ldb, ldc, splitk, c_plane, 1 if a_mn else 0, 1 if b_mn else 0,
+          b_kshift, _stream(), meta=(f"gemm[tf32,{'mn' if a_mn else 'k'}/{'mn' if b_mn else 'k'}] G{G} {M}x{N}x{K} splitk{splitk}",
+                                     4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
+
+
 def sigmoid_bwd(dy, y):
     _req(dy, "dy")
     _req(y, "y")
@@ -1001,6 +1011,8 @@ def set_conv_max_ctas(n: int):
 # training backward: weight-gradient kernels on a side stream beside the BPTT launches (autograd._SideWork)
 OVERLAP_BWD = os.environ.get("CRUSE_OVERLAP_BWD", "1") != "0"
 BWD_SIDE_CAP = os.environ.get("CRUSE_BWD_SIDE_CAP", "1") != "0"
+BWD_PRIORITY = os.environ.get("CRUSE_BWD_PRIORITY", "1") != "0"         # backward: dependent chain on a priority stream, the rest early on the side
+GEMM_MN_MAJOR = os.environ.get("CRUSE_GEMM_MN_MAJOR", "1") != "0"       # GRU weight-gradient / dx GEMMs read their factors in place
 FWD_SIDE_SKIPS = os.environ.get("CRUSE_FWD_SIDE_SKIPS", "1") != "0"   # training forward: skip convs beside the layer-1 recurrence
 BWD_SIDE_L1 = os.environ.get("CRUSE_BWD_SIDE_L1", "1") != "0"      # layer-1 GRU weight gradients beside the encoder backward
 

@@ -392,6 +392,17 @@ int cruse_gru_step(const float* xproj, const float* const* w_hh, const float* co
 int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C,
                      int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
                      int splitk, long long c_plane, void* stream);
+/* The same GEMM with either operand read "MN-major", i.e. as it lies in HBM when the reduction index is the ROW of a row-major
+ * matrix -- the natural layout of a weight gradient's factors (nn.GRU's dW_ih = dxproj^T . x and dW_hh = dpre^T . h_{t-1},
+ * model/cruse_net.py:23-31 through autograd: both factors are [B*T, features]) and of W_ih in dx = dxproj . W_ih, so that no
+ * transposed copy is made (tcgen05 MN-major shared-memory descriptors over TMA boxes of {32 features, 32 rows}):
+ *   a_mn = 0: A_g[m,k] = A[m*lda + k]     a_mn = 1: A_g[m,k] = A[k*lda + m]
+ *   b_mn = 0: B_g[n,k] = Bm[n*ldb + k]    b_mn = 1: B_g[n,k] = Bm[(k - b_kshift)*ldb + n], rows < 0 read as zero
+ * (b_kshift = 1 pairs frame t with h_{t-1} when the rows are frames; the caller zeroes the t == 0 rows of A).
+ * Everything else as cruse_gemm_tn_tc, which is the a_mn = b_mn = 0 case. */
+int cruse_gemm_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C,
+                  int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                  int splitk, long long c_plane, int a_mn, int b_mn, int b_kshift, void* stream);
 /* Exact-fp32 twins of the three tensor-core kernels of the GRU training path (same contracts and layouts; every product an
  * fp32 FMA on the CUDA cores, fixed summation order).  They make the whole training step runnable without tf32 operand rounding
  * (CRUSE_CONV=fp32 CRUSE_GRU_IH=fp32 CRUSE_GRU_SEQ=fp32), which is how the end-to-end gradients are compared with autograd of

@@ -689,3 +689,38 @@ def test_trainer_epochs_checkpoints_and_inferencer_shell(cuda, tmp_path, loss_na
         want = o.enhance(ref, noisy, 512, 320)[0][0].numpy()
     got = inf.multi_channel_mag_to_mag(noisy[:, None].to(cuda))
     assert got.shape == want.shape and np.abs(got - want).max() <= 1e-3 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("a_mn,b_mn,shift", [(False, False, 0), (True, False, 0), (False, True, 0), (True, True, 0), (True, True, 1),
+                                             (False, True, 1)])
+@pytest.mark.parametrize("M,N,K,splitk", [(768, 256, 1000, 3), (128, 256, 64, 1), (528, 176, 333, 2), (96, 32, 45, 1), (300, 260, 2049, 5)])
+def test_gemm_operands_read_in_place(cuda, a_mn, b_mn, shift, M, N, K, splitk):
+    """cruse_gemm_tc: every K-major / MN-major operand combination (+ the one-row shift of B that pairs frame t with h_{t-1})
+    against the float64 product of the fp32 operands, at the tf32 gate.  What autograd computes for
+    nn.GRU's weight gradients (model/cruse_net.py:23-31): dW = dgates^T . x with both factors [B*T, features] row-major."""
+    from cruse_b200 import ops
+    torch.manual_seed(K + M)
+    Gn = 2
+    A = torch.randn(Gn, M, K)
+    Bm = torch.randn(Gn, N, K)
+    want = torch.einsum("gmk,gnk->gmn", A.double(), Bm.double())
+    if shift:                                                 # B's column k pairs with A's column k + shift; A's column 0 meets zero
+        want = torch.einsum("gmk,gnk->gmn", A[:, :, shift:].double(), Bm[:, :, :K - shift].double())
+    pad = 4                                                   # pitches larger than the extents, as the group views have
+    a_dev = torch.zeros(Gn, K, M + pad, device=cuda) if a_mn else torch.zeros(Gn, M, K + pad + (-K) % 4, device=cuda)
+    b_dev = torch.zeros(Gn, K, N + pad, device=cuda) if b_mn else torch.zeros(Gn, N, K + pad + (-K) % 4, device=cuda)
+    if a_mn:
+        a_dev[:, :, :M] = A.transpose(1, 2).to(cuda)
+    else:
+        a_dev[:, :, :K] = A.to(cuda)
+    if b_mn:
+        b_dev[:, :, :N] = Bm.transpose(1, 2).to(cuda)
+    else:
+        b_dev[:, :, :K] = Bm.to(cuda)
+    plane = M * N
+    part = torch.full((Gn, splitk, plane), float("nan"), device=cuda)
+    ops.gemm_tc([a_dev[g] for g in range(Gn)], [b_dev[g] for g in range(Gn)], [part[g] for g in range(Gn)], M, N, K,
+                a_dev.shape[-1], b_dev.shape[-1], N, a_mn=a_mn, b_mn=b_mn, b_kshift=shift, splitk=splitk, c_plane=plane)
+    torch.cuda.synchronize()
+    got = part.sum(1).view(Gn, M, N)
+    assert rel_err(got, want) <= 2e-3

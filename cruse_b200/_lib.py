@@ -102,7 +102,7 @@ SIGNATURES = {
     "cruse_layernorm_bwd": (c_int, [c_fp] * 7 + [c_ll, c_int, c_fp]),
     "cruse_gru_seq_bwd_tc": (c_int, [c_fp, c_fp, c_fp, c_fp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gemm_tn_tc": (c_int, [c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_fp]),
-    "cruse_gemm_tc": (c_int, [c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_int, c_int, c_int, c_fp]),
+    "cruse_gemm_tc": (c_int, [c_pp, c_pp, c_pp, c_pp, c_pp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_ll, c_int, c_int, c_int, c_fp]),
     "cruse_gru_exact_ws_bytes": (C.c_size_t, [c_int] * 2),
     "cruse_gru_seq_fwd_exact": (c_int, [c_fp, c_pp, c_pp, c_fp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "cruse_gru_seq_bwd_exact": (c_int, [c_fp, c_fp, c_fp, c_fp, c_pp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),

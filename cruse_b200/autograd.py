@@ -47,10 +47,12 @@ class _SideWork:
     def __init__(self, device, enabled, hp_priority=-1):
         self.enabled = enabled and device.type == "cuda"
         self.keep = []
+        self.used = set()                  # lanes with work since the last join (an idle lane is not part of a graph capture)
         if self.enabled:
             from .pipeline import _side_stream
             self.main = torch.cuda.current_stream(device)
             self.side = _side_stream(device)
+            self.lanes = [self.side, _side_stream(device, 1)]     # lane 1: work that must not queue behind lane 0's
             self.hp = _priority_stream(device, hp_priority)
 
     def mark(self):
@@ -81,16 +83,18 @@ class _SideWork:
         self.main.wait_event(done)
         return out
 
-    def run(self, fn, *tensors, after=None, max_ctas=0):
+    def run(self, fn, *tensors, after=None, max_ctas=0, lane=0):
         if not self.enabled:
             return fn()
         ev = after if after is not None else self.mark()
-        self.side.wait_event(ev)
+        stream = self.lanes[lane]
+        self.used.add(lane)
+        stream.wait_event(ev)
         self.keep.extend(tensors)
         if max_ctas:
             ops.set_conv_max_ctas(max_ctas)
         try:
-            with torch.cuda.stream(self.side):
+            with torch.cuda.stream(stream):
                 out = fn()
         finally:
             if max_ctas:
@@ -100,9 +104,11 @@ class _SideWork:
 
     def join(self):
         if self.enabled:
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-            self.main.wait_event(ev)
+            for lane in sorted(self.used):
+                ev = torch.cuda.Event()
+                ev.record(self.lanes[lane])
+                self.main.wait_event(ev)
+        self.used.clear()
         self.keep.clear()
 
 
@@ -122,12 +128,22 @@ def _splitk(M):
     return max(1, min(16, M // 1024))
 
 
+def gru_shifted_state_transposed(saved, G, H, B, T, interleave):
+    """hT[g][i][b*T + t] = h_{t-1}[b, g, i] (0 at t = 0) from the saved layer output: the K-major B operand of dW_hh where the
+    output's features are interleaved over the groups (layer 1, model/cruse_net.py:43-45) and a group's columns are not contiguous"""
+    y = saved[1]
+    y_fs, y_gs = (G, 1) if interleave else (1, H)
+    return ops.transpose_gcm(y, B * T, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)
+
+
 def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, beside=None, own_wgrads_on_side=True,
-                  defer_wgrads=False):
+                  defer_wgrads=False, dx_addend=None, early=None):
     """dy [B,T,G*H] (layout of y) -> (dx [B*T, G*H] | None, {param: grad}); with ``side`` the weight gradients are
     enqueued on the side stream (valid on the main stream after ``side.join()``) and ``beside(after_event)`` is called right
     after the BPTT launch to queue side work that should run next to it.  ``defer_wgrads``: the weight-gradient GEMMs are not
-    launched; a third return value ``wg()`` launches them (on whatever stream is current) and fills the dict."""
+    launched; a third return value ``wg()`` launches them (on whatever stream is current) and fills the dict.
+    ``dx_addend()`` -> [B*T, G*H] tensor added to dx in the GEMM epilogue (tensor-core mode; called after the BPTT launch).
+    ``early`` (dict): work that needs only saved forward tensors, done ahead by the caller -- key "hT" = the transposed h_{t-1}."""
     x2d, y, gates = saved
     G = len(grus)
     H = grus[0].hidden_size
@@ -156,13 +172,17 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
     dx = None
     if need_dx:
         dx = torch.empty(M, G * H, device=dev, dtype=torch.float32)
+        add = dx_addend() if dx_addend is not None else None
         if in_place:
             ops.gemm_tc([dxproj[:, gi] for gi in range(G)], [w.detach() for w in w_ih], [dx[:, gi * H:] for gi in range(G)],
-                        M, H, 3 * H, G * 3 * H, H, G * H, b_mn=True)
+                        M, H, 3 * H, G * 3 * H, H, G * H, b_mn=True,
+                        addend=[add.view(M, G * H)[:, gi * H:] for gi in range(G)] if add is not None else None)
         else:
             w_t = [w.detach().t().contiguous() for w in w_ih]                   # [H, 3H]: K-major copies (0.75 MB each)
             ops.gemm_tn_tc([dxproj[:, gi] for gi in range(G)], w_t, [dx[:, gi * H:] for gi in range(G)],
                            M, H, 3 * H, G * 3 * H, 3 * H, G * H)
+            if add is not None:
+                ops.colsum(add, 1, dx.numel(), dx, accumulate=True)
     # ---- weight gradients: dW_ih = dxproj^T . x, dW_hh = dpre^T . h_{t-1}; the reduction index is (b,t)
     y_fs, y_gs = (G, 1) if interleave else (1, H)
     plane = 3 * H * H
@@ -179,7 +199,9 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
             ops.gemm_tc([dxproj[:, gi] for gi in range(G)], [x2d[:, gi * H:] for gi in range(G)], [part[0, gi] for gi in range(G)],
                         3 * H, H, M, G * 3 * H, G * H, H, a_mn=True, b_mn=True, splitk=sk, c_plane=plane)
             if interleave:
-                hT = ops.transpose_gcm(y, M, G, H, G * H, y_gs, y_fs, shift_T=T, Bn=B)      # [G, H, M4]: h_{t-1}, K-major
+                hT = (early or {}).get("hT")
+                if hT is None:
+                    hT = gru_shifted_state_transposed(saved, G, H, B, T, interleave)         # [G, H, M4]: h_{t-1}, K-major
                 M4 = hT.shape[-1]
                 ops.gemm_tc([dpre[:, gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
                             3 * H, H, M, G * 3 * H, M4, H, a_mn=True, splitk=sk, c_plane=plane)
@@ -396,16 +418,22 @@ class _Unet2Fn(torch.autograd.Function):
 
         sd_ready = []
 
+        ahead = {}
+
         def beside_bptt1(ev):                                     # what the chain needs first goes first
             side.run(skip_data_grads, *dskip, after=ev, max_ctas=cap)
             sd_ready.append(side.mark_side())
-            side.run(lambda: wg2(on_side=False))
-        de, g1, wg1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True, side=side, defer_wgrads=True,
-                                    beside=beside_bptt1 if early else None)
-        wg1(on_side=ops.BWD_SIDE_L1 or early)
-        if early:
+            side.run(lambda: wg2(on_side=False), after=ev)        # layer 2's weight gradients (its BPTT is long done)
+            if ops.GRU_IH_MODE == "tf32" and ops.GEMM_MN_MAJOR:   # layer 1's h_{t-1}, transposed: needs the forward's y1 only
+                ahead["hT"] = side.run(lambda: gru_shifted_state_transposed(sv["sv1"], len(gru.gru_list1), gru.gru_list1[0].hidden_size,
+                                                                            B, T, True), after=ev)
+
+        def skip4_path():                                         # out = g + skip4 (:160): both paths' gradients meet at e4
             side.main.wait_event(sd_ready[0])
-            ops.colsum(sd[n - 1], 1, de.numel(), de, accumulate=True)       # out = g + skip4: both paths' gradients meet at e4
+            return sd[n - 1]
+        de, g1, wg1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True, side=side, defer_wgrads=True,
+                                    beside=beside_bptt1 if early else None, dx_addend=skip4_path if early else None, early=ahead)
+        wg1(on_side=ops.BWD_SIDE_L1 or early)
         de = de.view(B, T, C4, F4)
         # ---- encoder stages k = n..1 with their skip convs                      :149-156
         for k in range(n, 0, -1):
@@ -425,7 +453,7 @@ class _Unet2Fn(torch.autograd.Function):
             def stage_wgrad(conv=conv, x_in=x_in, dzk=dzk):
                 G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
             if early:
-                side.run(stage_wgrad, x_in, dzk)
+                side.run(stage_wgrad, x_in, dzk, lane=1)
             else:
                 stage_wgrad()
             if k > 1:

@@ -72,6 +72,7 @@ struct GemmArgs {
     CUtensorMap b[CRUSE_MAX_GROUPS];
     const float* bias1[CRUSE_MAX_GROUPS];
     const float* bias2[CRUSE_MAX_GROUPS];
+    const float* addend[CRUSE_MAX_GROUPS];      // optional [M, N] matrix with C's pitch, added in the epilogue (split-K: plane 0 only)
     float* out[CRUSE_MAX_GROUPS];
 };
 
@@ -190,6 +191,7 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
         float* stg = reinterpret_cast<float*>(tiles) + quad * (32 * 36);
         const int rr = lane >> 3, cc = (lane & 7) * 4;           // store phase: lane -> (row rr + 4i, columns cc..cc+3)
         float* obase = args.out[g] + (size_t)split * c_plane + n0;
+        const float* abase = (split == 0 && args.addend[g]) ? args.addend[g] + n0 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= N) break;                      // warp-uniform
@@ -215,19 +217,24 @@ gemm_tn_tc_kernel(const __grid_constant__ GemmArgs args, int M, int N, int K, lo
                     if (mm < M) {
                         size_t mr = (size_t)mm;
                         if (tm_T > 0) { const int bq = mm / tm_T; mr = (size_t)(mm - bq * tm_T) * (size_t)(M / tm_T) + bq; }
-                        *reinterpret_cast<float4*>(obase + mr * ldc + c + cc) = *reinterpret_cast<const float4*>(stg + r * 36 + cc);
+                        float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + cc);
+                        if (abase) {
+                            const float4 ad = __ldg(reinterpret_cast<const float4*>(abase + mr * ldc + c + cc));
+                            o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+                        }
+                        *reinterpret_cast<float4*>(obase + mr * ldc + c + cc) = o;
                     }
                 }
             } else if (m < M) {                            // ragged N edge / unaligned C: direct stores
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    if (vec_ok && n0 + c + j + 3 < N) {
+                    if (vec_ok && !abase && n0 + c + j + 3 < N) {
                         *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[j] + s_bias[c + j], v[j + 1] + s_bias[c + j + 1],
                                                                                v[j + 2] + s_bias[c + j + 2], v[j + 3] + s_bias[c + j + 3]);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (n0 + c + j + e < N) orow[c + j + e] = v[j + e] + s_bias[c + j + e];
+                            if (n0 + c + j + e < N) orow[c + j + e] = v[j + e] + s_bias[c + j + e] + (abase ? __ldg(abase + mrow * ldc + c + j + e) : 0.f);
                     }
                 }
             }
@@ -401,7 +408,7 @@ int launch_gemm(GemmArgs& args, int G, int M, int N, int K, long long ldc, int b
                 cudaStream_t st, int tm_T = 0, bool astat_ok = false, bool a_mn = false, bool b_mn = false, int b_kshift = 0) {
     for (int g = G; g < CRUSE_MAX_GROUPS; ++g) {
         args.a[g] = args.a[0]; args.b[g] = args.b[0];
-        args.bias1[g] = nullptr; args.bias2[g] = nullptr; args.out[g] = nullptr;
+        args.bias1[g] = nullptr; args.bias2[g] = nullptr; args.addend[g] = nullptr; args.out[g] = nullptr;
     }
     if (g_astat && astat_ok && splitk == 1 && K == AS_NKB * BK && N % AS_BN == 0 && N <= AS_MAX_N && (ldc & 3) == 0) {
         static bool attr_set = false;
@@ -439,6 +446,7 @@ static int gru_ih_gemm_tc_impl(const float* x, const float* const* w_ih, const f
         if (int rc = make_tmap_2d(&args.b[g], w_ih[g], (uint64_t)3 * H, (uint64_t)H, (uint64_t)H * 4, astat ? AS_BN : BN, true)) return rc;
         args.bias1[g] = b_ih ? b_ih[g] : nullptr;
         args.bias2[g] = b_hh ? b_hh[g] : nullptr;
+        args.addend[g] = nullptr;
         args.out[g] = xproj + (size_t)g * 3 * H;
     }
     return launch_gemm(args, G, M, 3 * H, H, (long long)G * 3 * H, 2 * H, 1, 0, (cudaStream_t)stream, tm_T, astat);
@@ -475,14 +483,15 @@ extern "C" int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, c
         if (int rc = make_tmap_2d(&args.b[g], Bm[g], (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, BN, true)) return rc;
         args.bias1[g] = bias ? bias[g] : nullptr;
         args.bias2[g] = nullptr;
+        args.addend[g] = nullptr;
         args.out[g] = C[g];
     }
     return launch_gemm(args, G, M, N, K, ldc, 0, splitk, c_plane, (cudaStream_t)stream);
 }
 
-extern "C" int cruse_gemm_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C, int G,
-                             int M, int N, int K, long long lda, long long ldb, long long ldc, int splitk, long long c_plane,
-                             int a_mn, int b_mn, int b_kshift, void* stream) {
+extern "C" int cruse_gemm_tc(const float* const* A, const float* const* Bm, const float* const* bias, const float* const* addend,
+                             float* const* C, int G, int M, int N, int K, long long lda, long long ldb, long long ldc, int splitk,
+                             long long c_plane, int a_mn, int b_mn, int b_kshift, void* stream) {
     CRUSE_CHECK_ARG(A && Bm && C, "gemm_tc: null pointer table");
     CRUSE_CHECK_ARG(G > 0 && G <= CRUSE_MAX_GROUPS && M > 0 && N > 0 && K > 0 && splitk >= 1 && splitk <= 64,
                     "gemm_tc: bad sizes G=%d M=%d N=%d K=%d splitk=%d", G, M, N, K, splitk);
@@ -500,6 +509,8 @@ extern "C" int cruse_gemm_tc(const float* const* A, const float* const* Bm, cons
                           : make_tmap_2d(&args.b[g], Bm[g], (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, BN, true)) return rc;
         args.bias1[g] = bias ? bias[g] : nullptr;
         args.bias2[g] = nullptr;
+        args.addend[g] = addend ? addend[g] : nullptr;
+        CRUSE_CHECK_ARG(!args.addend[g] || (reinterpret_cast<uintptr_t>(args.addend[g]) & 15) == 0, "gemm_tc: addend %d is not 16-byte aligned", g);
         args.out[g] = C[g];
     }
     return launch_gemm(args, G, M, N, K, ldc, 0, splitk, c_plane, (cudaStream_t)stream, 0, false, a_mn != 0, b_mn != 0, b_kshift);

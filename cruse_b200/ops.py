@@ -971,12 +971,13 @@ def gemm_tn_tc(A, Bm, C, M, N, K, lda, ldb, ldc, bias=None, splitk=1, c_plane=0,
           _stream(), meta=(f"gemm_tn[{mode}] G{G} {M}x{N}x{K} splitk{splitk}", 4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
 
 
-def gemm_tc(A, Bm, C, M, N, K, lda, ldb, ldc, a_mn=False, b_mn=False, b_kshift=0, bias=None, splitk=1, c_plane=0):
+def gemm_tc(A, Bm, C, M, N, K, lda, ldb, ldc, a_mn=False, b_mn=False, b_kshift=0, bias=None, addend=None, splitk=1, c_plane=0):
     """gemm_tn_tc with either operand MN-major (stored [K rows][M | N contiguous], row pitch lda / ldb): C_g[m,n] =
-    sum_k A_g[m,k] B_g[n,k]; b_kshift pairs A's reduction index k with B's row k - b_kshift (rows < 0 are zero).  tf32 only."""
+    sum_k A_g[m,k] B_g[n,k] (+ addend_g[m,n], pitch ldc); b_kshift pairs A's reduction index k with B's row k - b_kshift
+    (rows < 0 are zero).  tf32 only."""
     G = len(A)
-    ta, tb, tcs, tbias = _ptr_table(A), _ptr_table(Bm), _ptr_table(C), _ptr_table(bias)
-    _call("cruse_gemm_tc", ta, tb, tbias, tcs, G, M, N, K, lda, ldb, ldc, splitk, c_plane, 1 if a_mn else 0, 1 if b_mn else 0,
+    ta, tb, tcs, tbias, tadd = _ptr_table(A), _ptr_table(Bm), _ptr_table(C), _ptr_table(bias), _ptr_table(addend)
+    _call("cruse_gemm_tc", ta, tb, tbias, tadd, tcs, G, M, N, K, lda, ldb, ldc, splitk, c_plane, 1 if a_mn else 0, 1 if b_mn else 0,
           b_kshift, _stream(), meta=(f"gemm[tf32,{'mn' if a_mn else 'k'}/{'mn' if b_mn else 'k'}] G{G} {M}x{N}x{K} splitk{splitk}",
                                      4 * G * (M * K + N * K + M * N * splitk), 2 * G * M * N * K))
 

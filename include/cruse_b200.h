@@ -399,9 +399,11 @@ int cruse_gemm_tn_tc(const float* const* A, const float* const* Bm, const float*
  *   a_mn = 0: A_g[m,k] = A[m*lda + k]     a_mn = 1: A_g[m,k] = A[k*lda + m]
  *   b_mn = 0: B_g[n,k] = Bm[n*ldb + k]    b_mn = 1: B_g[n,k] = Bm[(k - b_kshift)*ldb + n], rows < 0 read as zero
  * (b_kshift = 1 pairs frame t with h_{t-1} when the rows are frames; the caller zeroes the t == 0 rows of A).
- * Everything else as cruse_gemm_tn_tc, which is the a_mn = b_mn = 0 case. */
-int cruse_gemm_tc(const float* const* A, const float* const* Bm, const float* const* bias, float* const* C,
-                  int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
+ * addend (table or NULL): C_g += addend_g, an [M,N] matrix with C's pitch ldc, 16-byte aligned (split-K: added to plane 0) --
+ * where two gradient paths meet (out = g + skip4, model/cruse_net.py:160) the sum costs no extra pass.
+ * Everything else as cruse_gemm_tn_tc, which is the a_mn = b_mn = 0, addend = NULL case. */
+int cruse_gemm_tc(const float* const* A, const float* const* Bm, const float* const* bias, const float* const* addend,
+                  float* const* C, int G, int M, int N, int K, long long lda, long long ldb, long long ldc,
                   int splitk, long long c_plane, int a_mn, int b_mn, int b_kshift, void* stream);
 /* Exact-fp32 twins of the three tensor-core kernels of the GRU training path (same contracts and layouts; every product an
  * fp32 FMA on the CUDA cores, fixed summation order).  They make the whole training step runnable without tf32 operand rounding

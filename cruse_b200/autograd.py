@@ -128,6 +128,11 @@ def _splitk(M):
     return max(1, min(16, M // 1024))
 
 
+def gru_w_ih_transposed(grus):
+    """[H, 3H] copies of the input weights: the K-major B operand of dx = dxproj . W_ih"""
+    return [g.weight_ih_l0.detach().t().contiguous() for g in grus]
+
+
 def gru_shifted_state_transposed(saved, G, H, B, T, interleave):
     """hT[g][i][b*T + t] = h_{t-1}[b, g, i] (0 at t = 0) from the saved layer output: the K-major B operand of dW_hh where the
     output's features are interleaved over the groups (layer 1, model/cruse_net.py:43-45) and a group's columns are not contiguous"""
@@ -143,7 +148,8 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
     after the BPTT launch to queue side work that should run next to it.  ``defer_wgrads``: the weight-gradient GEMMs are not
     launched; a third return value ``wg()`` launches them (on whatever stream is current) and fills the dict.
     ``dx_addend()`` -> [B*T, G*H] tensor added to dx in the GEMM epilogue (tensor-core mode; called after the BPTT launch).
-    ``early`` (dict): work that needs only saved forward tensors, done ahead by the caller -- key "hT" = the transposed h_{t-1}."""
+    ``early`` (dict): work that needs only saved forward tensors / parameters, done ahead by the caller -- "hT" = the transposed
+    h_{t-1} (gru_shifted_state_transposed), "w_t" = gru_w_ih_transposed."""
     x2d, y, gates = saved
     G = len(grus)
     H = grus[0].hidden_size
@@ -168,17 +174,20 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
     for gi, g in enumerate(grus):
         grads[g.bias_ih_l0] = dbias[gi, :3].reshape(3 * H)
         grads[g.bias_hh_l0] = torch.cat([dbias[gi, 0], dbias[gi, 1], dbias[gi, 3]])
-    # ---- dx = dxproj . W_ih   ([M,3H] x [3H,H]): W_ih [3H, H] is the B operand with the reduction index as its ROW
+    # ---- dx = dxproj . W_ih   ([M,3H] x [3H,H]); B operand K-major -> W_ih^T copies (0.75 MB each; reading W_ih in place as an
+    # MN-major operand works too but was measured slower here: 109 vs 80 us beside the same side work)
     dx = None
     if need_dx:
         dx = torch.empty(M, G * H, device=dev, dtype=torch.float32)
         add = dx_addend() if dx_addend is not None else None
+        w_t = (early or {}).get("w_t")
+        if w_t is None:
+            w_t = gru_w_ih_transposed(grus)
         if in_place:
-            ops.gemm_tc([dxproj[:, gi] for gi in range(G)], [w.detach() for w in w_ih], [dx[:, gi * H:] for gi in range(G)],
-                        M, H, 3 * H, G * 3 * H, H, G * H, b_mn=True,
+            ops.gemm_tc([dxproj[:, gi] for gi in range(G)], w_t, [dx[:, gi * H:] for gi in range(G)],
+                        M, H, 3 * H, G * 3 * H, 3 * H, G * H,
                         addend=[add.view(M, G * H)[:, gi * H:] for gi in range(G)] if add is not None else None)
         else:
-            w_t = [w.detach().t().contiguous() for w in w_ih]                   # [H, 3H]: K-major copies (0.75 MB each)
             ops.gemm_tn_tc([dxproj[:, gi] for gi in range(G)], w_t, [dx[:, gi * H:] for gi in range(G)],
                            M, H, 3 * H, G * 3 * H, 3 * H, G * H)
             if add is not None:
@@ -363,6 +372,11 @@ class _Unet2Fn(torch.autograd.Function):
             free_sms = torch.cuda.get_device_properties(dmask.device).multi_processor_count - 8 * clusters
             cap = free_sms if free_sms >= 32 else 0
         deferred = []                                             # decoder / skip weight gradients: run beside the BPTT
+        ahead1, ahead2 = {}, {}                                   # small things the GRU backward needs, made early on the side
+        if early:
+            ahead2["w_t"] = side.run(lambda: gru_w_ih_transposed(m.gru.gru_list2))
+            ahead1["w_t"] = side.run(lambda: gru_w_ih_transposed(m.gru.gru_list1))
+            w_t_ready = side.mark_side()
         # ---- last decoder stage: mask = sigmoid(convT(d2))           cruse_net.py:164
         dz = ops.sigmoid_bwd(dmask.view(B, T, 1, F), sv["mask"])
 
@@ -410,7 +424,9 @@ class _Unet2Fn(torch.autograd.Function):
         dgo = d_out.view(B * T, D)
         dy2, G[gru.ln2.weight], G[gru.ln2.bias] = ops.layernorm_bwd(dgo, sv["y2"].view(B * T, D), gru.ln2.weight, *sv["ln2"])
         side_in = [t for d in deferred for t in d[1:]] + dskip
-        dz1, g2, wg2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False, side=side, defer_wgrads=True,
+        if early:
+            side.main.wait_event(w_t_ready)
+        dz1, g2, wg2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False, side=side, defer_wgrads=True, early=ahead2,
                                      beside=lambda ev: side.run(decoder_weight_grads, *side_in, after=ev, max_ctas=cap))
         if not early:
             wg2()
@@ -418,7 +434,7 @@ class _Unet2Fn(torch.autograd.Function):
 
         sd_ready = []
 
-        ahead = {}
+        ahead = ahead1
 
         def beside_bptt1(ev):                                     # what the chain needs first goes first
             side.run(skip_data_grads, *dskip, after=ev, max_ctas=cap)

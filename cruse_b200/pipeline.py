@@ -426,7 +426,17 @@ def train_forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflec
     from .loss import wo_male_frames_autograd
     F = model.in_feat
     X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)
-    S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
-    mask = unet2_frames_autograd(model, mag)
+    if noisy.is_cuda and ops.OVERLAP_BWD:
+        # the clean spectrum is read by the loss only: off the encoder's way, on the side stream (S stays referenced by the loss
+        # node until its backward has run, i.e. past every main-stream use)
+        main, side = torch.cuda.current_stream(noisy.device), _side_stream(noisy.device, 2)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
+        mask = unet2_frames_autograd(model, mag)
+        main.wait_stream(side)
+    else:
+        S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
+        mask = unet2_frames_autograd(model, mag)
     est = mask_apply(mask, X, n_fft, hop)
     return wo_male_frames_autograd(S, est, X, F)

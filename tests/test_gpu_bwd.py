@@ -719,8 +719,12 @@ def test_gemm_operands_read_in_place(cuda, a_mn, b_mn, shift, M, N, K, splitk):
         b_dev[:, :, :K] = Bm.to(cuda)
     plane = M * N
     part = torch.full((Gn, splitk, plane), float("nan"), device=cuda)
+    add = torch.randn(Gn, M, N, device=cuda) if (N % 4 == 0 and a_mn != b_mn) else None      # the epilogue addend (plane 0)
     ops.gemm_tc([a_dev[g] for g in range(Gn)], [b_dev[g] for g in range(Gn)], [part[g] for g in range(Gn)], M, N, K,
-                a_dev.shape[-1], b_dev.shape[-1], N, a_mn=a_mn, b_mn=b_mn, b_kshift=shift, splitk=splitk, c_plane=plane)
+                a_dev.shape[-1], b_dev.shape[-1], N, a_mn=a_mn, b_mn=b_mn, b_kshift=shift, splitk=splitk, c_plane=plane,
+                addend=[add[g] for g in range(Gn)] if add is not None else None)
     torch.cuda.synchronize()
     got = part.sum(1).view(Gn, M, N)
+    if add is not None:
+        want = want + add.double().cpu()
     assert rel_err(got, want) <= 2e-3

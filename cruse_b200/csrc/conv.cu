@@ -349,6 +349,7 @@ bn_stats_kernel(const float* __restrict__ z, float* __restrict__ stats_ws, int T
     const int per_fr4 = F >> 2;                                  // float4 per (frame, channel) row; F % 4 == 0
     for (int c = warp; c < C; c += nwarps) {
         float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4                                                // four independent loads in flight per lane, same summation order
         for (int i = lane; i < nfr * per_fr4; i += 32) {
             const int fr = i / per_fr4, q = i - fr * per_fr4;
             const float4 v = __ldg(reinterpret_cast<const float4*>(zb + ((size_t)fr * C + c) * F) + q);

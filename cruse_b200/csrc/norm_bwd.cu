@@ -23,22 +23,28 @@ __device__ __forceinline__ float act_grad(float a, float dy, int act, float alph
     }
 }
 
-// VEC = 4 (F % 4 == 0: a float4 never straddles a channel) or 1
-template <int VEC, bool APPLY>
+// VEC = 4 (F % 4 == 0: a float4 never straddles a channel) or 1.  NIT = vector elements of a frame per thread (compile time:
+// the per-thread state is NIT-sized register arrays; sized for the largest frame they cost 94 registers = 2 CTAs per SM, and a
+// thread had only its own two 16-byte loads in flight -- 2.5 TB/s).  UF frames are loaded together before any is used, so a
+// thread of the 1024-float frames of the 256-bin pyramid (NIT = 1) keeps 8 loads in flight.
+// Pass 1 ends with a fixed-order reduction: every thread leaves its sums in shared memory indexed by its position in the
+// frame, channel c then adds its contiguous range [c*F/VEC, (c+1)*F/VEC) in order (no shared-memory float atomics: those are
+// compare-and-swap loops, here up to 32 threads deep on one address, and their order is not fixed).
+template <int VEC, bool APPLY, int NIT>
 __global__ void __launch_bounds__(NB_THREADS)
 bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ alpha, int act, const float* __restrict__ mean,
                   const float* __restrict__ invstd, const float* __restrict__ coef, float* __restrict__ dz,
                   float* __restrict__ partials, long long n_frames, int C, int F) {
+    constexpr int UF = NIT == 1 ? 4 : (NIT == 2 ? 2 : 1);
     const int CF = C * F;
-    const int nit = (CF + NB_THREADS * VEC - 1) / (NB_THREADS * VEC);
-    float s1[NB_MAXIT], s2[NB_MAXIT], s3[NB_MAXIT];
-    float sc[NB_MAXIT], sh[NB_MAXIT], al[NB_MAXIT], mu[NB_MAXIT], is[NB_MAXIT], cA[NB_MAXIT], cM1[NB_MAXIT], cM2[NB_MAXIT];
+    float s1[NIT], s2[NIT], s3[NIT];
+    float sc[NIT], sh[NIT], al[NIT], mu[NIT], is[NIT], cA[NIT], cM1[NIT], cM2[NIT];
 #pragma unroll
-    for (int k = 0; k < NB_MAXIT; ++k) {
+    for (int k = 0; k < NIT; ++k) {
         s1[k] = s2[k] = s3[k] = 0.f;
         const int e = (threadIdx.x + k * NB_THREADS) * VEC;
-        const int c = (k < nit && e < CF) ? e / F : 0;
+        const int c = e < CF ? e / F : 0;
         sc[k] = scale ? __ldg(scale + c) : 1.f;
         sh[k] = shift ? __ldg(shift + c) : 0.f;
         al[k] = alpha ? __ldg(alpha + c) : 0.f;
@@ -48,60 +54,92 @@ bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
         cM1[k] = (APPLY && coef) ? __ldg(coef + C + c) : 0.f;
         cM2[k] = (APPLY && coef) ? __ldg(coef + 2 * C + c) : 0.f;
     }
-    for (long long fr = blockIdx.x; fr < n_frames; fr += gridDim.x) {
-        const float* dyf = dy + fr * CF;
-        const float* zf = z + fr * CF;
+    const long long stride = gridDim.x;
+    for (long long fr0 = blockIdx.x; fr0 < n_frames; fr0 += stride * UF) {
+        float dv[UF][NIT][VEC], zv[UF][NIT][VEC];
 #pragma unroll
-        for (int k = 0; k < NB_MAXIT; ++k) {
-            if (k >= nit) break;
-            const int e = (threadIdx.x + k * NB_THREADS) * VEC;
-            if (e >= CF) continue;
-            float dv[VEC], zv[VEC], ov[VEC];
-            if constexpr (VEC == 4) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(dyf + e)), b4 = __ldg(reinterpret_cast<const float4*>(zf + e));
-                dv[0] = a4.x; dv[1] = a4.y; dv[2] = a4.z; dv[3] = a4.w;
-                zv[0] = b4.x; zv[1] = b4.y; zv[2] = b4.z; zv[3] = b4.w;
-            } else {
-                dv[0] = __ldg(dyf + e);
-                zv[0] = __ldg(zf + e);
-            }
+        for (int u = 0; u < UF; ++u) {
+            const long long fr = fr0 + u * stride;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const float a = fmaf(zv[v], sc[k], sh[k]);
-                const float da = act_grad(a, dv[v], act, al[k]);
-                const float xh = (zv[v] - mu[k]) * is[k];
-                if (APPLY) {
-                    ov[v] = cA[k] * (da - cM1[k] - xh * cM2[k]);
-                } else {
-                    s1[k] += da;
-                    s2[k] += da * xh;
-                    if (act == CRUSE_ACT_PRELU && a <= 0.f) s3[k] += dv[v] * a;
+            for (int k = 0; k < NIT; ++k) {
+                const int e = (threadIdx.x + k * NB_THREADS) * VEC;
+                if (fr < n_frames && e < CF) {
+                    if constexpr (VEC == 4) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(dy + fr * CF + e)), b4 = __ldg(reinterpret_cast<const float4*>(z + fr * CF + e));
+                        dv[u][k][0] = a4.x; dv[u][k][1] = a4.y; dv[u][k][2] = a4.z; dv[u][k][3] = a4.w;
+                        zv[u][k][0] = b4.x; zv[u][k][1] = b4.y; zv[u][k][2] = b4.z; zv[u][k][3] = b4.w;
+                    } else {
+                        dv[u][k][0] = __ldg(dy + fr * CF + e);
+                        zv[u][k][0] = __ldg(z + fr * CF + e);
+                    }
                 }
             }
-            if (APPLY) {
-                if constexpr (VEC == 4) *reinterpret_cast<float4*>(dz + fr * CF + e) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-                else dz[fr * CF + e] = ov[0];
+        }
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {                       // frames in the order fr0, fr0 + stride, ...: the per-thread sums do not depend on UF
+            const long long fr = fr0 + u * stride;
+            if (fr >= n_frames) break;
+#pragma unroll
+            for (int k = 0; k < NIT; ++k) {
+                const int e = (threadIdx.x + k * NB_THREADS) * VEC;
+                if (e >= CF) continue;
+                float ov[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float a = fmaf(zv[u][k][v], sc[k], sh[k]);
+                    const float da = act_grad(a, dv[u][k][v], act, al[k]);
+                    const float xh = (zv[u][k][v] - mu[k]) * is[k];
+                    if (APPLY) {
+                        ov[v] = cA[k] * (da - cM1[k] - xh * cM2[k]);
+                    } else {
+                        s1[k] += da;
+                        s2[k] += da * xh;
+                        if (act == CRUSE_ACT_PRELU && a <= 0.f) s3[k] += dv[u][k][v] * a;
+                    }
+                }
+                if (APPLY) {
+                    if constexpr (VEC == 4) *reinterpret_cast<float4*>(dz + fr * CF + e) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    else dz[fr * CF + e] = ov[0];
+                }
             }
         }
     }
     if (!APPLY) {
-        extern __shared__ float s_acc[];   // [3*C]
-        for (int i = threadIdx.x; i < 3 * C; i += NB_THREADS) s_acc[i] = 0.f;
-        __syncthreads();
+        extern __shared__ float s_acc[];   // [3][NIT * NB_THREADS] sums by position in the frame
+        constexpr int NPOS = NIT * NB_THREADS;
 #pragma unroll
-        for (int k = 0; k < NB_MAXIT; ++k) {
-            if (k >= nit) break;
-            const int e = (threadIdx.x + k * NB_THREADS) * VEC;
-            if (e >= CF) continue;
-            const int c = e / F;
-            atomicAdd(&s_acc[c], s1[k]);
-            atomicAdd(&s_acc[C + c], s2[k]);
-            if (act == CRUSE_ACT_PRELU) atomicAdd(&s_acc[2 * C + c], s3[k]);
+        for (int k = 0; k < NIT; ++k) {
+            const int j = threadIdx.x + k * NB_THREADS;
+            const bool in = j * VEC < CF;
+            s_acc[j] = in ? s1[k] : 0.f;
+            s_acc[NPOS + j] = in ? s2[k] : 0.f;
+            s_acc[2 * NPOS + j] = in ? s3[k] : 0.f;
         }
         __syncthreads();
         float* o = partials + (size_t)blockIdx.x * 3 * C;
-        for (int i = threadIdx.x; i < 3 * C; i += NB_THREADS) o[i] = s_acc[i];
+        for (int i = threadIdx.x; i < 3 * C; i += NB_THREADS) {
+            const int q = i / C, c = i - q * C;
+            const int j0 = (c * F + VEC - 1) / VEC, j1 = ((c + 1) * F + VEC - 1) / VEC;      // VEC == 4: F % 4 == 0
+            float a = 0.f;
+            for (int j = j0; j < j1; ++j) a += s_acc[q * NPOS + j];
+            o[i] = a;
+        }
     }
+}
+
+template <int VEC, bool APPLY>
+static void launch_bn_act_bwd(int grid, cudaStream_t st, const float* dy, const float* z, const float* scale, const float* shift,
+                              const float* alpha, int act, const float* mean, const float* invstd, const float* coef, float* dz,
+                              float* partials, long long n_frames, int C, int F) {
+    const int nit = (C * F + NB_THREADS * VEC - 1) / (NB_THREADS * VEC);
+#define CRUSE_BN_BWD(NIT_)                                                                                                            \
+    bn_act_bwd_kernel<VEC, APPLY, NIT_><<<grid, NB_THREADS, APPLY ? 0 : sizeof(float) * 3 * NIT_ * NB_THREADS, st>>>(                  \
+        dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, partials, n_frames, C, F)
+    if (nit <= 1) CRUSE_BN_BWD(1);
+    else if (nit <= 2) CRUSE_BN_BWD(2);
+    else if (nit <= 4) CRUSE_BN_BWD(4);
+    else CRUSE_BN_BWD(8);
+#undef CRUSE_BN_BWD
 }
 
 // one block per channel: sums the partials (double), emits dgamma/dbeta/dalpha and the pass-2 coefficients
@@ -150,7 +188,7 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
                      float* __restrict__ partials, long long rows, int D) {
-    extern __shared__ float s_part[];   // [2*D]
+    extern __shared__ float s_part[];   // [nwarps][2*D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nit = (D + 127) / 128;
     float4 dg[LN_MAXIT], db[LN_MAXIT], gm[LN_MAXIT];
@@ -165,14 +203,20 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
         const float* xr = x + row * D;
         const float* dr = dy + row * D;
+        // all 16 loads of the row are issued before the first value is used: with the loads inside the loop below, behind its
+        // data-dependent early exit, each 128-column block waited for the previous one's arithmetic (8 round trips per row, 7 us)
         float4 xh[LN_MAXIT], g[LN_MAXIT];
+#pragma unroll
+        for (int k = 0; k < LN_MAXIT; ++k) {
+            const int i = lane * 4 + k * 128;
+            const bool in = i < D;                      // i >= k*128, so this also covers k >= nit
+            xh[k] = in ? __ldg(reinterpret_cast<const float4*>(xr + i)) : make_float4(mu, mu, mu, mu);
+            g[k] = in ? __ldg(reinterpret_cast<const float4*>(dr + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int k = 0; k < LN_MAXIT; ++k) {
-            if (k >= nit) break;
-            const int i = lane * 4 + k * 128;
-            if (i >= D) { xh[k] = g[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + i)), dv = __ldg(reinterpret_cast<const float4*>(dr + i));
+            const float4 xv = xh[k], dv = g[k];          // out of range: xhat = 0, dy = 0 -> contributes nothing
             xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
             g[k] = make_float4(dv.x * gm[k].x, dv.y * gm[k].y, dv.z * gm[k].z, dv.w * gm[k].w);
             a += (g[k].x + g[k].y) + (g[k].z + g[k].w);
@@ -194,19 +238,24 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
             *reinterpret_cast<float4*>(dx + row * D + i) = o;
         }
     }
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_part[i] = 0.f;
-    __syncthreads();
+    // every warp leaves its column sums in its own [2*D] slice, the CTA adds the slices in warp order (shared-memory float
+    // atomics -- compare-and-swap loops, eight warps deep here -- would leave the summation order open)
+    float* mine = s_part + (size_t)warp * 2 * D;
 #pragma unroll
     for (int k = 0; k < LN_MAXIT; ++k) {
         if (k >= nit) break;
         const int i = lane * 4 + k * 128;
         if (i >= D) continue;
-        atomicAdd(&s_part[i + 0], dg[k].x); atomicAdd(&s_part[i + 1], dg[k].y); atomicAdd(&s_part[i + 2], dg[k].z); atomicAdd(&s_part[i + 3], dg[k].w);
-        atomicAdd(&s_part[D + i + 0], db[k].x); atomicAdd(&s_part[D + i + 1], db[k].y); atomicAdd(&s_part[D + i + 2], db[k].z); atomicAdd(&s_part[D + i + 3], db[k].w);
+        *reinterpret_cast<float4*>(mine + i) = dg[k];
+        *reinterpret_cast<float4*>(mine + D + i) = db[k];
     }
     __syncthreads();
     float* o = partials + (size_t)blockIdx.x * 2 * D;
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) o[i] = s_part[i];
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+        float a = 0.f;
+        for (int w = 0; w < nwarps; ++w) a += s_part[(size_t)w * 2 * D + i];
+        o[i] = a;
+    }
 }
 
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz, long long n) {
@@ -239,12 +288,11 @@ extern "C" int cruse_bn_act_bwd_reduce(const float* dy, const float* z, const fl
     const int vec = (F & 3) == 0 ? 4 : 1;
     CRUSE_CHECK_ARG((long long)C * F <= (long long)NB_MAXIT * NB_THREADS * vec, "bn_act_bwd_reduce: frame of %d x %d floats is too large", C, F);
     const int grid = nb_grid(n_frames);
-    const size_t smem = sizeof(float) * 3 * C;
     cudaStream_t st = (cudaStream_t)stream;
     if (vec == 4)
-        bn_act_bwd_kernel<4, false><<<grid, NB_THREADS, smem, st>>>(dy, z, scale, shift, alpha, act, mean, invstd, nullptr, nullptr, partials, n_frames, C, F);
+        launch_bn_act_bwd<4, false>(grid, st, dy, z, scale, shift, alpha, act, mean, invstd, nullptr, nullptr, partials, n_frames, C, F);
     else
-        bn_act_bwd_kernel<1, false><<<grid, NB_THREADS, smem, st>>>(dy, z, scale, shift, alpha, act, mean, invstd, nullptr, nullptr, partials, n_frames, C, F);
+        launch_bn_act_bwd<1, false>(grid, st, dy, z, scale, shift, alpha, act, mean, invstd, nullptr, nullptr, partials, n_frames, C, F);
     CRUSE_LAUNCH_OK();
     return 0;
 }
@@ -272,9 +320,9 @@ extern "C" int cruse_bn_act_bwd_apply(const float* dy, const float* z, const flo
     if (g > n_frames) g = n_frames;
     cudaStream_t st = (cudaStream_t)stream;
     if (vec == 4)
-        bn_act_bwd_kernel<4, true><<<(int)g, NB_THREADS, 0, st>>>(dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, nullptr, n_frames, C, F);
+        launch_bn_act_bwd<4, true>((int)g, st, dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, nullptr, n_frames, C, F);
     else
-        bn_act_bwd_kernel<1, true><<<(int)g, NB_THREADS, 0, st>>>(dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, nullptr, n_frames, C, F);
+        launch_bn_act_bwd<1, true>((int)g, st, dy, z, scale, shift, alpha, act, mean, invstd, coef, dz, nullptr, n_frames, C, F);
     CRUSE_LAUNCH_OK();
     return 0;
 }
@@ -302,7 +350,9 @@ extern "C" int cruse_layernorm_bwd(const float* dy, const float* x, const float*
     CRUSE_CHECK_ARG(dy && x && mean && rstd && dx && partials, "layernorm_bwd: null pointer");
     CRUSE_CHECK_ARG(rows > 0 && D > 0 && (D % 4) == 0 && D <= LN_MAXIT * 128, "layernorm_bwd: bad sizes rows=%lld D=%d (D%%4==0, D<=%d)", rows, D, LN_MAXIT * 128);
     const int grid = cruse_layernorm_bwd_nparts(rows);
-    layernorm_bwd_kernel<<<grid, 256, sizeof(float) * 2 * D, (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, dx, partials, rows, D);
+    const size_t smem = sizeof(float) * 8 * 2 * D;          // one [2*D] slice per warp
+    CRUSE_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    layernorm_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dy, x, gamma, mean, rstd, dx, partials, rows, D);
     CRUSE_LAUNCH_OK();
     return 0;
 }

@@ -36,6 +36,33 @@ class _WoMale(torch.autograd.Function):
         return None, (dest * g if dest is not None else None), None, None, None
 
 
+class _WoMaleOfMask(torch.autograd.Function):
+    """wo_male(S, mask * X, X) on interleaved spectra [B,T,NF,2] over the masked bins, differentiable w.r.t. the mask: what the
+    training step composes from utils/utils.py:417-420 (est = mask * X) and loss_func/loss.py:121-148 as ONE autograd node -- the
+    upstream scalar gradient scales the mask gradient inside the mask_bwd kernel instead of a pass of its own over dL/d est."""
+
+    @staticmethod
+    def forward(ctx, ref, mask, unproc, n_fft, hop):
+        from .acoustics import hann_window
+        B, T, F = mask.shape
+        est, _ = ops.mask_istft_fwd(unproc, mask, hann_window(n_fft, n_fft, unproc.device), n_fft, hop, 0, want_est=True, want_wav=False)
+        loss, dest = ops.wo_male_fwd_bwd(ref, ops.layout_btf2(ref), est, ops.layout_btf2(est), unproc, ops.layout_btf2(unproc), B, T, F,
+                                         want_grad=True)
+        ctx.save_for_backward(dest, unproc)
+        ctx.F = F
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dest, unproc = ctx.saved_tensors
+        return None, ops.mask_bwd(dest, unproc, ctx.F, gscale=g.reshape(1).contiguous().float()), None, None, None
+
+
+def wo_male_of_mask(ref, mask, unproc, n_fft, hop):
+    """loss of the masked noisy spectrum against the clean one, mask [B,T,F] (requires grad), spectra [B,T,NF,2]"""
+    return _WoMaleOfMask.apply(ref.contiguous(), mask.contiguous(), unproc.contiguous(), n_fft, hop)
+
+
 def wo_male(ref, est, unproc, norm=False, eps=1e-8):
     """loss_func/loss.py:121-148 (repairs: App. A.4).  ref/est/unproc [B,2,T,F] -> 0-dim loss."""
     if ref.shape != est.shape:

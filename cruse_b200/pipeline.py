@@ -422,8 +422,8 @@ class CapturedTrainStep(CapturedForwardLoss):
 def train_forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflect"):
     """Training step forward: STFT + U-Net (saving what backward needs) + mask*X + wo_male -> loss with autograd
     history; ``loss.backward()`` runs the sm_100a backward kernels and fills ``param.grad``."""
-    from .autograd import mask_apply, unet2_frames_autograd
-    from .loss import wo_male_frames_autograd
+    from .autograd import unet2_frames_autograd
+    from .loss import wo_male_of_mask
     F = model.in_feat
     X, mag = stft_frames(noisy, n_fft, hop, n_fft, pad_mode, mag_bins=F, mag_eps=EPS_MAG)
     if noisy.is_cuda and ops.OVERLAP_BWD:
@@ -438,5 +438,4 @@ def train_forward_loss(model, noisy, clean, n_fft=512, hop=320, pad_mode="reflec
     else:
         S, _ = stft_frames(clean, n_fft, hop, n_fft, pad_mode)
         mask = unet2_frames_autograd(model, mag)
-    est = mask_apply(mask, X, n_fft, hop)
-    return wo_male_frames_autograd(S, est, X, F)
+    return wo_male_of_mask(S, mask, X, n_fft, hop)

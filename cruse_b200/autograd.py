@@ -302,7 +302,16 @@ class _Unet2Fn(torch.autograd.Function):
         x2d = e4.view(B * T, D)
         y1, sv1 = gru_layer_fwd_train(x2d, gru.gru_list1, B, T, True, side=side, beside=beside)   # :42-45
         z1, mean1, rstd1 = ops.layernorm_fwd(y1, gru.ln1.weight, gru.ln1.bias, gru.ln1.eps, want_stats=True)
-        y2, sv2 = gru_layer_fwd_train(z1.view(B * T, D), gru.gru_list2, B, T, False)  # :48-50
+        hT1 = []
+
+        def beside2(ev):
+            # backward's K-major copy of layer 1's shifted output (the one transposed operand left, gru_layer_bwd): it needs y1 only,
+            # and the layer-2 recurrence leaves 84 SMs idle
+            if ops.GRU_IH_MODE == "tf32" and ops.GEMM_MN_MAJOR and ops.BWD_PRIORITY:
+                hT1.append(side.run(lambda: gru_shifted_state_transposed(sv1, len(gru.gru_list1), gru.gru_list1[0].hidden_size, B, T, True),
+                                    y1, after=ev))
+        y2, sv2 = gru_layer_fwd_train(z1.view(B * T, D), gru.gru_list2, B, T, False, side=side,
+                                      beside=beside2 if side.enabled else None)      # :48-50
         side.join()
         out, mean2, rstd2 = ops.layernorm_fwd(y2, gru.ln2.weight, gru.ln2.bias, gru.ln2.eps,
                                               residual=skips[-1].view(B, T, D), want_stats=True)   # :51,160
@@ -328,6 +337,7 @@ class _Unet2Fn(torch.autograd.Function):
         ctx.train = train
         ctx.dims = (B, T, F, D, C4, F4)
         ctx.sv = dict(enc_in=enc_in, enc_z=enc_z, enc_bn=enc_bn, e4=e4, sv1=sv1, y1=y1, ln1=(mean1, rstd1), sv2=sv2, y2=y2,
+                      hT1=hT1[0] if hT1 else None,
                       ln2=(mean2, rstd2), dec_in=dec_in, dec_z=dec_z, dec_bn=dec_bn, d2=out, mask=mask)
         return mask.view(B, T, F)
 
@@ -408,11 +418,17 @@ class _Unet2Fn(torch.autograd.Function):
         def e_of(k_):                                             # output of encoder stage k_ (= input of its skip conv)
             return sv["e4"] if k_ == n else sv["enc_in"][k_]
 
+        def skip_wgrad(k_):
+            G[getattr(m, f"skip_connect_{k_}").weight], _ = ops.conv_wgrad(e_of(k_), dskip[k_ - 1], 1, 1, want_bias=False)
+
+        late_skip = 1 if early else 0                             # the widest (slowest) skip weight gradient moves beside BPTT 1:
+                                                                  # beside BPTT 2 the queue was 0.1 ms longer than the BPTT
+
         def decoder_weight_grads():
             for conv_, x_, dz_ in deferred:
                 G[conv_.weight], G[conv_.bias] = ops.convT_wgrad(x_, dz_)
-            for k_ in range(n, 0, -1):
-                G[getattr(m, f"skip_connect_{k_}").weight], _ = ops.conv_wgrad(e_of(k_), dskip[k_ - 1], 1, 1, want_bias=False)
+            for k_ in range(n, late_skip, -1):
+                skip_wgrad(k_)
 
         sd = [None] * n                                           # skip conv k's data gradient (index k-1), early schedule only
 
@@ -440,7 +456,11 @@ class _Unet2Fn(torch.autograd.Function):
             side.run(skip_data_grads, *dskip, after=ev, max_ctas=cap)
             sd_ready.append(side.mark_side())
             side.run(lambda: wg2(on_side=False), after=ev)        # layer 2's weight gradients (its BPTT is long done)
-            if ops.GRU_IH_MODE == "tf32" and ops.GEMM_MN_MAJOR:   # layer 1's h_{t-1}, transposed: needs the forward's y1 only
+            for k_ in range(late_skip, 0, -1):
+                side.run(lambda k_=k_: skip_wgrad(k_), after=ev, max_ctas=cap)
+            if sv.get("hT1") is not None:                          # layer 1's h_{t-1}, transposed: made in the forward pass
+                ahead["hT"] = sv["hT1"]
+            elif ops.GRU_IH_MODE == "tf32" and ops.GEMM_MN_MAJOR:
                 ahead["hT"] = side.run(lambda: gru_shifted_state_transposed(sv["sv1"], len(gru.gru_list1), gru.gru_list1[0].hidden_size,
                                                                             B, T, True), after=ev)
 
@@ -469,7 +489,7 @@ class _Unet2Fn(torch.autograd.Function):
             def stage_wgrad(conv=conv, x_in=x_in, dzk=dzk):
                 G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
             if early:
-                side.run(stage_wgrad, x_in, dzk, lane=1)
+                side.run(stage_wgrad, x_in, dzk, lane=k % 2)      # two lanes: the last two stages' weight gradients run side by side
             else:
                 stage_wgrad()
             if k > 1:

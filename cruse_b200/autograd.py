@@ -52,7 +52,7 @@ class _SideWork:
             from .pipeline import _side_stream
             self.main = torch.cuda.current_stream(device)
             self.side = _side_stream(device)
-            self.lanes = [self.side, _side_stream(device, 1)]     # lane 1: work that must not queue behind lane 0's
+            self.lanes = [self.side, _side_stream(device, 1), _side_stream(device, 2)]   # lanes 1, 2: work that must not queue behind lane 0's
             self.hp = _priority_stream(device, hp_priority)
 
     def mark(self):
@@ -489,7 +489,8 @@ class _Unet2Fn(torch.autograd.Function):
             def stage_wgrad(conv=conv, x_in=x_in, dzk=dzk):
                 G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
             if early:
-                side.run(stage_wgrad, x_in, dzk, lane=k % 2)      # two lanes: the last two stages' weight gradients run side by side
+                side.run(stage_wgrad, x_in, dzk, lane=1 + k % 2)  # own lanes (lane 0 holds layer 1's GEMMs): consecutive stages' weight
+                                                                  # gradients run side by side instead of one behind the other
             else:
                 stage_wgrad()
             if k > 1:

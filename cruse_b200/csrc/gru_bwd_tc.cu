@@ -324,21 +324,27 @@ gru_bwd_tc_kernel(const float* __restrict__ dy, const float* __restrict__ y, con
                     *reinterpret_cast<float2*>(dh0 + ((size_t)g * B + bg[i]) * H + u0) = make_float2(dhc[i].x + dhm[i].x, dhc[i].y + dhm[i].y);
         }
     }
-    // ---- bias gradients: sum over the cluster's utterances -> one partial row per (slice, group)
+    // ---- bias gradients: sum over the cluster's utterances -> one partial row per (slice, group).  Every thread leaves its
+    // sums (already over its NI utterances) in shared memory, 128 threads add the 16 utterance rows in order: fixed order, no
+    // shared-memory float atomics (threads whose units / utterances do not exist carry zeros)
     __syncthreads();
-    float* sb = sPart;                       // no remote writes are outstanding any more
-    for (int i = tid; i < 4 * 32; i += BW_THREADS) sb[i] = 0.f;
-    __syncthreads();
-    if (uvalid) {
-        atomicAdd(&sb[0 * 32 + 2 * jp], sb_r.x); atomicAdd(&sb[0 * 32 + 2 * jp + 1], sb_r.y);
-        atomicAdd(&sb[1 * 32 + 2 * jp], sb_z.x); atomicAdd(&sb[1 * 32 + 2 * jp + 1], sb_z.y);
-        atomicAdd(&sb[2 * 32 + 2 * jp], sb_n.x); atomicAdd(&sb[2 * 32 + 2 * jp + 1], sb_n.y);
-        atomicAdd(&sb[3 * 32 + 2 * jp], sb_hn.x); atomicAdd(&sb[3 * 32 + 2 * jp + 1], sb_hn.y);
+    // [16 utterance rows][4 gates x 32 units] = 8 KB over the operand tiles and the partial buffers behind them (>= 10 KB in the
+    // smallest instantiation): every MMA has completed and no remote write is outstanding any more
+    float* sb = reinterpret_cast<float*>(sD);
+    {
+        float* q = sb + b * 128 + 2 * jp;
+        q[0 * 32] = sb_r.x;  q[0 * 32 + 1] = sb_r.y;
+        q[1 * 32] = sb_z.x;  q[1 * 32 + 1] = sb_z.y;
+        q[2 * 32] = sb_n.x;  q[2 * 32 + 1] = sb_n.y;
+        q[3 * 32] = sb_hn.x; q[3 * 32 + 1] = sb_hn.y;
     }
     __syncthreads();
     if (dbias_part && tid < 128) {
         const int q = tid >> 5, unit = rank * BW_U + (tid & 31);
-        if (unit < H) dbias_part[(((size_t)bslice * G + g) * 4 + q) * H + unit] = sb[tid];
+        float a = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a += sb[r * 128 + tid];
+        if (unit < H) dbias_part[(((size_t)bslice * G + g) * 4 + q) * H + unit] = a;
     }
     tc::tc_fence_before();
     __syncthreads();

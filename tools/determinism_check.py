@@ -46,6 +46,8 @@ for rep in range(5):
     torch.cuda.synchronize()
     res.append((float(loss), {n: p.grad.clone() for n, p in ours.named_parameters() if p.grad is not None}))
 print("losses:", [f"{r[0]:.9f}" for r in res])
+bitwise = sum(all(torch.equal(res[0][1][n], r[1][n]) for r in res[1:]) for n in res[0][1])
+print(f"gradient tensors bitwise identical over {len(res)} runs: {bitwise} of {len(res[0][1])}")
 for n in res[0][1]:
     d = max(float((res[0][1][n] - r[1][n]).abs().max() / res[0][1][n].abs().max().clamp_min(1e-30)) for r in res[1:])
     if d > 1e-5:

@@ -190,9 +190,14 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 
 __device__ __forceinline__ float tanh_fast(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 // one MUFU per gate (tanh.approx; sigmoid(x) = 0.5 tanh(x/2) + 0.5) instead of ex2 + rcp: two MUFU latencies less on the per-step
 // critical path (measured r2: 1.14 -> 1.04 us per step, cfg-2 parity unchanged: mask 1.99e-4 vs 1.9e-4 of full scale, loss 2.7e-6).
-// Used when no gates are saved (inference); the training forward keeps the ex2/rcp gates its backward was validated with.
+// The training forward (gates saved for the BPTT) uses them too since the end of round 2 -- same gate arithmetic as inference;
+// measured at cfg-3: step 4.19 -> 4.16 ms, worst gradient rel-L2 against the oracle 3.25e-2 -> 3.28e-2 (conv4.weight, tf32 mode),
+// every gradient test unchanged (-DCRUSE_SEQ_TANH_TRAIN=0 restores the ex2/rcp gates there).
 #ifndef CRUSE_SEQ_TANH
 #define CRUSE_SEQ_TANH 1
+#endif
+#ifndef CRUSE_SEQ_TANH_TRAIN          // 1: the training forward (gates saved) uses the one-MUFU gates too
+#define CRUSE_SEQ_TANH_TRAIN 1
 #endif
 __device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
@@ -453,7 +458,7 @@ gru_seq_tc_kernel(const float* __restrict__ xproj, const SeqPtrs ptrs, const flo
                 const float pr = myPre[(0 * 32 + 4 * jq + e) * SQ_PRE_LD + b];
                 const float pz = myPre[(1 * 32 + 4 * jq + e) * SQ_PRE_LD + b];
                 ghn[e] = myPre[(2 * 32 + 4 * jq + e) * SQ_PRE_LD + b] + bhv[e];
-                if (CRUSE_SEQ_TANH && gp == nullptr) {
+                if (CRUSE_SEQ_TANH && (CRUSE_SEQ_TANH_TRAIN || gp == nullptr)) {
                     gr[e] = sigmoid_mufu(xrv[e] + pr);
                     gz[e] = sigmoid_mufu(xzv[e] + pz);
                     gn[e] = tanh_mufu(xnv[e] + gr[e] * ghn[e]);

@@ -266,6 +266,7 @@ class _Unet2Fn(torch.autograd.Function):
         sv = {}
         h = mag.view(B, T, 1, F)
         enc_in, enc_z, enc_bn, skips, enc_out = [], [], [], [], []
+        counters = []                                             # num_batches_tracked of the train-mode BatchNorms: one launch at the end
         for k in range(1, n + 1):                                                    # cruse_net.py:149-156
             conv, bn = getattr(m, f"conv{k}"), getattr(m, f"bn{k}")
             alpha = m._alpha(f"act{k}")
@@ -273,7 +274,7 @@ class _Unet2Fn(torch.autograd.Function):
             z, stats = ops.conv_fwd(h, conv.weight, conv.bias, None, None, None, "none", 2, 2, want_stats=True)
             Fo = z.shape[3]
             if train:
-                scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * Fo, bn)
+                scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * Fo, bn, counters=counters)
             else:
                 scale, shift = ops.bn_fold(bn)
                 mean, invstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
@@ -324,7 +325,7 @@ class _Unet2Fn(torch.autograd.Function):
             z, stats = ops.convT_fwd(out, conv.weight, conv.bias, None, None, None, "none", None, m.freqs[k - 1],
                                      want_stats=True)
             if train:
-                scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * m.freqs[k - 1], bn)
+                scale, shift, mean, invstd = ops.bn_finalize(stats, B * T * m.freqs[k - 1], bn, counters=counters)
             else:
                 scale, shift = ops.bn_fold(bn)
                 mean, invstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
@@ -332,6 +333,7 @@ class _Unet2Fn(torch.autograd.Function):
             dec_z.append(z)
             dec_bn.append((scale, shift, mean, invstd))
         mask = ops.convT_fwd(out, m.conv1_t.weight, m.conv1_t.bias, None, None, None, "sigmoid", None, m.freqs[0])  # :164
+        ops.bump_counters(counters)
         ctx.model = m
         ctx.names = names
         ctx.train = train

@@ -474,8 +474,10 @@ def bn_fold_many(bns):
     return out
 
 
-def bn_finalize(stats, count, bn, update_running=True):
-    """train-mode BatchNorm2d: per-CTA partials -> (scale, shift, save_mean, save_invstd); updates running stats."""
+def bn_finalize(stats, count, bn, update_running=True, counters=None):
+    """train-mode BatchNorm2d: per-CTA partials -> (scale, shift, save_mean, save_invstd); updates running stats.
+    ``counters`` (list): ``num_batches_tracked`` is appended instead of incremented -- the caller bumps all of a forward pass's
+    counters with ONE launch (``bump_counters``) instead of one single-element kernel per stage in the middle of the chain."""
     _req(stats, "stats", 2)
     nparts, C2 = stats.shape
     Cn = C2 // 2
@@ -491,8 +493,16 @@ def bn_finalize(stats, count, bn, update_running=True):
                                   _p(bn.running_var) if upd else None, _p(scale), _p(shift), _p(mean), _p(invstd),
                                   _stream())
     if upd and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        if counters is not None:
+            counters.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
     return scale, shift, mean, invstd
+
+
+def bump_counters(counters):
+    if counters:
+        torch._foreach_add_(counters, 1)
 
 
 def bn_act_fwd(z, scale, shift, alpha, act, skip=None):

@@ -491,7 +491,7 @@ class _Unet2Fn(torch.autograd.Function):
             def stage_wgrad(conv=conv, x_in=x_in, dzk=dzk):
                 G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
             if early:
-                side.run(stage_wgrad, x_in, dzk, lane=1 + k % 2)  # own lanes (lane 0 holds layer 1's GEMMs): consecutive stages' weight
+                side.run(stage_wgrad, x_in, dzk, lane=1 + k % 2, max_ctas=ops.BWD_TAIL_CAP)  # own lanes (lane 0 holds layer 1's GEMMs): consecutive stages' weight
                                                                   # gradients run side by side instead of one behind the other
             else:
                 stage_wgrad()

@@ -155,14 +155,43 @@ conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz, fl
     for (int i = tid; i < nW + Cout; i += WG_THREADS) o[i] = s_dw[i];
 }
 
-// out[j] (+)= sum_p ws[p*pitch + j], j < n   (double accumulation, fixed order)
+// out[j] (+)= sum_p ws[p*pitch + j], j < n   (double accumulation, fixed order).
+// LANES = 1: one thread per column walks the parts (the split-K planes of the GEMMs: a dozen parts, 200 k columns).
+// LANES = 8: a block covers 32 columns with 8 part lanes -- lane q adds the parts q, q+8, q+16, ... (four loads in flight), the
+// eight lane sums are then added in lane order: for the 300-600 per-CTA partials of the LayerNorm / conv weight-gradient kernels,
+// where one thread walking all parts alone took 15-60 us, partly on the dependent chain of the backward pass.
+template <int LANES>
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ ws, int nparts, int pitch, int n, float* __restrict__ out,
                                                      int accumulate) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    constexpr int COLS = 256 / LANES;
+    __shared__ double sh[LANES > 1 ? LANES : 1][LANES > 1 ? COLS + 1 : 1];
+    const int cx = threadIdx.x % COLS, q = threadIdx.x / COLS;
+    const int j = blockIdx.x * COLS + cx;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += (double)ws[(size_t)p * pitch + j];
-    out[j] = (float)(accumulate ? (double)out[j] + s : s);
+    if (j < n) {
+        const float* col = ws + j;
+        int p = q;
+        for (; p + 3 * LANES < nparts; p += 4 * LANES) {
+            const float a = col[(size_t)p * pitch], b = col[(size_t)(p + LANES) * pitch], c = col[(size_t)(p + 2 * LANES) * pitch],
+                        d = col[(size_t)(p + 3 * LANES) * pitch];
+            s += (double)a; s += (double)b; s += (double)c; s += (double)d;
+        }
+        for (; p < nparts; p += LANES) s += (double)col[(size_t)p * pitch];
+    }
+    if constexpr (LANES > 1) {
+        sh[q][cx] = s;
+        __syncthreads();
+        if (q != 0) return;
+        s = 0.0;
+#pragma unroll
+        for (int k = 0; k < LANES; ++k) s += sh[k][cx];
+    }
+    if (j < n) out[j] = (float)(accumulate ? (double)out[j] + s : s);
+}
+
+static void launch_colsum(const float* ws, int nparts, int pitch, int n, float* out, int accumulate, cudaStream_t st) {
+    if (nparts >= 64) colsum_kernel<8><<<(n + 31) / 32, 256, 0, st>>>(ws, nparts, pitch, n, out, accumulate);
+    else colsum_kernel<1><<<(n + 255) / 256, 256, 0, st>>>(ws, nparts, pitch, n, out, accumulate);
 }
 
 static size_t wgrad_smem(int KT, int Cin, int Fin, int Cout, int Fout) {
@@ -185,7 +214,7 @@ using namespace cruse;
 
 extern "C" int cruse_colsum(const float* ws, int nparts, int n, float* out, int accumulate, void* stream) {
     CRUSE_CHECK_ARG(ws && out && nparts > 0 && n > 0, "colsum: bad arguments");
-    colsum_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nparts, n, n, out, accumulate);
+    launch_colsum(ws, nparts, n, n, out, accumulate, (cudaStream_t)stream);
     CRUSE_LAUNCH_OK();
     return 0;
 }
@@ -226,10 +255,10 @@ extern "C" int cruse_conv_wgrad(const float* in, const float* dz, float* dw, flo
     {
         const int n = nW + Cout;
         // weights
-        colsum_kernel<<<(nW + 255) / 256, 256, 0, st>>>((const float*)ws, grid, n, nW, dw, 0);
+        launch_colsum((const float*)ws, grid, n, nW, dw, 0, st);
         CRUSE_LAUNCH_OK();
         if (dbias) {
-            colsum_kernel<<<(Cout + 255) / 256, 256, 0, st>>>((const float*)ws + nW, grid, n, Cout, dbias, 0);
+            launch_colsum((const float*)ws + nW, grid, n, Cout, dbias, 0, st);
             CRUSE_LAUNCH_OK();
         }
     }
@@ -264,10 +293,10 @@ extern "C" int cruse_convT_wgrad(const float* in, const float* dz, float* dw, fl
         conv_wgrad_kernel<1, 1, 2><<<grid, WG_THREADS, smem, st>>>(in, dz, (float*)ws, B, T, Cin, Fin, Cout, Fout);
         CRUSE_LAUNCH_OK();
     }
-    colsum_kernel<<<(nW + 255) / 256, 256, 0, st>>>((const float*)ws, grid, n, nW, dw, 0);
+    launch_colsum((const float*)ws, grid, n, nW, dw, 0, st);
     CRUSE_LAUNCH_OK();
     if (dbias) {
-        colsum_kernel<<<(Cout + 255) / 256, 256, 0, st>>>((const float*)ws + nW, grid, n, Cout, dbias, 0);
+        launch_colsum((const float*)ws + nW, grid, n, Cout, dbias, 0, st);
         CRUSE_LAUNCH_OK();
     }
     return 0;

@@ -1023,6 +1023,7 @@ def set_conv_max_ctas(n: int):
 OVERLAP_BWD = os.environ.get("CRUSE_OVERLAP_BWD", "1") != "0"
 BWD_SIDE_CAP = os.environ.get("CRUSE_BWD_SIDE_CAP", "1") != "0"
 BWD_PRIORITY = os.environ.get("CRUSE_BWD_PRIORITY", "1") != "0"         # backward: dependent chain on a priority stream, the rest early on the side
+BWD_TAIL_CAP = int(os.environ.get("CRUSE_BWD_TAIL_CAP", "0"))          # cap (CTAs) on the encoder weight gradients that run beside the encoder chain; 0 = none
 GEMM_MN_MAJOR = os.environ.get("CRUSE_GEMM_MN_MAJOR", "1") != "0"       # GRU weight-gradient / dx GEMMs read their factors in place
 FWD_SIDE_SKIPS = os.environ.get("CRUSE_FWD_SIDE_SKIPS", "1") != "0"   # training forward: skip convs beside the layer-1 recurrence
 BWD_SIDE_L1 = os.environ.get("CRUSE_BWD_SIDE_L1", "1") != "0"      # layer-1 GRU weight gradients beside the encoder backward

@@ -490,11 +490,11 @@ class _Unet2Fn(torch.autograd.Function):
 
             def stage_wgrad(conv=conv, x_in=x_in, dzk=dzk):
                 G[conv.weight], G[conv.bias] = ops.conv_wgrad(x_in, dzk, 2, 2)
-            if early:
+            if early and k > 1:
                 side.run(stage_wgrad, x_in, dzk, lane=1 + k % 2, max_ctas=ops.BWD_TAIL_CAP)  # own lanes (lane 0 holds layer 1's GEMMs): consecutive stages' weight
                                                                   # gradients run side by side instead of one behind the other
             else:
-                stage_wgrad()
+                stage_wgrad()                                     # stage 1's is the last kernel anything waits for: on the chain itself
             if k > 1:
                 de = ops.conv_dgrad(dzk, conv.weight, x_in.shape, 2, 2, addend=sd[k - 2] if early else None)
         side.join()

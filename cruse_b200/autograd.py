@@ -142,14 +142,16 @@ def gru_shifted_state_transposed(saved, G, H, B, T, interleave):
 
 
 def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, beside=None, own_wgrads_on_side=True,
-                  defer_wgrads=False, dx_addend=None, early=None):
+                  defer_wgrads=False, dx_addend=None, early=None, sink=None):
     """dy [B,T,G*H] (layout of y) -> (dx [B*T, G*H] | None, {param: grad}); with ``side`` the weight gradients are
     enqueued on the side stream (valid on the main stream after ``side.join()``) and ``beside(after_event)`` is called right
     after the BPTT launch to queue side work that should run next to it.  ``defer_wgrads``: the weight-gradient GEMMs are not
     launched; a third return value ``wg()`` launches them (on whatever stream is current) and fills the dict.
     ``dx_addend()`` -> [B*T, G*H] tensor added to dx in the GEMM epilogue (tensor-core mode; called after the BPTT launch).
     ``early`` (dict): work that needs only saved forward tensors / parameters, done ahead by the caller -- "hT" = the transposed
-    h_{t-1} (gru_shifted_state_transposed), "w_t" = gru_w_ih_transposed."""
+    h_{t-1} (gru_shifted_state_transposed), "w_t" = gru_w_ih_transposed.
+    ``sink`` ({parameter: tensor of its shape}): where the weight gradients -- 98 % of the model's gradient bytes -- are written
+    instead of fresh buffers (pipeline.CapturedTrainStep: views of its flat all_reduce buffer, so that they need no copy there)."""
     x2d, y, gates = saved
     G = len(grus)
     H = grus[0].hidden_size
@@ -228,17 +230,19 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
                            3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
             ops.gemm_tn_tc([dpT[gi] for gi in range(G)], [hT[gi] for gi in range(G)], [part[1, gi] for gi in range(G)],
                            3 * H, H, M, M4, M4, H, splitk=sk, c_plane=plane)
-        dw_ = torch.empty(2, G, plane, device=dev, dtype=torch.float32)
+        dw_ = [[None] * G, [None] * G]
         for a in range(2):
             for gi in range(G):
-                ops.colsum(part[a, gi], sk, plane, dw_[a, gi])
+                v = sink.get(grus[gi].weight_ih_l0 if a == 0 else grus[gi].weight_hh_l0) if sink else None
+                ok = v is not None and v.is_contiguous() and v.numel() == plane and v.dtype == torch.float32 and v.device == dev
+                dw_[a][gi] = ops.colsum(part[a, gi], sk, plane, v.view(plane) if ok else torch.empty(plane, device=dev, dtype=torch.float32))
         return dw_
 
     def wg(on_side=own_wgrads_on_side):
         dw = side.run(weight_grads, dxproj, dpre, x2d, y) if (side is not None and on_side) else weight_grads()
         for gi, g in enumerate(grus):
-            grads[g.weight_ih_l0] = dw[0, gi].view(3 * H, H)
-            grads[g.weight_hh_l0] = dw[1, gi].view(3 * H, H)
+            grads[g.weight_ih_l0] = dw[0][gi].view(3 * H, H)
+            grads[g.weight_hh_l0] = dw[1][gi].view(3 * H, H)
 
     if defer_wgrads:
         return dx, grads, wg
@@ -444,8 +448,9 @@ class _Unet2Fn(torch.autograd.Function):
         side_in = [t for d in deferred for t in d[1:]] + dskip
         if early:
             side.main.wait_event(w_t_ready)
+        sink = getattr(m, "_grad_sink", None)                      # set by CapturedTrainStep for the duration of its capture
         dz1, g2, wg2 = gru_layer_bwd(dy2.view(B, T, D), sv["sv2"], gru.gru_list2, B, T, False, side=side, defer_wgrads=True, early=ahead2,
-                                     beside=lambda ev: side.run(decoder_weight_grads, *side_in, after=ev, max_ctas=cap))
+                                     sink=sink, beside=lambda ev: side.run(decoder_weight_grads, *side_in, after=ev, max_ctas=cap))
         if not early:
             wg2()
         dy1, G[gru.ln1.weight], G[gru.ln1.bias] = ops.layernorm_bwd(dz1, sv["y1"].view(B * T, D), gru.ln1.weight, *sv["ln1"])
@@ -470,7 +475,8 @@ class _Unet2Fn(torch.autograd.Function):
             side.main.wait_event(sd_ready[0])
             return sd[n - 1]
         de, g1, wg1 = gru_layer_bwd(dy1.view(B, T, D), sv["sv1"], gru.gru_list1, B, T, True, side=side, defer_wgrads=True,
-                                    beside=beside_bptt1 if early else None, dx_addend=skip4_path if early else None, early=ahead)
+                                    beside=beside_bptt1 if early else None, dx_addend=skip4_path if early else None, early=ahead,
+                                    sink=sink)
         wg1(on_side=ops.BWD_SIDE_L1 or early)
         de = de.view(B, T, C4, F4)
         # ---- encoder stages k = n..1 with their skip convs                      :149-156

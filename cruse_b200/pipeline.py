@@ -381,13 +381,20 @@ class CapturedTrainStep(CapturedForwardLoss):
         from .distrib import flat_grad_views
         self.flat_grad, views = flat_grad_views(self.params)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            loss = train_forward_loss(model, self.noisy, self.clean, n_fft, hop, pad_mode)
-            loss.backward()
-            self.loss = loss.detach()
-            # the step's gradients end up in ONE flat buffer (the data-parallel all_reduce then runs in place on it)
-            got = [(v, p.grad) for v, p in zip(views, self.params) if p.grad is not None]
-            torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+        # the GRU weight gradients (12.6 of the 13.1 MB) are written into their slots of the flat buffer by the kernels that
+        # produce them (autograd.gru_layer_bwd, ``sink``); only during this capture: outside it, a second backward without
+        # zero_grad must ADD to p.grad, which a kernel writing into p.grad's own memory would break
+        model._grad_sink = {p: v for p, v in zip(self.params, views)}
+        try:
+            with torch.cuda.graph(self.graph):
+                loss = train_forward_loss(model, self.noisy, self.clean, n_fft, hop, pad_mode)
+                loss.backward()
+                self.loss = loss.detach()
+                # the step's gradients end up in ONE flat buffer (the data-parallel all_reduce then runs in place on it)
+                got = [(v, p.grad) for v, p in zip(views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+                torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+        finally:
+            del model._grad_sink
         self.grads = [v if p.grad is not None else None for v, p in zip(views, self.params)]
         with torch.no_grad():
             for b, saved in bn_state:

@@ -150,7 +150,7 @@ def gru_layer_bwd(dy, saved, grus, B, T, interleave, need_dx=True, side=None, be
     ``dx_addend()`` -> [B*T, G*H] tensor added to dx in the GEMM epilogue (tensor-core mode; called after the BPTT launch).
     ``early`` (dict): work that needs only saved forward tensors / parameters, done ahead by the caller -- "hT" = the transposed
     h_{t-1} (gru_shifted_state_transposed), "w_t" = gru_w_ih_transposed.
-    ``sink`` ({parameter: tensor of its shape}): where the weight gradients -- 98 % of the model's gradient bytes -- are written
+    ``sink`` ({parameter: tensor of its shape}): where the weight gradients -- 96 % of the model's gradient bytes -- are written
     instead of fresh buffers (pipeline.CapturedTrainStep: views of its flat all_reduce buffer, so that they need no copy there)."""
     x2d, y, gates = saved
     G = len(grus)

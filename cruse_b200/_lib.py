@@ -114,6 +114,11 @@ SIGNATURES = {
     "cruse_snr_mix_ws_bytes": (C.c_size_t, [c_int]),
     "cruse_snr_mix": (c_int, [c_fp] * 7 + [c_int, c_int, c_f, c_fp]),
     "cruse_pcm16_to_float": (c_int, [c_fp, c_fp, C.c_longlong, c_fp]),
+    "cruse_nccl_available": (c_int, []),
+    "cruse_nccl_unique_id": (c_int, [C.c_void_p]),
+    "cruse_nccl_comm_init": (c_int, [C.POINTER(C.c_void_p), c_int, c_int, C.c_void_p]),
+    "cruse_flat_allreduce": (c_int, [C.c_void_p, c_fp, c_ll, c_f, c_fp]),
+    "cruse_nccl_comm_destroy": (c_int, [C.c_void_p]),
     "cruse_transpose_gcm": (c_int, [c_fp, c_fp, c_fp, c_ll, c_int, c_int, c_ll, c_ll, c_ll, c_int, c_int, c_ll, c_fp]),
 }
 

@@ -38,15 +38,61 @@ def flat_grad_views(params, flat=None):
     return flat, views
 
 
-def sync_grad(params, group=None, flat=None):
+class FlatAllreduce:
+    """The same exchange through the library's own C entry point (``cruse_flat_allreduce``, include/cruse_b200.h: one
+    ncclAllReduce in place + the 1/world scale on the current stream) over a communicator of its own: rank 0 draws the NCCL
+    unique id, the existing process group (any backend) carries its 128 bytes to the other ranks, every rank joins.  What a
+    host that is not PyTorch would bind; ``sync_grad(..., flat=buf, native=FlatAllreduce())`` uses it instead of
+    ``torch.distributed.all_reduce``."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        from ._lib import check, lib
+        if not is_distributed(group):
+            raise RuntimeError("FlatAllreduce: torch.distributed is not initialised with more than one rank")
+        if not torch.cuda.is_available():
+            raise RuntimeError("FlatAllreduce: cruse_b200 runs on sm_100a only (no CPU fallback)")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        raw = (C.c_char * 128)()
+        if self.rank == 0:
+            check(lib().cruse_nccl_unique_id(raw), "cruse_nccl_unique_id")
+        ident = torch.tensor(list(bytes(raw)), dtype=torch.uint8)
+        on_device = dist.get_backend(group) == "nccl"
+        if on_device:
+            ident = ident.cuda()
+        dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (C.c_char * 128).from_buffer_copy(bytes(ident.cpu().tolist()))
+        self.comm = C.c_void_p()
+        check(lib().cruse_nccl_comm_init(C.byref(self.comm), self.world, self.rank, raw), "cruse_nccl_comm_init")
+
+    def __call__(self, flat):
+        from ._lib import check, lib
+        if not (flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()):
+            raise RuntimeError("FlatAllreduce: a contiguous float32 device buffer is needed")
+        check(lib().cruse_flat_allreduce(self.comm, flat.data_ptr(), flat.numel(), 1.0 / self.world,
+                                         torch.cuda.current_stream(flat.device).cuda_stream), "cruse_flat_allreduce")
+        return flat
+
+    def close(self):
+        from ._lib import check, lib
+        if self.comm:
+            check(lib().cruse_nccl_comm_destroy(self.comm), "cruse_nccl_comm_destroy")
+            self.comm = None
+
+
+def sync_grad(params, group=None, flat=None, native=None):
     """average ``p.grad`` over all ranks with ONE all_reduce (loss_func/distrib.py:100-116 semantics).
     ``flat``: the buffer the gradients already live in (``flat_grad_views``; pipeline.CapturedTrainStep.flat_grad):
-    reduced in place, two launches in total."""
+    reduced in place, two launches in total.  ``native`` (a ``FlatAllreduce``): through ``cruse_flat_allreduce`` instead of
+    ``torch.distributed.all_reduce``."""
     if not is_distributed(group):
         return None
     if flat is not None:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world_size(group))
+        if native is not None:
+            native(flat)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.div_(world_size(group))
         return flat.numel() * flat.element_size()
     ps = [p for p in params if p.grad is not None]
     if not ps:

@@ -447,6 +447,23 @@ int cruse_snr_mix(const float* clean, const float* noise, const float* snr_db, c
  * samples in the files' own format (half the bytes per step over PCIe).  16-byte aligned buffers. */
 int cruse_pcm16_to_float(const short* in, float* out, long long n, void* stream);
 
+/* =====================================================================================================
+ * a10: the gradient exchange of data-parallel training (loss_func/distrib.py:100-116 sync_grad: all_reduce(SUM) of every
+ * gradient, then division by the world size; train_base/trainer/base_trainer.py:31 DistributedDataParallel).
+ * ONE ncclAllReduce, in place, on the flat fp32 gradient buffer of the step + one scaling pass, on the caller's stream.
+ * NCCL is looked up at run time in the libnccl.so.2 of the process (torch's); without it these calls return an error
+ * (cruse_nccl_available() == 0) and the library still loads.
+ *   cruse_nccl_unique_id: rank 0 fills 128 bytes (ncclUniqueId) that the caller hands to every rank (any side channel);
+ *   cruse_nccl_comm_init: collective over all ranks, the rank's device must be current; *comm is an ncclComm_t;
+ *   cruse_flat_allreduce: buf[i] <- scale * sum_ranks buf[i], i < n (scale = 1 / world); buf 16-byte aligned;
+ *   cruse_nccl_comm_destroy.
+ * ===================================================================================================== */
+int cruse_nccl_available(void);
+int cruse_nccl_unique_id(void* id128);
+int cruse_nccl_comm_init(void** comm, int nranks, int rank, const void* id128);
+int cruse_flat_allreduce(void* comm, float* buf, long long n, float scale, void* stream);
+int cruse_nccl_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,3 +82,43 @@ def test_two_rank_gradient_average_equals_big_batch_gradient(cuda):
     # equal shards, loss = mean over (B,T,F): mean of the shard losses = the big-batch loss, averaged gradients = its gradient
     assert abs(res[0]["loss_mean_of_shards"] - res[0]["loss_big"]) <= 1e-5 * abs(res[0]["loss_big"])
     assert res[0]["worst_rel_l2"] <= 1e-3, res[0]
+
+
+def _worker_native(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from cruse_b200 import distrib
+        g = torch.Generator().manual_seed(100 + rank)
+        n = 3_269_017                                              # the parameter count of config B, not a multiple of 4
+        buf_native = torch.randn(n, generator=g).to(dev)          # a fresh allocation: 16-byte aligned start
+        buf_torch = buf_native.clone()
+        ar = distrib.FlatAllreduce()
+        ar(buf_native)
+        dist.all_reduce(buf_torch)
+        buf_torch.div_(world)
+        torch.cuda.synchronize()
+        out[rank] = {"max_abs_diff": float((buf_native - buf_torch).abs().max()), "scale": float(buf_torch.abs().max())}
+        ar.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_allreduce_entry_point_equals_torch_all_reduce(cuda):
+    """cruse_flat_allreduce (own communicator, ncclAllReduce in place + 1/world) against torch.distributed.all_reduce + div on the
+    same buffers: the average of loss_func/distrib.py:111-116."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_native, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1}
+    for r in res.values():
+        assert r["max_abs_diff"] <= 1e-6 * r["scale"], res

@@ -112,3 +112,18 @@ def test_ctypes_argument_counts_match_header_prototypes():
         params = " ".join(params.split())
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+
+
+def test_collective_entry_points_resolve_nccl_at_run_time():
+    """cruse_flat_allreduce & co. (include/cruse_b200.h, a10) look NCCL up in the process's libnccl.so.2 when first used: the
+    library loads without it, and with it rank 0 can draw the 128-byte unique id (no device needed for that)."""
+    import ctypes as C
+    from cruse_b200._lib import lib
+    have = lib().cruse_nccl_available()
+    assert have in (0, 1)
+    raw = (C.c_char * 128)()
+    rc = lib().cruse_nccl_unique_id(raw)
+    if have:
+        assert rc == 0 and any(bytes(raw))
+    else:
+        assert rc != 0 and b"libnccl" in lib().cruse_last_error()

@@ -73,3 +73,13 @@ def test_single_process_is_a_no_op():
     p.grad = torch.full((3,), 2.0)
     assert distrib.sync_grad([p]) is None and torch.equal(p.grad, torch.full((3,), 2.0))
     assert distrib.world_size() == 1
+
+
+def test_flat_allreduce_needs_an_initialised_group():
+    """distrib.FlatAllreduce (the cruse_flat_allreduce entry point) refuses to build a communicator outside a multi-rank job
+    instead of silently doing nothing -- the reference's sync_grad returns early there (loss_func/distrib.py:103-104), which
+    sync_grad mirrors; the explicit object does not."""
+    import pytest
+    from cruse_b200 import distrib
+    with pytest.raises(RuntimeError):
+        distrib.FlatAllreduce()
